@@ -1,0 +1,121 @@
+/* spmf_b200 -- C ABI of the B200-native ADVI step for sparse Poisson matrix factorisation.
+ *
+ * Drop-in boundary for ONE path of mederrata/spmf: the ELBO + gradient step of
+ * `PoissonFactorization` (reference: mederrata_spmf/poisson.py, class at :25-717, energy at
+ * :575-621, likelihood at :156-184, encoder at :623-701) and the slices of its un-vendored
+ * training stack (bayesianquilts / TFP: surrogate sampling, log q, GradientTape backward, Adam)
+ * that the step needs.  The reference is pure Python with no FFI; these are the entry points a
+ * reference-side binding (ctypes) would bind for that path.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless its name ends in `_host`; the caller owns all memory;
+ *  - no allocation, no global state, asynchronous on `stream` (a cudaStream_t passed as void*);
+ *  - return 0 on success, a negative SPMF_ERR_* for bad arguments / unsupported configurations,
+ *    or a positive cudaError_t if a launch failed;
+ *  - there is NO CPU fallback: without a CUDA device every compute entry point fails.
+ *
+ * Device layouts (KP = spmf_kpad(K), SV = spmf_draw_vec(S), NQ = S/SV; draw s = q*SV + sv):
+ *   params / grads / adam moments : flat fp32, tensor offsets from spmf_layout()
+ *                                   (order: v,w,u,s | u_eta,u_tau,s_eta,s_tau,u_eta_a,u_tau_a,s_eta_a,s_tau_a;
+ *                                    each as (loc|conc_raw , scale_raw); v stored transposed as (D,K))
+ *   noise                         : flat fp32 [var][s][elem]; N(0,1) for v,w,u,s, Gamma(alpha,1) otherwise
+ *   Ap, EV, GAp, GEVnz            : [NQ][D][KP][SV]   A' = a_d u_dk / eta_d,  EV = eta_d v_kd
+ *   PH, Gphinz                    : [NQ][D][SV]       phi_d = eta_d b_d w_d
+ *   z, dzr                        : [NQ][B][KP][SV]   z_bk and r_b * dL/dz_bk
+ *   rowacc                        : [NQ][B][4][SV]    per-row (sum x log lam - lgamma, z.vsum, |z|^2, #non-finite)
+ */
+#ifndef SPMF_B200_H
+#define SPMF_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPMF_OK 0
+#define SPMF_ERR_BAD_ARG (-1)
+#define SPMF_ERR_UNSUPPORTED (-2)
+#define SPMF_MAX_K 128
+#define SPMF_NUM_TENSORS 24
+#define SPMF_NUM_VARS 12
+#define SPMF_NUM_PARTS 16
+
+/* ---- layout helpers (host only, no device work) ---- */
+int spmf_kpad(int K);       /* latent dim padded to a power of two */
+int spmf_draw_vec(int S);   /* draws processed per vector lane: 4, 2 or 1 */
+/* tensor_offsets[25], noise_offsets[13] in floats.  Replaces the variable bookkeeping of
+ * create_distributions (poisson.py:403-573: surrogate_vars / var_list). */
+int spmf_layout(int D, int K, int S, long long* tensor_offsets_host, long long* noise_offsets_host);
+long long spmf_backward_scratch_floats(int D, int K, int S);
+long long spmf_backward_scratch_doubles(int D, int K, int S);
+
+/* ---- surrogate sampling [EXT L3: surrogate_distribution.sample(S)], poisson.py:403-573 ---- */
+int spmf_fill_noise(float* noise, const float* params, int D, int K, int S,
+                    unsigned long long seed, unsigned int step, void* stream);
+int spmf_sample(const float* params, const float* noise, int D, int K, int S, float* samples,
+                void* stream);
+/* encoding_matrix / intercept_matrix / decoding_matrix for every draw (poisson.py:652-701),
+ * plus vsum[NQ][KP][SV] = sum_d EV and phisum[NQ][SV] = sum_d PH for the closed-form -sum(rate). */
+int spmf_draw_operands(const float* params, const float* noise, const float* eta, int D, int K, int S,
+                       float* Ap, float* EV, float* PH, double* vsum, double* phisum,
+                       double* scratch, void* stream);
+
+/* ---- data term, sparse counts (poisson.py:156-184 log_likelihood_components, :597-618 z prior +
+ *      reduce, :623-650 encode) and its backward ---- */
+/* per-row constants of a CSR shard: rowsum[r] = sum_d x, lgam[r] = sum_d lgamma(x+1) */
+int spmf_csr_row_consts(const long long* rowptr, const float* vals, long long nrows, float* rowsum,
+                        float* lgam, void* stream);
+/* row pass: z = r_b * x.A' ; lambda at nonzeros ; dz ; per-row scalars.  r_b = rowsum*inv_xi if
+ * scale_rows else 1.  `rowptr` points at the first row of the batch; offsets index cols/vals. */
+int spmf_csr_rows(const long long* rowptr, const int* cols, const float* vals, const float* rowsum,
+                  const float* lgam, float inv_xi, int scale_rows, int nrows, int D, int K, int S,
+                  const float* Ap, const float* EV, const float* PH, const double* vsum, float* z,
+                  float* dzr, float* rowacc, int variant, void* stream);
+/* encode only (inference): z[NQ][B][KP][SV] */
+int spmf_csr_encode(const long long* rowptr, const int* cols, const float* vals, const float* rowsum,
+                    float inv_xi, int scale_rows, int nrows, int D, int K, int S, const float* Ap,
+                    float* z, void* stream);
+/* column pass over the CSC copy of the same batch (rows are batch-local): accumulates into
+ * GAp, GEVnz, Gphinz, which this call zeroes first. */
+int spmf_csc_cols(const int* colptr, const int* rows, const float* vals, int nnz, int nrows, int D,
+                  int K, int S, const float* z, const float* dzr, const float* EV, const float* PH,
+                  float* GAp, float* GEVnz, float* Gphinz, int variant, void* stream);
+/* sums over the rows of the batch: zcolsum[NQ][KP][SV], datasums[NQ][4][SV] */
+int spmf_batch_sums(const float* z, const float* rowacc, int nrows, int K, int S, double* zcolsum,
+                    double* datasums, double* scratch, void* stream);
+
+/* ---- backward to the 24 variational tensors + loss parts [EXT L3/L4 GradientTape] ----
+ * parts[S][16]: 12 prior terms in the reference's var_list order (poisson.py:572), log q, 'z', 'x'
+ * (the dict of unormalized_log_prob_parts, poisson.py:582-621), [15] = per-draw loss. */
+int spmf_backward_params(const float* params, const float* noise, const float* eta, int D, int K, int S,
+                         const float* GAp, const float* GEVnz, const float* Gphinz,
+                         const double* zcolsum, const double* datasums, const double* phisum,
+                         float batch_rows, float u_tau_scale, float s_tau_scale, float decay,
+                         float w_entropy, float w_prior, int world_size, float* grads, double* parts,
+                         float* scratch_f, double* scratch_d, void* stream);
+
+/* ---- optimiser [EXT L4: Adam + clip in bayesianquilts' batched_minimize] ---- */
+int spmf_adam_step(float* params, const float* grads, float* m, float* v, long long n, float lr,
+                   float beta1, float beta2, float eps, int step, float clip_value, float grad_scale,
+                   void* stream);
+int spmf_sumsq(const float* g, long long n, float* tmp, double* out, double* scratch, void* stream);
+int spmf_colsum(const float* in, long long n, int c, int q, double* out, double* scratch, void* stream);
+
+/* ---- data formats either side of the path ---- */
+/* compute_scales (poisson.py:113-154): colsum[D] (double) and colnnz[D] (float, as the reference
+ * accumulates the non-zero counter in fp32) over a CSR shard; accumulates (caller zeroes). */
+int spmf_csr_colstats(const int* cols, const float* vals, long long nnz, int D, double* colsum,
+                      float* colnnz, void* stream);
+/* CSR batch -> CSC batch (colptr[D+1], rows batch-local).  cursor: int[D+1] scratch. */
+int spmf_csr_to_csc(const long long* rowptr, const int* cols, const float* vals, int nrows, int D,
+                    int* colptr, int* rows_out, float* vals_out, int* cursor, void* stream);
+/* dense (B,D) fp32 counts -> CSR (rowptr[B+1] int64, cols, vals); two calls: count then fill. */
+int spmf_dense_count(const float* x, int nrows, int D, long long* rowptr, void* stream);
+int spmf_dense_fill(const float* x, int nrows, int D, const long long* rowptr, int* cols, float* vals,
+                    void* stream);
+
+const char* spmf_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPMF_B200_H */

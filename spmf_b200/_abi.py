@@ -1,0 +1,106 @@
+"""ctypes binding of the C ABI declared in include/spmf_b200.h.
+
+The shared library is the product: if it is missing or a call fails, we raise -- there is no
+CPU / PyTorch fallback for any compute entry point.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libspmf_b200.so")
+
+NUM_TENSORS = 24
+NUM_VARS = 12
+NUM_PARTS = 16
+MAX_K = 128
+
+
+class SpmfError(RuntimeError):
+    pass
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: build it with `python -m spmf_b200.build` "
+            "(nvcc, sm_100a).  spmf_b200 has no CPU fallback.")
+    return C.CDLL(LIB_PATH)
+
+
+_lib = _load()
+
+p = C.c_void_p
+i32 = C.c_int
+i64 = C.c_longlong
+f32 = C.c_float
+u64 = C.c_ulonglong
+u32 = C.c_uint
+
+_SIGS = {
+    "spmf_kpad": (i32, [i32]),
+    "spmf_draw_vec": (i32, [i32]),
+    "spmf_layout": (i32, [i32, i32, i32, C.POINTER(i64), C.POINTER(i64)]),
+    "spmf_backward_scratch_floats": (i64, [i32, i32, i32]),
+    "spmf_backward_scratch_doubles": (i64, [i32, i32, i32]),
+    "spmf_fill_noise": (i32, [p, p, i32, i32, i32, u64, u32, p]),
+    "spmf_sample": (i32, [p, p, i32, i32, i32, p, p]),
+    "spmf_draw_operands": (i32, [p, p, p, i32, i32, i32, p, p, p, p, p, p, p]),
+    "spmf_csr_row_consts": (i32, [p, p, i64, p, p, p]),
+    "spmf_csr_rows": (i32, [p, p, p, p, p, f32, i32, i32, i32, i32, i32, p, p, p, p, p, p, p, i32, p]),
+    "spmf_csr_encode": (i32, [p, p, p, p, f32, i32, i32, i32, i32, i32, p, p, p]),
+    "spmf_csc_cols": (i32, [p, p, p, i32, i32, i32, i32, i32, p, p, p, p, p, p, p, i32, p]),
+    "spmf_batch_sums": (i32, [p, p, i32, i32, i32, p, p, p, p]),
+    "spmf_backward_params": (i32, [p, p, p, i32, i32, i32, p, p, p, p, p, p, f32, f32, f32, f32, f32,
+                                   f32, i32, p, p, p, p, p]),
+    "spmf_adam_step": (i32, [p, p, p, p, i64, f32, f32, f32, f32, i32, f32, f32, p]),
+    "spmf_sumsq": (i32, [p, i64, p, p, p, p]),
+    "spmf_colsum": (i32, [p, i64, i32, i32, p, p, p]),
+    "spmf_csr_colstats": (i32, [p, p, i64, i32, p, p, p]),
+    "spmf_csr_to_csc": (i32, [p, p, p, i32, i32, p, p, p, p, p]),
+    "spmf_dense_count": (i32, [p, i32, i32, p, p]),
+    "spmf_dense_fill": (i32, [p, i32, i32, p, p, p, p]),
+    "spmf_version": (C.c_char_p, []),
+}
+
+EXPORTS = tuple(_SIGS)
+
+for _name, (_res, _args) in _SIGS.items():
+    _fn = getattr(_lib, _name)      # AttributeError here = header / library mismatch
+    _fn.restype = _res
+    _fn.argtypes = _args
+
+
+def _check(rc, name):
+    if rc != 0:
+        kind = {-1: "bad argument", -2: "unsupported configuration"}.get(rc, f"CUDA error {rc}")
+        raise SpmfError(f"{name} failed: {kind}")
+
+
+def call(name, *args):
+    """Call an int-returning entry point and raise on a non-zero status."""
+    _check(getattr(_lib, name)(*args), name)
+
+
+def kpad(K):
+    return _lib.spmf_kpad(K)
+
+
+def draw_vec(S):
+    return _lib.spmf_draw_vec(S)
+
+
+def layout(D, K, S):
+    t = (i64 * (NUM_TENSORS + 1))()
+    n = (i64 * (NUM_VARS + 1))()
+    _check(_lib.spmf_layout(D, K, S, t, n), "spmf_layout")
+    return list(t), list(n)
+
+
+def backward_scratch(D, K, S):
+    return (_lib.spmf_backward_scratch_floats(D, K, S), _lib.spmf_backward_scratch_doubles(D, K, S))
+
+
+def version():
+    return _lib.spmf_version().decode()

@@ -1,0 +1,161 @@
+// Scalar fp32 math shared by the sampling / prior kernels.  Every function is
+// __host__ __device__ so tests can run the exact same code on the CPU
+// (csrc/hostcheck.cpp) without a GPU.
+//
+// Restates TFP / bayesianquilts semantics needed by the ADVI step of
+// mederrata_spmf/poisson.py (surrogate at :403-539, priors at :225-377); see
+// SURVEY.md section 3.4.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define SPMF_HD __host__ __device__ __forceinline__
+#else
+#define SPMF_HD inline
+#endif
+
+namespace spmf {
+
+constexpr float kHalfLog2OverPi = -0.22579135264472743f;  // 0.5*log(2/pi)
+constexpr float kHalfLog2Pi = 0.9189385332046727f;        // 0.5*log(2*pi)
+constexpr float kLgammaHalf = 0.5723649429247001f;        // lgamma(0.5)
+constexpr float kLog2 = 0.6931471805599453f;
+
+SPMF_HD float softplusf(float x) { return fmaxf(x, 0.f) + log1pf(expf(-fabsf(x))); }
+SPMF_HD float sigmoidf(float x) {
+  float e = expf(-fabsf(x));
+  float s = 1.f / (1.f + e);
+  return x >= 0.f ? s : e * s;
+}
+// 1 - sigmoid(x) without cancellation
+SPMF_HD float one_minus_sigmoidf(float x) { return sigmoidf(-x); }
+SPMF_HD float log_sigmoidf(float x) { return -softplusf(-x); }
+
+SPMF_HD float digammaf_pos(float x) {
+  // x > 0.  Shift to x >= 6 with psi(x) = psi(x+1) - 1/x, then the asymptotic series.
+  float acc = 0.f;
+  while (x < 6.f) {
+    acc -= 1.f / x;
+    x += 1.f;
+  }
+  float r = 1.f / x, r2 = r * r;
+  return acc + logf(x) - 0.5f * r -
+         r2 * (1.f / 12.f - r2 * (1.f / 120.f - r2 * (1.f / 252.f)));
+}
+
+// dg/dalpha of a standard Gamma(alpha) draw g at fixed quantile (implicit
+// reparameterisation, Figurnov et al. 2018 -- what tf.random.gamma's gradient returns).
+//   g <= max(1, alpha+1): power series  (g/a) [sum T_n H_n - (log g - psi(a+1)) sum T_n]
+//   otherwise: Cephes igamc continued fraction differentiated in alpha.
+SPMF_HD float gamma_sample_der_alpha(float a, float x) {
+  if (!(x > 0.f)) return 0.f;
+  if (x <= 1.f || x <= a + 1.f) {
+    float T = 1.f, H = 0.f, sT = 1.f, sTH = 0.f;
+    for (int n = 1; n < 400; ++n) {
+      float inv = 1.f / (a + (float)n);
+      T *= x * inv;
+      H += inv;
+      sT += T;
+      sTH += T * H;
+      if (T * (1.f + H) < 1e-9f * sT) break;
+    }
+    return (x / a) * (sTH - (logf(x) - digammaf_pos(a + 1.f)) * sT);
+  }
+  float y = 1.f - a, z = x + y + 1.f;
+  float pkm2 = 1.f, qkm2 = x, pkm1 = x + 1.f, qkm1 = z * x;
+  float dpkm2 = 0.f, dqkm2 = 0.f, dpkm1 = 0.f, dqkm1 = -x;
+  float ans = pkm1 / qkm1;
+  float dans = (dpkm1 - ans * dqkm1) / qkm1;
+  for (int c = 1; c < 400; ++c) {
+    y += 1.f;
+    z += 2.f;
+    float fc = (float)c;
+    float yc = y * fc, dyc = -fc;
+    float pk = pkm1 * z - pkm2 * yc;
+    float qk = qkm1 * z - qkm2 * yc;
+    float dpk = dpkm1 * z - pkm1 - dpkm2 * yc - pkm2 * dyc;
+    float dqk = dqkm1 * z - qkm1 - dqkm2 * yc - qkm2 * dyc;
+    float nans = pk / qk;
+    float ndans = (dpk - nans * dqk) / qk;
+    float delta = fabsf(ndans - dans);
+    float scale = fabsf(ndans) + 1e-30f;
+    ans = nans;
+    dans = ndans;
+    pkm2 = pkm1; pkm1 = pk; qkm2 = qkm1; qkm1 = qk;
+    dpkm2 = dpkm1; dpkm1 = dpk; dqkm2 = dqkm1; dqkm1 = dqk;
+    if (fabsf(pk) > 1e18f || fabsf(qk) > 1e18f) {
+      const float sc = 1e-18f;
+      pkm2 *= sc; pkm1 *= sc; qkm2 *= sc; qkm1 *= sc;
+      dpkm2 *= sc; dpkm1 *= sc; dqkm2 *= sc; dqkm1 *= sc;
+    }
+    if (delta < 2e-8f * scale && c > 3) break;
+  }
+  return x * (dans + ans * (logf(x) - digammaf_pos(a)));
+}
+
+// ---------------------------------------------------------------------------
+// Philox4x32-10 counter RNG (Salmon et al. 2011).  Own implementation so that the
+// stream is a pure function of (seed, var, step, element) and identical on every rank.
+// ---------------------------------------------------------------------------
+struct U4 { uint32_t x, y, z, w; };
+
+SPMF_HD uint32_t mulhi32(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
+
+SPMF_HD U4 philox4x32_10(U4 ctr, uint32_t k0, uint32_t k1) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0 = mulhi32(M0, ctr.x), lo0 = M0 * ctr.x;
+    uint32_t hi1 = mulhi32(M1, ctr.z), lo1 = M1 * ctr.z;
+    U4 n;
+    n.x = hi1 ^ ctr.y ^ k0;
+    n.y = lo1;
+    n.z = hi0 ^ ctr.w ^ k1;
+    n.w = lo0;
+    ctr = n;
+    k0 += W0;
+    k1 += W1;
+  }
+  return ctr;
+}
+
+// (0,1] uniform from 32 random bits
+SPMF_HD float u01(uint32_t r) { return ((float)(r >> 8) + 1.0f) * (1.0f / 16777216.0f); }
+
+SPMF_HD void box_muller(uint32_t r0, uint32_t r1, float* n0, float* n1) {
+  float u = u01(r0), v = u01(r1);
+  float rad = sqrtf(-2.f * logf(u));
+  float ang = 6.283185307179586f * v;
+  *n0 = rad * cosf(ang);
+  *n1 = rad * sinf(ang);
+}
+
+// Marsaglia-Tsang standard Gamma(alpha) draw; one private Philox stream per element.
+SPMF_HD float gamma_draw(float alpha, uint32_t elem_lo, uint32_t elem_hi, uint32_t stream,
+                         uint32_t k0, uint32_t k1) {
+  float a = alpha < 1.f ? alpha + 1.f : alpha;
+  float d = a - 1.f / 3.f;
+  float c = 1.f / sqrtf(9.f * d);
+  float boost = 1.f;
+  float g = d;
+  for (uint32_t it = 0; it < 64; ++it) {
+    U4 ctr = {elem_lo, elem_hi, stream, it};
+    U4 r = philox4x32_10(ctr, k0, k1);
+    float n0, n1;
+    box_muller(r.x, r.y, &n0, &n1);
+    if (it == 0 && alpha < 1.f) boost = powf(u01(r.w), 1.f / alpha);
+    float v = 1.f + c * n0;
+    if (v <= 0.f) continue;
+    v = v * v * v;
+    float u = u01(r.z);
+    float x2 = n0 * n0;
+    if (u < 1.f - 0.0331f * x2 * x2 || logf(u) < 0.5f * x2 + d * (1.f - v + logf(v))) {
+      g = d * v;
+      break;
+    }
+  }
+  g *= boost;
+  return fmaxf(g, 1.17549435e-38f);
+}
+
+}  // namespace spmf

@@ -1,0 +1,495 @@
+// O(D*K*S) kernels around the data term: noise generation, reparameterised draws ->
+// gather operands, prior/entropy forward+backward chained with the data-term gradients,
+// deterministic reductions, Adam.  One warp per feature d, lanes over latent k; the
+// per-element math lives in spmf_model.cuh (shared with the CPU host check).
+//
+// Replaces, for the ADVI step of mederrata_spmf/poisson.py (paths relative to /root/reference):
+//   surrogate_distribution.sample / log_prob   [EXT L3], poisson.py:403-573
+//   prior_distribution.log_prob_parts           poisson.py:590
+//   encoding_matrix / intercept_matrix          poisson.py:652-701
+//   tf.GradientTape backward + Adam             [EXT L4]
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/spmf_b200.h"
+#include "spmf_model.cuh"
+
+namespace spmf {
+
+#define SPMF_CHECK_LAUNCH()                      \
+  do {                                           \
+    cudaError_t e__ = cudaGetLastError();        \
+    if (e__ != cudaSuccess) return (int)e__;     \
+  } while (0)
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ------------------------------------------------------------------ noise
+// Normal variables: 4 normals per Philox call; element index e -> (call e/4, slot e%4).
+__global__ void fill_normal_kernel(float* __restrict__ out, long long n, uint32_t stream,
+                                   uint32_t step, uint32_t k0, uint32_t k1) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long base = i * 4;
+  if (base >= n) return;
+  U4 ctr = {(uint32_t)(i & 0xffffffffu), (uint32_t)(i >> 32), stream, step};
+  U4 r = philox4x32_10(ctr, k0, k1);
+  float v[4];
+  box_muller(r.x, r.y, &v[0], &v[1]);
+  box_muller(r.z, r.w, &v[2], &v[3]);
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    if (base + j < n) out[base + j] = v[j];
+}
+
+// Gamma variables: out[s][e] ~ Gamma(softplus(conc_raw[e]), 1)
+__global__ void fill_gamma_kernel(float* __restrict__ out, const float* __restrict__ conc_raw,
+                                  long long nelem, int S, uint32_t stream, uint32_t step,
+                                  uint32_t k0, uint32_t k1) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nelem * S) return;
+  long long e = i % nelem;
+  float alpha = softplusf(conc_raw[e]);
+  // stream id folds the step so that (element, iteration) keep the whole counter space
+  out[i] = gamma_draw(alpha, (uint32_t)(i & 0xffffffffu), (uint32_t)(i >> 32),
+                      stream ^ (step * 0x9E3779B9u), k0, k1 ^ step);
+}
+
+// ------------------------------------------------------------------ draw -> operands
+template <int KK>
+__global__ void __launch_bounds__(128)
+draw_operands_kernel(Layout L, const float* __restrict__ P, const float* __restrict__ N,
+                     const float* __restrict__ eta, int SV, int KP, float* __restrict__ Ap,
+                     float* __restrict__ EV, float* __restrict__ PH) {
+  const int lane = threadIdx.x & 31;
+  const int d = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (d >= L.D) return;
+  LaneState<KK> st;
+  FeatState f;
+  lane_init<KK>(st, L, P, d, lane);
+  feat_init(f, L, P, d);
+  for (int s = 0; s < L.S; ++s) {
+    const int q = s / SV, sv = s - q * SV;
+    FeatDraw fd = feat_draw(f, L, N, d, s);
+#pragma unroll
+    for (int i = 0; i < KK; ++i) {
+      int k = lane + 32 * i;
+      if (k < KP) {
+        float ap = 0.f, ev = 0.f;
+        if (k < L.K) lane_operands<KK>(st, L, N, eta, d, lane, i, s, fd.a, &ap, &ev, nullptr, nullptr);
+        long long idx = (((long long)q * L.D + d) * KP + k) * SV + sv;
+        Ap[idx] = ap;
+        EV[idx] = ev;
+      }
+    }
+    if (lane == 0) PH[((long long)q * L.D + d) * SV + sv] = eta[d] * fd.b * fd.w.y;  // poisson.py:701
+  }
+}
+
+// Optional: materialise the draws themselves (API surface: surrogate_distribution.sample()).
+// out[var][s][elem] in the same layout as the noise buffer.
+__global__ void sample_kernel(Layout L, const float* __restrict__ P, const float* __restrict__ N,
+                              float* __restrict__ out) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  for (int v = 0; v < NUM_VARS; ++v) {
+    long long n = L.vsize[v] * L.S;
+    if (i < n) {
+      long long e = i % L.vsize[v];
+      float a = P[L.toff[2 * v] + e], b = P[L.toff[2 * v + 1] + e];
+      float nz = N[L.noff[v] + i];
+      float y;
+      if (v <= VAR_S) {
+        NParam p = nparam_init(a, b);
+        y = ndraw(p, nz).y;
+      } else {
+        y = softplusf(softplusf(b) / nz);
+      }
+      out[L.noff[v] + i] = y;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ backward (per feature)
+template <int KK>
+__global__ void __launch_bounds__(128)
+backward_feat_kernel(Layout L, Hyper h, const float* __restrict__ P, const float* __restrict__ N,
+                     const float* __restrict__ eta, int SV, int KP,
+                     const float* __restrict__ GAp, const float* __restrict__ GEVnz,
+                     const float* __restrict__ Gphinz, const double* __restrict__ zcolsum,
+                     float* __restrict__ grads, float* __restrict__ scr_utau,
+                     float* __restrict__ scr_parts) {
+  const int lane = threadIdx.x & 31;
+  const int d = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (d >= L.D) return;
+  LaneState<KK> st;
+  FeatState f;
+  lane_init<KK>(st, L, P, d, lane);
+  feat_init(f, L, P, d);
+  for (int s = 0; s < L.S; ++s) {
+    const int q = s / SV, sv = s - q * SV;
+    FeatDraw fd = feat_draw(f, L, N, d, s);
+    float da = 0.f, pp[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < KK; ++i) {
+      int k = lane + 32 * i;
+      if (k < L.K) {
+        long long idx = (((long long)q * L.D + d) * KP + k) * SV + sv;
+        DkUp up;
+        up.GAp = GAp[idx];
+        up.GEV = GEVnz[idx] - (float)zcolsum[((long long)q * KP + k) * SV + sv];
+        DkOut o = lane_step<KK>(st, L, h, N, eta, d, lane, i, s, fd.a, up);
+        da += o.da;
+        scr_utau[((long long)s * L.D + d) * L.K + k] = o.dutau;
+#pragma unroll
+        for (int j = 0; j < 5; ++j) pp[j] += o.parts[j];
+      }
+    }
+    da = warp_sum(da);
+#pragma unroll
+    for (int j = 0; j < 5; ++j) pp[j] = warp_sum(pp[j]);
+    if (lane == 0) {
+      float fp[7];
+      feat_step(f, fd, L, h, N, eta, d, s, da, Gphinz[((long long)q * L.D + d) * SV + sv], fp);
+      float* o = scr_parts + ((long long)d * L.S + s) * NUM_PARTS;
+      o[P_V] = pp[1]; o[P_W] = fp[0]; o[P_U] = pp[0]; o[P_UETA] = pp[2]; o[P_UTAU] = 0.f;
+      o[P_SETA] = fp[2]; o[P_STAU] = fp[3]; o[P_S] = fp[1]; o[P_UETAA] = pp[3]; o[P_UTAUA] = 0.f;
+      o[P_SETAA] = fp[4]; o[P_STAUA] = fp[5]; o[P_LOGQ] = pp[4] + fp[6];
+      o[P_Z] = 0.f; o[P_X] = 0.f; o[15] = 0.f;
+    }
+  }
+  const float invS = 1.f / (float)L.S;
+  const float wer = h.w_entropy * h.rep_scale;
+#pragma unroll
+  for (int i = 0; i < KK; ++i) {
+    int k = lane + 32 * i;
+    if (k < L.K) {
+      long long e = (long long)d * L.K + k;
+      nparam_finish(st.u[i], P[L.toff[U_RHO] + e], invS, wer, &grads[L.toff[U_LOC] + e], &grads[L.toff[U_RHO] + e]);
+      nparam_finish(st.v[i], P[L.toff[V_RHO] + e], invS, wer, &grads[L.toff[V_LOC] + e], &grads[L.toff[V_RHO] + e]);
+      gparam_finish(st.ue[i], P[L.toff[UETA_C] + e], P[L.toff[UETA_B] + e], invS, &grads[L.toff[UETA_C] + e], &grads[L.toff[UETA_B] + e]);
+      gparam_finish(st.ua[i], P[L.toff[UETAA_C] + e], P[L.toff[UETAA_B] + e], invS, &grads[L.toff[UETAA_C] + e], &grads[L.toff[UETAA_B] + e]);
+    }
+  }
+  if (lane == 0) {
+    const int D = L.D;
+    nparam_finish(f.w, P[L.toff[W_RHO] + d], invS, wer, &grads[L.toff[W_LOC] + d], &grads[L.toff[W_RHO] + d]);
+    nparam_finish(f.s0, P[L.toff[S_RHO] + d], invS, wer, &grads[L.toff[S_LOC] + d], &grads[L.toff[S_RHO] + d]);
+    nparam_finish(f.s1, P[L.toff[S_RHO] + D + d], invS, wer, &grads[L.toff[S_LOC] + D + d], &grads[L.toff[S_RHO] + D + d]);
+    gparam_finish(f.se0, P[L.toff[SETA_C] + d], P[L.toff[SETA_B] + d], invS, &grads[L.toff[SETA_C] + d], &grads[L.toff[SETA_B] + d]);
+    gparam_finish(f.se1, P[L.toff[SETA_C] + D + d], P[L.toff[SETA_B] + D + d], invS, &grads[L.toff[SETA_C] + D + d], &grads[L.toff[SETA_B] + D + d]);
+    gparam_finish(f.st, P[L.toff[STAU_C] + d], P[L.toff[STAU_B] + d], invS, &grads[L.toff[STAU_C] + d], &grads[L.toff[STAU_B] + d]);
+    gparam_finish(f.sea0, P[L.toff[SETAA_C] + d], P[L.toff[SETAA_B] + d], invS, &grads[L.toff[SETAA_C] + d], &grads[L.toff[SETAA_B] + d]);
+    gparam_finish(f.sea1, P[L.toff[SETAA_C] + D + d], P[L.toff[SETAA_B] + D + d], invS, &grads[L.toff[SETAA_C] + D + d], &grads[L.toff[SETAA_B] + D + d]);
+    gparam_finish(f.sta, P[L.toff[STAUA_C] + d], P[L.toff[STAUA_B] + d], invS, &grads[L.toff[STAUA_C] + d], &grads[L.toff[STAUA_B] + d]);
+  }
+}
+
+// ------------------------------------------------------------------ backward (per latent k)
+__global__ void backward_lat_kernel(Layout L, Hyper h, const float* __restrict__ P,
+                                    const float* __restrict__ N, const double* __restrict__ dutau,
+                                    float* __restrict__ grads, float* __restrict__ scr_lat) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= L.K) return;
+  LatState t;
+  lat_init(t, L, P, k);
+  for (int s = 0; s < L.S; ++s) {
+    float pp[3];
+    lat_step(t, L, h, N, k, s, (float)dutau[(long long)s * L.K + k], pp);
+    float* o = scr_lat + ((long long)k * L.S + s) * NUM_PARTS;
+    for (int j = 0; j < NUM_PARTS; ++j) o[j] = 0.f;
+    o[P_UTAU] = pp[0]; o[P_UTAUA] = pp[1]; o[P_LOGQ] = pp[2];
+  }
+  const float invS = 1.f / (float)L.S;
+  gparam_finish(t.ut, P[L.toff[UTAU_C] + k], P[L.toff[UTAU_B] + k], invS, &grads[L.toff[UTAU_C] + k], &grads[L.toff[UTAU_B] + k]);
+  gparam_finish(t.uta, P[L.toff[UTAUA_C] + k], P[L.toff[UTAUA_B] + k], invS, &grads[L.toff[UTAUA_C] + k], &grads[L.toff[UTAUA_B] + k]);
+}
+
+// ------------------------------------------------------------------ deterministic reductions
+// out[q][split][c] = sum over rows of in[q][row][c] for rows of this split (fixed order).
+template <typename TIn>
+__global__ void reduce_rows_kernel(const TIn* __restrict__ in, double* __restrict__ out,
+                                   long long n, int c, int nsplit) {
+  __shared__ double sm[8][33];
+  const int cx = blockIdx.x * 32 + threadIdx.x;
+  const int split = blockIdx.y, q = blockIdx.z;
+  const long long chunk = (n + nsplit - 1) / nsplit;
+  const long long r0 = split * chunk;
+  long long r1 = r0 + chunk;
+  if (r1 > n) r1 = n;
+  double acc = 0.0;
+  if (cx < c) {
+    const TIn* base = in + (long long)q * n * c + cx;
+    for (long long r = r0 + threadIdx.y; r < r1; r += 8) acc += (double)base[r * c];
+  }
+  sm[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && cx < c) {
+    double t = 0.0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t += sm[j][threadIdx.x];
+    out[((long long)q * nsplit + split) * c + cx] = t;
+  }
+}
+
+// parts[s][p] (double) and loss from the reduced pieces.
+//   featparts[S*16], latparts[S*16]: prior/logq sums;
+//   data[NQ][4][SV]: (sum_nz x log lam - sum lgamma(x+1), sum z.vsum, sum z^2, #non-finite)
+//   Lx = sum_nz [x log lam - lgamma(x+1)] - sum z.vsum - B * phisum   (SURVEY 3.4 closed form)
+//   Lz = B*K*0.5*log(2/pi) - 0.5 * sum z^2                            (poisson.py:599-604)
+__global__ void finalize_parts_kernel(int S, int SV, int K, const double* __restrict__ featparts,
+                                      const double* __restrict__ latparts,
+                                      const double* __restrict__ data, const double* __restrict__ phisum,
+                                      double batch_rows, double w_entropy,
+                                      double w_prior, double* __restrict__ parts_out,
+                                      float* __restrict__ comm) {
+  int s = threadIdx.x;
+  if (s >= S) return;
+  double* o = parts_out + (long long)s * NUM_PARTS;
+  for (int p = 0; p <= P_LOGQ; ++p) o[p] = featparts[s * NUM_PARTS + p] + latparts[s * NUM_PARTS + p];
+  const int q = s / SV, sv = s - q * SV;
+  const double* dd = data + ((long long)q * 4) * SV;   // data[q][4][SV]
+  double xlog = dd[0 * SV + sv], zv = dd[1 * SV + sv], z2 = dd[2 * SV + sv];
+  o[P_X] = xlog - zv - batch_rows * phisum[q * SV + sv];
+  o[P_Z] = batch_rows * (double)K * (double)kHalfLog2OverPi - 0.5 * z2;
+  double prior = 0.0;
+  for (int p = 0; p < P_LOGQ; ++p) prior += o[p];
+  o[15] = w_entropy * o[P_LOGQ] - w_prior * prior - o[P_Z] - o[P_X];   // per-draw loss
+  // data parts as (hi, lo) float pairs inside the all-reduced gradient block: summed across ranks
+  // by the same collective as the gradients and recombined in double on the host side.
+  if (4 * s + 3 < kCommSlack) {
+    float zh = (float)o[P_Z], xh = (float)o[P_X];
+    comm[4 * s + 0] = zh; comm[4 * s + 1] = (float)(o[P_Z] - (double)zh);
+    comm[4 * s + 2] = xh; comm[4 * s + 3] = (float)(o[P_X] - (double)xh);
+  }
+}
+
+// ------------------------------------------------------------------ Adam  [EXT L4]
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, long long n, float lr, float b1, float b2, float eps,
+                            float bc1, float bc2, float clip_value, float grad_scale) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float gi = g[i] * grad_scale;
+  if (!isfinite(gi)) gi = 0.f;                 // non-finite gradients are dropped, not propagated
+  if (clip_value > 0.f) gi = fminf(fmaxf(gi, -clip_value), clip_value);
+  float mi = b1 * m[i] + (1.f - b1) * gi;
+  float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+  m[i] = mi;
+  v[i] = vi;
+  p[i] -= lr * (mi / bc1) / (sqrtf(vi / bc2) + eps);
+}
+
+// sum of squares (double) of a float vector, deterministic two-stage via reduce_rows
+__global__ void square_kernel(const float* __restrict__ g, float* __restrict__ out, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    float x = g[i];
+    out[i] = isfinite(x) ? x * x : 0.f;
+  }
+}
+
+static Hyper make_hyper(float u_tau_scale, float s_tau_scale, float decay, float w_entropy,
+                        float w_prior, int world, float batch_rows) {
+  Hyper h;
+  h.u_tau_b = 1.f / (u_tau_scale * u_tau_scale);
+  h.s_tau_b = 1.f / (s_tau_scale * s_tau_scale);
+  h.decay = decay;
+  h.w_entropy = w_entropy;
+  h.w_prior = w_prior;
+  h.rep_scale = 1.f / (float)world;
+  h.batch_rows = batch_rows;
+  return h;
+}
+
+static int nsplit_for(long long n) {
+  long long s = (n + 255) / 256;
+  if (s < 1) s = 1;
+  if (s > 64) s = 64;
+  return (int)s;
+}
+
+// out (double[q][c]) = column sums of in[q][n][c]; scratch needs q*nsplit*c doubles.
+template <typename TIn>
+static int reduce_rows(const TIn* in, double* out, double* scratch, long long n, int c, int q,
+                       cudaStream_t st) {
+  if (n <= 0 || c <= 0 || q <= 0) return SPMF_ERR_BAD_ARG;
+  int ns = nsplit_for(n);
+  dim3 blk(32, 8);
+  if (ns == 1) {
+    reduce_rows_kernel<TIn><<<dim3((c + 31) / 32, 1, q), blk, 0, st>>>(in, out, n, c, 1);
+  } else {
+    reduce_rows_kernel<TIn><<<dim3((c + 31) / 32, ns, q), blk, 0, st>>>(in, scratch, n, c, ns);
+    reduce_rows_kernel<double><<<dim3((c + 31) / 32, 1, q), blk, 0, st>>>(scratch, out, ns, c, 1);
+  }
+  SPMF_CHECK_LAUNCH();
+  return SPMF_OK;
+}
+
+}  // namespace spmf
+
+using namespace spmf;
+
+extern "C" {
+
+int spmf_kpad(int K) {
+  int kp = 1;
+  while (kp < K) kp <<= 1;
+  return kp;
+}
+
+int spmf_draw_vec(int S) { return (S % 4 == 0) ? 4 : (S % 2 == 0) ? 2 : 1; }
+
+int spmf_layout(int D, int K, int S, long long* tensor_offsets, long long* noise_offsets) {
+  if (D <= 0 || K <= 0 || S <= 0 || K > SPMF_MAX_K) return SPMF_ERR_BAD_ARG;
+  Layout L = make_layout(D, K, S);
+  for (int i = 0; i <= NUM_TENSORS; ++i) tensor_offsets[i] = L.toff[i];
+  for (int i = 0; i <= NUM_VARS; ++i) noise_offsets[i] = L.noff[i];
+  return SPMF_OK;
+}
+
+int spmf_fill_noise(float* noise, const float* params, int D, int K, int S, unsigned long long seed,
+                    unsigned int step, void* stream) {
+  if (!noise || !params || D <= 0 || K <= 0 || S <= 0 || K > SPMF_MAX_K) return SPMF_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  Layout L = make_layout(D, K, S);
+  uint32_t k0 = (uint32_t)(seed & 0xffffffffu), k1 = (uint32_t)(seed >> 32);
+  for (int v = 0; v < NUM_VARS; ++v) {
+    long long n = L.vsize[v] * S;
+    if (v <= VAR_S) {
+      long long calls = (n + 3) / 4;
+      fill_normal_kernel<<<(unsigned)((calls + 255) / 256), 256, 0, st>>>(noise + L.noff[v], n, (uint32_t)v, step, k0, k1);
+    } else {
+      fill_gamma_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(noise + L.noff[v], params + L.toff[2 * v], L.vsize[v], S, (uint32_t)v, step, k0, k1);
+    }
+  }
+  SPMF_CHECK_LAUNCH();
+  return SPMF_OK;
+}
+
+int spmf_sample(const float* params, const float* noise, int D, int K, int S, float* samples,
+                void* stream) {
+  if (!params || !noise || !samples || K > SPMF_MAX_K) return SPMF_ERR_BAD_ARG;
+  Layout L = make_layout(D, K, S);
+  long long nmax = (long long)D * K * S;
+  if (nmax < 2LL * D * S) nmax = 2LL * D * S;
+  sample_kernel<<<(unsigned)((nmax + 255) / 256), 256, 0, (cudaStream_t)stream>>>(L, params, noise, samples);
+  SPMF_CHECK_LAUNCH();
+  return SPMF_OK;
+}
+
+int spmf_draw_operands(const float* params, const float* noise, const float* eta, int D, int K, int S,
+                       float* Ap, float* EV, float* PH, double* vsum, double* phisum,
+                       double* scratch, void* stream) {
+  if (!params || !noise || !eta || !Ap || !EV || !PH || !vsum || !phisum || !scratch) return SPMF_ERR_BAD_ARG;
+  if (D <= 0 || K <= 0 || S <= 0 || K > SPMF_MAX_K) return SPMF_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  Layout L = make_layout(D, K, S);
+  const int KP = spmf_kpad(K), SV = spmf_draw_vec(S), NQ = S / SV;
+  dim3 grid((D + 3) / 4);
+  if (KP <= 32) draw_operands_kernel<1><<<grid, 128, 0, st>>>(L, params, noise, eta, SV, KP, Ap, EV, PH);
+  else if (KP <= 64) draw_operands_kernel<2><<<grid, 128, 0, st>>>(L, params, noise, eta, SV, KP, Ap, EV, PH);
+  else draw_operands_kernel<4><<<grid, 128, 0, st>>>(L, params, noise, eta, SV, KP, Ap, EV, PH);
+  SPMF_CHECK_LAUNCH();
+  int rc = reduce_rows<float>(EV, vsum, scratch, D, KP * SV, NQ, st);
+  if (rc) return rc;
+  return reduce_rows<float>(PH, phisum, scratch, D, SV, NQ, st);
+}
+
+int spmf_backward_params(const float* params, const float* noise, const float* eta, int D, int K, int S,
+                         const float* GAp, const float* GEVnz, const float* Gphinz,
+                         const double* zcolsum, const double* datasums, const double* phisum,
+                         float batch_rows, float u_tau_scale, float s_tau_scale,
+                         float decay, float w_entropy, float w_prior, int world_size, float* grads,
+                         double* parts, float* scr_f, double* scr_d, void* stream) {
+  if (!params || !noise || !eta || !GAp || !GEVnz || !Gphinz || !zcolsum || !datasums || !phisum ||
+      !grads || !parts || !scr_f || !scr_d)
+    return SPMF_ERR_BAD_ARG;
+  if (D <= 0 || K <= 0 || S <= 0 || K > SPMF_MAX_K || world_size <= 0) return SPMF_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  Layout L = make_layout(D, K, S);
+  Hyper h = make_hyper(u_tau_scale, s_tau_scale, decay, w_entropy, w_prior, world_size, batch_rows);
+  const int KP = spmf_kpad(K), SV = spmf_draw_vec(S);
+  // float scratch: scr_utau [S][D][K] | scr_parts [D][S*16] | scr_lat [K][S*16]
+  float* scr_utau = scr_f;
+  float* scr_parts = scr_utau + (long long)S * D * K;
+  float* scr_lat = scr_parts + (long long)D * S * NUM_PARTS;
+  // double scratch: dutau [S][K] | featparts [S*16] | latparts [S*16] | reduce scratch
+  double* dutau = scr_d;
+  double* featparts = dutau + (long long)S * K;
+  double* latparts = featparts + (long long)S * NUM_PARTS;
+  double* rscr = latparts + (long long)S * NUM_PARTS;
+  dim3 grid((D + 3) / 4);
+  if (KP <= 32) backward_feat_kernel<1><<<grid, 128, 0, st>>>(L, h, params, noise, eta, SV, KP, GAp, GEVnz, Gphinz, zcolsum, grads, scr_utau, scr_parts);
+  else if (KP <= 64) backward_feat_kernel<2><<<grid, 128, 0, st>>>(L, h, params, noise, eta, SV, KP, GAp, GEVnz, Gphinz, zcolsum, grads, scr_utau, scr_parts);
+  else backward_feat_kernel<4><<<grid, 128, 0, st>>>(L, h, params, noise, eta, SV, KP, GAp, GEVnz, Gphinz, zcolsum, grads, scr_utau, scr_parts);
+  SPMF_CHECK_LAUNCH();
+  int rc = reduce_rows<float>(scr_utau, dutau, rscr, D, K, S, st);
+  if (rc) return rc;
+  rc = reduce_rows<float>(scr_parts, featparts, rscr, D, S * NUM_PARTS, 1, st);
+  if (rc) return rc;
+  backward_lat_kernel<<<(K + 63) / 64, 64, 0, st>>>(L, h, params, noise, dutau, grads, scr_lat);
+  SPMF_CHECK_LAUNCH();
+  rc = reduce_rows<float>(scr_lat, latparts, rscr, K, S * NUM_PARTS, 1, st);
+  if (rc) return rc;
+  finalize_parts_kernel<<<1, ((S + 31) / 32) * 32, 0, st>>>(S, SV, K, featparts, latparts, datasums, phisum,
+                                                           (double)batch_rows,
+                                                           (double)w_entropy, (double)w_prior, parts,
+                                                           grads + L.comm_off);
+  SPMF_CHECK_LAUNCH();
+  return SPMF_OK;
+}
+
+long long spmf_backward_scratch_floats(int D, int K, int S) {
+  return (long long)S * D * K + (long long)D * S * NUM_PARTS + (long long)K * S * NUM_PARTS;
+}
+long long spmf_backward_scratch_doubles(int D, int K, int S) {
+  long long c = (long long)S * NUM_PARTS;
+  if (c < K) c = K;
+  return (long long)S * K + 2LL * S * NUM_PARTS + 64LL * S * c + 64LL * spmf_kpad(K) * S + 1024;
+}
+
+int spmf_adam_step(float* params, const float* grads, float* m, float* v, long long n, float lr,
+                   float beta1, float beta2, float eps, int step, float clip_value, float grad_scale,
+                   void* stream) {
+  if (!params || !grads || !m || !v || n <= 0 || step <= 0) return SPMF_ERR_BAD_ARG;
+  float bc1 = 1.f - powf(beta1, (float)step), bc2 = 1.f - powf(beta2, (float)step);
+  adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(params, grads, m, v, n, lr, beta1, beta2, eps, bc1, bc2, clip_value, grad_scale);
+  SPMF_CHECK_LAUNCH();
+  return SPMF_OK;
+}
+
+int spmf_sumsq(const float* g, long long n, float* tmp, double* out, double* scratch, void* stream) {
+  if (!g || !tmp || !out || !scratch || n <= 0) return SPMF_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  square_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(g, tmp, n);
+  SPMF_CHECK_LAUNCH();
+  // view tmp as [rows][32] (tail handled by treating n as rows of 1 channel when not divisible)
+  long long rows = n / 32;
+  int rc;
+  if (rows * 32 == n) {
+    rc = reduce_rows<float>(tmp, scratch + 64 * 32, scratch, rows, 32, 1, st);
+    if (rc) return rc;
+    return reduce_rows<double>(scratch + 64 * 32, out, scratch, 32, 1, 1, st);
+  }
+  return reduce_rows<float>(tmp, out, scratch, n, 1, 1, st);
+}
+
+int spmf_batch_sums(const float* z, const float* rowacc, int nrows, int K, int S, double* zcolsum,
+                    double* datasums, double* scratch, void* stream) {
+  if (!z || !rowacc || !zcolsum || !datasums || !scratch || nrows <= 0 || K <= 0 || K > SPMF_MAX_K || S <= 0)
+    return SPMF_ERR_BAD_ARG;
+  const int KP = spmf_kpad(K), SV = spmf_draw_vec(S), NQ = S / SV;
+  int rc = reduce_rows<float>(z, zcolsum, scratch, nrows, KP * SV, NQ, (cudaStream_t)stream);
+  if (rc) return rc;
+  return reduce_rows<float>(rowacc, datasums, scratch, nrows, 4 * SV, NQ, (cudaStream_t)stream);
+}
+
+int spmf_colsum(const float* in, long long n, int c, int q, double* out, double* scratch, void* stream) {
+  if (!in || !out || !scratch) return SPMF_ERR_BAD_ARG;
+  return reduce_rows<float>(in, out, scratch, n, c, q, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,613 @@
+// Data term of the ADVI step on sparse (CSR + CSC) count batches, sm_100a.
+//
+// Never materialises the (S,B,D) rate matrix of the reference (poisson.py:174-184).  Per nonzero:
+//   row pass    (CSR, row-owned outputs):  z_b = r_b sum_d x A'_d ;  lambda = z_b.EV_d + phi_d ;
+//               x log lambda ;  dz_b = sum_d (x/lambda) EV_d - vsum - z_b
+//   column pass (CSC, column-owned outputs, recomputes lambda):  GEV_d = sum_b (x/lambda) z_b ;
+//               Gphi_d = sum_b x/lambda ;  GA'_d = sum_b x r_b dz_b
+// The -sum(rate) part of the Poisson log-likelihood is closed form and handled
+// by vsum / zcolsum / phisum, O(BK + KD).
+//
+// Thread mapping (variant 0, generic): a group of LPN = min(KP,32) lanes owns one row / one slice
+// of the CSC stream; lane gl holds latent k = gl + LPN*i, each as an SV-wide vector of draws, so a
+// gather of one operand row [KP][SV] is one coalesced KP*SV*4-byte read.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/spmf_b200.h"
+
+namespace spmf {
+
+#define SPMF_CHECK_LAUNCH()                      \
+  do {                                           \
+    cudaError_t e__ = cudaGetLastError();        \
+    if (e__ != cudaSuccess) return (int)e__;     \
+  } while (0)
+
+template <int SV>
+__device__ __forceinline__ void ldv(float (&r)[SV], const float* __restrict__ p) {
+  if constexpr (SV == 4) {
+    float4 t = __ldg(reinterpret_cast<const float4*>(p));
+    r[0] = t.x; r[1] = t.y; r[2] = t.z; r[3] = t.w;
+  } else if constexpr (SV == 2) {
+    float2 t = __ldg(reinterpret_cast<const float2*>(p));
+    r[0] = t.x; r[1] = t.y;
+  } else {
+    r[0] = __ldg(p);
+  }
+}
+template <int SV>
+__device__ __forceinline__ void stv(float* __restrict__ p, const float (&r)[SV]) {
+  if constexpr (SV == 4) {
+    *reinterpret_cast<float4*>(p) = make_float4(r[0], r[1], r[2], r[3]);
+  } else if constexpr (SV == 2) {
+    *reinterpret_cast<float2*>(p) = make_float2(r[0], r[1]);
+  } else {
+    p[0] = r[0];
+  }
+}
+
+template <int LPN>
+__device__ __forceinline__ float group_sum(float v, unsigned mask) {
+#pragma unroll
+  for (int o = LPN / 2; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o);
+  return v;
+}
+
+constexpr int kWarpsPerBlock = 4;
+
+// ------------------------------------------------------------------ row pass
+template <int KP, int SV, bool ENCODE_ONLY>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+csr_rows_kernel(const long long* __restrict__ rowptr, const int* __restrict__ cols,
+                const float* __restrict__ vals, const float* __restrict__ rowsum,
+                const float* __restrict__ lgam, float inv_xi, int scale_rows, int nrows, int D,
+                const float* __restrict__ Ap, const float* __restrict__ EV,
+                const float* __restrict__ PH, const double* __restrict__ vsum,
+                float* __restrict__ z, float* __restrict__ dzr, float* __restrict__ rowacc) {
+  constexpr int LPN = KP < 32 ? KP : 32;
+  constexpr int KPL = KP / LPN;
+  constexpr int GPW = 32 / LPN;
+  const int lane = threadIdx.x & 31;
+  const int gl = lane % LPN;
+  const int grp = (threadIdx.x >> 5) * GPW + lane / LPN;
+  const int row = blockIdx.x * (kWarpsPerBlock * GPW) + grp;
+  const int q = blockIdx.y;
+  const unsigned gmask = (LPN == 32) ? 0xffffffffu : (((1u << LPN) - 1u) << ((lane / LPN) * LPN));
+  if (row >= nrows) return;
+
+  const float* Apq = Ap + (long long)q * D * KP * SV;
+  const long long j0 = rowptr[row], j1 = rowptr[row + 1];
+  const float r = scale_rows ? rowsum[row] * inv_xi : 1.f;   // poisson.py:644-649
+
+  // ---- z = r * sum_d x A'_d          (poisson.py:640-643 with 1/eta folded into A')
+  float zz[KPL][SV];
+#pragma unroll
+  for (int i = 0; i < KPL; ++i)
+#pragma unroll
+    for (int v = 0; v < SV; ++v) zz[i][v] = 0.f;
+  for (long long j = j0; j < j1; ++j) {
+    const int d = __ldg(cols + j);
+    const float x = __ldg(vals + j);
+#pragma unroll
+    for (int i = 0; i < KPL; ++i) {
+      float a[SV];
+      ldv<SV>(a, Apq + ((long long)d * KP + gl + LPN * i) * SV);
+#pragma unroll
+      for (int v = 0; v < SV; ++v) zz[i][v] = fmaf(x, a[v], zz[i][v]);
+    }
+  }
+  float* zq = z + ((long long)q * nrows + row) * KP * SV;
+#pragma unroll
+  for (int i = 0; i < KPL; ++i) {
+#pragma unroll
+    for (int v = 0; v < SV; ++v) zz[i][v] *= r;
+    stv<SV>(zq + (gl + LPN * i) * SV, zz[i]);
+  }
+  if constexpr (ENCODE_ONLY) return;
+
+  // ---- lambda at the nonzeros, x log lambda, dz      (poisson.py:174-184)
+  const float* EVq = EV + (long long)q * D * KP * SV;
+  const float* PHq = PH + (long long)q * D * SV;
+  float dz[KPL][SV];
+  float xlog[SV], bad[SV];
+#pragma unroll
+  for (int v = 0; v < SV; ++v) { xlog[v] = 0.f; bad[v] = 0.f; }
+#pragma unroll
+  for (int i = 0; i < KPL; ++i)
+#pragma unroll
+    for (int v = 0; v < SV; ++v) dz[i][v] = 0.f;
+  for (long long j = j0; j < j1; ++j) {
+    const int d = __ldg(cols + j);
+    const float x = __ldg(vals + j);
+    float e[KPL][SV], p[SV], ph[SV];
+#pragma unroll
+    for (int v = 0; v < SV; ++v) p[v] = 0.f;
+#pragma unroll
+    for (int i = 0; i < KPL; ++i) {
+      ldv<SV>(e[i], EVq + ((long long)d * KP + gl + LPN * i) * SV);
+#pragma unroll
+      for (int v = 0; v < SV; ++v) p[v] = fmaf(zz[i][v], e[i][v], p[v]);
+    }
+    ldv<SV>(ph, PHq + (long long)d * SV);
+#pragma unroll
+    for (int v = 0; v < SV; ++v) {
+      const float lam = group_sum<LPN>(p[v], gmask) + ph[v];   // poisson.py:177
+      const float t = x * __logf(lam);
+      const float gq = __fdividef(x, lam);
+      if (isfinite(t) && isfinite(gq)) {
+        xlog[v] += t;
+#pragma unroll
+        for (int i = 0; i < KPL; ++i) dz[i][v] = fmaf(gq, e[i][v], dz[i][v]);
+      } else {
+        bad[v] += 1.f;   // reported, see rowacc slot 3 (guard of poisson.py:606-616)
+      }
+    }
+  }
+  // ---- closed-form parts and per-row scalars
+  const double* vsq = vsum + (long long)q * KP * SV;
+  float zv[SV], z2[SV];
+#pragma unroll
+  for (int v = 0; v < SV; ++v) { zv[v] = 0.f; z2[v] = 0.f; }
+  float* dq = dzr + ((long long)q * nrows + row) * KP * SV;
+#pragma unroll
+  for (int i = 0; i < KPL; ++i) {
+    float o[SV];
+#pragma unroll
+    for (int v = 0; v < SV; ++v) {
+      const float vs = (float)vsq[(gl + LPN * i) * SV + v];
+      zv[v] = fmaf(zz[i][v], vs, zv[v]);
+      z2[v] = fmaf(zz[i][v], zz[i][v], z2[v]);
+      o[v] = r * (dz[i][v] - vs - zz[i][v]);     // dL/dz includes the HalfNormal(1) z prior (:599-604)
+    }
+    stv<SV>(dq + (gl + LPN * i) * SV, o);
+  }
+#pragma unroll
+  for (int v = 0; v < SV; ++v) {
+    zv[v] = group_sum<LPN>(zv[v], gmask);
+    z2[v] = group_sum<LPN>(z2[v], gmask);
+  }
+  if (gl == 0) {
+    float* ra = rowacc + ((long long)q * nrows + row) * 4 * SV;
+    const float lg = lgam[row];
+#pragma unroll
+    for (int v = 0; v < SV; ++v) {
+      ra[0 * SV + v] = xlog[v] - lg;
+      ra[1 * SV + v] = zv[v];
+      ra[2 * SV + v] = z2[v];
+      ra[3 * SV + v] = bad[v];
+    }
+  }
+}
+
+// ------------------------------------------------------------------ column pass
+constexpr int kSliceLen = 256;
+
+template <int KP, int SV>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+csc_cols_kernel(const int* __restrict__ colptr, const int* __restrict__ rows,
+                const float* __restrict__ vals, int nnz, int nrows, int D,
+                const float* __restrict__ z, const float* __restrict__ dzr,
+                const float* __restrict__ EV, const float* __restrict__ PH,
+                float* __restrict__ GAp, float* __restrict__ GEV, float* __restrict__ Gphi) {
+  constexpr int LPN = KP < 32 ? KP : 32;
+  constexpr int KPL = KP / LPN;
+  constexpr int GPW = 32 / LPN;
+  const int lane = threadIdx.x & 31;
+  const int gl = lane % LPN;
+  const int grp = (threadIdx.x >> 5) * GPW + lane / LPN;
+  const int slice = blockIdx.x * (kWarpsPerBlock * GPW) + grp;
+  const int q = blockIdx.y;
+  const unsigned gmask = (LPN == 32) ? 0xffffffffu : (((1u << LPN) - 1u) << ((lane / LPN) * LPN));
+  const int j0 = slice * kSliceLen;
+  if (j0 >= nnz) return;
+  const int j1 = min(j0 + kSliceLen, nnz);
+
+  const float* zq = z + (long long)q * nrows * KP * SV;
+  const float* dq = dzr + (long long)q * nrows * KP * SV;
+  const float* EVq = EV + (long long)q * D * KP * SV;
+  const float* PHq = PH + (long long)q * D * SV;
+  float* GApq = GAp + (long long)q * D * KP * SV;
+  float* GEVq = GEV + (long long)q * D * KP * SV;
+  float* Gphq = Gphi + (long long)q * D * SV;
+
+  // column containing position j0: largest d with colptr[d] <= j0
+  int lo = 0, hi = D;   // invariant: colptr[lo] <= j0 < colptr[hi]... (colptr[D] = nnz > j0)
+  while (hi - lo > 1) {
+    int mid = (lo + hi) >> 1;
+    if (__ldg(colptr + mid) <= j0) lo = mid; else hi = mid;
+  }
+  int d = lo;
+  int next = __ldg(colptr + d + 1);
+
+  float ev[KPL][SV], ph[SV], aEV[KPL][SV], aAp[KPL][SV], aPh[SV];
+  auto load_col = [&](int dd) {
+#pragma unroll
+    for (int i = 0; i < KPL; ++i) {
+      ldv<SV>(ev[i], EVq + ((long long)dd * KP + gl + LPN * i) * SV);
+#pragma unroll
+      for (int v = 0; v < SV; ++v) { aEV[i][v] = 0.f; aAp[i][v] = 0.f; }
+    }
+    ldv<SV>(ph, PHq + (long long)dd * SV);
+#pragma unroll
+    for (int v = 0; v < SV; ++v) aPh[v] = 0.f;
+  };
+  auto flush_col = [&](int dd) {
+#pragma unroll
+    for (int i = 0; i < KPL; ++i) {
+      const long long o = ((long long)dd * KP + gl + LPN * i) * SV;
+#pragma unroll
+      for (int v = 0; v < SV; ++v) {
+        atomicAdd(GEVq + o + v, aEV[i][v]);
+        atomicAdd(GApq + o + v, aAp[i][v]);
+      }
+    }
+    if (gl == 0) {
+#pragma unroll
+      for (int v = 0; v < SV; ++v) atomicAdd(Gphq + (long long)dd * SV + v, aPh[v]);
+    }
+  };
+  load_col(d);
+  int pending = 0;
+  for (int j = j0; j < j1; ++j) {
+    if (j >= next) {
+      if (pending) flush_col(d);
+      pending = 0;
+      do {
+        ++d;
+        next = __ldg(colptr + d + 1);
+      } while (j >= next);
+      load_col(d);
+    }
+    const int b = __ldg(rows + j);
+    const float x = __ldg(vals + j);
+    float zz[KPL][SV], dd[KPL][SV], p[SV];
+#pragma unroll
+    for (int v = 0; v < SV; ++v) p[v] = 0.f;
+#pragma unroll
+    for (int i = 0; i < KPL; ++i) {
+      ldv<SV>(zz[i], zq + ((long long)b * KP + gl + LPN * i) * SV);
+      ldv<SV>(dd[i], dq + ((long long)b * KP + gl + LPN * i) * SV);
+#pragma unroll
+      for (int v = 0; v < SV; ++v) p[v] = fmaf(zz[i][v], ev[i][v], p[v]);
+    }
+#pragma unroll
+    for (int v = 0; v < SV; ++v) {
+      const float lam = group_sum<LPN>(p[v], gmask) + ph[v];
+      float gq = __fdividef(x, lam);
+      if (!isfinite(gq) || !isfinite(__logf(lam))) gq = 0.f;   // same entries the row pass dropped
+      aPh[v] += gq;
+#pragma unroll
+      for (int i = 0; i < KPL; ++i) {
+        aEV[i][v] = fmaf(gq, zz[i][v], aEV[i][v]);
+        aAp[i][v] = fmaf(x, dd[i][v], aAp[i][v]);
+      }
+    }
+    pending = 1;
+  }
+  if (pending) flush_col(d);
+}
+
+// ------------------------------------------------------------------ data-format kernels
+__global__ void csr_row_consts_kernel(const long long* __restrict__ rowptr,
+                                      const float* __restrict__ vals, long long nrows,
+                                      float* __restrict__ rowsum, float* __restrict__ lgam) {
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= nrows) return;
+  const long long j0 = rowptr[row], j1 = rowptr[row + 1];
+  float s = 0.f, l = 0.f;
+  for (long long j = j0 + lane; j < j1; j += 32) {
+    const float x = __ldg(vals + j);
+    s += x;
+    l += lgammaf(x + 1.f);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    l += __shfl_xor_sync(0xffffffffu, l, o);
+  }
+  if (lane == 0) { rowsum[row] = s; lgam[row] = l; }
+}
+
+__global__ void csr_colstats_kernel(const int* __restrict__ cols, const float* __restrict__ vals,
+                                    long long nnz, double* __restrict__ colsum,
+                                    float* __restrict__ colnnz) {
+  long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; j < nnz; j += stride) {
+    const float x = __ldg(vals + j);
+    const int d = __ldg(cols + j);
+    atomicAdd(colsum + d, (double)x);
+    if (x > 0.f) atomicAdd(colnnz + d, 1.0f);   // fp32 counter as poisson.py:126-130
+  }
+}
+
+__global__ void count_cols_kernel(const long long* __restrict__ rowptr, const int* __restrict__ cols,
+                                  int nrows, int* __restrict__ cnt) {
+  const long long base = rowptr[0], end = rowptr[nrows];
+  long long j = base + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; j < end; j += stride) atomicAdd(cnt + __ldg(cols + j), 1);
+}
+
+// single-block exclusive scan: out[0..n] (n+1 entries), also copies to cursor
+__global__ void exscan_int_kernel(const int* __restrict__ in, int n, int* __restrict__ out,
+                                  int* __restrict__ cursor) {
+  __shared__ int warp_tot[32];
+  __shared__ int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int base = 0; base < n; base += blockDim.x) {
+    const int i = base + threadIdx.x;
+    const int v = i < n ? in[i] : 0;
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) warp_tot[w] = x;
+    __syncthreads();
+    if (w == 0) {
+      int t = lane < (blockDim.x >> 5) ? warp_tot[lane] : 0;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int y = __shfl_up_sync(0xffffffffu, t, o);
+        if (lane >= o) t += y;
+      }
+      warp_tot[lane] = t;   // inclusive over warps
+    }
+    __syncthreads();
+    const int excl = carry + (w ? warp_tot[w - 1] : 0) + x - v;
+    if (i < n) { out[i] = excl; if (cursor) cursor[i] = excl; }
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) carry = excl + v;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { out[n] = carry; if (cursor) cursor[n] = carry; }
+}
+
+__global__ void scatter_csc_kernel(const long long* __restrict__ rowptr, const int* __restrict__ cols,
+                                   const float* __restrict__ vals, int nrows, int* __restrict__ cursor,
+                                   int* __restrict__ rows_out, float* __restrict__ vals_out) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= nrows) return;
+  const long long j0 = rowptr[row], j1 = rowptr[row + 1];
+  for (long long j = j0 + lane; j < j1; j += 32) {
+    const int d = __ldg(cols + j);
+    const int pos = atomicAdd(cursor + d, 1);
+    rows_out[pos] = row;
+    vals_out[pos] = __ldg(vals + j);
+  }
+}
+
+__global__ void dense_count_kernel(const float* __restrict__ x, int nrows, int D,
+                                   long long* __restrict__ cnt) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= nrows) return;
+  int c = 0;
+  for (int d = lane; d < D; d += 32) c += (x[(long long)row * D + d] != 0.f);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if (lane == 0) cnt[row + 1] = c;
+  if (row == 0 && lane == 0) cnt[0] = 0;
+}
+
+// single-block inclusive scan in place over rowptr[1..n] (int64)
+__global__ void incscan_ll_kernel(long long* __restrict__ a, int n) {
+  __shared__ long long warp_tot[32];
+  __shared__ long long carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int base = 0; base < n; base += blockDim.x) {
+    const int i = base + threadIdx.x;
+    long long x = i < n ? a[1 + i] : 0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      long long y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) warp_tot[w] = x;
+    __syncthreads();
+    if (w == 0) {
+      long long t = lane < (blockDim.x >> 5) ? warp_tot[lane] : 0;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        long long y = __shfl_up_sync(0xffffffffu, t, o);
+        if (lane >= o) t += y;
+      }
+      warp_tot[lane] = t;
+    }
+    __syncthreads();
+    const long long incl = carry + (w ? warp_tot[w - 1] : 0) + x;
+    if (i < n) a[1 + i] = incl;
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) carry = incl;
+    __syncthreads();
+  }
+}
+
+__global__ void dense_fill_kernel(const float* __restrict__ x, int nrows, int D,
+                                  const long long* __restrict__ rowptr, int* __restrict__ cols,
+                                  float* __restrict__ vals) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= nrows) return;
+  long long pos = rowptr[row];
+  for (int d0 = 0; d0 < D; d0 += 32) {
+    const int d = d0 + lane;
+    const float v = d < D ? x[(long long)row * D + d] : 0.f;
+    const unsigned m = __ballot_sync(0xffffffffu, v != 0.f);
+    if (v != 0.f) {
+      const long long o = pos + __popc(m & ((1u << lane) - 1u));
+      cols[o] = d;
+      vals[o] = v;
+    }
+    pos += __popc(m);
+  }
+}
+
+// ------------------------------------------------------------------ dispatch
+template <int KP, int SV, bool ENC>
+static int launch_rows(const long long* rowptr, const int* cols, const float* vals,
+                       const float* rowsum, const float* lgam, float inv_xi, int scale_rows, int nrows,
+                       int D, int NQ, const float* Ap, const float* EV, const float* PH,
+                       const double* vsum, float* z, float* dzr, float* rowacc, cudaStream_t st) {
+  constexpr int LPN = KP < 32 ? KP : 32;
+  constexpr int GPW = 32 / LPN;
+  dim3 grid((nrows + kWarpsPerBlock * GPW - 1) / (kWarpsPerBlock * GPW), NQ);
+  csr_rows_kernel<KP, SV, ENC><<<grid, kWarpsPerBlock * 32, 0, st>>>(
+      rowptr, cols, vals, rowsum, lgam, inv_xi, scale_rows, nrows, D, Ap, EV, PH, vsum, z, dzr, rowacc);
+  SPMF_CHECK_LAUNCH();
+  return SPMF_OK;
+}
+
+template <int KP, int SV>
+static int launch_cols(const int* colptr, const int* rows, const float* vals, int nnz, int nrows,
+                       int D, int NQ, const float* z, const float* dzr, const float* EV,
+                       const float* PH, float* GAp, float* GEV, float* Gphi, cudaStream_t st) {
+  constexpr int LPN = KP < 32 ? KP : 32;
+  constexpr int GPW = 32 / LPN;
+  const int nslices = (nnz + kSliceLen - 1) / kSliceLen;
+  if (nslices == 0) return SPMF_OK;
+  dim3 grid((nslices + kWarpsPerBlock * GPW - 1) / (kWarpsPerBlock * GPW), NQ);
+  csc_cols_kernel<KP, SV><<<grid, kWarpsPerBlock * 32, 0, st>>>(colptr, rows, vals, nnz, nrows, D, z,
+                                                               dzr, EV, PH, GAp, GEV, Gphi);
+  SPMF_CHECK_LAUNCH();
+  return SPMF_OK;
+}
+
+#define SPMF_DISPATCH_KP_SV(KP, SV, CALL)                                    \
+  do {                                                                       \
+    switch (KP) {                                                            \
+      case 1: SPMF_DISPATCH_SV(1, SV, CALL); break;                          \
+      case 2: SPMF_DISPATCH_SV(2, SV, CALL); break;                          \
+      case 4: SPMF_DISPATCH_SV(4, SV, CALL); break;                          \
+      case 8: SPMF_DISPATCH_SV(8, SV, CALL); break;                          \
+      case 16: SPMF_DISPATCH_SV(16, SV, CALL); break;                        \
+      case 32: SPMF_DISPATCH_SV(32, SV, CALL); break;                        \
+      case 64: SPMF_DISPATCH_SV(64, SV, CALL); break;                        \
+      case 128: SPMF_DISPATCH_SV(128, SV, CALL); break;                      \
+      default: return SPMF_ERR_UNSUPPORTED;                                  \
+    }                                                                        \
+  } while (0)
+#define SPMF_DISPATCH_SV(KPC, SV, CALL)                                      \
+  do {                                                                       \
+    if (SV == 4) { CALL(KPC, 4); } else if (SV == 2) { CALL(KPC, 2); } else { CALL(KPC, 1); } \
+  } while (0)
+
+}  // namespace spmf
+
+using namespace spmf;
+
+extern "C" {
+
+int spmf_csr_row_consts(const long long* rowptr, const float* vals, long long nrows, float* rowsum,
+                        float* lgam, void* stream) {
+  if (!rowptr || !vals || !rowsum || !lgam || nrows <= 0) return SPMF_ERR_BAD_ARG;
+  csr_row_consts_kernel<<<(unsigned)((nrows + 3) / 4), 128, 0, (cudaStream_t)stream>>>(rowptr, vals, nrows, rowsum, lgam);
+  SPMF_CHECK_LAUNCH();
+  return SPMF_OK;
+}
+
+int spmf_csr_rows(const long long* rowptr, const int* cols, const float* vals, const float* rowsum,
+                  const float* lgam, float inv_xi, int scale_rows, int nrows, int D, int K, int S,
+                  const float* Ap, const float* EV, const float* PH, const double* vsum, float* z,
+                  float* dzr, float* rowacc, int variant, void* stream) {
+  if (!rowptr || !cols || !vals || !rowsum || !lgam || !Ap || !EV || !PH || !vsum || !z || !dzr || !rowacc)
+    return SPMF_ERR_BAD_ARG;
+  if (nrows <= 0 || D <= 0 || K <= 0 || K > SPMF_MAX_K || S <= 0) return SPMF_ERR_BAD_ARG;
+  if (variant != 0) return SPMF_ERR_UNSUPPORTED;
+  const int KP = spmf_kpad(K), SV = spmf_draw_vec(S), NQ = S / SV;
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = SPMF_OK;
+#define CALL_ROWS(KPC, SVC) rc = launch_rows<KPC, SVC, false>(rowptr, cols, vals, rowsum, lgam, inv_xi, scale_rows, nrows, D, NQ, Ap, EV, PH, vsum, z, dzr, rowacc, st)
+  SPMF_DISPATCH_KP_SV(KP, SV, CALL_ROWS);
+#undef CALL_ROWS
+  return rc;
+}
+
+int spmf_csr_encode(const long long* rowptr, const int* cols, const float* vals, const float* rowsum,
+                    float inv_xi, int scale_rows, int nrows, int D, int K, int S, const float* Ap,
+                    float* z, void* stream) {
+  if (!rowptr || !cols || !vals || !rowsum || !Ap || !z) return SPMF_ERR_BAD_ARG;
+  if (nrows <= 0 || D <= 0 || K <= 0 || K > SPMF_MAX_K || S <= 0) return SPMF_ERR_BAD_ARG;
+  const int KP = spmf_kpad(K), SV = spmf_draw_vec(S), NQ = S / SV;
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = SPMF_OK;
+#define CALL_ENC(KPC, SVC) rc = launch_rows<KPC, SVC, true>(rowptr, cols, vals, rowsum, nullptr, inv_xi, scale_rows, nrows, D, NQ, Ap, nullptr, nullptr, nullptr, z, nullptr, nullptr, st)
+  SPMF_DISPATCH_KP_SV(KP, SV, CALL_ENC);
+#undef CALL_ENC
+  return rc;
+}
+
+int spmf_csc_cols(const int* colptr, const int* rows, const float* vals, int nnz, int nrows, int D,
+                  int K, int S, const float* z, const float* dzr, const float* EV, const float* PH,
+                  float* GAp, float* GEVnz, float* Gphinz, int variant, void* stream) {
+  if (!colptr || !rows || !vals || !z || !dzr || !EV || !PH || !GAp || !GEVnz || !Gphinz) return SPMF_ERR_BAD_ARG;
+  if (nnz < 0 || nrows <= 0 || D <= 0 || K <= 0 || K > SPMF_MAX_K || S <= 0) return SPMF_ERR_BAD_ARG;
+  if (variant != 0) return SPMF_ERR_UNSUPPORTED;
+  const int KP = spmf_kpad(K), SV = spmf_draw_vec(S), NQ = S / SV;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t nb = (size_t)NQ * D * KP * SV * sizeof(float);
+  cudaError_t e = cudaMemsetAsync(GAp, 0, nb, st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(GEVnz, 0, nb, st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(Gphinz, 0, (size_t)NQ * D * SV * sizeof(float), st);
+  if (e != cudaSuccess) return (int)e;
+  int rc = SPMF_OK;
+#define CALL_COLS(KPC, SVC) rc = launch_cols<KPC, SVC>(colptr, rows, vals, nnz, nrows, D, NQ, z, dzr, EV, PH, GAp, GEVnz, Gphinz, st)
+  SPMF_DISPATCH_KP_SV(KP, SV, CALL_COLS);
+#undef CALL_COLS
+  return rc;
+}
+
+int spmf_csr_colstats(const int* cols, const float* vals, long long nnz, int D, double* colsum,
+                      float* colnnz, void* stream) {
+  if (!cols || !vals || !colsum || !colnnz || nnz < 0 || D <= 0) return SPMF_ERR_BAD_ARG;
+  if (nnz == 0) return SPMF_OK;
+  long long blocks = (nnz + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  csr_colstats_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(cols, vals, nnz, colsum, colnnz);
+  SPMF_CHECK_LAUNCH();
+  return SPMF_OK;
+}
+
+int spmf_csr_to_csc(const long long* rowptr, const int* cols, const float* vals, int nrows, int D,
+                    int* colptr, int* rows_out, float* vals_out, int* cursor, void* stream) {
+  if (!rowptr || !cols || !vals || !colptr || !rows_out || !vals_out || !cursor) return SPMF_ERR_BAD_ARG;
+  if (nrows <= 0 || D <= 0) return SPMF_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(cursor, 0, (size_t)(D + 1) * sizeof(int), st);
+  if (e != cudaSuccess) return (int)e;
+  count_cols_kernel<<<148 * 8, 256, 0, st>>>(rowptr, cols, nrows, cursor);
+  exscan_int_kernel<<<1, 1024, 0, st>>>(cursor, D, colptr, cursor);
+  scatter_csc_kernel<<<(nrows + 3) / 4, 128, 0, st>>>(rowptr, cols, vals, nrows, cursor, rows_out, vals_out);
+  SPMF_CHECK_LAUNCH();
+  return SPMF_OK;
+}
+
+int spmf_dense_count(const float* x, int nrows, int D, long long* rowptr, void* stream) {
+  if (!x || !rowptr || nrows <= 0 || D <= 0) return SPMF_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  dense_count_kernel<<<(nrows + 3) / 4, 128, 0, st>>>(x, nrows, D, rowptr);
+  incscan_ll_kernel<<<1, 1024, 0, st>>>(rowptr, nrows);
+  SPMF_CHECK_LAUNCH();
+  return SPMF_OK;
+}
+
+int spmf_dense_fill(const float* x, int nrows, int D, const long long* rowptr, int* cols, float* vals,
+                    void* stream) {
+  if (!x || !rowptr || !cols || !vals || nrows <= 0 || D <= 0) return SPMF_ERR_BAD_ARG;
+  dense_fill_kernel<<<(nrows + 3) / 4, 128, 0, (cudaStream_t)stream>>>(x, nrows, D, rowptr, cols, vals);
+  SPMF_CHECK_LAUNCH();
+  return SPMF_OK;
+}
+
+const char* spmf_version(void) { return "spmf_b200 0.1 (sm_100a)"; }
+
+}  // extern "C"

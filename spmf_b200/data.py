@@ -1,0 +1,215 @@
+"""Count-matrix containers on the device: CSR shard, per-batch CSC copy, row constants.
+
+The reference streams dense `(B,D)` minibatches through tf.data as dicts keyed by `count_key`
+(tests/spmf_test.py:17-27, bin/factorize_csv.py:75-112).  Here the dataset (or this rank's row
+shard of it) is resident in HBM as CSR: int64 row pointers, int32 column indices, fp32 counts --
+8 B per nonzero -- and every minibatch is a contiguous row range whose CSC copy (for the
+column-owned gradients) is built once on the device and cached.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from . import _abi
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+@dataclass
+class DeviceBatch:
+    """One minibatch on the device.  `rowptr` has nrows+1 entries indexing `cols`/`vals`."""
+    rowptr: torch.Tensor          # int64 [nrows+1] (absolute offsets into cols / vals)
+    cols: torch.Tensor            # int32 [>= rowptr[-1]]
+    vals: torch.Tensor            # fp32
+    rowsum: torch.Tensor          # fp32 [nrows]
+    lgam: torch.Tensor            # fp32 [nrows]  sum_d lgamma(x+1)
+    nrows: int
+    nnz: int
+    D: int
+    colptr: Optional[torch.Tensor] = None   # int32 [D+1]
+    crows: Optional[torch.Tensor] = None    # int32 [nnz] batch-local rows
+    cvals: Optional[torch.Tensor] = None    # fp32 [nnz]
+
+    def ensure_csc(self):
+        if self.colptr is None:
+            dev = self.vals.device
+            self.colptr = torch.empty(self.D + 1, dtype=torch.int32, device=dev)
+            self.crows = torch.empty(max(self.nnz, 1), dtype=torch.int32, device=dev)
+            self.cvals = torch.empty(max(self.nnz, 1), dtype=torch.float32, device=dev)
+            cursor = torch.empty(self.D + 1, dtype=torch.int32, device=dev)
+            _abi.call("spmf_csr_to_csc", _ptr(self.rowptr), _ptr(self.cols), _ptr(self.vals),
+                      self.nrows, self.D, _ptr(self.colptr), _ptr(self.crows), _ptr(self.cvals),
+                      _ptr(cursor), _stream())
+        return self
+
+
+class CsrShard:
+    """This rank's rows of the count matrix, resident on the device."""
+
+    def __init__(self, rowptr, cols, vals, D, device=None):
+        device = torch.device(device) if device is not None else torch.device("cuda")
+        self.rowptr = torch.as_tensor(rowptr).to(device=device, dtype=torch.int64).contiguous()
+        self.cols = torch.as_tensor(cols).to(device=device, dtype=torch.int32).contiguous()
+        self.vals = torch.as_tensor(vals).to(device=device, dtype=torch.float32).contiguous()
+        self.D = int(D)
+        self.nrows = self.rowptr.numel() - 1
+        self.nnz = int(self.vals.numel())
+        self.rowsum = torch.empty(self.nrows, dtype=torch.float32, device=device)
+        self.lgam = torch.empty(self.nrows, dtype=torch.float32, device=device)
+        if self.nrows > 0:
+            _abi.call("spmf_csr_row_consts", _ptr(self.rowptr), _ptr(self.vals), self.nrows,
+                      _ptr(self.rowsum), _ptr(self.lgam), _stream())
+        self._rowptr_host = None
+        self._batches: Dict[tuple, DeviceBatch] = {}
+
+    # ---- constructors -------------------------------------------------
+    @classmethod
+    def from_dense(cls, x, device=None):
+        """Dense (N,D) counts (torch / numpy, host or device) -> CSR on the device, compacted by a kernel."""
+        device = torch.device(device) if device is not None else torch.device("cuda")
+        xd = torch.as_tensor(x).to(device=device, dtype=torch.float32).contiguous()
+        n, D = xd.shape
+        rowptr = torch.empty(n + 1, dtype=torch.int64, device=device)
+        _abi.call("spmf_dense_count", _ptr(xd), n, D, _ptr(rowptr), _stream())
+        nnz = int(rowptr[-1].item())
+        cols = torch.empty(max(nnz, 1), dtype=torch.int32, device=device)
+        vals = torch.empty(max(nnz, 1), dtype=torch.float32, device=device)
+        _abi.call("spmf_dense_fill", _ptr(xd), n, D, _ptr(rowptr), _ptr(cols), _ptr(vals), _stream())
+        return cls(rowptr, cols[:nnz] if nnz else cols[:0], vals[:nnz] if nnz else vals[:0], D, device)
+
+    @classmethod
+    def from_scipy(cls, m, device=None):
+        m = m.tocsr()
+        return cls(torch.from_numpy(m.indptr.astype(np.int64)), torch.from_numpy(m.indices.astype(np.int32)),
+                   torch.from_numpy(m.data.astype(np.float32)), m.shape[1], device)
+
+    # ---- batches --------------------------------------------------------
+    def rowptr_host(self):
+        if self._rowptr_host is None:
+            self._rowptr_host = self.rowptr.cpu()
+        return self._rowptr_host
+
+    def batch(self, row0, nrows, cache=True) -> DeviceBatch:
+        key = (int(row0), int(nrows))
+        if cache and key in self._batches:
+            return self._batches[key]
+        rp = self.rowptr_host()
+        nnz = int(rp[row0 + nrows] - rp[row0])
+        b = DeviceBatch(rowptr=self.rowptr[row0:row0 + nrows + 1], cols=self.cols, vals=self.vals,
+                        rowsum=self.rowsum[row0:row0 + nrows], lgam=self.lgam[row0:row0 + nrows],
+                        nrows=int(nrows), nnz=nnz, D=self.D)
+        if cache:
+            self._batches[key] = b
+        return b
+
+    def num_batches(self, batch_rows, drop_remainder=False):
+        if drop_remainder:
+            return self.nrows // batch_rows
+        return (self.nrows + batch_rows - 1) // batch_rows
+
+    def iter_batches(self, batch_rows, order=None, drop_remainder=False):
+        nb = self.num_batches(batch_rows, drop_remainder)
+        order = range(nb) if order is None else order
+        for i in order:
+            r0 = i * batch_rows
+            yield self.batch(r0, min(batch_rows, self.nrows - r0))
+
+    def column_stats(self):
+        """colsum (float64 [D]) and col_nnz (float32 [D]) of this shard -- compute_scales, poisson.py:118-134."""
+        dev = self.vals.device
+        colsum = torch.zeros(self.D, dtype=torch.float64, device=dev)
+        colnnz = torch.zeros(self.D, dtype=torch.float32, device=dev)
+        _abi.call("spmf_csr_colstats", _ptr(self.cols), _ptr(self.vals), self.nnz, self.D,
+                  _ptr(colsum), _ptr(colnnz), _stream())
+        return colsum, colnnz
+
+
+def as_device_batch(counts, device, D=None) -> DeviceBatch:
+    """Accept what a reference-style data factory may yield under `count_key`: a DeviceBatch, a
+    dense torch/numpy array, or a scipy.sparse matrix."""
+    if isinstance(counts, DeviceBatch):
+        return counts
+    if isinstance(counts, CsrShard):
+        return counts.batch(0, counts.nrows)
+    if hasattr(counts, "tocsr"):
+        sh = CsrShard.from_scipy(counts, device)
+    else:
+        sh = CsrShard.from_dense(counts, device)
+    return sh.batch(0, sh.nrows, cache=False)
+
+
+# ---------------------------------------------------------------------------
+# Synthetic generators.  Generated on the host with numpy for small parity
+# cases and on the device for the bench shapes.
+# ---------------------------------------------------------------------------
+def synth_noise_dense(N, D, rate=1.0, seed=0):
+    """notebooks/factorizing_random_noise.ipynb:51-62 generator: iid Poisson(rate)."""
+    rng = np.random.default_rng(seed)
+    return rng.poisson(rate, size=(N, D)).astype(np.float32)
+
+
+def synth_linear_dense(N, D, k_true=3, seed=0):
+    """notebooks/factorize_linear_structure.ipynb:53-67 generator: every 3rd column is
+    Poisson(Z.V) with V=|N(1.5,0.5)|, Z=|N(0,1)|, the rest Poisson(1) noise."""
+    rng = np.random.default_rng(seed)
+    n_sig = len(range(0, D, 3))
+    V = np.abs(rng.normal(1.5, 0.5, size=(k_true, n_sig)))
+    Z = np.abs(rng.normal(0.0, 1.0, size=(N, k_true)))
+    X = rng.poisson(1.0, size=(N, D)).astype(np.float32)
+    X[:, ::3] = rng.poisson(Z @ V).astype(np.float32)
+    return X
+
+
+def synth_scrna_csr_device(nrows, D, density=0.05, seed=0, device="cuda", sigma_gene=1.5, sigma_cell=0.5):
+    """scRNA-seq shaped sparse counts on the device: x_bd ~ Poisson(c_b g_d),
+    c_b ~ LogNormal(0, sigma_cell^2), g_d ~ LogNormal(m, sigma_gene^2) with m solved so the mean
+    P(x>0) equals `density`.  Returns a CsrShard.  Rows are generated in chunks to bound memory."""
+    dev = torch.device(device)
+    gen = torch.Generator(device=dev).manual_seed(int(seed))
+    g = torch.exp(sigma_gene * torch.randn(D, generator=gen, device=dev, dtype=torch.float64))
+    c = torch.exp(sigma_cell * torch.randn(nrows, generator=gen, device=dev, dtype=torch.float64))
+    # solve m: mean_{b,d} (1 - exp(-c_b g_d e^m)) = density on a subsample (bisection)
+    cs = c[: min(nrows, 2048)]
+    lo, hi = -30.0, 10.0
+    for _ in range(60):
+        mid = 0.5 * (lo + hi)
+        dens = (1.0 - torch.exp(-cs[:, None] * g[None, :] * np.exp(mid))).mean().item()
+        lo, hi = (mid, hi) if dens < density else (lo, mid)
+    g = g * np.exp(0.5 * (lo + hi))
+    rowptrs, cols_l, vals_l = [torch.zeros(1, dtype=torch.int64, device=dev)], [], []
+    base = 0
+    chunk = max(1, min(nrows, (1 << 27) // max(D, 1)))
+    for r0 in range(0, nrows, chunk):
+        r1 = min(nrows, r0 + chunk)
+        lam = (c[r0:r1, None] * g[None, :]).to(torch.float32)
+        x = torch.poisson(lam, generator=gen)
+        # every column keeps at least one nonzero (the reference's compute_scales divides by the
+        # per-column nonzero count, poisson.py:136-138: an all-zero column turns xi into NaN) ...
+        ds = torch.arange(D, device=dev)
+        rs = ds % nrows
+        m = (rs >= r0) & (rs < r1)
+        x[rs[m] - r0, ds[m]] = torch.clamp(x[rs[m] - r0, ds[m]], min=1.0)
+        # ... and every row at least one, so that row scaling is defined
+        empty = x.sum(1) == 0
+        if bool(empty.any()):
+            x[empty, int(torch.argmax(g))] = 1.0
+        nzmask = x != 0
+        counts = nzmask.sum(1)
+        rp = torch.cumsum(counts, 0) + base
+        idx = nzmask.nonzero(as_tuple=False)
+        cols_l.append(idx[:, 1].to(torch.int32))
+        vals_l.append(x[nzmask])
+        rowptrs.append(rp)
+        base = int(rp[-1].item())
+        del lam, x, nzmask, idx
+    return CsrShard(torch.cat(rowptrs), torch.cat(cols_l), torch.cat(vals_l), D, dev)

@@ -1,0 +1,182 @@
+"""Launch sequence of one ADVI step on one GPU: owns the device workspace and calls the C ABI.
+
+Replaces, for `PoissonFactorization`, what bayesianquilts' `minibatch_fit_surrogate_posterior`
+does per batch in the reference stack [EXT L3/L4] (call site tests/spmf_test.py:35-43):
+draw S reparameterised samples, evaluate `log q - unormalized_log_prob` (poisson.py:575-621) and
+back-propagate to the 24 variational tensors -- as six fused CUDA launches instead of a
+TensorFlow graph, never materialising the (S,B,D) rate tensor of poisson.py:174-184.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import _abi
+from .data import DeviceBatch, _ptr, _stream
+from .variables import VariableLayout, PART_NAMES
+
+
+class StepWorkspace:
+    """All per-step device buffers for fixed (D, K, S) and a maximum batch size."""
+
+    def __init__(self, D, K, S, max_rows, device):
+        self.D, self.K, self.S = D, K, S
+        self.KP, self.SV = _abi.kpad(K), _abi.draw_vec(S)
+        self.NQ = S // self.SV
+        self.max_rows = 0
+        self.device = device
+        f32, f64 = torch.float32, torch.float64
+        C = self.KP * self.SV
+        n_op = self.NQ * D * C
+        self.Ap = torch.empty(n_op, dtype=f32, device=device)
+        self.EV = torch.empty(n_op, dtype=f32, device=device)
+        self.PH = torch.empty(self.NQ * D * self.SV, dtype=f32, device=device)
+        self.GAp = torch.empty(n_op, dtype=f32, device=device)
+        self.GEV = torch.empty(n_op, dtype=f32, device=device)
+        self.Gph = torch.empty(self.NQ * D * self.SV, dtype=f32, device=device)
+        self.vsum = torch.empty(self.NQ * C, dtype=f64, device=device)
+        self.phisum = torch.empty(self.NQ * self.SV, dtype=f64, device=device)
+        self.zcolsum = torch.empty(self.NQ * C, dtype=f64, device=device)
+        self.datasums = torch.empty(self.NQ * 4 * self.SV, dtype=f64, device=device)
+        nf, nd = _abi.backward_scratch(D, K, S)
+        self.scr_f = torch.empty(nf, dtype=f32, device=device)
+        self.scr_d = torch.empty(nd, dtype=f64, device=device)
+        self.parts = torch.zeros(S * _abi.NUM_PARTS, dtype=f64, device=device)
+        self.ensure_rows(max_rows)
+
+    def ensure_rows(self, nrows):
+        if nrows <= self.max_rows:
+            return
+        C = self.KP * self.SV
+        self.max_rows = int(nrows)
+        self.z = torch.empty(self.NQ * nrows * C, dtype=torch.float32, device=self.device)
+        self.dzr = torch.empty(self.NQ * nrows * C, dtype=torch.float32, device=self.device)
+        self.rowacc = torch.empty(self.NQ * nrows * 4 * self.SV, dtype=torch.float32, device=self.device)
+
+
+class AdviEngine:
+    """ELBO + gradient of one minibatch; optimiser state; everything stays on the device."""
+
+    def __init__(self, D, K, S, device, u_tau_scale, s_tau_scale, decay, scale_rows=True,
+                 entropy_weight=1.0, prior_weight=1.0, world_size=1, seed=0, max_rows=0):
+        if K > _abi.MAX_K:
+            raise _abi.SpmfError(f"latent_dim {K} > {_abi.MAX_K} is not supported by the CUDA path")
+        self.D, self.K, self.S = int(D), int(K), int(S)
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _abi.SpmfError("spmf_b200 computes on CUDA devices only (no CPU fallback)")
+        self.layout = VariableLayout(D, K, S)
+        self.u_tau_scale, self.s_tau_scale, self.decay = float(u_tau_scale), float(s_tau_scale), float(decay)
+        self.scale_rows = bool(scale_rows)
+        self.entropy_weight, self.prior_weight = float(entropy_weight), float(prior_weight)
+        self.world_size = int(world_size)
+        self.seed = int(seed)
+        L = self.layout
+        self.params = torch.zeros(L.n_params, dtype=torch.float32, device=self.device)
+        L.fill_initial(self.params, self.u_tau_scale, self.s_tau_scale)
+        self.grads = torch.zeros_like(self.params)
+        self.adam_m = torch.zeros_like(self.params)
+        self.adam_v = torch.zeros_like(self.params)
+        self.noise = torch.empty(L.n_noise, dtype=torch.float32, device=self.device)
+        self.eta = torch.ones(D, dtype=torch.float32, device=self.device)
+        self.inv_xi = 1.0
+        self._ws = None
+        self._max_rows = max_rows
+        self.opt_step = 0
+        self.rng_step = 0
+        self.launches = 0     # CUDA kernel launches issued through the ABI (bench's gpu_launches)
+
+    @property
+    def ws(self) -> StepWorkspace:
+        if self._ws is None:     # lazily: sampling-only uses (surrogate.sample) never need it
+            self._ws = StepWorkspace(self.D, self.K, self.S, self._max_rows, self.device)
+        return self._ws
+
+    # ------------------------------------------------------------------ pieces
+    def fill_noise(self, step=None):
+        step = self.rng_step if step is None else step
+        _abi.call("spmf_fill_noise", _ptr(self.noise), _ptr(self.params), self.D, self.K, self.S,
+                  self.seed, step, _stream())
+        self.rng_step = step + 1
+        self.launches += 12
+
+    def draw_operands(self):
+        w = self.ws
+        _abi.call("spmf_draw_operands", _ptr(self.params), _ptr(self.noise), _ptr(self.eta), self.D,
+                  self.K, self.S, _ptr(w.Ap), _ptr(w.EV), _ptr(w.PH), _ptr(w.vsum), _ptr(w.phisum),
+                  _ptr(w.scr_d), _stream())
+        self.launches += 5
+
+    def data_term(self, b: DeviceBatch, variant=0):
+        w = self.ws
+        w.ensure_rows(b.nrows)
+        b.ensure_csc()
+        st = _stream()
+        _abi.call("spmf_csr_rows", _ptr(b.rowptr), _ptr(b.cols), _ptr(b.vals), _ptr(b.rowsum),
+                  _ptr(b.lgam), self.inv_xi, int(self.scale_rows), b.nrows, self.D, self.K, self.S,
+                  _ptr(w.Ap), _ptr(w.EV), _ptr(w.PH), _ptr(w.vsum), _ptr(w.z), _ptr(w.dzr),
+                  _ptr(w.rowacc), variant, st)
+        _abi.call("spmf_batch_sums", _ptr(w.z), _ptr(w.rowacc), b.nrows, self.K, self.S,
+                  _ptr(w.zcolsum), _ptr(w.datasums), _ptr(w.scr_d), st)
+        _abi.call("spmf_csc_cols", _ptr(b.colptr), _ptr(b.crows), _ptr(b.cvals), b.nnz, b.nrows,
+                  self.D, self.K, self.S, _ptr(w.z), _ptr(w.dzr), _ptr(w.EV), _ptr(w.PH), _ptr(w.GAp),
+                  _ptr(w.GEV), _ptr(w.Gph), variant, st)
+        self.launches += 1 + 4 + 1
+
+    def backward_params(self, batch_rows):
+        w = self.ws
+        _abi.call("spmf_backward_params", _ptr(self.params), _ptr(self.noise), _ptr(self.eta), self.D,
+                  self.K, self.S, _ptr(w.GAp), _ptr(w.GEV), _ptr(w.Gph), _ptr(w.zcolsum),
+                  _ptr(w.datasums), _ptr(w.phisum), float(batch_rows), self.u_tau_scale,
+                  self.s_tau_scale, self.decay, self.entropy_weight, self.prior_weight,
+                  self.world_size, _ptr(self.grads), _ptr(w.parts), _ptr(w.scr_f), _ptr(w.scr_d),
+                  _stream())
+        self.launches += 8
+
+    # ------------------------------------------------------------------ one step
+    def loss_and_grad(self, batch: DeviceBatch, fresh_noise=True, variant=0):
+        """Fills self.grads and self.ws.parts for `batch`; returns the (S,16) parts tensor (device,
+        float64): 12 prior terms in var_list order, logq, z, x, per-draw loss."""
+        if fresh_noise:
+            self.fill_noise()
+        self.draw_operands()
+        self.data_term(batch, variant)
+        self.backward_params(batch.nrows)
+        return self.ws.parts.view(self.S, _abi.NUM_PARTS)
+
+    def loss_value(self, parts=None):
+        """mean_s [ w_e log q - w_p prior - z - x ]  as a 0-d device tensor."""
+        parts = self.ws.parts.view(self.S, _abi.NUM_PARTS) if parts is None else parts
+        return parts[:, 15].mean()
+
+    def adam_step(self, lr, beta1=0.9, beta2=0.999, eps=1e-7, clip_value=0.0, grad_scale=1.0):
+        self.opt_step += 1
+        _abi.call("spmf_adam_step", _ptr(self.params), _ptr(self.grads), _ptr(self.adam_m),
+                  _ptr(self.adam_v), self.layout.n_params, float(lr), beta1, beta2, eps,
+                  self.opt_step, float(clip_value), float(grad_scale), _stream())
+        self.launches += 1
+
+    def clear_comm_slack(self):
+        L = self.layout
+        self.grads[L.comm_off: L.comm_off + L.comm_slack].zero_()
+
+    # ------------------------------------------------------------------ helpers
+    def set_noise_from(self, noise_dict):
+        """Parity hook: load host-provided base noise {var: (S,*shape)} instead of Philox draws."""
+        for name, t in noise_dict.items():
+            self.layout.noise_view(self.noise, name).copy_(
+                torch.as_tensor(t).to(device=self.device, dtype=torch.float32))
+
+    def noise_dict(self):
+        return {name: self.layout.noise_view(self.noise, name).clone() for name in self.layout.shapes}
+
+    def parts_dict(self):
+        p = self.ws.parts.view(self.S, _abi.NUM_PARTS).cpu()
+        return {n: p[:, i] for i, n in enumerate(PART_NAMES)}
+
+    def samples(self):
+        out = torch.empty_like(self.noise)
+        _abi.call("spmf_sample", _ptr(self.params), _ptr(self.noise), self.D, self.K, self.S,
+                  _ptr(out), _stream())
+        return {name: self.layout.noise_view(out, name) for name in self.layout.shapes}

@@ -1,0 +1,50 @@
+"""Row-sharded data parallelism: one process per GPU, one all-reduce per step.
+
+The reference only carries a `strategy` hook (tf.distribute, poisson.py:60,72,82-83) that every
+driver leaves at None; this is the net-new multi-GPU path.  Every rank holds the
+same variational parameters and draws the same Philox noise, evaluates the data term on its own
+rows, and adds its 1/world share of the prior + entropy gradient of the data-touched tensors
+(v, w, u, s).  ONE `all_reduce(sum)` over the contiguous block
+    [ grads of v,w,u,s (loc|scale_raw) | per-draw 'z','x' parts as (hi,lo) float pairs ]
+then yields the exact full-batch gradient and loss on every rank.  The other 16 tensors only see
+prior/entropy terms, are computed redundantly (deterministic kernels => bit-identical replicas)
+and are not communicated.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from . import _abi
+
+
+def shard_rows(n_rows, rank, world):
+    """Contiguous row block [lo, hi) of this rank (SURVEY.md 8e partition)."""
+    base, rem = divmod(n_rows, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def comm_block(eng):
+    """The all-reduced view: data-touched gradients followed by the scalar slack."""
+    return eng.grads[: eng.layout.n_data_block]
+
+
+def unpack_data_parts(eng, parts):
+    """Write the all-reduced ('z','x') sums back into parts[:,13:15] and recompute the per-draw loss."""
+    L = eng.layout
+    S = eng.S
+    sl = eng.grads[L.comm_off: L.comm_off + 4 * S].to(torch.float64).view(S, 4)
+    parts[:, 13] = sl[:, 0] + sl[:, 1]
+    parts[:, 14] = sl[:, 2] + sl[:, 3]
+    prior = parts[:, :12].sum(1)
+    parts[:, 15] = eng.entropy_weight * parts[:, 12] - eng.prior_weight * prior - parts[:, 13] - parts[:, 14]
+    eng.grads[L.comm_off: L.comm_off + L.comm_slack].zero_()
+    return parts
+
+
+def allreduce_step(eng, parts, group=None):
+    """All-reduce gradients + data parts in one collective; returns the global loss (0-d tensor)."""
+    dist.all_reduce(comm_block(eng), op=dist.ReduceOp.SUM, group=group)
+    unpack_data_parts(eng, parts)
+    return parts[:, 15].mean()

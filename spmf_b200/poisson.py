@@ -1,0 +1,470 @@
+"""`PoissonFactorization` -- host-side mirror of the reference's model surface.
+
+Same names, argument meaning and dict keys as mederrata_spmf/poisson.py::PoissonFactorization
+(class at poisson.py:25-717; constructor :56-64), backed by the sm_100a kernels behind the C ABI
+(include/spmf_b200.h) instead of a TensorFlow-Probability graph.  The training loop the reference
+inherits from bayesianquilts (`fit`, call site tests/spmf_test.py:35-43; legacy `calibrate_advi`,
+bin/factorize_csv.py:121-124) is re-created here as thin host code around `AdviEngine`.
+
+Differences that are deliberate:
+  * arithmetic is fp32 on the GPU (the reference defaults to float64 on the CPU); parity with the
+    float64 oracle is checked at 1e-4 relative;
+  * batches may be dense arrays (compacted to CSR by a kernel), scipy.sparse matrices, or
+    device-resident `DeviceBatch`es cut from a `CsrShard`;
+  * `log_transform=True`, `horshoe_plus=False` and custom encoder/decoder callables have no CUDA
+    path yet and raise (no silent fallback).
+"""
+from __future__ import annotations
+
+import math
+import pickle
+from typing import Callable, Dict, Iterable, Optional
+
+import numpy as np
+import torch
+
+from . import _abi
+from .data import CsrShard, DeviceBatch, as_device_batch, _ptr, _stream
+from .engine import AdviEngine
+from .variables import VAR_LIST, NORMAL_VARS, var_shapes
+
+
+class _SurrogateDistribution:
+    """Stand-in for `self.surrogate_distribution` (a tfd.JointDistributionNamed in the reference,
+    poisson.py:567-569): `.sample(n)` returns a dict of reference-shaped draws."""
+
+    def __init__(self, model):
+        self._m = model
+
+    def sample(self, n=None, seed=None):
+        m = self._m
+        S = 1 if n is None else int(n)
+        eng = m._engine_for(S)
+        eng.fill_noise(step=(seed if seed is not None else eng.rng_step))
+        out = {k: v.clone() for k, v in eng.samples().items()}
+        if n is None:
+            out = {k: v[0] for k, v in out.items()}
+        return out
+
+    @property
+    def trainable_variables(self):
+        return self._m.surrogate_vars
+
+    @property
+    def variables(self):
+        return self._m.surrogate_vars
+
+
+class PoissonFactorization:
+    """Sparse (horseshoe) Poisson matrix factorisation, ADVI on B200."""
+
+    bijectors = None
+    var_list = []
+    s_tau_scale = 1
+
+    def __init__(self, latent_dim=None, feature_dim=None, u_tau_scale=0.01, s_tau_scale=1.,
+                 symmetry_breaking_decay=0.99, strategy=None, encoder_function=None,
+                 decoder_function=None, scale_columns=True, scale_rows=True, log_transform=False,
+                 horshoe_plus=True, column_norms=None, count_key='counts',
+                 initialize_distributions=True, dtype=torch.float32, device=None,
+                 entropy_weight=1.0, prior_weight=1.0, seed=0, process_group=None, **kwargs):
+        if encoder_function is not None or decoder_function is not None:
+            raise _abi.SpmfError("custom encoder/decoder callables have no CUDA path")
+        if log_transform:
+            raise _abi.SpmfError("log_transform=True has no CUDA path yet (needs the dense rate)")
+        if not horshoe_plus:
+            raise _abi.SpmfError("horshoe_plus=False (AbsHorseshoe priors) has no CUDA path yet")
+        if feature_dim is None:
+            raise ValueError("feature_dim is required")
+        self.scale_rows = scale_rows                      # poisson.py:85-92
+        self.scale_columns = scale_columns
+        self.horseshoe_plus = horshoe_plus
+        self.count_key = count_key
+        self.dtype = dtype
+        self.symmetry_breaking_decay = symmetry_breaking_decay
+        self.log_transform = log_transform
+        self.feature_dim = int(feature_dim)
+        self.latent_dim = self.feature_dim if latent_dim is None else int(latent_dim)
+        self.u_tau_scale = float(u_tau_scale)
+        self.s_tau_scale = float(s_tau_scale)
+        self.strategy = strategy
+        self.process_group = process_group
+        self.entropy_weight, self.prior_weight = float(entropy_weight), float(prior_weight)
+        self.seed = int(seed)
+        self.device = torch.device(device) if device is not None else torch.device("cuda")
+        self.eta_i = torch.ones(1, self.feature_dim, dtype=torch.float64)
+        self.xi_u_global = 1.
+        if column_norms is not None:
+            self.eta_i = torch.as_tensor(column_norms, dtype=torch.float64).reshape(1, -1).cpu()
+        self.calibrated_expectations = {}
+        self._engines: Dict[int, AdviEngine] = {}
+        self._params = None
+        if initialize_distributions:
+            self.create_distributions()
+        print(f"Feature dim: {self.feature_dim} -> Latent dim {self.latent_dim}")   # poisson.py:110-111
+
+    # ------------------------------------------------------------------ distributions
+    def create_distributions(self):
+        """poisson.py:212-573: (re)initialise the 24 variational tensors; priors are implicit in
+        the kernels (spmf_model.cuh)."""
+        self.bijectors = {k: 'softplus' for k in VAR_LIST}          # all Softplus, poisson.py:215-224,297-301
+        self.var_list = list(VAR_LIST)                               # poisson.py:572
+        self._engines = {}
+        self._params = None
+        eng = self._engine_for(1)
+        self._params = eng.params
+        self.surrogate_distribution = _SurrogateDistribution(self)
+        self.prior_distribution = None
+        self.set_calibration_expectations()
+
+    def _engine_for(self, S) -> AdviEngine:
+        S = int(S)
+        if S not in self._engines:
+            world = 1
+            if self.process_group is not None or (torch.distributed.is_available()
+                                                  and torch.distributed.is_initialized()):
+                world = torch.distributed.get_world_size(self.process_group)
+            eng = AdviEngine(self.feature_dim, self.latent_dim, S, self.device, self.u_tau_scale,
+                             self.s_tau_scale, self.symmetry_breaking_decay, self.scale_rows,
+                             self.entropy_weight, self.prior_weight, world, self.seed)
+            if self._params is not None:                # engines share parameters / optimiser state
+                first = next(iter(self._engines.values()))
+                eng.params, eng.grads = first.params, first.grads
+                eng.adam_m, eng.adam_v = first.adam_m, first.adam_v
+            self._engines[S] = eng
+            self._push_scales(eng)
+        return self._engines[S]
+
+    def _push_scales(self, eng):
+        eng.eta.copy_(self.eta_i.reshape(-1).to(torch.float32))
+        xi = float(self.xi_u_global)
+        eng.inv_xi = 1.0 / xi if self.scale_rows else 1.0
+        eng.scale_rows = bool(self.scale_rows)
+
+    @property
+    def surrogate_vars(self):
+        """24 tensors, reference order (2 per var_list entry), views into the flat device buffer."""
+        eng = self._engine_for(1)
+        return list(eng.layout.views(eng.params).values())
+
+    def surrogate_parameters(self):
+        eng = self._engine_for(1)
+        return eng.layout.views(eng.params)
+
+    # ------------------------------------------------------------------ compute_scales
+    def compute_scales(self, data_factory, compute_normalization=True, n=None):
+        """poisson.py:113-154.  `data_factory()` yields batches (dicts keyed by count_key); a
+        `CsrShard` may be passed directly."""
+        if not (self.scale_columns and compute_normalization):
+            return
+        print("Looping through the entire dataset once to get some stats")          # poisson.py:116
+        colsum = torch.zeros(self.feature_dim, dtype=torch.float64, device=self.device)
+        colnnz = torch.zeros(self.feature_dim, dtype=torch.float32, device=self.device)
+        if isinstance(data_factory, CsrShard):
+            shards = [data_factory]
+        else:
+            shards = []
+            for batch in iter(data_factory()):
+                c = batch[self.count_key] if isinstance(batch, dict) else batch
+                if isinstance(c, DeviceBatch):
+                    n0 = int(c.rowptr[0].item())
+                    cols, vals = c.cols[n0:n0 + c.nnz], c.vals[n0:n0 + c.nnz]
+                    _abi.call("spmf_csr_colstats", _ptr(cols), _ptr(vals), c.nnz, self.feature_dim,
+                              _ptr(colsum), _ptr(colnnz), _stream())
+                else:
+                    shards.append(c if isinstance(c, CsrShard) else
+                                  (CsrShard.from_scipy(c, self.device) if hasattr(c, "tocsr")
+                                   else CsrShard.from_dense(c, self.device)))
+        for sh in shards:
+            cs, cn = sh.column_stats()
+            colsum += cs
+            colnnz += cn
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            torch.distributed.all_reduce(colsum, group=self.process_group)
+            torch.distributed.all_reduce(colnnz, group=self.process_group)
+        self._set_scales_from_stats(colsum.cpu(), colnnz.cpu())
+
+    def _set_scales_from_stats(self, colsum, colnnz):
+        colmeans_nonzero = colsum.to(torch.float64) / colnnz.to(torch.float64)      # :136-138
+        rowmean_nonzero = colmeans_nonzero.sum()                                     # :139-140
+        self.eta_i = torch.where(colmeans_nonzero > 1, colmeans_nonzero,
+                                 torch.ones_like(colmeans_nonzero)).reshape(1, -1)   # :142-149
+        self.xi_u_global = float(rowmean_nonzero) if self.scale_rows else 1.          # :151-154
+        for eng in self._engines.values():
+            self._push_scales(eng)
+
+    # ------------------------------------------------------------------ encoder / decoder surface
+    def set_calibration_expectations(self, samples=24, seed=12345):
+        """[EXT] BayesianModel.set_calibration_expectations (called at poisson.py:573): posterior
+        means of every variable, estimated from surrogate draws."""
+        draws = self.surrogate_distribution.sample(samples, seed=seed)
+        self.calibrated_expectations = {k: v.mean(0) for k, v in draws.items()}
+
+    def encoding_matrix(self, u=None, s=None):
+        """A = (s0/(s0+s1)) u, shape (...,D,K)   (poisson.py:652-666)."""
+        u = self.calibrated_expectations['u'] if u is None else u
+        s = self.calibrated_expectations['s'] if s is None else s
+        weights = s / s.sum(-2, keepdim=True)
+        return weights[..., 0, :].unsqueeze(-1) * u
+
+    def decoding_matrix(self, v=None):
+        """poisson.py:668-678."""
+        return self.calibrated_expectations['v'] if v is None else v
+
+    def intercept_matrix(self, w=None, s=None):
+        """phi = eta (s1/(s0+s1)) w, shape (...,1,D)   (poisson.py:680-701)."""
+        w = self.calibrated_expectations['w'] if w is None else w
+        s = self.calibrated_expectations['s'] if s is None else s
+        weights = s / s.sum(-2, keepdim=True)
+        eta = self.eta_i.to(device=w.device, dtype=w.dtype)
+        return eta * weights[..., 1, :].unsqueeze(-2) * w
+
+    def _operands_from_theta(self, eng, u, v, w, s):
+        """Pack explicit draws (S leading axis) into the kernels' gather layout."""
+        S, D, K = eng.S, self.feature_dim, self.latent_dim
+        ws = eng.ws
+        f32 = dict(device=self.device, dtype=torch.float32)
+        eta = self.eta_i.reshape(-1).to(**f32)
+        u, v, w, s = (torch.as_tensor(t).to(**f32) for t in (u, v, w, s))
+        if u.dim() == 2:
+            u, v, w, s = u[None], v[None], w[None], s[None]
+        a = s[:, 0, :] / (s[:, 0, :] + s[:, 1, :])
+        b = 1.0 - a
+        Ap = a[:, :, None] * u / eta[None, :, None]                  # (S,D,K)
+        EV = eta[None, :, None] * v.transpose(-1, -2)                # (S,D,K)
+        PH = eta[None, :] * b * w[:, 0, :]                           # (S,D)
+
+        def pack(t):   # (S,D,K) -> [NQ][D][KP][SV]
+            o = torch.zeros(ws.NQ, D, ws.KP, ws.SV, **f32)
+            o[:, :, :K, :] = t.view(ws.NQ, ws.SV, D, K).permute(0, 2, 3, 1)
+            return o.reshape(-1)
+        ws.Ap.copy_(pack(Ap))
+        ws.EV.copy_(pack(EV))
+        ws.PH.copy_(PH.view(ws.NQ, ws.SV, D).permute(0, 2, 1).reshape(-1))
+        ws.vsum.copy_(ws.EV.view(ws.NQ, D, ws.KP * ws.SV).to(torch.float64).sum(1).reshape(-1))
+        ws.phisum.copy_(ws.PH.view(ws.NQ, D, ws.SV).to(torch.float64).sum(1).reshape(-1))
+
+    def _unpack_rows(self, eng, flat, nrows):
+        ws = eng.ws
+        t = flat[:ws.NQ * nrows * ws.KP * ws.SV].view(ws.NQ, nrows, ws.KP, ws.SV)
+        return t.permute(0, 3, 1, 2).reshape(eng.S, nrows, ws.KP)[..., :self.latent_dim]
+
+    def encode(self, x, u=None, s=None):
+        """z = (x/eta) A * rowsum(x)/xi, shape (...,B,K)   (poisson.py:623-650)."""
+        u = self.calibrated_expectations['u'] if u is None else u
+        s = self.calibrated_expectations['s'] if s is None else s
+        batched = torch.as_tensor(u).dim() == 3
+        S = u.shape[0] if batched else 1
+        eng = self._engine_for(S)
+        b = as_device_batch(x, self.device, self.feature_dim)
+        eng.ws.ensure_rows(b.nrows)
+        D, K = self.feature_dim, self.latent_dim
+        zeros_v = torch.zeros((S, K, D) if batched else (K, D), device=self.device)
+        zeros_w = torch.zeros((S, 1, D) if batched else (1, D), device=self.device)
+        self._operands_from_theta(eng, u, zeros_v, zeros_w, s)
+        ws = eng.ws
+        _abi.call("spmf_csr_encode", _ptr(b.rowptr), _ptr(b.cols), _ptr(b.vals), _ptr(b.rowsum),
+                  eng.inv_xi, int(self.scale_rows), b.nrows, D, K, S, _ptr(ws.Ap), _ptr(ws.z), _stream())
+        z = self._unpack_rows(eng, ws.z, b.nrows).clone()
+        return z if batched else z[0]
+
+    # ------------------------------------------------------------------ energy
+    def unormalized_log_prob_parts(self, data, prior_weight=1., **params):
+        """poisson.py:582-621: dict of 14 (S,) terms -- 12 priors, 'z', 'x' -- evaluated by the
+        CUDA data-term kernels for explicit draws `params` (each with a leading sample axis)."""
+        S = params['u'].shape[0] if params['u'].dim() == 3 else 1
+        eng = self._engine_for(S)
+        b = as_device_batch(data[self.count_key] if isinstance(data, dict) else data, self.device)
+        self._operands_from_theta(eng, params['u'], params['v'], params['w'], params['s'])
+        eng.data_term(b)
+        ws = eng.ws
+        ds = ws.datasums.view(ws.NQ, 4, ws.SV).permute(0, 2, 1).reshape(S, 4)
+        ph = ws.phisum.view(S)
+        x_part = ds[:, 0] - ds[:, 1] - b.nrows * ph
+        z_part = b.nrows * self.latent_dim * 0.5 * math.log(2.0 / math.pi) - 0.5 * ds[:, 2]
+        parts = {k: v * prior_weight for k, v in self._prior_parts_torch(params).items()}
+        parts['z'] = z_part
+        parts['x'] = x_part
+        return parts
+
+    def unormalized_log_prob(self, data=None, prior_weight=1., **params):
+        # poisson.py:575-580 -- the caller's prior_weight is discarded there; kept for parity.
+        parts = self.unormalized_log_prob_parts(data, prior_weight=1., **params)
+        return sum(parts.values())
+
+    def _prior_parts_torch(self, th):
+        """Prior terms for explicit draws (API path only; the training step uses the fused kernel).
+        Small O(S*D*K) torch expressions on the device -- poisson.py:225-377."""
+        f64 = dict(device=self.device, dtype=torch.float64)
+        th = {k: torch.as_tensor(v).to(**f64) for k, v in th.items()}
+        th = {k: (v[None] if v.dim() == 2 else v) for k, v in th.items()}
+        c0, lgh = 0.5 * math.log(2.0 / math.pi), math.lgamma(0.5)
+        ck = self.symmetry_breaking_decay ** torch.arange(self.latent_dim, **f64)[None, :]
+        red = lambda t: t.sum((-1, -2))
+        hn = lambda y, sc: c0 - torch.log(sc) - 0.5 * (y / sc) ** 2
+        ig = lambda y, c, b: c * torch.log(b) - math.lgamma(c) - (c + 1) * torch.log(y) - b / y
+        sig = lambda y, c, b: ig(y * y, c, b) + torch.log(2 * y)
+        one = torch.ones((), **f64)
+        return {
+            'v': red(hn(th['v'], 0.1 * one)), 'w': red(hn(th['w'], one)),
+            'u': red(hn(th['u'], th['u_eta'] * th['u_tau'] * ck)),
+            'u_eta': red(sig(th['u_eta'], 0.5, 1.0 / th['u_eta_a'])),
+            'u_tau': red(sig(th['u_tau'], 0.5, 1.0 / th['u_tau_a'])),
+            's_eta': red(sig(th['s_eta'], 0.5, 1.0 / th['s_eta_a'])),
+            's_tau': red(sig(th['s_tau'], 0.5, 1.0 / th['s_tau_a'])),
+            's': red(hn(th['s'], th['s_eta'] * th['s_tau'])),
+            'u_eta_a': red(ig(th['u_eta_a'], 0.5, one)),
+            'u_tau_a': red(ig(th['u_tau_a'], 0.5, one / self.u_tau_scale ** 2)),
+            's_eta_a': red(ig(th['s_eta_a'], 0.5, one)),
+            's_tau_a': red(ig(th['s_tau_a'], 0.5, one / self.s_tau_scale ** 2)),
+        }
+
+    def log_likelihood_components(self, s, u, v, w, data, *args, **kwargs):
+        """poisson.py:156-184: {'log_likelihood','rate'}, both (S,B,D) -- dense by definition, so
+        this diagnostic surface materialises them with torch ops on the device; the training step
+        never calls it."""
+        c = data[self.count_key] if isinstance(data, dict) else data
+        x = torch.as_tensor(c.toarray() if hasattr(c, "toarray") else c).to(self.device, torch.float32)
+        f32 = dict(device=self.device, dtype=torch.float32)
+        s, u, v, w = (torch.as_tensor(t).to(**f32) for t in (s, u, v, w))
+        z = self.encode(x, u, s)
+        rate = torch.matmul(z, v) * self.eta_i.to(**f32) + self.intercept_matrix(w, s)
+        ll = torch.xlogy(x, rate) - rate - torch.lgamma(x + 1.0)
+        return {'log_likelihood': ll, 'rate': rate}
+
+    def predictive_distribution(self, s, u, v, w, data, *args, **kwargs):
+        """poisson.py:187-210 (the reference reduces a key 'll' that does not exist; here 'll' is
+        the log-likelihood summed over the trailing (B,D) axes when draws carry a sample axis)."""
+        out = self.log_likelihood_components(s=s, u=u, v=v, w=w, data=data)
+        if torch.as_tensor(u).dim() > 2:
+            out['ll'] = out['log_likelihood'].sum((-1, -2))
+        return out
+
+    def unormalized_log_prob_list(self, *x):
+        """poisson.py:703-709 (positional wrapper; needs `data` bound by the caller)."""
+        return self.unormalized_log_prob(**{v: t for v, t in zip(self.var_list, x)})
+
+    # ------------------------------------------------------------------ training loop [EXT L4]
+    def elbo_step(self, batch, sample_size, learning_rate=None, clip_value=0.0, variant=0):
+        """One ADVI step on one minibatch: loss + gradients (+ all-reduce + Adam if learning_rate)."""
+        eng = self._engine_for(sample_size)
+        c = batch[self.count_key] if isinstance(batch, dict) else batch
+        b = as_device_batch(c, self.device)
+        parts = eng.loss_and_grad(b, variant=variant)
+        loss = eng.loss_value(parts)
+        if eng.world_size > 1:
+            from .parallel import allreduce_step
+            loss = allreduce_step(eng, parts, self.process_group)
+        else:
+            eng.clear_comm_slack()
+        if learning_rate is not None:
+            eng.adam_step(learning_rate, clip_value=clip_value)
+        return loss
+
+    def fit(self, batched_data_factory, batch_size=None, dataset_size=None, num_steps=100,
+            learning_rate=0.01, rel_tol=1e-4, abs_tol=None, clip_value=0.0, sample_size=8,
+            sample_batches=1, max_decay_steps=25, lr_decay_factor=0.99, patience=5, verbose=True,
+            **kwargs):
+        """Minibatch ADVI (call site tests/spmf_test.py:35-43).  [EXT] behaviour restated from the
+        reference's notebook logs: an epoch is one pass over
+        `batched_data_factory()`; the mean batch loss is tracked; on improvement the parameters are
+        snapshotted, on a plateau the learning rate decays by `lr_decay_factor` and the best
+        snapshot is restored; stops on rel_tol / abs_tol / max_decay_steps / num_steps.
+        Returns the list of epoch losses."""
+        S = int(sample_size) * int(sample_batches)
+        eng = self._engine_for(S)
+        losses, best, best_state = [], float('inf'), None
+        lr, decays, since_best = float(learning_rate), 0, 0
+        for epoch in range(int(num_steps)):
+            acc = torch.zeros((), dtype=torch.float64, device=self.device)
+            nb, last = 0, None
+            for batch in iter(batched_data_factory()):
+                last = self.elbo_step(batch, S, learning_rate=lr, clip_value=clip_value)
+                acc += last
+                nb += 1
+            if nb == 0:
+                raise ValueError("batched_data_factory() yielded no batches")
+            mean_loss = float(acc.item()) / nb                 # one host sync per epoch
+            losses.append(mean_loss)
+            if verbose:
+                print(f"Epoch {epoch}: average-batch loss: {mean_loss} last batch loss: {float(last.item())}")
+            if not math.isfinite(mean_loss):
+                if best_state is not None:
+                    if verbose:
+                        print("Got NaN, restoring a checkpoint")
+                    self._restore(eng, best_state)
+                lr *= lr_decay_factor
+                decays += 1
+            elif mean_loss < best:
+                improved = best - mean_loss
+                prev_best = best
+                best, since_best = mean_loss, 0
+                best_state = self._snapshot(eng)
+                if math.isfinite(prev_best):
+                    if abs_tol is not None and improved < abs_tol:
+                        break
+                    if rel_tol is not None and improved < rel_tol * abs(prev_best):
+                        break
+            else:
+                since_best += 1
+                if since_best >= patience:
+                    lr *= lr_decay_factor
+                    decays += 1
+                    since_best = 0
+                    if verbose:
+                        print(f"New learning rate: {lr}")
+                    self._restore(eng, best_state)
+            if decays >= max_decay_steps:
+                break
+        else:
+            if verbose:
+                print("Terminating because we are out of iterations")
+        self.set_calibration_expectations()
+        return losses
+
+    calibrate_advi = fit     # legacy name used by bin/factorize_csv.py:121-124
+
+    @staticmethod
+    def _snapshot(eng):
+        return (eng.params.clone(), eng.adam_m.clone(), eng.adam_v.clone(), eng.opt_step)
+
+    @staticmethod
+    def _restore(eng, st):
+        eng.params.copy_(st[0]); eng.adam_m.copy_(st[1]); eng.adam_v.copy_(st[2]); eng.opt_step = st[3]
+
+    # ------------------------------------------------------------------ persistence
+    def state(self):
+        return {
+            'surrogate_vars': [t.detach().cpu().clone() for t in self.surrogate_vars],
+            'eta_i': self.eta_i.clone(), 'xi_u_global': float(self.xi_u_global),
+            'hyper': dict(latent_dim=self.latent_dim, feature_dim=self.feature_dim,
+                          u_tau_scale=self.u_tau_scale, s_tau_scale=self.s_tau_scale,
+                          symmetry_breaking_decay=self.symmetry_breaking_decay,
+                          scale_columns=self.scale_columns, scale_rows=self.scale_rows,
+                          count_key=self.count_key),
+        }
+
+    def save(self, filename):
+        """[EXT] BayesianModel.save (dill pickle in the reference; bin/factorize_csv.py:136-139)."""
+        with open(filename, 'wb') as f:
+            pickle.dump(self.state(), f)
+
+    def reconstitute(self, state):
+        """poisson.py:711-717: re-create distributions, then assign the saved tensors in order."""
+        self.create_distributions()
+        for dst, value in zip(self.surrogate_vars, state['surrogate_vars']):
+            dst.copy_(torch.as_tensor(value).to(device=self.device, dtype=torch.float32))
+        if 'eta_i' in state:
+            self.eta_i = torch.as_tensor(state['eta_i'], dtype=torch.float64).reshape(1, -1)
+            self.xi_u_global = float(state.get('xi_u_global', 1.0))
+            for eng in self._engines.values():
+                self._push_scales(eng)
+
+    @classmethod
+    def load(cls, filename, device=None):
+        with open(filename, 'rb') as f:
+            state = pickle.load(f)
+        m = cls(device=device, **state['hyper'])
+        m.reconstitute(state)
+        m.set_calibration_expectations()
+        return m
