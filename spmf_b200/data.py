@@ -134,11 +134,19 @@ class CsrShard:
         return colsum, colnnz
 
 
+_UPLOADERS = {}
+
+
 def as_device_batch(counts, device, D=None) -> DeviceBatch:
     """Accept what a reference-style data factory may yield under `count_key`: a DeviceBatch, a
     dense torch/numpy array, or a scipy.sparse matrix."""
     if isinstance(counts, DeviceBatch):
         return counts
+    if isinstance(counts, HostCsrBatch):
+        up = _UPLOADERS.get((str(device), counts.D))
+        if up is None:
+            up = _UPLOADERS[(str(device), counts.D)] = BatchUploader(device, counts.D)
+        return up.upload(counts)
     if isinstance(counts, CsrShard):
         return counts.batch(0, counts.nrows)
     if hasattr(counts, "tocsr"):
@@ -213,3 +221,85 @@ def synth_scrna_csr_device(nrows, D, density=0.05, seed=0, device="cuda", sigma_
         base = int(rp[-1].item())
         del lam, x, nzmask, idx
     return CsrShard(torch.cat(rowptrs), torch.cat(cols_l), torch.cat(vals_l), D, dev)
+
+
+# ---------------------------------------------------------------------------
+# Host-resident CSR (pinned) -- the streaming path: each step's minibatch is copied H2D, its row
+# constants and CSC copy are built on the device, then the step runs.  This is what a reference
+# style `data_factory` yielding host batches costs end to end.
+# ---------------------------------------------------------------------------
+@dataclass
+class HostCsrBatch:
+    rowptr: torch.Tensor   # int64 [nrows+1], zero-based, pinned host
+    cols: torch.Tensor     # int32 [nnz], pinned host
+    vals: torch.Tensor     # fp32 [nnz], pinned host
+    D: int
+
+    @property
+    def nrows(self):
+        return self.rowptr.numel() - 1
+
+    @property
+    def nnz(self):
+        return int(self.vals.numel())
+
+    def nbytes(self):
+        return self.rowptr.numel() * 8 + self.cols.numel() * 4 + self.vals.numel() * 4
+
+
+class HostCsr:
+    """A CSR shard kept in pinned host memory; `batch()` slices are zero-copy views."""
+
+    def __init__(self, rowptr, cols, vals, D):
+        self.rowptr = torch.as_tensor(rowptr).to(torch.int64).contiguous()
+        self.cols = torch.as_tensor(cols).to(torch.int32).contiguous().pin_memory()
+        self.vals = torch.as_tensor(vals).to(torch.float32).contiguous().pin_memory()
+        self.D = int(D)
+        self.nrows = self.rowptr.numel() - 1
+
+    @classmethod
+    def from_shard(cls, shard: CsrShard):
+        return cls(shard.rowptr.cpu(), shard.cols.cpu(), shard.vals.cpu(), shard.D)
+
+    def batch(self, row0, nrows) -> HostCsrBatch:
+        j0, j1 = int(self.rowptr[row0]), int(self.rowptr[row0 + nrows])
+        rp = (self.rowptr[row0:row0 + nrows + 1] - j0).contiguous().pin_memory()
+        return HostCsrBatch(rp, self.cols[j0:j1], self.vals[j0:j1], self.D)
+
+
+class BatchUploader:
+    """Reusable device staging for host batches: async H2D of (rowptr, cols, vals), then the row
+    constants and the CSC copy are built by kernels on the same stream."""
+
+    def __init__(self, device, D, max_rows=0, max_nnz=0):
+        self.device, self.D = torch.device(device), int(D)
+        self._alloc(max_rows, max_nnz)
+
+    def _alloc(self, rows, nnz):
+        dev = self.device
+        self.cap_rows, self.cap_nnz = int(rows), int(nnz)
+        self.rowptr = torch.empty(rows + 1, dtype=torch.int64, device=dev)
+        self.cols = torch.empty(max(nnz, 1), dtype=torch.int32, device=dev)
+        self.vals = torch.empty(max(nnz, 1), dtype=torch.float32, device=dev)
+        self.rowsum = torch.empty(max(rows, 1), dtype=torch.float32, device=dev)
+        self.lgam = torch.empty(max(rows, 1), dtype=torch.float32, device=dev)
+        self.colptr = torch.empty(self.D + 1, dtype=torch.int32, device=dev)
+        self.cursor = torch.empty(self.D + 1, dtype=torch.int32, device=dev)
+        self.crows = torch.empty(max(nnz, 1), dtype=torch.int32, device=dev)
+        self.cvals = torch.empty(max(nnz, 1), dtype=torch.float32, device=dev)
+
+    def upload(self, hb: HostCsrBatch) -> DeviceBatch:
+        n, nnz = hb.nrows, hb.nnz
+        if n > self.cap_rows or nnz > self.cap_nnz:
+            self._alloc(max(n, self.cap_rows), max(int(nnz * 1.25), self.cap_nnz))
+        self.rowptr[:n + 1].copy_(hb.rowptr, non_blocking=True)
+        self.cols[:nnz].copy_(hb.cols, non_blocking=True)
+        self.vals[:nnz].copy_(hb.vals, non_blocking=True)
+        st = _stream()
+        _abi.call("spmf_csr_row_consts", _ptr(self.rowptr), _ptr(self.vals), n, _ptr(self.rowsum),
+                  _ptr(self.lgam), st)
+        _abi.call("spmf_csr_to_csc", _ptr(self.rowptr), _ptr(self.cols), _ptr(self.vals), n, self.D,
+                  _ptr(self.colptr), _ptr(self.crows), _ptr(self.cvals), _ptr(self.cursor), st)
+        return DeviceBatch(rowptr=self.rowptr[:n + 1], cols=self.cols, vals=self.vals,
+                           rowsum=self.rowsum[:n], lgam=self.lgam[:n], nrows=n, nnz=nnz, D=self.D,
+                           colptr=self.colptr, crows=self.crows, cvals=self.cvals)

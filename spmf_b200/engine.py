@@ -86,6 +86,7 @@ class AdviEngine:
         self.opt_step = 0
         self.rng_step = 0
         self.launches = 0     # CUDA kernel launches issued through the ABI (bench's gpu_launches)
+        self.kernel_events = None   # when a dict: name -> [(start,end) CUDA events] around the hot kernels
 
     @property
     def ws(self) -> StepWorkspace:
@@ -113,16 +114,28 @@ class AdviEngine:
         w.ensure_rows(b.nrows)
         b.ensure_csc()
         st = _stream()
+        ev = self.kernel_events
+        if ev is not None:
+            e0, e1, e2, e3 = (torch.cuda.Event(enable_timing=True) for _ in range(4))
+            e0.record()
         _abi.call("spmf_csr_rows", _ptr(b.rowptr), _ptr(b.cols), _ptr(b.vals), _ptr(b.rowsum),
                   _ptr(b.lgam), self.inv_xi, int(self.scale_rows), b.nrows, self.D, self.K, self.S,
                   _ptr(w.Ap), _ptr(w.EV), _ptr(w.PH), _ptr(w.vsum), _ptr(w.z), _ptr(w.dzr),
                   _ptr(w.rowacc), variant, st)
+        if ev is not None:
+            e1.record()
         _abi.call("spmf_batch_sums", _ptr(w.z), _ptr(w.rowacc), b.nrows, self.K, self.S,
                   _ptr(w.zcolsum), _ptr(w.datasums), _ptr(w.scr_d), st)
+        if ev is not None:
+            e2.record()
         _abi.call("spmf_csc_cols", _ptr(b.colptr), _ptr(b.crows), _ptr(b.cvals), b.nnz, b.nrows,
                   self.D, self.K, self.S, _ptr(w.z), _ptr(w.dzr), _ptr(w.EV), _ptr(w.PH), _ptr(w.GAp),
                   _ptr(w.GEV), _ptr(w.Gph), variant, st)
-        self.launches += 1 + 4 + 1
+        if ev is not None:
+            e3.record()
+            ev.setdefault("csr_rows", []).append((e0, e1, b.nnz, b.nrows))
+            ev.setdefault("csc_cols", []).append((e2, e3, b.nnz, b.nrows))
+        self.launches += 1 + 4 + 1 + 3   # rows, 4 reduce launches, cols (+3 memsets)
 
     def backward_params(self, batch_rows):
         w = self.ws
