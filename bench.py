@@ -213,9 +213,11 @@ def main():
     eng.kernel_events = {}
     launches0 = eng.launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.nvtx.range_push("spmf_timed")
     e0.record()
     run_steps(args.steps, lambda i: batches[(args.warmup + i) % len(batches)], args.lr)
     e1.record()
+    torch.cuda.nvtx.range_pop()
     barrier()
     ms = e0.elapsed_time(e1)
     launches = eng.launches - launches0
@@ -264,7 +266,9 @@ def main():
     KP, SV = eng.ws.KP, eng.ws.SV
     C = KP * S                                        # channels per row/column: KP * SV * NQ
     kern = {}
-    for name, evs in kev.items():
+    phases = {name: sum(a.elapsed_time(b) for a, b, _, _ in evs) / len(evs)
+              for name, evs in kev.items() if name not in ("csr_rows", "csc_cols")}
+    for name, evs in ((n, e) for n, e in kev.items() if n in ("csr_rows", "csc_cols")):
         dur = [a.elapsed_time(b) for a, b, _, _ in evs]
         nz = [n for _, _, n, _ in evs]
         if name == "csr_rows":      # CSR stream + both operand tables + z, dzr out (fp32)
@@ -279,6 +283,7 @@ def main():
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                 "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
                 "kernel_ms": kern[dom]["ms"], "kernel_share_of_step": kern[dom]["ms"] / step_ms,
+                "phases_ms": phases,
                 "kernels": {k: {"ms": v["ms"], "alg_GBps": v["bytes"] / (v["ms"] * 1e-3) / 1e9,
                                 "fp32_TFLOPs": v["flop"] / (v["ms"] * 1e-3) / 1e12} for k, v in kern.items()},
                 "note": "gather/FMA-bound SpMM+SDDMM at K*S=128 channels: per nonzero 8 B of HBM vs ~2 KB of "

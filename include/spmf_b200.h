@@ -19,9 +19,9 @@
  *                                   (order: v,w,u,s | u_eta,u_tau,s_eta,s_tau,u_eta_a,u_tau_a,s_eta_a,s_tau_a;
  *                                    each as (loc|conc_raw , scale_raw); v stored transposed as (D,K))
  *   noise                         : flat fp32 [var][s][elem]; N(0,1) for v,w,u,s, Gamma(alpha,1) otherwise
- *   Ap, EV, GAp, GEVnz            : [NQ][D][KP][SV]   A' = a_d u_dk / eta_d,  EV = eta_d v_kd
+ *   Ap, EV, GAp, GEVnz            : [NQ][D][SV][KP]   A' = a_d u_dk / eta_d,  EV = eta_d v_kd  (k innermost)
  *   PH, Gphinz                    : [NQ][D][SV]       phi_d = eta_d b_d w_d
- *   z, dzr                        : [NQ][B][KP][SV]   z_bk and r_b * dL/dz_bk
+ *   z, dzr                        : [NQ][B][SV][KP]   z_bk and r_b * dL/dz_bk
  *   rowacc                        : [NQ][B][4][SV]    per-row (sum x log lam - lgamma, z.vsum, |z|^2, #non-finite)
  */
 #ifndef SPMF_B200_H
@@ -54,7 +54,7 @@ int spmf_fill_noise(float* noise, const float* params, int D, int K, int S,
 int spmf_sample(const float* params, const float* noise, int D, int K, int S, float* samples,
                 void* stream);
 /* encoding_matrix / intercept_matrix / decoding_matrix for every draw (poisson.py:652-701),
- * plus vsum[NQ][KP][SV] = sum_d EV and phisum[NQ][SV] = sum_d PH for the closed-form -sum(rate). */
+ * plus vsum[NQ][SV][KP] = sum_d EV and phisum[NQ][SV] = sum_d PH for the closed-form -sum(rate). */
 int spmf_draw_operands(const float* params, const float* noise, const float* eta, int D, int K, int S,
                        float* Ap, float* EV, float* PH, double* vsum, double* phisum,
                        double* scratch, void* stream);
@@ -70,7 +70,7 @@ int spmf_csr_rows(const long long* rowptr, const int* cols, const float* vals, c
                   const float* lgam, float inv_xi, int scale_rows, int nrows, int D, int K, int S,
                   const float* Ap, const float* EV, const float* PH, const double* vsum, float* z,
                   float* dzr, float* rowacc, int variant, void* stream);
-/* encode only (inference): z[NQ][B][KP][SV] */
+/* encode only (inference): z[NQ][B][SV][KP] */
 int spmf_csr_encode(const long long* rowptr, const int* cols, const float* vals, const float* rowsum,
                     float inv_xi, int scale_rows, int nrows, int D, int K, int S, const float* Ap,
                     float* z, void* stream);
@@ -79,7 +79,7 @@ int spmf_csr_encode(const long long* rowptr, const int* cols, const float* vals,
 int spmf_csc_cols(const int* colptr, const int* rows, const float* vals, int nnz, int nrows, int D,
                   int K, int S, const float* z, const float* dzr, const float* EV, const float* PH,
                   float* GAp, float* GEVnz, float* Gphinz, int variant, void* stream);
-/* sums over the rows of the batch: zcolsum[NQ][KP][SV], datasums[NQ][4][SV] */
+/* sums over the rows of the batch: zcolsum[NQ][SV][KP], datasums[NQ][4][SV] */
 int spmf_batch_sums(const float* z, const float* rowacc, int nrows, int K, int S, double* zcolsum,
                     double* datasums, double* scratch, void* stream);
 

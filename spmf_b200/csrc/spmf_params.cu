@@ -80,7 +80,7 @@ draw_operands_kernel(Layout L, const float* __restrict__ P, const float* __restr
       if (k < KP) {
         float ap = 0.f, ev = 0.f;
         if (k < L.K) lane_operands<KK>(st, L, N, eta, d, lane, i, s, fd.a, &ap, &ev, nullptr, nullptr);
-        long long idx = (((long long)q * L.D + d) * KP + k) * SV + sv;
+        long long idx = (((long long)q * L.D + d) * SV + sv) * KP + k;
         Ap[idx] = ap;
         EV[idx] = ev;
       }
@@ -136,10 +136,10 @@ backward_feat_kernel(Layout L, Hyper h, const float* __restrict__ P, const float
     for (int i = 0; i < KK; ++i) {
       int k = lane + 32 * i;
       if (k < L.K) {
-        long long idx = (((long long)q * L.D + d) * KP + k) * SV + sv;
+        long long idx = (((long long)q * L.D + d) * SV + sv) * KP + k;
         DkUp up;
         up.GAp = GAp[idx];
-        up.GEV = GEVnz[idx] - (float)zcolsum[((long long)q * KP + k) * SV + sv];
+        up.GEV = GEVnz[idx] - (float)zcolsum[((long long)q * SV + sv) * KP + k];
         DkOut o = lane_step<KK>(st, L, h, N, eta, d, lane, i, s, fd.a, up);
         da += o.da;
         scr_utau[((long long)s * L.D + d) * L.K + k] = o.dutau;

@@ -8,9 +8,9 @@
 // The -sum(rate) part of the Poisson log-likelihood is closed form and handled
 // by vsum / zcolsum / phisum, O(BK + KD).
 //
-// Thread mapping (variant 0, generic): a group of LPN = min(KP,32) lanes owns one row / one slice
-// of the CSC stream; lane gl holds latent k = gl + LPN*i, each as an SV-wide vector of draws, so a
-// gather of one operand row [KP][SV] is one coalesced KP*SV*4-byte read.
+// Thread mapping: see `Map` below -- operand records are [SV][KP] (k innermost), a slot of up to
+// 32 lanes owns one nonzero at a time, so a gather of one record is one coalesced SV*KP*4-byte read
+// and the k-contraction is in-lane FMAs plus a log2(RG)-step butterfly.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -24,195 +24,269 @@ namespace spmf {
     if (e__ != cudaSuccess) return (int)e__;     \
   } while (0)
 
-template <int SV>
-__device__ __forceinline__ void ldv(float (&r)[SV], const float* __restrict__ p) {
-  if constexpr (SV == 4) {
+// ---- thread mapping shared by the row and column passes -------------------------------------
+// Operand records are [SV][KP] floats (k innermost).  A "slot" of LPN lanes owns one nonzero at a
+// time: lane_in = s*RG + kg holds, for draw s, the k-vectors nv = i*RG + kg (i < VPL), each VW wide.
+// The k-contraction is VW*VPL FMAs in-lane followed by a butterfly over the RG lanes of draw s.
+template <int KP, int SV>
+struct Map {
+  static constexpr int VW = KP < 4 ? KP : 4;            // floats per vector load (over k)
+  static constexpr int NV = KP / VW;                     // k-vectors per draw
+  static constexpr int LPN = (SV * NV) < 32 ? (SV * NV) : 32;   // lanes per nonzero slot
+  static constexpr int RG = LPN / SV;                    // lanes sharing one draw
+  static constexpr int VPL = NV / RG;                    // vectors per lane
+  static constexpr int REC = SV * KP;                    // floats per operand record
+  static constexpr int THREADS = 128;
+  static constexpr int NSLOT = THREADS / LPN;            // slots per CTA
+};
+
+template <int VW>
+__device__ __forceinline__ void ldv(float (&r)[VW], const float* __restrict__ p) {
+  if constexpr (VW == 4) {
     float4 t = __ldg(reinterpret_cast<const float4*>(p));
     r[0] = t.x; r[1] = t.y; r[2] = t.z; r[3] = t.w;
-  } else if constexpr (SV == 2) {
+  } else if constexpr (VW == 2) {
     float2 t = __ldg(reinterpret_cast<const float2*>(p));
     r[0] = t.x; r[1] = t.y;
   } else {
     r[0] = __ldg(p);
   }
 }
-template <int SV>
-__device__ __forceinline__ void stv(float* __restrict__ p, const float (&r)[SV]) {
-  if constexpr (SV == 4) {
+template <int VW>
+__device__ __forceinline__ void ldv_s(float (&r)[VW], const float* p) {   // shared / generic
+  if constexpr (VW == 4) {
+    float4 t = *reinterpret_cast<const float4*>(p);
+    r[0] = t.x; r[1] = t.y; r[2] = t.z; r[3] = t.w;
+  } else if constexpr (VW == 2) {
+    float2 t = *reinterpret_cast<const float2*>(p);
+    r[0] = t.x; r[1] = t.y;
+  } else {
+    r[0] = *p;
+  }
+}
+template <int VW>
+__device__ __forceinline__ void stv(float* p, const float (&r)[VW]) {
+  if constexpr (VW == 4) {
     *reinterpret_cast<float4*>(p) = make_float4(r[0], r[1], r[2], r[3]);
-  } else if constexpr (SV == 2) {
+  } else if constexpr (VW == 2) {
     *reinterpret_cast<float2*>(p) = make_float2(r[0], r[1]);
   } else {
     p[0] = r[0];
   }
 }
 
-template <int LPN>
+template <int RG>
 __device__ __forceinline__ float group_sum(float v, unsigned mask) {
 #pragma unroll
-  for (int o = LPN / 2; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o);
+  for (int o = RG / 2; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o);
   return v;
 }
 
-constexpr int kWarpsPerBlock = 4;
+template <int LPN>
+__device__ __forceinline__ unsigned slot_mask(int lane) {
+  if constexpr (LPN == 32) return 0xffffffffu;
+  else return ((1u << LPN) - 1u) << ((lane / LPN) * LPN);
+}
 
 // ------------------------------------------------------------------ row pass
+// One CTA per row, NSLOT slots striding over the row's nonzeros; slot partials meet in shared
+// memory.  z stays in registers between the two sweeps; the rate matrix is never written.
 template <int KP, int SV, bool ENCODE_ONLY>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+__global__ void __launch_bounds__(128)
 csr_rows_kernel(const long long* __restrict__ rowptr, const int* __restrict__ cols,
                 const float* __restrict__ vals, const float* __restrict__ rowsum,
                 const float* __restrict__ lgam, float inv_xi, int scale_rows, int nrows, int D,
                 const float* __restrict__ Ap, const float* __restrict__ EV,
                 const float* __restrict__ PH, const double* __restrict__ vsum,
                 float* __restrict__ z, float* __restrict__ dzr, float* __restrict__ rowacc) {
-  constexpr int LPN = KP < 32 ? KP : 32;
-  constexpr int KPL = KP / LPN;
-  constexpr int GPW = 32 / LPN;
+  using M = Map<KP, SV>;
+  constexpr int VW = M::VW, LPN = M::LPN, RG = M::RG, VPL = M::VPL, REC = M::REC, NSLOT = M::NSLOT;
+  __shared__ __align__(16) float part[NSLOT * REC];
+  __shared__ float sc[NSLOT][SV][2];
   const int lane = threadIdx.x & 31;
-  const int gl = lane % LPN;
-  const int grp = (threadIdx.x >> 5) * GPW + lane / LPN;
-  const int row = blockIdx.x * (kWarpsPerBlock * GPW) + grp;
-  const int q = blockIdx.y;
-  const unsigned gmask = (LPN == 32) ? 0xffffffffu : (((1u << LPN) - 1u) << ((lane / LPN) * LPN));
-  if (row >= nrows) return;
+  const int slot = threadIdx.x / LPN;
+  const int li = threadIdx.x % LPN;
+  const int s = li / RG, kg = li % RG;
+  const int row = blockIdx.x, q = blockIdx.y;
+  const unsigned gmask = slot_mask<LPN>(lane);
+  int off[VPL];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) off[i] = s * KP + (i * RG + kg) * VW;
 
-  const float* Apq = Ap + (long long)q * D * KP * SV;
+  const float* Apq = Ap + (long long)q * D * REC;
   const long long j0 = rowptr[row], j1 = rowptr[row + 1];
   const float r = scale_rows ? rowsum[row] * inv_xi : 1.f;   // poisson.py:644-649
 
   // ---- z = r * sum_d x A'_d          (poisson.py:640-643 with 1/eta folded into A')
-  float zz[KPL][SV];
+  float zz[VPL][VW];
 #pragma unroll
-  for (int i = 0; i < KPL; ++i)
+  for (int i = 0; i < VPL; ++i)
 #pragma unroll
-    for (int v = 0; v < SV; ++v) zz[i][v] = 0.f;
-  for (long long j = j0; j < j1; ++j) {
+    for (int w = 0; w < VW; ++w) zz[i][w] = 0.f;
+#pragma unroll 4
+  for (long long j = j0 + slot; j < j1; j += NSLOT) {
     const int d = __ldg(cols + j);
     const float x = __ldg(vals + j);
+    const float* rec = Apq + (long long)d * REC;
 #pragma unroll
-    for (int i = 0; i < KPL; ++i) {
-      float a[SV];
-      ldv<SV>(a, Apq + ((long long)d * KP + gl + LPN * i) * SV);
+    for (int i = 0; i < VPL; ++i) {
+      float a[VW];
+      ldv<VW>(a, rec + off[i]);
 #pragma unroll
-      for (int v = 0; v < SV; ++v) zz[i][v] = fmaf(x, a[v], zz[i][v]);
+      for (int w = 0; w < VW; ++w) zz[i][w] = fmaf(x, a[w], zz[i][w]);
     }
   }
-  float* zq = z + ((long long)q * nrows + row) * KP * SV;
+  if constexpr (NSLOT > 1) {
 #pragma unroll
-  for (int i = 0; i < KPL; ++i) {
+    for (int i = 0; i < VPL; ++i) stv<VW>(part + slot * REC + off[i], zz[i]);
+    __syncthreads();
 #pragma unroll
-    for (int v = 0; v < SV; ++v) zz[i][v] *= r;
-    stv<SV>(zq + (gl + LPN * i) * SV, zz[i]);
+    for (int i = 0; i < VPL; ++i) {
+#pragma unroll
+      for (int w = 0; w < VW; ++w) zz[i][w] = 0.f;
+#pragma unroll
+      for (int t = 0; t < NSLOT; ++t) {       // fixed order: every slot ends with the same bits
+        float a[VW];
+        ldv_s<VW>(a, part + t * REC + off[i]);
+#pragma unroll
+        for (int w = 0; w < VW; ++w) zz[i][w] += a[w];
+      }
+    }
+  }
+  float* zq = z + ((long long)q * nrows + row) * REC;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+#pragma unroll
+    for (int w = 0; w < VW; ++w) zz[i][w] *= r;
+    if (slot == 0) stv<VW>(zq + off[i], zz[i]);
   }
   if constexpr (ENCODE_ONLY) return;
 
   // ---- lambda at the nonzeros, x log lambda, dz      (poisson.py:174-184)
-  const float* EVq = EV + (long long)q * D * KP * SV;
+  const float* EVq = EV + (long long)q * D * REC;
   const float* PHq = PH + (long long)q * D * SV;
-  float dz[KPL][SV];
-  float xlog[SV], bad[SV];
+  float dz[VPL][VW];
+  float xlog = 0.f, bad = 0.f;
 #pragma unroll
-  for (int v = 0; v < SV; ++v) { xlog[v] = 0.f; bad[v] = 0.f; }
+  for (int i = 0; i < VPL; ++i)
 #pragma unroll
-  for (int i = 0; i < KPL; ++i)
-#pragma unroll
-    for (int v = 0; v < SV; ++v) dz[i][v] = 0.f;
-  for (long long j = j0; j < j1; ++j) {
+    for (int w = 0; w < VW; ++w) dz[i][w] = 0.f;
+#pragma unroll 2
+  for (long long j = j0 + slot; j < j1; j += NSLOT) {
     const int d = __ldg(cols + j);
     const float x = __ldg(vals + j);
-    float e[KPL][SV], p[SV], ph[SV];
+    const float* rec = EVq + (long long)d * REC;
+    const float ph = __ldg(PHq + (long long)d * SV + s);
+    float e[VPL][VW];
+    float p = 0.f;
 #pragma unroll
-    for (int v = 0; v < SV; ++v) p[v] = 0.f;
+    for (int i = 0; i < VPL; ++i) {
+      ldv<VW>(e[i], rec + off[i]);
 #pragma unroll
-    for (int i = 0; i < KPL; ++i) {
-      ldv<SV>(e[i], EVq + ((long long)d * KP + gl + LPN * i) * SV);
-#pragma unroll
-      for (int v = 0; v < SV; ++v) p[v] = fmaf(zz[i][v], e[i][v], p[v]);
+      for (int w = 0; w < VW; ++w) p = fmaf(zz[i][w], e[i][w], p);
     }
-    ldv<SV>(ph, PHq + (long long)d * SV);
+    const float lam = group_sum<RG>(p, gmask) + ph;          // poisson.py:177
+    const float t = x * __logf(lam);
+    const float gq = __fdividef(x, lam);
+    if (isfinite(t) && isfinite(gq)) {
+      xlog += t;
 #pragma unroll
-    for (int v = 0; v < SV; ++v) {
-      const float lam = group_sum<LPN>(p[v], gmask) + ph[v];   // poisson.py:177
-      const float t = x * __logf(lam);
-      const float gq = __fdividef(x, lam);
-      if (isfinite(t) && isfinite(gq)) {
-        xlog[v] += t;
+      for (int i = 0; i < VPL; ++i)
 #pragma unroll
-        for (int i = 0; i < KPL; ++i) dz[i][v] = fmaf(gq, e[i][v], dz[i][v]);
-      } else {
-        bad[v] += 1.f;   // reported, see rowacc slot 3 (guard of poisson.py:606-616)
+        for (int w = 0; w < VW; ++w) dz[i][w] = fmaf(gq, e[i][w], dz[i][w]);
+    } else {
+      bad += 1.f;   // reported through rowacc slot 3 (guard of poisson.py:606-616)
+    }
+  }
+  if constexpr (NSLOT > 1) {
+    __syncthreads();   // everyone is done reading `part` (z partials)
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) stv<VW>(part + slot * REC + off[i], dz[i]);
+    if (kg == 0) { sc[slot][s][0] = xlog; sc[slot][s][1] = bad; }
+    __syncthreads();
+    if (slot != 0) return;
+    xlog = 0.f; bad = 0.f;
+#pragma unroll
+    for (int t = 0; t < NSLOT; ++t) { xlog += sc[t][s][0]; bad += sc[t][s][1]; }
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+#pragma unroll
+      for (int w = 0; w < VW; ++w) dz[i][w] = 0.f;
+#pragma unroll
+      for (int t = 0; t < NSLOT; ++t) {
+        float a[VW];
+        ldv_s<VW>(a, part + t * REC + off[i]);
+#pragma unroll
+        for (int w = 0; w < VW; ++w) dz[i][w] += a[w];
       }
     }
   }
-  // ---- closed-form parts and per-row scalars
-  const double* vsq = vsum + (long long)q * KP * SV;
-  float zv[SV], z2[SV];
+  // ---- closed-form parts and per-row scalars (slot 0 only from here)
+  const double* vsq = vsum + (long long)q * REC;
+  float zv = 0.f, z2 = 0.f;
+  float* dq = dzr + ((long long)q * nrows + row) * REC;
 #pragma unroll
-  for (int v = 0; v < SV; ++v) { zv[v] = 0.f; z2[v] = 0.f; }
-  float* dq = dzr + ((long long)q * nrows + row) * KP * SV;
+  for (int i = 0; i < VPL; ++i) {
+    float o[VW];
 #pragma unroll
-  for (int i = 0; i < KPL; ++i) {
-    float o[SV];
-#pragma unroll
-    for (int v = 0; v < SV; ++v) {
-      const float vs = (float)vsq[(gl + LPN * i) * SV + v];
-      zv[v] = fmaf(zz[i][v], vs, zv[v]);
-      z2[v] = fmaf(zz[i][v], zz[i][v], z2[v]);
-      o[v] = r * (dz[i][v] - vs - zz[i][v]);     // dL/dz includes the HalfNormal(1) z prior (:599-604)
+    for (int w = 0; w < VW; ++w) {
+      const float vs = (float)vsq[off[i] + w];
+      zv = fmaf(zz[i][w], vs, zv);
+      z2 = fmaf(zz[i][w], zz[i][w], z2);
+      o[w] = r * (dz[i][w] - vs - zz[i][w]);   // dL/dz includes the HalfNormal(1) z prior (:599-604)
     }
-    stv<SV>(dq + (gl + LPN * i) * SV, o);
+    stv<VW>(dq + off[i], o);
   }
-#pragma unroll
-  for (int v = 0; v < SV; ++v) {
-    zv[v] = group_sum<LPN>(zv[v], gmask);
-    z2[v] = group_sum<LPN>(z2[v], gmask);
-  }
-  if (gl == 0) {
+  zv = group_sum<RG>(zv, gmask);
+  z2 = group_sum<RG>(z2, gmask);
+  if (kg == 0) {
     float* ra = rowacc + ((long long)q * nrows + row) * 4 * SV;
-    const float lg = lgam[row];
-#pragma unroll
-    for (int v = 0; v < SV; ++v) {
-      ra[0 * SV + v] = xlog[v] - lg;
-      ra[1 * SV + v] = zv[v];
-      ra[2 * SV + v] = z2[v];
-      ra[3 * SV + v] = bad[v];
-    }
+    ra[0 * SV + s] = xlog - lgam[row];
+    ra[1 * SV + s] = zv;
+    ra[2 * SV + s] = z2;
+    ra[3 * SV + s] = bad;
   }
 }
 
 // ------------------------------------------------------------------ column pass
+// Each slot walks a fixed-length slice of the CSC nonzero stream (perfect balance, coalesced
+// streaming), keeps the current column's EV record and accumulators in registers and flushes with
+// atomics when the column changes (only columns that straddle slices are contended).
 constexpr int kSliceLen = 256;
 
 template <int KP, int SV>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+__global__ void __launch_bounds__(128)
 csc_cols_kernel(const int* __restrict__ colptr, const int* __restrict__ rows,
                 const float* __restrict__ vals, int nnz, int nrows, int D,
                 const float* __restrict__ z, const float* __restrict__ dzr,
                 const float* __restrict__ EV, const float* __restrict__ PH,
                 float* __restrict__ GAp, float* __restrict__ GEV, float* __restrict__ Gphi) {
-  constexpr int LPN = KP < 32 ? KP : 32;
-  constexpr int KPL = KP / LPN;
-  constexpr int GPW = 32 / LPN;
+  using M = Map<KP, SV>;
+  constexpr int VW = M::VW, LPN = M::LPN, RG = M::RG, VPL = M::VPL, REC = M::REC, NSLOT = M::NSLOT;
   const int lane = threadIdx.x & 31;
-  const int gl = lane % LPN;
-  const int grp = (threadIdx.x >> 5) * GPW + lane / LPN;
-  const int slice = blockIdx.x * (kWarpsPerBlock * GPW) + grp;
+  const int slot = threadIdx.x / LPN;
+  const int li = threadIdx.x % LPN;
+  const int s = li / RG, kg = li % RG;
   const int q = blockIdx.y;
-  const unsigned gmask = (LPN == 32) ? 0xffffffffu : (((1u << LPN) - 1u) << ((lane / LPN) * LPN));
+  const unsigned gmask = slot_mask<LPN>(lane);
+  const int slice = blockIdx.x * NSLOT + slot;
   const int j0 = slice * kSliceLen;
   if (j0 >= nnz) return;
   const int j1 = min(j0 + kSliceLen, nnz);
+  int off[VPL];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) off[i] = s * KP + (i * RG + kg) * VW;
 
-  const float* zq = z + (long long)q * nrows * KP * SV;
-  const float* dq = dzr + (long long)q * nrows * KP * SV;
-  const float* EVq = EV + (long long)q * D * KP * SV;
+  const float* zq = z + (long long)q * nrows * REC;
+  const float* dq = dzr + (long long)q * nrows * REC;
+  const float* EVq = EV + (long long)q * D * REC;
   const float* PHq = PH + (long long)q * D * SV;
-  float* GApq = GAp + (long long)q * D * KP * SV;
-  float* GEVq = GEV + (long long)q * D * KP * SV;
+  float* GApq = GAp + (long long)q * D * REC;
+  float* GEVq = GEV + (long long)q * D * REC;
   float* Gphq = Gphi + (long long)q * D * SV;
 
-  // column containing position j0: largest d with colptr[d] <= j0
-  int lo = 0, hi = D;   // invariant: colptr[lo] <= j0 < colptr[hi]... (colptr[D] = nnz > j0)
+  // column containing position j0: largest d with colptr[d] <= j0  (colptr[D] = nnz > j0)
+  int lo = 0, hi = D;
   while (hi - lo > 1) {
     int mid = (lo + hi) >> 1;
     if (__ldg(colptr + mid) <= j0) lo = mid; else hi = mid;
@@ -220,35 +294,32 @@ csc_cols_kernel(const int* __restrict__ colptr, const int* __restrict__ rows,
   int d = lo;
   int next = __ldg(colptr + d + 1);
 
-  float ev[KPL][SV], ph[SV], aEV[KPL][SV], aAp[KPL][SV], aPh[SV];
+  float ev[VPL][VW], aEV[VPL][VW], aAp[VPL][VW], ph, aPh;
   auto load_col = [&](int dd) {
 #pragma unroll
-    for (int i = 0; i < KPL; ++i) {
-      ldv<SV>(ev[i], EVq + ((long long)dd * KP + gl + LPN * i) * SV);
+    for (int i = 0; i < VPL; ++i) {
+      ldv<VW>(ev[i], EVq + (long long)dd * REC + off[i]);
 #pragma unroll
-      for (int v = 0; v < SV; ++v) { aEV[i][v] = 0.f; aAp[i][v] = 0.f; }
+      for (int w = 0; w < VW; ++w) { aEV[i][w] = 0.f; aAp[i][w] = 0.f; }
     }
-    ldv<SV>(ph, PHq + (long long)dd * SV);
-#pragma unroll
-    for (int v = 0; v < SV; ++v) aPh[v] = 0.f;
+    ph = __ldg(PHq + (long long)dd * SV + s);
+    aPh = 0.f;
   };
   auto flush_col = [&](int dd) {
 #pragma unroll
-    for (int i = 0; i < KPL; ++i) {
-      const long long o = ((long long)dd * KP + gl + LPN * i) * SV;
+    for (int i = 0; i < VPL; ++i) {
+      const long long o = (long long)dd * REC + off[i];
 #pragma unroll
-      for (int v = 0; v < SV; ++v) {
-        atomicAdd(GEVq + o + v, aEV[i][v]);
-        atomicAdd(GApq + o + v, aAp[i][v]);
+      for (int w = 0; w < VW; ++w) {
+        atomicAdd(GEVq + o + w, aEV[i][w]);
+        atomicAdd(GApq + o + w, aAp[i][w]);
       }
     }
-    if (gl == 0) {
-#pragma unroll
-      for (int v = 0; v < SV; ++v) atomicAdd(Gphq + (long long)dd * SV + v, aPh[v]);
-    }
+    if (kg == 0) atomicAdd(Gphq + (long long)dd * SV + s, aPh);
   };
   load_col(d);
   int pending = 0;
+#pragma unroll 2
   for (int j = j0; j < j1; ++j) {
     if (j >= next) {
       if (pending) flush_col(d);
@@ -261,28 +332,26 @@ csc_cols_kernel(const int* __restrict__ colptr, const int* __restrict__ rows,
     }
     const int b = __ldg(rows + j);
     const float x = __ldg(vals + j);
-    float zz[KPL][SV], dd[KPL][SV], p[SV];
+    float zz[VPL][VW], dd[VPL][VW];
+    float p = 0.f;
 #pragma unroll
-    for (int v = 0; v < SV; ++v) p[v] = 0.f;
+    for (int i = 0; i < VPL; ++i) {
+      ldv<VW>(zz[i], zq + (long long)b * REC + off[i]);
+      ldv<VW>(dd[i], dq + (long long)b * REC + off[i]);
 #pragma unroll
-    for (int i = 0; i < KPL; ++i) {
-      ldv<SV>(zz[i], zq + ((long long)b * KP + gl + LPN * i) * SV);
-      ldv<SV>(dd[i], dq + ((long long)b * KP + gl + LPN * i) * SV);
-#pragma unroll
-      for (int v = 0; v < SV; ++v) p[v] = fmaf(zz[i][v], ev[i][v], p[v]);
+      for (int w = 0; w < VW; ++w) p = fmaf(zz[i][w], ev[i][w], p);
     }
+    const float lam = group_sum<RG>(p, gmask) + ph;
+    float gq = __fdividef(x, lam);
+    if (!isfinite(gq) || !isfinite(__logf(lam))) gq = 0.f;   // same entries the row pass dropped
+    aPh += gq;
 #pragma unroll
-    for (int v = 0; v < SV; ++v) {
-      const float lam = group_sum<LPN>(p[v], gmask) + ph[v];
-      float gq = __fdividef(x, lam);
-      if (!isfinite(gq) || !isfinite(__logf(lam))) gq = 0.f;   // same entries the row pass dropped
-      aPh[v] += gq;
+    for (int i = 0; i < VPL; ++i)
 #pragma unroll
-      for (int i = 0; i < KPL; ++i) {
-        aEV[i][v] = fmaf(gq, zz[i][v], aEV[i][v]);
-        aAp[i][v] = fmaf(x, dd[i][v], aAp[i][v]);
+      for (int w = 0; w < VW; ++w) {
+        aEV[i][w] = fmaf(gq, zz[i][w], aEV[i][w]);
+        aAp[i][w] = fmaf(x, dd[i][w], aAp[i][w]);
       }
-    }
     pending = 1;
   }
   if (pending) flush_col(d);
@@ -458,10 +527,8 @@ static int launch_rows(const long long* rowptr, const int* cols, const float* va
                        const float* rowsum, const float* lgam, float inv_xi, int scale_rows, int nrows,
                        int D, int NQ, const float* Ap, const float* EV, const float* PH,
                        const double* vsum, float* z, float* dzr, float* rowacc, cudaStream_t st) {
-  constexpr int LPN = KP < 32 ? KP : 32;
-  constexpr int GPW = 32 / LPN;
-  dim3 grid((nrows + kWarpsPerBlock * GPW - 1) / (kWarpsPerBlock * GPW), NQ);
-  csr_rows_kernel<KP, SV, ENC><<<grid, kWarpsPerBlock * 32, 0, st>>>(
+  dim3 grid(nrows, NQ);
+  csr_rows_kernel<KP, SV, ENC><<<grid, 128, 0, st>>>(
       rowptr, cols, vals, rowsum, lgam, inv_xi, scale_rows, nrows, D, Ap, EV, PH, vsum, z, dzr, rowacc);
   SPMF_CHECK_LAUNCH();
   return SPMF_OK;
@@ -471,13 +538,12 @@ template <int KP, int SV>
 static int launch_cols(const int* colptr, const int* rows, const float* vals, int nnz, int nrows,
                        int D, int NQ, const float* z, const float* dzr, const float* EV,
                        const float* PH, float* GAp, float* GEV, float* Gphi, cudaStream_t st) {
-  constexpr int LPN = KP < 32 ? KP : 32;
-  constexpr int GPW = 32 / LPN;
+  constexpr int NSLOT = Map<KP, SV>::NSLOT;
   const int nslices = (nnz + kSliceLen - 1) / kSliceLen;
   if (nslices == 0) return SPMF_OK;
-  dim3 grid((nslices + kWarpsPerBlock * GPW - 1) / (kWarpsPerBlock * GPW), NQ);
-  csc_cols_kernel<KP, SV><<<grid, kWarpsPerBlock * 32, 0, st>>>(colptr, rows, vals, nnz, nrows, D, z,
-                                                               dzr, EV, PH, GAp, GEV, Gphi);
+  dim3 grid((nslices + NSLOT - 1) / NSLOT, NQ);
+  csc_cols_kernel<KP, SV><<<grid, 128, 0, st>>>(colptr, rows, vals, nnz, nrows, D, z, dzr, EV, PH,
+                                               GAp, GEV, Gphi);
   SPMF_CHECK_LAUNCH();
   return SPMF_OK;
 }

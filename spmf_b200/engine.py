@@ -147,15 +147,31 @@ class AdviEngine:
                   _stream())
         self.launches += 8
 
+    def _mark(self, name, start):
+        """Phase timing hook (bench): CUDA events on the launching stream around a phase."""
+        ev = self.kernel_events
+        if ev is None:
+            return None
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        if start is not None:
+            ev.setdefault(name, []).append((start, e, 0, 0))
+        return e
+
     # ------------------------------------------------------------------ one step
     def loss_and_grad(self, batch: DeviceBatch, fresh_noise=True, variant=0):
         """Fills self.grads and self.ws.parts for `batch`; returns the (S,16) parts tensor (device,
         float64): 12 prior terms in var_list order, logq, z, x, per-draw loss."""
+        t = self._mark(None, None)
         if fresh_noise:
             self.fill_noise()
+            t = self._mark("fill_noise", t)
         self.draw_operands()
+        t = self._mark("draw_operands", t)
         self.data_term(batch, variant)
+        t = self._mark("data_term", t)
         self.backward_params(batch.nrows)
+        self._mark("backward_params", t)
         return self.ws.parts.view(self.S, _abi.NUM_PARTS)
 
     def loss_value(self, parts=None):
@@ -165,9 +181,11 @@ class AdviEngine:
 
     def adam_step(self, lr, beta1=0.9, beta2=0.999, eps=1e-7, clip_value=0.0, grad_scale=1.0):
         self.opt_step += 1
+        t = self._mark(None, None)
         _abi.call("spmf_adam_step", _ptr(self.params), _ptr(self.grads), _ptr(self.adam_m),
                   _ptr(self.adam_v), self.layout.n_params, float(lr), beta1, beta2, eps,
                   self.opt_step, float(clip_value), float(grad_scale), _stream())
+        self._mark("adam", t)
         self.launches += 1
 
     def clear_comm_slack(self):

@@ -234,9 +234,9 @@ class PoissonFactorization:
         EV = eta[None, :, None] * v.transpose(-1, -2)                # (S,D,K)
         PH = eta[None, :] * b * w[:, 0, :]                           # (S,D)
 
-        def pack(t):   # (S,D,K) -> [NQ][D][KP][SV]
-            o = torch.zeros(ws.NQ, D, ws.KP, ws.SV, **f32)
-            o[:, :, :K, :] = t.view(ws.NQ, ws.SV, D, K).permute(0, 2, 3, 1)
+        def pack(t):   # (S,D,K) -> [NQ][D][SV][KP]
+            o = torch.zeros(ws.NQ, D, ws.SV, ws.KP, **f32)
+            o[:, :, :, :K] = t.view(ws.NQ, ws.SV, D, K).permute(0, 2, 1, 3)
             return o.reshape(-1)
         ws.Ap.copy_(pack(Ap))
         ws.EV.copy_(pack(EV))
@@ -246,8 +246,8 @@ class PoissonFactorization:
 
     def _unpack_rows(self, eng, flat, nrows):
         ws = eng.ws
-        t = flat[:ws.NQ * nrows * ws.KP * ws.SV].view(ws.NQ, nrows, ws.KP, ws.SV)
-        return t.permute(0, 3, 1, 2).reshape(eng.S, nrows, ws.KP)[..., :self.latent_dim]
+        t = flat[:ws.NQ * nrows * ws.KP * ws.SV].view(ws.NQ, nrows, ws.SV, ws.KP)
+        return t.permute(0, 2, 1, 3).reshape(eng.S, nrows, ws.KP)[..., :self.latent_dim]
 
     def encode(self, x, u=None, s=None):
         """z = (x/eta) A * rowsum(x)/xi, shape (...,B,K)   (poisson.py:623-650)."""
