@@ -86,8 +86,12 @@ int spmf_batch_sums(const float* z, const float* rowacc, int nrows, int K, int S
 /* ---- backward to the 24 variational tensors + loss parts [EXT L3/L4 GradientTape] ----
  * parts[S][16]: 12 prior terms in the reference's var_list order (poisson.py:572), log q, 'z', 'x'
  * (the dict of unormalized_log_prob_parts, poisson.py:582-621), [15] = per-draw loss. */
-int spmf_backward_params(const float* params, const float* noise, const float* eta, int D, int K, int S,
-                         const float* GAp, const float* GEVnz, const float* Gphinz,
+/* dgda[var][s][elem] (noise layout, Gamma variables only) = d g / d alpha of every Gamma draw:
+ * the implicit-reparameterisation gradient tf.random.gamma supplies in the reference stack [EXT]. */
+int spmf_gamma_grad(const float* params, const float* noise, int D, int K, int S, float* dgda,
+                    void* stream);
+int spmf_backward_params(const float* params, const float* noise, const float* dgda, const float* eta,
+                         int D, int K, int S, const float* GAp, const float* GEVnz, const float* Gphinz,
                          const double* zcolsum, const double* datasums, const double* phisum,
                          float batch_rows, float u_tau_scale, float s_tau_scale, float decay,
                          float w_entropy, float w_prior, int world_size, float* grads, double* parts,

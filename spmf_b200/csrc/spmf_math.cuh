@@ -14,6 +14,11 @@
 #else
 #define SPMF_HD inline
 #endif
+#if defined(__CUDA_ARCH__)
+#define SPMF_RCP(x) __frcp_rn(x)
+#else
+#define SPMF_RCP(x) (1.f / (x))
+#endif
 
 namespace spmf {
 
@@ -53,7 +58,7 @@ SPMF_HD float gamma_sample_der_alpha(float a, float x) {
   if (x <= 1.f || x <= a + 1.f) {
     float T = 1.f, H = 0.f, sT = 1.f, sTH = 0.f;
     for (int n = 1; n < 400; ++n) {
-      float inv = 1.f / (a + (float)n);
+      float inv = SPMF_RCP(a + (float)n);
       T *= x * inv;
       H += inv;
       sT += T;

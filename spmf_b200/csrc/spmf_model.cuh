@@ -66,10 +66,13 @@ struct Hyper {
 };
 
 // ---------------- Normal-based factor:  y = softplus(loc + softplus(rho) * eps) ----------------
-struct NParam { float loc, sig, acc_dt, acc_dte; };
+struct NParam { float loc, sig, logsig, acc_dt, acc_dte; };
 struct NDraw { float t, y, sg; };
 
-SPMF_HD NParam nparam_init(float loc, float rho) { return NParam{loc, softplusf(rho), 0.f, 0.f}; }
+SPMF_HD NParam nparam_init(float loc, float rho) {
+  float sig = softplusf(rho);
+  return NParam{loc, sig, logf(sig), 0.f, 0.f};
+}
 SPMF_HD NDraw ndraw(const NParam& p, float eps) {
   NDraw d;
   d.t = fmaf(p.sig, eps, p.loc);
@@ -79,7 +82,7 @@ SPMF_HD NDraw ndraw(const NParam& p, float eps) {
 }
 // log q(y) = log N(t; loc, sig) - log sigmoid(t)     [EXT tfb.Softplus fldj]
 SPMF_HD float nlogq(const NParam& p, const NDraw& d, float eps) {
-  return -0.5f * eps * eps - logf(p.sig) - kHalfLog2Pi - log_sigmoidf(d.t);
+  return -0.5f * eps * eps - p.logsig - kHalfLog2Pi - log_sigmoidf(d.t);
 }
 // Gy = d loss_s / d y (data+prior part, already weighted); we = entropy weight
 SPMF_HD void nparam_bwd(NParam& p, const NDraw& d, float eps, float Gy, float we) {
@@ -94,7 +97,7 @@ SPMF_HD void nparam_finish(const NParam& p, float rho, float invS, float we, flo
 }
 
 // ------------- InverseGamma-based factor:  y = softplus(beta / g),  g ~ Gamma(alpha,1) -------------
-struct GParam { float alpha, beta, psi, acc_da, acc_db; };
+struct GParam { float alpha, beta, psi, c0, acc_da, acc_db; };   // c0 = -log(beta) - lgamma(alpha)
 struct GDraw { float t, y, sg, g; };
 
 SPMF_HD GParam gparam_init(float conc_raw, float scale_raw) {
@@ -102,6 +105,7 @@ SPMF_HD GParam gparam_init(float conc_raw, float scale_raw) {
   p.alpha = softplusf(conc_raw);
   p.beta = softplusf(scale_raw);
   p.psi = digammaf_pos(p.alpha);
+  p.c0 = -logf(p.beta) - lgammaf(p.alpha);
   p.acc_da = 0.f;
   p.acc_db = 0.f;
   return p;
@@ -116,13 +120,14 @@ SPMF_HD GDraw gdraw(const GParam& p, float g) {
 }
 // log q(y) = log InvGamma(t; alpha, beta) - log sigmoid(t), with beta/t = g, log t = log beta - log g
 SPMF_HD float glogq(const GParam& p, const GDraw& d) {
-  return -logf(p.beta) - lgammaf(p.alpha) + (p.alpha + 1.f) * logf(d.g) - d.g - log_sigmoidf(d.t);
+  return p.c0 + (p.alpha + 1.f) * logf(d.g) - d.g - log_sigmoidf(d.t);
 }
-SPMF_HD void gparam_bwd(GParam& p, const GDraw& d, float Gy, float we) {
+// dgda = d g / d alpha of the Gamma draw (implicit reparameterisation), precomputed per draw by
+// gamma_grad_kernel since it depends on (alpha, g) only.
+SPMF_HD void gparam_bwd(GParam& p, const GDraw& d, float dgda, float Gy, float we) {
   float g = d.g;
   float dlogq_dt = (g / p.beta) * (g - (p.alpha + 1.f)) - one_minus_sigmoidf(d.t);
   float dt = Gy * d.sg + we * dlogq_dt;
-  float dgda = gamma_sample_der_alpha(p.alpha, g);
   p.acc_da += we * (logf(g) - p.psi) - dt * (p.beta / (g * g)) * dgda;
   p.acc_db += we * (p.alpha - g) / p.beta + dt / g;
 }
@@ -163,6 +168,7 @@ struct LaneState {
   NParam u[KK], v[KK];
   GParam ue[KK], ua[KK];
   GParam ut[KK];   // u_tau[k] (replicated per lane, accumulators unused here)
+  float ck[KK];    // symmetry_breaking_decay^k (poisson.py:225-226)
 };
 struct FeatState {
   NParam w, s0, s1;
@@ -175,12 +181,13 @@ struct ModelPtrs {
   const float* eta;      // [D]
 };
 
-SPMF_HD float ck_of(const Hyper& h, int k) { return powf(h.decay, (float)k); }
 
 template <int KK>
-SPMF_HD void lane_init(LaneState<KK>& st, const Layout& L, const float* P, int d, int lane) {
+SPMF_HD void lane_init(LaneState<KK>& st, const Layout& L, const float* P, int d, int lane,
+                       float decay = 1.f) {
   for (int i = 0; i < KK; ++i) {
     int k = lane + 32 * i;
+    st.ck[i] = powf(decay, (float)k);
     if (k < L.K) {
       long long e = (long long)d * L.K + k;
       st.u[i] = nparam_init(P[L.toff[U_LOC] + e], P[L.toff[U_RHO] + e]);
@@ -240,7 +247,8 @@ struct DkOut { float da; float dutau; float parts[5]; };  // parts: U, V, UETA, 
 
 template <int KK>
 SPMF_HD DkOut lane_step(LaneState<KK>& st, const Layout& L, const Hyper& h, const float* N,
-                        const float* eta, int d, int lane, int i, int s, float a_d, DkUp up) {
+                        const float* G, const float* eta, int d, int lane, int i, int s, float a_d,
+                        DkUp up) {
   DkOut o;
   int k = lane + 32 * i;
   const long long DK = (long long)L.D * L.K;
@@ -251,7 +259,7 @@ SPMF_HD DkOut lane_step(LaneState<KK>& st, const Layout& L, const Hyper& h, cons
   GDraw ue = gdraw(st.ue[i], N[L.noff[VAR_UETA] + e]);
   GDraw ua = gdraw(st.ua[i], N[L.noff[VAR_UETAA] + e]);
   GDraw ut = gdraw(st.ut[i], N[L.noff[VAR_UTAU] + (long long)s * L.K + k]);
-  float ck = ck_of(h, k);
+  const float ck = st.ck[i];
   float sigma = ue.y * ut.y * ck;
   float du, dsig, dv, dtmp, due, dua, dua2;
   float pu = halfnormal(u.y, sigma, &du, &dsig);                 // poisson.py:247-251
@@ -266,8 +274,8 @@ SPMF_HD DkOut lane_step(LaneState<KK>& st, const Layout& L, const Hyper& h, cons
   float Gy_ua = -h.w_prior * (dua + dua2);
   nparam_bwd(st.u[i], u, eps_u, Gy_u, wer);
   nparam_bwd(st.v[i], v, eps_v, Gy_v, wer);
-  gparam_bwd(st.ue[i], ue, Gy_ue, h.w_entropy);
-  gparam_bwd(st.ua[i], ua, Gy_ua, h.w_entropy);
+  gparam_bwd(st.ue[i], ue, G[L.noff[VAR_UETA] + e], Gy_ue, h.w_entropy);
+  gparam_bwd(st.ua[i], ua, G[L.noff[VAR_UETAA] + e], Gy_ua, h.w_entropy);
   o.da = up.GAp * u.y * ieta;                    // d L / d a_d contribution
   o.dutau = dsig * ue.y * ck;                    // d prior_u / d u_tau[k] contribution
   o.parts[0] = pu; o.parts[1] = pv; o.parts[2] = pue; o.parts[3] = pua;
@@ -280,8 +288,8 @@ SPMF_HD DkOut lane_step(LaneState<KK>& st, const Layout& L, const Hyper& h, cons
 // Gphi = sum over nonzeros of x/lambda (closed-form -B applied here).
 // parts out: W, S, SETA, STAU, SETAA, STAUA, LOGQ
 SPMF_HD void feat_step(FeatState& f, const FeatDraw& fd, const Layout& L, const Hyper& h,
-                       const float* N, const float* eta, int d, int s, float da, float Gphi_nz,
-                       float parts[7]) {
+                       const float* N, const float* G, const float* eta, int d, int s, float da,
+                       float Gphi_nz, float parts[7]) {
   const long long D = L.D;
   float eps_w = N[L.noff[VAR_W] + s * D + d];
   float eps_s0 = N[L.noff[VAR_S] + s * 2 * D + d];
@@ -316,12 +324,12 @@ SPMF_HD void feat_step(FeatState& f, const FeatDraw& fd, const Layout& L, const 
   nparam_bwd(f.w, fd.w, eps_w, -(wpr * dw + dw_data), wer);
   nparam_bwd(f.s0, fd.s0, eps_s0, -(wpr * d_s0 + ds0_data), wer);
   nparam_bwd(f.s1, fd.s1, eps_s1, -(wpr * d_s1 + ds1_data), wer);
-  gparam_bwd(f.se0, se0, -h.w_prior * (dsig0 * st.y + dse0), h.w_entropy);
-  gparam_bwd(f.se1, se1, -h.w_prior * (dsig1 * st.y + dse1), h.w_entropy);
-  gparam_bwd(f.st, st, -h.w_prior * (dsig0 * se0.y + dsig1 * se1.y + dst), h.w_entropy);
-  gparam_bwd(f.sea0, sea0, -h.w_prior * (dsea0 + dsea0b), h.w_entropy);
-  gparam_bwd(f.sea1, sea1, -h.w_prior * (dsea1 + dsea1b), h.w_entropy);
-  gparam_bwd(f.sta, sta, -h.w_prior * (dsta + dstab), h.w_entropy);
+  gparam_bwd(f.se0, se0, G[L.noff[VAR_SETA] + s * 2 * D + d], -h.w_prior * (dsig0 * st.y + dse0), h.w_entropy);
+  gparam_bwd(f.se1, se1, G[L.noff[VAR_SETA] + s * 2 * D + D + d], -h.w_prior * (dsig1 * st.y + dse1), h.w_entropy);
+  gparam_bwd(f.st, st, G[L.noff[VAR_STAU] + s * D + d], -h.w_prior * (dsig0 * se0.y + dsig1 * se1.y + dst), h.w_entropy);
+  gparam_bwd(f.sea0, sea0, G[L.noff[VAR_SETAA] + s * 2 * D + d], -h.w_prior * (dsea0 + dsea0b), h.w_entropy);
+  gparam_bwd(f.sea1, sea1, G[L.noff[VAR_SETAA] + s * 2 * D + D + d], -h.w_prior * (dsea1 + dsea1b), h.w_entropy);
+  gparam_bwd(f.sta, sta, G[L.noff[VAR_STAUA] + s * D + d], -h.w_prior * (dsta + dstab), h.w_entropy);
 
   parts[0] = pw;
   parts[1] = ps0 + ps1;
@@ -341,15 +349,15 @@ SPMF_HD void lat_init(LatState& t, const Layout& L, const float* P, int k) {
   t.ut = gparam_init(P[L.toff[UTAU_C] + k], P[L.toff[UTAU_B] + k]);
   t.uta = gparam_init(P[L.toff[UTAUA_C] + k], P[L.toff[UTAUA_B] + k]);
 }
-SPMF_HD void lat_step(LatState& t, const Layout& L, const Hyper& h, const float* N, int k, int s,
-                      float dutau, float parts[3]) {
+SPMF_HD void lat_step(LatState& t, const Layout& L, const Hyper& h, const float* N, const float* G,
+                      int k, int s, float dutau, float parts[3]) {
   GDraw ut = gdraw(t.ut, N[L.noff[VAR_UTAU] + (long long)s * L.K + k]);
   GDraw uta = gdraw(t.uta, N[L.noff[VAR_UTAUA] + (long long)s * L.K + k]);
   float dut, duta, duta2;
   float put = sqrt_ig_half(ut.y, uta.y, &dut, &duta);           // poisson.py:323-331
   float puta = ig_half(uta.y, h.u_tau_b, &duta2);               // poisson.py:332-341
-  gparam_bwd(t.ut, ut, -h.w_prior * (dutau + dut), h.w_entropy);
-  gparam_bwd(t.uta, uta, -h.w_prior * (duta + duta2), h.w_entropy);
+  gparam_bwd(t.ut, ut, G[L.noff[VAR_UTAU] + (long long)s * L.K + k], -h.w_prior * (dutau + dut), h.w_entropy);
+  gparam_bwd(t.uta, uta, G[L.noff[VAR_UTAUA] + (long long)s * L.K + k], -h.w_prior * (duta + duta2), h.w_entropy);
   parts[0] = put;
   parts[1] = puta;
   parts[2] = glogq(t.ut, ut) + glogq(t.uta, uta);

@@ -58,6 +58,19 @@ __global__ void fill_gamma_kernel(float* __restrict__ out, const float* __restri
                       stream ^ (step * 0x9E3779B9u), k0, k1 ^ step);
 }
 
+// dg/dalpha of every Gamma draw (implicit reparameterisation): depends on (alpha, g) only, so it
+// is evaluated here, fully parallel and off the critical path of the data term.
+__global__ void gamma_grad_kernel(Layout L, const float* __restrict__ P, const float* __restrict__ N,
+                                  float* __restrict__ G) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int v = VAR_UETA + blockIdx.y;
+  const long long n = L.vsize[v] * L.S;
+  if (i >= n) return;
+  const long long e = i % L.vsize[v];
+  const float alpha = softplusf(P[L.toff[2 * v] + e]);
+  G[L.noff[v] + i] = gamma_sample_der_alpha(alpha, N[L.noff[v] + i]);
+}
+
 // ------------------------------------------------------------------ draw -> operands
 template <int KK>
 __global__ void __launch_bounds__(128)
@@ -116,7 +129,7 @@ __global__ void sample_kernel(Layout L, const float* __restrict__ P, const float
 template <int KK>
 __global__ void __launch_bounds__(128)
 backward_feat_kernel(Layout L, Hyper h, const float* __restrict__ P, const float* __restrict__ N,
-                     const float* __restrict__ eta, int SV, int KP,
+                     const float* __restrict__ G, const float* __restrict__ eta, int SV, int KP,
                      const float* __restrict__ GAp, const float* __restrict__ GEVnz,
                      const float* __restrict__ Gphinz, const double* __restrict__ zcolsum,
                      float* __restrict__ grads, float* __restrict__ scr_utau,
@@ -126,7 +139,7 @@ backward_feat_kernel(Layout L, Hyper h, const float* __restrict__ P, const float
   if (d >= L.D) return;
   LaneState<KK> st;
   FeatState f;
-  lane_init<KK>(st, L, P, d, lane);
+  lane_init<KK>(st, L, P, d, lane, h.decay);
   feat_init(f, L, P, d);
   for (int s = 0; s < L.S; ++s) {
     const int q = s / SV, sv = s - q * SV;
@@ -140,7 +153,7 @@ backward_feat_kernel(Layout L, Hyper h, const float* __restrict__ P, const float
         DkUp up;
         up.GAp = GAp[idx];
         up.GEV = GEVnz[idx] - (float)zcolsum[((long long)q * SV + sv) * KP + k];
-        DkOut o = lane_step<KK>(st, L, h, N, eta, d, lane, i, s, fd.a, up);
+        DkOut o = lane_step<KK>(st, L, h, N, G, eta, d, lane, i, s, fd.a, up);
         da += o.da;
         scr_utau[((long long)s * L.D + d) * L.K + k] = o.dutau;
 #pragma unroll
@@ -152,7 +165,7 @@ backward_feat_kernel(Layout L, Hyper h, const float* __restrict__ P, const float
     for (int j = 0; j < 5; ++j) pp[j] = warp_sum(pp[j]);
     if (lane == 0) {
       float fp[7];
-      feat_step(f, fd, L, h, N, eta, d, s, da, Gphinz[((long long)q * L.D + d) * SV + sv], fp);
+      feat_step(f, fd, L, h, N, G, eta, d, s, da, Gphinz[((long long)q * L.D + d) * SV + sv], fp);
       float* o = scr_parts + ((long long)d * L.S + s) * NUM_PARTS;
       o[P_V] = pp[1]; o[P_W] = fp[0]; o[P_U] = pp[0]; o[P_UETA] = pp[2]; o[P_UTAU] = 0.f;
       o[P_SETA] = fp[2]; o[P_STAU] = fp[3]; o[P_S] = fp[1]; o[P_UETAA] = pp[3]; o[P_UTAUA] = 0.f;
@@ -189,7 +202,8 @@ backward_feat_kernel(Layout L, Hyper h, const float* __restrict__ P, const float
 
 // ------------------------------------------------------------------ backward (per latent k)
 __global__ void backward_lat_kernel(Layout L, Hyper h, const float* __restrict__ P,
-                                    const float* __restrict__ N, const double* __restrict__ dutau,
+                                    const float* __restrict__ N, const float* __restrict__ G,
+                                    const double* __restrict__ dutau,
                                     float* __restrict__ grads, float* __restrict__ scr_lat) {
   int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= L.K) return;
@@ -197,7 +211,7 @@ __global__ void backward_lat_kernel(Layout L, Hyper h, const float* __restrict__
   lat_init(t, L, P, k);
   for (int s = 0; s < L.S; ++s) {
     float pp[3];
-    lat_step(t, L, h, N, k, s, (float)dutau[(long long)s * L.K + k], pp);
+    lat_step(t, L, h, N, G, k, s, (float)dutau[(long long)s * L.K + k], pp);
     float* o = scr_lat + ((long long)k * L.S + s) * NUM_PARTS;
     for (int j = 0; j < NUM_PARTS; ++j) o[j] = 0.f;
     o[P_UTAU] = pp[0]; o[P_UTAUA] = pp[1]; o[P_LOGQ] = pp[2];
@@ -398,14 +412,26 @@ int spmf_draw_operands(const float* params, const float* noise, const float* eta
   return reduce_rows<float>(PH, phisum, scratch, D, SV, NQ, st);
 }
 
-int spmf_backward_params(const float* params, const float* noise, const float* eta, int D, int K, int S,
-                         const float* GAp, const float* GEVnz, const float* Gphinz,
+int spmf_gamma_grad(const float* params, const float* noise, int D, int K, int S, float* dgda,
+                    void* stream) {
+  if (!params || !noise || !dgda || D <= 0 || K <= 0 || S <= 0 || K > SPMF_MAX_K) return SPMF_ERR_BAD_ARG;
+  Layout L = make_layout(D, K, S);
+  long long nmax = (long long)D * K * S;
+  if (nmax < 2LL * D * S) nmax = 2LL * D * S;
+  dim3 grid((unsigned)((nmax + 127) / 128), NUM_VARS - VAR_UETA);
+  gamma_grad_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(L, params, noise, dgda);
+  SPMF_CHECK_LAUNCH();
+  return SPMF_OK;
+}
+
+int spmf_backward_params(const float* params, const float* noise, const float* dgda, const float* eta,
+                         int D, int K, int S, const float* GAp, const float* GEVnz, const float* Gphinz,
                          const double* zcolsum, const double* datasums, const double* phisum,
                          float batch_rows, float u_tau_scale, float s_tau_scale,
                          float decay, float w_entropy, float w_prior, int world_size, float* grads,
                          double* parts, float* scr_f, double* scr_d, void* stream) {
-  if (!params || !noise || !eta || !GAp || !GEVnz || !Gphinz || !zcolsum || !datasums || !phisum ||
-      !grads || !parts || !scr_f || !scr_d)
+  if (!params || !noise || !dgda || !eta || !GAp || !GEVnz || !Gphinz || !zcolsum || !datasums ||
+      !phisum || !grads || !parts || !scr_f || !scr_d)
     return SPMF_ERR_BAD_ARG;
   if (D <= 0 || K <= 0 || S <= 0 || K > SPMF_MAX_K || world_size <= 0) return SPMF_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
@@ -422,15 +448,15 @@ int spmf_backward_params(const float* params, const float* noise, const float* e
   double* latparts = featparts + (long long)S * NUM_PARTS;
   double* rscr = latparts + (long long)S * NUM_PARTS;
   dim3 grid((D + 3) / 4);
-  if (KP <= 32) backward_feat_kernel<1><<<grid, 128, 0, st>>>(L, h, params, noise, eta, SV, KP, GAp, GEVnz, Gphinz, zcolsum, grads, scr_utau, scr_parts);
-  else if (KP <= 64) backward_feat_kernel<2><<<grid, 128, 0, st>>>(L, h, params, noise, eta, SV, KP, GAp, GEVnz, Gphinz, zcolsum, grads, scr_utau, scr_parts);
-  else backward_feat_kernel<4><<<grid, 128, 0, st>>>(L, h, params, noise, eta, SV, KP, GAp, GEVnz, Gphinz, zcolsum, grads, scr_utau, scr_parts);
+  if (KP <= 32) backward_feat_kernel<1><<<grid, 128, 0, st>>>(L, h, params, noise, dgda, eta, SV, KP, GAp, GEVnz, Gphinz, zcolsum, grads, scr_utau, scr_parts);
+  else if (KP <= 64) backward_feat_kernel<2><<<grid, 128, 0, st>>>(L, h, params, noise, dgda, eta, SV, KP, GAp, GEVnz, Gphinz, zcolsum, grads, scr_utau, scr_parts);
+  else backward_feat_kernel<4><<<grid, 128, 0, st>>>(L, h, params, noise, dgda, eta, SV, KP, GAp, GEVnz, Gphinz, zcolsum, grads, scr_utau, scr_parts);
   SPMF_CHECK_LAUNCH();
   int rc = reduce_rows<float>(scr_utau, dutau, rscr, D, K, S, st);
   if (rc) return rc;
   rc = reduce_rows<float>(scr_parts, featparts, rscr, D, S * NUM_PARTS, 1, st);
   if (rc) return rc;
-  backward_lat_kernel<<<(K + 63) / 64, 64, 0, st>>>(L, h, params, noise, dutau, grads, scr_lat);
+  backward_lat_kernel<<<(K + 63) / 64, 64, 0, st>>>(L, h, params, noise, dgda, dutau, grads, scr_lat);
   SPMF_CHECK_LAUNCH();
   rc = reduce_rows<float>(scr_lat, latparts, rscr, K, S * NUM_PARTS, 1, st);
   if (rc) return rc;

@@ -79,6 +79,7 @@ class AdviEngine:
         self.adam_m = torch.zeros_like(self.params)
         self.adam_v = torch.zeros_like(self.params)
         self.noise = torch.empty(L.n_noise, dtype=torch.float32, device=self.device)
+        self.dgda = torch.zeros(L.n_noise, dtype=torch.float32, device=self.device)
         self.eta = torch.ones(D, dtype=torch.float32, device=self.device)
         self.inv_xi = 1.0
         self._ws = None
@@ -137,10 +138,15 @@ class AdviEngine:
             ev.setdefault("csc_cols", []).append((e2, e3, b.nnz, b.nrows))
         self.launches += 1 + 4 + 1 + 3   # rows, 4 reduce launches, cols (+3 memsets)
 
+    def gamma_grad(self):
+        _abi.call("spmf_gamma_grad", _ptr(self.params), _ptr(self.noise), self.D, self.K, self.S,
+                  _ptr(self.dgda), _stream())
+        self.launches += 1
+
     def backward_params(self, batch_rows):
         w = self.ws
-        _abi.call("spmf_backward_params", _ptr(self.params), _ptr(self.noise), _ptr(self.eta), self.D,
-                  self.K, self.S, _ptr(w.GAp), _ptr(w.GEV), _ptr(w.Gph), _ptr(w.zcolsum),
+        _abi.call("spmf_backward_params", _ptr(self.params), _ptr(self.noise), _ptr(self.dgda),
+                  _ptr(self.eta), self.D, self.K, self.S, _ptr(w.GAp), _ptr(w.GEV), _ptr(w.Gph), _ptr(w.zcolsum),
                   _ptr(w.datasums), _ptr(w.phisum), float(batch_rows), self.u_tau_scale,
                   self.s_tau_scale, self.decay, self.entropy_weight, self.prior_weight,
                   self.world_size, _ptr(self.grads), _ptr(w.parts), _ptr(w.scr_f), _ptr(w.scr_d),
@@ -166,6 +172,8 @@ class AdviEngine:
         if fresh_noise:
             self.fill_noise()
             t = self._mark("fill_noise", t)
+        self.gamma_grad()
+        t = self._mark("gamma_grad", t)
         self.draw_operands()
         t = self._mark("draw_operands", t)
         self.data_term(batch, variant)

@@ -86,13 +86,21 @@ void hc_backward_params(const float* P, const float* N, const float* eta, int D,
   h.decay = decay; h.w_entropy = w_entropy; h.w_prior = w_prior;
   h.rep_scale = 1.f / (float)world; h.batch_rows = batch_rows;
   std::vector<double> dutau((size_t)S * K, 0.0);
+  // dg/dalpha of every Gamma draw, as gamma_grad_kernel computes it
+  std::vector<float> Gv((size_t)L.noff[NUM_VARS], 0.f);
+  for (int v = VAR_UETA; v < NUM_VARS; ++v)
+    for (long long i = 0; i < L.vsize[v] * S; ++i) {
+      long long e = i % L.vsize[v];
+      Gv[L.noff[v] + i] = gamma_sample_der_alpha(softplusf(P[L.toff[2 * v] + e]), N[L.noff[v] + i]);
+    }
+  const float* G = Gv.data();
   std::memset(parts, 0, sizeof(double) * S * NUM_PARTS);
   const float invS = 1.f / (float)S;
   const float wer = h.w_entropy * h.rep_scale;
   for (int d = 0; d < D; ++d) {
     LaneState<4> st[32];
     FeatState f;
-    for (int lane = 0; lane < 32; ++lane) lane_init<4>(st[lane], L, P, d, lane);
+    for (int lane = 0; lane < 32; ++lane) lane_init<4>(st[lane], L, P, d, lane, h.decay);
     feat_init(f, L, P, d);
     for (int s = 0; s < S; ++s) {
       FeatDraw fd = feat_draw(f, L, N, d, s);
@@ -103,14 +111,14 @@ void hc_backward_params(const float* P, const float* N, const float* eta, int D,
           if (k < K) {
             long long idx = ((long long)s * D + d) * K + k;
             DkUp up{GAp[idx], GEV[idx]};
-            DkOut o = lane_step<4>(st[lane], L, h, N, eta, d, lane, i, s, fd.a, up);
+            DkOut o = lane_step<4>(st[lane], L, h, N, G, eta, d, lane, i, s, fd.a, up);
             da += o.da;
             dutau[(size_t)s * K + k] += o.dutau;
             for (int j = 0; j < 5; ++j) pp[j] += o.parts[j];
           }
         }
       float fp[7];
-      feat_step(f, fd, L, h, N, eta, d, s, da, Gphinz[(long long)s * D + d], fp);
+      feat_step(f, fd, L, h, N, G, eta, d, s, da, Gphinz[(long long)s * D + d], fp);
       double* o = parts + (size_t)s * NUM_PARTS;
       o[P_U] += pp[0]; o[P_V] += pp[1]; o[P_UETA] += pp[2]; o[P_UETAA] += pp[3];
       o[P_W] += fp[0]; o[P_S] += fp[1]; o[P_SETA] += fp[2]; o[P_STAU] += fp[3];
@@ -142,7 +150,7 @@ void hc_backward_params(const float* P, const float* N, const float* eta, int D,
     lat_init(t, L, P, k);
     for (int s = 0; s < S; ++s) {
       float pp[3];
-      lat_step(t, L, h, N, k, s, (float)dutau[(size_t)s * K + k], pp);
+      lat_step(t, L, h, N, G, k, s, (float)dutau[(size_t)s * K + k], pp);
       double* o = parts + (size_t)s * NUM_PARTS;
       o[P_UTAU] += pp[0]; o[P_UTAUA] += pp[1]; o[P_LOGQ] += pp[2];
     }
