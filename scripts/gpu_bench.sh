@@ -15,6 +15,6 @@ echo "ncu list rc=$?"
 if [ "$2" == "full" ]; then
 $CMD > gpurun_out/plain.log 2>&1 &&
 ncu --set full --clock-control none --import-source on --nvtx --nvtx-include "spmf_timed/" \
-    -k regex:'csr_rows_kernel|csc_cols_kernel|backward_feat_kernel|gamma_grad_kernel' -c 8 -f -o gpurun_out/prof_$TAG $CMD > gpurun_out/ncu_full.log 2>&1
+    -k regex:'csr_rows_kernel|csc_cols_kernel|backward_dk_kernel|backward_feat_kernel|gamma_grad_kernel' -c 10 -f -o gpurun_out/prof_$TAG $CMD > gpurun_out/ncu_full.log 2>&1
 echo "ncu full rc=$?"; tail -3 gpurun_out/ncu_full.log
 fi

@@ -63,7 +63,7 @@ SPMF_HD float gamma_sample_der_alpha(float a, float x) {
       H += inv;
       sT += T;
       sTH += T * H;
-      if (T * (1.f + H) < 1e-9f * sT) break;
+      if (T * (1.f + H) < 1e-7f * sT) break;
     }
     return (x / a) * (sTH - (logf(x) - digammaf_pos(a + 1.f)) * sT);
   }
@@ -94,7 +94,7 @@ SPMF_HD float gamma_sample_der_alpha(float a, float x) {
       pkm2 *= sc; pkm1 *= sc; qkm2 *= sc; qkm1 *= sc;
       dpkm2 *= sc; dpkm1 *= sc; dqkm2 *= sc; dqkm1 *= sc;
     }
-    if (delta < 2e-8f * scale && c > 3) break;
+    if (delta < 1e-6f * scale && c > 3) break;
   }
   return x * (dans + ans * (logf(x) - digammaf_pos(a)));
 }

@@ -125,25 +125,30 @@ __global__ void sample_kernel(Layout L, const float* __restrict__ P, const float
   }
 }
 
-// ------------------------------------------------------------------ backward (per feature)
+// ------------------------------------------------------------------ backward, (d,k)-shaped tensors
+// One warp per feature d, lanes over k: u, v, u_eta, u_eta_a.  Emits da[s][d] = sum_k GA' u / eta
+// (needed by the per-feature kernel), the per-(s,d,k) contribution to d prior_u / d u_tau, and
+// this feature's share of the prior / log q sums.
 template <int KK>
 __global__ void __launch_bounds__(128)
-backward_feat_kernel(Layout L, Hyper h, const float* __restrict__ P, const float* __restrict__ N,
-                     const float* __restrict__ G, const float* __restrict__ eta, int SV, int KP,
-                     const float* __restrict__ GAp, const float* __restrict__ GEVnz,
-                     const float* __restrict__ Gphinz, const double* __restrict__ zcolsum,
-                     float* __restrict__ grads, float* __restrict__ scr_utau,
-                     float* __restrict__ scr_parts) {
+backward_dk_kernel(Layout L, Hyper h, const float* __restrict__ P, const float* __restrict__ N,
+                   const float* __restrict__ G, const float* __restrict__ eta, int SV, int KP,
+                   const float* __restrict__ GAp, const float* __restrict__ GEVnz,
+                   const double* __restrict__ zcolsum, float* __restrict__ grads,
+                   float* __restrict__ scr_utau, float* __restrict__ scr_parts,
+                   float* __restrict__ scr_da) {
   const int lane = threadIdx.x & 31;
   const int d = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (d >= L.D) return;
   LaneState<KK> st;
-  FeatState f;
   lane_init<KK>(st, L, P, d, lane, h.decay);
-  feat_init(f, L, P, d);
+  const NParam s0 = nparam_init(P[L.toff[S_LOC] + d], P[L.toff[S_RHO] + d]);
+  const NParam s1 = nparam_init(P[L.toff[S_LOC] + L.D + d], P[L.toff[S_RHO] + L.D + d]);
   for (int s = 0; s < L.S; ++s) {
     const int q = s / SV, sv = s - q * SV;
-    FeatDraw fd = feat_draw(f, L, N, d, s);
+    const float y0 = ndraw(s0, N[L.noff[VAR_S] + (long long)s * 2 * L.D + d]).y;
+    const float y1 = ndraw(s1, N[L.noff[VAR_S] + (long long)s * 2 * L.D + L.D + d]).y;
+    const float a_d = y0 / (y0 + y1);                       // poisson.py:661-663
     float da = 0.f, pp[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int i = 0; i < KK; ++i) {
@@ -153,7 +158,7 @@ backward_feat_kernel(Layout L, Hyper h, const float* __restrict__ P, const float
         DkUp up;
         up.GAp = GAp[idx];
         up.GEV = GEVnz[idx] - (float)zcolsum[((long long)q * SV + sv) * KP + k];
-        DkOut o = lane_step<KK>(st, L, h, N, G, eta, d, lane, i, s, fd.a, up);
+        DkOut o = lane_step<KK>(st, L, h, N, G, eta, d, lane, i, s, a_d, up);
         da += o.da;
         scr_utau[((long long)s * L.D + d) * L.K + k] = o.dutau;
 #pragma unroll
@@ -164,13 +169,11 @@ backward_feat_kernel(Layout L, Hyper h, const float* __restrict__ P, const float
 #pragma unroll
     for (int j = 0; j < 5; ++j) pp[j] = warp_sum(pp[j]);
     if (lane == 0) {
-      float fp[7];
-      feat_step(f, fd, L, h, N, G, eta, d, s, da, Gphinz[((long long)q * L.D + d) * SV + sv], fp);
+      scr_da[(long long)s * L.D + d] = da;
       float* o = scr_parts + ((long long)d * L.S + s) * NUM_PARTS;
-      o[P_V] = pp[1]; o[P_W] = fp[0]; o[P_U] = pp[0]; o[P_UETA] = pp[2]; o[P_UTAU] = 0.f;
-      o[P_SETA] = fp[2]; o[P_STAU] = fp[3]; o[P_S] = fp[1]; o[P_UETAA] = pp[3]; o[P_UTAUA] = 0.f;
-      o[P_SETAA] = fp[4]; o[P_STAUA] = fp[5]; o[P_LOGQ] = pp[4] + fp[6];
-      o[P_Z] = 0.f; o[P_X] = 0.f; o[15] = 0.f;
+#pragma unroll
+      for (int j = 0; j < NUM_PARTS; ++j) o[j] = 0.f;
+      o[P_U] = pp[0]; o[P_V] = pp[1]; o[P_UETA] = pp[2]; o[P_UETAA] = pp[3]; o[P_LOGQ] = pp[4];
     }
   }
   const float invS = 1.f / (float)L.S;
@@ -186,18 +189,41 @@ backward_feat_kernel(Layout L, Hyper h, const float* __restrict__ P, const float
       gparam_finish(st.ua[i], P[L.toff[UETAA_C] + e], P[L.toff[UETAA_B] + e], invS, &grads[L.toff[UETAA_C] + e], &grads[L.toff[UETAA_B] + e]);
     }
   }
-  if (lane == 0) {
-    const int D = L.D;
-    nparam_finish(f.w, P[L.toff[W_RHO] + d], invS, wer, &grads[L.toff[W_LOC] + d], &grads[L.toff[W_RHO] + d]);
-    nparam_finish(f.s0, P[L.toff[S_RHO] + d], invS, wer, &grads[L.toff[S_LOC] + d], &grads[L.toff[S_RHO] + d]);
-    nparam_finish(f.s1, P[L.toff[S_RHO] + D + d], invS, wer, &grads[L.toff[S_LOC] + D + d], &grads[L.toff[S_RHO] + D + d]);
-    gparam_finish(f.se0, P[L.toff[SETA_C] + d], P[L.toff[SETA_B] + d], invS, &grads[L.toff[SETA_C] + d], &grads[L.toff[SETA_B] + d]);
-    gparam_finish(f.se1, P[L.toff[SETA_C] + D + d], P[L.toff[SETA_B] + D + d], invS, &grads[L.toff[SETA_C] + D + d], &grads[L.toff[SETA_B] + D + d]);
-    gparam_finish(f.st, P[L.toff[STAU_C] + d], P[L.toff[STAU_B] + d], invS, &grads[L.toff[STAU_C] + d], &grads[L.toff[STAU_B] + d]);
-    gparam_finish(f.sea0, P[L.toff[SETAA_C] + d], P[L.toff[SETAA_B] + d], invS, &grads[L.toff[SETAA_C] + d], &grads[L.toff[SETAA_B] + d]);
-    gparam_finish(f.sea1, P[L.toff[SETAA_C] + D + d], P[L.toff[SETAA_B] + D + d], invS, &grads[L.toff[SETAA_C] + D + d], &grads[L.toff[SETAA_B] + D + d]);
-    gparam_finish(f.sta, P[L.toff[STAUA_C] + d], P[L.toff[STAUA_B] + d], invS, &grads[L.toff[STAUA_C] + d], &grads[L.toff[STAUA_B] + d]);
+}
+
+// ------------------------------------------------------------------ backward, per-feature tensors
+// One thread per feature d: w, s, s_eta, s_tau, s_eta_a, s_tau_a (runs after backward_dk_kernel).
+__global__ void __launch_bounds__(128)
+backward_feat_kernel(Layout L, Hyper h, const float* __restrict__ P, const float* __restrict__ N,
+                     const float* __restrict__ G, const float* __restrict__ eta, int SV,
+                     const float* __restrict__ Gphinz, const float* __restrict__ scr_da,
+                     float* __restrict__ grads, float* __restrict__ scr_parts) {
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= L.D) return;
+  FeatState f;
+  feat_init(f, L, P, d);
+  for (int s = 0; s < L.S; ++s) {
+    const int q = s / SV, sv = s - q * SV;
+    FeatDraw fd = feat_draw(f, L, N, d, s);
+    float fp[7];
+    feat_step(f, fd, L, h, N, G, eta, d, s, scr_da[(long long)s * L.D + d],
+              Gphinz[((long long)q * L.D + d) * SV + sv], fp);
+    float* o = scr_parts + ((long long)d * L.S + s) * NUM_PARTS;
+    o[P_W] = fp[0]; o[P_S] = fp[1]; o[P_SETA] = fp[2]; o[P_STAU] = fp[3];
+    o[P_SETAA] = fp[4]; o[P_STAUA] = fp[5]; o[P_LOGQ] += fp[6];
   }
+  const float invS = 1.f / (float)L.S;
+  const float wer = h.w_entropy * h.rep_scale;
+  const int D = L.D;
+  nparam_finish(f.w, P[L.toff[W_RHO] + d], invS, wer, &grads[L.toff[W_LOC] + d], &grads[L.toff[W_RHO] + d]);
+  nparam_finish(f.s0, P[L.toff[S_RHO] + d], invS, wer, &grads[L.toff[S_LOC] + d], &grads[L.toff[S_RHO] + d]);
+  nparam_finish(f.s1, P[L.toff[S_RHO] + D + d], invS, wer, &grads[L.toff[S_LOC] + D + d], &grads[L.toff[S_RHO] + D + d]);
+  gparam_finish(f.se0, P[L.toff[SETA_C] + d], P[L.toff[SETA_B] + d], invS, &grads[L.toff[SETA_C] + d], &grads[L.toff[SETA_B] + d]);
+  gparam_finish(f.se1, P[L.toff[SETA_C] + D + d], P[L.toff[SETA_B] + D + d], invS, &grads[L.toff[SETA_C] + D + d], &grads[L.toff[SETA_B] + D + d]);
+  gparam_finish(f.st, P[L.toff[STAU_C] + d], P[L.toff[STAU_B] + d], invS, &grads[L.toff[STAU_C] + d], &grads[L.toff[STAU_B] + d]);
+  gparam_finish(f.sea0, P[L.toff[SETAA_C] + d], P[L.toff[SETAA_B] + d], invS, &grads[L.toff[SETAA_C] + d], &grads[L.toff[SETAA_B] + d]);
+  gparam_finish(f.sea1, P[L.toff[SETAA_C] + D + d], P[L.toff[SETAA_B] + D + d], invS, &grads[L.toff[SETAA_C] + D + d], &grads[L.toff[SETAA_B] + D + d]);
+  gparam_finish(f.sta, P[L.toff[STAUA_C] + d], P[L.toff[STAUA_B] + d], invS, &grads[L.toff[STAUA_C] + d], &grads[L.toff[STAUA_B] + d]);
 }
 
 // ------------------------------------------------------------------ backward (per latent k)
@@ -438,7 +464,7 @@ int spmf_backward_params(const float* params, const float* noise, const float* d
   Layout L = make_layout(D, K, S);
   Hyper h = make_hyper(u_tau_scale, s_tau_scale, decay, w_entropy, w_prior, world_size, batch_rows);
   const int KP = spmf_kpad(K), SV = spmf_draw_vec(S);
-  // float scratch: scr_utau [S][D][K] | scr_parts [D][S*16] | scr_lat [K][S*16]
+  // float scratch: scr_utau [S][D][K] | scr_parts [D][S*16] | scr_lat [K][S*16] | scr_da [S][D]
   float* scr_utau = scr_f;
   float* scr_parts = scr_utau + (long long)S * D * K;
   float* scr_lat = scr_parts + (long long)D * S * NUM_PARTS;
@@ -447,10 +473,12 @@ int spmf_backward_params(const float* params, const float* noise, const float* d
   double* featparts = dutau + (long long)S * K;
   double* latparts = featparts + (long long)S * NUM_PARTS;
   double* rscr = latparts + (long long)S * NUM_PARTS;
+  float* scr_da = scr_lat + (long long)K * S * NUM_PARTS;
   dim3 grid((D + 3) / 4);
-  if (KP <= 32) backward_feat_kernel<1><<<grid, 128, 0, st>>>(L, h, params, noise, dgda, eta, SV, KP, GAp, GEVnz, Gphinz, zcolsum, grads, scr_utau, scr_parts);
-  else if (KP <= 64) backward_feat_kernel<2><<<grid, 128, 0, st>>>(L, h, params, noise, dgda, eta, SV, KP, GAp, GEVnz, Gphinz, zcolsum, grads, scr_utau, scr_parts);
-  else backward_feat_kernel<4><<<grid, 128, 0, st>>>(L, h, params, noise, dgda, eta, SV, KP, GAp, GEVnz, Gphinz, zcolsum, grads, scr_utau, scr_parts);
+  if (KP <= 32) backward_dk_kernel<1><<<grid, 128, 0, st>>>(L, h, params, noise, dgda, eta, SV, KP, GAp, GEVnz, zcolsum, grads, scr_utau, scr_parts, scr_da);
+  else if (KP <= 64) backward_dk_kernel<2><<<grid, 128, 0, st>>>(L, h, params, noise, dgda, eta, SV, KP, GAp, GEVnz, zcolsum, grads, scr_utau, scr_parts, scr_da);
+  else backward_dk_kernel<4><<<grid, 128, 0, st>>>(L, h, params, noise, dgda, eta, SV, KP, GAp, GEVnz, zcolsum, grads, scr_utau, scr_parts, scr_da);
+  backward_feat_kernel<<<(D + 127) / 128, 128, 0, st>>>(L, h, params, noise, dgda, eta, SV, Gphinz, scr_da, grads, scr_parts);
   SPMF_CHECK_LAUNCH();
   int rc = reduce_rows<float>(scr_utau, dutau, rscr, D, K, S, st);
   if (rc) return rc;
@@ -469,7 +497,7 @@ int spmf_backward_params(const float* params, const float* noise, const float* d
 }
 
 long long spmf_backward_scratch_floats(int D, int K, int S) {
-  return (long long)S * D * K + (long long)D * S * NUM_PARTS + (long long)K * S * NUM_PARTS;
+  return (long long)S * D * K + (long long)D * S * NUM_PARTS + (long long)K * S * NUM_PARTS + (long long)S * D;
 }
 long long spmf_backward_scratch_doubles(int D, int K, int S) {
   long long c = (long long)S * NUM_PARTS;

@@ -123,17 +123,38 @@ csr_rows_kernel(const long long* __restrict__ rowptr, const int* __restrict__ co
   for (int i = 0; i < VPL; ++i)
 #pragma unroll
     for (int w = 0; w < VW; ++w) zz[i][w] = 0.f;
-#pragma unroll 4
-  for (long long j = j0 + slot; j < j1; j += NSLOT) {
-    const int d = __ldg(cols + j);
-    const float x = __ldg(vals + j);
-    const float* rec = Apq + (long long)d * REC;
+  // Software pipeline: U nonzeros per slot in flight; the (col,val) pairs of the next batch are
+  // fetched while the current batch's records are being gathered (two dependent L2 latencies).
+  constexpr int U = VPL >= 4 ? 2 : 4;
+  int dcur[U];
+  float xcur[U];
+  auto load_idx = [&](long long jb, int (&dd)[U], float (&xx)[U]) {
 #pragma unroll
-    for (int i = 0; i < VPL; ++i) {
-      float a[VW];
-      ldv<VW>(a, rec + off[i]);
+    for (int u = 0; u < U; ++u) {
+      const long long j = jb + (long long)u * NSLOT;
+      const bool ok = j < j1;
+      dd[u] = ok ? __ldg(cols + j) : 0;
+      xx[u] = ok ? __ldg(vals + j) : 0.f;      // x = 0 neutralises a padded lane
+    }
+  };
+  load_idx(j0 + slot, dcur, xcur);
+  for (long long jb = j0 + slot; jb < j1; jb += (long long)U * NSLOT) {
+    float a[U][VPL][VW];
 #pragma unroll
-      for (int w = 0; w < VW; ++w) zz[i][w] = fmaf(x, a[w], zz[i][w]);
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) ldv<VW>(a[u][i], Apq + (long long)dcur[u] * REC + off[i]);
+    int dn[U];
+    float xn[U];
+    load_idx(jb + (long long)U * NSLOT, dn, xn);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+#pragma unroll
+      for (int i = 0; i < VPL; ++i)
+#pragma unroll
+        for (int w = 0; w < VW; ++w) zz[i][w] = fmaf(xcur[u], a[u][i][w], zz[i][w]);
+      dcur[u] = dn[u];
+      xcur[u] = xn[u];
     }
   }
   if constexpr (NSLOT > 1) {
@@ -171,31 +192,45 @@ csr_rows_kernel(const long long* __restrict__ rowptr, const int* __restrict__ co
   for (int i = 0; i < VPL; ++i)
 #pragma unroll
     for (int w = 0; w < VW; ++w) dz[i][w] = 0.f;
-#pragma unroll 2
-  for (long long j = j0 + slot; j < j1; j += NSLOT) {
-    const int d = __ldg(cols + j);
-    const float x = __ldg(vals + j);
-    const float* rec = EVq + (long long)d * REC;
-    const float ph = __ldg(PHq + (long long)d * SV + s);
-    float e[VPL][VW];
-    float p = 0.f;
+  load_idx(j0 + slot, dcur, xcur);
+  for (long long jb = j0 + slot; jb < j1; jb += (long long)U * NSLOT) {
+    float e[U][VPL][VW], ph[U], p[U];
 #pragma unroll
-    for (int i = 0; i < VPL; ++i) {
-      ldv<VW>(e[i], rec + off[i]);
+    for (int u = 0; u < U; ++u) {
 #pragma unroll
-      for (int w = 0; w < VW; ++w) p = fmaf(zz[i][w], e[i][w], p);
+      for (int i = 0; i < VPL; ++i) ldv<VW>(e[u][i], EVq + (long long)dcur[u] * REC + off[i]);
+      ph[u] = __ldg(PHq + (long long)dcur[u] * SV + s);
     }
-    const float lam = group_sum<RG>(p, gmask) + ph;          // poisson.py:177
-    const float t = x * __logf(lam);
-    const float gq = __fdividef(x, lam);
-    if (isfinite(t) && isfinite(gq)) {
-      xlog += t;
+    int dn[U];
+    float xn[U];
+    load_idx(jb + (long long)U * NSLOT, dn, xn);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      p[u] = 0.f;
 #pragma unroll
       for (int i = 0; i < VPL; ++i)
 #pragma unroll
-        for (int w = 0; w < VW; ++w) dz[i][w] = fmaf(gq, e[i][w], dz[i][w]);
-    } else {
-      bad += 1.f;   // reported through rowacc slot 3 (guard of poisson.py:606-616)
+        for (int w = 0; w < VW; ++w) p[u] = fmaf(zz[i][w], e[u][i][w], p[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) p[u] = group_sum<RG>(p[u], gmask);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const bool valid = jb + (long long)u * NSLOT < j1;
+      const float x = xcur[u];
+      const float lam = p[u] + ph[u];                        // poisson.py:177
+      const float t = x * __logf(lam);
+      float gq = __fdividef(x, lam);
+      const bool ok = isfinite(t) && isfinite(gq);
+      xlog += (valid && ok) ? t : 0.f;
+      bad += (valid && !ok) ? 1.f : 0.f;   // reported through rowacc slot 3 (guard of poisson.py:606-616)
+      gq = (valid && ok) ? gq : 0.f;
+#pragma unroll
+      for (int i = 0; i < VPL; ++i)
+#pragma unroll
+        for (int w = 0; w < VW; ++w) dz[i][w] = fmaf(gq, e[u][i][w], dz[i][w]);
+      dcur[u] = dn[u];
+      xcur[u] = xn[u];
     }
   }
   if constexpr (NSLOT > 1) {
@@ -319,40 +354,63 @@ csc_cols_kernel(const int* __restrict__ colptr, const int* __restrict__ rows,
   };
   load_col(d);
   int pending = 0;
-#pragma unroll 2
-  for (int j = j0; j < j1; ++j) {
-    if (j >= next) {
-      if (pending) flush_col(d);
-      pending = 0;
-      do {
-        ++d;
-        next = __ldg(colptr + d + 1);
-      } while (j >= next);
-      load_col(d);
-    }
-    const int b = __ldg(rows + j);
-    const float x = __ldg(vals + j);
-    float zz[VPL][VW], dd[VPL][VW];
-    float p = 0.f;
+  constexpr int U = VPL >= 4 ? 2 : 4;
+  for (int jb = j0; jb < j1; jb += U) {
+    int bb[U];
+    float xx[U];
+    if (U == 4 && jb + 4 <= j1) {                 // slices start 256-aligned: 16-byte vector loads
+      const int4 b4 = __ldg(reinterpret_cast<const int4*>(rows + jb));
+      const float4 x4 = __ldg(reinterpret_cast<const float4*>(vals + jb));
+      bb[0] = b4.x; bb[1] = b4.y; bb[U - 2] = b4.z; bb[U - 1] = b4.w;
+      xx[0] = x4.x; xx[1] = x4.y; xx[U - 2] = x4.z; xx[U - 1] = x4.w;
+    } else {
 #pragma unroll
-    for (int i = 0; i < VPL; ++i) {
-      ldv<VW>(zz[i], zq + (long long)b * REC + off[i]);
-      ldv<VW>(dd[i], dq + (long long)b * REC + off[i]);
-#pragma unroll
-      for (int w = 0; w < VW; ++w) p = fmaf(zz[i][w], ev[i][w], p);
-    }
-    const float lam = group_sum<RG>(p, gmask) + ph;
-    float gq = __fdividef(x, lam);
-    if (!isfinite(gq) || !isfinite(__logf(lam))) gq = 0.f;   // same entries the row pass dropped
-    aPh += gq;
-#pragma unroll
-    for (int i = 0; i < VPL; ++i)
-#pragma unroll
-      for (int w = 0; w < VW; ++w) {
-        aEV[i][w] = fmaf(gq, zz[i][w], aEV[i][w]);
-        aAp[i][w] = fmaf(x, dd[i][w], aAp[i][w]);
+      for (int u = 0; u < U; ++u) {
+        const bool ok = jb + u < j1;
+        bb[u] = ok ? __ldg(rows + jb + u) : 0;
+        xx[u] = ok ? __ldg(vals + jb + u) : 0.f;
       }
-    pending = 1;
+    }
+    float zz[U][VPL][VW], dd[U][VPL][VW];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) {
+        ldv<VW>(zz[u][i], zq + (long long)bb[u] * REC + off[i]);
+        ldv<VW>(dd[u][i], dq + (long long)bb[u] * REC + off[i]);
+      }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int j = jb + u;
+      if (j < j1) {
+        if (j >= next) {
+          if (pending) flush_col(d);
+          pending = 0;
+          do {
+            ++d;
+            next = __ldg(colptr + d + 1);
+          } while (j >= next);
+          load_col(d);
+        }
+        float p = 0.f;
+#pragma unroll
+        for (int i = 0; i < VPL; ++i)
+#pragma unroll
+          for (int w = 0; w < VW; ++w) p = fmaf(zz[u][i][w], ev[i][w], p);
+        const float lam = group_sum<RG>(p, gmask) + ph;
+        float gq = __fdividef(xx[u], lam);
+        if (!isfinite(gq) || !isfinite(__logf(lam))) gq = 0.f;   // same entries the row pass dropped
+        aPh += gq;
+#pragma unroll
+        for (int i = 0; i < VPL; ++i)
+#pragma unroll
+          for (int w = 0; w < VW; ++w) {
+            aEV[i][w] = fmaf(gq, zz[u][i][w], aEV[i][w]);
+            aAp[i][w] = fmaf(xx[u], dd[u][i][w], aAp[i][w]);
+          }
+        pending = 1;
+      }
+    }
   }
   if (pending) flush_col(d);
 }

@@ -151,7 +151,7 @@ class AdviEngine:
                   self.s_tau_scale, self.decay, self.entropy_weight, self.prior_weight,
                   self.world_size, _ptr(self.grads), _ptr(w.parts), _ptr(w.scr_f), _ptr(w.scr_d),
                   _stream())
-        self.launches += 8
+        self.launches += 9
 
     def _mark(self, name, start):
         """Phase timing hook (bench): CUDA events on the launching stream around a phase."""
