@@ -91,6 +91,25 @@ __device__ __forceinline__ unsigned slot_mask(int lane) {
 // ------------------------------------------------------------------ row pass
 // One CTA per row, NSLOT slots striding over the row's nonzeros; slot partials meet in shared
 // memory.  z stays in registers between the two sweeps; the rate matrix is never written.
+// Hot loops use 32-bit row-local indices, U nonzeros per slot in flight, and fetch the next
+// batch's (col,val) pairs while the current records are gathered.
+
+// rate guard (poisson.py:606-616): an entry whose rate is not a positive finite number has a
+// non-finite log-likelihood; it is dropped from value and gradient and counted.
+__device__ __forceinline__ bool rate_ok(float lam) { return lam > 0.f && lam <= 3.402823466e38f; }
+// single-MUFU log2 / reciprocal (flush-to-zero forms: no subnormal fix-up code in the hot loop;
+// a rate is a sum of positive terms >= phi and never subnormal)
+__device__ __forceinline__ float fast_lg2(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float fast_rcp(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 template <int KP, int SV, bool ENCODE_ONLY>
 __global__ void __launch_bounds__(128)
 csr_rows_kernel(const long long* __restrict__ rowptr, const int* __restrict__ cols,
@@ -101,6 +120,7 @@ csr_rows_kernel(const long long* __restrict__ rowptr, const int* __restrict__ co
                 float* __restrict__ z, float* __restrict__ dzr, float* __restrict__ rowacc) {
   using M = Map<KP, SV>;
   constexpr int VW = M::VW, LPN = M::LPN, RG = M::RG, VPL = M::VPL, REC = M::REC, NSLOT = M::NSLOT;
+  constexpr int U = VPL >= 4 ? 2 : 4;
   __shared__ __align__(16) float part[NSLOT * REC];
   __shared__ float sc[NSLOT][SV][2];
   const int lane = threadIdx.x & 31;
@@ -113,48 +133,66 @@ csr_rows_kernel(const long long* __restrict__ rowptr, const int* __restrict__ co
 #pragma unroll
   for (int i = 0; i < VPL; ++i) off[i] = s * KP + (i * RG + kg) * VW;
 
-  const float* Apq = Ap + (long long)q * D * REC;
-  const long long j0 = rowptr[row], j1 = rowptr[row + 1];
+  const long long j0 = rowptr[row];
+  const int n = (int)(rowptr[row + 1] - j0);
+  const int* __restrict__ rc = cols + j0;          // row-local views: 32-bit indexing below
+  const float* __restrict__ rv = vals + j0;
+  const int cnt = slot < n ? (n - slot + NSLOT - 1) / NSLOT : 0;   // nonzeros of this slot
+  const int nb = cnt / U;                                          // full batches
   const float r = scale_rows ? rowsum[row] * inv_xi : 1.f;   // poisson.py:644-649
 
   // ---- z = r * sum_d x A'_d          (poisson.py:640-643 with 1/eta folded into A')
+  const float* Apl = Ap + (size_t)q * D * REC;
   float zz[VPL][VW];
 #pragma unroll
   for (int i = 0; i < VPL; ++i)
 #pragma unroll
     for (int w = 0; w < VW; ++w) zz[i][w] = 0.f;
-  // Software pipeline: U nonzeros per slot in flight; the (col,val) pairs of the next batch are
-  // fetched while the current batch's records are being gathered (two dependent L2 latencies).
-  constexpr int U = VPL >= 4 ? 2 : 4;
-  int dcur[U];
-  float xcur[U];
-  auto load_idx = [&](long long jb, int (&dd)[U], float (&xx)[U]) {
+  {
+    int dcur[U];
+    float xcur[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const long long j = jb + (long long)u * NSLOT;
-      const bool ok = j < j1;
-      dd[u] = ok ? __ldg(cols + j) : 0;
-      xx[u] = ok ? __ldg(vals + j) : 0.f;      // x = 0 neutralises a padded lane
+      const int t = nb > 0 ? slot + u * NSLOT : 0;
+      dcur[u] = nb > 0 ? __ldg(rc + t) : 0;
+      xcur[u] = nb > 0 ? __ldg(rv + t) : 0.f;
     }
-  };
-  load_idx(j0 + slot, dcur, xcur);
-  for (long long jb = j0 + slot; jb < j1; jb += (long long)U * NSLOT) {
-    float a[U][VPL][VW];
+    for (int b = 0; b < nb; ++b) {
+      float a[U][VPL][VW];
 #pragma unroll
-    for (int u = 0; u < U; ++u)
+      for (int u = 0; u < U; ++u)
 #pragma unroll
-      for (int i = 0; i < VPL; ++i) ldv<VW>(a[u][i], Apq + (long long)dcur[u] * REC + off[i]);
-    int dn[U];
-    float xn[U];
-    load_idx(jb + (long long)U * NSLOT, dn, xn);
+        for (int i = 0; i < VPL; ++i) ldv<VW>(a[u][i], Apl + (unsigned)dcur[u] * REC + off[i]);
+      const int bn = min(b + 1, nb - 1);            // last iteration re-reads its own batch
+      int dn[U];
+      float xn[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
+      for (int u = 0; u < U; ++u) {
+        const int t = slot + (bn * U + u) * NSLOT;
+        dn[u] = __ldg(rc + t);
+        xn[u] = __ldg(rv + t);
+      }
 #pragma unroll
-      for (int i = 0; i < VPL; ++i)
+      for (int u = 0; u < U; ++u) {
 #pragma unroll
-        for (int w = 0; w < VW; ++w) zz[i][w] = fmaf(xcur[u], a[u][i][w], zz[i][w]);
-      dcur[u] = dn[u];
-      xcur[u] = xn[u];
+        for (int i = 0; i < VPL; ++i)
+#pragma unroll
+          for (int w = 0; w < VW; ++w) zz[i][w] = fmaf(xcur[u], a[u][i][w], zz[i][w]);
+        dcur[u] = dn[u];
+        xcur[u] = xn[u];
+      }
+    }
+    for (int c = nb * U; c < cnt; ++c) {            // tail (< U nonzeros)
+      const int t = slot + c * NSLOT;
+      const int d = __ldg(rc + t);
+      const float x = __ldg(rv + t);
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) {
+        float a[VW];
+        ldv<VW>(a, Apl + (unsigned)d * REC + off[i]);
+#pragma unroll
+        for (int w = 0; w < VW; ++w) zz[i][w] = fmaf(x, a[w], zz[i][w]);
+      }
     }
   }
   if constexpr (NSLOT > 1) {
@@ -174,7 +212,7 @@ csr_rows_kernel(const long long* __restrict__ rowptr, const int* __restrict__ co
       }
     }
   }
-  float* zq = z + ((long long)q * nrows + row) * REC;
+  float* zq = z + ((size_t)q * nrows + row) * REC;
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
 #pragma unroll
@@ -184,65 +222,103 @@ csr_rows_kernel(const long long* __restrict__ rowptr, const int* __restrict__ co
   if constexpr (ENCODE_ONLY) return;
 
   // ---- lambda at the nonzeros, x log lambda, dz      (poisson.py:174-184)
-  const float* EVq = EV + (long long)q * D * REC;
-  const float* PHq = PH + (long long)q * D * SV;
+  const float* EVl = EV + (size_t)q * D * REC;
+  const float* PHl = PH + (size_t)q * D * SV + s;
   float dz[VPL][VW];
-  float xlog = 0.f, bad = 0.f;
+  float xlog2 = 0.f;     // sum x log2(lambda); scaled by ln 2 at the end
+  int bad = 0;
 #pragma unroll
   for (int i = 0; i < VPL; ++i)
 #pragma unroll
     for (int w = 0; w < VW; ++w) dz[i][w] = 0.f;
-  load_idx(j0 + slot, dcur, xcur);
-  for (long long jb = j0 + slot; jb < j1; jb += (long long)U * NSLOT) {
-    float e[U][VPL][VW], ph[U], p[U];
+  {
+    int dcur[U];
+    float xcur[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-#pragma unroll
-      for (int i = 0; i < VPL; ++i) ldv<VW>(e[u][i], EVq + (long long)dcur[u] * REC + off[i]);
-      ph[u] = __ldg(PHq + (long long)dcur[u] * SV + s);
+      const int t = nb > 0 ? slot + u * NSLOT : 0;
+      dcur[u] = nb > 0 ? __ldg(rc + t) : 0;
+      xcur[u] = nb > 0 ? __ldg(rv + t) : 0.f;
     }
-    int dn[U];
-    float xn[U];
-    load_idx(jb + (long long)U * NSLOT, dn, xn);
+    for (int b = 0; b < nb; ++b) {
+      float e[U][VPL][VW], ph[U], p[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      p[u] = 0.f;
+      for (int u = 0; u < U; ++u) {
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) ldv<VW>(e[u][i], EVl + (unsigned)dcur[u] * REC + off[i]);
+        ph[u] = __ldg(PHl + (unsigned)dcur[u] * SV);
+      }
+      const int bn = min(b + 1, nb - 1);
+      int dn[U];
+      float xn[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int t = slot + (bn * U + u) * NSLOT;
+        dn[u] = __ldg(rc + t);
+        xn[u] = __ldg(rv + t);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        p[u] = 0.f;
+#pragma unroll
+        for (int i = 0; i < VPL; ++i)
+#pragma unroll
+          for (int w = 0; w < VW; ++w) p[u] = fmaf(zz[i][w], e[u][i][w], p[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) p[u] = group_sum<RG>(p[u], gmask);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const float lam = p[u] + ph[u];                        // poisson.py:177
+        const bool ok = rate_ok(lam);
+        const float lg = ok ? fast_lg2(lam) : 0.f;
+        const float gq = ok ? xcur[u] * fast_rcp(lam) : 0.f;
+        bad += ok ? 0 : 1;
+        xlog2 = fmaf(xcur[u], lg, xlog2);
+#pragma unroll
+        for (int i = 0; i < VPL; ++i)
+#pragma unroll
+          for (int w = 0; w < VW; ++w) dz[i][w] = fmaf(gq, e[u][i][w], dz[i][w]);
+        dcur[u] = dn[u];
+        xcur[u] = xn[u];
+      }
+    }
+    for (int c = nb * U; c < cnt; ++c) {            // tail
+      const int t = slot + c * NSLOT;
+      const int d = __ldg(rc + t);
+      const float x = __ldg(rv + t);
+      float e[VPL][VW];
+      float p = 0.f;
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) {
+        ldv<VW>(e[i], EVl + (unsigned)d * REC + off[i]);
+#pragma unroll
+        for (int w = 0; w < VW; ++w) p = fmaf(zz[i][w], e[i][w], p);
+      }
+      const float lam = group_sum<RG>(p, gmask) + __ldg(PHl + (unsigned)d * SV);
+      const bool ok = rate_ok(lam);
+      const float lg = ok ? fast_lg2(lam) : 0.f;
+      const float gq = ok ? x * fast_rcp(lam) : 0.f;
+      bad += ok ? 0 : 1;
+      xlog2 = fmaf(x, lg, xlog2);
 #pragma unroll
       for (int i = 0; i < VPL; ++i)
 #pragma unroll
-        for (int w = 0; w < VW; ++w) p[u] = fmaf(zz[i][w], e[u][i][w], p[u]);
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) p[u] = group_sum<RG>(p[u], gmask);
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const bool valid = jb + (long long)u * NSLOT < j1;
-      const float x = xcur[u];
-      const float lam = p[u] + ph[u];                        // poisson.py:177
-      const float t = x * __logf(lam);
-      float gq = __fdividef(x, lam);
-      const bool ok = isfinite(t) && isfinite(gq);
-      xlog += (valid && ok) ? t : 0.f;
-      bad += (valid && !ok) ? 1.f : 0.f;   // reported through rowacc slot 3 (guard of poisson.py:606-616)
-      gq = (valid && ok) ? gq : 0.f;
-#pragma unroll
-      for (int i = 0; i < VPL; ++i)
-#pragma unroll
-        for (int w = 0; w < VW; ++w) dz[i][w] = fmaf(gq, e[u][i][w], dz[i][w]);
-      dcur[u] = dn[u];
-      xcur[u] = xn[u];
+        for (int w = 0; w < VW; ++w) dz[i][w] = fmaf(gq, e[i][w], dz[i][w]);
     }
   }
+  float xlog = xlog2 * 0.6931471805599453f;
+  float fbad = (float)bad;
   if constexpr (NSLOT > 1) {
     __syncthreads();   // everyone is done reading `part` (z partials)
 #pragma unroll
     for (int i = 0; i < VPL; ++i) stv<VW>(part + slot * REC + off[i], dz[i]);
-    if (kg == 0) { sc[slot][s][0] = xlog; sc[slot][s][1] = bad; }
+    if (kg == 0) { sc[slot][s][0] = xlog; sc[slot][s][1] = fbad; }
     __syncthreads();
     if (slot != 0) return;
-    xlog = 0.f; bad = 0.f;
+    xlog = 0.f; fbad = 0.f;
 #pragma unroll
-    for (int t = 0; t < NSLOT; ++t) { xlog += sc[t][s][0]; bad += sc[t][s][1]; }
+    for (int t = 0; t < NSLOT; ++t) { xlog += sc[t][s][0]; fbad += sc[t][s][1]; }
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
 #pragma unroll
@@ -257,9 +333,9 @@ csr_rows_kernel(const long long* __restrict__ rowptr, const int* __restrict__ co
     }
   }
   // ---- closed-form parts and per-row scalars (slot 0 only from here)
-  const double* vsq = vsum + (long long)q * REC;
+  const double* vsq = vsum + (size_t)q * REC;
   float zv = 0.f, z2 = 0.f;
-  float* dq = dzr + ((long long)q * nrows + row) * REC;
+  float* dq = dzr + ((size_t)q * nrows + row) * REC;
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
     float o[VW];
@@ -275,11 +351,11 @@ csr_rows_kernel(const long long* __restrict__ rowptr, const int* __restrict__ co
   zv = group_sum<RG>(zv, gmask);
   z2 = group_sum<RG>(z2, gmask);
   if (kg == 0) {
-    float* ra = rowacc + ((long long)q * nrows + row) * 4 * SV;
+    float* ra = rowacc + ((size_t)q * nrows + row) * 4 * SV;
     ra[0 * SV + s] = xlog - lgam[row];
     ra[1 * SV + s] = zv;
     ra[2 * SV + s] = z2;
-    ra[3 * SV + s] = bad;
+    ra[3 * SV + s] = fbad;
   }
 }
 
@@ -298,6 +374,7 @@ csc_cols_kernel(const int* __restrict__ colptr, const int* __restrict__ rows,
                 float* __restrict__ GAp, float* __restrict__ GEV, float* __restrict__ Gphi) {
   using M = Map<KP, SV>;
   constexpr int VW = M::VW, LPN = M::LPN, RG = M::RG, VPL = M::VPL, REC = M::REC, NSLOT = M::NSLOT;
+  constexpr int U = VPL >= 4 ? 2 : 4;
   const int lane = threadIdx.x & 31;
   const int slot = threadIdx.x / LPN;
   const int li = threadIdx.x % LPN;
@@ -312,13 +389,13 @@ csc_cols_kernel(const int* __restrict__ colptr, const int* __restrict__ rows,
 #pragma unroll
   for (int i = 0; i < VPL; ++i) off[i] = s * KP + (i * RG + kg) * VW;
 
-  const float* zq = z + (long long)q * nrows * REC;
-  const float* dq = dzr + (long long)q * nrows * REC;
-  const float* EVq = EV + (long long)q * D * REC;
-  const float* PHq = PH + (long long)q * D * SV;
-  float* GApq = GAp + (long long)q * D * REC;
-  float* GEVq = GEV + (long long)q * D * REC;
-  float* Gphq = Gphi + (long long)q * D * SV;
+  const float* zl = z + (size_t)q * nrows * REC;
+  const float* dl = dzr + (size_t)q * nrows * REC;
+  const float* EVl = EV + (size_t)q * D * REC;
+  const float* PHl = PH + (size_t)q * D * SV + s;
+  float* GApq = GAp + (size_t)q * D * REC;
+  float* GEVq = GEV + (size_t)q * D * REC;
+  float* Gphq = Gphi + (size_t)q * D * SV + s;
 
   // column containing position j0: largest d with colptr[d] <= j0  (colptr[D] = nnz > j0)
   int lo = 0, hi = D;
@@ -333,86 +410,90 @@ csc_cols_kernel(const int* __restrict__ colptr, const int* __restrict__ rows,
   auto load_col = [&](int dd) {
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
-      ldv<VW>(ev[i], EVq + (long long)dd * REC + off[i]);
+      ldv<VW>(ev[i], EVl + (unsigned)dd * REC + off[i]);
 #pragma unroll
       for (int w = 0; w < VW; ++w) { aEV[i][w] = 0.f; aAp[i][w] = 0.f; }
     }
-    ph = __ldg(PHq + (long long)dd * SV + s);
+    ph = __ldg(PHl + (unsigned)dd * SV);
     aPh = 0.f;
   };
   auto flush_col = [&](int dd) {
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
-      const long long o = (long long)dd * REC + off[i];
+      const unsigned o = (unsigned)dd * REC + off[i];
 #pragma unroll
       for (int w = 0; w < VW; ++w) {
         atomicAdd(GEVq + o + w, aEV[i][w]);
         atomicAdd(GApq + o + w, aAp[i][w]);
       }
     }
-    if (kg == 0) atomicAdd(Gphq + (long long)dd * SV + s, aPh);
+    if (kg == 0) atomicAdd(Gphq + (unsigned)dd * SV, aPh);
+  };
+  auto one = [&](int j, float x, const float (&zz)[VPL][VW], const float (&dd)[VPL][VW]) {
+    if (j >= next) {
+      flush_col(d);
+      do {
+        ++d;
+        next = __ldg(colptr + d + 1);
+      } while (j >= next);
+      load_col(d);
+    }
+    float p = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i)
+#pragma unroll
+      for (int w = 0; w < VW; ++w) p = fmaf(zz[i][w], ev[i][w], p);
+    const float lam = group_sum<RG>(p, gmask) + ph;
+    const float gq = rate_ok(lam) ? x * fast_rcp(lam) : 0.f;    // same entries the row pass dropped
+    aPh += gq;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i)
+#pragma unroll
+      for (int w = 0; w < VW; ++w) {
+        aEV[i][w] = fmaf(gq, zz[i][w], aEV[i][w]);
+        aAp[i][w] = fmaf(x, dd[i][w], aAp[i][w]);
+      }
   };
   load_col(d);
-  int pending = 0;
-  constexpr int U = VPL >= 4 ? 2 : 4;
-  for (int jb = j0; jb < j1; jb += U) {
+  const int nfull = (j1 - j0) / U;
+  for (int b = 0; b < nfull; ++b) {
+    const int jb = j0 + b * U;
     int bb[U];
     float xx[U];
-    if (U == 4 && jb + 4 <= j1) {                 // slices start 256-aligned: 16-byte vector loads
+    if constexpr (U == 4) {                       // slices start 256-aligned: 16-byte vector loads
       const int4 b4 = __ldg(reinterpret_cast<const int4*>(rows + jb));
       const float4 x4 = __ldg(reinterpret_cast<const float4*>(vals + jb));
-      bb[0] = b4.x; bb[1] = b4.y; bb[U - 2] = b4.z; bb[U - 1] = b4.w;
-      xx[0] = x4.x; xx[1] = x4.y; xx[U - 2] = x4.z; xx[U - 1] = x4.w;
+      bb[0] = b4.x; bb[1] = b4.y; bb[2] = b4.z; bb[3] = b4.w;
+      xx[0] = x4.x; xx[1] = x4.y; xx[2] = x4.z; xx[3] = x4.w;
     } else {
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const bool ok = jb + u < j1;
-        bb[u] = ok ? __ldg(rows + jb + u) : 0;
-        xx[u] = ok ? __ldg(vals + jb + u) : 0.f;
-      }
+      const int2 b2 = __ldg(reinterpret_cast<const int2*>(rows + jb));
+      const float2 x2 = __ldg(reinterpret_cast<const float2*>(vals + jb));
+      bb[0] = b2.x; bb[1] = b2.y;
+      xx[0] = x2.x; xx[1] = x2.y;
     }
     float zz[U][VPL][VW], dd[U][VPL][VW];
 #pragma unroll
     for (int u = 0; u < U; ++u)
 #pragma unroll
       for (int i = 0; i < VPL; ++i) {
-        ldv<VW>(zz[u][i], zq + (long long)bb[u] * REC + off[i]);
-        ldv<VW>(dd[u][i], dq + (long long)bb[u] * REC + off[i]);
+        ldv<VW>(zz[u][i], zl + (unsigned)bb[u] * REC + off[i]);
+        ldv<VW>(dd[u][i], dl + (unsigned)bb[u] * REC + off[i]);
       }
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int j = jb + u;
-      if (j < j1) {
-        if (j >= next) {
-          if (pending) flush_col(d);
-          pending = 0;
-          do {
-            ++d;
-            next = __ldg(colptr + d + 1);
-          } while (j >= next);
-          load_col(d);
-        }
-        float p = 0.f;
-#pragma unroll
-        for (int i = 0; i < VPL; ++i)
-#pragma unroll
-          for (int w = 0; w < VW; ++w) p = fmaf(zz[u][i][w], ev[i][w], p);
-        const float lam = group_sum<RG>(p, gmask) + ph;
-        float gq = __fdividef(xx[u], lam);
-        if (!isfinite(gq) || !isfinite(__logf(lam))) gq = 0.f;   // same entries the row pass dropped
-        aPh += gq;
-#pragma unroll
-        for (int i = 0; i < VPL; ++i)
-#pragma unroll
-          for (int w = 0; w < VW; ++w) {
-            aEV[i][w] = fmaf(gq, zz[u][i][w], aEV[i][w]);
-            aAp[i][w] = fmaf(xx[u], dd[u][i][w], aAp[i][w]);
-          }
-        pending = 1;
-      }
-    }
+    for (int u = 0; u < U; ++u) one(jb + u, xx[u], zz[u], dd[u]);
   }
-  if (pending) flush_col(d);
+  for (int j = j0 + nfull * U; j < j1; ++j) {     // tail of the last slice
+    const int b = __ldg(rows + j);
+    const float x = __ldg(vals + j);
+    float zz[VPL][VW], dd[VPL][VW];
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      ldv<VW>(zz[i], zl + (unsigned)b * REC + off[i]);
+      ldv<VW>(dd[i], dl + (unsigned)b * REC + off[i]);
+    }
+    one(j, x, zz, dd);
+  }
+  flush_col(d);
 }
 
 // ------------------------------------------------------------------ data-format kernels
