@@ -217,3 +217,52 @@ def test_fit_reduces_loss():
     assert np.isfinite(losses).all() and losses[-1] < losses[0]
     A = model.encoding_matrix()
     assert A.shape == (D, K) and bool(torch.isfinite(A).all())
+
+
+import glob as _glob
+import os as _os
+
+_GOLDEN = sorted(_glob.glob(_os.path.join(_os.path.dirname(__file__), "golden", "*.npz")))
+
+
+@pytest.mark.parametrize("path", _GOLDEN, ids=[_os.path.basename(p) for p in _GOLDEN])
+def test_step_matches_committed_golden(path):
+    """CUDA step vs the committed oracle fixtures (tests/golden/make_golden.py)."""
+    import spmf_b200
+    g = np.load(path)
+    D, K, B, S, N = (int(v) for v in g["meta"])
+    dev = torch.device("cuda:0")
+    model = spmf_b200.PoissonFactorization(latent_dim=K, feature_dim=D, u_tau_scale=1.0 / np.sqrt(N * D), device=dev)
+    model.compute_scales(lambda: [{'counts': g["x"]}])
+    assert rel_err(model.eta_i.numpy(), g["eta"]) < 1e-12
+    eng = model._engine_for(S)
+    _load(eng, {k[6:]: torch.tensor(g[k]) for k in g.files if k.startswith("param:")})
+    eng.set_noise_from({k[6:]: torch.tensor(g[k]) for k in g.files if k.startswith("noise:")})
+    parts = eng.loss_and_grad(spmf_b200.as_device_batch(g["x"], dev), fresh_noise=False)
+    loss = float(eng.loss_value(parts).item())
+    assert abs(loss - float(g["loss"])) <= TOL * abs(float(g["loss"]))
+    grads = eng.layout.views(eng.grads)
+    for k in (f for f in g.files if f.startswith("grad:")):
+        name = k[5:]
+        tol = TOL if name.split('/')[0] in ('v', 'w', 'u', 's') else TOL_IG
+        assert rel_err(grads[name].cpu().numpy(), g[k]) <= tol, name
+
+
+def test_streamed_host_batches_match_resident():
+    """HostCsr -> H2D -> device CSC build gives the same step as the resident shard."""
+    import spmf_b200
+    from spmf_b200.data import HostCsr
+    dev = torch.device("cuda:0")
+    D, K, S, B = 200, 8, 4, 128
+    x = make_counts(3 * B, D, seed=12, kind="sparse")
+    sh = spmf_b200.CsrShard.from_dense(x, dev)
+    host = HostCsr.from_shard(sh)
+    model = spmf_b200.PoissonFactorization(latent_dim=K, feature_dim=D, u_tau_scale=1e-3, device=dev, seed=5)
+    model.compute_scales(sh)
+    eng = model._engine_for(S)
+    eng.fill_noise(step=0)
+    p0 = eng.loss_and_grad(sh.batch(B, B), fresh_noise=False).clone()
+    g0 = eng.grads.clone()
+    p1 = eng.loss_and_grad(spmf_b200.as_device_batch(host.batch(B, B), dev), fresh_noise=False).clone()
+    assert rel_err(p1.cpu().numpy(), p0.cpu().numpy()) < 1e-6
+    assert rel_err(eng.grads.cpu().numpy(), g0.cpu().numpy()) < 2e-5
