@@ -49,8 +49,10 @@ long long spmf_backward_scratch_floats(int D, int K, int S);
 long long spmf_backward_scratch_doubles(int D, int K, int S);
 
 /* ---- surrogate sampling [EXT L3: surrogate_distribution.sample(S)], poisson.py:403-573 ---- */
+#define SPMF_NOISE_NORMAL 1 /* N(0,1) base draws of v, w, u, s */
+#define SPMF_NOISE_GAMMA 2  /* Gamma(alpha,1) draws of the 8 InverseGamma-based variables */
 int spmf_fill_noise(float* noise, const float* params, int D, int K, int S,
-                    unsigned long long seed, unsigned int step, void* stream);
+                    unsigned long long seed, unsigned int step, int which, void* stream);
 int spmf_sample(const float* params, const float* noise, int D, int K, int S, float* samples,
                 void* stream);
 /* encoding_matrix / intercept_matrix / decoding_matrix for every draw (poisson.py:652-701),

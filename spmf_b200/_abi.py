@@ -44,7 +44,7 @@ _SIGS = {
     "spmf_layout": (i32, [i32, i32, i32, C.POINTER(i64), C.POINTER(i64)]),
     "spmf_backward_scratch_floats": (i64, [i32, i32, i32]),
     "spmf_backward_scratch_doubles": (i64, [i32, i32, i32]),
-    "spmf_fill_noise": (i32, [p, p, i32, i32, i32, u64, u32, p]),
+    "spmf_fill_noise": (i32, [p, p, i32, i32, i32, u64, u32, i32, p]),
     "spmf_sample": (i32, [p, p, i32, i32, i32, p, p]),
     "spmf_draw_operands": (i32, [p, p, p, i32, i32, i32, p, p, p, p, p, p, p]),
     "spmf_csr_row_consts": (i32, [p, p, i64, p, p, p]),

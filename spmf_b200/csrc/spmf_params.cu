@@ -29,33 +29,37 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 // ------------------------------------------------------------------ noise
-// Normal variables: 4 normals per Philox call; element index e -> (call e/4, slot e%4).
-__global__ void fill_normal_kernel(float* __restrict__ out, long long n, uint32_t stream,
-                                   uint32_t step, uint32_t k0, uint32_t k1) {
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  long long base = i * 4;
+// Normal variables (blockIdx.y = v,w,u,s): 4 normals per Philox call; element e -> (call e/4, slot e%4).
+__global__ void fill_normal_kernel(Layout L, float* __restrict__ noise, uint32_t step, uint32_t k0,
+                                   uint32_t k1) {
+  const int v = blockIdx.y;
+  const long long n = L.vsize[v] * L.S;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long base = i * 4;
   if (base >= n) return;
-  U4 ctr = {(uint32_t)(i & 0xffffffffu), (uint32_t)(i >> 32), stream, step};
+  float* out = noise + L.noff[v];
+  U4 ctr = {(uint32_t)(i & 0xffffffffu), (uint32_t)(i >> 32), (uint32_t)v, step};
   U4 r = philox4x32_10(ctr, k0, k1);
-  float v[4];
-  box_muller(r.x, r.y, &v[0], &v[1]);
-  box_muller(r.z, r.w, &v[2], &v[3]);
+  float x[4];
+  box_muller(r.x, r.y, &x[0], &x[1]);
+  box_muller(r.z, r.w, &x[2], &x[3]);
 #pragma unroll
   for (int j = 0; j < 4; ++j)
-    if (base + j < n) out[base + j] = v[j];
+    if (base + j < n) out[base + j] = x[j];
 }
 
-// Gamma variables: out[s][e] ~ Gamma(softplus(conc_raw[e]), 1)
-__global__ void fill_gamma_kernel(float* __restrict__ out, const float* __restrict__ conc_raw,
-                                  long long nelem, int S, uint32_t stream, uint32_t step,
-                                  uint32_t k0, uint32_t k1) {
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nelem * S) return;
-  long long e = i % nelem;
-  float alpha = softplusf(conc_raw[e]);
+// Gamma variables (blockIdx.y = the 8 InverseGamma-based ones): out[s][e] ~ Gamma(softplus(conc_raw[e]), 1)
+__global__ void fill_gamma_kernel(Layout L, float* __restrict__ noise, const float* __restrict__ P,
+                                  uint32_t step, uint32_t k0, uint32_t k1) {
+  const int v = VAR_UETA + blockIdx.y;
+  const long long n = L.vsize[v] * L.S;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const long long e = i % L.vsize[v];
+  const float alpha = softplusf(P[L.toff[2 * v] + e]);
   // stream id folds the step so that (element, iteration) keep the whole counter space
-  out[i] = gamma_draw(alpha, (uint32_t)(i & 0xffffffffu), (uint32_t)(i >> 32),
-                      stream ^ (step * 0x9E3779B9u), k0, k1 ^ step);
+  noise[L.noff[v] + i] = gamma_draw(alpha, (uint32_t)(i & 0xffffffffu), (uint32_t)(i >> 32),
+                                    (uint32_t)v ^ (step * 0x9E3779B9u), k0, k1 ^ step);
 }
 
 // dg/dalpha of every Gamma draw (implicit reparameterisation): depends on (alpha, g) only, so it
@@ -391,19 +395,20 @@ int spmf_layout(int D, int K, int S, long long* tensor_offsets, long long* noise
 }
 
 int spmf_fill_noise(float* noise, const float* params, int D, int K, int S, unsigned long long seed,
-                    unsigned int step, void* stream) {
-  if (!noise || !params || D <= 0 || K <= 0 || S <= 0 || K > SPMF_MAX_K) return SPMF_ERR_BAD_ARG;
+                    unsigned int step, int which, void* stream) {
+  if (!noise || !params || D <= 0 || K <= 0 || S <= 0 || K > SPMF_MAX_K || !(which & 3)) return SPMF_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   Layout L = make_layout(D, K, S);
   uint32_t k0 = (uint32_t)(seed & 0xffffffffu), k1 = (uint32_t)(seed >> 32);
-  for (int v = 0; v < NUM_VARS; ++v) {
-    long long n = L.vsize[v] * S;
-    if (v <= VAR_S) {
-      long long calls = (n + 3) / 4;
-      fill_normal_kernel<<<(unsigned)((calls + 255) / 256), 256, 0, st>>>(noise + L.noff[v], n, (uint32_t)v, step, k0, k1);
-    } else {
-      fill_gamma_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(noise + L.noff[v], params + L.toff[2 * v], L.vsize[v], S, (uint32_t)v, step, k0, k1);
-    }
+  long long nmax = (long long)D * K * S;
+  if (nmax < 2LL * D * S) nmax = 2LL * D * S;
+  if (which & SPMF_NOISE_NORMAL) {
+    dim3 grid((unsigned)(((nmax + 3) / 4 + 255) / 256), VAR_S + 1);
+    fill_normal_kernel<<<grid, 256, 0, st>>>(L, noise, step, k0, k1);
+  }
+  if (which & SPMF_NOISE_GAMMA) {
+    dim3 grid((unsigned)((nmax + 255) / 256), NUM_VARS - VAR_UETA);
+    fill_gamma_kernel<<<grid, 256, 0, st>>>(L, noise, params, step, k0, k1);
   }
   SPMF_CHECK_LAUNCH();
   return SPMF_OK;

@@ -110,6 +110,23 @@ __device__ __forceinline__ float fast_rcp(float x) {
   return y;
 }
 
+// U consecutive (col,val) pairs as one vector load each (U = 4: 16 B, U = 2: 8 B; p aligned)
+template <int U>
+__device__ __forceinline__ void ld_idx(const int* __restrict__ pc, const float* __restrict__ pv,
+                                       int (&d)[U], float (&x)[U]) {
+  if constexpr (U == 4) {
+    const int4 c = __ldg(reinterpret_cast<const int4*>(pc));
+    const float4 v = __ldg(reinterpret_cast<const float4*>(pv));
+    d[0] = c.x; d[1] = c.y; d[2] = c.z; d[3] = c.w;
+    x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
+  } else {
+    const int2 c = __ldg(reinterpret_cast<const int2*>(pc));
+    const float2 v = __ldg(reinterpret_cast<const float2*>(pv));
+    d[0] = c.x; d[1] = c.y;
+    x[0] = v.x; x[1] = v.y;
+  }
+}
+
 template <int KP, int SV, bool ENCODE_ONLY>
 __global__ void __launch_bounds__(128)
 csr_rows_kernel(const long long* __restrict__ rowptr, const int* __restrict__ cols,
@@ -133,12 +150,22 @@ csr_rows_kernel(const long long* __restrict__ rowptr, const int* __restrict__ co
 #pragma unroll
   for (int i = 0; i < VPL; ++i) off[i] = s * KP + (i * RG + kg) * VW;
 
+  // Row-local index space [0,n).  The nonzero stream is consumed in aligned groups of U (one
+  // 16-byte load for U columns, one for U values, shared by the whole slot): `head` elements up
+  // to the first aligned position, `ng` full groups dealt round-robin to the slots, then a tail;
+  // head and tail (< 2U elements) go through a scalar path on the last slot.
   const long long j0 = rowptr[row];
   const int n = (int)(rowptr[row + 1] - j0);
-  const int* __restrict__ rc = cols + j0;          // row-local views: 32-bit indexing below
+  const int head = min(n, (int)((U - (j0 & (U - 1))) & (U - 1)));
+  const int ng = (n - head) / U;
+  const int* __restrict__ gc = cols + j0 + head;   // aligned group base
+  const float* __restrict__ gv = vals + j0 + head;
+  const int* __restrict__ rc = cols + j0;
   const float* __restrict__ rv = vals + j0;
-  const int cnt = slot < n ? (n - slot + NSLOT - 1) / NSLOT : 0;   // nonzeros of this slot
-  const int nb = cnt / U;                                          // full batches
+  const int my_groups = slot < ng ? (ng - slot + NSLOT - 1) / NSLOT : 0;
+  // scalar extras of the last slot: [0,head) U [head + ng*U, n)
+  const int n_extra = (slot == NSLOT - 1) ? n - ng * U : 0;
+  auto extra_index = [&](int e) { return e < head ? e : e - head + head + ng * U; };
   const float r = scale_rows ? rowsum[row] * inv_xi : 1.f;   // poisson.py:644-649
 
   // ---- z = r * sum_d x A'_d          (poisson.py:640-643 with 1/eta folded into A')
@@ -151,27 +178,17 @@ csr_rows_kernel(const long long* __restrict__ rowptr, const int* __restrict__ co
   {
     int dcur[U];
     float xcur[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int t = nb > 0 ? slot + u * NSLOT : 0;
-      dcur[u] = nb > 0 ? __ldg(rc + t) : 0;
-      xcur[u] = nb > 0 ? __ldg(rv + t) : 0.f;
-    }
-    for (int b = 0; b < nb; ++b) {
+    if (my_groups > 0) ld_idx<U>(gc + slot * U, gv + slot * U, dcur, xcur);
+    for (int b = 0; b < my_groups; ++b) {
       float a[U][VPL][VW];
 #pragma unroll
       for (int u = 0; u < U; ++u)
 #pragma unroll
         for (int i = 0; i < VPL; ++i) ldv<VW>(a[u][i], Apl + (unsigned)dcur[u] * REC + off[i]);
-      const int bn = min(b + 1, nb - 1);            // last iteration re-reads its own batch
+      const int gn = slot + min(b + 1, my_groups - 1) * NSLOT;   // last iteration re-reads its own group
       int dn[U];
       float xn[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int t = slot + (bn * U + u) * NSLOT;
-        dn[u] = __ldg(rc + t);
-        xn[u] = __ldg(rv + t);
-      }
+      ld_idx<U>(gc + gn * U, gv + gn * U, dn, xn);
 #pragma unroll
       for (int u = 0; u < U; ++u) {
 #pragma unroll
@@ -182,8 +199,8 @@ csr_rows_kernel(const long long* __restrict__ rowptr, const int* __restrict__ co
         xcur[u] = xn[u];
       }
     }
-    for (int c = nb * U; c < cnt; ++c) {            // tail (< U nonzeros)
-      const int t = slot + c * NSLOT;
+    for (int e = 0; e < n_extra; ++e) {
+      const int t = extra_index(e);
       const int d = __ldg(rc + t);
       const float x = __ldg(rv + t);
 #pragma unroll
@@ -234,13 +251,8 @@ csr_rows_kernel(const long long* __restrict__ rowptr, const int* __restrict__ co
   {
     int dcur[U];
     float xcur[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int t = nb > 0 ? slot + u * NSLOT : 0;
-      dcur[u] = nb > 0 ? __ldg(rc + t) : 0;
-      xcur[u] = nb > 0 ? __ldg(rv + t) : 0.f;
-    }
-    for (int b = 0; b < nb; ++b) {
+    if (my_groups > 0) ld_idx<U>(gc + slot * U, gv + slot * U, dcur, xcur);
+    for (int b = 0; b < my_groups; ++b) {
       float e[U][VPL][VW], ph[U], p[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
@@ -248,15 +260,10 @@ csr_rows_kernel(const long long* __restrict__ rowptr, const int* __restrict__ co
         for (int i = 0; i < VPL; ++i) ldv<VW>(e[u][i], EVl + (unsigned)dcur[u] * REC + off[i]);
         ph[u] = __ldg(PHl + (unsigned)dcur[u] * SV);
       }
-      const int bn = min(b + 1, nb - 1);
+      const int gn = slot + min(b + 1, my_groups - 1) * NSLOT;
       int dn[U];
       float xn[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int t = slot + (bn * U + u) * NSLOT;
-        dn[u] = __ldg(rc + t);
-        xn[u] = __ldg(rv + t);
-      }
+      ld_idx<U>(gc + gn * U, gv + gn * U, dn, xn);
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         p[u] = 0.f;
@@ -283,8 +290,8 @@ csr_rows_kernel(const long long* __restrict__ rowptr, const int* __restrict__ co
         xcur[u] = xn[u];
       }
     }
-    for (int c = nb * U; c < cnt; ++c) {            // tail
-      const int t = slot + c * NSLOT;
+    for (int ex = 0; ex < n_extra; ++ex) {
+      const int t = extra_index(ex);
       const int d = __ldg(rc + t);
       const float x = __ldg(rv + t);
       float e[VPL][VW];

@@ -83,6 +83,7 @@ class AdviEngine:
         self.eta = torch.ones(D, dtype=torch.float32, device=self.device)
         self.inv_xi = 1.0
         self._ws = None
+        self._side = None
         self._max_rows = max_rows
         self.opt_step = 0
         self.rng_step = 0
@@ -96,12 +97,16 @@ class AdviEngine:
         return self._ws
 
     # ------------------------------------------------------------------ pieces
-    def fill_noise(self, step=None):
+    NOISE_NORMAL, NOISE_GAMMA = 1, 2
+
+    def fill_noise(self, step=None, which=3, advance=True):
+        """Philox draws for `step`: N(0,1) for v,w,u,s (which&1), Gamma(alpha,1) for the rest (which&2)."""
         step = self.rng_step if step is None else step
         _abi.call("spmf_fill_noise", _ptr(self.noise), _ptr(self.params), self.D, self.K, self.S,
-                  self.seed, step, _stream())
-        self.rng_step = step + 1
-        self.launches += 12
+                  self.seed, step, which, _stream())
+        if advance:
+            self.rng_step = step + 1
+        self.launches += (which & 1) + ((which >> 1) & 1)
 
     def draw_operands(self):
         w = self.ws
@@ -167,19 +172,33 @@ class AdviEngine:
     # ------------------------------------------------------------------ one step
     def loss_and_grad(self, batch: DeviceBatch, fresh_noise=True, variant=0):
         """Fills self.grads and self.ws.parts for `batch`; returns the (S,16) parts tensor (device,
-        float64): 12 prior terms in var_list order, logq, z, x, per-draw loss."""
+        float64): 12 prior terms in var_list order, logq, z, x, per-draw loss.
+
+        Two streams: the Gamma draws and their implicit gradients (ALU/MUFU-bound, needed only by
+        the backward) run on a side stream underneath the gather-bound data-term kernels."""
+        main = torch.cuda.current_stream()
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.device)
+            self._fork, self._join = torch.cuda.Event(), torch.cuda.Event()
+        step = self.rng_step
         t = self._mark(None, None)
         if fresh_noise:
-            self.fill_noise()
-            t = self._mark("fill_noise", t)
-        self.gamma_grad()
-        t = self._mark("gamma_grad", t)
+            self.fill_noise(step, self.NOISE_NORMAL, advance=False)
+            t = self._mark("fill_normals", t)
+        self._fork.record(main)
+        self._side.wait_event(self._fork)
+        with torch.cuda.stream(self._side):
+            if fresh_noise:
+                self.fill_noise(step, self.NOISE_GAMMA, advance=True)
+            self.gamma_grad()
+            self._join.record(self._side)
         self.draw_operands()
         t = self._mark("draw_operands", t)
         self.data_term(batch, variant)
         t = self._mark("data_term", t)
+        main.wait_event(self._join)
         self.backward_params(batch.nrows)
-        self._mark("backward_params", t)
+        self._mark("join_side+backward_params", t)
         return self.ws.parts.view(self.S, _abi.NUM_PARTS)
 
     def loss_value(self, parts=None):

@@ -57,7 +57,7 @@ def test_bad_arguments_are_rejected():
     with pytest.raises(_abi.SpmfError):
         _abi.layout(10, _abi.MAX_K + 1, 1)
     with pytest.raises(_abi.SpmfError):       # null pointers
-        _abi.call("spmf_fill_noise", None, None, 10, 2, 1, 0, 0, None)
+        _abi.call("spmf_fill_noise", None, None, 10, 2, 1, 0, 0, 3, None)
     with pytest.raises(_abi.SpmfError):
         _abi.call("spmf_csr_rows", *([None] * 5), 1.0, 1, 4, 10, 2, 1, *([None] * 7), 0, None)
 
