@@ -8,6 +8,7 @@ TensorFlow graph, never materialising the (S,B,D) rate tensor of poisson.py:174-
 """
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import torch
@@ -84,6 +85,7 @@ class AdviEngine:
         self.inv_xi = 1.0
         self._ws = None
         self._side = None
+        self.stream_mode = os.environ.get("SPMF_STREAMS", "single")
         self._max_rows = max_rows
         self.opt_step = 0
         self.rng_step = 0
@@ -176,29 +178,45 @@ class AdviEngine:
 
         Two streams: the Gamma draws and their implicit gradients (ALU/MUFU-bound, needed only by
         the backward) run on a side stream underneath the gather-bound data-term kernels."""
-        main = torch.cuda.current_stream()
+        if self.stream_mode == "single":
+            t = self._mark(None, None)
+            if fresh_noise:
+                self.fill_noise()
+                t = self._mark("fill_noise", t)
+            self.gamma_grad()
+            t = self._mark("gamma_grad", t)
+            self.draw_operands()
+            t = self._mark("draw_operands", t)
+            self.data_term(batch, variant)
+            t = self._mark("data_term", t)
+            self.backward_params(batch.nrows)
+            self._mark("backward_params", t)
+            return self.ws.parts.view(self.S, _abi.NUM_PARTS)
+        # "prio": hot path on a high-priority stream, Gamma work on a low-priority one
+        caller = torch.cuda.current_stream()
         if self._side is None:
-            self._side = torch.cuda.Stream(device=self.device)
-            self._fork, self._join = torch.cuda.Event(), torch.cuda.Event()
+            lo, hi = torch.cuda.Stream.priority_range() if hasattr(torch.cuda.Stream, "priority_range") else (0, -1)
+            self._hot = torch.cuda.Stream(device=self.device, priority=-1)
+            self._side = torch.cuda.Stream(device=self.device, priority=0)
+            self._fork, self._join, self._done = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
         step = self.rng_step
-        t = self._mark(None, None)
-        if fresh_noise:
-            self.fill_noise(step, self.NOISE_NORMAL, advance=False)
-            t = self._mark("fill_normals", t)
-        self._fork.record(main)
+        self._fork.record(caller)
+        self._hot.wait_event(self._fork)
         self._side.wait_event(self._fork)
         with torch.cuda.stream(self._side):
             if fresh_noise:
                 self.fill_noise(step, self.NOISE_GAMMA, advance=True)
             self.gamma_grad()
             self._join.record(self._side)
-        self.draw_operands()
-        t = self._mark("draw_operands", t)
-        self.data_term(batch, variant)
-        t = self._mark("data_term", t)
-        main.wait_event(self._join)
-        self.backward_params(batch.nrows)
-        self._mark("join_side+backward_params", t)
+        with torch.cuda.stream(self._hot):
+            if fresh_noise:
+                self.fill_noise(step, self.NOISE_NORMAL, advance=False)
+            self.draw_operands()
+            self.data_term(batch, variant)
+            self._hot.wait_event(self._join)
+            self.backward_params(batch.nrows)
+            self._done.record(self._hot)
+        caller.wait_event(self._done)
         return self.ws.parts.view(self.S, _abi.NUM_PARTS)
 
     def loss_value(self, parts=None):

@@ -266,3 +266,16 @@ def test_streamed_host_batches_match_resident():
     p1 = eng.loss_and_grad(spmf_b200.as_device_batch(host.batch(B, B), dev), fresh_noise=False).clone()
     assert rel_err(p1.cpu().numpy(), p0.cpu().numpy()) < 1e-6
     assert rel_err(eng.grads.cpu().numpy(), g0.cpu().numpy()) < 2e-5
+
+
+def test_data_parallel_two_gpus():
+    """Row-sharded step on 2 GPUs == single-GPU step on the whole batch (skipped with < 2 GPUs)."""
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29517",
+                          _os.path.join(root, "tests", "dp_check.py")], capture_output=True, text=True, timeout=600)
+    assert "DP_CHECK_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
