@@ -19,9 +19,10 @@
  *                                   (order: v,w,u,s | u_eta,u_tau,s_eta,s_tau,u_eta_a,u_tau_a,s_eta_a,s_tau_a;
  *                                    each as (loc|conc_raw , scale_raw); v stored transposed as (D,K))
  *   noise                         : flat fp32 [var][s][elem]; N(0,1) for v,w,u,s, Gamma(alpha,1) otherwise
- *   Ap, EV, GAp, GEVnz            : [NQ][D][SV][KP]   A' = a_d u_dk / eta_d,  EV = eta_d v_kd  (k innermost)
+ *   Ap, EV, GAp, GEVnz            : [NQ][D][REC]      A' = a_d u_dk / eta_d,  EV = eta_d v_kd; REC = SV*KP floats,
+ *                                                      element (sv,k) at spmf_rec_pos(KP,SV,sv,k)
  *   PH, Gphinz                    : [NQ][D][SV]       phi_d = eta_d b_d w_d
- *   z, dzr                        : [NQ][B][SV][KP]   z_bk and r_b * dL/dz_bk
+ *   z, dzr                        : [NQ][B][REC]      z_bk and r_b * dL/dz_bk (same record layout)
  *   rowacc                        : [NQ][B][4][SV]    per-row (sum x log lam - lgamma, z.vsum, |z|^2, #non-finite)
  */
 #ifndef SPMF_B200_H
@@ -42,6 +43,9 @@ extern "C" {
 /* ---- layout helpers (host only, no device work) ---- */
 int spmf_kpad(int K);       /* latent dim padded to a power of two */
 int spmf_draw_vec(int S);   /* draws processed per vector lane: 4, 2 or 1 */
+/* position of (draw sv, latent k) inside one SV*KP-float gather record (k-vector-major, see
+ * csrc/spmf_record.cuh); negative on bad arguments. */
+int spmf_rec_pos(int KP, int SV, int sv, int k);
 /* tensor_offsets[25], noise_offsets[13] in floats.  Replaces the variable bookkeeping of
  * create_distributions (poisson.py:403-573: surrogate_vars / var_list). */
 int spmf_layout(int D, int K, int S, long long* tensor_offsets_host, long long* noise_offsets_host);

@@ -41,6 +41,7 @@ u32 = C.c_uint
 _SIGS = {
     "spmf_kpad": (i32, [i32]),
     "spmf_draw_vec": (i32, [i32]),
+    "spmf_rec_pos": (i32, [i32, i32, i32, i32]),
     "spmf_layout": (i32, [i32, i32, i32, C.POINTER(i64), C.POINTER(i64)]),
     "spmf_backward_scratch_floats": (i64, [i32, i32, i32]),
     "spmf_backward_scratch_doubles": (i64, [i32, i32, i32]),
@@ -90,6 +91,20 @@ def kpad(K):
 
 def draw_vec(S):
     return _lib.spmf_draw_vec(S)
+
+
+_REC_PERM = {}
+
+
+def rec_perm(KP, SV):
+    """perm[sv*KP + k] = position of (sv,k) inside a gather record (list of ints, cached)."""
+    key = (KP, SV)
+    if key not in _REC_PERM:
+        perm = [_lib.spmf_rec_pos(KP, SV, sv, k) for sv in range(SV) for k in range(KP)]
+        if min(perm) < 0 or sorted(perm) != list(range(KP * SV)):
+            raise SpmfError("spmf_rec_pos does not define a permutation")
+        _REC_PERM[key] = perm
+    return _REC_PERM[key]
 
 
 def layout(D, K, S):

@@ -13,6 +13,7 @@
 
 #include "../../include/spmf_b200.h"
 #include "spmf_model.cuh"
+#include "spmf_record.cuh"
 
 namespace spmf {
 
@@ -97,7 +98,7 @@ draw_operands_kernel(Layout L, const float* __restrict__ P, const float* __restr
       if (k < KP) {
         float ap = 0.f, ev = 0.f;
         if (k < L.K) lane_operands<KK>(st, L, N, eta, d, lane, i, s, fd.a, &ap, &ev, nullptr, nullptr);
-        long long idx = (((long long)q * L.D + d) * SV + sv) * KP + k;
+        long long idx = ((long long)q * L.D + d) * SV * KP + rec_pos(KP, SV, sv, k);
         Ap[idx] = ap;
         EV[idx] = ev;
       }
@@ -158,10 +159,11 @@ backward_dk_kernel(Layout L, Hyper h, const float* __restrict__ P, const float* 
     for (int i = 0; i < KK; ++i) {
       int k = lane + 32 * i;
       if (k < L.K) {
-        long long idx = (((long long)q * L.D + d) * SV + sv) * KP + k;
+        const int rp = rec_pos(KP, SV, sv, k);
+        long long idx = ((long long)q * L.D + d) * SV * KP + rp;
         DkUp up;
         up.GAp = GAp[idx];
-        up.GEV = GEVnz[idx] - (float)zcolsum[((long long)q * SV + sv) * KP + k];
+        up.GEV = GEVnz[idx] - (float)zcolsum[(long long)q * SV * KP + rp];
         DkOut o = lane_step<KK>(st, L, h, N, G, eta, d, lane, i, s, a_d, up);
         da += o.da;
         scr_utau[((long long)s * L.D + d) * L.K + k] = o.dutau;
@@ -385,6 +387,11 @@ int spmf_kpad(int K) {
 }
 
 int spmf_draw_vec(int S) { return (S % 4 == 0) ? 4 : (S % 2 == 0) ? 2 : 1; }
+
+int spmf_rec_pos(int KP, int SV, int sv, int k) {
+  if (KP <= 0 || (KP & (KP - 1)) || SV <= 0 || sv < 0 || sv >= SV || k < 0 || k >= KP) return SPMF_ERR_BAD_ARG;
+  return rec_pos(KP, SV, sv, k);
+}
 
 int spmf_layout(int D, int K, int S, long long* tensor_offsets, long long* noise_offsets) {
   if (D <= 0 || K <= 0 || S <= 0 || K > SPMF_MAX_K) return SPMF_ERR_BAD_ARG;

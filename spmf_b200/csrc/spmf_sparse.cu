@@ -8,13 +8,14 @@
 // The -sum(rate) part of the Poisson log-likelihood is closed form and handled
 // by vsum / zcolsum / phisum, O(BK + KD).
 //
-// Thread mapping: see `Map` below -- operand records are [SV][KP] (k innermost), a slot of up to
-// 32 lanes owns one nonzero at a time, so a gather of one record is one coalesced SV*KP*4-byte read
-// and the k-contraction is in-lane FMAs plus a log2(RG)-step butterfly.
+// Thread mapping: see `Map` below and spmf_record.cuh -- a slot of LPN = SV*RG lanes owns one
+// nonzero at a time and gathers its record with VPL coalesced vector loads; every lane holds up to
+// 16 latent dims of one draw, so the k-contraction is in-lane FMAs plus log2(RG) shuffle steps.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 #include "../../include/spmf_b200.h"
+#include "spmf_record.cuh"
 
 namespace spmf {
 
@@ -32,12 +33,15 @@ template <int KP, int SV>
 struct Map {
   static constexpr int VW = KP < 4 ? KP : 4;            // floats per vector load (over k)
   static constexpr int NV = KP / VW;                     // k-vectors per draw
-  static constexpr int LPN = (SV * NV) < 32 ? (SV * NV) : 32;   // lanes per nonzero slot
-  static constexpr int RG = LPN / SV;                    // lanes sharing one draw
-  static constexpr int VPL = NV / RG;                    // vectors per lane
-  static constexpr int REC = SV * KP;                    // floats per operand record
+  static constexpr int VPL = NV < 4 ? NV : 4;            // vectors per lane (<= 16 latent dims)
+  static constexpr int RG = NV / VPL;                    // lanes sharing one draw
+  static constexpr int LPN = SV * RG;                    // lanes per nonzero slot (<= 32)
+  static constexpr int REC = SV * KP;                    // floats per record
   static constexpr int THREADS = 128;
   static constexpr int NSLOT = THREADS / LPN;            // slots per CTA
+  static constexpr int SPW = 32 / LPN;                   // slots per warp
+  // float offset of vector i of lane (s,kg) inside a record -- see spmf_record.cuh
+  __device__ static __forceinline__ int off(int i, int s, int kg) { return ((i * SV + s) * RG + kg) * VW; }
 };
 
 template <int VW>
@@ -79,6 +83,15 @@ template <int RG>
 __device__ __forceinline__ float group_sum(float v, unsigned mask) {
 #pragma unroll
   for (int o = RG / 2; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o);
+  return v;
+}
+
+// sum over the slots of a warp (lanes with equal position inside their slot); every lane of the
+// warp must call it.  The xor butterfly is symmetric, so all lanes end with identical bits.
+template <int LPN>
+__device__ __forceinline__ float warp_slot_sum(float v) {
+#pragma unroll
+  for (int o = LPN; o < 32; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
 
@@ -138,8 +151,9 @@ csr_rows_kernel(const long long* __restrict__ rowptr, const int* __restrict__ co
   using M = Map<KP, SV>;
   constexpr int VW = M::VW, LPN = M::LPN, RG = M::RG, VPL = M::VPL, REC = M::REC, NSLOT = M::NSLOT;
   constexpr int U = VPL >= 4 ? 2 : 4;
-  __shared__ __align__(16) float part[NSLOT * REC];
-  __shared__ float sc[NSLOT][SV][2];
+  constexpr int SPW = M::SPW, NWARP = 4;
+  __shared__ __align__(16) float part[NWARP * REC];
+  __shared__ float sc[NWARP][SV][2];
   const int lane = threadIdx.x & 31;
   const int slot = threadIdx.x / LPN;
   const int li = threadIdx.x % LPN;
@@ -148,7 +162,7 @@ csr_rows_kernel(const long long* __restrict__ rowptr, const int* __restrict__ co
   const unsigned gmask = slot_mask<LPN>(lane);
   int off[VPL];
 #pragma unroll
-  for (int i = 0; i < VPL; ++i) off[i] = s * KP + (i * RG + kg) * VW;
+  for (int i = 0; i < VPL; ++i) off[i] = M::off(i, s, kg);
 
   // Row-local index space [0,n).  The nonzero stream is consumed in aligned groups of U (one
   // 16-byte load for U columns, one for U values, shared by the whole slot): `head` elements up
@@ -212,21 +226,26 @@ csr_rows_kernel(const long long* __restrict__ rowptr, const int* __restrict__ co
       }
     }
   }
-  if constexpr (NSLOT > 1) {
+  // slot partials -> row total: shuffle across the slots of a warp, then the 4 warps through smem
+  const int warp = threadIdx.x >> 5;
+  const bool warp_lead = (lane < LPN);            // slot 0 of this warp
 #pragma unroll
-    for (int i = 0; i < VPL; ++i) stv<VW>(part + slot * REC + off[i], zz[i]);
-    __syncthreads();
+  for (int i = 0; i < VPL; ++i) {
 #pragma unroll
-    for (int i = 0; i < VPL; ++i) {
+    for (int w = 0; w < VW; ++w) zz[i][w] = warp_slot_sum<LPN>(zz[i][w]);
+    if (warp_lead) stv<VW>(part + warp * REC + off[i], zz[i]);
+  }
+  __syncthreads();
 #pragma unroll
-      for (int w = 0; w < VW; ++w) zz[i][w] = 0.f;
+  for (int i = 0; i < VPL; ++i) {
 #pragma unroll
-      for (int t = 0; t < NSLOT; ++t) {       // fixed order: every slot ends with the same bits
-        float a[VW];
-        ldv_s<VW>(a, part + t * REC + off[i]);
+    for (int w = 0; w < VW; ++w) zz[i][w] = 0.f;
 #pragma unroll
-        for (int w = 0; w < VW; ++w) zz[i][w] += a[w];
-      }
+    for (int t = 0; t < NWARP; ++t) {       // fixed order: every slot ends with the same bits
+      float a[VW];
+      ldv_s<VW>(a, part + t * REC + off[i]);
+#pragma unroll
+      for (int w = 0; w < VW; ++w) zz[i][w] += a[w];
     }
   }
   float* zq = z + ((size_t)q * nrows + row) * REC;
@@ -316,27 +335,31 @@ csr_rows_kernel(const long long* __restrict__ rowptr, const int* __restrict__ co
   }
   float xlog = xlog2 * 0.6931471805599453f;
   float fbad = (float)bad;
-  if constexpr (NSLOT > 1) {
-    __syncthreads();   // everyone is done reading `part` (z partials)
+  __syncthreads();   // everyone is done reading `part` (z partials)
+  xlog = warp_slot_sum<LPN>(xlog);
+  fbad = warp_slot_sum<LPN>(fbad);
 #pragma unroll
-    for (int i = 0; i < VPL; ++i) stv<VW>(part + slot * REC + off[i], dz[i]);
-    if (kg == 0) { sc[slot][s][0] = xlog; sc[slot][s][1] = fbad; }
-    __syncthreads();
-    if (slot != 0) return;
-    xlog = 0.f; fbad = 0.f;
+  for (int i = 0; i < VPL; ++i) {
 #pragma unroll
-    for (int t = 0; t < NSLOT; ++t) { xlog += sc[t][s][0]; fbad += sc[t][s][1]; }
+    for (int w = 0; w < VW; ++w) dz[i][w] = warp_slot_sum<LPN>(dz[i][w]);
+    if (warp_lead) stv<VW>(part + warp * REC + off[i], dz[i]);
+  }
+  if (warp_lead && kg == 0) { sc[warp][s][0] = xlog; sc[warp][s][1] = fbad; }
+  __syncthreads();
+  if (slot != 0) return;
+  xlog = 0.f; fbad = 0.f;
 #pragma unroll
-    for (int i = 0; i < VPL; ++i) {
+  for (int t = 0; t < NWARP; ++t) { xlog += sc[t][s][0]; fbad += sc[t][s][1]; }
 #pragma unroll
-      for (int w = 0; w < VW; ++w) dz[i][w] = 0.f;
+  for (int i = 0; i < VPL; ++i) {
 #pragma unroll
-      for (int t = 0; t < NSLOT; ++t) {
-        float a[VW];
-        ldv_s<VW>(a, part + t * REC + off[i]);
+    for (int w = 0; w < VW; ++w) dz[i][w] = 0.f;
 #pragma unroll
-        for (int w = 0; w < VW; ++w) dz[i][w] += a[w];
-      }
+    for (int t = 0; t < NWARP; ++t) {
+      float a[VW];
+      ldv_s<VW>(a, part + t * REC + off[i]);
+#pragma unroll
+      for (int w = 0; w < VW; ++w) dz[i][w] += a[w];
     }
   }
   // ---- closed-form parts and per-row scalars (slot 0 only from here)
@@ -373,7 +396,7 @@ csr_rows_kernel(const long long* __restrict__ rowptr, const int* __restrict__ co
 constexpr int kSliceLen = 256;
 
 template <int KP, int SV>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 4)
 csc_cols_kernel(const int* __restrict__ colptr, const int* __restrict__ rows,
                 const float* __restrict__ vals, int nnz, int nrows, int D,
                 const float* __restrict__ z, const float* __restrict__ dzr,
@@ -394,7 +417,7 @@ csc_cols_kernel(const int* __restrict__ colptr, const int* __restrict__ rows,
   const int j1 = min(j0 + kSliceLen, nnz);
   int off[VPL];
 #pragma unroll
-  for (int i = 0; i < VPL; ++i) off[i] = s * KP + (i * RG + kg) * VW;
+  for (int i = 0; i < VPL; ++i) off[i] = M::off(i, s, kg);
 
   const float* zl = z + (size_t)q * nrows * REC;
   const float* dl = dzr + (size_t)q * nrows * REC;

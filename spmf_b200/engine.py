@@ -85,7 +85,7 @@ class AdviEngine:
         self.inv_xi = 1.0
         self._ws = None
         self._side = None
-        self.stream_mode = os.environ.get("SPMF_STREAMS", "single")
+        self.stream_mode = os.environ.get("SPMF_STREAMS", "prio")
         self._max_rows = max_rows
         self.opt_step = 0
         self.rng_step = 0

@@ -234,10 +234,14 @@ class PoissonFactorization:
         EV = eta[None, :, None] * v.transpose(-1, -2)                # (S,D,K)
         PH = eta[None, :] * b * w[:, 0, :]                           # (S,D)
 
-        def pack(t):   # (S,D,K) -> [NQ][D][SV][KP]
+        perm = torch.tensor(_abi.rec_perm(ws.KP, ws.SV), device=self.device)
+
+        def pack(t):   # (S,D,K) -> [NQ][D][REC] in the kernels' record order
             o = torch.zeros(ws.NQ, D, ws.SV, ws.KP, **f32)
             o[:, :, :, :K] = t.view(ws.NQ, ws.SV, D, K).permute(0, 2, 1, 3)
-            return o.reshape(-1)
+            rec = torch.empty(ws.NQ, D, ws.SV * ws.KP, **f32)
+            rec[:, :, perm] = o.reshape(ws.NQ, D, ws.SV * ws.KP)
+            return rec.reshape(-1)
         ws.Ap.copy_(pack(Ap))
         ws.EV.copy_(pack(EV))
         ws.PH.copy_(PH.view(ws.NQ, ws.SV, D).permute(0, 2, 1).reshape(-1))
@@ -246,7 +250,9 @@ class PoissonFactorization:
 
     def _unpack_rows(self, eng, flat, nrows):
         ws = eng.ws
-        t = flat[:ws.NQ * nrows * ws.KP * ws.SV].view(ws.NQ, nrows, ws.SV, ws.KP)
+        perm = torch.tensor(_abi.rec_perm(ws.KP, ws.SV), device=flat.device)
+        t = flat[:ws.NQ * nrows * ws.KP * ws.SV].view(ws.NQ, nrows, ws.SV * ws.KP)[:, :, perm]
+        t = t.view(ws.NQ, nrows, ws.SV, ws.KP)
         return t.permute(0, 2, 1, 3).reshape(eng.S, nrows, ws.KP)[..., :self.latent_dim]
 
     def encode(self, x, u=None, s=None):
