@@ -118,6 +118,10 @@ int spmf_csr_colstats(const int* cols, const float* vals, long long nnz, int D, 
 /* CSR batch -> CSC batch (colptr[D+1], rows batch-local).  cursor: int[D+1] scratch. */
 int spmf_csr_to_csc(const long long* rowptr, const int* cols, const float* vals, int nrows, int D,
                     int* colptr, int* rows_out, float* vals_out, int* cursor, void* stream);
+/* compact transfer format of a CSR batch: uint16 column ids (D <= 65536) and / or uint16 counts,
+ * widened on the device (either source may be NULL = that array was sent at full width). */
+int spmf_csr_unpack16(const unsigned short* cols16, const unsigned short* vals16, long long nnz,
+                      int* cols, float* vals, void* stream);
 /* dense (B,D) fp32 counts -> CSR (rowptr[B+1] int64, cols, vals); two calls: count then fill. */
 int spmf_dense_count(const float* x, int nrows, int D, long long* rowptr, void* stream);
 int spmf_dense_fill(const float* x, int nrows, int D, const long long* rowptr, int* cols, float* vals,

@@ -622,6 +622,18 @@ __global__ void scatter_csc_kernel(const long long* __restrict__ rowptr, const i
   }
 }
 
+// compact host format -> device CSR arrays: uint16 column ids (D <= 65536) and/or uint16 counts
+__global__ void csr_unpack16_kernel(const unsigned short* __restrict__ c16,
+                                    const unsigned short* __restrict__ v16, long long nnz,
+                                    int* __restrict__ cols, float* __restrict__ vals) {
+  long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; j < nnz; j += stride) {
+    if (c16) cols[j] = (int)c16[j];
+    if (v16) vals[j] = (float)v16[j];
+  }
+}
+
 __global__ void dense_count_kernel(const float* __restrict__ x, int nrows, int D,
                                    long long* __restrict__ cnt) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -822,6 +834,17 @@ int spmf_csr_to_csc(const long long* rowptr, const int* cols, const float* vals,
   count_cols_kernel<<<148 * 8, 256, 0, st>>>(rowptr, cols, nrows, cursor);
   exscan_int_kernel<<<1, 1024, 0, st>>>(cursor, D, colptr, cursor);
   scatter_csc_kernel<<<(nrows + 3) / 4, 128, 0, st>>>(rowptr, cols, vals, nrows, cursor, rows_out, vals_out);
+  SPMF_CHECK_LAUNCH();
+  return SPMF_OK;
+}
+
+int spmf_csr_unpack16(const unsigned short* cols16, const unsigned short* vals16, long long nnz,
+                      int* cols, float* vals, void* stream) {
+  if ((!cols16 && !vals16) || (cols16 && !cols) || (vals16 && !vals) || nnz < 0) return SPMF_ERR_BAD_ARG;
+  if (nnz == 0) return SPMF_OK;
+  long long blocks = (nnz + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  csr_unpack16_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(cols16, vals16, nnz, cols, vals);
   SPMF_CHECK_LAUNCH();
   return SPMF_OK;
 }

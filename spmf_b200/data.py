@@ -231,8 +231,8 @@ def synth_scrna_csr_device(nrows, D, density=0.05, seed=0, device="cuda", sigma_
 @dataclass
 class HostCsrBatch:
     rowptr: torch.Tensor   # int64 [nrows+1], zero-based, pinned host
-    cols: torch.Tensor     # int32 [nnz], pinned host
-    vals: torch.Tensor     # fp32 [nnz], pinned host
+    cols: torch.Tensor     # int32 or uint16 (compact) [nnz], pinned host
+    vals: torch.Tensor     # fp32 or uint16 (compact) [nnz], pinned host
     D: int
 
     @property
@@ -244,32 +244,47 @@ class HostCsrBatch:
         return int(self.vals.numel())
 
     def nbytes(self):
-        return self.rowptr.numel() * 8 + self.cols.numel() * 4 + self.vals.numel() * 4
+        return (self.rowptr.numel() * 8 + self.cols.numel() * self.cols.element_size()
+                + self.vals.numel() * self.vals.element_size())
 
 
 class HostCsr:
-    """A CSR shard kept in pinned host memory; `batch()` slices are zero-copy views."""
+    """A CSR shard kept in pinned host memory; `batch()` slices are zero-copy views.
 
-    def __init__(self, rowptr, cols, vals, D):
+    compact=True stores column ids as uint16 when D <= 65536 and counts as uint16 when they are
+    integers <= 65535 (count data almost always is): 4 B instead of 8 B per nonzero cross PCIe and
+    a kernel widens them on the device."""
+
+    def __init__(self, rowptr, cols, vals, D, compact=True):
         self.rowptr = torch.as_tensor(rowptr).to(torch.int64).contiguous()
-        self.cols = torch.as_tensor(cols).to(torch.int32).contiguous().pin_memory()
-        self.vals = torch.as_tensor(vals).to(torch.float32).contiguous().pin_memory()
+        cols = torch.as_tensor(cols).to(torch.int32).contiguous()
+        vals = torch.as_tensor(vals).to(torch.float32).contiguous()
         self.D = int(D)
         self.nrows = self.rowptr.numel() - 1
+        if compact and self.D <= 65536:
+            cols = cols.to(torch.uint16)
+        if compact and vals.numel() and float(vals.max()) <= 65535 and float(vals.min()) >= 0 \
+                and bool((vals == vals.round()).all()):
+            vals = vals.to(torch.uint16)
+        self.cols, self.vals = cols.pin_memory(), vals.pin_memory()
 
     @classmethod
-    def from_shard(cls, shard: CsrShard):
-        return cls(shard.rowptr.cpu(), shard.cols.cpu(), shard.vals.cpu(), shard.D)
+    def from_shard(cls, shard: CsrShard, compact=True):
+        return cls(shard.rowptr.cpu(), shard.cols.cpu(), shard.vals.cpu(), shard.D, compact)
 
     def batch(self, row0, nrows) -> HostCsrBatch:
         j0, j1 = int(self.rowptr[row0]), int(self.rowptr[row0 + nrows])
         rp = (self.rowptr[row0:row0 + nrows + 1] - j0).contiguous().pin_memory()
         return HostCsrBatch(rp, self.cols[j0:j1], self.vals[j0:j1], self.D)
 
+    def iter_batches(self, batch_rows):
+        for r0 in range(0, self.nrows, batch_rows):
+            yield self.batch(r0, min(batch_rows, self.nrows - r0))
+
 
 class BatchUploader:
-    """Reusable device staging for host batches: async H2D of (rowptr, cols, vals), then the row
-    constants and the CSC copy are built by kernels on the same stream."""
+    """Reusable device staging for host batches: async H2D of (rowptr, cols, vals), widening of the
+    compact format, then the row constants and the CSC copy are built by kernels on the same stream."""
 
     def __init__(self, device, D, max_rows=0, max_nnz=0):
         self.device, self.D = torch.device(device), int(D)
@@ -278,24 +293,38 @@ class BatchUploader:
     def _alloc(self, rows, nnz):
         dev = self.device
         self.cap_rows, self.cap_nnz = int(rows), int(nnz)
+        n = max(nnz, 1) + 8
         self.rowptr = torch.empty(rows + 1, dtype=torch.int64, device=dev)
-        self.cols = torch.empty(max(nnz, 1), dtype=torch.int32, device=dev)
-        self.vals = torch.empty(max(nnz, 1), dtype=torch.float32, device=dev)
+        self.cols = torch.empty(n, dtype=torch.int32, device=dev)
+        self.vals = torch.empty(n, dtype=torch.float32, device=dev)
+        self.c16 = torch.empty(n, dtype=torch.uint16, device=dev)
+        self.v16 = torch.empty(n, dtype=torch.uint16, device=dev)
         self.rowsum = torch.empty(max(rows, 1), dtype=torch.float32, device=dev)
         self.lgam = torch.empty(max(rows, 1), dtype=torch.float32, device=dev)
         self.colptr = torch.empty(self.D + 1, dtype=torch.int32, device=dev)
         self.cursor = torch.empty(self.D + 1, dtype=torch.int32, device=dev)
-        self.crows = torch.empty(max(nnz, 1), dtype=torch.int32, device=dev)
-        self.cvals = torch.empty(max(nnz, 1), dtype=torch.float32, device=dev)
+        self.crows = torch.empty(n, dtype=torch.int32, device=dev)
+        self.cvals = torch.empty(n, dtype=torch.float32, device=dev)
 
     def upload(self, hb: HostCsrBatch) -> DeviceBatch:
         n, nnz = hb.nrows, hb.nnz
         if n > self.cap_rows or nnz > self.cap_nnz:
             self._alloc(max(n, self.cap_rows), max(int(nnz * 1.25), self.cap_nnz))
-        self.rowptr[:n + 1].copy_(hb.rowptr, non_blocking=True)
-        self.cols[:nnz].copy_(hb.cols, non_blocking=True)
-        self.vals[:nnz].copy_(hb.vals, non_blocking=True)
         st = _stream()
+        self.rowptr[:n + 1].copy_(hb.rowptr, non_blocking=True)
+        c16 = v16 = None
+        if hb.cols.dtype == torch.uint16:
+            c16 = self.c16[:nnz]
+            c16.copy_(hb.cols, non_blocking=True)
+        else:
+            self.cols[:nnz].copy_(hb.cols, non_blocking=True)
+        if hb.vals.dtype == torch.uint16:
+            v16 = self.v16[:nnz]
+            v16.copy_(hb.vals, non_blocking=True)
+        else:
+            self.vals[:nnz].copy_(hb.vals, non_blocking=True)
+        if c16 is not None or v16 is not None:
+            _abi.call("spmf_csr_unpack16", _ptr(c16), _ptr(v16), nnz, _ptr(self.cols), _ptr(self.vals), st)
         _abi.call("spmf_csr_row_consts", _ptr(self.rowptr), _ptr(self.vals), n, _ptr(self.rowsum),
                   _ptr(self.lgam), st)
         _abi.call("spmf_csr_to_csc", _ptr(self.rowptr), _ptr(self.cols), _ptr(self.vals), n, self.D,
@@ -303,3 +332,45 @@ class BatchUploader:
         return DeviceBatch(rowptr=self.rowptr[:n + 1], cols=self.cols, vals=self.vals,
                            rowsum=self.rowsum[:n], lgam=self.lgam[:n], nrows=n, nnz=nnz, D=self.D,
                            colptr=self.colptr, crows=self.crows, cvals=self.cvals)
+
+
+def prefetch_to_device(host_batches, device, depth=2):
+    """Generator: uploads HostCsrBatch items `depth` ahead on a copy stream (H2D, widening, row
+    constants, CSC build) while the consumer computes on the current stream.  What tf.data's
+    `prefetch(AUTOTUNE)` does for the reference's drivers (bin/factorize_csv.py:110-112)."""
+    device = torch.device(device)
+    it = iter(host_batches)
+    copy = torch.cuda.Stream(device=device)
+    ups, freed = {}, [None] * depth
+    queue = []
+
+    def issue(slot):
+        try:
+            hb = next(it)
+        except StopIteration:
+            return False
+        if not isinstance(hb, HostCsrBatch):
+            hb = hb["counts"] if isinstance(hb, dict) else hb
+        if slot not in ups:
+            ups[slot] = BatchUploader(device, hb.D)
+        if freed[slot] is not None:
+            copy.wait_event(freed[slot])            # the step that used this staging set is done
+        with torch.cuda.stream(copy):
+            db = ups[slot].upload(hb)
+            ev = torch.cuda.Event()
+            ev.record(copy)
+        queue.append((db, ev, slot))
+        return True
+
+    for sidx in range(depth):
+        if not issue(sidx):
+            break
+    while queue:
+        db, ev, slot = queue.pop(0)
+        main = torch.cuda.current_stream()
+        main.wait_event(ev)
+        yield db
+        done = torch.cuda.Event()
+        done.record(torch.cuda.current_stream())    # consumer has enqueued its step by now
+        freed[slot] = done
+        issue(slot)

@@ -384,7 +384,7 @@ class PoissonFactorization:
         for epoch in range(int(num_steps)):
             acc = torch.zeros((), dtype=torch.float64, device=self.device)
             nb, last = 0, None
-            for batch in iter(batched_data_factory()):
+            for batch in self._device_batches(batched_data_factory()):
                 last = self.elbo_step(batch, S, learning_rate=lr, clip_value=clip_value)
                 acc += last
                 nb += 1
@@ -429,6 +429,22 @@ class PoissonFactorization:
         return losses
 
     calibrate_advi = fit     # legacy name used by bin/factorize_csv.py:121-124
+
+    def _device_batches(self, batches):
+        """Host-resident CSR batches are uploaded one ahead on a copy stream; anything else passes through."""
+        from .data import HostCsrBatch, prefetch_to_device
+        it = iter(batches)
+        try:
+            first = next(it)
+        except StopIteration:
+            return iter(())
+        import itertools
+        chained = itertools.chain([first], it)
+        c = first[self.count_key] if isinstance(first, dict) else first
+        if isinstance(c, HostCsrBatch):
+            return prefetch_to_device((b[self.count_key] if isinstance(b, dict) else b for b in chained),
+                                      self.device)
+        return chained
 
     @staticmethod
     def _snapshot(eng):

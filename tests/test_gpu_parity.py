@@ -263,9 +263,21 @@ def test_streamed_host_batches_match_resident():
     eng.fill_noise(step=0)
     p0 = eng.loss_and_grad(sh.batch(B, B), fresh_noise=False).clone()
     g0 = eng.grads.clone()
+    assert host.cols.dtype == torch.uint16 and host.vals.dtype == torch.uint16      # compact transfer format
     p1 = eng.loss_and_grad(spmf_b200.as_device_batch(host.batch(B, B), dev), fresh_noise=False).clone()
     assert rel_err(p1.cpu().numpy(), p0.cpu().numpy()) < 1e-6
     assert rel_err(eng.grads.cpu().numpy(), g0.cpu().numpy()) < 2e-5
+    # prefetched stream of host batches: same batches, same order, same results
+    from spmf_b200.data import prefetch_to_device
+    wide = HostCsr.from_shard(sh, compact=False)
+    for hsrc in (host, wide):
+        got = []
+        for db in prefetch_to_device(hsrc.iter_batches(B), dev):
+            got.append(eng.loss_and_grad(db, fresh_noise=False)[:, 13:15].clone())
+        ref = [eng.loss_and_grad(sh.batch(i * B, B), fresh_noise=False)[:, 13:15].clone() for i in range(3)]
+        assert len(got) == 3
+        for a, b in zip(got, ref):
+            assert rel_err(a.cpu().numpy(), b.cpu().numpy()) < 1e-6
 
 
 def test_data_parallel_two_gpus():
