@@ -115,9 +115,10 @@ int spmf_colsum(const float* in, long long n, int c, int q, double* out, double*
  * accumulates the non-zero counter in fp32) over a CSR shard; accumulates (caller zeroes). */
 int spmf_csr_colstats(const int* cols, const float* vals, long long nnz, int D, double* colsum,
                       float* colnnz, void* stream);
-/* CSR batch -> CSC batch (colptr[D+1], rows batch-local).  cursor: int[D+1] scratch. */
+/* CSR batch -> CSC batch (colptr[D+1], rows batch-local).  scratch: spmf_csc_scratch_ints(D) ints. */
+long long spmf_csc_scratch_ints(int D);
 int spmf_csr_to_csc(const long long* rowptr, const int* cols, const float* vals, int nrows, int D,
-                    int* colptr, int* rows_out, float* vals_out, int* cursor, void* stream);
+                    int* colptr, int* rows_out, float* vals_out, int* scratch, void* stream);
 /* compact transfer format of a CSR batch: uint16 column ids (D <= 65536) and / or uint16 counts,
  * widened on the device (either source may be NULL = that array was sent at full width). */
 int spmf_csr_unpack16(const unsigned short* cols16, const unsigned short* vals16, long long nnz,

@@ -60,6 +60,7 @@ _SIGS = {
     "spmf_sumsq": (i32, [p, i64, p, p, p, p]),
     "spmf_colsum": (i32, [p, i64, i32, i32, p, p, p]),
     "spmf_csr_colstats": (i32, [p, p, i64, i32, p, p, p]),
+    "spmf_csc_scratch_ints": (i64, [i32]),
     "spmf_csr_to_csc": (i32, [p, p, p, i32, i32, p, p, p, p, p]),
     "spmf_csr_unpack16": (i32, [p, p, i64, p, p, p]),
     "spmf_dense_count": (i32, [p, i32, i32, p, p]),

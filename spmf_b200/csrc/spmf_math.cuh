@@ -37,6 +37,20 @@ SPMF_HD float sigmoidf(float x) {
 SPMF_HD float one_minus_sigmoidf(float x) { return sigmoidf(-x); }
 SPMF_HD float log_sigmoidf(float x) { return -softplusf(-x); }
 
+// softplus(t), sigmoid(t), 1 - sigmoid(t) and log sigmoid(t) from ONE exp, one log1p, one reciprocal
+struct Sp4 { float y, sg, oms, lsg; };
+SPMF_HD Sp4 softplus4(float t) {
+  const float e = expf(-fabsf(t));
+  const float l = log1pf(e);
+  const float r = 1.f / (1.f + e);
+  Sp4 o;
+  o.y = fmaxf(t, 0.f) + l;
+  o.sg = t >= 0.f ? r : e * r;
+  o.oms = t >= 0.f ? e * r : r;
+  o.lsg = fminf(t, 0.f) - l;
+  return o;
+}
+
 SPMF_HD float digammaf_pos(float x) {
   // x > 0.  Shift to x >= 6 with psi(x) = psi(x+1) - 1/x, then the asymptotic series.
   float acc = 0.f;

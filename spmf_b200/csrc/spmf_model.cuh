@@ -67,7 +67,7 @@ struct Hyper {
 
 // ---------------- Normal-based factor:  y = softplus(loc + softplus(rho) * eps) ----------------
 struct NParam { float loc, sig, logsig, acc_dt, acc_dte; };
-struct NDraw { float t, y, sg; };
+struct NDraw { float t, y, sg, oms, lsg; };   // pre-softplus t, softplus, sigmoid, 1-sigmoid, log sigmoid
 
 SPMF_HD NParam nparam_init(float loc, float rho) {
   float sig = softplusf(rho);
@@ -76,17 +76,17 @@ SPMF_HD NParam nparam_init(float loc, float rho) {
 SPMF_HD NDraw ndraw(const NParam& p, float eps) {
   NDraw d;
   d.t = fmaf(p.sig, eps, p.loc);
-  d.y = softplusf(d.t);
-  d.sg = sigmoidf(d.t);
+  const Sp4 f = softplus4(d.t);
+  d.y = f.y; d.sg = f.sg; d.oms = f.oms; d.lsg = f.lsg;
   return d;
 }
 // log q(y) = log N(t; loc, sig) - log sigmoid(t)     [EXT tfb.Softplus fldj]
 SPMF_HD float nlogq(const NParam& p, const NDraw& d, float eps) {
-  return -0.5f * eps * eps - p.logsig - kHalfLog2Pi - log_sigmoidf(d.t);
+  return -0.5f * eps * eps - p.logsig - kHalfLog2Pi - d.lsg;
 }
 // Gy = d loss_s / d y (data+prior part, already weighted); we = entropy weight
 SPMF_HD void nparam_bwd(NParam& p, const NDraw& d, float eps, float Gy, float we) {
-  float dt = Gy * d.sg - we * one_minus_sigmoidf(d.t);
+  float dt = Gy * d.sg - we * d.oms;
   p.acc_dt += dt;
   p.acc_dte += dt * eps;
 }
@@ -98,7 +98,7 @@ SPMF_HD void nparam_finish(const NParam& p, float rho, float invS, float we, flo
 
 // ------------- InverseGamma-based factor:  y = softplus(beta / g),  g ~ Gamma(alpha,1) -------------
 struct GParam { float alpha, beta, psi, c0, acc_da, acc_db; };   // c0 = -log(beta) - lgamma(alpha)
-struct GDraw { float t, y, sg, g; };
+struct GDraw { float t, y, sg, oms, lsg, g; };
 
 SPMF_HD GParam gparam_init(float conc_raw, float scale_raw) {
   GParam p;
@@ -114,19 +114,19 @@ SPMF_HD GDraw gdraw(const GParam& p, float g) {
   GDraw d;
   d.g = g;
   d.t = p.beta / g;
-  d.y = softplusf(d.t);
-  d.sg = sigmoidf(d.t);
+  const Sp4 f = softplus4(d.t);
+  d.y = f.y; d.sg = f.sg; d.oms = f.oms; d.lsg = f.lsg;
   return d;
 }
 // log q(y) = log InvGamma(t; alpha, beta) - log sigmoid(t), with beta/t = g, log t = log beta - log g
 SPMF_HD float glogq(const GParam& p, const GDraw& d) {
-  return p.c0 + (p.alpha + 1.f) * logf(d.g) - d.g - log_sigmoidf(d.t);
+  return p.c0 + (p.alpha + 1.f) * logf(d.g) - d.g - d.lsg;
 }
 // dgda = d g / d alpha of the Gamma draw (implicit reparameterisation), precomputed per draw by
 // gamma_grad_kernel since it depends on (alpha, g) only.
 SPMF_HD void gparam_bwd(GParam& p, const GDraw& d, float dgda, float Gy, float we) {
   float g = d.g;
-  float dlogq_dt = (g / p.beta) * (g - (p.alpha + 1.f)) - one_minus_sigmoidf(d.t);
+  float dlogq_dt = (g / p.beta) * (g - (p.alpha + 1.f)) - d.oms;
   float dt = Gy * d.sg + we * dlogq_dt;
   p.acc_da += we * (logf(g) - p.psi) - dt * (p.beta / (g * g)) * dgda;
   p.acc_db += we * (p.alpha - g) / p.beta + dt / g;

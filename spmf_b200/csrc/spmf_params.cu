@@ -135,7 +135,7 @@ __global__ void sample_kernel(Layout L, const float* __restrict__ P, const float
 // (needed by the per-feature kernel), the per-(s,d,k) contribution to d prior_u / d u_tau, and
 // this feature's share of the prior / log q sums.
 template <int KK>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, KK == 1 ? 6 : 3)
 backward_dk_kernel(Layout L, Hyper h, const float* __restrict__ P, const float* __restrict__ N,
                    const float* __restrict__ G, const float* __restrict__ eta, int SV, int KP,
                    const float* __restrict__ GAp, const float* __restrict__ GEVnz,
@@ -357,6 +357,59 @@ static int nsplit_for(long long n) {
   return (int)s;
 }
 
+// Two independent column-sum jobs per launch (they always come in pairs around the data term).
+struct RJob { const void* in; double* out; long long n; int c, q, ns; };
+
+template <typename TIn>
+__global__ void reduce_rows2_kernel(RJob A, RJob B) {
+  __shared__ double sm[8][33];
+  const bool isB = (int)blockIdx.z >= A.q;
+  const RJob J = isB ? B : A;
+  const int q = isB ? blockIdx.z - A.q : blockIdx.z;
+  const int split = blockIdx.y;
+  if (split >= J.ns || (int)blockIdx.x * 32 >= J.c) return;
+  const int cx = blockIdx.x * 32 + threadIdx.x;
+  const long long chunk = (J.n + J.ns - 1) / J.ns;
+  const long long r0 = split * chunk;
+  long long r1 = r0 + chunk;
+  if (r1 > J.n) r1 = J.n;
+  double acc = 0.0;
+  if (cx < J.c) {
+    const TIn* base = (const TIn*)J.in + (long long)q * J.n * J.c + cx;
+    for (long long r = r0 + threadIdx.y; r < r1; r += 8) acc += (double)base[r * J.c];
+  }
+  sm[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && cx < J.c) {
+    double t = 0.0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t += sm[j][threadIdx.x];
+    J.out[((long long)q * J.ns + split) * J.c + cx] = t;
+  }
+}
+
+// outA/outB = column sums of two float arrays; 2 launches in total (fixed summation order).
+static int reduce_rows_pair(const float* inA, double* outA, long long nA, int cA, int qA,
+                            const float* inB, double* outB, long long nB, int cB, int qB,
+                            double* scratch, cudaStream_t st) {
+  if (nA <= 0 || cA <= 0 || qA <= 0 || nB <= 0 || cB <= 0 || qB <= 0) return SPMF_ERR_BAD_ARG;
+  const int nsA = nsplit_for(nA), nsB = nsplit_for(nB);
+  double* pA = scratch;
+  double* pB = scratch + (long long)qA * nsA * cA;
+  const int cmax = cA > cB ? cA : cB, nsmax = nsA > nsB ? nsA : nsB;
+  dim3 blk(32, 8);
+  RJob a1{inA, nsA == 1 ? outA : pA, nA, cA, qA, nsA}, b1{inB, nsB == 1 ? outB : pB, nB, cB, qB, nsB};
+  reduce_rows2_kernel<float><<<dim3((cmax + 31) / 32, nsmax, qA + qB), blk, 0, st>>>(a1, b1);
+  if (nsA > 1 || nsB > 1) {
+    // second stage over the split partials; a job that needed no split gets an empty descriptor
+    RJob a2{pA, outA, nsA, cA, nsA > 1 ? qA : 0, 1}, b2{pB, outB, nsB, cB, nsB > 1 ? qB : 0, 1};
+    if (a2.q + b2.q > 0)
+      reduce_rows2_kernel<double><<<dim3((cmax + 31) / 32, 1, a2.q + b2.q), blk, 0, st>>>(a2, b2);
+  }
+  SPMF_CHECK_LAUNCH();
+  return SPMF_OK;
+}
+
 // out (double[q][c]) = column sums of in[q][n][c]; scratch needs q*nsplit*c doubles.
 template <typename TIn>
 static int reduce_rows(const TIn* in, double* out, double* scratch, long long n, int c, int q,
@@ -445,9 +498,7 @@ int spmf_draw_operands(const float* params, const float* noise, const float* eta
   else if (KP <= 64) draw_operands_kernel<2><<<grid, 128, 0, st>>>(L, params, noise, eta, SV, KP, Ap, EV, PH);
   else draw_operands_kernel<4><<<grid, 128, 0, st>>>(L, params, noise, eta, SV, KP, Ap, EV, PH);
   SPMF_CHECK_LAUNCH();
-  int rc = reduce_rows<float>(EV, vsum, scratch, D, KP * SV, NQ, st);
-  if (rc) return rc;
-  return reduce_rows<float>(PH, phisum, scratch, D, SV, NQ, st);
+  return reduce_rows_pair(EV, vsum, D, KP * SV, NQ, PH, phisum, D, SV, NQ, scratch, st);
 }
 
 int spmf_gamma_grad(const float* params, const float* noise, int D, int K, int S, float* dgda,
@@ -492,9 +543,7 @@ int spmf_backward_params(const float* params, const float* noise, const float* d
   else backward_dk_kernel<4><<<grid, 128, 0, st>>>(L, h, params, noise, dgda, eta, SV, KP, GAp, GEVnz, zcolsum, grads, scr_utau, scr_parts, scr_da);
   backward_feat_kernel<<<(D + 127) / 128, 128, 0, st>>>(L, h, params, noise, dgda, eta, SV, Gphinz, scr_da, grads, scr_parts);
   SPMF_CHECK_LAUNCH();
-  int rc = reduce_rows<float>(scr_utau, dutau, rscr, D, K, S, st);
-  if (rc) return rc;
-  rc = reduce_rows<float>(scr_parts, featparts, rscr, D, S * NUM_PARTS, 1, st);
+  int rc = reduce_rows_pair(scr_utau, dutau, D, K, S, scr_parts, featparts, D, S * NUM_PARTS, 1, rscr, st);
   if (rc) return rc;
   backward_lat_kernel<<<(K + 63) / 64, 64, 0, st>>>(L, h, params, noise, dgda, dutau, grads, scr_lat);
   SPMF_CHECK_LAUNCH();
@@ -514,7 +563,8 @@ long long spmf_backward_scratch_floats(int D, int K, int S) {
 long long spmf_backward_scratch_doubles(int D, int K, int S) {
   long long c = (long long)S * NUM_PARTS;
   if (c < K) c = K;
-  return (long long)S * K + 2LL * S * NUM_PARTS + 64LL * S * c + 64LL * spmf_kpad(K) * S + 1024;
+  return (long long)S * K + 2LL * S * NUM_PARTS + 64LL * S * (K + NUM_PARTS) + 64LL * S * c +
+         64LL * (spmf_kpad(K) + 8) * S + 1024;
 }
 
 int spmf_adam_step(float* params, const float* grads, float* m, float* v, long long n, float lr,
@@ -548,9 +598,8 @@ int spmf_batch_sums(const float* z, const float* rowacc, int nrows, int K, int S
   if (!z || !rowacc || !zcolsum || !datasums || !scratch || nrows <= 0 || K <= 0 || K > SPMF_MAX_K || S <= 0)
     return SPMF_ERR_BAD_ARG;
   const int KP = spmf_kpad(K), SV = spmf_draw_vec(S), NQ = S / SV;
-  int rc = reduce_rows<float>(z, zcolsum, scratch, nrows, KP * SV, NQ, (cudaStream_t)stream);
-  if (rc) return rc;
-  return reduce_rows<float>(rowacc, datasums, scratch, nrows, 4 * SV, NQ, (cudaStream_t)stream);
+  return reduce_rows_pair(z, zcolsum, nrows, KP * SV, NQ, rowacc, datasums, nrows, 4 * SV, NQ, scratch,
+                          (cudaStream_t)stream);
 }
 
 int spmf_colsum(const float* in, long long n, int c, int q, double* out, double* scratch, void* stream) {

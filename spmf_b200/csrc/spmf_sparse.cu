@@ -527,6 +527,14 @@ csc_cols_kernel(const int* __restrict__ colptr, const int* __restrict__ rows,
 }
 
 // ------------------------------------------------------------------ data-format kernels
+// lgamma(x+1) for integer counts x < 64 (almost every entry of a count matrix)
+__constant__ float kLgamTab[64] = {0f, 0f, 0.693147181f, 1.79175947f, 3.17805383f, 4.78749174f, 6.57925121f, 8.52516136f, 10.6046029f, 12.8018275f, 15.1044126f, 17.5023078f, 19.9872145f, 22.5521639f, 25.1912212f, 27.8992714f, 30.6718601f, 33.5050735f, 36.3954452f, 39.3398842f, 42.3356165f, 45.3801389f, 48.4711814f, 51.6066756f, 54.7847294f, 58.0036052f, 61.2617018f, 64.5575386f, 67.8897431f, 71.257039f, 74.6582363f, 78.0922236f, 81.5579595f, 85.054467f, 88.5808275f, 92.1361756f, 95.7196945f, 99.3306125f, 102.968199f, 106.63176f, 110.32064f, 114.034212f, 117.771881f, 121.533082f, 125.317271f, 129.123934f, 132.952575f, 136.802723f, 140.673924f, 144.565744f, 148.477767f, 152.409593f, 156.360836f, 160.331128f, 164.320112f, 168.327445f, 172.352797f, 176.395848f, 180.456291f, 184.533829f, 188.628173f, 192.739047f, 196.866182f, 201.009316f};
+
+__device__ __forceinline__ float lgamma1p_count(float x) {
+  const int i = (int)x;
+  return (x >= 0.f && x < 64.f && (float)i == x) ? kLgamTab[i] : lgammaf(x + 1.f);
+}
+
 __global__ void csr_row_consts_kernel(const long long* __restrict__ rowptr,
                                       const float* __restrict__ vals, long long nrows,
                                       float* __restrict__ rowsum, float* __restrict__ lgam) {
@@ -538,7 +546,7 @@ __global__ void csr_row_consts_kernel(const long long* __restrict__ rowptr,
   for (long long j = j0 + lane; j < j1; j += 32) {
     const float x = __ldg(vals + j);
     s += x;
-    l += lgammaf(x + 1.f);
+    l += lgamma1p_count(x);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -567,6 +575,76 @@ __global__ void count_cols_kernel(const long long* __restrict__ rowptr, const in
   long long j = base + (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (; j < end; j += stride) atomicAdd(cnt + __ldg(cols + j), 1);
+}
+
+// ---- block-partitioned transpose (D*4 bytes fit in shared memory) -------------------------------
+// The batch's rows are cut into kTrBlocks contiguous ranges of equal nonzero count.  Pass 1: each
+// CTA histograms its range's columns in shared memory.  Pass 2: per column, exclusive scan over the
+// CTAs.  Pass 3: each CTA scatters its range with shared-memory cursors.  No global atomics, and
+// column segments come out ordered by row block.
+constexpr int kTrBlocks = 148;
+constexpr int kTrThreads = 1024;
+
+__device__ __forceinline__ int tr_row_bound(const long long* __restrict__ rowptr, int nrows, long long target) {
+  int lo = 0, hi = nrows;        // first row r with rowptr[r] >= target
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (rowptr[mid] < target) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+__global__ void __launch_bounds__(kTrThreads)
+csc_block_hist_kernel(const long long* __restrict__ rowptr, const int* __restrict__ cols, int nrows,
+                      int D, int* __restrict__ blockhist) {
+  extern __shared__ int h[];
+  for (int d = threadIdx.x; d < D; d += blockDim.x) h[d] = 0;
+  __syncthreads();
+  const long long base = rowptr[0], nnz = rowptr[nrows] - base;
+  const int r0 = tr_row_bound(rowptr, nrows, base + nnz * blockIdx.x / gridDim.x);
+  const int r1 = (blockIdx.x + 1 == gridDim.x) ? nrows
+                                               : tr_row_bound(rowptr, nrows, base + nnz * (blockIdx.x + 1) / gridDim.x);
+  const long long j0 = rowptr[r0], j1 = rowptr[r1];
+  for (long long j = j0 + threadIdx.x; j < j1; j += blockDim.x) atomicAdd(&h[__ldg(cols + j)], 1);
+  __syncthreads();
+  int* out = blockhist + (long long)blockIdx.x * D;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) out[d] = h[d];
+}
+
+__global__ void csc_block_scan_kernel(int* __restrict__ blockhist, int nblocks, int D, int* __restrict__ colcnt) {
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= D) return;
+  int run = 0;
+  for (int b = 0; b < nblocks; ++b) {
+    const int t = blockhist[(long long)b * D + d];
+    blockhist[(long long)b * D + d] = run;
+    run += t;
+  }
+  colcnt[d] = run;
+}
+
+__global__ void __launch_bounds__(kTrThreads)
+csc_block_scatter_kernel(const long long* __restrict__ rowptr, const int* __restrict__ cols,
+                         const float* __restrict__ vals, int nrows, int D,
+                         const int* __restrict__ colptr, const int* __restrict__ blockhist,
+                         int* __restrict__ rows_out, float* __restrict__ vals_out) {
+  extern __shared__ int cur[];
+  const int* bh = blockhist + (long long)blockIdx.x * D;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) cur[d] = colptr[d] + bh[d];
+  __syncthreads();
+  const long long base = rowptr[0], nnz = rowptr[nrows] - base;
+  const int r0 = tr_row_bound(rowptr, nrows, base + nnz * blockIdx.x / gridDim.x);
+  const int r1 = (blockIdx.x + 1 == gridDim.x) ? nrows
+                                               : tr_row_bound(rowptr, nrows, base + nnz * (blockIdx.x + 1) / gridDim.x);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  for (int row = r0 + warp; row < r1; row += nwarp) {
+    const long long j0 = rowptr[row], j1 = rowptr[row + 1];
+    for (long long j = j0 + lane; j < j1; j += 32) {
+      const int pos = atomicAdd(&cur[__ldg(cols + j)], 1);
+      rows_out[pos] = row;
+      vals_out[pos] = __ldg(vals + j);
+    }
+  }
 }
 
 // single-block exclusive scan: out[0..n] (n+1 entries), also copies to cursor
@@ -824,16 +902,36 @@ int spmf_csr_colstats(const int* cols, const float* vals, long long nnz, int D, 
   return SPMF_OK;
 }
 
+long long spmf_csc_scratch_ints(int D) { return (long long)(kTrBlocks + 1) * ((long long)D + 1); }
+
 int spmf_csr_to_csc(const long long* rowptr, const int* cols, const float* vals, int nrows, int D,
-                    int* colptr, int* rows_out, float* vals_out, int* cursor, void* stream) {
-  if (!rowptr || !cols || !vals || !colptr || !rows_out || !vals_out || !cursor) return SPMF_ERR_BAD_ARG;
+                    int* colptr, int* rows_out, float* vals_out, int* scratch, void* stream) {
+  if (!rowptr || !cols || !vals || !colptr || !rows_out || !vals_out || !scratch) return SPMF_ERR_BAD_ARG;
   if (nrows <= 0 || D <= 0) return SPMF_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
-  cudaError_t e = cudaMemsetAsync(cursor, 0, (size_t)(D + 1) * sizeof(int), st);
-  if (e != cudaSuccess) return (int)e;
-  count_cols_kernel<<<148 * 8, 256, 0, st>>>(rowptr, cols, nrows, cursor);
-  exscan_int_kernel<<<1, 1024, 0, st>>>(cursor, D, colptr, cursor);
-  scatter_csc_kernel<<<(nrows + 3) / 4, 128, 0, st>>>(rowptr, cols, vals, nrows, cursor, rows_out, vals_out);
+  int* colcnt = scratch;                       // [D+1]
+  int* blockhist = scratch + (D + 1);          // [kTrBlocks][D]
+  const size_t smem = (size_t)D * sizeof(int);
+  if (smem <= 200 * 1024) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaFuncSetAttribute(csc_block_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      cudaFuncSetAttribute(csc_block_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      attr_set = true;
+    }
+    const int nb = nrows < kTrBlocks ? nrows : kTrBlocks;
+    csc_block_hist_kernel<<<nb, kTrThreads, smem, st>>>(rowptr, cols, nrows, D, blockhist);
+    csc_block_scan_kernel<<<(D + 255) / 256, 256, 0, st>>>(blockhist, nb, D, colcnt);
+    exscan_int_kernel<<<1, 1024, 0, st>>>(colcnt, D, colptr, nullptr);
+    csc_block_scatter_kernel<<<nb, kTrThreads, smem, st>>>(rowptr, cols, vals, nrows, D, colptr, blockhist,
+                                                          rows_out, vals_out);
+  } else {                                     // very wide matrices: global atomic cursors
+    cudaError_t e = cudaMemsetAsync(colcnt, 0, (size_t)(D + 1) * sizeof(int), st);
+    if (e != cudaSuccess) return (int)e;
+    count_cols_kernel<<<148 * 8, 256, 0, st>>>(rowptr, cols, nrows, colcnt);
+    exscan_int_kernel<<<1, 1024, 0, st>>>(colcnt, D, colptr, colcnt);
+    scatter_csc_kernel<<<(nrows + 3) / 4, 128, 0, st>>>(rowptr, cols, vals, nrows, colcnt, rows_out, vals_out);
+  }
   SPMF_CHECK_LAUNCH();
   return SPMF_OK;
 }

@@ -46,7 +46,7 @@ class DeviceBatch:
             self.colptr = torch.empty(self.D + 1, dtype=torch.int32, device=dev)
             self.crows = torch.empty(max(self.nnz, 1), dtype=torch.int32, device=dev)
             self.cvals = torch.empty(max(self.nnz, 1), dtype=torch.float32, device=dev)
-            cursor = torch.empty(self.D + 1, dtype=torch.int32, device=dev)
+            cursor = torch.empty(_abi._lib.spmf_csc_scratch_ints(self.D), dtype=torch.int32, device=dev)
             _abi.call("spmf_csr_to_csc", _ptr(self.rowptr), _ptr(self.cols), _ptr(self.vals),
                       self.nrows, self.D, _ptr(self.colptr), _ptr(self.crows), _ptr(self.cvals),
                       _ptr(cursor), _stream())
@@ -302,7 +302,7 @@ class BatchUploader:
         self.rowsum = torch.empty(max(rows, 1), dtype=torch.float32, device=dev)
         self.lgam = torch.empty(max(rows, 1), dtype=torch.float32, device=dev)
         self.colptr = torch.empty(self.D + 1, dtype=torch.int32, device=dev)
-        self.cursor = torch.empty(self.D + 1, dtype=torch.int32, device=dev)
+        self.cursor = torch.empty(_abi._lib.spmf_csc_scratch_ints(self.D), dtype=torch.int32, device=dev)
         self.crows = torch.empty(n, dtype=torch.int32, device=dev)
         self.cvals = torch.empty(n, dtype=torch.float32, device=dev)
 
