@@ -528,7 +528,7 @@ csc_cols_kernel(const int* __restrict__ colptr, const int* __restrict__ rows,
 
 // ------------------------------------------------------------------ data-format kernels
 // lgamma(x+1) for integer counts x < 64 (almost every entry of a count matrix)
-__constant__ float kLgamTab[64] = {0f, 0f, 0.693147181f, 1.79175947f, 3.17805383f, 4.78749174f, 6.57925121f, 8.52516136f, 10.6046029f, 12.8018275f, 15.1044126f, 17.5023078f, 19.9872145f, 22.5521639f, 25.1912212f, 27.8992714f, 30.6718601f, 33.5050735f, 36.3954452f, 39.3398842f, 42.3356165f, 45.3801389f, 48.4711814f, 51.6066756f, 54.7847294f, 58.0036052f, 61.2617018f, 64.5575386f, 67.8897431f, 71.257039f, 74.6582363f, 78.0922236f, 81.5579595f, 85.054467f, 88.5808275f, 92.1361756f, 95.7196945f, 99.3306125f, 102.968199f, 106.63176f, 110.32064f, 114.034212f, 117.771881f, 121.533082f, 125.317271f, 129.123934f, 132.952575f, 136.802723f, 140.673924f, 144.565744f, 148.477767f, 152.409593f, 156.360836f, 160.331128f, 164.320112f, 168.327445f, 172.352797f, 176.395848f, 180.456291f, 184.533829f, 188.628173f, 192.739047f, 196.866182f, 201.009316f};
+__constant__ float kLgamTab[64] = {0.000000000e+00f, 0.000000000e+00f, 6.931471806e-01f, 1.791759469e+00f, 3.178053830e+00f, 4.787491743e+00f, 6.579251212e+00f, 8.525161361e+00f, 1.060460290e+01f, 1.280182748e+01f, 1.510441257e+01f, 1.750230785e+01f, 1.998721450e+01f, 2.255216385e+01f, 2.519122118e+01f, 2.789927138e+01f, 3.067186011e+01f, 3.350507345e+01f, 3.639544521e+01f, 3.933988419e+01f, 4.233561646e+01f, 4.538013890e+01f, 4.847118135e+01f, 5.160667557e+01f, 5.478472940e+01f, 5.800360522e+01f, 6.126170176e+01f, 6.455753863e+01f, 6.788974314e+01f, 7.125703897e+01f, 7.465823635e+01f, 7.809222355e+01f, 8.155795946e+01f, 8.505446702e+01f, 8.858082754e+01f, 9.213617560e+01f, 9.571969454e+01f, 9.933061245e+01f, 1.029681986e+02f, 1.066317603e+02f, 1.103206397e+02f, 1.140342118e+02f, 1.177718814e+02f, 1.215330815e+02f, 1.253172711e+02f, 1.291239336e+02f, 1.329525750e+02f, 1.368027226e+02f, 1.406739236e+02f, 1.445657439e+02f, 1.484777670e+02f, 1.524095926e+02f, 1.563608363e+02f, 1.603311282e+02f, 1.643201123e+02f, 1.683274454e+02f, 1.723527971e+02f, 1.763958484e+02f, 1.804562914e+02f, 1.845338289e+02f, 1.886281734e+02f, 1.927390473e+02f, 1.968661817e+02f, 2.010093164e+02f};
 
 __device__ __forceinline__ float lgamma1p_count(float x) {
   const int i = (int)x;
@@ -615,10 +615,15 @@ __global__ void csc_block_scan_kernel(int* __restrict__ blockhist, int nblocks, 
   const int d = blockIdx.x * blockDim.x + threadIdx.x;
   if (d >= D) return;
   int run = 0;
-  for (int b = 0; b < nblocks; ++b) {
-    const int t = blockhist[(long long)b * D + d];
-    blockhist[(long long)b * D + d] = run;
-    run += t;
+  for (int b0 = 0; b0 < nblocks; b0 += 16) {          // 16 independent loads in flight per thread
+    int t[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) t[i] = (b0 + i < nblocks) ? blockhist[(long long)(b0 + i) * D + d] : 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      if (b0 + i < nblocks) blockhist[(long long)(b0 + i) * D + d] = run;
+      run += t[i];
+    }
   }
   colcnt[d] = run;
 }
@@ -921,7 +926,7 @@ int spmf_csr_to_csc(const long long* rowptr, const int* cols, const float* vals,
     }
     const int nb = nrows < kTrBlocks ? nrows : kTrBlocks;
     csc_block_hist_kernel<<<nb, kTrThreads, smem, st>>>(rowptr, cols, nrows, D, blockhist);
-    csc_block_scan_kernel<<<(D + 255) / 256, 256, 0, st>>>(blockhist, nb, D, colcnt);
+    csc_block_scan_kernel<<<(D + 63) / 64, 64, 0, st>>>(blockhist, nb, D, colcnt);
     exscan_int_kernel<<<1, 1024, 0, st>>>(colcnt, D, colptr, nullptr);
     csc_block_scatter_kernel<<<nb, kTrThreads, smem, st>>>(rowptr, cols, vals, nrows, D, colptr, blockhist,
                                                           rows_out, vals_out);
