@@ -128,6 +128,53 @@ int spmf_dense_count(const float* x, int nrows, int D, long long* rowptr, void* 
 int spmf_dense_fill(const float* x, int nrows, int D, const long long* rowptr, int* cols, float* vals,
                     void* stream);
 
+/* ---- one call per step / per uploaded batch ----
+ * spmf_advi_step issues the whole sequence above (noise, Gamma gradients, operands, row pass, sums,
+ * column pass, backward, optional Adam) from native code.  Streams: `caller_stream` is the stream
+ * the caller orders its work on; if `hot_stream` / `side_stream` are given (with the three events)
+ * the data-term path runs on `hot_stream`, the Gamma work on `side_stream`, fork/join by events,
+ * and `caller_stream` waits for the result.  The ev_rows/ev_cols events, if non-NULL, bracket the
+ * two hot kernels (bench instrumentation).  adam_lr <= 0 skips the optimiser (multi-GPU: all-reduce
+ * the gradient block first, then call spmf_adam_step). */
+typedef struct spmf_step_args {
+  /* model */
+  int D, K, S, world_size;
+  float u_tau_scale, s_tau_scale, decay, w_entropy, w_prior;
+  float inv_xi;
+  int scale_rows;
+  /* noise */
+  int fresh_noise;
+  unsigned int rng_step;
+  unsigned long long seed;
+  /* flat buffers */
+  float *params, *grads, *adam_m, *adam_v, *noise, *dgda;
+  const float* eta;
+  long long n_params, comm_off, comm_slack;
+  /* workspace */
+  float *Ap, *EV, *PH, *GAp, *GEV, *Gph, *z, *dzr, *rowacc, *scr_f;
+  double *vsum, *phisum, *zcolsum, *datasums, *parts, *scr_d;
+  /* batch */
+  const long long* rowptr;
+  const int* cols;
+  const float* vals;
+  const float *rowsum, *lgam;
+  const int *colptr, *crows;
+  const float* cvals;
+  int nrows, nnz;
+  /* optimiser */
+  float adam_lr, adam_beta1, adam_beta2, adam_eps, clip_value;
+  int adam_t;
+  /* streams / events (cudaStream_t / cudaEvent_t) */
+  void *caller_stream, *hot_stream, *side_stream;
+  void *ev_fork, *ev_join, *ev_done;
+  void *ev_rows0, *ev_rows1, *ev_cols0, *ev_cols1;
+} spmf_step_args;
+int spmf_advi_step(const spmf_step_args* args);
+/* widen a compact batch (either 16-bit source may be NULL), build its row constants and CSC copy */
+int spmf_prepare_batch(const unsigned short* cols16, const unsigned short* vals16, const long long* rowptr,
+                       int* cols, float* vals, int nrows, long long nnz, int D, float* rowsum, float* lgam,
+                       int* colptr, int* crows, float* cvals, int* scratch, void* stream);
+
 const char* spmf_version(void);
 
 #ifdef __cplusplus

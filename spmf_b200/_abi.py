@@ -68,6 +68,30 @@ _SIGS = {
     "spmf_version": (C.c_char_p, []),
 }
 
+
+
+class StepArgs(C.Structure):
+    """Mirror of `spmf_step_args` (include/spmf_b200.h), field for field."""
+    _fields_ = (
+        [(n, i32) for n in ("D", "K", "S", "world_size")]
+        + [(n, f32) for n in ("u_tau_scale", "s_tau_scale", "decay", "w_entropy", "w_prior", "inv_xi")]
+        + [("scale_rows", i32), ("fresh_noise", i32), ("rng_step", u32), ("seed", u64)]
+        + [(n, p) for n in ("params", "grads", "adam_m", "adam_v", "noise", "dgda", "eta")]
+        + [(n, i64) for n in ("n_params", "comm_off", "comm_slack")]
+        + [(n, p) for n in ("Ap", "EV", "PH", "GAp", "GEV", "Gph", "z", "dzr", "rowacc", "scr_f",
+                            "vsum", "phisum", "zcolsum", "datasums", "parts", "scr_d",
+                            "rowptr", "cols", "vals", "rowsum", "lgam", "colptr", "crows", "cvals")]
+        + [("nrows", i32), ("nnz", i32)]
+        + [(n, f32) for n in ("adam_lr", "adam_beta1", "adam_beta2", "adam_eps", "clip_value")]
+        + [("adam_t", i32)]
+        + [(n, p) for n in ("caller_stream", "hot_stream", "side_stream", "ev_fork", "ev_join", "ev_done",
+                            "ev_rows0", "ev_rows1", "ev_cols0", "ev_cols1")]
+    )
+
+
+_SIGS["spmf_advi_step"] = (i32, [C.POINTER(StepArgs)])
+_SIGS["spmf_prepare_batch"] = (i32, [p, p, p, p, p, i32, i64, i32, p, p, p, p, p, p, p])
+
 EXPORTS = tuple(_SIGS)
 
 for _name, (_res, _args) in _SIGS.items():

@@ -1,0 +1,85 @@
+// One ADVI step (and one batch upload) as a single C-ABI call each: the whole launch sequence is
+// issued from native code so the host language pays one FFI crossing per step instead of one per
+// kernel.  Same sequence as the individual entry points; see include/spmf_b200.h.
+//
+// Replaces, per minibatch, bayesianquilts' minibatch_fit_surrogate_posterior body [EXT L3/L4]
+// around PoissonFactorization.unormalized_log_prob (poisson.py:575-621).
+#include <cuda_runtime.h>
+
+#include "../../include/spmf_b200.h"
+
+#define STEP_TRY(call)            \
+  do {                            \
+    int rc__ = (call);            \
+    if (rc__ != SPMF_OK) return rc__; \
+  } while (0)
+#define CUDA_TRY(call)                         \
+  do {                                         \
+    cudaError_t e__ = (call);                  \
+    if (e__ != cudaSuccess) return (int)e__;   \
+  } while (0)
+
+extern "C" {
+
+int spmf_advi_step(const spmf_step_args* a) {
+  if (!a) return SPMF_ERR_BAD_ARG;
+  cudaStream_t caller = (cudaStream_t)a->caller_stream;
+  cudaStream_t hot = a->hot_stream ? (cudaStream_t)a->hot_stream : caller;
+  cudaStream_t side = a->side_stream ? (cudaStream_t)a->side_stream : hot;
+  const bool multi = (hot != caller) || (side != hot);
+  if (multi && (!a->ev_fork || !a->ev_join || !a->ev_done)) return SPMF_ERR_BAD_ARG;
+  const int D = a->D, K = a->K, S = a->S;
+
+  if (multi) {
+    CUDA_TRY(cudaEventRecord((cudaEvent_t)a->ev_fork, caller));
+    if (hot != caller) CUDA_TRY(cudaStreamWaitEvent(hot, (cudaEvent_t)a->ev_fork, 0));
+    if (side != caller) CUDA_TRY(cudaStreamWaitEvent(side, (cudaEvent_t)a->ev_fork, 0));
+  }
+  // ---- Gamma draws + implicit gradients: only the backward needs them (side stream)
+  if (a->fresh_noise)
+    STEP_TRY(spmf_fill_noise(a->noise, a->params, D, K, S, a->seed, a->rng_step, SPMF_NOISE_GAMMA, side));
+  STEP_TRY(spmf_gamma_grad(a->params, a->noise, D, K, S, a->dgda, side));
+  if (side != hot) CUDA_TRY(cudaEventRecord((cudaEvent_t)a->ev_join, side));
+
+  // ---- hot path
+  if (a->fresh_noise)
+    STEP_TRY(spmf_fill_noise(a->noise, a->params, D, K, S, a->seed, a->rng_step, SPMF_NOISE_NORMAL, hot));
+  STEP_TRY(spmf_draw_operands(a->params, a->noise, a->eta, D, K, S, a->Ap, a->EV, a->PH, a->vsum, a->phisum,
+                              a->scr_d, hot));
+  if (a->ev_rows0) CUDA_TRY(cudaEventRecord((cudaEvent_t)a->ev_rows0, hot));
+  STEP_TRY(spmf_csr_rows(a->rowptr, a->cols, a->vals, a->rowsum, a->lgam, a->inv_xi, a->scale_rows, a->nrows,
+                         D, K, S, a->Ap, a->EV, a->PH, a->vsum, a->z, a->dzr, a->rowacc, 0, hot));
+  if (a->ev_rows1) CUDA_TRY(cudaEventRecord((cudaEvent_t)a->ev_rows1, hot));
+  STEP_TRY(spmf_batch_sums(a->z, a->rowacc, a->nrows, K, S, a->zcolsum, a->datasums, a->scr_d, hot));
+  if (a->ev_cols0) CUDA_TRY(cudaEventRecord((cudaEvent_t)a->ev_cols0, hot));
+  STEP_TRY(spmf_csc_cols(a->colptr, a->crows, a->cvals, a->nnz, a->nrows, D, K, S, a->z, a->dzr, a->EV, a->PH,
+                         a->GAp, a->GEV, a->Gph, 0, hot));
+  if (a->ev_cols1) CUDA_TRY(cudaEventRecord((cudaEvent_t)a->ev_cols1, hot));
+  if (side != hot) CUDA_TRY(cudaStreamWaitEvent(hot, (cudaEvent_t)a->ev_join, 0));
+  STEP_TRY(spmf_backward_params(a->params, a->noise, a->dgda, a->eta, D, K, S, a->GAp, a->GEV, a->Gph, a->zcolsum,
+                                a->datasums, a->phisum, (float)a->nrows, a->u_tau_scale, a->s_tau_scale,
+                                a->decay, a->w_entropy, a->w_prior, a->world_size, a->grads, a->parts,
+                                a->scr_f, a->scr_d, hot));
+  if (a->adam_lr > 0.f) {
+    if (a->world_size > 1) return SPMF_ERR_BAD_ARG;      // the all-reduce must come between backward and Adam
+    // the scalar slack inside the gradient block is host-side bookkeeping, not a parameter gradient
+    CUDA_TRY(cudaMemsetAsync(a->grads + a->comm_off, 0, (size_t)a->comm_slack * sizeof(float), hot));
+    STEP_TRY(spmf_adam_step(a->params, a->grads, a->adam_m, a->adam_v, a->n_params, a->adam_lr, a->adam_beta1,
+                            a->adam_beta2, a->adam_eps, a->adam_t, a->clip_value, 1.0f, hot));
+  }
+  if (hot != caller) {
+    CUDA_TRY(cudaEventRecord((cudaEvent_t)a->ev_done, hot));
+    CUDA_TRY(cudaStreamWaitEvent(caller, (cudaEvent_t)a->ev_done, 0));
+  }
+  return SPMF_OK;
+}
+
+int spmf_prepare_batch(const unsigned short* cols16, const unsigned short* vals16, const long long* rowptr,
+                       int* cols, float* vals, int nrows, long long nnz, int D, float* rowsum, float* lgam,
+                       int* colptr, int* crows, float* cvals, int* scratch, void* stream) {
+  if (cols16 || vals16) STEP_TRY(spmf_csr_unpack16(cols16, vals16, nnz, cols, vals, stream));
+  STEP_TRY(spmf_csr_row_consts(rowptr, vals, nrows, rowsum, lgam, stream));
+  return spmf_csr_to_csc(rowptr, cols, vals, nrows, D, colptr, crows, cvals, scratch, stream);
+}
+
+}  // extern "C"

@@ -323,12 +323,9 @@ class BatchUploader:
             v16.copy_(hb.vals, non_blocking=True)
         else:
             self.vals[:nnz].copy_(hb.vals, non_blocking=True)
-        if c16 is not None or v16 is not None:
-            _abi.call("spmf_csr_unpack16", _ptr(c16), _ptr(v16), nnz, _ptr(self.cols), _ptr(self.vals), st)
-        _abi.call("spmf_csr_row_consts", _ptr(self.rowptr), _ptr(self.vals), n, _ptr(self.rowsum),
-                  _ptr(self.lgam), st)
-        _abi.call("spmf_csr_to_csc", _ptr(self.rowptr), _ptr(self.cols), _ptr(self.vals), n, self.D,
-                  _ptr(self.colptr), _ptr(self.crows), _ptr(self.cvals), _ptr(self.cursor), st)
+        _abi.call("spmf_prepare_batch", _ptr(c16), _ptr(v16), _ptr(self.rowptr), _ptr(self.cols),
+                  _ptr(self.vals), n, nnz, self.D, _ptr(self.rowsum), _ptr(self.lgam), _ptr(self.colptr),
+                  _ptr(self.crows), _ptr(self.cvals), _ptr(self.cursor), st)
         return DeviceBatch(rowptr=self.rowptr[:n + 1], cols=self.cols, vals=self.vals,
                            rowsum=self.rowsum[:n], lgam=self.lgam[:n], nrows=n, nnz=nnz, D=self.D,
                            colptr=self.colptr, crows=self.crows, cvals=self.cvals)

@@ -48,7 +48,7 @@ class StepWorkspace:
 
     def ensure_rows(self, nrows):
         if nrows <= self.max_rows:
-            return
+            return False
         C = self.KP * self.SV
         self.max_rows = int(nrows)
         self.z = torch.empty(self.NQ * nrows * C, dtype=torch.float32, device=self.device)
@@ -85,6 +85,7 @@ class AdviEngine:
         self.inv_xi = 1.0
         self._ws = None
         self._side = None
+        self._args = None
         self.stream_mode = os.environ.get("SPMF_STREAMS", "prio")
         self._max_rows = max_rows
         self.opt_step = 0
@@ -172,52 +173,75 @@ class AdviEngine:
         return e
 
     # ------------------------------------------------------------------ one step
+    def _step_args(self):
+        """The (cached) argument block of spmf_advi_step: everything that does not change per batch."""
+        if self._args is None:
+            a, w, L = _abi.StepArgs(), self.ws, self.layout
+            a.D, a.K, a.S, a.world_size = self.D, self.K, self.S, self.world_size
+            a.u_tau_scale, a.s_tau_scale, a.decay = self.u_tau_scale, self.s_tau_scale, self.decay
+            a.w_entropy, a.w_prior, a.seed = self.entropy_weight, self.prior_weight, self.seed
+            for name in ("params", "grads", "adam_m", "adam_v", "noise", "dgda", "eta"):
+                setattr(a, name, _ptr(getattr(self, name)))
+            a.n_params, a.comm_off, a.comm_slack = L.n_params, L.comm_off, L.comm_slack
+            for name in ("Ap", "EV", "PH", "GAp", "GEV", "Gph", "scr_f", "vsum", "phisum", "zcolsum",
+                         "datasums", "parts", "scr_d"):
+                setattr(a, name, _ptr(getattr(w, name)))
+            if self.stream_mode == "prio":
+                self._hot = torch.cuda.Stream(device=self.device, priority=-1)
+                self._side = torch.cuda.Stream(device=self.device, priority=0)
+                self._sync_events = [torch.cuda.Event() for _ in range(3)]
+                for e in self._sync_events:
+                    e.record()                       # materialise the cudaEvent_t handles
+                a.hot_stream, a.side_stream = self._hot.cuda_stream, self._side.cuda_stream
+                a.ev_fork, a.ev_join, a.ev_done = (e.cuda_event for e in self._sync_events)
+            self._args = a
+        return self._args
+
+    def step(self, batch: DeviceBatch, fresh_noise=True, lr=None, clip_value=0.0, beta1=0.9, beta2=0.999,
+             eps=1e-7):
+        """ONE native call: noise -> operands -> row pass -> column pass -> backward (-> Adam when `lr`
+        is given and world_size == 1).  Gamma draws / implicit gradients run on a low-priority side
+        stream underneath the gather-bound data-term kernels (stream_mode "prio")."""
+        w = self.ws
+        if batch.nrows > w.max_rows:
+            w.ensure_rows(batch.nrows)
+            self._args = None
+        batch.ensure_csc()
+        a = self._step_args()
+        a.z, a.dzr, a.rowacc = _ptr(w.z), _ptr(w.dzr), _ptr(w.rowacc)
+        a.inv_xi, a.scale_rows = self.inv_xi, int(self.scale_rows)
+        a.fresh_noise, a.rng_step = int(fresh_noise), self.rng_step
+        a.rowptr, a.cols, a.vals = _ptr(batch.rowptr), _ptr(batch.cols), _ptr(batch.vals)
+        a.rowsum, a.lgam = _ptr(batch.rowsum), _ptr(batch.lgam)
+        a.colptr, a.crows, a.cvals = _ptr(batch.colptr), _ptr(batch.crows), _ptr(batch.cvals)
+        a.nrows, a.nnz = batch.nrows, batch.nnz
+        do_adam = lr is not None and self.world_size == 1
+        a.adam_lr = float(lr) if do_adam else 0.0
+        a.adam_beta1, a.adam_beta2, a.adam_eps, a.clip_value = beta1, beta2, eps, float(clip_value)
+        a.adam_t = self.opt_step + 1
+        a.caller_stream = _stream()
+        ev = self.kernel_events
+        if ev is not None:
+            tev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            for e in tev:
+                e.record()
+            a.ev_rows0, a.ev_rows1, a.ev_cols0, a.ev_cols1 = (e.cuda_event for e in tev)
+            ev.setdefault("csr_rows", []).append((tev[0], tev[1], batch.nnz, batch.nrows))
+            ev.setdefault("csc_cols", []).append((tev[2], tev[3], batch.nnz, batch.nrows))
+        else:
+            a.ev_rows0 = a.ev_rows1 = a.ev_cols0 = a.ev_cols1 = None
+        _abi.call("spmf_advi_step", a)
+        if fresh_noise:
+            self.rng_step += 1
+        if do_adam:
+            self.opt_step += 1
+        self.launches += 19 + (1 if do_adam else 0)
+        return w.parts.view(self.S, _abi.NUM_PARTS)
+
     def loss_and_grad(self, batch: DeviceBatch, fresh_noise=True, variant=0):
         """Fills self.grads and self.ws.parts for `batch`; returns the (S,16) parts tensor (device,
-        float64): 12 prior terms in var_list order, logq, z, x, per-draw loss.
-
-        Two streams: the Gamma draws and their implicit gradients (ALU/MUFU-bound, needed only by
-        the backward) run on a side stream underneath the gather-bound data-term kernels."""
-        if self.stream_mode == "single":
-            t = self._mark(None, None)
-            if fresh_noise:
-                self.fill_noise()
-                t = self._mark("fill_noise", t)
-            self.gamma_grad()
-            t = self._mark("gamma_grad", t)
-            self.draw_operands()
-            t = self._mark("draw_operands", t)
-            self.data_term(batch, variant)
-            t = self._mark("data_term", t)
-            self.backward_params(batch.nrows)
-            self._mark("backward_params", t)
-            return self.ws.parts.view(self.S, _abi.NUM_PARTS)
-        # "prio": hot path on a high-priority stream, Gamma work on a low-priority one
-        caller = torch.cuda.current_stream()
-        if self._side is None:
-            lo, hi = torch.cuda.Stream.priority_range() if hasattr(torch.cuda.Stream, "priority_range") else (0, -1)
-            self._hot = torch.cuda.Stream(device=self.device, priority=-1)
-            self._side = torch.cuda.Stream(device=self.device, priority=0)
-            self._fork, self._join, self._done = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
-        step = self.rng_step
-        self._fork.record(caller)
-        self._hot.wait_event(self._fork)
-        self._side.wait_event(self._fork)
-        with torch.cuda.stream(self._side):
-            if fresh_noise:
-                self.fill_noise(step, self.NOISE_GAMMA, advance=True)
-            self.gamma_grad()
-            self._join.record(self._side)
-        with torch.cuda.stream(self._hot):
-            if fresh_noise:
-                self.fill_noise(step, self.NOISE_NORMAL, advance=False)
-            self.draw_operands()
-            self.data_term(batch, variant)
-            self._hot.wait_event(self._join)
-            self.backward_params(batch.nrows)
-            self._done.record(self._hot)
-        caller.wait_event(self._done)
-        return self.ws.parts.view(self.S, _abi.NUM_PARTS)
+        float64): 12 prior terms in var_list order, logq, z, x, per-draw loss."""
+        return self.step(batch, fresh_noise=fresh_noise, lr=None)
 
     def loss_value(self, parts=None):
         """mean_s [ w_e log q - w_p prior - z - x ]  as a 0-d device tensor."""

@@ -356,15 +356,17 @@ class PoissonFactorization:
         eng = self._engine_for(sample_size)
         c = batch[self.count_key] if isinstance(batch, dict) else batch
         b = as_device_batch(c, self.device)
-        parts = eng.loss_and_grad(b, variant=variant)
-        loss = eng.loss_value(parts)
         if eng.world_size > 1:
             from .parallel import allreduce_step
+            parts = eng.step(b, lr=None)
             loss = allreduce_step(eng, parts, self.process_group)
+            if learning_rate is not None:
+                eng.adam_step(learning_rate, clip_value=clip_value)
         else:
-            eng.clear_comm_slack()
-        if learning_rate is not None:
-            eng.adam_step(learning_rate, clip_value=clip_value)
+            parts = eng.step(b, lr=learning_rate, clip_value=clip_value)   # one native call, Adam included
+            loss = eng.loss_value(parts)
+            if learning_rate is None:
+                eng.clear_comm_slack()
         return loss
 
     def fit(self, batched_data_factory, batch_size=None, dataset_size=None, num_steps=100,

@@ -96,3 +96,20 @@ def test_variable_views_roundtrip_on_host():
     assert abs(float(sp(views['u_tau_a/scale_raw'][0, 0])) - 1e4) < 1e-2
     views['v/loc'][1, 4] = 7.0
     assert flat[L.toff[0] + 4 * 3 + 1] == 7.0
+
+
+def test_step_args_struct_matches_header(tmp_path):
+    """ctypes mirror of spmf_step_args has the C layout (size and a few offsets), checked with gcc."""
+    import subprocess
+    from spmf_b200 import _abi
+    src = tmp_path / "sz.c"
+    fields = ["seed", "params", "n_params", "vsum", "rowptr", "nrows", "adam_lr", "adam_t", "caller_stream", "ev_cols1"]
+    prints = "".join(f'printf("%zu\\n", offsetof(spmf_step_args, {f}));' for f in fields)
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "%s"\nint main(){printf("%%zu\\n", sizeof(spmf_step_args));%s return 0;}\n'
+                   % (HEADER, prints))
+    exe = tmp_path / "sz"
+    subprocess.check_call(["gcc", "-o", str(exe), str(src)])
+    out = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    assert out[0] == ctypes.sizeof(_abi.StepArgs)
+    for f, off in zip(fields, out[1:]):
+        assert getattr(_abi.StepArgs, f).offset == off, f
