@@ -240,19 +240,27 @@ def main():
     from spmf_b200.data import prefetch_to_device
     host = HostCsr.from_shard(shard)
     hbatches = [host.batch(i * B, B) for i in range(len(batches))]
-    loss_host = torch.empty(1, dtype=torch.float64).pin_memory()
+
+    loss_bufs = [torch.empty(1, dtype=torch.float64).pin_memory() for _ in range(2)]
+    losses_read = []
 
     def run_e2e(n, start):
-        # the loss of step i is read back (blocking D2H) right after step i+1 has been enqueued, so
-        # the host never leaves the GPU idle while it prepares the next launch sequence
+        # each step's loss is copied D2H asynchronously right behind the step; the host blocks on the
+        # PREVIOUS step's copy only, so launches for step i+1 are issued while step i runs
         src = (hbatches[(start + i) % len(hbatches)] for i in range(n))
         prev = None
-        for db in prefetch_to_device(src, dev):
+        for i, db in enumerate(prefetch_to_device(src, dev)):
             loss = model.elbo_step({"counts": db}, S, learning_rate=args.lr, variant=args.variant)
+            buf = loss_bufs[i & 1]
+            buf.copy_(loss.reshape(1), non_blocking=True)             # D2H read of this step's result
+            ev = torch.cuda.Event()
+            ev.record()
             if prev is not None:
-                loss_host.copy_(prev.reshape(1), non_blocking=False)  # D2H read of a step's result
-            prev = loss
-        loss_host.copy_(prev.reshape(1), non_blocking=False)
+                prev[0].synchronize()
+                losses_read.append(float(prev[1][0]))
+            prev = (ev, buf)
+        prev[0].synchronize()
+        losses_read.append(float(prev[1][0]))
 
     run_e2e(args.warmup, 0)
     barrier()
