@@ -274,7 +274,12 @@ def main():
         # PREVIOUS step's copy only, so launches for step i+1 are issued while step i runs
         src = (hbatches[(start + i) % len(hbatches)] for i in range(n))
         prev = None
+        tlast = time.perf_counter()
         for i, db in enumerate(prefetch_to_device(src, dev)):
+            if os.environ.get("BENCH_DEBUG"):
+                tnow = time.perf_counter()
+                print(f"e2e iter {i} host dt {1e3 * (tnow - tlast):.2f} ms", file=sys.stderr)
+                tlast = tnow
             loss = model.elbo_step({"counts": db}, S, learning_rate=args.lr, variant=args.variant)
             buf = loss_bufs[i & 1]
             buf.copy_(loss.reshape(1), non_blocking=True)             # D2H read of this step's result

@@ -331,14 +331,19 @@ class BatchUploader:
                            colptr=self.colptr, crows=self.crows, cvals=self.cvals)
 
 
+_PREFETCH_POOL = {}
+
+
 def prefetch_to_device(host_batches, device, depth=2):
     """Generator: uploads HostCsrBatch items `depth` ahead on a copy stream (H2D, widening, row
     constants, CSC build) while the consumer computes on the current stream.  What tf.data's
     `prefetch(AUTOTUNE)` does for the reference's drivers (bin/factorize_csv.py:110-112)."""
     device = torch.device(device)
     it = iter(host_batches)
-    copy = torch.cuda.Stream(device=device)
-    ups, freed = {}, [None] * depth
+    # staging buffers and the copy stream persist across calls: no allocation once warmed up
+    pool = _PREFETCH_POOL.setdefault(str(device), {"stream": torch.cuda.Stream(device=device), "ups": {}})
+    copy, ups = pool["stream"], pool["ups"]
+    freed = [None] * depth
     queue = []
 
     def issue(slot):
@@ -348,12 +353,12 @@ def prefetch_to_device(host_batches, device, depth=2):
             return False
         if not isinstance(hb, HostCsrBatch):
             hb = hb["counts"] if isinstance(hb, dict) else hb
-        if slot not in ups:
-            ups[slot] = BatchUploader(device, hb.D)
+        if (slot, hb.D) not in ups:
+            ups[(slot, hb.D)] = BatchUploader(device, hb.D)
         if freed[slot] is not None:
             copy.wait_event(freed[slot])            # the step that used this staging set is done
         with torch.cuda.stream(copy):
-            db = ups[slot].upload(hb)
+            db = ups[(slot, hb.D)].upload(hb)
             ev = torch.cuda.Event()
             ev.record(copy)
         queue.append((db, ev, slot))
