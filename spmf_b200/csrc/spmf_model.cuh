@@ -113,23 +113,24 @@ SPMF_HD GParam gparam_init(float conc_raw, float scale_raw) {
 SPMF_HD GDraw gdraw(const GParam& p, float g) {
   GDraw d;
   d.g = g;
-  d.t = p.beta / g;
+  d.t = p.beta * SPMF_RCPF(g);
   const Sp4 f = softplus4(d.t);
   d.y = f.y; d.sg = f.sg; d.oms = f.oms; d.lsg = f.lsg;
   return d;
 }
 // log q(y) = log InvGamma(t; alpha, beta) - log sigmoid(t), with beta/t = g, log t = log beta - log g
 SPMF_HD float glogq(const GParam& p, const GDraw& d) {
-  return p.c0 + (p.alpha + 1.f) * logf(d.g) - d.g - d.lsg;
+  return p.c0 + (p.alpha + 1.f) * SPMF_LOGF(d.g) - d.g - d.lsg;
 }
 // dgda = d g / d alpha of the Gamma draw (implicit reparameterisation), precomputed per draw by
 // gamma_grad_kernel since it depends on (alpha, g) only.
 SPMF_HD void gparam_bwd(GParam& p, const GDraw& d, float dgda, float Gy, float we) {
   float g = d.g;
-  float dlogq_dt = (g / p.beta) * (g - (p.alpha + 1.f)) - d.oms;
+  const float ig = SPMF_RCPF(g), ib = SPMF_RCPF(p.beta);
+  float dlogq_dt = (g * ib) * (g - (p.alpha + 1.f)) - d.oms;
   float dt = Gy * d.sg + we * dlogq_dt;
-  p.acc_da += we * (logf(g) - p.psi) - dt * (p.beta / (g * g)) * dgda;
-  p.acc_db += we * (p.alpha - g) / p.beta + dt / g;
+  p.acc_da += we * (SPMF_LOGF(g) - p.psi) - dt * (p.beta * ig * ig) * dgda;
+  p.acc_db += we * (p.alpha - g) * ib + dt * ig;
 }
 SPMF_HD void gparam_finish(const GParam& p, float conc_raw, float scale_raw, float invS,
                            float* g_conc, float* g_scale) {
@@ -140,23 +141,23 @@ SPMF_HD void gparam_finish(const GParam& p, float conc_raw, float scale_raw, flo
 // ---------------- prior log-densities with derivatives [EXT TFP definitions] ----------------
 // HalfNormal(y; sigma): value, d/dy, d/dsigma
 SPMF_HD float halfnormal(float y, float sigma, float* dy, float* dsigma) {
-  float is = 1.f / sigma, r = y * is;
+  float is = SPMF_RCPF(sigma), r = y * is;
   *dy = -r * is;
   *dsigma = (r * r - 1.f) * is;
-  return kHalfLog2OverPi - logf(sigma) - 0.5f * r * r;
+  return kHalfLog2OverPi - SPMF_LOGF(sigma) - 0.5f * r * r;
 }
 // SqrtInverseGamma(y; 0.5, scale = 1/a): value, d/dy, d/da
 SPMF_HD float sqrt_ig_half(float y, float a, float* dy, float* da) {
-  float iy = 1.f / y, ia = 1.f / a, iy2 = iy * iy;
+  float iy = SPMF_RCPF(y), ia = SPMF_RCPF(a), iy2 = iy * iy;
   *dy = -2.f * iy + 2.f * ia * iy2 * iy;
   *da = -0.5f * ia + ia * ia * iy2;
-  return -0.5f * logf(a) - kLgammaHalf - 2.f * logf(y) - ia * iy2 + kLog2;
+  return -0.5f * SPMF_LOGF(a) - kLgammaHalf - 2.f * SPMF_LOGF(y) - ia * iy2 + kLog2;
 }
 // InverseGamma(a; 0.5, b): value, d/da
 SPMF_HD float ig_half(float a, float b, float* da) {
-  float ia = 1.f / a;
+  float ia = SPMF_RCPF(a);
   *da = -1.5f * ia + b * ia * ia;
-  return 0.5f * logf(b) - kLgammaHalf - 1.5f * logf(a) - b * ia;
+  return 0.5f * SPMF_LOGF(b) - kLgammaHalf - 1.5f * SPMF_LOGF(a) - b * ia;
 }
 
 // ---------------------------------------------------------------------------------------

@@ -198,26 +198,42 @@ backward_dk_kernel(Layout L, Hyper h, const float* __restrict__ P, const float* 
 }
 
 // ------------------------------------------------------------------ backward, per-feature tensors
-// One thread per feature d: w, s, s_eta, s_tau, s_eta_a, s_tau_a (runs after backward_dk_kernel).
+// G = SV lanes per feature d, each taking every G-th draw: w, s, s_eta, s_tau, s_eta_a, s_tau_a
+// (runs after backward_dk_kernel).  Accumulators meet through a fixed xor butterfly.
+__device__ __forceinline__ void group_add(float& v, int G) {
+  for (int o = G >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+}
+
 __global__ void __launch_bounds__(128)
 backward_feat_kernel(Layout L, Hyper h, const float* __restrict__ P, const float* __restrict__ N,
                      const float* __restrict__ G, const float* __restrict__ eta, int SV,
                      const float* __restrict__ Gphinz, const float* __restrict__ scr_da,
                      float* __restrict__ grads, float* __restrict__ scr_parts) {
-  const int d = blockIdx.x * blockDim.x + threadIdx.x;
-  if (d >= L.D) return;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int dreal = t / SV, sg = t - dreal * SV;
+  const bool valid = dreal < L.D;
+  const int d = valid ? dreal : L.D - 1;           // out-of-range lanes shadow the last feature (no writes)
   FeatState f;
   feat_init(f, L, P, d);
-  for (int s = 0; s < L.S; ++s) {
+  for (int s = sg; s < L.S; s += SV) {
     const int q = s / SV, sv = s - q * SV;
     FeatDraw fd = feat_draw(f, L, N, d, s);
     float fp[7];
     feat_step(f, fd, L, h, N, G, eta, d, s, scr_da[(long long)s * L.D + d],
               Gphinz[((long long)q * L.D + d) * SV + sv], fp);
-    float* o = scr_parts + ((long long)d * L.S + s) * NUM_PARTS;
-    o[P_W] = fp[0]; o[P_S] = fp[1]; o[P_SETA] = fp[2]; o[P_STAU] = fp[3];
-    o[P_SETAA] = fp[4]; o[P_STAUA] = fp[5]; o[P_LOGQ] += fp[6];
+    if (valid) {
+      float* o = scr_parts + ((long long)d * L.S + s) * NUM_PARTS;
+      o[P_W] = fp[0]; o[P_S] = fp[1]; o[P_SETA] = fp[2]; o[P_STAU] = fp[3];
+      o[P_SETAA] = fp[4]; o[P_STAUA] = fp[5]; o[P_LOGQ] += fp[6];
+    }
   }
+  NParam* np[3] = {&f.w, &f.s0, &f.s1};
+  GParam* gp[6] = {&f.se0, &f.se1, &f.st, &f.sea0, &f.sea1, &f.sta};
+#pragma unroll
+  for (int i = 0; i < 3; ++i) { group_add(np[i]->acc_dt, SV); group_add(np[i]->acc_dte, SV); }
+#pragma unroll
+  for (int i = 0; i < 6; ++i) { group_add(gp[i]->acc_da, SV); group_add(gp[i]->acc_db, SV); }
+  if (!valid || sg != 0) return;
   const float invS = 1.f / (float)L.S;
   const float wer = h.w_entropy * h.rep_scale;
   const int D = L.D;
@@ -541,7 +557,7 @@ int spmf_backward_params(const float* params, const float* noise, const float* d
   if (KP <= 32) backward_dk_kernel<1><<<grid, 128, 0, st>>>(L, h, params, noise, dgda, eta, SV, KP, GAp, GEVnz, zcolsum, grads, scr_utau, scr_parts, scr_da);
   else if (KP <= 64) backward_dk_kernel<2><<<grid, 128, 0, st>>>(L, h, params, noise, dgda, eta, SV, KP, GAp, GEVnz, zcolsum, grads, scr_utau, scr_parts, scr_da);
   else backward_dk_kernel<4><<<grid, 128, 0, st>>>(L, h, params, noise, dgda, eta, SV, KP, GAp, GEVnz, zcolsum, grads, scr_utau, scr_parts, scr_da);
-  backward_feat_kernel<<<(D + 127) / 128, 128, 0, st>>>(L, h, params, noise, dgda, eta, SV, Gphinz, scr_da, grads, scr_parts);
+  backward_feat_kernel<<<(int)(((long long)D * SV + 127) / 128), 128, 0, st>>>(L, h, params, noise, dgda, eta, SV, Gphinz, scr_da, grads, scr_parts);
   SPMF_CHECK_LAUNCH();
   int rc = reduce_rows_pair(scr_utau, dutau, D, K, S, scr_parts, featparts, D, S * NUM_PARTS, 1, rscr, st);
   if (rc) return rc;
