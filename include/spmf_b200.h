@@ -96,6 +96,9 @@ int spmf_batch_sums(const float* z, const float* rowacc, int nrows, int K, int S
  * the implicit-reparameterisation gradient tf.random.gamma supplies in the reference stack [EXT]. */
 int spmf_gamma_grad(const float* params, const float* noise, int D, int K, int S, float* dgda,
                     void* stream);
+/* Gamma draws (same Philox stream as spmf_fill_noise) and their implicit gradients in one pass */
+int spmf_gamma_draw_grad(const float* params, float* noise, float* dgda, int D, int K, int S,
+                         unsigned long long seed, unsigned int step, void* stream);
 int spmf_backward_params(const float* params, const float* noise, const float* dgda, const float* eta,
                          int D, int K, int S, const float* GAp, const float* GEVnz, const float* Gphinz,
                          const double* zcolsum, const double* datasums, const double* phisum,

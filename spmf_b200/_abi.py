@@ -54,6 +54,7 @@ _SIGS = {
     "spmf_csc_cols": (i32, [p, p, p, i32, i32, i32, i32, i32, p, p, p, p, p, p, p, i32, p]),
     "spmf_batch_sums": (i32, [p, p, i32, i32, i32, p, p, p, p]),
     "spmf_gamma_grad": (i32, [p, p, i32, i32, i32, p, p]),
+    "spmf_gamma_draw_grad": (i32, [p, p, p, i32, i32, i32, u64, u32, p]),
     "spmf_backward_params": (i32, [p, p, p, p, i32, i32, i32, p, p, p, p, p, p, f32, f32, f32, f32, f32,
                                    f32, i32, p, p, p, p, p]),
     "spmf_adam_step": (i32, [p, p, p, p, i64, f32, f32, f32, f32, i32, f32, f32, p]),

@@ -23,11 +23,13 @@
 #define SPMF_LOGF(x) __logf(x)
 #define SPMF_EXPF(x) __expf(x)
 #define SPMF_RCPF(x) __fdividef(1.f, (x))
+#define SPMF_COSF(x) __cosf(x)
 #else
 #define SPMF_RCP(x) (1.f / (x))
 #define SPMF_LOGF(x) logf(x)
 #define SPMF_EXPF(x) expf(x)
 #define SPMF_RCPF(x) (1.f / (x))
+#define SPMF_COSF(x) cosf(x)
 #endif
 
 namespace spmf {
@@ -123,6 +125,80 @@ SPMF_HD float gamma_sample_der_alpha(float a, float x) {
   return x * (dans + ans * (logf(x) - digammaf_pos(a)));
 }
 
+// Same gradient for up to 4 draws of ONE variable (shared alpha): the series terms 1/(a+n) and
+// H_n, digamma and the loop control are shared, which is how the per-step kernel evaluates it.
+// psi = digamma(a).  Results match gamma_sample_der_alpha() to rounding.
+SPMF_HD float gamma_der_cf(float a, float psi, float x) {
+  float y = 1.f - a, z = x + y + 1.f;
+  float pkm2 = 1.f, qkm2 = x, pkm1 = x + 1.f, qkm1 = z * x;
+  float dpkm2 = 0.f, dqkm2 = 0.f, dpkm1 = 0.f, dqkm1 = -x;
+  float ans = pkm1 / qkm1;
+  float dans = (dpkm1 - ans * dqkm1) / qkm1;
+  for (int c = 1; c < 400; ++c) {
+    y += 1.f;
+    z += 2.f;
+    const float fc = (float)c;
+    const float yc = y * fc;
+    const float pk = pkm1 * z - pkm2 * yc;
+    const float qk = qkm1 * z - qkm2 * yc;
+    const float dpk = dpkm1 * z - pkm1 - dpkm2 * yc + pkm2 * fc;
+    const float dqk = dqkm1 * z - qkm1 - dqkm2 * yc + qkm2 * fc;
+    const float iq = SPMF_RCPF(qk);
+    const float nans = pk * iq;
+    const float ndans = (dpk - nans * dqk) * iq;
+    const float delta = fabsf(ndans - dans);
+    const float scale = fabsf(ndans) + 1e-30f;
+    ans = nans;
+    dans = ndans;
+    pkm2 = pkm1; pkm1 = pk; qkm2 = qkm1; qkm1 = qk;
+    dpkm2 = dpkm1; dpkm1 = dpk; dqkm2 = dqkm1; dqkm1 = dqk;
+    if (fabsf(pk) > 1e18f || fabsf(qk) > 1e18f) {
+      const float sc = 1e-18f;
+      pkm2 *= sc; pkm1 *= sc; qkm2 *= sc; qkm1 *= sc;
+      dpkm2 *= sc; dpkm1 *= sc; dqkm2 *= sc; dqkm1 *= sc;
+    }
+    if (delta < 1e-6f * scale && c > 3) break;
+  }
+  return x * (dans + ans * (SPMF_LOGF(x) - psi));
+}
+
+SPMF_HD void gamma_sample_der_alpha4(float a, float psi, const float (&x)[4], int n, float (&out)[4]) {
+  bool ser[4];
+  bool any_ser = false;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    ser[j] = j < n && x[j] > 0.f && (x[j] <= 1.f || x[j] <= a + 1.f);
+    any_ser = any_ser || ser[j];
+    out[j] = 0.f;
+  }
+  if (any_ser) {
+    float T[4], sT[4], sTH[4], xs[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { T[j] = 1.f; sT[j] = 1.f; sTH[j] = 0.f; xs[j] = ser[j] ? x[j] : 0.f; }
+    float H = 0.f;
+    for (int k = 1; k < 400; ++k) {
+      const float inv = SPMF_RCPF(a + (float)k);
+      H += inv;
+      bool done = true;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        T[j] *= xs[j] * inv;
+        sT[j] += T[j];
+        sTH[j] = fmaf(T[j], H, sTH[j]);
+        done = done && (T[j] * (1.f + H) < 1e-7f * sT[j]);
+      }
+      if (done) break;
+    }
+    const float psi1 = psi + 1.f / a;          // digamma(a+1)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (ser[j]) out[j] = (x[j] / a) * (sTH[j] - (SPMF_LOGF(x[j]) - psi1) * sT[j]);
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    if (j < n && !ser[j] && x[j] > 0.f) out[j] = gamma_der_cf(a, psi, x[j]);
+}
+
 // ---------------------------------------------------------------------------
 // Philox4x32-10 counter RNG (Salmon et al. 2011).  Own implementation so that the
 // stream is a pure function of (seed, var, step, element) and identical on every rank.
@@ -170,15 +246,14 @@ SPMF_HD float gamma_draw(float alpha, uint32_t elem_lo, uint32_t elem_hi, uint32
   for (uint32_t it = 0; it < 64; ++it) {
     U4 ctr = {elem_lo, elem_hi, stream, it};
     U4 r = philox4x32_10(ctr, k0, k1);
-    float n0, n1;
-    box_muller(r.x, r.y, &n0, &n1);
+    const float n0 = sqrtf(-2.f * SPMF_LOGF(u01(r.x))) * SPMF_COSF(6.283185307179586f * u01(r.y));
     if (it == 0 && alpha < 1.f) boost = powf(u01(r.w), 1.f / alpha);
     float v = 1.f + c * n0;
     if (v <= 0.f) continue;
     v = v * v * v;
     float u = u01(r.z);
     float x2 = n0 * n0;
-    if (u < 1.f - 0.0331f * x2 * x2 || logf(u) < 0.5f * x2 + d * (1.f - v + logf(v))) {
+    if (u < 1.f - 0.0331f * x2 * x2 || SPMF_LOGF(u) < 0.5f * x2 + d * (1.f - v + SPMF_LOGF(v))) {
       g = d * v;
       break;
     }

@@ -49,31 +49,45 @@ __global__ void fill_normal_kernel(Layout L, float* __restrict__ noise, uint32_t
     if (base + j < n) out[base + j] = x[j];
 }
 
-// Gamma variables (blockIdx.y = the 8 InverseGamma-based ones): out[s][e] ~ Gamma(softplus(conc_raw[e]), 1)
-__global__ void fill_gamma_kernel(Layout L, float* __restrict__ noise, const float* __restrict__ P,
-                                  uint32_t step, uint32_t k0, uint32_t k1) {
+// Gamma variables (blockIdx.y = the 8 InverseGamma-based ones), one thread per element, all S
+// draws: g[s][e] ~ Gamma(softplus(conc_raw[e]), 1) (Philox stream keyed by s*nelem+e) when `draw`,
+// and dg/dalpha of every draw (implicit reparameterisation) -- it depends on (alpha, g) only, so
+// it is evaluated here, fully parallel, off the critical path of the data term.
+__global__ void __launch_bounds__(128)
+gamma_kernel(Layout L, const float* __restrict__ P, float* __restrict__ N, float* __restrict__ G,
+             int draw, int grad, uint32_t step, uint32_t k0, uint32_t k1) {
   const int v = VAR_UETA + blockIdx.y;
-  const long long n = L.vsize[v] * L.S;
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const long long e = i % L.vsize[v];
+  const long long nelem = L.vsize[v];
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= nelem) return;
   const float alpha = softplusf(P[L.toff[2 * v] + e]);
-  // stream id folds the step so that (element, iteration) keep the whole counter space
-  noise[L.noff[v] + i] = gamma_draw(alpha, (uint32_t)(i & 0xffffffffu), (uint32_t)(i >> 32),
-                                    (uint32_t)v ^ (step * 0x9E3779B9u), k0, k1 ^ step);
-}
-
-// dg/dalpha of every Gamma draw (implicit reparameterisation): depends on (alpha, g) only, so it
-// is evaluated here, fully parallel and off the critical path of the data term.
-__global__ void gamma_grad_kernel(Layout L, const float* __restrict__ P, const float* __restrict__ N,
-                                  float* __restrict__ G) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int v = VAR_UETA + blockIdx.y;
-  const long long n = L.vsize[v] * L.S;
-  if (i >= n) return;
-  const long long e = i % L.vsize[v];
-  const float alpha = softplusf(P[L.toff[2 * v] + e]);
-  G[L.noff[v] + i] = gamma_sample_der_alpha(alpha, N[L.noff[v] + i]);
+  const float psi = grad ? digammaf_pos(alpha) : 0.f;
+  float* Nv = N + L.noff[v];
+  float* Gv = G + L.noff[v];
+  for (int s0 = 0; s0 < L.S; s0 += 4) {
+    const int ns = L.S - s0 < 4 ? L.S - s0 : 4;
+    float g[4] = {1.f, 1.f, 1.f, 1.f}, o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (j < ns) {
+        const long long i = (long long)(s0 + j) * nelem + e;
+        if (draw) {
+          // stream id folds the step so that (element, iteration) keep the whole counter space
+          g[j] = gamma_draw(alpha, (uint32_t)(i & 0xffffffffu), (uint32_t)(i >> 32),
+                            (uint32_t)v ^ (step * 0x9E3779B9u), k0, k1 ^ step);
+          Nv[i] = g[j];
+        } else {
+          g[j] = Nv[i];
+        }
+      }
+    }
+    if (grad) {
+      gamma_sample_der_alpha4(alpha, psi, g, ns, o);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (j < ns) Gv[(long long)(s0 + j) * nelem + e] = o[j];
+    }
+  }
 }
 
 // ------------------------------------------------------------------ draw -> operands
@@ -483,8 +497,9 @@ int spmf_fill_noise(float* noise, const float* params, int D, int K, int S, unsi
     fill_normal_kernel<<<grid, 256, 0, st>>>(L, noise, step, k0, k1);
   }
   if (which & SPMF_NOISE_GAMMA) {
-    dim3 grid((unsigned)((nmax + 255) / 256), NUM_VARS - VAR_UETA);
-    fill_gamma_kernel<<<grid, 256, 0, st>>>(L, noise, params, step, k0, k1);
+    long long emax = (long long)D * K > 2LL * D ? (long long)D * K : 2LL * D;
+    dim3 grid((unsigned)((emax + 127) / 128), NUM_VARS - VAR_UETA);
+    gamma_kernel<<<grid, 128, 0, st>>>(L, params, noise, noise, 1, 0, step, k0, k1);
   }
   SPMF_CHECK_LAUNCH();
   return SPMF_OK;
@@ -521,10 +536,22 @@ int spmf_gamma_grad(const float* params, const float* noise, int D, int K, int S
                     void* stream) {
   if (!params || !noise || !dgda || D <= 0 || K <= 0 || S <= 0 || K > SPMF_MAX_K) return SPMF_ERR_BAD_ARG;
   Layout L = make_layout(D, K, S);
-  long long nmax = (long long)D * K * S;
-  if (nmax < 2LL * D * S) nmax = 2LL * D * S;
-  dim3 grid((unsigned)((nmax + 127) / 128), NUM_VARS - VAR_UETA);
-  gamma_grad_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(L, params, noise, dgda);
+  long long emax = (long long)D * K > 2LL * D ? (long long)D * K : 2LL * D;
+  dim3 grid((unsigned)((emax + 127) / 128), NUM_VARS - VAR_UETA);
+  gamma_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(L, params, const_cast<float*>(noise), dgda, 0, 1, 0, 0, 0);
+  SPMF_CHECK_LAUNCH();
+  return SPMF_OK;
+}
+
+/* Gamma draws and their implicit gradients in one pass (what a training step uses). */
+int spmf_gamma_draw_grad(const float* params, float* noise, float* dgda, int D, int K, int S,
+                         unsigned long long seed, unsigned int step, void* stream) {
+  if (!params || !noise || !dgda || D <= 0 || K <= 0 || S <= 0 || K > SPMF_MAX_K) return SPMF_ERR_BAD_ARG;
+  Layout L = make_layout(D, K, S);
+  long long emax = (long long)D * K > 2LL * D ? (long long)D * K : 2LL * D;
+  dim3 grid((unsigned)((emax + 127) / 128), NUM_VARS - VAR_UETA);
+  gamma_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(L, params, noise, dgda, 1, 1, step,
+                                                      (uint32_t)(seed & 0xffffffffu), (uint32_t)(seed >> 32));
   SPMF_CHECK_LAUNCH();
   return SPMF_OK;
 }

@@ -37,8 +37,9 @@ int spmf_advi_step(const spmf_step_args* a) {
   }
   // ---- Gamma draws + implicit gradients: only the backward needs them (side stream)
   if (a->fresh_noise)
-    STEP_TRY(spmf_fill_noise(a->noise, a->params, D, K, S, a->seed, a->rng_step, SPMF_NOISE_GAMMA, side));
-  STEP_TRY(spmf_gamma_grad(a->params, a->noise, D, K, S, a->dgda, side));
+    STEP_TRY(spmf_gamma_draw_grad(a->params, a->noise, a->dgda, D, K, S, a->seed, a->rng_step, side));
+  else
+    STEP_TRY(spmf_gamma_grad(a->params, a->noise, D, K, S, a->dgda, side));
   if (side != hot) CUDA_TRY(cudaEventRecord((cudaEvent_t)a->ev_join, side));
 
   // ---- hot path

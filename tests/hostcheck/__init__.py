@@ -29,6 +29,7 @@ _ll = np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS")
 _u = np.ctypeslib.ndpointer(dtype=np.uint32, flags="C_CONTIGUOUS")
 lib.hc_gamma_grad.argtypes = [_f, _f, _f, C.c_int]
 lib.hc_digamma.argtypes = [_f, _f, C.c_int]
+lib.hc_gamma_grad4.argtypes = [_f, _f, _f, C.c_int]
 lib.hc_softplus.argtypes = [_f, _f, _f, C.c_int]
 lib.hc_normals.argtypes = [_f, C.c_longlong, C.c_uint, C.c_uint, C.c_ulonglong]
 lib.hc_gammas.argtypes = [_f, C.c_longlong, C.c_float, C.c_uint, C.c_ulonglong]
@@ -43,6 +44,13 @@ def gamma_grad(a, x):
     a = np.ascontiguousarray(a, np.float32); x = np.ascontiguousarray(x, np.float32)
     out = np.empty_like(a)
     lib.hc_gamma_grad(a, x, out, a.size)
+    return out
+
+
+def gamma_grad4(a, x):
+    a = np.ascontiguousarray(a, np.float32); x = np.ascontiguousarray(x, np.float32)
+    out = np.empty_like(a)
+    lib.hc_gamma_grad4(a, x, out, a.size)
     return out
 
 

@@ -14,6 +14,14 @@ extern "C" {
 void hc_gamma_grad(const float* a, const float* x, float* out, int n) {
   for (int i = 0; i < n; ++i) out[i] = gamma_sample_der_alpha(a[i], x[i]);
 }
+// 4-draw variant used by gamma_kernel: every group of 4 consecutive x share a[4*g]
+void hc_gamma_grad4(const float* a, const float* x, float* out, int n) {
+  for (int i = 0; i + 4 <= n; i += 4) {
+    float xs[4] = {x[i], x[i + 1], x[i + 2], x[i + 3]}, o[4];
+    gamma_sample_der_alpha4(a[i], digammaf_pos(a[i]), xs, 4, o);
+    for (int j = 0; j < 4; ++j) out[i + j] = o[j];
+  }
+}
 void hc_digamma(const float* x, float* out, int n) {
   for (int i = 0; i < n; ++i) out[i] = digammaf_pos(x[i]);
 }

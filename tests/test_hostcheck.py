@@ -45,6 +45,8 @@ def test_fp32_gamma_gradient_and_digamma():
         ref = O.gamma_sample_der_alpha(torch.full((x.size,), a, dtype=torch.float64),
                                        torch.tensor(x, dtype=torch.float64)).numpy()
         assert np.max(np.abs(got - ref) / np.abs(ref)) < 2e-5, a
+        got4 = hc.gamma_grad4(np.full_like(x, a), x)           # the 4-draws-per-thread form the kernel uses
+        assert np.max(np.abs(got4 - ref) / np.abs(ref)) < 2e-5, a
     x = np.linspace(0.01, 60, 5000).astype(np.float32)
     ref = special.digamma(x.astype(np.float64))
     assert np.max(np.abs(hc.digamma(x) - ref) / np.maximum(1, np.abs(ref))) < 2e-6
