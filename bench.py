@@ -186,8 +186,16 @@ def main():
     ap.add_argument("--variant", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--lr", type=float, default=0.01)
+    ap.add_argument("--K", type=int, default=None, help="override the workload's latent dim (C5 sweep)")
+    ap.add_argument("--S", type=int, default=None, help="override the number of Monte-Carlo draws")
     args = ap.parse_args()
-    wl = WORKLOADS[args.workload]
+    wl = dict(WORKLOADS[args.workload])
+    if args.K:
+        wl["K"] = args.K
+        wl["desc"] += f" [K overridden to {args.K}]"
+    if args.S:
+        wl["S"] = args.S
+        wl["desc"] += f" [S overridden to {args.S}]"
     if args.impl == "reference":
         run_reference(args, wl)
         return

@@ -235,7 +235,7 @@ class AdviEngine:
             self.rng_step += 1
         if do_adam:
             self.opt_step += 1
-        self.launches += 19 + (1 if do_adam else 0)
+        self.launches += 17 + (1 if do_adam else 0)   # kernels issued by spmf_advi_step
         return w.parts.view(self.S, _abi.NUM_PARTS)
 
     def loss_and_grad(self, batch: DeviceBatch, fresh_noise=True, variant=0):
