@@ -131,6 +131,51 @@ int spmf_dense_count(const float* x, int nrows, int D, long long* rowptr, void* 
 int spmf_dense_fill(const float* x, int nrows, int D, const long long* rowptr, int* cols, float* vals,
                     void* stream);
 
+/* ---- hybrid path: tcgen05 tensor-core GEMMs on the dense hot-column block + gathers elsewhere ----
+ * The two products of the step that touch the counts only (encode x.A', poisson.py:640-643, and its
+ * transpose GA' = x^T.dzr in the backward) run on the 5th-gen tensor cores for the H most
+ * populated columns; the per-nonzero terms (rate, x/rate) stay on the gather kernels.
+ * Column order: `rank[d]` = table row of feature d (descending column population), so the hot block
+ * is rows [0,H) of every operand table.  All *_ranked entry points take rank == NULL as identity. */
+int spmf_hybrid_supported(int K, int S); /* 1 if REC = KP*SV is 32, 64 or 128 with KP in {8,16,32} */
+int spmf_draw_operands_ranked(const float* params, const float* noise, const float* eta, const int* rank,
+                              int D, int K, int S, float* Ap, float* EV, float* PH, double* vsum,
+                              double* phisum, double* scratch, void* stream);
+int spmf_backward_params_ranked(const float* params, const float* noise, const float* dgda, const float* eta,
+                                const int* rank, int D, int K, int S, const float* GAp, const float* GEVnz,
+                                const float* Gphinz, const double* zcolsum, const double* datasums,
+                                const double* phisum, float batch_rows, float u_tau_scale, float s_tau_scale,
+                                float decay, float w_entropy, float w_prior, int world_size, float* grads,
+                                double* parts, float* scr_f, double* scr_d, void* stream);
+/* CSR batch (original column ids) -> ranked + partitioned CSR (zero-based rowptr_out[nrows+1]; per row
+ * the entries covered by the tensor-core products first, stored with a NEGATIVE value as their flag,
+ * the others from rowmid[row] on) and the dense hot block as bf16: xhot[nrows][ldx] (ldx >= H,
+ * multiple of 64) and its transpose xthot[ceil64(H)][ldxt] (ldxt >= nrows, multiple of 64); both are
+ * zeroed here.  Covered = rank < H and the count is exactly representable in bf16. */
+int spmf_hot_split(const long long* rowptr, const int* cols, const float* vals, int nrows, long long nnz,
+                   const int* rank, int H, long long* rowptr_out, int* cols_out, float* vals_out, int* rowmid,
+                   void* xhot, long long ldx, void* xthot, long long ldxt, void* stream);
+/* fp32 src[NQ][R][C] (row stride lds) -> bf16 dst[NQ][3][C][ldd] transposed, hi+mid+lo = src to 24 bits;
+ * destination columns [R, Rpad) are written as zeros. */
+int spmf_split3_transpose(const float* src, long long lds, long long src_qstride, int R, int Rpad, int C,
+                          void* dst3, long long ldd, long long dst_tstride, long long dst_qstride, int NQ,
+                          void* stream);
+/* C[q][M][N] (fp32, row stride ldc, accumulated with atomics) += A[q][M][Kd] (bf16, row stride lda)
+ * * (B3[q][0]+B3[q][1]+B3[q][2])[N][Kd]^T (bf16, row stride ldb) on tcgen05; N in {32,64,128},
+ * Kd % 64 == 0, `splits` = split-K factor. */
+int spmf_umma_gemm3(const void* A, long long lda, long long a_qstride, int M, const void* B3, long long ldb,
+                    long long b_tstride, long long b_qstride, float* C, long long ldc, long long c_qstride,
+                    int N, int Kd, int NQ, int splits, void* stream);
+/* row / column passes of the hybrid step (same outputs as spmf_csr_rows / spmf_csc_cols): `z` must
+ * hold the GEMM's un-scaled hot block of x.A' on entry; GA' of covered entries is left to the GEMM. */
+int spmf_csr_rows_hybrid(const long long* rowptr, const int* cols, const float* vals, const int* rowmid,
+                         const float* rowsum, const float* lgam, float inv_xi, int scale_rows, int nrows,
+                         int D, int K, int S, const float* Ap, const float* EV, const float* PH,
+                         const double* vsum, float* z, float* dzr, float* rowacc, void* stream);
+int spmf_csc_cols_hybrid(const int* colptr, const int* rows, const float* vals, int nnz, int nrows, int D,
+                         int K, int S, const float* z, const float* dzr, const float* EV, const float* PH,
+                         float* GAp, float* GEVnz, float* Gphinz, void* stream);
+
 /* ---- one call per step / per uploaded batch ----
  * spmf_advi_step issues the whole sequence above (noise, Gamma gradients, operands, row pass, sums,
  * column pass, backward, optional Adam) from native code.  Streams: `caller_stream` is the stream
@@ -171,6 +216,15 @@ typedef struct spmf_step_args {
   void *caller_stream, *hot_stream, *side_stream;
   void *ev_fork, *ev_join, *ev_done;
   void *ev_rows0, *ev_rows1, *ev_cols0, *ev_cols1;
+  /* hybrid path (hot_cols > 0): rowptr/cols/vals/colptr/crows/cvals above are the ranked, partitioned
+   * arrays of spmf_hot_split (rowptr zero-based); rank maps feature -> table row */
+  const int* rank;
+  int hot_cols, gemm_splits;
+  long long ldx, ldxt, ldt;        /* row strides (elements) of xhot, xthot and of ApT3 / dzrT3 */
+  const int* rowmid;
+  const void *xhot, *xthot;
+  void *ApT3, *dzrT3;              /* bf16 workspaces [NQ][3][REC][ldt] */
+  void *ev_gemm0, *ev_gemm1;       /* optional events around the tensor-core launches of the column side */
 } spmf_step_args;
 int spmf_advi_step(const spmf_step_args* args);
 /* widen a compact batch (either 16-bit source may be NULL), build its row constants and CSC copy */

@@ -67,6 +67,16 @@ _SIGS = {
     "spmf_dense_count": (i32, [p, i32, i32, p, p]),
     "spmf_dense_fill": (i32, [p, i32, i32, p, p, p, p]),
     "spmf_version": (C.c_char_p, []),
+    # hybrid path (tcgen05 hot block)
+    "spmf_hybrid_supported": (i32, [i32, i32]),
+    "spmf_draw_operands_ranked": (i32, [p, p, p, p, i32, i32, i32, p, p, p, p, p, p, p]),
+    "spmf_backward_params_ranked": (i32, [p, p, p, p, p, i32, i32, i32, p, p, p, p, p, p, f32, f32, f32, f32,
+                                          f32, f32, i32, p, p, p, p, p]),
+    "spmf_hot_split": (i32, [p, p, p, i32, i64, p, i32, p, p, p, p, p, i64, p, i64, p]),
+    "spmf_split3_transpose": (i32, [p, i64, i64, i32, i32, i32, p, i64, i64, i64, i32, p]),
+    "spmf_umma_gemm3": (i32, [p, i64, i64, i32, p, i64, i64, i64, p, i64, i64, i32, i32, i32, i32, p]),
+    "spmf_csr_rows_hybrid": (i32, [p, p, p, p, p, p, f32, i32, i32, i32, i32, i32, p, p, p, p, p, p, p, p]),
+    "spmf_csc_cols_hybrid": (i32, [p, p, p, i32, i32, i32, i32, i32, p, p, p, p, p, p, p, p]),
 }
 
 
@@ -87,6 +97,9 @@ class StepArgs(C.Structure):
         + [("adam_t", i32)]
         + [(n, p) for n in ("caller_stream", "hot_stream", "side_stream", "ev_fork", "ev_join", "ev_done",
                             "ev_rows0", "ev_rows1", "ev_cols0", "ev_cols1")]
+        + [("rank", p), ("hot_cols", i32), ("gemm_splits", i32)]
+        + [(n, i64) for n in ("ldx", "ldxt", "ldt")]
+        + [(n, p) for n in ("rowmid", "xhot", "xthot", "ApT3", "dzrT3", "ev_gemm0", "ev_gemm1")]
     )
 
 

@@ -94,11 +94,12 @@ gamma_kernel(Layout L, const float* __restrict__ P, float* __restrict__ N, float
 template <int KK>
 __global__ void __launch_bounds__(128)
 draw_operands_kernel(Layout L, const float* __restrict__ P, const float* __restrict__ N,
-                     const float* __restrict__ eta, int SV, int KP, float* __restrict__ Ap,
-                     float* __restrict__ EV, float* __restrict__ PH) {
+                     const float* __restrict__ eta, const int* __restrict__ rank, int SV, int KP,
+                     float* __restrict__ Ap, float* __restrict__ EV, float* __restrict__ PH) {
   const int lane = threadIdx.x & 31;
   const int d = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (d >= L.D) return;
+  const int dr = rank ? rank[d] : d;      // table row of feature d (hot-column ordering)
   LaneState<KK> st;
   FeatState f;
   lane_init<KK>(st, L, P, d, lane);
@@ -112,12 +113,12 @@ draw_operands_kernel(Layout L, const float* __restrict__ P, const float* __restr
       if (k < KP) {
         float ap = 0.f, ev = 0.f;
         if (k < L.K) lane_operands<KK>(st, L, N, eta, d, lane, i, s, fd.a, &ap, &ev, nullptr, nullptr);
-        long long idx = ((long long)q * L.D + d) * SV * KP + rec_pos(KP, SV, sv, k);
+        long long idx = ((long long)q * L.D + dr) * SV * KP + rec_pos(KP, SV, sv, k);
         Ap[idx] = ap;
         EV[idx] = ev;
       }
     }
-    if (lane == 0) PH[((long long)q * L.D + d) * SV + sv] = eta[d] * fd.b * fd.w.y;  // poisson.py:701
+    if (lane == 0) PH[((long long)q * L.D + dr) * SV + sv] = eta[d] * fd.b * fd.w.y;  // poisson.py:701
   }
 }
 
@@ -151,7 +152,8 @@ __global__ void sample_kernel(Layout L, const float* __restrict__ P, const float
 template <int KK>
 __global__ void __launch_bounds__(128, KK == 1 ? 6 : 3)
 backward_dk_kernel(Layout L, Hyper h, const float* __restrict__ P, const float* __restrict__ N,
-                   const float* __restrict__ G, const float* __restrict__ eta, int SV, int KP,
+                   const float* __restrict__ G, const float* __restrict__ eta,
+                   const int* __restrict__ rank, int SV, int KP,
                    const float* __restrict__ GAp, const float* __restrict__ GEVnz,
                    const double* __restrict__ zcolsum, float* __restrict__ grads,
                    float* __restrict__ scr_utau, float* __restrict__ scr_parts,
@@ -159,6 +161,7 @@ backward_dk_kernel(Layout L, Hyper h, const float* __restrict__ P, const float* 
   const int lane = threadIdx.x & 31;
   const int d = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (d >= L.D) return;
+  const int dr = rank ? rank[d] : d;
   LaneState<KK> st;
   lane_init<KK>(st, L, P, d, lane, h.decay);
   const NParam s0 = nparam_init(P[L.toff[S_LOC] + d], P[L.toff[S_RHO] + d]);
@@ -174,7 +177,7 @@ backward_dk_kernel(Layout L, Hyper h, const float* __restrict__ P, const float* 
       int k = lane + 32 * i;
       if (k < L.K) {
         const int rp = rec_pos(KP, SV, sv, k);
-        long long idx = ((long long)q * L.D + d) * SV * KP + rp;
+        long long idx = ((long long)q * L.D + dr) * SV * KP + rp;
         DkUp up;
         up.GAp = GAp[idx];
         up.GEV = GEVnz[idx] - (float)zcolsum[(long long)q * SV * KP + rp];
@@ -220,13 +223,15 @@ __device__ __forceinline__ void group_add(float& v, int G) {
 
 __global__ void __launch_bounds__(128)
 backward_feat_kernel(Layout L, Hyper h, const float* __restrict__ P, const float* __restrict__ N,
-                     const float* __restrict__ G, const float* __restrict__ eta, int SV,
+                     const float* __restrict__ G, const float* __restrict__ eta,
+                     const int* __restrict__ rank, int SV,
                      const float* __restrict__ Gphinz, const float* __restrict__ scr_da,
                      float* __restrict__ grads, float* __restrict__ scr_parts) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int dreal = t / SV, sg = t - dreal * SV;
   const bool valid = dreal < L.D;
   const int d = valid ? dreal : L.D - 1;           // out-of-range lanes shadow the last feature (no writes)
+  const int dr = rank ? rank[d] : d;
   FeatState f;
   feat_init(f, L, P, d);
   for (int s = sg; s < L.S; s += SV) {
@@ -234,7 +239,7 @@ backward_feat_kernel(Layout L, Hyper h, const float* __restrict__ P, const float
     FeatDraw fd = feat_draw(f, L, N, d, s);
     float fp[7];
     feat_step(f, fd, L, h, N, G, eta, d, s, scr_da[(long long)s * L.D + d],
-              Gphinz[((long long)q * L.D + d) * SV + sv], fp);
+              Gphinz[((long long)q * L.D + dr) * SV + sv], fp);
     if (valid) {
       float* o = scr_parts + ((long long)d * L.S + s) * NUM_PARTS;
       o[P_W] = fp[0]; o[P_S] = fp[1]; o[P_SETA] = fp[2]; o[P_STAU] = fp[3];
@@ -519,15 +524,21 @@ int spmf_sample(const float* params, const float* noise, int D, int K, int S, fl
 int spmf_draw_operands(const float* params, const float* noise, const float* eta, int D, int K, int S,
                        float* Ap, float* EV, float* PH, double* vsum, double* phisum,
                        double* scratch, void* stream) {
+  return spmf_draw_operands_ranked(params, noise, eta, nullptr, D, K, S, Ap, EV, PH, vsum, phisum, scratch, stream);
+}
+
+int spmf_draw_operands_ranked(const float* params, const float* noise, const float* eta, const int* rank,
+                              int D, int K, int S, float* Ap, float* EV, float* PH, double* vsum,
+                              double* phisum, double* scratch, void* stream) {
   if (!params || !noise || !eta || !Ap || !EV || !PH || !vsum || !phisum || !scratch) return SPMF_ERR_BAD_ARG;
   if (D <= 0 || K <= 0 || S <= 0 || K > SPMF_MAX_K) return SPMF_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   Layout L = make_layout(D, K, S);
   const int KP = spmf_kpad(K), SV = spmf_draw_vec(S), NQ = S / SV;
   dim3 grid((D + 3) / 4);
-  if (KP <= 32) draw_operands_kernel<1><<<grid, 128, 0, st>>>(L, params, noise, eta, SV, KP, Ap, EV, PH);
-  else if (KP <= 64) draw_operands_kernel<2><<<grid, 128, 0, st>>>(L, params, noise, eta, SV, KP, Ap, EV, PH);
-  else draw_operands_kernel<4><<<grid, 128, 0, st>>>(L, params, noise, eta, SV, KP, Ap, EV, PH);
+  if (KP <= 32) draw_operands_kernel<1><<<grid, 128, 0, st>>>(L, params, noise, eta, rank, SV, KP, Ap, EV, PH);
+  else if (KP <= 64) draw_operands_kernel<2><<<grid, 128, 0, st>>>(L, params, noise, eta, rank, SV, KP, Ap, EV, PH);
+  else draw_operands_kernel<4><<<grid, 128, 0, st>>>(L, params, noise, eta, rank, SV, KP, Ap, EV, PH);
   SPMF_CHECK_LAUNCH();
   return reduce_rows_pair(EV, vsum, D, KP * SV, NQ, PH, phisum, D, SV, NQ, scratch, st);
 }
@@ -562,6 +573,17 @@ int spmf_backward_params(const float* params, const float* noise, const float* d
                          float batch_rows, float u_tau_scale, float s_tau_scale,
                          float decay, float w_entropy, float w_prior, int world_size, float* grads,
                          double* parts, float* scr_f, double* scr_d, void* stream) {
+  return spmf_backward_params_ranked(params, noise, dgda, eta, nullptr, D, K, S, GAp, GEVnz, Gphinz, zcolsum,
+                                     datasums, phisum, batch_rows, u_tau_scale, s_tau_scale, decay, w_entropy,
+                                     w_prior, world_size, grads, parts, scr_f, scr_d, stream);
+}
+
+int spmf_backward_params_ranked(const float* params, const float* noise, const float* dgda, const float* eta,
+                                const int* rank, int D, int K, int S, const float* GAp, const float* GEVnz,
+                                const float* Gphinz, const double* zcolsum, const double* datasums,
+                                const double* phisum, float batch_rows, float u_tau_scale, float s_tau_scale,
+                                float decay, float w_entropy, float w_prior, int world_size, float* grads,
+                                double* parts, float* scr_f, double* scr_d, void* stream) {
   if (!params || !noise || !dgda || !eta || !GAp || !GEVnz || !Gphinz || !zcolsum || !datasums ||
       !phisum || !grads || !parts || !scr_f || !scr_d)
     return SPMF_ERR_BAD_ARG;
@@ -581,10 +603,10 @@ int spmf_backward_params(const float* params, const float* noise, const float* d
   double* rscr = latparts + (long long)S * NUM_PARTS;
   float* scr_da = scr_lat + (long long)K * S * NUM_PARTS;
   dim3 grid((D + 3) / 4);
-  if (KP <= 32) backward_dk_kernel<1><<<grid, 128, 0, st>>>(L, h, params, noise, dgda, eta, SV, KP, GAp, GEVnz, zcolsum, grads, scr_utau, scr_parts, scr_da);
-  else if (KP <= 64) backward_dk_kernel<2><<<grid, 128, 0, st>>>(L, h, params, noise, dgda, eta, SV, KP, GAp, GEVnz, zcolsum, grads, scr_utau, scr_parts, scr_da);
-  else backward_dk_kernel<4><<<grid, 128, 0, st>>>(L, h, params, noise, dgda, eta, SV, KP, GAp, GEVnz, zcolsum, grads, scr_utau, scr_parts, scr_da);
-  backward_feat_kernel<<<(int)(((long long)D * SV + 127) / 128), 128, 0, st>>>(L, h, params, noise, dgda, eta, SV, Gphinz, scr_da, grads, scr_parts);
+  if (KP <= 32) backward_dk_kernel<1><<<grid, 128, 0, st>>>(L, h, params, noise, dgda, eta, rank, SV, KP, GAp, GEVnz, zcolsum, grads, scr_utau, scr_parts, scr_da);
+  else if (KP <= 64) backward_dk_kernel<2><<<grid, 128, 0, st>>>(L, h, params, noise, dgda, eta, rank, SV, KP, GAp, GEVnz, zcolsum, grads, scr_utau, scr_parts, scr_da);
+  else backward_dk_kernel<4><<<grid, 128, 0, st>>>(L, h, params, noise, dgda, eta, rank, SV, KP, GAp, GEVnz, zcolsum, grads, scr_utau, scr_parts, scr_da);
+  backward_feat_kernel<<<(int)(((long long)D * SV + 127) / 128), 128, 0, st>>>(L, h, params, noise, dgda, eta, rank, SV, Gphinz, scr_da, grads, scr_parts);
   SPMF_CHECK_LAUNCH();
   int rc = reduce_rows_pair(scr_utau, dutau, D, K, S, scr_parts, featparts, D, S * NUM_PARTS, 1, rscr, st);
   if (rc) return rc;

@@ -140,18 +140,27 @@ __device__ __forceinline__ void ld_idx(const int* __restrict__ pc, const float* 
   }
 }
 
-template <int KP, int SV, bool ENCODE_ONLY>
+// MODE 0: training row pass.  MODE 1: encode only (z).  MODE 2: hybrid -- the hot-column block of
+// the encode product already sits in z (tcgen05 GEMM, spmf_umma.cu); sweep 1 adds the entries the
+// GEMM does not cover (stored after rowmid[row], positive values) and sweep 2 runs over every entry
+// (covered ones carry a negative sign as their flag).
+constexpr int kRowsTrain = 0, kRowsEncode = 1, kRowsHybrid = 2;
+
+template <int KP, int SV, int MODE>
 __global__ void __launch_bounds__(128)
 csr_rows_kernel(const long long* __restrict__ rowptr, const int* __restrict__ cols,
                 const float* __restrict__ vals, const float* __restrict__ rowsum,
                 const float* __restrict__ lgam, float inv_xi, int scale_rows, int nrows, int D,
                 const float* __restrict__ Ap, const float* __restrict__ EV,
                 const float* __restrict__ PH, const double* __restrict__ vsum,
-                float* __restrict__ z, float* __restrict__ dzr, float* __restrict__ rowacc) {
+                float* __restrict__ z, float* __restrict__ dzr, float* __restrict__ rowacc,
+                const int* __restrict__ rowmid) {
+  constexpr bool ENCODE_ONLY = (MODE == kRowsEncode);
+  constexpr bool HYBRID = (MODE == kRowsHybrid);
   using M = Map<KP, SV>;
   constexpr int VW = M::VW, LPN = M::LPN, RG = M::RG, VPL = M::VPL, REC = M::REC, NSLOT = M::NSLOT;
   constexpr int U = VPL >= 4 ? 2 : 4;
-  constexpr int SPW = M::SPW, NWARP = 4;
+  constexpr int NWARP = 4;
   __shared__ __align__(16) float part[NWARP * REC];
   __shared__ float sc[NWARP][SV][2];
   const int lane = threadIdx.x & 31;
@@ -164,22 +173,32 @@ csr_rows_kernel(const long long* __restrict__ rowptr, const int* __restrict__ co
 #pragma unroll
   for (int i = 0; i < VPL; ++i) off[i] = M::off(i, s, kg);
 
-  // Row-local index space [0,n).  The nonzero stream is consumed in aligned groups of U (one
-  // 16-byte load for U columns, one for U values, shared by the whole slot): `head` elements up
-  // to the first aligned position, `ng` full groups dealt round-robin to the slots, then a tail;
-  // head and tail (< 2U elements) go through a scalar path on the last slot.
+  // Row-local index space.  The nonzero stream is consumed in aligned groups of U (one 16-byte
+  // load for U columns, one for U values, shared by the whole slot): `head` elements up to the
+  // first aligned position, `ng` full groups dealt round-robin to the slots, then a tail; head and
+  // tail (< 2U elements) go through a scalar path on the last slot.
+  struct Range {
+    int head, ng, my_groups, n_extra;
+    const int* gc; const float* gv; const int* rc; const float* rv;
+    __device__ __forceinline__ int extra_index(int e) const { return e < head ? e : e + ng * U; }
+  };
+  auto make_range = [&](long long jstart, int cnt) {
+    Range R;
+    R.head = min(cnt, (int)((U - (jstart & (U - 1))) & (U - 1)));
+    R.ng = (cnt - R.head) / U;
+    R.gc = cols + jstart + R.head;   // aligned group base
+    R.gv = vals + jstart + R.head;
+    R.rc = cols + jstart;
+    R.rv = vals + jstart;
+    R.my_groups = slot < R.ng ? (R.ng - slot + NSLOT - 1) / NSLOT : 0;
+    R.n_extra = (slot == NSLOT - 1) ? cnt - R.ng * U : 0;   // [0,head) U [head + ng*U, cnt)
+    return R;
+  };
   const long long j0 = rowptr[row];
   const int n = (int)(rowptr[row + 1] - j0);
-  const int head = min(n, (int)((U - (j0 & (U - 1))) & (U - 1)));
-  const int ng = (n - head) / U;
-  const int* __restrict__ gc = cols + j0 + head;   // aligned group base
-  const float* __restrict__ gv = vals + j0 + head;
-  const int* __restrict__ rc = cols + j0;
-  const float* __restrict__ rv = vals + j0;
-  const int my_groups = slot < ng ? (ng - slot + NSLOT - 1) / NSLOT : 0;
-  // scalar extras of the last slot: [0,head) U [head + ng*U, n)
-  const int n_extra = (slot == NSLOT - 1) ? n - ng * U : 0;
-  auto extra_index = [&](int e) { return e < head ? e : e - head + head + ng * U; };
+  const int mid = HYBRID ? rowmid[row] : 0;          // sweep 1 starts here in hybrid mode
+  const Range R1 = make_range(j0 + mid, n - mid);
+  const Range R2 = HYBRID ? make_range(j0, n) : R1;
   const float r = scale_rows ? rowsum[row] * inv_xi : 1.f;   // poisson.py:644-649
 
   // ---- z = r * sum_d x A'_d          (poisson.py:640-643 with 1/eta folded into A')
@@ -192,17 +211,17 @@ csr_rows_kernel(const long long* __restrict__ rowptr, const int* __restrict__ co
   {
     int dcur[U];
     float xcur[U];
-    if (my_groups > 0) ld_idx<U>(gc + slot * U, gv + slot * U, dcur, xcur);
-    for (int b = 0; b < my_groups; ++b) {
+    if (R1.my_groups > 0) ld_idx<U>(R1.gc + slot * U, R1.gv + slot * U, dcur, xcur);
+    for (int b = 0; b < R1.my_groups; ++b) {
       float a[U][VPL][VW];
 #pragma unroll
       for (int u = 0; u < U; ++u)
 #pragma unroll
         for (int i = 0; i < VPL; ++i) ldv<VW>(a[u][i], Apl + (unsigned)dcur[u] * REC + off[i]);
-      const int gn = slot + min(b + 1, my_groups - 1) * NSLOT;   // last iteration re-reads its own group
+      const int gn = slot + min(b + 1, R1.my_groups - 1) * NSLOT;   // last iteration re-reads its own group
       int dn[U];
       float xn[U];
-      ld_idx<U>(gc + gn * U, gv + gn * U, dn, xn);
+      ld_idx<U>(R1.gc + gn * U, R1.gv + gn * U, dn, xn);
 #pragma unroll
       for (int u = 0; u < U; ++u) {
 #pragma unroll
@@ -213,10 +232,10 @@ csr_rows_kernel(const long long* __restrict__ rowptr, const int* __restrict__ co
         xcur[u] = xn[u];
       }
     }
-    for (int e = 0; e < n_extra; ++e) {
-      const int t = extra_index(e);
-      const int d = __ldg(rc + t);
-      const float x = __ldg(rv + t);
+    for (int e = 0; e < R1.n_extra; ++e) {
+      const int t = R1.extra_index(e);
+      const int d = __ldg(R1.rc + t);
+      const float x = __ldg(R1.rv + t);
 #pragma unroll
       for (int i = 0; i < VPL; ++i) {
         float a[VW];
@@ -251,10 +270,19 @@ csr_rows_kernel(const long long* __restrict__ rowptr, const int* __restrict__ co
   float* zq = z + ((size_t)q * nrows + row) * REC;
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
+    if constexpr (HYBRID) {                 // hot-column block of x.A' from the tensor-core GEMM
+      float a[VW];
+      ldv_s<VW>(a, zq + off[i]);
+#pragma unroll
+      for (int w = 0; w < VW; ++w) zz[i][w] += a[w];
+    }
 #pragma unroll
     for (int w = 0; w < VW; ++w) zz[i][w] *= r;
-    if (slot == 0) stv<VW>(zq + off[i], zz[i]);
   }
+  if constexpr (HYBRID) __syncthreads();    // every slot has read the GEMM block before slot 0 overwrites it
+#pragma unroll
+  for (int i = 0; i < VPL; ++i)
+    if (slot == 0) stv<VW>(zq + off[i], zz[i]);
   if constexpr (ENCODE_ONLY) return;
 
   // ---- lambda at the nonzeros, x log lambda, dz      (poisson.py:174-184)
@@ -270,8 +298,12 @@ csr_rows_kernel(const long long* __restrict__ rowptr, const int* __restrict__ co
   {
     int dcur[U];
     float xcur[U];
-    if (my_groups > 0) ld_idx<U>(gc + slot * U, gv + slot * U, dcur, xcur);
-    for (int b = 0; b < my_groups; ++b) {
+    if (R2.my_groups > 0) ld_idx<U>(R2.gc + slot * U, R2.gv + slot * U, dcur, xcur);
+    if constexpr (HYBRID) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) xcur[u] = fabsf(xcur[u]);
+    }
+    for (int b = 0; b < R2.my_groups; ++b) {
       float e[U][VPL][VW], ph[U], p[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
@@ -279,10 +311,14 @@ csr_rows_kernel(const long long* __restrict__ rowptr, const int* __restrict__ co
         for (int i = 0; i < VPL; ++i) ldv<VW>(e[u][i], EVl + (unsigned)dcur[u] * REC + off[i]);
         ph[u] = __ldg(PHl + (unsigned)dcur[u] * SV);
       }
-      const int gn = slot + min(b + 1, my_groups - 1) * NSLOT;
+      const int gn = slot + min(b + 1, R2.my_groups - 1) * NSLOT;
       int dn[U];
       float xn[U];
-      ld_idx<U>(gc + gn * U, gv + gn * U, dn, xn);
+      ld_idx<U>(R2.gc + gn * U, R2.gv + gn * U, dn, xn);
+      if constexpr (HYBRID) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) xn[u] = fabsf(xn[u]);
+      }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         p[u] = 0.f;
@@ -309,10 +345,10 @@ csr_rows_kernel(const long long* __restrict__ rowptr, const int* __restrict__ co
         xcur[u] = xn[u];
       }
     }
-    for (int ex = 0; ex < n_extra; ++ex) {
-      const int t = extra_index(ex);
-      const int d = __ldg(rc + t);
-      const float x = __ldg(rv + t);
+    for (int ex = 0; ex < R2.n_extra; ++ex) {
+      const int t = R2.extra_index(ex);
+      const int d = __ldg(R2.rc + t);
+      const float x = HYBRID ? fabsf(__ldg(R2.rv + t)) : __ldg(R2.rv + t);
       float e[VPL][VW];
       float p = 0.f;
 #pragma unroll
@@ -395,7 +431,9 @@ csr_rows_kernel(const long long* __restrict__ rowptr, const int* __restrict__ co
 // atomics when the column changes (only columns that straddle slices are contended).
 constexpr int kSliceLen = 256;
 
-template <int KP, int SV>
+// HYBRID: entries whose value carries a negative sign are covered by the tensor-core GEMM for the
+// GA' product (spmf_umma.cu): their dzr gather is skipped; every other term uses |x|.
+template <int KP, int SV, bool HYBRID>
 __global__ void __launch_bounds__(128, 4)
 csc_cols_kernel(const int* __restrict__ colptr, const int* __restrict__ rows,
                 const float* __restrict__ vals, int nnz, int nrows, int D,
@@ -503,23 +541,38 @@ csc_cols_kernel(const int* __restrict__ colptr, const int* __restrict__ rows,
     }
     float zz[U][VPL][VW], dd[U][VPL][VW];
 #pragma unroll
-    for (int u = 0; u < U; ++u)
+    for (int u = 0; u < U; ++u) {
+      const bool cov = HYBRID && xx[u] < 0.f;
+      if constexpr (HYBRID) xx[u] = fabsf(xx[u]);
 #pragma unroll
       for (int i = 0; i < VPL; ++i) {
         ldv<VW>(zz[u][i], zl + (unsigned)bb[u] * REC + off[i]);
-        ldv<VW>(dd[u][i], dl + (unsigned)bb[u] * REC + off[i]);
+        if (!cov) {
+          ldv<VW>(dd[u][i], dl + (unsigned)bb[u] * REC + off[i]);
+        } else {
+#pragma unroll
+          for (int w = 0; w < VW; ++w) dd[u][i][w] = 0.f;
+        }
       }
+    }
 #pragma unroll
     for (int u = 0; u < U; ++u) one(jb + u, xx[u], zz[u], dd[u]);
   }
   for (int j = j0 + nfull * U; j < j1; ++j) {     // tail of the last slice
     const int b = __ldg(rows + j);
-    const float x = __ldg(vals + j);
+    float x = __ldg(vals + j);
+    const bool cov = HYBRID && x < 0.f;
+    if constexpr (HYBRID) x = fabsf(x);
     float zz[VPL][VW], dd[VPL][VW];
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
       ldv<VW>(zz[i], zl + (unsigned)b * REC + off[i]);
-      ldv<VW>(dd[i], dl + (unsigned)b * REC + off[i]);
+      if (!cov) {
+        ldv<VW>(dd[i], dl + (unsigned)b * REC + off[i]);
+      } else {
+#pragma unroll
+        for (int w = 0; w < VW; ++w) dd[i][w] = 0.f;
+      }
     }
     one(j, x, zz, dd);
   }
@@ -785,20 +838,83 @@ __global__ void dense_fill_kernel(const float* __restrict__ x, int nrows, int D,
   }
 }
 
+__device__ __forceinline__ bool hot_covered(int r, float x, int H) {   // rank in the block, x > 0 exact in bf16
+  return r < H && x > 0.f && __uint_as_float(__float_as_uint(x) & 0xffff0000u) == x;
+}
+
+__global__ void __launch_bounds__(128)
+hot_split_kernel(const long long* __restrict__ rowptr, const int* __restrict__ cols,
+                 const float* __restrict__ vals, int nrows, const int* __restrict__ rank, int H,
+                 long long* __restrict__ rowptr_out, int* __restrict__ cols_out,
+                 float* __restrict__ vals_out, int* __restrict__ rowmid,
+                 unsigned short* __restrict__ xhot, long long ldx, unsigned short* __restrict__ xthot,
+                 long long ldxt) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= nrows) return;
+  const long long base = rowptr[0];
+  const long long j0 = rowptr[row], j1 = rowptr[row + 1];
+  const long long o0 = j0 - base;
+  if (lane == 0) {
+    rowptr_out[row] = o0;
+    if (row == nrows - 1) rowptr_out[nrows] = j1 - base;
+  }
+  // pass 1: number of covered entries
+  int ncov = 0;
+  for (long long j = j0 + lane; j < j1; j += 32) {
+    const int r = rank ? __ldg(rank + __ldg(cols + j)) : __ldg(cols + j);
+    ncov += hot_covered(r, __ldg(vals + j), H) ? 1 : 0;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ncov += __shfl_xor_sync(0xffffffffu, ncov, o);
+  if (lane == 0) rowmid[row] = ncov;
+  // pass 2: stable partition
+  long long pc = o0, pu = o0 + ncov;
+  for (long long jb = j0; jb < j1; jb += 32) {
+    const long long j = jb + lane;
+    const bool in = j < j1;
+    int r = 0;
+    float x = 0.f;
+    if (in) {
+      r = rank ? __ldg(rank + __ldg(cols + j)) : __ldg(cols + j);
+      x = __ldg(vals + j);
+    }
+    const bool cov = in && hot_covered(r, x, H);
+    const unsigned mc = __ballot_sync(0xffffffffu, cov);
+    const unsigned mu = __ballot_sync(0xffffffffu, in && !cov);
+    const unsigned below = (1u << lane) - 1u;
+    if (cov) {
+      const long long o = pc + __popc(mc & below);
+      cols_out[o] = r;
+      vals_out[o] = -x;
+      const unsigned short hx = (unsigned short)(__float_as_uint(x) >> 16);
+      xhot[(long long)row * ldx + r] = hx;
+      xthot[(long long)r * ldxt + row] = hx;
+    } else if (in) {
+      const long long o = pu + __popc(mu & below);
+      cols_out[o] = r;
+      vals_out[o] = x;
+    }
+    pc += __popc(mc);
+    pu += __popc(mu);
+  }
+}
+
 // ------------------------------------------------------------------ dispatch
-template <int KP, int SV, bool ENC>
+template <int KP, int SV, int MODE>
 static int launch_rows(const long long* rowptr, const int* cols, const float* vals,
                        const float* rowsum, const float* lgam, float inv_xi, int scale_rows, int nrows,
                        int D, int NQ, const float* Ap, const float* EV, const float* PH,
-                       const double* vsum, float* z, float* dzr, float* rowacc, cudaStream_t st) {
+                       const double* vsum, float* z, float* dzr, float* rowacc, const int* rowmid,
+                       cudaStream_t st) {
   dim3 grid(nrows, NQ);
-  csr_rows_kernel<KP, SV, ENC><<<grid, 128, 0, st>>>(
-      rowptr, cols, vals, rowsum, lgam, inv_xi, scale_rows, nrows, D, Ap, EV, PH, vsum, z, dzr, rowacc);
+  csr_rows_kernel<KP, SV, MODE><<<grid, 128, 0, st>>>(
+      rowptr, cols, vals, rowsum, lgam, inv_xi, scale_rows, nrows, D, Ap, EV, PH, vsum, z, dzr, rowacc, rowmid);
   SPMF_CHECK_LAUNCH();
   return SPMF_OK;
 }
 
-template <int KP, int SV>
+template <int KP, int SV, bool HYBRID>
 static int launch_cols(const int* colptr, const int* rows, const float* vals, int nnz, int nrows,
                        int D, int NQ, const float* z, const float* dzr, const float* EV,
                        const float* PH, float* GAp, float* GEV, float* Gphi, cudaStream_t st) {
@@ -806,8 +922,8 @@ static int launch_cols(const int* colptr, const int* rows, const float* vals, in
   const int nslices = (nnz + kSliceLen - 1) / kSliceLen;
   if (nslices == 0) return SPMF_OK;
   dim3 grid((nslices + NSLOT - 1) / NSLOT, NQ);
-  csc_cols_kernel<KP, SV><<<grid, 128, 0, st>>>(colptr, rows, vals, nnz, nrows, D, z, dzr, EV, PH,
-                                               GAp, GEV, Gphi);
+  csc_cols_kernel<KP, SV, HYBRID><<<grid, 128, 0, st>>>(colptr, rows, vals, nnz, nrows, D, z, dzr, EV, PH,
+                                                       GAp, GEV, Gphi);
   SPMF_CHECK_LAUNCH();
   return SPMF_OK;
 }
@@ -856,7 +972,7 @@ int spmf_csr_rows(const long long* rowptr, const int* cols, const float* vals, c
   const int KP = spmf_kpad(K), SV = spmf_draw_vec(S), NQ = S / SV;
   cudaStream_t st = (cudaStream_t)stream;
   int rc = SPMF_OK;
-#define CALL_ROWS(KPC, SVC) rc = launch_rows<KPC, SVC, false>(rowptr, cols, vals, rowsum, lgam, inv_xi, scale_rows, nrows, D, NQ, Ap, EV, PH, vsum, z, dzr, rowacc, st)
+#define CALL_ROWS(KPC, SVC) rc = launch_rows<KPC, SVC, kRowsTrain>(rowptr, cols, vals, rowsum, lgam, inv_xi, scale_rows, nrows, D, NQ, Ap, EV, PH, vsum, z, dzr, rowacc, nullptr, st)
   SPMF_DISPATCH_KP_SV(KP, SV, CALL_ROWS);
 #undef CALL_ROWS
   return rc;
@@ -870,7 +986,7 @@ int spmf_csr_encode(const long long* rowptr, const int* cols, const float* vals,
   const int KP = spmf_kpad(K), SV = spmf_draw_vec(S), NQ = S / SV;
   cudaStream_t st = (cudaStream_t)stream;
   int rc = SPMF_OK;
-#define CALL_ENC(KPC, SVC) rc = launch_rows<KPC, SVC, true>(rowptr, cols, vals, rowsum, nullptr, inv_xi, scale_rows, nrows, D, NQ, Ap, nullptr, nullptr, nullptr, z, nullptr, nullptr, st)
+#define CALL_ENC(KPC, SVC) rc = launch_rows<KPC, SVC, kRowsEncode>(rowptr, cols, vals, rowsum, nullptr, inv_xi, scale_rows, nrows, D, NQ, Ap, nullptr, nullptr, nullptr, z, nullptr, nullptr, nullptr, st)
   SPMF_DISPATCH_KP_SV(KP, SV, CALL_ENC);
 #undef CALL_ENC
   return rc;
@@ -890,10 +1006,87 @@ int spmf_csc_cols(const int* colptr, const int* rows, const float* vals, int nnz
   if (e == cudaSuccess) e = cudaMemsetAsync(Gphinz, 0, (size_t)NQ * D * SV * sizeof(float), st);
   if (e != cudaSuccess) return (int)e;
   int rc = SPMF_OK;
-#define CALL_COLS(KPC, SVC) rc = launch_cols<KPC, SVC>(colptr, rows, vals, nnz, nrows, D, NQ, z, dzr, EV, PH, GAp, GEVnz, Gphinz, st)
+#define CALL_COLS(KPC, SVC) rc = launch_cols<KPC, SVC, false>(colptr, rows, vals, nnz, nrows, D, NQ, z, dzr, EV, PH, GAp, GEVnz, Gphinz, st)
   SPMF_DISPATCH_KP_SV(KP, SV, CALL_COLS);
 #undef CALL_COLS
   return rc;
+}
+
+// ---- hybrid (tensor-core hot block + gather) variants --------------------------------------------
+// Supported record shapes: REC = KP*SV in {32, 64, 128} (the N of the tcgen05 GEMM).
+#define SPMF_DISPATCH_HYBRID(KP, SV, CALL)                                   \
+  do {                                                                       \
+    if (KP == 32 && SV == 4) { CALL(32, 4); }                                \
+    else if (KP == 32 && SV == 2) { CALL(32, 2); }                           \
+    else if (KP == 32 && SV == 1) { CALL(32, 1); }                           \
+    else if (KP == 16 && SV == 4) { CALL(16, 4); }                           \
+    else if (KP == 16 && SV == 2) { CALL(16, 2); }                           \
+    else if (KP == 8 && SV == 4) { CALL(8, 4); }                             \
+    else return SPMF_ERR_UNSUPPORTED;                                        \
+  } while (0)
+
+int spmf_hybrid_supported(int K, int S) {
+  if (K <= 0 || K > SPMF_MAX_K || S <= 0) return 0;
+  const int KP = spmf_kpad(K), SV = spmf_draw_vec(S);
+  return (KP == 32 && (SV == 4 || SV == 2 || SV == 1)) || (KP == 16 && (SV == 4 || SV == 2)) || (KP == 8 && SV == 4);
+}
+
+int spmf_csr_rows_hybrid(const long long* rowptr, const int* cols, const float* vals, const int* rowmid,
+                         const float* rowsum, const float* lgam, float inv_xi, int scale_rows, int nrows,
+                         int D, int K, int S, const float* Ap, const float* EV, const float* PH,
+                         const double* vsum, float* z, float* dzr, float* rowacc, void* stream) {
+  if (!rowptr || !cols || !vals || !rowmid || !rowsum || !lgam || !Ap || !EV || !PH || !vsum || !z || !dzr || !rowacc)
+    return SPMF_ERR_BAD_ARG;
+  if (nrows <= 0 || D <= 0 || K <= 0 || K > SPMF_MAX_K || S <= 0) return SPMF_ERR_BAD_ARG;
+  const int KP = spmf_kpad(K), SV = spmf_draw_vec(S), NQ = S / SV;
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = SPMF_OK;
+#define CALL_ROWS_H(KPC, SVC) rc = launch_rows<KPC, SVC, kRowsHybrid>(rowptr, cols, vals, rowsum, lgam, inv_xi, scale_rows, nrows, D, NQ, Ap, EV, PH, vsum, z, dzr, rowacc, rowmid, st)
+  SPMF_DISPATCH_HYBRID(KP, SV, CALL_ROWS_H);
+#undef CALL_ROWS_H
+  return rc;
+}
+
+int spmf_csc_cols_hybrid(const int* colptr, const int* rows, const float* vals, int nnz, int nrows, int D,
+                         int K, int S, const float* z, const float* dzr, const float* EV, const float* PH,
+                         float* GAp, float* GEVnz, float* Gphinz, void* stream) {
+  if (!colptr || !rows || !vals || !z || !dzr || !EV || !PH || !GAp || !GEVnz || !Gphinz) return SPMF_ERR_BAD_ARG;
+  if (nnz < 0 || nrows <= 0 || D <= 0 || K <= 0 || K > SPMF_MAX_K || S <= 0) return SPMF_ERR_BAD_ARG;
+  const int KP = spmf_kpad(K), SV = spmf_draw_vec(S), NQ = S / SV;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t nb = (size_t)NQ * D * KP * SV * sizeof(float);
+  cudaError_t e = cudaMemsetAsync(GAp, 0, nb, st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(GEVnz, 0, nb, st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(Gphinz, 0, (size_t)NQ * D * SV * sizeof(float), st);
+  if (e != cudaSuccess) return (int)e;
+  int rc = SPMF_OK;
+#define CALL_COLS_H(KPC, SVC) rc = launch_cols<KPC, SVC, true>(colptr, rows, vals, nnz, nrows, D, NQ, z, dzr, EV, PH, GAp, GEVnz, Gphinz, st)
+  SPMF_DISPATCH_HYBRID(KP, SV, CALL_COLS_H);
+#undef CALL_COLS_H
+  return rc;
+}
+
+// ---- hot split: CSR batch (original column ids) -> ranked, partitioned CSR + dense bf16 hot block ----
+// A nonzero is "covered" by the tensor-core products when its column's rank is < H and its value
+// is exactly representable in bf16 (integer counts <= 256).  Per row, covered entries come first
+// (stored with a negative sign as their flag), the rest after rowmid[row]; column ids become ranks.
+// xhot[b][rank] / xthot[rank][b] receive the covered values (both pre-zeroed here).
+int spmf_hot_split(const long long* rowptr, const int* cols, const float* vals, int nrows, long long nnz,
+                   const int* rank, int H, long long* rowptr_out, int* cols_out, float* vals_out, int* rowmid,
+                   void* xhot, long long ldx, void* xthot, long long ldxt, void* stream) {
+  if (!rowptr || !cols || !vals || !rowptr_out || !cols_out || !vals_out || !rowmid || !xhot || !xthot)
+    return SPMF_ERR_BAD_ARG;
+  if (nrows <= 0 || nnz < 0 || H <= 0 || ldx < H || ldxt < nrows) return SPMF_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long hp = (H + 63) / 64 * 64;
+  cudaError_t e = cudaMemsetAsync(xhot, 0, (size_t)nrows * ldx * 2, st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(xthot, 0, (size_t)hp * ldxt * 2, st);
+  if (e != cudaSuccess) return (int)e;
+  hot_split_kernel<<<(nrows + 3) / 4, 128, 0, st>>>(rowptr, cols, vals, nrows, rank, H, rowptr_out, cols_out,
+                                                    vals_out, rowmid, (unsigned short*)xhot, ldx,
+                                                    (unsigned short*)xthot, ldxt);
+  SPMF_CHECK_LAUNCH();
+  return SPMF_OK;
 }
 
 int spmf_csr_colstats(const int* cols, const float* vals, long long nnz, int D, double* colsum,

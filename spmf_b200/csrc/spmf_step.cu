@@ -43,24 +43,56 @@ int spmf_advi_step(const spmf_step_args* a) {
   if (side != hot) CUDA_TRY(cudaEventRecord((cudaEvent_t)a->ev_join, side));
 
   // ---- hot path
+  const bool hybrid = a->hot_cols > 0;
+  if (hybrid && (!a->rank || !a->rowmid || !a->xhot || !a->xthot || !a->ApT3 || !a->dzrT3)) return SPMF_ERR_BAD_ARG;
   if (a->fresh_noise)
     STEP_TRY(spmf_fill_noise(a->noise, a->params, D, K, S, a->seed, a->rng_step, SPMF_NOISE_NORMAL, hot));
-  STEP_TRY(spmf_draw_operands(a->params, a->noise, a->eta, D, K, S, a->Ap, a->EV, a->PH, a->vsum, a->phisum,
-                              a->scr_d, hot));
+  STEP_TRY(spmf_draw_operands_ranked(a->params, a->noise, a->eta, hybrid ? a->rank : nullptr, D, K, S, a->Ap, a->EV,
+                                     a->PH, a->vsum, a->phisum, a->scr_d, hot));
+  const int KP = spmf_kpad(K), SV = spmf_draw_vec(S), NQ = S / SV, REC = KP * SV;
   if (a->ev_rows0) CUDA_TRY(cudaEventRecord((cudaEvent_t)a->ev_rows0, hot));
-  STEP_TRY(spmf_csr_rows(a->rowptr, a->cols, a->vals, a->rowsum, a->lgam, a->inv_xi, a->scale_rows, a->nrows,
-                         D, K, S, a->Ap, a->EV, a->PH, a->vsum, a->z, a->dzr, a->rowacc, 0, hot));
+  if (!hybrid) {
+    STEP_TRY(spmf_csr_rows(a->rowptr, a->cols, a->vals, a->rowsum, a->lgam, a->inv_xi, a->scale_rows, a->nrows,
+                           D, K, S, a->Ap, a->EV, a->PH, a->vsum, a->z, a->dzr, a->rowacc, 0, hot));
+  } else {
+    // encode product of the hot block on the tensor cores: z = X_hot . A'[0:H]  (un-scaled)
+    const int H = a->hot_cols;
+    const int Hp = (H + 63) / 64 * 64;
+    STEP_TRY(spmf_split3_transpose(a->Ap, REC, (long long)D * REC, H, Hp, REC, a->ApT3, a->ldt,
+                                   (long long)REC * a->ldt, 3LL * REC * a->ldt, NQ, hot));
+    CUDA_TRY(cudaMemsetAsync(a->z, 0, (size_t)NQ * a->nrows * REC * sizeof(float), hot));
+    STEP_TRY(spmf_umma_gemm3(a->xhot, a->ldx, 0, a->nrows, a->ApT3, a->ldt, (long long)REC * a->ldt,
+                             3LL * REC * a->ldt, a->z, REC, (long long)a->nrows * REC, REC, Hp, NQ,
+                             a->gemm_splits, hot));
+    STEP_TRY(spmf_csr_rows_hybrid(a->rowptr, a->cols, a->vals, a->rowmid, a->rowsum, a->lgam, a->inv_xi,
+                                  a->scale_rows, a->nrows, D, K, S, a->Ap, a->EV, a->PH, a->vsum, a->z, a->dzr,
+                                  a->rowacc, hot));
+  }
   if (a->ev_rows1) CUDA_TRY(cudaEventRecord((cudaEvent_t)a->ev_rows1, hot));
   STEP_TRY(spmf_batch_sums(a->z, a->rowacc, a->nrows, K, S, a->zcolsum, a->datasums, a->scr_d, hot));
   if (a->ev_cols0) CUDA_TRY(cudaEventRecord((cudaEvent_t)a->ev_cols0, hot));
-  STEP_TRY(spmf_csc_cols(a->colptr, a->crows, a->cvals, a->nnz, a->nrows, D, K, S, a->z, a->dzr, a->EV, a->PH,
-                         a->GAp, a->GEV, a->Gph, 0, hot));
+  if (!hybrid) {
+    STEP_TRY(spmf_csc_cols(a->colptr, a->crows, a->cvals, a->nnz, a->nrows, D, K, S, a->z, a->dzr, a->EV, a->PH,
+                           a->GAp, a->GEV, a->Gph, 0, hot));
+  } else {
+    STEP_TRY(spmf_csc_cols_hybrid(a->colptr, a->crows, a->cvals, a->nnz, a->nrows, D, K, S, a->z, a->dzr, a->EV,
+                                  a->PH, a->GAp, a->GEV, a->Gph, hot));
+    // GA'[0:H] += X_hot^T . dzr on the tensor cores
+    const int H = a->hot_cols;
+    const int Bp = (a->nrows + 63) / 64 * 64;
+    if (a->ev_gemm0) CUDA_TRY(cudaEventRecord((cudaEvent_t)a->ev_gemm0, hot));
+    STEP_TRY(spmf_split3_transpose(a->dzr, REC, (long long)a->nrows * REC, a->nrows, Bp, REC, a->dzrT3, a->ldt,
+                                   (long long)REC * a->ldt, 3LL * REC * a->ldt, NQ, hot));
+    STEP_TRY(spmf_umma_gemm3(a->xthot, a->ldxt, 0, H, a->dzrT3, a->ldt, (long long)REC * a->ldt,
+                             3LL * REC * a->ldt, a->GAp, REC, (long long)D * REC, REC, Bp, NQ, a->gemm_splits, hot));
+    if (a->ev_gemm1) CUDA_TRY(cudaEventRecord((cudaEvent_t)a->ev_gemm1, hot));
+  }
   if (a->ev_cols1) CUDA_TRY(cudaEventRecord((cudaEvent_t)a->ev_cols1, hot));
   if (side != hot) CUDA_TRY(cudaStreamWaitEvent(hot, (cudaEvent_t)a->ev_join, 0));
-  STEP_TRY(spmf_backward_params(a->params, a->noise, a->dgda, a->eta, D, K, S, a->GAp, a->GEV, a->Gph, a->zcolsum,
-                                a->datasums, a->phisum, (float)a->nrows, a->u_tau_scale, a->s_tau_scale,
-                                a->decay, a->w_entropy, a->w_prior, a->world_size, a->grads, a->parts,
-                                a->scr_f, a->scr_d, hot));
+  STEP_TRY(spmf_backward_params_ranked(a->params, a->noise, a->dgda, a->eta, hybrid ? a->rank : nullptr, D, K, S,
+                                       a->GAp, a->GEV, a->Gph, a->zcolsum, a->datasums, a->phisum, (float)a->nrows,
+                                       a->u_tau_scale, a->s_tau_scale, a->decay, a->w_entropy, a->w_prior,
+                                       a->world_size, a->grads, a->parts, a->scr_f, a->scr_d, hot));
   if (a->adam_lr > 0.f) {
     if (a->world_size > 1) return SPMF_ERR_BAD_ARG;      // the all-reduce must come between backward and Adam
     // the scalar slack inside the gradient block is host-side bookkeeping, not a parameter gradient

@@ -25,6 +25,28 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+def _ceil64(n):
+    return (int(n) + 63) // 64 * 64
+
+
+@dataclass
+class HotSplit:
+    """Hybrid form of a minibatch (spmf_hot_split): ranked + partitioned CSR, its CSC copy, and the
+    dense bf16 hot-column block with its transpose -- the operands of the tcgen05 GEMMs."""
+    H: int
+    rowptr: torch.Tensor          # int64 [nrows+1], zero-based
+    cols: torch.Tensor            # int32 [nnz]   column RANKS
+    vals: torch.Tensor            # fp32 [nnz]    negative = covered by the tensor-core products
+    rowmid: torch.Tensor          # int32 [nrows] first uncovered entry of each row (row-local)
+    xhot: torch.Tensor            # bf16 [nrows][ldx]
+    xthot: torch.Tensor           # bf16 [ceil64(H)][ldxt]
+    ldx: int
+    ldxt: int
+    colptr: torch.Tensor          # int32 [D+1]
+    crows: torch.Tensor
+    cvals: torch.Tensor
+
+
 @dataclass
 class DeviceBatch:
     """One minibatch on the device.  `rowptr` has nrows+1 entries indexing `cols`/`vals`."""
@@ -39,6 +61,38 @@ class DeviceBatch:
     colptr: Optional[torch.Tensor] = None   # int32 [D+1]
     crows: Optional[torch.Tensor] = None    # int32 [nnz] batch-local rows
     cvals: Optional[torch.Tensor] = None    # fp32 [nnz]
+    hot: Optional[HotSplit] = None          # hybrid form (built for one (rank, H) ordering)
+
+    def ensure_hot(self, rank, H, bufs=None):
+        """Build (once) the hybrid form for the column ordering `rank` (int32 [D] device tensor) with
+        H hot columns.  `bufs` may supply reusable staging (the streaming uploader)."""
+        if self.hot is not None and self.hot.H == H:
+            return self.hot
+        dev = self.vals.device
+        n, nnz = self.nrows, self.nnz
+        ldx, ldxt = _ceil64(H), _ceil64(n)
+        m = max(nnz, 1) + 8
+        if bufs is None:
+            bufs = dict(rowptr=torch.empty(n + 1, dtype=torch.int64, device=dev),
+                        cols=torch.empty(m, dtype=torch.int32, device=dev),
+                        vals=torch.empty(m, dtype=torch.float32, device=dev),
+                        rowmid=torch.empty(n, dtype=torch.int32, device=dev),
+                        xhot=torch.empty(n * ldx, dtype=torch.bfloat16, device=dev),
+                        xthot=torch.empty(ldx * ldxt, dtype=torch.bfloat16, device=dev),
+                        colptr=torch.empty(self.D + 1, dtype=torch.int32, device=dev),
+                        crows=torch.empty(m, dtype=torch.int32, device=dev),
+                        cvals=torch.empty(m, dtype=torch.float32, device=dev),
+                        scratch=torch.empty(_abi._lib.spmf_csc_scratch_ints(self.D), dtype=torch.int32, device=dev))
+        st = _stream()
+        _abi.call("spmf_hot_split", _ptr(self.rowptr), _ptr(self.cols), _ptr(self.vals), n, nnz, _ptr(rank), H,
+                  _ptr(bufs["rowptr"]), _ptr(bufs["cols"]), _ptr(bufs["vals"]), _ptr(bufs["rowmid"]),
+                  _ptr(bufs["xhot"]), ldx, _ptr(bufs["xthot"]), ldxt, st)
+        _abi.call("spmf_csr_to_csc", _ptr(bufs["rowptr"]), _ptr(bufs["cols"]), _ptr(bufs["vals"]), n, self.D,
+                  _ptr(bufs["colptr"]), _ptr(bufs["crows"]), _ptr(bufs["cvals"]), _ptr(bufs["scratch"]), st)
+        self.hot = HotSplit(H=H, rowptr=bufs["rowptr"], cols=bufs["cols"], vals=bufs["vals"],
+                            rowmid=bufs["rowmid"], xhot=bufs["xhot"], xthot=bufs["xthot"], ldx=ldx, ldxt=ldxt,
+                            colptr=bufs["colptr"], crows=bufs["crows"], cvals=bufs["cvals"])
+        return self.hot
 
     def ensure_csc(self):
         if self.colptr is None:
@@ -286,8 +340,9 @@ class BatchUploader:
     """Reusable device staging for host batches: async H2D of (rowptr, cols, vals), widening of the
     compact format, then the row constants and the CSC copy are built by kernels on the same stream."""
 
-    def __init__(self, device, D, max_rows=0, max_nnz=0):
+    def __init__(self, device, D, max_rows=0, max_nnz=0, hot=None):
         self.device, self.D = torch.device(device), int(D)
+        self.hot = hot if (hot is not None and hot[0] is not None and hot[1] > 0) else None   # (rank, H)
         self._alloc(max_rows, max_nnz)
 
     def _alloc(self, rows, nnz):
@@ -305,6 +360,17 @@ class BatchUploader:
         self.cursor = torch.empty(_abi._lib.spmf_csc_scratch_ints(self.D), dtype=torch.int32, device=dev)
         self.crows = torch.empty(n, dtype=torch.int32, device=dev)
         self.cvals = torch.empty(n, dtype=torch.float32, device=dev)
+        self.hot_bufs = None
+        if self.hot is not None:
+            H = int(self.hot[1])
+            ldx, ldxt = _ceil64(H), _ceil64(max(rows, 1))
+            self.hot_bufs = dict(rowptr=torch.empty(rows + 1, dtype=torch.int64, device=dev),
+                                 cols=torch.empty(n, dtype=torch.int32, device=dev),
+                                 vals=torch.empty(n, dtype=torch.float32, device=dev),
+                                 rowmid=torch.empty(max(rows, 1), dtype=torch.int32, device=dev),
+                                 xhot=torch.empty(max(rows, 1) * ldx, dtype=torch.bfloat16, device=dev),
+                                 xthot=torch.empty(ldx * ldxt, dtype=torch.bfloat16, device=dev),
+                                 colptr=self.colptr, crows=self.crows, cvals=self.cvals, scratch=self.cursor)
 
     def upload(self, hb: HostCsrBatch) -> DeviceBatch:
         n, nnz = hb.nrows, hb.nnz
@@ -323,6 +389,17 @@ class BatchUploader:
             v16.copy_(hb.vals, non_blocking=True)
         else:
             self.vals[:nnz].copy_(hb.vals, non_blocking=True)
+        if self.hot is not None:
+            # hybrid form: widen, row constants, then the ranked/partitioned CSR + dense bf16 block and
+            # its CSC copy -- all on this (copy) stream, into persistent staging
+            if c16 is not None or v16 is not None:
+                _abi.call("spmf_csr_unpack16", _ptr(c16), _ptr(v16), nnz, _ptr(self.cols), _ptr(self.vals), st)
+            _abi.call("spmf_csr_row_consts", _ptr(self.rowptr), _ptr(self.vals), n, _ptr(self.rowsum),
+                      _ptr(self.lgam), st)
+            db = DeviceBatch(rowptr=self.rowptr[:n + 1], cols=self.cols, vals=self.vals, rowsum=self.rowsum[:n],
+                             lgam=self.lgam[:n], nrows=n, nnz=nnz, D=self.D)
+            db.ensure_hot(self.hot[0], int(self.hot[1]), bufs=self.hot_bufs)
+            return db
         _abi.call("spmf_prepare_batch", _ptr(c16), _ptr(v16), _ptr(self.rowptr), _ptr(self.cols),
                   _ptr(self.vals), n, nnz, self.D, _ptr(self.rowsum), _ptr(self.lgam), _ptr(self.colptr),
                   _ptr(self.crows), _ptr(self.cvals), _ptr(self.cursor), st)
@@ -334,7 +411,7 @@ class BatchUploader:
 _PREFETCH_POOL = {}
 
 
-def prefetch_to_device(host_batches, device, depth=2):
+def prefetch_to_device(host_batches, device, depth=2, hot=None):
     """Generator: uploads HostCsrBatch items `depth` ahead on a copy stream (H2D, widening, row
     constants, CSC build) while the consumer computes on the current stream.  What tf.data's
     `prefetch(AUTOTUNE)` does for the reference's drivers (bin/factorize_csv.py:110-112)."""
@@ -343,6 +420,7 @@ def prefetch_to_device(host_batches, device, depth=2):
     # staging buffers and the copy stream persist across calls: no allocation once warmed up
     pool = _PREFETCH_POOL.setdefault(str(device), {"stream": torch.cuda.Stream(device=device), "ups": {}})
     copy, ups = pool["stream"], pool["ups"]
+    hot_key = None if hot is None or hot[0] is None or hot[1] <= 0 else (hot[0].data_ptr(), int(hot[1]))
     freed = [None] * depth
     queue = []
 
@@ -353,12 +431,13 @@ def prefetch_to_device(host_batches, device, depth=2):
             return False
         if not isinstance(hb, HostCsrBatch):
             hb = hb["counts"] if isinstance(hb, dict) else hb
-        if (slot, hb.D) not in ups:
-            ups[(slot, hb.D)] = BatchUploader(device, hb.D)
+        key = (slot, hb.D, hot_key)
+        if key not in ups:
+            ups[key] = BatchUploader(device, hb.D, hot=hot)
         if freed[slot] is not None:
             copy.wait_event(freed[slot])            # the step that used this staging set is done
         with torch.cuda.stream(copy):
-            db = ups[(slot, hb.D)].upload(hb)
+            db = ups[key].upload(hb)
             ev = torch.cuda.Event()
             ev.record(copy)
         queue.append((db, ev, slot))

@@ -46,6 +46,17 @@ class StepWorkspace:
         self.parts = torch.zeros(S * _abi.NUM_PARTS, dtype=f64, device=device)
         self.ensure_rows(max_rows)
 
+    def ensure_hybrid(self, H, nrows):
+        """bf16 split operands of the tcgen05 GEMMs: ApT3 / dzrT3 as [NQ][3][REC][ldt]."""
+        ldt = max((int(H) + 63) // 64 * 64, (int(nrows) + 63) // 64 * 64)
+        if getattr(self, "ldt", 0) >= ldt:
+            return False
+        n = self.NQ * 3 * self.KP * self.SV * ldt
+        self.ldt = ldt
+        self.ApT3 = torch.zeros(n, dtype=torch.bfloat16, device=self.device)
+        self.dzrT3 = torch.zeros(n, dtype=torch.bfloat16, device=self.device)
+        return True
+
     def ensure_rows(self, nrows):
         if nrows <= self.max_rows:
             return False
@@ -82,6 +93,9 @@ class AdviEngine:
         self.noise = torch.empty(L.n_noise, dtype=torch.float32, device=self.device)
         self.dgda = torch.zeros(L.n_noise, dtype=torch.float32, device=self.device)
         self.eta = torch.ones(D, dtype=torch.float32, device=self.device)
+        self.rank = None          # int32 [D]: table row of each feature (hot-column ordering), or None
+        self.hot_cols = 0         # H > 0 enables the hybrid (tensor-core hot block + gather) step
+        self.hybrid_ok = bool(_abi._lib.spmf_hybrid_supported(self.K, self.S))
         self.inv_xi = 1.0
         self._ws = None
         self._side = None
@@ -206,15 +220,30 @@ class AdviEngine:
         if batch.nrows > w.max_rows:
             w.ensure_rows(batch.nrows)
             self._args = None
-        batch.ensure_csc()
+        hybrid = self.hot_cols > 0 and self.hybrid_ok and self.rank is not None and batch.nnz > 0
+        if hybrid:
+            h = batch.ensure_hot(self.rank, self.hot_cols)
+            if w.ensure_hybrid(self.hot_cols, batch.nrows):
+                self._args = None
+        else:
+            batch.ensure_csc()
         a = self._step_args()
         a.z, a.dzr, a.rowacc = _ptr(w.z), _ptr(w.dzr), _ptr(w.rowacc)
         a.inv_xi, a.scale_rows = self.inv_xi, int(self.scale_rows)
         a.fresh_noise, a.rng_step = int(fresh_noise), self.rng_step
-        a.rowptr, a.cols, a.vals = _ptr(batch.rowptr), _ptr(batch.cols), _ptr(batch.vals)
         a.rowsum, a.lgam = _ptr(batch.rowsum), _ptr(batch.lgam)
-        a.colptr, a.crows, a.cvals = _ptr(batch.colptr), _ptr(batch.crows), _ptr(batch.cvals)
         a.nrows, a.nnz = batch.nrows, batch.nnz
+        if hybrid:
+            a.rowptr, a.cols, a.vals = _ptr(h.rowptr), _ptr(h.cols), _ptr(h.vals)
+            a.colptr, a.crows, a.cvals = _ptr(h.colptr), _ptr(h.crows), _ptr(h.cvals)
+            a.rank, a.hot_cols, a.gemm_splits = _ptr(self.rank), int(self.hot_cols), 0
+            a.rowmid, a.xhot, a.xthot = _ptr(h.rowmid), _ptr(h.xhot), _ptr(h.xthot)
+            a.ldx, a.ldxt, a.ldt = h.ldx, h.ldxt, w.ldt
+            a.ApT3, a.dzrT3 = _ptr(w.ApT3), _ptr(w.dzrT3)
+        else:
+            a.rowptr, a.cols, a.vals = _ptr(batch.rowptr), _ptr(batch.cols), _ptr(batch.vals)
+            a.colptr, a.crows, a.cvals = _ptr(batch.colptr), _ptr(batch.crows), _ptr(batch.cvals)
+            a.rank, a.hot_cols = None, 0
         do_adam = lr is not None and self.world_size == 1
         a.adam_lr = float(lr) if do_adam else 0.0
         a.adam_beta1, a.adam_beta2, a.adam_eps, a.clip_value = beta1, beta2, eps, float(clip_value)
@@ -235,7 +264,7 @@ class AdviEngine:
             self.rng_step += 1
         if do_adam:
             self.opt_step += 1
-        self.launches += 17 + (1 if do_adam else 0)   # kernels issued by spmf_advi_step
+        self.launches += 17 + (1 if do_adam else 0) + (4 if hybrid else 0)   # kernels issued by spmf_advi_step
         return w.parts.view(self.S, _abi.NUM_PARTS)
 
     def loss_and_grad(self, batch: DeviceBatch, fresh_noise=True, variant=0):

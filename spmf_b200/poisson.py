@@ -17,6 +17,7 @@ Differences that are deliberate:
 from __future__ import annotations
 
 import math
+import os
 import pickle
 from typing import Callable, Dict, Iterable, Optional
 
@@ -67,7 +68,8 @@ class PoissonFactorization:
                  decoder_function=None, scale_columns=True, scale_rows=True, log_transform=False,
                  horshoe_plus=True, column_norms=None, count_key='counts',
                  initialize_distributions=True, dtype=torch.float32, device=None,
-                 entropy_weight=1.0, prior_weight=1.0, seed=0, process_group=None, **kwargs):
+                 entropy_weight=1.0, prior_weight=1.0, seed=0, process_group=None, hot_density=None,
+                 **kwargs):
         if encoder_function is not None or decoder_function is not None:
             raise _abi.SpmfError("custom encoder/decoder callables have no CUDA path")
         if log_transform:
@@ -96,6 +98,13 @@ class PoissonFactorization:
         self.xi_u_global = 1.
         if column_norms is not None:
             self.eta_i = torch.as_tensor(column_norms, dtype=torch.float64).reshape(1, -1).cpu()
+        # columns populated in at least this fraction of the rows form the dense "hot block" whose
+        # count products run on the tcgen05 tensor cores (0 disables the hybrid step)
+        if hot_density is None:
+            hot_density = float(os.environ.get("SPMF_HOT_DENSITY", "0.03"))
+        self.hot_density = float(hot_density)
+        self.col_rank = None        # int32 [D] device tensor: rank of each feature by population
+        self.hot_cols = 0
         self.calibrated_expectations = {}
         self._engines: Dict[int, AdviEngine] = {}
         self._params = None
@@ -140,6 +149,7 @@ class PoissonFactorization:
         xi = float(self.xi_u_global)
         eng.inv_xi = 1.0 / xi if self.scale_rows else 1.0
         eng.scale_rows = bool(self.scale_rows)
+        eng.rank, eng.hot_cols = self.col_rank, int(self.hot_cols)
 
     @property
     def surrogate_vars(self):
@@ -160,6 +170,7 @@ class PoissonFactorization:
         print("Looping through the entire dataset once to get some stats")          # poisson.py:116
         colsum = torch.zeros(self.feature_dim, dtype=torch.float64, device=self.device)
         colnnz = torch.zeros(self.feature_dim, dtype=torch.float32, device=self.device)
+        nrows_seen = 0
         if isinstance(data_factory, CsrShard):
             shards = [data_factory]
         else:
@@ -167,6 +178,7 @@ class PoissonFactorization:
             for batch in iter(data_factory()):
                 c = batch[self.count_key] if isinstance(batch, dict) else batch
                 if isinstance(c, DeviceBatch):
+                    nrows_seen += c.nrows
                     n0 = int(c.rowptr[0].item())
                     cols, vals = c.cols[n0:n0 + c.nnz], c.vals[n0:n0 + c.nnz]
                     _abi.call("spmf_csr_colstats", _ptr(cols), _ptr(vals), c.nnz, self.feature_dim,
@@ -179,10 +191,29 @@ class PoissonFactorization:
             cs, cn = sh.column_stats()
             colsum += cs
             colnnz += cn
+            nrows_seen += sh.nrows
+        nrows_all = torch.tensor([float(nrows_seen)], dtype=torch.float64, device=self.device)
         if torch.distributed.is_available() and torch.distributed.is_initialized():
             torch.distributed.all_reduce(colsum, group=self.process_group)
             torch.distributed.all_reduce(colnnz, group=self.process_group)
+            torch.distributed.all_reduce(nrows_all, group=self.process_group)
+        self._choose_hot_columns(colnnz, float(nrows_all.item()))
         self._set_scales_from_stats(colsum.cpu(), colnnz.cpu())
+
+    def _choose_hot_columns(self, colnnz, nrows):
+        """Column ordering for the hybrid step: features ranked by how many rows populate them; the
+        H columns populated in >= hot_density of the rows form the tensor-core block.  Identical on
+        every rank (computed from the all-reduced counts)."""
+        self.col_rank, self.hot_cols = None, 0
+        if self.hot_density <= 0 or nrows <= 0 or not _abi._lib.spmf_hybrid_supported(self.latent_dim, 4):
+            return
+        order = torch.argsort(colnnz.to(torch.float64), descending=True, stable=True)
+        H = int((colnnz.to(torch.float64) >= self.hot_density * nrows).sum().item())
+        if H < 64:                      # not worth a GEMM
+            return
+        rank = torch.empty(self.feature_dim, dtype=torch.int32, device=self.device)
+        rank[order] = torch.arange(self.feature_dim, dtype=torch.int32, device=self.device)
+        self.col_rank, self.hot_cols = rank, H
 
     def _set_scales_from_stats(self, colsum, colnnz):
         colmeans_nonzero = colsum.to(torch.float64) / colnnz.to(torch.float64)      # :136-138
@@ -445,7 +476,7 @@ class PoissonFactorization:
         c = first[self.count_key] if isinstance(first, dict) else first
         if isinstance(c, HostCsrBatch):
             return prefetch_to_device((b[self.count_key] if isinstance(b, dict) else b for b in chained),
-                                      self.device)
+                                      self.device, hot=(self.col_rank, self.hot_cols))
         return chained
 
     @staticmethod

@@ -1,0 +1,199 @@
+"""GPU tests of the hybrid step: tcgen05 GEMMs on the dense hot-column block + gather kernels.
+
+* the tensor-core GEMM (bf16 counts x 3-way bf16 split of an fp32 operand) against float64;
+* the hot split (ranked, partitioned CSR + dense bf16 block) against a numpy restatement;
+* the full ADVI step in hybrid mode against the float64 oracle, same tolerances as the gather path
+  (1e-4 relative; 5e-4 for the InverseGamma-family tensors), and against the gather path itself."""
+import numpy as np
+import pytest
+import torch
+
+from tests.util import make_counts, make_oracle, perturbed_params, rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-4
+TOL_IG = 5e-4
+
+
+def _ptr(t):
+    return t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+@pytest.mark.parametrize("M,N,Kd,NQ,splits", [
+    (128, 128, 64, 1, 1),        # one tile, one stage
+    (300, 128, 192, 1, 1),       # ragged M, three chunks (pipeline wraps once)
+    (257, 64, 640, 2, 3),        # split-K with atomics, two draw groups, N=64
+    (96, 32, 448, 1, 0),         # M < tile, N=32, automatic split
+    (1024, 128, 1024, 1, 2),     # many chunks per CTA: every stage / phase parity reused
+])
+def test_umma_gemm3_matches_float64(M, N, Kd, NQ, splits):
+    from spmf_b200 import _abi
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device="cpu").manual_seed(M * 7 + N)
+    A = torch.randint(0, 40, (M, Kd), generator=g).to(torch.float32)
+    A[torch.rand(M, Kd, generator=g) < 0.6] = 0
+    Bsrc = torch.randn(NQ, Kd, N, generator=g) * torch.exp(2 * torch.randn(NQ, Kd, N, generator=g))
+    Ad = A.to(dev).to(torch.bfloat16).contiguous()
+    Bd = Bsrc.to(dev).contiguous()
+    ldt = Kd
+    B3 = torch.zeros(NQ, 3, N, ldt, dtype=torch.bfloat16, device=dev)
+    _abi.call("spmf_split3_transpose", _ptr(Bd), N, Kd * N, Kd, Kd, N, _ptr(B3), ldt, N * ldt, 3 * N * ldt, NQ,
+              _stream())
+    torch.cuda.synchronize()
+    # the three terms reproduce the fp32 operand to 24 bits
+    rec = B3.to(torch.float64).sum(1).transpose(1, 2).cpu()
+    assert rel_err(rec.numpy(), Bsrc.double().numpy()) < 2e-7
+    C0 = torch.randn(NQ, M, N, generator=g)
+    C = C0.to(dev).contiguous()
+    _abi.call("spmf_umma_gemm3", _ptr(Ad), Kd, 0, M, _ptr(B3), ldt, N * ldt, 3 * N * ldt, _ptr(C), N, M * N,
+              N, Kd, NQ, splits, _stream())
+    torch.cuda.synchronize()
+    ref = C0.double() + torch.einsum("mk,qkn->qmn", A.double(), Bsrc.double())
+    err = (C.cpu().double() - ref).abs().max() / ref.abs().max()
+    assert float(err) < 2e-6, float(err)
+
+
+def test_hot_split_partitions_and_fills_dense_block():
+    from spmf_b200 import _abi
+    from spmf_b200.data import CsrShard
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(3)
+    B, D, H = 70, 90, 33
+    x = rng.poisson(0.8, size=(B, D)).astype(np.float32)
+    x[rng.random((B, D)) < 0.02] = 300.0          # not exact in bf16 -> stays on the gather path
+    x[5, :] = 0
+    x[5, 7] = 2.5                                  # exact in bf16, non-integer
+    x[6, 3] = 257.0                                # not exact
+    rank = rng.permutation(D).astype(np.int32)
+    sh = CsrShard.from_dense(torch.from_numpy(x), dev)
+    b = sh.batch(0, B)
+    h = b.ensure_hot(torch.from_numpy(rank).to(dev), H)
+    torch.cuda.synchronize()
+    rp = h.rowptr.cpu().numpy()
+    cols, vals, mid = h.cols.cpu().numpy(), h.vals.cpu().numpy(), h.rowmid.cpu().numpy()
+    xh = h.xhot.view(B, h.ldx).float().cpu().numpy()
+    xt = h.xthot.view(h.ldx, h.ldxt).float().cpu().numpy()
+    assert rp[0] == 0 and rp[-1] == int((x != 0).sum())
+    dense = np.zeros((B, D), np.float32)
+    exp_hot = np.zeros((B, h.ldx), np.float32)
+    for r in range(B):
+        seg = slice(rp[r], rp[r + 1])
+        c, v = cols[seg], vals[seg]
+        assert (v[:mid[r]] < 0).all() and (v[mid[r]:] > 0).all()
+        assert (c[:mid[r]] < H).all()
+        dense[r, c] = np.abs(v)
+        exp_hot[r, c[:mid[r]]] = -v[:mid[r]]
+    inv = np.empty(D, np.int64)
+    inv[rank] = np.arange(D)
+    assert np.array_equal(dense[:, rank], x)                      # ranked ids, values intact
+    # coverage rule: rank < H and exactly representable in bf16
+    xr = x[:, inv]                                                # columns in rank order
+    exact = torch.from_numpy(xr).to(torch.bfloat16).float().numpy() == xr
+    cov = (xr > 0) & exact & (np.arange(D)[None, :] < H)
+    assert not cov[:, H:].any() and np.array_equal(exp_hot[:, :H] != 0, cov[:, :H])
+    assert np.array_equal(xh, exp_hot) and np.array_equal(xt[:, :B], exp_hot.T[:, :B])
+    assert (xt[:, B:] == 0).all() and (xh[:, H:] == 0).all()
+    # CSC copy carries the same flags
+    cp = h.colptr.cpu().numpy()
+    assert cp[-1] == rp[-1]
+    cr, cv = h.crows.cpu().numpy(), h.cvals.cpu().numpy()
+    back = np.zeros((B, D), np.float32)
+    for d in range(D):
+        back[cr[cp[d]:cp[d + 1]], d] = cv[cp[d]:cp[d + 1]]
+    assert np.array_equal(np.abs(back), xr) and np.array_equal(back < 0, cov)
+
+
+def _step(model, eng, params, noise, batch):
+    views = eng.layout.views(eng.params)
+    for k, v in params.items():
+        views[k].copy_(v.to(device=eng.device, dtype=torch.float32))
+    eng.set_noise_from(noise)
+    parts = eng.loss_and_grad(batch, fresh_noise=False)
+    torch.cuda.synchronize()
+    return float(eng.loss_value(parts).item())
+
+
+@pytest.mark.parametrize("D,K,B,S,kind,big", [
+    (128, 32, 200, 4, "noise", False),     # REC=128, every column hot, ragged row tile
+    (300, 32, 96, 4, "sparse", True),      # hot + cold columns, counts > 256 mixed in
+    (200, 16, 150, 4, "linear", False),    # REC=64
+    (96, 8, 130, 4, "linear", False),      # REC=32
+    (160, 32, 70, 2, "noise", True),       # SV=2 -> REC=64
+    (130, 20, 300, 8, "sparse", False),    # K padded to 32, two draw groups
+])
+def test_hybrid_step_matches_oracle_and_gather_path(D, K, B, S, kind, big):
+    import spmf_b200
+    from oracle.spmf_oracle import draw_noise
+    dev = torch.device("cuda:0")
+    x = make_counts(B, D, seed=11, kind=kind)
+    if big:
+        rng = np.random.default_rng(5)
+        m = (rng.random(x.shape) < 0.01) & (x > 0)
+        x[m] = 300.0 + x[m]
+    N = 10 * B
+    oracle = make_oracle(D, K, N, x)
+    params = perturbed_params(oracle, 0.3, 11)
+    noise = draw_noise(oracle, params, S, seed=12)
+    ref_loss, ref_grads, ref_parts = oracle.loss_and_grads(params, noise, {'counts': torch.tensor(x, dtype=torch.float64)})
+
+    out = {}
+    for name, dens in (("hybrid", 0.03), ("gather", 0.0)):
+        model = spmf_b200.PoissonFactorization(latent_dim=K, feature_dim=D, u_tau_scale=1.0 / np.sqrt(N * D),
+                                               device=dev, hot_density=dens)
+        model.compute_scales(lambda: [{'counts': x}])
+        eng = model._engine_for(S)
+        if name == "hybrid":
+            assert eng.hot_cols >= 64 and eng.hybrid_ok, (eng.hot_cols, eng.hybrid_ok)
+        else:
+            assert eng.hot_cols == 0
+        batch = spmf_b200.as_device_batch(x, dev)
+        loss = _step(model, eng, params, noise, batch)
+        if name == "hybrid":
+            assert batch.hot is not None and batch.hot.H == eng.hot_cols
+        assert abs(loss - ref_loss) <= TOL * abs(ref_loss), (name, loss, ref_loss)
+        pd = eng.parts_dict()
+        for pn in list(ref_parts):
+            ref = ref_parts[pn].numpy()
+            assert np.abs(pd[pn].numpy() - ref).max() <= TOL * max(np.abs(ref).max(), 1.0), (name, pn)
+        grads = {k: v.cpu().numpy().copy() for k, v in eng.layout.views(eng.grads).items()}
+        for k, g in ref_grads.items():
+            tol = TOL if k.split('/')[0] in ('v', 'w', 'u', 's') else TOL_IG
+            e = rel_err(grads[k], g.numpy())
+            assert e <= tol, (name, k, e)
+        out[name] = (loss, grads)
+    # the two CUDA paths agree with each other far inside the oracle tolerance
+    assert abs(out["hybrid"][0] - out["gather"][0]) <= 2e-6 * abs(out["gather"][0])
+    for k in out["gather"][1]:
+        assert rel_err(out["hybrid"][1][k], out["gather"][1][k]) <= 2e-5, k
+
+
+def test_hybrid_fit_reduces_loss_and_streams():
+    """Training through the public API in hybrid mode: resident batches and host-streamed batches
+    give the same losses; the loss goes down."""
+    import spmf_b200
+    from spmf_b200.data import CsrShard, HostCsr
+    dev = torch.device("cuda:0")
+    B, D, K = 256, 192, 16
+    x = make_counts(4 * B, D, seed=2, kind="linear")
+    sh = CsrShard.from_dense(torch.from_numpy(x), dev)
+
+    def run(stream):
+        model = spmf_b200.PoissonFactorization(latent_dim=K, feature_dim=D, u_tau_scale=1.0 / np.sqrt(x.size),
+                                               device=dev, seed=3)
+        model.compute_scales(sh)
+        assert model.hot_cols >= 64
+        if stream:
+            host = HostCsr.from_shard(sh)
+            fac = lambda: ({'counts': hb} for hb in host.iter_batches(B))
+        else:
+            fac = lambda: ({'counts': b} for b in sh.iter_batches(B))
+        return model.fit(fac, num_steps=4, learning_rate=0.05, sample_size=4, verbose=False, rel_tol=None)
+
+    a, b = run(False), run(True)
+    assert a[-1] < a[0]
+    assert np.allclose(a, b, rtol=1e-5), (a, b)
