@@ -188,6 +188,8 @@ def main():
     ap.add_argument("--lr", type=float, default=0.01)
     ap.add_argument("--K", type=int, default=None, help="override the workload's latent dim (C5 sweep)")
     ap.add_argument("--S", type=int, default=None, help="override the number of Monte-Carlo draws")
+    ap.add_argument("--hot-density", type=float, default=None,
+                    help="column population threshold of the tensor-core hot block (0 = gather kernels only)")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
     if args.K:
@@ -219,12 +221,16 @@ def main():
     shard = make_shard(wl, dev, seed=1234 + 3 + 1000 * rank)
     n_total = shard.nrows * world
     model = spmf_b200.PoissonFactorization(latent_dim=K, feature_dim=D, u_tau_scale=1.0 / np.sqrt(n_total * D),
-                                           device=dev, seed=1234)
+                                           device=dev, seed=1234, hot_density=args.hot_density)
     model.compute_scales(shard)
     batches = list(shard.iter_batches(B))
-    for b in batches:
-        b.ensure_csc()
     eng = model._engine_for(S)
+    hybrid = eng.hot_cols > 0 and eng.hybrid_ok
+    for b in batches:
+        if hybrid:
+            b.ensure_hot(eng.rank, eng.hot_cols)     # ranked CSR/CSC + dense bf16 hot block, built once
+        else:
+            b.ensure_csc()
     eng.ws.ensure_rows(B)
     torch.cuda.synchronize()
 
@@ -283,7 +289,7 @@ def main():
         src = (hbatches[(start + i) % len(hbatches)] for i in range(n))
         prev = None
         tlast = time.perf_counter()
-        for i, db in enumerate(prefetch_to_device(src, dev)):
+        for i, db in enumerate(prefetch_to_device(src, dev, hot=(model.col_rank, model.hot_cols) if hybrid else None)):
             if os.environ.get("BENCH_DEBUG"):
                 tnow = time.perf_counter()
                 print(f"e2e iter {i} host dt {1e3 * (tnow - tlast):.2f} ms", file=sys.stderr)
@@ -338,6 +344,15 @@ def main():
             byts = [8.0 * n + 4 * (D + 1) + 2 * B * C * 4 + D * C * 4 + D * S * 4 + 2 * D * C * 4 + D * S * 4 for n in nz]
         kern[name] = {"ms": sum(dur) / len(dur), "bytes": sum(byts) / len(byts),
                       "flop": sum(nz) / len(nz) * (6 if name == "csr_rows" else 6) * K * S}
+    if hybrid and "umma_gemm_gradA" in kev:
+        # tensor-core side of the column pass: split + tcgen05 GEMM GA'[0:H] += X_hot^T . dzr (3 bf16 terms)
+        dur = [a.elapsed_time(b) for a, b, _, _ in kev["umma_gemm_gradA"]]
+        Hp, Bp = (eng.hot_cols + 63) // 64 * 64, (B + 63) // 64 * 64
+        gemm_ms = sum(dur) / len(dur)
+        gemm_info = {"ms": gemm_ms, "bf16_TFLOPs": 2.0 * eng.hot_cols * Bp * C * 3 / (gemm_ms * 1e-3) / 1e12,
+                     "shape": f"M={eng.hot_cols} N={C} K={Bp} x3 bf16 terms", "Hp": Hp}
+    else:
+        gemm_info = None
     dom = max(kern, key=lambda k: kern[k]["ms"])
     achieved = kern[dom]["bytes"] / (kern[dom]["ms"] * 1e-3) / 1e9
     step_ms = ms_max / args.steps
@@ -346,8 +361,11 @@ def main():
                 "kernel_ms": kern[dom]["ms"], "kernel_share_of_step": kern[dom]["ms"] / step_ms,
                 "kernels": {k: {"ms": v["ms"], "alg_GBps": v["bytes"] / (v["ms"] * 1e-3) / 1e9,
                                 "fp32_TFLOPs": v["flop"] / (v["ms"] * 1e-3) / 1e12} for k, v in kern.items()},
+                "hot_cols": int(eng.hot_cols) if hybrid else 0, "umma_gemm_gradA": None,
                 "note": "gather/FMA-bound SpMM+SDDMM at K*S=128 channels: per nonzero 8 B of HBM vs ~2 KB of "
                         "L2/L1 gather and 12*K*S flop; fp32 FMA peak 74.4 TFLOP/s (148 SM x 128 lanes x 2 x 1.965 GHz)"}
+
+    roofline["umma_gemm_gradA"] = gemm_info
 
     # ------------------------------------------------ CPU baseline (rank 0, bounded sample)
     cpu = None

@@ -147,34 +147,57 @@ int spmf_backward_params_ranked(const float* params, const float* noise, const f
                                 const double* phisum, float batch_rows, float u_tau_scale, float s_tau_scale,
                                 float decay, float w_entropy, float w_prior, int world_size, float* grads,
                                 double* parts, float* scr_f, double* scr_d, void* stream);
+/* Operands of the tcgen05 GEMM live in global memory "UMMA-tiled": tile by tile in the byte order the
+ * tensor core reads from shared memory (K-major, no swizzle), so that a pipeline stage is two
+ * contiguous TMA bulk copies.  A (bf16 counts): tiles [row/128][k/64] of 128 x 64; B3 (three bf16
+ * terms of an fp32 operand): tiles [k/64][term] of N x 64.  Sizes / element offsets: */
+long long spmf_umma_tiled_a_elems(long long M, long long Kd);          /* bf16 elements, M and Kd padded */
+long long spmf_umma_tiled_b_elems(int N, long long Kd);
+long long spmf_umma_tiled_a_index(long long row, long long k, long long Kd);
+int spmf_umma_tile_a(const void* src_bf16, long long ld, int M, int Kd, void* dst, void* stream); /* row-major -> tiled */
 /* CSR batch (original column ids) -> ranked + partitioned CSR (zero-based rowptr_out[nrows+1]; per row
  * the entries covered by the tensor-core products first, stored with a NEGATIVE value as their flag,
- * the others from rowmid[row] on) and the dense hot block as bf16: xhot[nrows][ldx] (ldx >= H,
- * multiple of 64) and its transpose xthot[ceil64(H)][ldxt] (ldxt >= nrows, multiple of 64); both are
- * zeroed here.  Covered = rank < H and the count is exactly representable in bf16. */
+ * the others from rowmid[row] on) and the dense hot block as UMMA-tiled bf16: xhot = X[nrows][Hp] and
+ * its transpose xthot = X^T[H][Bp] (Hp = ceil64(H), Bp = ceil64(nrows); sizes from
+ * spmf_umma_tiled_a_elems; both zeroed here).  Covered = rank < H and the count is exactly
+ * representable in bf16. */
 int spmf_hot_split(const long long* rowptr, const int* cols, const float* vals, int nrows, long long nnz,
                    const int* rank, int H, long long* rowptr_out, int* cols_out, float* vals_out, int* rowmid,
-                   void* xhot, long long ldx, void* xthot, long long ldxt, void* stream);
-/* fp32 src[NQ][R][C] (row stride lds) -> bf16 dst[NQ][3][C][ldd] transposed, hi+mid+lo = src to 24 bits;
- * destination columns [R, Rpad) are written as zeros. */
+                   void* xhot, void* xthot, void* stream);
+/* fp32 src[NQ][R][C] (row stride lds) -> UMMA-tiled B3 operand dst[NQ] with k = source row (i.e. the
+ * transpose), hi+mid+lo = src to 24 bits; k in [R, Rpad) is written as zeros.  C % 32 == 0, Rpad % 64 == 0. */
 int spmf_split3_transpose(const float* src, long long lds, long long src_qstride, int R, int Rpad, int C,
-                          void* dst3, long long ldd, long long dst_tstride, long long dst_qstride, int NQ,
-                          void* stream);
-/* C[q][M][N] (fp32, row stride ldc, accumulated with atomics) += A[q][M][Kd] (bf16, row stride lda)
- * * (B3[q][0]+B3[q][1]+B3[q][2])[N][Kd]^T (bf16, row stride ldb) on tcgen05; N in {32,64,128},
- * Kd % 64 == 0, `splits` = split-K factor. */
-int spmf_umma_gemm3(const void* A, long long lda, long long a_qstride, int M, const void* B3, long long ldb,
-                    long long b_tstride, long long b_qstride, float* C, long long ldc, long long c_qstride,
-                    int N, int Kd, int NQ, int splits, void* stream);
+                          void* dst3, long long dst_qstride, int NQ, void* stream);
+/* C[q][M][N] (fp32, row stride ldc, accumulated with atomics) += A[q] (UMMA-tiled, M x Kd)
+ * * (B3[q] hi+mid+lo)^T (UMMA-tiled, N x Kd) on tcgen05; N in {32,64,128}, Kd % 64 == 0,
+ * `splits` = split-K factor (<= 0: automatic). */
+int spmf_umma_gemm3(const void* A, long long a_qstride, int M, const void* B3, long long b_qstride, float* C,
+                    long long ldc, long long c_qstride, int N, int Kd, int NQ, int splits, void* stream);
 /* row / column passes of the hybrid step (same outputs as spmf_csr_rows / spmf_csc_cols): `z` must
  * hold the GEMM's un-scaled hot block of x.A' on entry; GA' of covered entries is left to the GEMM. */
 int spmf_csr_rows_hybrid(const long long* rowptr, const int* cols, const float* vals, const int* rowmid,
                          const float* rowsum, const float* lgam, float inv_xi, int scale_rows, int nrows,
                          int D, int K, int S, const float* Ap, const float* EV, const float* PH,
                          const double* vsum, float* z, float* dzr, float* rowacc, void* stream);
-int spmf_csc_cols_hybrid(const int* colptr, const int* rows, const float* vals, int nnz, int nrows, int D,
-                         int K, int S, const float* z, const float* dzr, const float* EV, const float* PH,
-                         float* GAp, float* GEVnz, float* Gphinz, void* stream);
+/* column pass over the two CSC copies of a hot-split batch: `hot_*` holds the covered entries (GEV and
+ * Gphi only -- their GA' comes from the GEMM), `cold_*` the rest (full column pass).  Zeroes the three
+ * tables first.  nnz_bound >= either copy's count (the counts themselves are colptr[D], device side). */
+int spmf_csc_cols_hybrid(const int* hot_colptr, const int* hot_rows, const float* hot_vals,
+                         const int* cold_colptr, const int* cold_rows, const float* cold_vals, int nnz_bound,
+                         int nrows, int D, int K, int S, const float* z, const float* dzr, const float* EV,
+                         const float* PH, float* GAp, float* GEVnz, float* Gphinz, void* stream);
+/* the pieces of spmf_csc_cols_hybrid, for callers that overlap them on several streams: zero the three
+ * column-gradient tables; accumulate (atomics) one CSC copy into them -- covered != 0: GEV and Gphi
+ * only (hot copy), covered == 0: full column pass (cold copy). */
+int spmf_zero_col_grads(float* GAp, float* GEVnz, float* Gphinz, int D, int K, int S, void* stream);
+int spmf_csc_cols_accum(const int* colptr, const int* rows, const float* vals, int nnz_bound, int nrows, int D,
+                        int K, int S, const float* z, const float* dzr, const float* EV, const float* PH,
+                        float* GAp, float* GEVnz, float* Gphinz, int covered, void* stream);
+/* CSC copy of ONE part of a partitioned CSR (spmf_hot_split): part 0 = the first rowmid[r] entries of
+ * every row, part 1 = the rest; values are stored as |x|.  rowmid == NULL: whole rows. */
+int spmf_csr_to_csc_part(const long long* rowptr, const int* rowmid, int part, const int* cols, const float* vals,
+                         int nrows, int D, int* colptr, int* rows_out, float* vals_out, int* scratch,
+                         void* stream);
 
 /* ---- one call per step / per uploaded batch ----
  * spmf_advi_step issues the whole sequence above (noise, Gamma gradients, operands, row pass, sums,
@@ -220,11 +243,17 @@ typedef struct spmf_step_args {
    * arrays of spmf_hot_split (rowptr zero-based); rank maps feature -> table row */
   const int* rank;
   int hot_cols, gemm_splits;
-  long long ldx, ldxt, ldt;        /* row strides (elements) of xhot, xthot and of ApT3 / dzrT3 */
+  long long t3_qstride;            /* elements between draw groups in ApT3 / dzrT3 */
   const int* rowmid;
-  const void *xhot, *xthot;
-  void *ApT3, *dzrT3;              /* bf16 workspaces [NQ][3][REC][ldt] */
+  const int *hot_colptr, *hot_crows;   /* CSC of the covered entries (colptr/crows/cvals above: the rest) */
+  const float* hot_cvals;
+  const void *xhot, *xthot;        /* UMMA-tiled bf16 hot block and its transpose (spmf_hot_split) */
+  void *ApT3, *dzrT3;              /* UMMA-tiled bf16 B3 workspaces, [NQ] x spmf_umma_tiled_b_elems */
   void *ev_gemm0, *ev_gemm1;       /* optional events around the tensor-core launches of the column side */
+  /* optional: two more streams (+ three events) on which the GA' GEMM and the cold column pass run
+   * concurrently with the hot column pass; NULL = everything in order on the hot stream */
+  void *aux_stream1, *aux_stream2;
+  void *ev_aux_fork, *ev_aux_join1, *ev_aux_join2;
 } spmf_step_args;
 int spmf_advi_step(const spmf_step_args* args);
 /* widen a compact batch (either 16-bit source may be NULL), build its row constants and CSC copy */

@@ -72,11 +72,18 @@ _SIGS = {
     "spmf_draw_operands_ranked": (i32, [p, p, p, p, i32, i32, i32, p, p, p, p, p, p, p]),
     "spmf_backward_params_ranked": (i32, [p, p, p, p, p, i32, i32, i32, p, p, p, p, p, p, f32, f32, f32, f32,
                                           f32, f32, i32, p, p, p, p, p]),
-    "spmf_hot_split": (i32, [p, p, p, i32, i64, p, i32, p, p, p, p, p, i64, p, i64, p]),
-    "spmf_split3_transpose": (i32, [p, i64, i64, i32, i32, i32, p, i64, i64, i64, i32, p]),
-    "spmf_umma_gemm3": (i32, [p, i64, i64, i32, p, i64, i64, i64, p, i64, i64, i32, i32, i32, i32, p]),
+    "spmf_umma_tiled_a_elems": (i64, [i64, i64]),
+    "spmf_umma_tiled_b_elems": (i64, [i32, i64]),
+    "spmf_umma_tiled_a_index": (i64, [i64, i64, i64]),
+    "spmf_umma_tile_a": (i32, [p, i64, i32, i32, p, p]),
+    "spmf_hot_split": (i32, [p, p, p, i32, i64, p, i32, p, p, p, p, p, p, p]),
+    "spmf_split3_transpose": (i32, [p, i64, i64, i32, i32, i32, p, i64, i32, p]),
+    "spmf_umma_gemm3": (i32, [p, i64, i32, p, i64, p, i64, i64, i32, i32, i32, i32, p]),
     "spmf_csr_rows_hybrid": (i32, [p, p, p, p, p, p, f32, i32, i32, i32, i32, i32, p, p, p, p, p, p, p, p]),
-    "spmf_csc_cols_hybrid": (i32, [p, p, p, i32, i32, i32, i32, i32, p, p, p, p, p, p, p, p]),
+    "spmf_csc_cols_hybrid": (i32, [p, p, p, p, p, p, i32, i32, i32, i32, i32, p, p, p, p, p, p, p, p]),
+    "spmf_zero_col_grads": (i32, [p, p, p, i32, i32, i32, p]),
+    "spmf_csc_cols_accum": (i32, [p, p, p, i32, i32, i32, i32, i32, p, p, p, p, p, p, p, i32, p]),
+    "spmf_csr_to_csc_part": (i32, [p, p, i32, p, p, i32, i32, p, p, p, p, p]),
 }
 
 
@@ -98,8 +105,10 @@ class StepArgs(C.Structure):
         + [(n, p) for n in ("caller_stream", "hot_stream", "side_stream", "ev_fork", "ev_join", "ev_done",
                             "ev_rows0", "ev_rows1", "ev_cols0", "ev_cols1")]
         + [("rank", p), ("hot_cols", i32), ("gemm_splits", i32)]
-        + [(n, i64) for n in ("ldx", "ldxt", "ldt")]
-        + [(n, p) for n in ("rowmid", "xhot", "xthot", "ApT3", "dzrT3", "ev_gemm0", "ev_gemm1")]
+        + [("t3_qstride", i64)]
+        + [(n, p) for n in ("rowmid", "hot_colptr", "hot_crows", "hot_cvals", "xhot", "xthot", "ApT3", "dzrT3",
+                            "ev_gemm0", "ev_gemm1", "aux_stream1", "aux_stream2", "ev_aux_fork", "ev_aux_join1",
+                            "ev_aux_join2")]
     )
 
 

@@ -16,6 +16,7 @@
 
 #include "../../include/spmf_b200.h"
 #include "spmf_record.cuh"
+#include "spmf_umma_layout.cuh"
 
 namespace spmf {
 
@@ -431,18 +432,20 @@ csr_rows_kernel(const long long* __restrict__ rowptr, const int* __restrict__ co
 // atomics when the column changes (only columns that straddle slices are contended).
 constexpr int kSliceLen = 256;
 
-// HYBRID: entries whose value carries a negative sign are covered by the tensor-core GEMM for the
-// GA' product (spmf_umma.cu): their dzr gather is skipped; every other term uses |x|.
-template <int KP, int SV, bool HYBRID>
-__global__ void __launch_bounds__(128, 4)
+// NO_GA: the hot-block variant of the hybrid step -- every entry of this CSC is covered by the
+// tensor-core GEMM for the GA' product (spmf_umma.cu), so only z is gathered (GEV, Gphi); with the
+// dzr record and its accumulators gone the kernel keeps four nonzeros in flight per slot instead of two.
+// `nnz_bound` sizes the grid; the actual count is colptr[D] (known on the device only).
+template <int KP, int SV, bool NO_GA>
+__global__ void __launch_bounds__(128, NO_GA ? 5 : 4)
 csc_cols_kernel(const int* __restrict__ colptr, const int* __restrict__ rows,
-                const float* __restrict__ vals, int nnz, int nrows, int D,
+                const float* __restrict__ vals, int nnz_bound, int nrows, int D,
                 const float* __restrict__ z, const float* __restrict__ dzr,
                 const float* __restrict__ EV, const float* __restrict__ PH,
-                float* __restrict__ GAp, float* __restrict__ GEV, float* __restrict__ Gphi) {
+                float* __restrict__ GAp, float* __restrict__ GEV, float* __restrict__ Gphi, int slice_len) {
   using M = Map<KP, SV>;
   constexpr int VW = M::VW, LPN = M::LPN, RG = M::RG, VPL = M::VPL, REC = M::REC, NSLOT = M::NSLOT;
-  constexpr int U = VPL >= 4 ? 2 : 4;
+  constexpr int U = (VPL >= 4 && !NO_GA) ? 2 : 4;
   const int lane = threadIdx.x & 31;
   const int slot = threadIdx.x / LPN;
   const int li = threadIdx.x % LPN;
@@ -450,9 +453,10 @@ csc_cols_kernel(const int* __restrict__ colptr, const int* __restrict__ rows,
   const int q = blockIdx.y;
   const unsigned gmask = slot_mask<LPN>(lane);
   const int slice = blockIdx.x * NSLOT + slot;
-  const int j0 = slice * kSliceLen;
+  const int j0 = slice * slice_len;          // slice_len is a multiple of 4: 16-byte index loads stay aligned
+  const int nnz = min(nnz_bound, __ldg(colptr + D));
   if (j0 >= nnz) return;
-  const int j1 = min(j0 + kSliceLen, nnz);
+  const int j1 = min(j0 + slice_len, nnz);
   int off[VPL];
 #pragma unroll
   for (int i = 0; i < VPL; ++i) off[i] = M::off(i, s, kg);
@@ -474,13 +478,16 @@ csc_cols_kernel(const int* __restrict__ colptr, const int* __restrict__ rows,
   int d = lo;
   int next = __ldg(colptr + d + 1);
 
-  float ev[VPL][VW], aEV[VPL][VW], aAp[VPL][VW], ph, aPh;
+  float ev[VPL][VW], aEV[VPL][VW], aAp[NO_GA ? 1 : VPL][VW], ph, aPh;
   auto load_col = [&](int dd) {
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
       ldv<VW>(ev[i], EVl + (unsigned)dd * REC + off[i]);
 #pragma unroll
-      for (int w = 0; w < VW; ++w) { aEV[i][w] = 0.f; aAp[i][w] = 0.f; }
+      for (int w = 0; w < VW; ++w) {
+        aEV[i][w] = 0.f;
+        if constexpr (!NO_GA) aAp[i][w] = 0.f;
+      }
     }
     ph = __ldg(PHl + (unsigned)dd * SV);
     aPh = 0.f;
@@ -492,12 +499,12 @@ csc_cols_kernel(const int* __restrict__ colptr, const int* __restrict__ rows,
 #pragma unroll
       for (int w = 0; w < VW; ++w) {
         atomicAdd(GEVq + o + w, aEV[i][w]);
-        atomicAdd(GApq + o + w, aAp[i][w]);
+        if constexpr (!NO_GA) atomicAdd(GApq + o + w, aAp[i][w]);
       }
     }
     if (kg == 0) atomicAdd(Gphq + (unsigned)dd * SV, aPh);
   };
-  auto one = [&](int j, float x, const float (&zz)[VPL][VW], const float (&dd)[VPL][VW]) {
+  auto one = [&](int j, float x, const float (&zz)[VPL][VW], const float (&dd)[NO_GA ? 1 : VPL][VW]) {
     if (j >= next) {
       flush_col(d);
       do {
@@ -519,7 +526,7 @@ csc_cols_kernel(const int* __restrict__ colptr, const int* __restrict__ rows,
 #pragma unroll
       for (int w = 0; w < VW; ++w) {
         aEV[i][w] = fmaf(gq, zz[i][w], aEV[i][w]);
-        aAp[i][w] = fmaf(x, dd[i][w], aAp[i][w]);
+        if constexpr (!NO_GA) aAp[i][w] = fmaf(x, dd[i][w], aAp[i][w]);
       }
   };
   load_col(d);
@@ -539,40 +546,25 @@ csc_cols_kernel(const int* __restrict__ colptr, const int* __restrict__ rows,
       bb[0] = b2.x; bb[1] = b2.y;
       xx[0] = x2.x; xx[1] = x2.y;
     }
-    float zz[U][VPL][VW], dd[U][VPL][VW];
+    float zz[U][VPL][VW], dd[U][NO_GA ? 1 : VPL][VW];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const bool cov = HYBRID && xx[u] < 0.f;
-      if constexpr (HYBRID) xx[u] = fabsf(xx[u]);
+    for (int u = 0; u < U; ++u)
 #pragma unroll
       for (int i = 0; i < VPL; ++i) {
         ldv<VW>(zz[u][i], zl + (unsigned)bb[u] * REC + off[i]);
-        if (!cov) {
-          ldv<VW>(dd[u][i], dl + (unsigned)bb[u] * REC + off[i]);
-        } else {
-#pragma unroll
-          for (int w = 0; w < VW; ++w) dd[u][i][w] = 0.f;
-        }
+        if constexpr (!NO_GA) ldv<VW>(dd[u][i], dl + (unsigned)bb[u] * REC + off[i]);
       }
-    }
 #pragma unroll
     for (int u = 0; u < U; ++u) one(jb + u, xx[u], zz[u], dd[u]);
   }
   for (int j = j0 + nfull * U; j < j1; ++j) {     // tail of the last slice
     const int b = __ldg(rows + j);
-    float x = __ldg(vals + j);
-    const bool cov = HYBRID && x < 0.f;
-    if constexpr (HYBRID) x = fabsf(x);
-    float zz[VPL][VW], dd[VPL][VW];
+    const float x = __ldg(vals + j);
+    float zz[VPL][VW], dd[NO_GA ? 1 : VPL][VW];
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
       ldv<VW>(zz[i], zl + (unsigned)b * REC + off[i]);
-      if (!cov) {
-        ldv<VW>(dd[i], dl + (unsigned)b * REC + off[i]);
-      } else {
-#pragma unroll
-        for (int w = 0; w < VW; ++w) dd[i][w] = 0.f;
-      }
+      if constexpr (!NO_GA) ldv<VW>(dd[i], dl + (unsigned)b * REC + off[i]);
     }
     one(j, x, zz, dd);
   }
@@ -622,12 +614,26 @@ __global__ void csr_colstats_kernel(const int* __restrict__ cols, const float* _
   }
 }
 
-__global__ void count_cols_kernel(const long long* __restrict__ rowptr, const int* __restrict__ cols,
-                                  int nrows, int* __restrict__ cnt) {
-  const long long base = rowptr[0], end = rowptr[nrows];
-  long long j = base + (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (; j < end; j += stride) atomicAdd(cnt + __ldg(cols + j), 1);
+// Row r's entries of one part of a partitioned CSR (spmf_hot_split): part 0 = the first rowmid[r]
+// entries, part 1 = the rest; rowmid == nullptr = the whole row.
+__device__ __forceinline__ void part_range(const long long* __restrict__ rowptr, const int* __restrict__ rowmid,
+                                           int part, int row, long long& j0, long long& j1) {
+  j0 = rowptr[row];
+  j1 = rowptr[row + 1];
+  if (rowmid) {
+    const long long m = j0 + rowmid[row];
+    if (part == 0) j1 = m; else j0 = m;
+  }
+}
+
+__global__ void count_cols_kernel(const long long* __restrict__ rowptr, const int* __restrict__ rowmid, int part,
+                                  const int* __restrict__ cols, int nrows, int* __restrict__ cnt) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= nrows) return;
+  long long j0, j1;
+  part_range(rowptr, rowmid, part, row, j0, j1);
+  for (long long j = j0 + lane; j < j1; j += 32) atomicAdd(cnt + __ldg(cols + j), 1);
 }
 
 // ---- block-partitioned transpose (D*4 bytes fit in shared memory) -------------------------------
@@ -648,8 +654,8 @@ __device__ __forceinline__ int tr_row_bound(const long long* __restrict__ rowptr
 }
 
 __global__ void __launch_bounds__(kTrThreads)
-csc_block_hist_kernel(const long long* __restrict__ rowptr, const int* __restrict__ cols, int nrows,
-                      int D, int* __restrict__ blockhist) {
+csc_block_hist_kernel(const long long* __restrict__ rowptr, const int* __restrict__ rowmid, int part,
+                      const int* __restrict__ cols, int nrows, int D, int* __restrict__ blockhist) {
   extern __shared__ int h[];
   for (int d = threadIdx.x; d < D; d += blockDim.x) h[d] = 0;
   __syncthreads();
@@ -657,8 +663,17 @@ csc_block_hist_kernel(const long long* __restrict__ rowptr, const int* __restric
   const int r0 = tr_row_bound(rowptr, nrows, base + nnz * blockIdx.x / gridDim.x);
   const int r1 = (blockIdx.x + 1 == gridDim.x) ? nrows
                                                : tr_row_bound(rowptr, nrows, base + nnz * (blockIdx.x + 1) / gridDim.x);
-  const long long j0 = rowptr[r0], j1 = rowptr[r1];
-  for (long long j = j0 + threadIdx.x; j < j1; j += blockDim.x) atomicAdd(&h[__ldg(cols + j)], 1);
+  if (!rowmid) {
+    const long long j0 = rowptr[r0], j1 = rowptr[r1];
+    for (long long j = j0 + threadIdx.x; j < j1; j += blockDim.x) atomicAdd(&h[__ldg(cols + j)], 1);
+  } else {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    for (int row = r0 + warp; row < r1; row += nwarp) {
+      long long j0, j1;
+      part_range(rowptr, rowmid, part, row, j0, j1);
+      for (long long j = j0 + lane; j < j1; j += 32) atomicAdd(&h[__ldg(cols + j)], 1);
+    }
+  }
   __syncthreads();
   int* out = blockhist + (long long)blockIdx.x * D;
   for (int d = threadIdx.x; d < D; d += blockDim.x) out[d] = h[d];
@@ -682,8 +697,8 @@ __global__ void csc_block_scan_kernel(int* __restrict__ blockhist, int nblocks, 
 }
 
 __global__ void __launch_bounds__(kTrThreads)
-csc_block_scatter_kernel(const long long* __restrict__ rowptr, const int* __restrict__ cols,
-                         const float* __restrict__ vals, int nrows, int D,
+csc_block_scatter_kernel(const long long* __restrict__ rowptr, const int* __restrict__ rowmid, int part,
+                         const int* __restrict__ cols, const float* __restrict__ vals, int nrows, int D,
                          const int* __restrict__ colptr, const int* __restrict__ blockhist,
                          int* __restrict__ rows_out, float* __restrict__ vals_out) {
   extern __shared__ int cur[];
@@ -696,11 +711,12 @@ csc_block_scatter_kernel(const long long* __restrict__ rowptr, const int* __rest
                                                : tr_row_bound(rowptr, nrows, base + nnz * (blockIdx.x + 1) / gridDim.x);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   for (int row = r0 + warp; row < r1; row += nwarp) {
-    const long long j0 = rowptr[row], j1 = rowptr[row + 1];
+    long long j0, j1;
+    part_range(rowptr, rowmid, part, row, j0, j1);
     for (long long j = j0 + lane; j < j1; j += 32) {
       const int pos = atomicAdd(&cur[__ldg(cols + j)], 1);
       rows_out[pos] = row;
-      vals_out[pos] = __ldg(vals + j);
+      vals_out[pos] = fabsf(__ldg(vals + j));     // the sign is the hot-split coverage flag
     }
   }
 }
@@ -743,18 +759,20 @@ __global__ void exscan_int_kernel(const int* __restrict__ in, int n, int* __rest
   if (threadIdx.x == 0) { out[n] = carry; if (cursor) cursor[n] = carry; }
 }
 
-__global__ void scatter_csc_kernel(const long long* __restrict__ rowptr, const int* __restrict__ cols,
-                                   const float* __restrict__ vals, int nrows, int* __restrict__ cursor,
-                                   int* __restrict__ rows_out, float* __restrict__ vals_out) {
+__global__ void scatter_csc_kernel(const long long* __restrict__ rowptr, const int* __restrict__ rowmid, int part,
+                                   const int* __restrict__ cols, const float* __restrict__ vals, int nrows,
+                                   int* __restrict__ cursor, int* __restrict__ rows_out,
+                                   float* __restrict__ vals_out) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= nrows) return;
-  const long long j0 = rowptr[row], j1 = rowptr[row + 1];
+  long long j0, j1;
+  part_range(rowptr, rowmid, part, row, j0, j1);
   for (long long j = j0 + lane; j < j1; j += 32) {
     const int d = __ldg(cols + j);
     const int pos = atomicAdd(cursor + d, 1);
     rows_out[pos] = row;
-    vals_out[pos] = __ldg(vals + j);
+    vals_out[pos] = fabsf(__ldg(vals + j));
   }
 }
 
@@ -847,8 +865,8 @@ hot_split_kernel(const long long* __restrict__ rowptr, const int* __restrict__ c
                  const float* __restrict__ vals, int nrows, const int* __restrict__ rank, int H,
                  long long* __restrict__ rowptr_out, int* __restrict__ cols_out,
                  float* __restrict__ vals_out, int* __restrict__ rowmid,
-                 unsigned short* __restrict__ xhot, long long ldx, unsigned short* __restrict__ xthot,
-                 long long ldxt) {
+                 unsigned short* __restrict__ xhot, long long hchunks, unsigned short* __restrict__ xthot,
+                 long long bchunks) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= nrows) return;
@@ -888,8 +906,8 @@ hot_split_kernel(const long long* __restrict__ rowptr, const int* __restrict__ c
       cols_out[o] = r;
       vals_out[o] = -x;
       const unsigned short hx = (unsigned short)(__float_as_uint(x) >> 16);
-      xhot[(long long)row * ldx + r] = hx;
-      xthot[(long long)r * ldxt + row] = hx;
+      xhot[tiledA_index(row, r, hchunks)] = hx;      // UMMA-tiled X[nrows][Hp]
+      xthot[tiledA_index(r, row, bchunks)] = hx;     // UMMA-tiled X^T[H][Bp]
     } else if (in) {
       const long long o = pu + __popc(mu & below);
       cols_out[o] = r;
@@ -914,16 +932,17 @@ static int launch_rows(const long long* rowptr, const int* cols, const float* va
   return SPMF_OK;
 }
 
-template <int KP, int SV, bool HYBRID>
+template <int KP, int SV, bool NO_GA>
 static int launch_cols(const int* colptr, const int* rows, const float* vals, int nnz, int nrows,
                        int D, int NQ, const float* z, const float* dzr, const float* EV,
-                       const float* PH, float* GAp, float* GEV, float* Gphi, cudaStream_t st) {
+                       const float* PH, float* GAp, float* GEV, float* Gphi, cudaStream_t st,
+                       int slice_len = kSliceLen) {
   constexpr int NSLOT = Map<KP, SV>::NSLOT;
-  const int nslices = (nnz + kSliceLen - 1) / kSliceLen;
+  const int nslices = (nnz + slice_len - 1) / slice_len;
   if (nslices == 0) return SPMF_OK;
   dim3 grid((nslices + NSLOT - 1) / NSLOT, NQ);
-  csc_cols_kernel<KP, SV, HYBRID><<<grid, 128, 0, st>>>(colptr, rows, vals, nnz, nrows, D, z, dzr, EV, PH,
-                                                       GAp, GEV, Gphi);
+  csc_cols_kernel<KP, SV, NO_GA><<<grid, 128, 0, st>>>(colptr, rows, vals, nnz, nrows, D, z, dzr, EV, PH,
+                                                      GAp, GEV, Gphi, slice_len);
   SPMF_CHECK_LAUNCH();
   return SPMF_OK;
 }
@@ -1047,22 +1066,48 @@ int spmf_csr_rows_hybrid(const long long* rowptr, const int* cols, const float* 
   return rc;
 }
 
-int spmf_csc_cols_hybrid(const int* colptr, const int* rows, const float* vals, int nnz, int nrows, int D,
-                         int K, int S, const float* z, const float* dzr, const float* EV, const float* PH,
-                         float* GAp, float* GEVnz, float* Gphinz, void* stream) {
-  if (!colptr || !rows || !vals || !z || !dzr || !EV || !PH || !GAp || !GEVnz || !Gphinz) return SPMF_ERR_BAD_ARG;
-  if (nnz < 0 || nrows <= 0 || D <= 0 || K <= 0 || K > SPMF_MAX_K || S <= 0) return SPMF_ERR_BAD_ARG;
+int spmf_zero_col_grads(float* GAp, float* GEVnz, float* Gphinz, int D, int K, int S, void* stream) {
+  if (!GAp || !GEVnz || !Gphinz || D <= 0 || K <= 0 || K > SPMF_MAX_K || S <= 0) return SPMF_ERR_BAD_ARG;
   const int KP = spmf_kpad(K), SV = spmf_draw_vec(S), NQ = S / SV;
   cudaStream_t st = (cudaStream_t)stream;
   const size_t nb = (size_t)NQ * D * KP * SV * sizeof(float);
   cudaError_t e = cudaMemsetAsync(GAp, 0, nb, st);
   if (e == cudaSuccess) e = cudaMemsetAsync(GEVnz, 0, nb, st);
   if (e == cudaSuccess) e = cudaMemsetAsync(Gphinz, 0, (size_t)NQ * D * SV * sizeof(float), st);
-  if (e != cudaSuccess) return (int)e;
+  return e == cudaSuccess ? SPMF_OK : (int)e;
+}
+
+int spmf_csc_cols_accum(const int* colptr, const int* rows, const float* vals, int nnz_bound, int nrows, int D,
+                        int K, int S, const float* z, const float* dzr, const float* EV, const float* PH,
+                        float* GAp, float* GEVnz, float* Gphinz, int covered, void* stream) {
+  if (!colptr || !rows || !vals || !z || !dzr || !EV || !PH || !GAp || !GEVnz || !Gphinz) return SPMF_ERR_BAD_ARG;
+  if (nnz_bound < 0 || nrows <= 0 || D <= 0 || K <= 0 || K > SPMF_MAX_K || S <= 0) return SPMF_ERR_BAD_ARG;
+  const int KP = spmf_kpad(K), SV = spmf_draw_vec(S), NQ = S / SV;
+  cudaStream_t st = (cudaStream_t)stream;
   int rc = SPMF_OK;
-#define CALL_COLS_H(KPC, SVC) rc = launch_cols<KPC, SVC, true>(colptr, rows, vals, nnz, nrows, D, NQ, z, dzr, EV, PH, GAp, GEVnz, Gphinz, st)
-  SPMF_DISPATCH_HYBRID(KP, SV, CALL_COLS_H);
-#undef CALL_COLS_H
+  if (covered) {     // GEV and Gphi only: GA' of these entries comes from the tensor-core GEMM
+#define CALL_COLS_HOT(KPC, SVC) rc = launch_cols<KPC, SVC, true>(colptr, rows, vals, nnz_bound, nrows, D, NQ, z, dzr, EV, PH, GAp, GEVnz, Gphinz, st)
+    SPMF_DISPATCH_HYBRID(KP, SV, CALL_COLS_HOT);
+#undef CALL_COLS_HOT
+  } else {           // sparse remainder: short slices keep every SM busy on a small stream
+#define CALL_COLS_COLD(KPC, SVC) rc = launch_cols<KPC, SVC, false>(colptr, rows, vals, nnz_bound, nrows, D, NQ, z, dzr, EV, PH, GAp, GEVnz, Gphinz, st, 64)
+    SPMF_DISPATCH_HYBRID(KP, SV, CALL_COLS_COLD);
+#undef CALL_COLS_COLD
+  }
+  return rc;
+}
+
+int spmf_csc_cols_hybrid(const int* hot_colptr, const int* hot_rows, const float* hot_vals,
+                         const int* cold_colptr, const int* cold_rows, const float* cold_vals, int nnz_bound,
+                         int nrows, int D, int K, int S, const float* z, const float* dzr, const float* EV,
+                         const float* PH, float* GAp, float* GEVnz, float* Gphinz, void* stream) {
+  int rc = spmf_zero_col_grads(GAp, GEVnz, Gphinz, D, K, S, stream);
+  if (rc == SPMF_OK)
+    rc = spmf_csc_cols_accum(hot_colptr, hot_rows, hot_vals, nnz_bound, nrows, D, K, S, z, dzr, EV, PH, GAp, GEVnz,
+                             Gphinz, 1, stream);
+  if (rc == SPMF_OK)
+    rc = spmf_csc_cols_accum(cold_colptr, cold_rows, cold_vals, nnz_bound, nrows, D, K, S, z, dzr, EV, PH, GAp,
+                             GEVnz, Gphinz, 0, stream);
   return rc;
 }
 
@@ -1073,18 +1118,18 @@ int spmf_csc_cols_hybrid(const int* colptr, const int* rows, const float* vals, 
 // xhot[b][rank] / xthot[rank][b] receive the covered values (both pre-zeroed here).
 int spmf_hot_split(const long long* rowptr, const int* cols, const float* vals, int nrows, long long nnz,
                    const int* rank, int H, long long* rowptr_out, int* cols_out, float* vals_out, int* rowmid,
-                   void* xhot, long long ldx, void* xthot, long long ldxt, void* stream) {
+                   void* xhot, void* xthot, void* stream) {
   if (!rowptr || !cols || !vals || !rowptr_out || !cols_out || !vals_out || !rowmid || !xhot || !xthot)
     return SPMF_ERR_BAD_ARG;
-  if (nrows <= 0 || nnz < 0 || H <= 0 || ldx < H || ldxt < nrows) return SPMF_ERR_BAD_ARG;
+  if (nrows <= 0 || nnz < 0 || H <= 0) return SPMF_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
-  const long long hp = (H + 63) / 64 * 64;
-  cudaError_t e = cudaMemsetAsync(xhot, 0, (size_t)nrows * ldx * 2, st);
-  if (e == cudaSuccess) e = cudaMemsetAsync(xthot, 0, (size_t)hp * ldxt * 2, st);
+  const long long hp = (H + 63) / 64 * 64, bp = ((long long)nrows + 63) / 64 * 64;
+  cudaError_t e = cudaMemsetAsync(xhot, 0, (size_t)spmf_umma_tiled_a_elems(nrows, hp) * 2, st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(xthot, 0, (size_t)spmf_umma_tiled_a_elems(H, bp) * 2, st);
   if (e != cudaSuccess) return (int)e;
   hot_split_kernel<<<(nrows + 3) / 4, 128, 0, st>>>(rowptr, cols, vals, nrows, rank, H, rowptr_out, cols_out,
-                                                    vals_out, rowmid, (unsigned short*)xhot, ldx,
-                                                    (unsigned short*)xthot, ldxt);
+                                                    vals_out, rowmid, (unsigned short*)xhot, hp / 64,
+                                                    (unsigned short*)xthot, bp / 64);
   SPMF_CHECK_LAUNCH();
   return SPMF_OK;
 }
@@ -1104,8 +1149,14 @@ long long spmf_csc_scratch_ints(int D) { return (long long)(kTrBlocks + 1) * ((l
 
 int spmf_csr_to_csc(const long long* rowptr, const int* cols, const float* vals, int nrows, int D,
                     int* colptr, int* rows_out, float* vals_out, int* scratch, void* stream) {
+  return spmf_csr_to_csc_part(rowptr, nullptr, 0, cols, vals, nrows, D, colptr, rows_out, vals_out, scratch, stream);
+}
+
+int spmf_csr_to_csc_part(const long long* rowptr, const int* rowmid, int part, const int* cols, const float* vals,
+                         int nrows, int D, int* colptr, int* rows_out, float* vals_out, int* scratch,
+                         void* stream) {
   if (!rowptr || !cols || !vals || !colptr || !rows_out || !vals_out || !scratch) return SPMF_ERR_BAD_ARG;
-  if (nrows <= 0 || D <= 0) return SPMF_ERR_BAD_ARG;
+  if (nrows <= 0 || D <= 0 || (part != 0 && part != 1)) return SPMF_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   int* colcnt = scratch;                       // [D+1]
   int* blockhist = scratch + (D + 1);          // [kTrBlocks][D]
@@ -1118,17 +1169,18 @@ int spmf_csr_to_csc(const long long* rowptr, const int* cols, const float* vals,
       attr_set = true;
     }
     const int nb = nrows < kTrBlocks ? nrows : kTrBlocks;
-    csc_block_hist_kernel<<<nb, kTrThreads, smem, st>>>(rowptr, cols, nrows, D, blockhist);
+    csc_block_hist_kernel<<<nb, kTrThreads, smem, st>>>(rowptr, rowmid, part, cols, nrows, D, blockhist);
     csc_block_scan_kernel<<<(D + 63) / 64, 64, 0, st>>>(blockhist, nb, D, colcnt);
     exscan_int_kernel<<<1, 1024, 0, st>>>(colcnt, D, colptr, nullptr);
-    csc_block_scatter_kernel<<<nb, kTrThreads, smem, st>>>(rowptr, cols, vals, nrows, D, colptr, blockhist,
-                                                          rows_out, vals_out);
+    csc_block_scatter_kernel<<<nb, kTrThreads, smem, st>>>(rowptr, rowmid, part, cols, vals, nrows, D, colptr,
+                                                          blockhist, rows_out, vals_out);
   } else {                                     // very wide matrices: global atomic cursors
     cudaError_t e = cudaMemsetAsync(colcnt, 0, (size_t)(D + 1) * sizeof(int), st);
     if (e != cudaSuccess) return (int)e;
-    count_cols_kernel<<<148 * 8, 256, 0, st>>>(rowptr, cols, nrows, colcnt);
+    count_cols_kernel<<<(nrows + 7) / 8, 256, 0, st>>>(rowptr, rowmid, part, cols, nrows, colcnt);
     exscan_int_kernel<<<1, 1024, 0, st>>>(colcnt, D, colptr, colcnt);
-    scatter_csc_kernel<<<(nrows + 3) / 4, 128, 0, st>>>(rowptr, cols, vals, nrows, colcnt, rows_out, vals_out);
+    scatter_csc_kernel<<<(nrows + 3) / 4, 128, 0, st>>>(rowptr, rowmid, part, cols, vals, nrows, colcnt, rows_out,
+                                                       vals_out);
   }
   SPMF_CHECK_LAUNCH();
   return SPMF_OK;

@@ -44,7 +44,9 @@ int spmf_advi_step(const spmf_step_args* a) {
 
   // ---- hot path
   const bool hybrid = a->hot_cols > 0;
-  if (hybrid && (!a->rank || !a->rowmid || !a->xhot || !a->xthot || !a->ApT3 || !a->dzrT3)) return SPMF_ERR_BAD_ARG;
+  if (hybrid && (!a->rank || !a->rowmid || !a->xhot || !a->xthot || !a->ApT3 || !a->dzrT3 || !a->hot_colptr ||
+                 !a->hot_crows || !a->hot_cvals))
+    return SPMF_ERR_BAD_ARG;
   if (a->fresh_noise)
     STEP_TRY(spmf_fill_noise(a->noise, a->params, D, K, S, a->seed, a->rng_step, SPMF_NOISE_NORMAL, hot));
   STEP_TRY(spmf_draw_operands_ranked(a->params, a->noise, a->eta, hybrid ? a->rank : nullptr, D, K, S, a->Ap, a->EV,
@@ -58,12 +60,10 @@ int spmf_advi_step(const spmf_step_args* a) {
     // encode product of the hot block on the tensor cores: z = X_hot . A'[0:H]  (un-scaled)
     const int H = a->hot_cols;
     const int Hp = (H + 63) / 64 * 64;
-    STEP_TRY(spmf_split3_transpose(a->Ap, REC, (long long)D * REC, H, Hp, REC, a->ApT3, a->ldt,
-                                   (long long)REC * a->ldt, 3LL * REC * a->ldt, NQ, hot));
+    STEP_TRY(spmf_split3_transpose(a->Ap, REC, (long long)D * REC, H, Hp, REC, a->ApT3, a->t3_qstride, NQ, hot));
     CUDA_TRY(cudaMemsetAsync(a->z, 0, (size_t)NQ * a->nrows * REC * sizeof(float), hot));
-    STEP_TRY(spmf_umma_gemm3(a->xhot, a->ldx, 0, a->nrows, a->ApT3, a->ldt, (long long)REC * a->ldt,
-                             3LL * REC * a->ldt, a->z, REC, (long long)a->nrows * REC, REC, Hp, NQ,
-                             a->gemm_splits, hot));
+    STEP_TRY(spmf_umma_gemm3(a->xhot, 0, a->nrows, a->ApT3, a->t3_qstride, a->z, REC, (long long)a->nrows * REC,
+                             REC, Hp, NQ, a->gemm_splits, hot));
     STEP_TRY(spmf_csr_rows_hybrid(a->rowptr, a->cols, a->vals, a->rowmid, a->rowsum, a->lgam, a->inv_xi,
                                   a->scale_rows, a->nrows, D, K, S, a->Ap, a->EV, a->PH, a->vsum, a->z, a->dzr,
                                   a->rowacc, hot));
@@ -75,17 +75,37 @@ int spmf_advi_step(const spmf_step_args* a) {
     STEP_TRY(spmf_csc_cols(a->colptr, a->crows, a->cvals, a->nnz, a->nrows, D, K, S, a->z, a->dzr, a->EV, a->PH,
                            a->GAp, a->GEV, a->Gph, 0, hot));
   } else {
-    STEP_TRY(spmf_csc_cols_hybrid(a->colptr, a->crows, a->cvals, a->nnz, a->nrows, D, K, S, a->z, a->dzr, a->EV,
-                                  a->PH, a->GAp, a->GEV, a->Gph, hot));
-    // GA'[0:H] += X_hot^T . dzr on the tensor cores
+    // three independent accumulations into the (zeroed) column-gradient tables:
+    //   hot CSC (covered entries): GEV, Gphi          -- gather kernel, hot stream
+    //   GA'[0:H] += X_hot^T . dzr                     -- tcgen05 GEMM, aux stream 1
+    //   cold CSC (everything else): GEV, Gphi, GA'    -- gather kernel, aux stream 2
     const int H = a->hot_cols;
     const int Bp = (a->nrows + 63) / 64 * 64;
-    if (a->ev_gemm0) CUDA_TRY(cudaEventRecord((cudaEvent_t)a->ev_gemm0, hot));
-    STEP_TRY(spmf_split3_transpose(a->dzr, REC, (long long)a->nrows * REC, a->nrows, Bp, REC, a->dzrT3, a->ldt,
-                                   (long long)REC * a->ldt, 3LL * REC * a->ldt, NQ, hot));
-    STEP_TRY(spmf_umma_gemm3(a->xthot, a->ldxt, 0, H, a->dzrT3, a->ldt, (long long)REC * a->ldt,
-                             3LL * REC * a->ldt, a->GAp, REC, (long long)D * REC, REC, Bp, NQ, a->gemm_splits, hot));
-    if (a->ev_gemm1) CUDA_TRY(cudaEventRecord((cudaEvent_t)a->ev_gemm1, hot));
+    const bool fork = a->aux_stream1 && a->aux_stream2 && a->ev_aux_fork && a->ev_aux_join1 && a->ev_aux_join2;
+    cudaStream_t s1 = fork ? (cudaStream_t)a->aux_stream1 : hot;
+    cudaStream_t s2 = fork ? (cudaStream_t)a->aux_stream2 : hot;
+    STEP_TRY(spmf_zero_col_grads(a->GAp, a->GEV, a->Gph, D, K, S, hot));
+    if (fork) {
+      CUDA_TRY(cudaEventRecord((cudaEvent_t)a->ev_aux_fork, hot));
+      CUDA_TRY(cudaStreamWaitEvent(s1, (cudaEvent_t)a->ev_aux_fork, 0));
+      CUDA_TRY(cudaStreamWaitEvent(s2, (cudaEvent_t)a->ev_aux_fork, 0));
+    }
+    if (a->ev_gemm0) CUDA_TRY(cudaEventRecord((cudaEvent_t)a->ev_gemm0, s1));
+    STEP_TRY(spmf_split3_transpose(a->dzr, REC, (long long)a->nrows * REC, a->nrows, Bp, REC, a->dzrT3,
+                                   a->t3_qstride, NQ, s1));
+    STEP_TRY(spmf_umma_gemm3(a->xthot, 0, H, a->dzrT3, a->t3_qstride, a->GAp, REC, (long long)D * REC, REC, Bp, NQ,
+                             a->gemm_splits, s1));
+    if (a->ev_gemm1) CUDA_TRY(cudaEventRecord((cudaEvent_t)a->ev_gemm1, s1));
+    STEP_TRY(spmf_csc_cols_accum(a->colptr, a->crows, a->cvals, a->nnz, a->nrows, D, K, S, a->z, a->dzr, a->EV,
+                                 a->PH, a->GAp, a->GEV, a->Gph, 0, s2));
+    STEP_TRY(spmf_csc_cols_accum(a->hot_colptr, a->hot_crows, a->hot_cvals, a->nnz, a->nrows, D, K, S, a->z, a->dzr,
+                                 a->EV, a->PH, a->GAp, a->GEV, a->Gph, 1, hot));
+    if (fork) {
+      CUDA_TRY(cudaEventRecord((cudaEvent_t)a->ev_aux_join1, s1));
+      CUDA_TRY(cudaEventRecord((cudaEvent_t)a->ev_aux_join2, s2));
+      CUDA_TRY(cudaStreamWaitEvent(hot, (cudaEvent_t)a->ev_aux_join1, 0));
+      CUDA_TRY(cudaStreamWaitEvent(hot, (cudaEvent_t)a->ev_aux_join2, 0));
+    }
   }
   if (a->ev_cols1) CUDA_TRY(cudaEventRecord((cudaEvent_t)a->ev_cols1, hot));
   if (side != hot) CUDA_TRY(cudaStreamWaitEvent(hot, (cudaEvent_t)a->ev_join, 0));

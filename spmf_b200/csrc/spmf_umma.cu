@@ -10,20 +10,20 @@
 // product with fp32 accumulation in tensor memory.  N = SV*KP channels (32, 64 or 128).
 //
 // One CTA = one 128-row tile of C and a range of K (split-K; partial tiles meet through fp32
-// atomics in C).  Operands are staged by cp.async into the canonical K-major no-swizzle UMMA layout
-// (8-row x 16-byte core matrices, LBO = 128 B, SBO = 1 KiB), three stages deep; one thread issues
-// the MMAs and commits them to an mbarrier per stage; the accumulator is read back with tcgen05.ld
-// by the four warps (warp w owns TMEM lanes 32w..32w+31).
+// atomics in C).  Operands live in global memory already in the canonical K-major no-swizzle UMMA
+// byte order (8-row x 16-byte core matrices, LBO = 128 B, SBO = 1 KiB), tile by tile, so a stage is
+// two contiguous TMA bulk copies (cp.async.bulk + mbarrier complete_tx), three stages deep.  One
+// thread produces, one thread issues the MMAs and commits them to the stage's "empty" mbarrier; the
+// accumulator is read back with tcgen05.ld by the four warps (warp w owns TMEM lanes 32w..32w+31).
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 #include "../../include/spmf_b200.h"
+#include "spmf_umma_layout.cuh"
 
 namespace spmf {
 
-constexpr int kGemmBM = 128;      // rows of C per CTA (UMMA M)
-constexpr int kGemmBK = 64;       // k elements per stage (4 UMMA k-steps of 16)
 constexpr int kGemmStages = 3;
 constexpr int kGemmThreads = 128;
 
@@ -83,11 +83,6 @@ __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
   } while (!done);
 }
 
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes)
-               : "memory");
-}
-
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   uint32_t r[32];
   asm volatile(
@@ -104,35 +99,39 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// One stage: A tile [128][64] bf16 (16 KiB) followed by three B tiles [N][64] bf16 (N*128 B each).
 template <int N>
 struct GemmSmem {
-  static constexpr int A_BYTES = kGemmBM * kGemmBK * 2;
-  static constexpr int B_BYTES = N * kGemmBK * 2;
-  static constexpr int STAGE_BYTES = A_BYTES + 3 * B_BYTES;
+  static constexpr int A_BYTES = kTileABytes;
+  static constexpr int B_BYTES = 3 * N * kGemmBK * 2;            // the three terms of one k-chunk
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int TOTAL = kGemmStages * STAGE_BYTES + 128;
 };
 
-// canonical K-major no-swizzle offset of the 16-byte chunk (row r, k-chunk kc) inside a [rows][64] tile
-__device__ __forceinline__ uint32_t core_off(int r, int kc) {
-  return (uint32_t)((((r >> 3) * (kGemmBK / 8) + kc) << 7) + ((r & 7) << 4));
+__device__ __forceinline__ void mbar_expect_tx(uint32_t mbar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t mbar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(mbar)
+               : "memory");
 }
 
+// C[q][M][N] += A[M][Kd] . (B3[q][0] + B3[q][1] + B3[q][2])[N][Kd]^T, operands UMMA-tiled (see above).
+// Warp 0 lane 0: TMA producer.  Warp 1 lane 0: MMA issuer.  All four warps: epilogue.
 template <int N>
 __global__ void __launch_bounds__(kGemmThreads, 1)
-umma_gemm3_kernel(const __nv_bfloat16* __restrict__ A, long long lda, long long a_qstride, int M,
-                  const __nv_bfloat16* __restrict__ B, long long ldb, long long b_tstride,
-                  long long b_qstride, float* __restrict__ C, long long ldc, long long c_qstride,
-                  int kchunks, int chunks_per_split) {
+umma_gemm3_kernel(const __nv_bfloat16* __restrict__ A, long long a_qstride, int M,
+                  const __nv_bfloat16* __restrict__ B, long long b_qstride, float* __restrict__ C,
+                  long long ldc, long long c_qstride, int kchunks, int chunks_per_split) {
   using SM = GemmSmem<N>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  // 128-byte aligned base (descriptor addresses are in 16-byte units)
   const uint32_t sbase = (smem_u32(smem_raw) + 127u) & ~127u;
-  __shared__ __align__(8) unsigned long long mbar_store[kGemmStages + 1];
+  __shared__ __align__(8) unsigned long long mbar_store[2 * kGemmStages + 1];
   __shared__ uint32_t tmem_base_slot;
 
-  const int tid = threadIdx.x, warp = tid >> 5;
-  const int m0 = blockIdx.x * kGemmBM;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int mt = blockIdx.x;
+  const int m0 = mt * kGemmBM;
   const int q = blockIdx.z;
   const int c0 = blockIdx.y * chunks_per_split;
   const int c1 = min(kchunks, c0 + chunks_per_split);
@@ -142,16 +141,20 @@ umma_gemm3_kernel(const __nv_bfloat16* __restrict__ A, long long lda, long long 
   B += (long long)q * b_qstride;
   C += (long long)q * c_qstride;
 
-  uint32_t mbar[kGemmStages + 1];
+  uint32_t full[kGemmStages], empty[kGemmStages];
 #pragma unroll
-  for (int i = 0; i <= kGemmStages; ++i) mbar[i] = smem_u32(&mbar_store[i]);
+  for (int i = 0; i < kGemmStages; ++i) {
+    full[i] = smem_u32(&mbar_store[i]);
+    empty[i] = smem_u32(&mbar_store[kGemmStages + i]);
+  }
+  const uint32_t done = smem_u32(&mbar_store[2 * kGemmStages]);
   if (tid == 0) {
 #pragma unroll
-    for (int i = 0; i <= kGemmStages; ++i) mbar_init(mbar[i], 1);
+    for (int i = 0; i < kGemmStages; ++i) { mbar_init(full[i], 1); mbar_init(empty[i], 1); }
+    mbar_init(done, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 0) {
-    __syncwarp();
+  if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
                  "r"((uint32_t)N)
                  : "memory");
@@ -162,57 +165,29 @@ umma_gemm3_kernel(const __nv_bfloat16* __restrict__ A, long long lda, long long 
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_acc = tmem_base_slot;
 
-  // ---- loader: 16-byte chunks; thread -> (row group, k-chunk) so that 8 consecutive lanes write one
-  // contiguous 128-byte core matrix (rows r..r+7 of one k-chunk)
-  auto load_stage = [&](int stage, int chunk) {
-    const uint32_t sA = sbase + stage * SM::STAGE_BYTES;
-    const long long k0 = (long long)chunk * kGemmBK;
-    // A: 128 rows x 8 chunks = 1024 chunks / 128 threads
-#pragma unroll
-    for (int it = 0; it < (kGemmBM * 8) / kGemmThreads; ++it) {
-      const int idx = it * kGemmThreads + tid;
-      const int r = (idx & 7) | ((idx >> 6) << 3);      // 8 lanes = 8 rows of one core matrix
-      const int kc = (idx >> 3) & 7;
-      const int row = m0 + r;
-      const bool ok = row < M;
-      const __nv_bfloat16* src = A + (long long)(ok ? row : 0) * lda + k0 + kc * 8;
-      cp_async16(sA + core_off(r, kc), src, ok ? 16u : 0u);
+  if (warp == 0 && lane == 0) {
+    // ===== TMA producer: two contiguous bulk copies per stage =====
+    const __nv_bfloat16* At = A + ((long long)mt * kchunks + c0) * (SM::A_BYTES / 2);
+    const __nv_bfloat16* Bt = B + (long long)c0 * (SM::B_BYTES / 2);
+    for (int i = 0; i < nchunks; ++i) {
+      const int stage = i % kGemmStages;
+      if (i >= kGemmStages) mbar_wait(empty[stage], (uint32_t)((i / kGemmStages - 1) & 1));
+      const uint32_t sA = sbase + stage * SM::STAGE_BYTES;
+      mbar_expect_tx(full[stage], (uint32_t)SM::STAGE_BYTES);
+      tma_bulk_g2s(sA, At + (long long)i * (SM::A_BYTES / 2), SM::A_BYTES, full[stage]);
+      tma_bulk_g2s(sA + SM::A_BYTES, Bt + (long long)i * (SM::B_BYTES / 2), SM::B_BYTES, full[stage]);
     }
-    // B: three [N][64] tiles
-#pragma unroll
-    for (int t = 0; t < 3; ++t) {
-      const uint32_t sB = sA + SM::A_BYTES + t * SM::B_BYTES;
-      const __nv_bfloat16* Bt = B + (long long)t * b_tstride;
-#pragma unroll
-      for (int it = 0; it < (N * 8) / kGemmThreads; ++it) {
-        const int idx = it * kGemmThreads + tid;
-        const int r = (idx & 7) | ((idx >> 6) << 3);
-        const int kc = (idx >> 3) & 7;
-        cp_async16(sB + core_off(r, kc), Bt + (long long)r * ldb + k0 + kc * 8, 16u);
-      }
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-  };
-
-  constexpr uint32_t IDESC = umma_idesc_bf16(kGemmBM, N);
-  // prologue: stages 0 .. S-2
-#pragma unroll
-  for (int s = 0; s < kGemmStages - 1; ++s) {
-    if (s < nchunks) load_stage(s, c0 + s);
-    else asm volatile("cp.async.commit_group;" ::: "memory");
-  }
-
-  for (int i = 0; i < nchunks; ++i) {
-    const int stage = i % kGemmStages;
-    asm volatile("cp.async.wait_group %0;" ::"n"(kGemmStages - 2) : "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> tensor-core reads
-    __syncthreads();
-    if (tid == 0) {
+  } else if (warp == 1 && lane == 0) {
+    // ===== MMA issuer =====
+    constexpr uint32_t IDESC = umma_idesc_bf16(kGemmBM, N);
+    for (int i = 0; i < nchunks; ++i) {
+      const int stage = i % kGemmStages;
+      mbar_wait(full[stage], (uint32_t)((i / kGemmStages) & 1));
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t sA = sbase + stage * SM::STAGE_BYTES;
 #pragma unroll
       for (int t = 0; t < 3; ++t) {
-        const uint32_t sB = sA + SM::A_BYTES + t * SM::B_BYTES;
+        const uint32_t sB = sA + SM::A_BYTES + t * (N * kGemmBK * 2);
 #pragma unroll
         for (int j = 0; j < kGemmBK / 16; ++j) {
           const uint64_t ad = umma_desc(sA + j * 256, 128, (kGemmBK / 8) * 128);
@@ -220,23 +195,12 @@ umma_gemm3_kernel(const __nv_bfloat16* __restrict__ A, long long lda, long long 
           umma_bf16(tmem_acc, ad, bd, IDESC, (i | t | j) ? 1u : 0u);
         }
       }
-      umma_commit(mbar[stage]);          // arrives when the MMAs reading this stage are done
+      umma_commit(empty[stage]);         // frees the stage once these MMAs have read it
     }
-    // refill the stage used by iteration i-1 with chunk i+S-1 once its MMAs have retired
-    const int nxt = i + kGemmStages - 1;
-    if (nxt < nchunks) {
-      if (i >= 1) {
-        const int pstage = (i - 1) % kGemmStages;
-        mbar_wait(mbar[pstage], (uint32_t)(((i - 1) / kGemmStages) & 1));
-      }
-      load_stage(nxt % kGemmStages, c0 + nxt);
-    } else {
-      asm volatile("cp.async.commit_group;" ::: "memory");
-    }
+    umma_commit(done);                   // commits retire in order: covers every MMA above
   }
-  // all MMAs issued; wait for the last commit (covers every earlier MMA: commits retire in order)
-  if (tid == 0) umma_commit(mbar[kGemmStages]);
-  mbar_wait(mbar[kGemmStages], 0u);
+  __syncwarp();
+  mbar_wait(done, 0u);
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
   // ---- epilogue: TMEM lane = row of the tile; warp w reads lanes 32w..32w+31
@@ -254,17 +218,16 @@ umma_gemm3_kernel(const __nv_bfloat16* __restrict__ A, long long lda, long long 
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 0) {
+  if (warp == 2) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"((uint32_t)N) : "memory");
   }
 }
 
-// fp32 [R][C] (row stride lds) -> three bf16 arrays [C][ldd] (transposed), hi + mid + lo = x to 24 bits.
-// Destination columns [R, Rpad) are written as zeros (the GEMM's K padding).
+// fp32 src[R][C] (row stride lds) -> the UMMA-tiled B3 operand (3 bf16 terms, hi + mid + lo = x to
+// 24 bits) with k = the source ROW index (i.e. transposed); k in [R, Rpad) is written as zeros.
 __global__ void __launch_bounds__(256)
 split3_transpose_kernel(const float* __restrict__ src, long long lds, long long src_qstride, int R, int Rpad,
-                        int Ccols, __nv_bfloat16* __restrict__ dst, long long ldd, long long dst_tstride,
-                        long long dst_qstride) {
+                        int Ccols, __nv_bfloat16* __restrict__ dst, long long dst_qstride) {
   __shared__ float tile[32][33];
   const int q = blockIdx.z;
   src += (long long)q * src_qstride;
@@ -277,28 +240,28 @@ split3_transpose_kernel(const float* __restrict__ src, long long lds, long long 
     tile[ty + 8 * i][tx] = (r < R && c < Ccols) ? src[(long long)r * lds + c] : 0.f;
   }
   __syncthreads();
+  // each thread: one channel c, 4 consecutive k (8 bytes of a 16-byte core-matrix row)
+  const int c = cbase + (threadIdx.x >> 3), kq = (threadIdx.x & 7) * 4;
+  if (c < Ccols && r0 + kq < Rpad) {
+    __nv_bfloat16 o[3][4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int c = cbase + ty + 8 * i, r = r0 + tx;
-    if (c < Ccols && r < Rpad) {
-      const float x = tile[tx][ty + 8 * i];      // zero beyond R
+    for (int j = 0; j < 4; ++j) {
+      const float x = tile[kq + j][threadIdx.x >> 3];        // zero beyond R
       const __nv_bfloat16 h = __float2bfloat16_rn(x);
       const float r1 = x - __bfloat162float(h);
       const __nv_bfloat16 m = __float2bfloat16_rn(r1);
       const float r2 = r1 - __bfloat162float(m);
-      const __nv_bfloat16 l = __float2bfloat16_rn(r2);
-      const long long o = (long long)c * ldd + r;
-      dst[o] = h;
-      dst[dst_tstride + o] = m;
-      dst[2 * dst_tstride + o] = l;
+      o[0][j] = h; o[1][j] = m; o[2][j] = __float2bfloat16_rn(r2);
     }
+#pragma unroll
+    for (int t = 0; t < 3; ++t)
+      *reinterpret_cast<uint2*>(dst + tiledB_index(t, c, r0 + kq, Ccols)) = *reinterpret_cast<const uint2*>(o[t]);
   }
 }
 
 template <int N>
-static int launch_gemm3(const __nv_bfloat16* A, long long lda, long long aq, int M, const __nv_bfloat16* B,
-                        long long ldb, long long bt, long long bq, float* C, long long ldc, long long cq,
-                        int Kd, int NQ, int splits, cudaStream_t st) {
+static int launch_gemm3(const __nv_bfloat16* A, long long aq, int M, const __nv_bfloat16* B, long long bq, float* C,
+                        long long ldc, long long cq, int Kd, int NQ, int splits, cudaStream_t st) {
   using SM = GemmSmem<N>;
   static bool attr = false;
   if (!attr) {
@@ -308,15 +271,27 @@ static int launch_gemm3(const __nv_bfloat16* A, long long lda, long long aq, int
   }
   const int kchunks = Kd / kGemmBK;
   const int mtiles = (M + kGemmBM - 1) / kGemmBM;
-  if (splits <= 0) splits = (2 * 148 + mtiles * NQ - 1) / (mtiles * NQ);   // ~two CTAs' worth of work per SM
+  if (splits <= 0) splits = (148 + mtiles * NQ - 1) / (mtiles * NQ);   // one resident CTA per SM
   if (splits < 1) splits = 1;
   if (splits > kchunks) splits = kchunks;
   const int per = (kchunks + splits - 1) / splits;
   splits = (kchunks + per - 1) / per;
-  dim3 grid((M + kGemmBM - 1) / kGemmBM, splits, NQ);
-  umma_gemm3_kernel<N><<<grid, kGemmThreads, SM::TOTAL, st>>>(A, lda, aq, M, B, ldb, bt, bq, C, ldc, cq, kchunks, per);
+  dim3 grid(mtiles, splits, NQ);
+  umma_gemm3_kernel<N><<<grid, kGemmThreads, SM::TOTAL, st>>>(A, aq, M, B, bq, C, ldc, cq, kchunks, per);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? SPMF_OK : (int)e;
+}
+
+// row-major bf16 [M][ld] -> UMMA-tiled A (test / tooling helper; the product path writes the tiled
+// form directly in spmf_hot_split)
+__global__ void tile_a_kernel(const __nv_bfloat16* __restrict__ src, long long ld, int M, int Kd,
+                              __nv_bfloat16* __restrict__ dst) {
+  const long long n = (long long)((M + 127) / 128 * 128) * Kd;
+  const long long kchunks = Kd / kGemmBK;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / Kd, k = i - row * Kd;
+    dst[tiledA_index(row, k, kchunks)] = row < M ? src[row * ld + k] : __float2bfloat16_rn(0.f);
+  }
 }
 
 }  // namespace spmf
@@ -325,30 +300,39 @@ using namespace spmf;
 
 extern "C" {
 
-int spmf_umma_gemm3(const void* A, long long lda, long long a_qstride, int M, const void* B3, long long ldb,
-                    long long b_tstride, long long b_qstride, float* C, long long ldc, long long c_qstride,
-                    int N, int Kd, int NQ, int splits, void* stream) {
+long long spmf_umma_tiled_a_elems(long long M, long long Kd) { return (M + 127) / 128 * 128 * ((Kd + 63) / 64 * 64); }
+long long spmf_umma_tiled_b_elems(int N, long long Kd) { return 3LL * N * ((Kd + 63) / 64 * 64); }
+long long spmf_umma_tiled_a_index(long long row, long long k, long long Kd) { return tiledA_index(row, k, Kd / kGemmBK); }
+
+int spmf_umma_tile_a(const void* src, long long ld, int M, int Kd, void* dst, void* stream) {
+  if (!src || !dst || M <= 0 || Kd <= 0 || Kd % kGemmBK) return SPMF_ERR_BAD_ARG;
+  tile_a_kernel<<<148 * 4, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)src, ld, M, Kd, (__nv_bfloat16*)dst);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? SPMF_OK : (int)e;
+}
+
+int spmf_umma_gemm3(const void* A, long long a_qstride, int M, const void* B3, long long b_qstride, float* C,
+                    long long ldc, long long c_qstride, int N, int Kd, int NQ, int splits, void* stream) {
   if (!A || !B3 || !C || M <= 0 || Kd <= 0 || NQ <= 0) return SPMF_ERR_BAD_ARG;
-  if (Kd % kGemmBK || lda % 8 || ldb % 8 || ldc % 4) return SPMF_ERR_BAD_ARG;   // 16-byte chunks / float4 atomics
+  if (Kd % kGemmBK || ldc % 4) return SPMF_ERR_BAD_ARG;          // whole k-chunks; float4 atomics
   if (((uintptr_t)A | (uintptr_t)B3 | (uintptr_t)C) & 15) return SPMF_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   const __nv_bfloat16* a = (const __nv_bfloat16*)A;
   const __nv_bfloat16* b = (const __nv_bfloat16*)B3;
   switch (N) {
-    case 32: return launch_gemm3<32>(a, lda, a_qstride, M, b, ldb, b_tstride, b_qstride, C, ldc, c_qstride, Kd, NQ, splits, st);
-    case 64: return launch_gemm3<64>(a, lda, a_qstride, M, b, ldb, b_tstride, b_qstride, C, ldc, c_qstride, Kd, NQ, splits, st);
-    case 128: return launch_gemm3<128>(a, lda, a_qstride, M, b, ldb, b_tstride, b_qstride, C, ldc, c_qstride, Kd, NQ, splits, st);
+    case 32: return launch_gemm3<32>(a, a_qstride, M, b, b_qstride, C, ldc, c_qstride, Kd, NQ, splits, st);
+    case 64: return launch_gemm3<64>(a, a_qstride, M, b, b_qstride, C, ldc, c_qstride, Kd, NQ, splits, st);
+    case 128: return launch_gemm3<128>(a, a_qstride, M, b, b_qstride, C, ldc, c_qstride, Kd, NQ, splits, st);
     default: return SPMF_ERR_UNSUPPORTED;
   }
 }
 
 int spmf_split3_transpose(const float* src, long long lds, long long src_qstride, int R, int Rpad, int Ccols,
-                          void* dst3, long long ldd, long long dst_tstride, long long dst_qstride, int NQ,
-                          void* stream) {
-  if (!src || !dst3 || R <= 0 || Rpad < R || Rpad > ldd || Ccols <= 0 || NQ <= 0) return SPMF_ERR_BAD_ARG;
-  dim3 grid((Rpad + 31) / 32, (Ccols + 31) / 32, NQ);
+                          void* dst3, long long dst_qstride, int NQ, void* stream) {
+  if (!src || !dst3 || R <= 0 || Rpad < R || Rpad % kGemmBK || Ccols <= 0 || Ccols % 32 || NQ <= 0) return SPMF_ERR_BAD_ARG;
+  dim3 grid((Rpad + 31) / 32, Ccols / 32, NQ);
   split3_transpose_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, lds, src_qstride, R, Rpad, Ccols,
-                                                                  (__nv_bfloat16*)dst3, ldd, dst_tstride, dst_qstride);
+                                                                  (__nv_bfloat16*)dst3, dst_qstride);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? SPMF_OK : (int)e;
 }

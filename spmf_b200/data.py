@@ -38,13 +38,14 @@ class HotSplit:
     cols: torch.Tensor            # int32 [nnz]   column RANKS
     vals: torch.Tensor            # fp32 [nnz]    negative = covered by the tensor-core products
     rowmid: torch.Tensor          # int32 [nrows] first uncovered entry of each row (row-local)
-    xhot: torch.Tensor            # bf16 [nrows][ldx]
-    xthot: torch.Tensor           # bf16 [ceil64(H)][ldxt]
-    ldx: int
-    ldxt: int
-    colptr: torch.Tensor          # int32 [D+1]
+    xhot: torch.Tensor            # bf16, UMMA-tiled X[nrows][ceil64(H)]   (see include/spmf_b200.h)
+    xthot: torch.Tensor           # bf16, UMMA-tiled X^T[H][ceil64(nrows)]
+    colptr: torch.Tensor          # CSC of the entries NOT covered by the GEMMs: int32 [D+1]
     crows: torch.Tensor
     cvals: torch.Tensor
+    hcolptr: torch.Tensor         # CSC of the covered entries
+    hcrows: torch.Tensor
+    hcvals: torch.Tensor
 
 
 @dataclass
@@ -70,28 +71,35 @@ class DeviceBatch:
             return self.hot
         dev = self.vals.device
         n, nnz = self.nrows, self.nnz
-        ldx, ldxt = _ceil64(H), _ceil64(n)
         m = max(nnz, 1) + 8
+        na = _abi._lib.spmf_umma_tiled_a_elems(n, _ceil64(H))
+        nt = _abi._lib.spmf_umma_tiled_a_elems(H, _ceil64(n))
         if bufs is None:
             bufs = dict(rowptr=torch.empty(n + 1, dtype=torch.int64, device=dev),
                         cols=torch.empty(m, dtype=torch.int32, device=dev),
                         vals=torch.empty(m, dtype=torch.float32, device=dev),
                         rowmid=torch.empty(n, dtype=torch.int32, device=dev),
-                        xhot=torch.empty(n * ldx, dtype=torch.bfloat16, device=dev),
-                        xthot=torch.empty(ldx * ldxt, dtype=torch.bfloat16, device=dev),
+                        xhot=torch.empty(na, dtype=torch.bfloat16, device=dev),
+                        xthot=torch.empty(nt, dtype=torch.bfloat16, device=dev),
                         colptr=torch.empty(self.D + 1, dtype=torch.int32, device=dev),
                         crows=torch.empty(m, dtype=torch.int32, device=dev),
                         cvals=torch.empty(m, dtype=torch.float32, device=dev),
+                        hcolptr=torch.empty(self.D + 1, dtype=torch.int32, device=dev),
+                        hcrows=torch.empty(m, dtype=torch.int32, device=dev),
+                        hcvals=torch.empty(m, dtype=torch.float32, device=dev),
                         scratch=torch.empty(_abi._lib.spmf_csc_scratch_ints(self.D), dtype=torch.int32, device=dev))
         st = _stream()
         _abi.call("spmf_hot_split", _ptr(self.rowptr), _ptr(self.cols), _ptr(self.vals), n, nnz, _ptr(rank), H,
                   _ptr(bufs["rowptr"]), _ptr(bufs["cols"]), _ptr(bufs["vals"]), _ptr(bufs["rowmid"]),
-                  _ptr(bufs["xhot"]), ldx, _ptr(bufs["xthot"]), ldxt, st)
-        _abi.call("spmf_csr_to_csc", _ptr(bufs["rowptr"]), _ptr(bufs["cols"]), _ptr(bufs["vals"]), n, self.D,
-                  _ptr(bufs["colptr"]), _ptr(bufs["crows"]), _ptr(bufs["cvals"]), _ptr(bufs["scratch"]), st)
+                  _ptr(bufs["xhot"]), _ptr(bufs["xthot"]), st)
+        for part, pre in ((0, "h"), (1, "")):       # covered entries / the rest
+            _abi.call("spmf_csr_to_csc_part", _ptr(bufs["rowptr"]), _ptr(bufs["rowmid"]), part, _ptr(bufs["cols"]),
+                      _ptr(bufs["vals"]), n, self.D, _ptr(bufs[pre + "colptr"]), _ptr(bufs[pre + "crows"]),
+                      _ptr(bufs[pre + "cvals"]), _ptr(bufs["scratch"]), st)
         self.hot = HotSplit(H=H, rowptr=bufs["rowptr"], cols=bufs["cols"], vals=bufs["vals"],
-                            rowmid=bufs["rowmid"], xhot=bufs["xhot"], xthot=bufs["xthot"], ldx=ldx, ldxt=ldxt,
-                            colptr=bufs["colptr"], crows=bufs["crows"], cvals=bufs["cvals"])
+                            rowmid=bufs["rowmid"], xhot=bufs["xhot"], xthot=bufs["xthot"],
+                            colptr=bufs["colptr"], crows=bufs["crows"], cvals=bufs["cvals"],
+                            hcolptr=bufs["hcolptr"], hcrows=bufs["hcrows"], hcvals=bufs["hcvals"])
         return self.hot
 
     def ensure_csc(self):
@@ -363,14 +371,18 @@ class BatchUploader:
         self.hot_bufs = None
         if self.hot is not None:
             H = int(self.hot[1])
-            ldx, ldxt = _ceil64(H), _ceil64(max(rows, 1))
+            na = _abi._lib.spmf_umma_tiled_a_elems(max(rows, 1), _ceil64(H))
+            nt = _abi._lib.spmf_umma_tiled_a_elems(H, _ceil64(max(rows, 1)))
             self.hot_bufs = dict(rowptr=torch.empty(rows + 1, dtype=torch.int64, device=dev),
                                  cols=torch.empty(n, dtype=torch.int32, device=dev),
                                  vals=torch.empty(n, dtype=torch.float32, device=dev),
                                  rowmid=torch.empty(max(rows, 1), dtype=torch.int32, device=dev),
-                                 xhot=torch.empty(max(rows, 1) * ldx, dtype=torch.bfloat16, device=dev),
-                                 xthot=torch.empty(ldx * ldxt, dtype=torch.bfloat16, device=dev),
-                                 colptr=self.colptr, crows=self.crows, cvals=self.cvals, scratch=self.cursor)
+                                 xhot=torch.empty(na, dtype=torch.bfloat16, device=dev),
+                                 xthot=torch.empty(nt, dtype=torch.bfloat16, device=dev),
+                                 colptr=self.colptr, crows=self.crows, cvals=self.cvals,
+                                 hcolptr=torch.empty(self.D + 1, dtype=torch.int32, device=dev),
+                                 hcrows=torch.empty(n, dtype=torch.int32, device=dev),
+                                 hcvals=torch.empty(n, dtype=torch.float32, device=dev), scratch=self.cursor)
 
     def upload(self, hb: HostCsrBatch) -> DeviceBatch:
         n, nnz = hb.nrows, hb.nnz

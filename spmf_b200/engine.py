@@ -47,14 +47,15 @@ class StepWorkspace:
         self.ensure_rows(max_rows)
 
     def ensure_hybrid(self, H, nrows):
-        """bf16 split operands of the tcgen05 GEMMs: ApT3 / dzrT3 as [NQ][3][REC][ldt]."""
-        ldt = max((int(H) + 63) // 64 * 64, (int(nrows) + 63) // 64 * 64)
-        if getattr(self, "ldt", 0) >= ldt:
+        """bf16 three-term operands of the tcgen05 GEMMs (UMMA-tiled B3): ApT3 over the hot columns,
+        dzrT3 over the batch rows; one block of `t3_qstride` elements per draw group."""
+        kd = max((int(H) + 63) // 64 * 64, (int(nrows) + 63) // 64 * 64)
+        if getattr(self, "t3_kd", 0) >= kd:
             return False
-        n = self.NQ * 3 * self.KP * self.SV * ldt
-        self.ldt = ldt
-        self.ApT3 = torch.zeros(n, dtype=torch.bfloat16, device=self.device)
-        self.dzrT3 = torch.zeros(n, dtype=torch.bfloat16, device=self.device)
+        self.t3_kd = kd
+        self.t3_qstride = int(_abi._lib.spmf_umma_tiled_b_elems(self.KP * self.SV, kd))
+        self.ApT3 = torch.zeros(self.NQ * self.t3_qstride, dtype=torch.bfloat16, device=self.device)
+        self.dzrT3 = torch.zeros(self.NQ * self.t3_qstride, dtype=torch.bfloat16, device=self.device)
         return True
 
     def ensure_rows(self, nrows):
@@ -208,6 +209,14 @@ class AdviEngine:
                     e.record()                       # materialise the cudaEvent_t handles
                 a.hot_stream, a.side_stream = self._hot.cuda_stream, self._side.cuda_stream
                 a.ev_fork, a.ev_join, a.ev_done = (e.cuda_event for e in self._sync_events)
+                # hybrid step: the GA' GEMM and the cold column pass run next to the hot column pass
+                self._aux = [torch.cuda.Stream(device=self.device, priority=-1) for _ in range(2)]
+                self._aux_events = [torch.cuda.Event() for _ in range(3)]
+                for e in self._aux_events:
+                    e.record()
+                if os.environ.get("SPMF_AUX_STREAMS", "1") != "0":
+                    a.aux_stream1, a.aux_stream2 = (st.cuda_stream for st in self._aux)
+                    a.ev_aux_fork, a.ev_aux_join1, a.ev_aux_join2 = (e.cuda_event for e in self._aux_events)
             self._args = a
         return self._args
 
@@ -236,9 +245,10 @@ class AdviEngine:
         if hybrid:
             a.rowptr, a.cols, a.vals = _ptr(h.rowptr), _ptr(h.cols), _ptr(h.vals)
             a.colptr, a.crows, a.cvals = _ptr(h.colptr), _ptr(h.crows), _ptr(h.cvals)
+            a.hot_colptr, a.hot_crows, a.hot_cvals = _ptr(h.hcolptr), _ptr(h.hcrows), _ptr(h.hcvals)
             a.rank, a.hot_cols, a.gemm_splits = _ptr(self.rank), int(self.hot_cols), 0
             a.rowmid, a.xhot, a.xthot = _ptr(h.rowmid), _ptr(h.xhot), _ptr(h.xthot)
-            a.ldx, a.ldxt, a.ldt = h.ldx, h.ldxt, w.ldt
+            a.t3_qstride = w.t3_qstride
             a.ApT3, a.dzrT3 = _ptr(w.ApT3), _ptr(w.dzrT3)
         else:
             a.rowptr, a.cols, a.vals = _ptr(batch.rowptr), _ptr(batch.cols), _ptr(batch.vals)
@@ -251,20 +261,25 @@ class AdviEngine:
         a.caller_stream = _stream()
         ev = self.kernel_events
         if ev is not None:
-            tev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            tev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
             for e in tev:
                 e.record()
-            a.ev_rows0, a.ev_rows1, a.ev_cols0, a.ev_cols1 = (e.cuda_event for e in tev)
+            a.ev_rows0, a.ev_rows1, a.ev_cols0, a.ev_cols1 = (e.cuda_event for e in tev[:4])
             ev.setdefault("csr_rows", []).append((tev[0], tev[1], batch.nnz, batch.nrows))
             ev.setdefault("csc_cols", []).append((tev[2], tev[3], batch.nnz, batch.nrows))
+            if hybrid:
+                a.ev_gemm0, a.ev_gemm1 = tev[4].cuda_event, tev[5].cuda_event
+                ev.setdefault("umma_gemm_gradA", []).append((tev[4], tev[5], batch.nnz, batch.nrows))
+            else:
+                a.ev_gemm0 = a.ev_gemm1 = None
         else:
-            a.ev_rows0 = a.ev_rows1 = a.ev_cols0 = a.ev_cols1 = None
+            a.ev_rows0 = a.ev_rows1 = a.ev_cols0 = a.ev_cols1 = a.ev_gemm0 = a.ev_gemm1 = None
         _abi.call("spmf_advi_step", a)
         if fresh_noise:
             self.rng_step += 1
         if do_adam:
             self.opt_step += 1
-        self.launches += 17 + (1 if do_adam else 0) + (4 if hybrid else 0)   # kernels issued by spmf_advi_step
+        self.launches += 17 + (1 if do_adam else 0) + (5 if hybrid else 0)   # kernels issued by spmf_advi_step
         return w.parts.view(self.S, _abi.NUM_PARTS)
 
     def loss_and_grad(self, batch: DeviceBatch, fresh_noise=True, variant=0):

@@ -38,20 +38,25 @@ def test_umma_gemm3_matches_float64(M, N, Kd, NQ, splits):
     A = torch.randint(0, 40, (M, Kd), generator=g).to(torch.float32)
     A[torch.rand(M, Kd, generator=g) < 0.6] = 0
     Bsrc = torch.randn(NQ, Kd, N, generator=g) * torch.exp(2 * torch.randn(NQ, Kd, N, generator=g))
-    Ad = A.to(dev).to(torch.bfloat16).contiguous()
+    Arow = A.to(dev).to(torch.bfloat16).contiguous()
+    Ad = torch.empty(_abi._lib.spmf_umma_tiled_a_elems(M, Kd), dtype=torch.bfloat16, device=dev)
+    _abi.call("spmf_umma_tile_a", _ptr(Arow), Kd, M, Kd, _ptr(Ad), _stream())
+    # the tiling helper agrees with the index function the producers use
+    probe = [(0, 0), (M - 1, Kd - 1), (M // 2, 17), (min(M - 1, 129), 64 % Kd)]
+    for r, k in probe:
+        assert float(Ad[_abi._lib.spmf_umma_tiled_a_index(r, k, Kd)]) == float(Arow[r, k])
     Bd = Bsrc.to(dev).contiguous()
-    ldt = Kd
-    B3 = torch.zeros(NQ, 3, N, ldt, dtype=torch.bfloat16, device=dev)
-    _abi.call("spmf_split3_transpose", _ptr(Bd), N, Kd * N, Kd, Kd, N, _ptr(B3), ldt, N * ldt, 3 * N * ldt, NQ,
-              _stream())
+    qs = _abi._lib.spmf_umma_tiled_b_elems(N, Kd)
+    B3 = torch.zeros(NQ * qs, dtype=torch.bfloat16, device=dev)
+    _abi.call("spmf_split3_transpose", _ptr(Bd), N, Kd * N, Kd, Kd, N, _ptr(B3), qs, NQ, _stream())
     torch.cuda.synchronize()
-    # the three terms reproduce the fp32 operand to 24 bits
-    rec = B3.to(torch.float64).sum(1).transpose(1, 2).cpu()
+    # the three terms reproduce the fp32 operand to 24 bits: tiles [k/64][term] of N x 64, core matrices 8 x 8
+    t = B3.view(NQ, Kd // 64, 3, N // 8, 8, 8, 8).to(torch.float64).sum(2)      # q, kc, n8, k8, n, k
+    rec = t.permute(0, 1, 3, 5, 2, 4).reshape(NQ, Kd, N).cpu()                  # q, (kc,k8,k), (n8,n)
     assert rel_err(rec.numpy(), Bsrc.double().numpy()) < 2e-7
     C0 = torch.randn(NQ, M, N, generator=g)
     C = C0.to(dev).contiguous()
-    _abi.call("spmf_umma_gemm3", _ptr(Ad), Kd, 0, M, _ptr(B3), ldt, N * ldt, 3 * N * ldt, _ptr(C), N, M * N,
-              N, Kd, NQ, splits, _stream())
+    _abi.call("spmf_umma_gemm3", _ptr(Ad), 0, M, _ptr(B3), qs, _ptr(C), N, M * N, N, Kd, NQ, splits, _stream())
     torch.cuda.synchronize()
     ref = C0.double() + torch.einsum("mk,qkn->qmn", A.double(), Bsrc.double())
     err = (C.cpu().double() - ref).abs().max() / ref.abs().max()
@@ -76,11 +81,19 @@ def test_hot_split_partitions_and_fills_dense_block():
     torch.cuda.synchronize()
     rp = h.rowptr.cpu().numpy()
     cols, vals, mid = h.cols.cpu().numpy(), h.vals.cpu().numpy(), h.rowmid.cpu().numpy()
-    xh = h.xhot.view(B, h.ldx).float().cpu().numpy()
-    xt = h.xthot.view(h.ldx, h.ldxt).float().cpu().numpy()
+    Hp, Bp = (H + 63) // 64 * 64, (B + 63) // 64 * 64
+
+    def untile(t, rows, kd):     # UMMA-tiled [rows/128][kd/64] tiles of (16 x 8) core matrices of 8 x 8
+        rp_ = (rows + 127) // 128 * 128
+        v = t[:rp_ * kd].view(rp_ // 128, kd // 64, 16, 8, 8, 8).float()      # mt, kc, r8, k8, r, k
+        return v.permute(0, 2, 4, 1, 3, 5).reshape(rp_, kd).cpu().numpy()
+    xh = untile(h.xhot, B, Hp)[:B]
+    xt = untile(h.xthot, H, Bp)
+    assert (xt[H:] == 0).all()
+    xt = xt[:Hp] if xt.shape[0] >= Hp else np.vstack([xt, np.zeros((Hp - xt.shape[0], Bp), np.float32)])
     assert rp[0] == 0 and rp[-1] == int((x != 0).sum())
     dense = np.zeros((B, D), np.float32)
-    exp_hot = np.zeros((B, h.ldx), np.float32)
+    exp_hot = np.zeros((B, Hp), np.float32)
     for r in range(B):
         seg = slice(rp[r], rp[r + 1])
         c, v = cols[seg], vals[seg]
@@ -98,14 +111,16 @@ def test_hot_split_partitions_and_fills_dense_block():
     assert not cov[:, H:].any() and np.array_equal(exp_hot[:, :H] != 0, cov[:, :H])
     assert np.array_equal(xh, exp_hot) and np.array_equal(xt[:, :B], exp_hot.T[:, :B])
     assert (xt[:, B:] == 0).all() and (xh[:, H:] == 0).all()
-    # CSC copy carries the same flags
-    cp = h.colptr.cpu().numpy()
-    assert cp[-1] == rp[-1]
-    cr, cv = h.crows.cpu().numpy(), h.cvals.cpu().numpy()
-    back = np.zeros((B, D), np.float32)
-    for d in range(D):
-        back[cr[cp[d]:cp[d + 1]], d] = cv[cp[d]:cp[d + 1]]
-    assert np.array_equal(np.abs(back), xr) and np.array_equal(back < 0, cov)
+    # the two CSC copies: covered entries / the rest, values as |x|
+    for cp_t, cr_t, cv_t, want in ((h.hcolptr, h.hcrows, h.hcvals, np.where(cov, xr, 0)),
+                                   (h.colptr, h.crows, h.cvals, np.where(cov, 0, xr))):
+        cp = cp_t.cpu().numpy()
+        cr, cv = cr_t.cpu().numpy(), cv_t.cpu().numpy()
+        assert cp[0] == 0 and cp[-1] == int((want != 0).sum())
+        back = np.zeros((B, D), np.float32)
+        for d in range(D):
+            back[cr[cp[d]:cp[d + 1]], d] = cv[cp[d]:cp[d + 1]]
+        assert np.array_equal(back, want)
 
 
 def _step(model, eng, params, noise, batch):
@@ -184,7 +199,7 @@ def test_hybrid_fit_reduces_loss_and_streams():
 
     def run(stream):
         model = spmf_b200.PoissonFactorization(latent_dim=K, feature_dim=D, u_tau_scale=1.0 / np.sqrt(x.size),
-                                               device=dev, seed=3)
+                                               device=dev, seed=3, hot_density=0.03)
         model.compute_scales(sh)
         assert model.hot_cols >= 64
         if stream:
