@@ -173,6 +173,12 @@ int spmf_split3_transpose(const float* src, long long lds, long long src_qstride
  * `splits` = split-K factor (<= 0: automatic). */
 int spmf_umma_gemm3(const void* A, long long a_qstride, int M, const void* B3, long long b_qstride, float* C,
                     long long ldc, long long c_qstride, int N, int Kd, int NQ, int splits, void* stream);
+/* bring-up probe: one CTA, raw shared-memory operand images, explicit descriptor fields (major-ness,
+ * leading / stride byte offsets, byte step per k=16 MMA); dumps the 128-lane x N-column fp32
+ * accumulator block to out[128][N].  Pins the UMMA conventions the kernels rely on (tests only). */
+int spmf_umma_probe(const void* a_img, int a_bytes, const void* b_img, int b_bytes, int M, int N, int a_mn,
+                    int b_mn, int lbo_a, int sbo_a, int step_a, int lbo_b, int sbo_b, int step_b, int nk,
+                    float* out, void* stream);
 /* row / column passes of the hybrid step (same outputs as spmf_csr_rows / spmf_csc_cols): `z` must
  * hold the GEMM's un-scaled hot block of x.A' on entry; GA' of covered entries is left to the GEMM. */
 int spmf_csr_rows_hybrid(const long long* rowptr, const int* cols, const float* vals, const int* rowmid,
@@ -186,6 +192,23 @@ int spmf_csc_cols_hybrid(const int* hot_colptr, const int* hot_rows, const float
                          const int* cold_colptr, const int* cold_rows, const float* cold_vals, int nnz_bound,
                          int nrows, int D, int K, int S, const float* z, const float* dzr, const float* EV,
                          const float* PH, float* GAp, float* GEVnz, float* Gphinz, void* stream);
+/* ---- tile-hybrid step: the per-nonzero terms of the hot block on the tensor cores as well ----
+ * spmf_hot_tile fuses, per 128-row x 64-column tile and draw: rate = z.EV + phi (tcgen05.mma into
+ * tensor memory), x log rate and w = x/rate on the CUDA cores, then dz += w.EV and GEV = w^T.z,
+ * Gphi = w^T.1 as two more MMAs -- the (S,B,D) rate tensor of poisson.py:174-184 never exists.
+ * Order: spmf_hot_ev_tiles (per step) ; spmf_csr_rows_cold (z final, raw cold partials) ;
+ * spmf_hot_tile (adds the hot block into dzacc / rowacc, atomics into GEVnz / Gphinz, which must be
+ * zeroed before) ; spmf_rows_finish (dzr = r (dz - vsum - z), per-row scalars). */
+long long spmf_hot_tile_scratch_bytes(int H, int K, int S);   /* size of the EVt workspace */
+int spmf_hot_ev_tiles(const float* EV, const float* PH, int D, int H, int K, int S, void* EVt, void* stream);
+int spmf_csr_rows_cold(const long long* rowptr, const int* cols, const float* vals, const int* rowmid,
+                       const float* rowsum, float inv_xi, int scale_rows, int nrows, int D, int K, int S,
+                       const float* Ap, const float* EV, const float* PH, float* z, float* dzacc, float* rowacc,
+                       void* stream);
+int spmf_hot_tile(const void* xhot, const void* EVt, const float* z, int nrows, int D, int H, int K, int S,
+                  float* dzacc, float* rowacc, float* GEVnz, float* Gphinz, void* stream);
+int spmf_rows_finish(const float* rowsum, const float* lgam, float inv_xi, int scale_rows, int nrows, int K, int S,
+                     const double* vsum, const float* z, float* dzr, float* rowacc, void* stream);
 /* the pieces of spmf_csc_cols_hybrid, for callers that overlap them on several streams: zero the three
  * column-gradient tables; accumulate (atomics) one CSC copy into them -- covered != 0: GEV and Gphi
  * only (hot copy), covered == 0: full column pass (cold copy). */
@@ -254,6 +277,10 @@ typedef struct spmf_step_args {
    * concurrently with the hot column pass; NULL = everything in order on the hot stream */
   void *aux_stream1, *aux_stream2;
   void *ev_aux_fork, *ev_aux_join1, *ev_aux_join2;
+  /* hot_mode 2: the per-nonzero terms of the hot block run in the fused tcgen05 tile kernel
+   * (spmf_hot_tile) instead of the gather kernels; EVt = workspace of spmf_hot_tile_scratch_bytes */
+  int hot_mode;
+  void* EVt;
 } spmf_step_args;
 int spmf_advi_step(const spmf_step_args* args);
 /* widen a compact batch (either 16-bit source may be NULL), build its row constants and CSC copy */

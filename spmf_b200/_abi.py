@@ -76,11 +76,17 @@ _SIGS = {
     "spmf_umma_tiled_b_elems": (i64, [i32, i64]),
     "spmf_umma_tiled_a_index": (i64, [i64, i64, i64]),
     "spmf_umma_tile_a": (i32, [p, i64, i32, i32, p, p]),
+    "spmf_umma_probe": (i32, [p, i32, p, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, p, p]),
     "spmf_hot_split": (i32, [p, p, p, i32, i64, p, i32, p, p, p, p, p, p, p]),
     "spmf_split3_transpose": (i32, [p, i64, i64, i32, i32, i32, p, i64, i32, p]),
     "spmf_umma_gemm3": (i32, [p, i64, i32, p, i64, p, i64, i64, i32, i32, i32, i32, p]),
     "spmf_csr_rows_hybrid": (i32, [p, p, p, p, p, p, f32, i32, i32, i32, i32, i32, p, p, p, p, p, p, p, p]),
     "spmf_csc_cols_hybrid": (i32, [p, p, p, p, p, p, i32, i32, i32, i32, i32, p, p, p, p, p, p, p, p]),
+    "spmf_hot_tile_scratch_bytes": (i64, [i32, i32, i32]),
+    "spmf_hot_ev_tiles": (i32, [p, p, i32, i32, i32, i32, p, p]),
+    "spmf_csr_rows_cold": (i32, [p, p, p, p, p, f32, i32, i32, i32, i32, i32, p, p, p, p, p, p, p]),
+    "spmf_hot_tile": (i32, [p, p, p, i32, i32, i32, i32, i32, p, p, p, p, p]),
+    "spmf_rows_finish": (i32, [p, p, f32, i32, i32, i32, i32, p, p, p, p, p]),
     "spmf_zero_col_grads": (i32, [p, p, p, i32, i32, i32, p]),
     "spmf_csc_cols_accum": (i32, [p, p, p, i32, i32, i32, i32, i32, p, p, p, p, p, p, p, i32, p]),
     "spmf_csr_to_csc_part": (i32, [p, p, i32, p, p, i32, i32, p, p, p, p, p]),
@@ -109,6 +115,7 @@ class StepArgs(C.Structure):
         + [(n, p) for n in ("rowmid", "hot_colptr", "hot_crows", "hot_cvals", "xhot", "xthot", "ApT3", "dzrT3",
                             "ev_gemm0", "ev_gemm1", "aux_stream1", "aux_stream2", "ev_aux_fork", "ev_aux_join1",
                             "ev_aux_join2")]
+        + [("hot_mode", i32), ("EVt", p)]
     )
 
 

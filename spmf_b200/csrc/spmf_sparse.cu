@@ -145,7 +145,10 @@ __device__ __forceinline__ void ld_idx(const int* __restrict__ pc, const float* 
 // the encode product already sits in z (tcgen05 GEMM, spmf_umma.cu); sweep 1 adds the entries the
 // GEMM does not cover (stored after rowmid[row], positive values) and sweep 2 runs over every entry
 // (covered ones carry a negative sign as their flag).
-constexpr int kRowsTrain = 0, kRowsEncode = 1, kRowsHybrid = 2;
+// MODE 3: cold part of the tile-hybrid step -- as MODE 2, but sweep 2 also skips the covered entries
+// (the tcgen05 tile kernel, spmf_hot_tile.cu, owns them) and dzr / rowacc receive RAW partial sums
+// (un-scaled sum w.EV, sum x log lambda, #non-finite) that spmf_rows_finish completes.
+constexpr int kRowsTrain = 0, kRowsEncode = 1, kRowsHybrid = 2, kRowsCold = 3;
 
 template <int KP, int SV, int MODE>
 __global__ void __launch_bounds__(128)
@@ -157,7 +160,9 @@ csr_rows_kernel(const long long* __restrict__ rowptr, const int* __restrict__ co
                 float* __restrict__ z, float* __restrict__ dzr, float* __restrict__ rowacc,
                 const int* __restrict__ rowmid) {
   constexpr bool ENCODE_ONLY = (MODE == kRowsEncode);
-  constexpr bool HYBRID = (MODE == kRowsHybrid);
+  constexpr bool COLD = (MODE == kRowsCold);
+  constexpr bool ZIN = (MODE == kRowsHybrid) || COLD;     // z holds the GEMM's hot block on entry
+  constexpr bool HYBRID = (MODE == kRowsHybrid);          // sweep 2 sees signed (flagged) values
   using M = Map<KP, SV>;
   constexpr int VW = M::VW, LPN = M::LPN, RG = M::RG, VPL = M::VPL, REC = M::REC, NSLOT = M::NSLOT;
   constexpr int U = VPL >= 4 ? 2 : 4;
@@ -197,7 +202,7 @@ csr_rows_kernel(const long long* __restrict__ rowptr, const int* __restrict__ co
   };
   const long long j0 = rowptr[row];
   const int n = (int)(rowptr[row + 1] - j0);
-  const int mid = HYBRID ? rowmid[row] : 0;          // sweep 1 starts here in hybrid mode
+  const int mid = ZIN ? rowmid[row] : 0;             // sweep 1 starts here in the hybrid modes
   const Range R1 = make_range(j0 + mid, n - mid);
   const Range R2 = HYBRID ? make_range(j0, n) : R1;
   const float r = scale_rows ? rowsum[row] * inv_xi : 1.f;   // poisson.py:644-649
@@ -271,7 +276,7 @@ csr_rows_kernel(const long long* __restrict__ rowptr, const int* __restrict__ co
   float* zq = z + ((size_t)q * nrows + row) * REC;
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
-    if constexpr (HYBRID) {                 // hot-column block of x.A' from the tensor-core GEMM
+    if constexpr (ZIN) {                    // hot-column block of x.A' from the tensor-core GEMM
       float a[VW];
       ldv_s<VW>(a, zq + off[i]);
 #pragma unroll
@@ -280,7 +285,7 @@ csr_rows_kernel(const long long* __restrict__ rowptr, const int* __restrict__ co
 #pragma unroll
     for (int w = 0; w < VW; ++w) zz[i][w] *= r;
   }
-  if constexpr (HYBRID) __syncthreads();    // every slot has read the GEMM block before slot 0 overwrites it
+  if constexpr (ZIN) __syncthreads();       // every slot has read the GEMM block before slot 0 overwrites it
 #pragma unroll
   for (int i = 0; i < VPL; ++i)
     if (slot == 0) stv<VW>(zq + off[i], zz[i]);
@@ -399,10 +404,22 @@ csr_rows_kernel(const long long* __restrict__ rowptr, const int* __restrict__ co
       for (int w = 0; w < VW; ++w) dz[i][w] += a[w];
     }
   }
+  float* dq = dzr + ((size_t)q * nrows + row) * REC;
+  if constexpr (COLD) {       // raw partial sums; spmf_hot_tile adds its share, spmf_rows_finish completes
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) stv<VW>(dq + off[i], dz[i]);
+    if (kg == 0) {
+      float* ra = rowacc + ((size_t)q * nrows + row) * 4 * SV;
+      ra[0 * SV + s] = xlog;
+      ra[1 * SV + s] = 0.f;
+      ra[2 * SV + s] = 0.f;
+      ra[3 * SV + s] = fbad;
+    }
+    return;
+  }
   // ---- closed-form parts and per-row scalars (slot 0 only from here)
   const double* vsq = vsum + (size_t)q * REC;
   float zv = 0.f, z2 = 0.f;
-  float* dq = dzr + ((size_t)q * nrows + row) * REC;
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
     float o[VW];
@@ -1063,6 +1080,22 @@ int spmf_csr_rows_hybrid(const long long* rowptr, const int* cols, const float* 
 #define CALL_ROWS_H(KPC, SVC) rc = launch_rows<KPC, SVC, kRowsHybrid>(rowptr, cols, vals, rowsum, lgam, inv_xi, scale_rows, nrows, D, NQ, Ap, EV, PH, vsum, z, dzr, rowacc, rowmid, st)
   SPMF_DISPATCH_HYBRID(KP, SV, CALL_ROWS_H);
 #undef CALL_ROWS_H
+  return rc;
+}
+
+int spmf_csr_rows_cold(const long long* rowptr, const int* cols, const float* vals, const int* rowmid,
+                       const float* rowsum, float inv_xi, int scale_rows, int nrows, int D, int K, int S,
+                       const float* Ap, const float* EV, const float* PH, float* z, float* dzacc, float* rowacc,
+                       void* stream) {
+  if (!rowptr || !cols || !vals || !rowmid || !rowsum || !Ap || !EV || !PH || !z || !dzacc || !rowacc)
+    return SPMF_ERR_BAD_ARG;
+  if (nrows <= 0 || D <= 0 || K <= 0 || K > SPMF_MAX_K || S <= 0) return SPMF_ERR_BAD_ARG;
+  const int KP = spmf_kpad(K), SV = spmf_draw_vec(S), NQ = S / SV;
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = SPMF_OK;
+#define CALL_ROWS_C(KPC, SVC) rc = launch_rows<KPC, SVC, kRowsCold>(rowptr, cols, vals, rowsum, nullptr, inv_xi, scale_rows, nrows, D, NQ, Ap, EV, PH, nullptr, z, dzacc, rowacc, rowmid, st)
+  SPMF_DISPATCH_HYBRID(KP, SV, CALL_ROWS_C);
+#undef CALL_ROWS_C
   return rc;
 }
 

@@ -64,9 +64,22 @@ int spmf_advi_step(const spmf_step_args* a) {
     CUDA_TRY(cudaMemsetAsync(a->z, 0, (size_t)NQ * a->nrows * REC * sizeof(float), hot));
     STEP_TRY(spmf_umma_gemm3(a->xhot, 0, a->nrows, a->ApT3, a->t3_qstride, a->z, REC, (long long)a->nrows * REC,
                              REC, Hp, NQ, a->gemm_splits, hot));
-    STEP_TRY(spmf_csr_rows_hybrid(a->rowptr, a->cols, a->vals, a->rowmid, a->rowsum, a->lgam, a->inv_xi,
-                                  a->scale_rows, a->nrows, D, K, S, a->Ap, a->EV, a->PH, a->vsum, a->z, a->dzr,
-                                  a->rowacc, hot));
+    if (a->hot_mode == 2) {
+      // per-nonzero terms of the hot block in the fused tcgen05 tile kernel; the gather kernel keeps
+      // the uncovered entries only
+      if (!a->EVt) return SPMF_ERR_BAD_ARG;
+      STEP_TRY(spmf_hot_ev_tiles(a->EV, a->PH, D, H, K, S, a->EVt, hot));
+      STEP_TRY(spmf_zero_col_grads(a->GAp, a->GEV, a->Gph, D, K, S, hot));
+      STEP_TRY(spmf_csr_rows_cold(a->rowptr, a->cols, a->vals, a->rowmid, a->rowsum, a->inv_xi, a->scale_rows,
+                                  a->nrows, D, K, S, a->Ap, a->EV, a->PH, a->z, a->dzr, a->rowacc, hot));
+      STEP_TRY(spmf_hot_tile(a->xhot, a->EVt, a->z, a->nrows, D, H, K, S, a->dzr, a->rowacc, a->GEV, a->Gph, hot));
+      STEP_TRY(spmf_rows_finish(a->rowsum, a->lgam, a->inv_xi, a->scale_rows, a->nrows, K, S, a->vsum, a->z, a->dzr,
+                                a->rowacc, hot));
+    } else {
+      STEP_TRY(spmf_csr_rows_hybrid(a->rowptr, a->cols, a->vals, a->rowmid, a->rowsum, a->lgam, a->inv_xi,
+                                    a->scale_rows, a->nrows, D, K, S, a->Ap, a->EV, a->PH, a->vsum, a->z, a->dzr,
+                                    a->rowacc, hot));
+    }
   }
   if (a->ev_rows1) CUDA_TRY(cudaEventRecord((cudaEvent_t)a->ev_rows1, hot));
   STEP_TRY(spmf_batch_sums(a->z, a->rowacc, a->nrows, K, S, a->zcolsum, a->datasums, a->scr_d, hot));
@@ -84,7 +97,7 @@ int spmf_advi_step(const spmf_step_args* a) {
     const bool fork = a->aux_stream1 && a->aux_stream2 && a->ev_aux_fork && a->ev_aux_join1 && a->ev_aux_join2;
     cudaStream_t s1 = fork ? (cudaStream_t)a->aux_stream1 : hot;
     cudaStream_t s2 = fork ? (cudaStream_t)a->aux_stream2 : hot;
-    STEP_TRY(spmf_zero_col_grads(a->GAp, a->GEV, a->Gph, D, K, S, hot));
+    if (a->hot_mode != 2) STEP_TRY(spmf_zero_col_grads(a->GAp, a->GEV, a->Gph, D, K, S, hot));
     if (fork) {
       CUDA_TRY(cudaEventRecord((cudaEvent_t)a->ev_aux_fork, hot));
       CUDA_TRY(cudaStreamWaitEvent(s1, (cudaEvent_t)a->ev_aux_fork, 0));
@@ -98,8 +111,9 @@ int spmf_advi_step(const spmf_step_args* a) {
     if (a->ev_gemm1) CUDA_TRY(cudaEventRecord((cudaEvent_t)a->ev_gemm1, s1));
     STEP_TRY(spmf_csc_cols_accum(a->colptr, a->crows, a->cvals, a->nnz, a->nrows, D, K, S, a->z, a->dzr, a->EV,
                                  a->PH, a->GAp, a->GEV, a->Gph, 0, s2));
-    STEP_TRY(spmf_csc_cols_accum(a->hot_colptr, a->hot_crows, a->hot_cvals, a->nnz, a->nrows, D, K, S, a->z, a->dzr,
-                                 a->EV, a->PH, a->GAp, a->GEV, a->Gph, 1, hot));
+    if (a->hot_mode != 2)      // (mode 2: GEV / Gphi of the covered entries came from the tile kernel)
+      STEP_TRY(spmf_csc_cols_accum(a->hot_colptr, a->hot_crows, a->hot_cvals, a->nnz, a->nrows, D, K, S, a->z,
+                                   a->dzr, a->EV, a->PH, a->GAp, a->GEV, a->Gph, 1, hot));
     if (fork) {
       CUDA_TRY(cudaEventRecord((cudaEvent_t)a->ev_aux_join1, s1));
       CUDA_TRY(cudaEventRecord((cudaEvent_t)a->ev_aux_join2, s2));

@@ -21,83 +21,12 @@
 
 #include "../../include/spmf_b200.h"
 #include "spmf_umma_layout.cuh"
+#include "spmf_umma_ptx.cuh"
 
 namespace spmf {
 
 constexpr int kGemmStages = 3;
 constexpr int kGemmThreads = 128;
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return (uint32_t)__cvta_generic_to_shared(p);
-}
-
-// 64-bit shared-memory matrix descriptor, K-major, no swizzle (cute::UMMA::SmemDescriptor):
-// start address >> 4 in [0,14), leading byte offset >> 4 in [16,30) (next 16-byte chunk along K),
-// stride byte offset >> 4 in [32,46) (next group of 8 rows), version = 1 in [46,48).
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr >> 4) & 0x3fffu);
-  d |= (uint64_t)((lbo >> 4) & 0x3fffu) << 16;
-  d |= (uint64_t)((sbo >> 4) & 0x3fffu) << 32;
-  d |= (uint64_t)1 << 46;
-  return d;
-}
-
-// instruction descriptor (cute::UMMA::InstrDescriptor): D = f32, A = B = bf16, both K-major
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                          uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-
-__device__ __forceinline__ void umma_commit(uint32_t mbar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar)
-               : "memory");
-}
-
-__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
-}
-
-__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
-  uint32_t done;
-  do {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t"
-        "}\n"
-        : "=r"(done)
-        : "r"(mbar), "r"(parity)
-        : "memory");
-  } while (!done);
-}
-
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-  uint32_t r[32];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
 
 template <int N>
 struct GemmSmem {
@@ -106,15 +35,6 @@ struct GemmSmem {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int TOTAL = kGemmStages * STAGE_BYTES + 128;
 };
-
-__device__ __forceinline__ void mbar_expect_tx(uint32_t mbar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t mbar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-               "l"(src), "r"(bytes), "r"(mbar)
-               : "memory");
-}
 
 // C[q][M][N] += A[M][Kd] . (B3[q][0] + B3[q][1] + B3[q][2])[N][Kd]^T, operands UMMA-tiled (see above).
 // Warp 0 lane 0: TMA producer.  Warp 1 lane 0: MMA issuer.  All four warps: epilogue.
@@ -259,6 +179,69 @@ split3_transpose_kernel(const float* __restrict__ src, long long lds, long long 
   }
 }
 
+// Probe (tests / bring-up): one CTA copies raw operand images into shared memory, issues `nk` MMAs with
+// the given descriptor fields and dumps the whole 128-lane x N-column accumulator block.  Used to pin
+// the MN-major descriptor conventions and the M=64 accumulator layout against numpy.
+__global__ void __launch_bounds__(128, 1)
+umma_probe_kernel(const unsigned char* __restrict__ a_img, int a_bytes, const unsigned char* __restrict__ b_img,
+                  int b_bytes, int M, int N, int a_mn, int b_mn, int lbo_a, int sbo_a, int step_a, int lbo_b,
+                  int sbo_b, int step_b, int nk, float* __restrict__ out) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 127u) & ~127u;
+  unsigned char* sp = smem_raw + (sbase - smem_u32(smem_raw));
+  __shared__ __align__(8) unsigned long long mb;
+  __shared__ uint32_t tslot;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int a_pad = (a_bytes + 127) & ~127;
+  for (int i = tid; i < a_bytes; i += 128) sp[i] = a_img[i];
+  for (int i = tid; i < b_bytes; i += 128) sp[a_pad + i] = b_img[i];
+  const uint32_t mbar = smem_u32(&mb);
+  if (tid == 0) {
+    mbar_init(mbar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tslot)), "r"(256u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tacc = tslot;
+  // clear the block so untouched lanes read back as zeros: one dummy-free way is tcgen05.st
+  {
+    const uint32_t taddr = tacc + ((uint32_t)(warp * 32) << 16);
+    for (int c = 0; c < N; ++c)
+      asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr + c), "r"(0u) : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  if (tid == 0) {
+    const uint32_t idesc = umma_idesc_bf16(M, N, a_mn, b_mn);
+    for (int j = 0; j < nk; ++j) {
+      const uint64_t ad = umma_desc(sbase + j * step_a, lbo_a, sbo_a);
+      const uint64_t bd = umma_desc(sbase + a_pad + j * step_b, lbo_b, sbo_b);
+      umma_bf16(tacc, ad, bd, idesc, j ? 1u : 0u);
+    }
+    umma_commit(mbar);
+  }
+  __syncwarp();
+  mbar_wait(mbar, 0u);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  for (int cb = 0; cb < N / 32; ++cb) {
+    float v[32];
+    tmem_ld32(tacc + ((uint32_t)(warp * 32) << 16) + (uint32_t)(cb * 32), v);
+    for (int j = 0; j < 32; ++j) out[(long long)tid * N + cb * 32 + j] = v[j];
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tacc), "r"(256u) : "memory");
+}
+
 template <int N>
 static int launch_gemm3(const __nv_bfloat16* A, long long aq, int M, const __nv_bfloat16* B, long long bq, float* C,
                         long long ldc, long long cq, int Kd, int NQ, int splits, cudaStream_t st) {
@@ -325,6 +308,22 @@ int spmf_umma_gemm3(const void* A, long long a_qstride, int M, const void* B3, l
     case 128: return launch_gemm3<128>(a, a_qstride, M, b, b_qstride, C, ldc, c_qstride, Kd, NQ, splits, st);
     default: return SPMF_ERR_UNSUPPORTED;
   }
+}
+
+int spmf_umma_probe(const void* a_img, int a_bytes, const void* b_img, int b_bytes, int M, int N, int a_mn,
+                    int b_mn, int lbo_a, int sbo_a, int step_a, int lbo_b, int sbo_b, int step_b, int nk,
+                    float* out, void* stream) {
+  if (!a_img || !b_img || !out || a_bytes <= 0 || b_bytes <= 0 || nk <= 0) return SPMF_ERR_BAD_ARG;
+  if ((M != 64 && M != 128) || N % 32 || N < 32 || N > 256) return SPMF_ERR_BAD_ARG;
+  const int smem = ((a_bytes + 127) & ~127) + b_bytes + 256;
+  if (smem > 200 * 1024) return SPMF_ERR_BAD_ARG;
+  cudaError_t e = cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return (int)e;
+  umma_probe_kernel<<<1, 128, smem, (cudaStream_t)stream>>>((const unsigned char*)a_img, a_bytes,
+                                                          (const unsigned char*)b_img, b_bytes, M, N, a_mn, b_mn,
+                                                          lbo_a, sbo_a, step_a, lbo_b, sbo_b, step_b, nk, out);
+  e = cudaGetLastError();
+  return e == cudaSuccess ? SPMF_OK : (int)e;
 }
 
 int spmf_split3_transpose(const float* src, long long lds, long long src_qstride, int R, int Rpad, int Ccols,

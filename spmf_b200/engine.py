@@ -56,6 +56,8 @@ class StepWorkspace:
         self.t3_qstride = int(_abi._lib.spmf_umma_tiled_b_elems(self.KP * self.SV, kd))
         self.ApT3 = torch.zeros(self.NQ * self.t3_qstride, dtype=torch.bfloat16, device=self.device)
         self.dzrT3 = torch.zeros(self.NQ * self.t3_qstride, dtype=torch.bfloat16, device=self.device)
+        self.EVt = torch.zeros(max(int(_abi._lib.spmf_hot_tile_scratch_bytes(int(H), self.K, self.S)), 16),
+                               dtype=torch.uint8, device=self.device)
         return True
 
     def ensure_rows(self, nrows):
@@ -97,6 +99,8 @@ class AdviEngine:
         self.rank = None          # int32 [D]: table row of each feature (hot-column ordering), or None
         self.hot_cols = 0         # H > 0 enables the hybrid (tensor-core hot block + gather) step
         self.hybrid_ok = bool(_abi._lib.spmf_hybrid_supported(self.K, self.S))
+        # 1: tensor cores for the two count products only; 2: also the per-nonzero terms of the hot block
+        self.hot_mode = int(os.environ.get("SPMF_HOT_MODE", "2"))
         self.inv_xi = 1.0
         self._ws = None
         self._side = None
@@ -250,6 +254,7 @@ class AdviEngine:
             a.rowmid, a.xhot, a.xthot = _ptr(h.rowmid), _ptr(h.xhot), _ptr(h.xthot)
             a.t3_qstride = w.t3_qstride
             a.ApT3, a.dzrT3 = _ptr(w.ApT3), _ptr(w.dzrT3)
+            a.hot_mode, a.EVt = int(self.hot_mode), _ptr(w.EVt)
         else:
             a.rowptr, a.cols, a.vals = _ptr(batch.rowptr), _ptr(batch.cols), _ptr(batch.vals)
             a.colptr, a.crows, a.cvals = _ptr(batch.colptr), _ptr(batch.crows), _ptr(batch.cvals)
