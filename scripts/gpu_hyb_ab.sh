@@ -3,9 +3,8 @@
 cd "${GRAFT_REPO_ROOT:-.}"
 mkdir -p gpurun_out
 TAG=${1:-h1}
-timeout 600 python -m pytest tests/test_gpu_hybrid.py -q -x 2>&1 | tail -30 | tee gpurun_out/pytest_hyb_$TAG.log
 for hd in ${HDS:-0.03 0.015 0}; do
-  timeout 600 python bench.py --steps 32 --warmup 4 --no-cpu-baseline --hot-density $hd > gpurun_out/ab_${TAG}_$hd.json 2> gpurun_out/ab_${TAG}_$hd.err
+  SPMF_HOT_MODE=${HOTMODE:-2} timeout 600 python bench.py --steps 32 --warmup 4 --no-cpu-baseline --hot-density $hd > gpurun_out/ab_${TAG}_$hd.json 2> gpurun_out/ab_${TAG}_$hd.err
   echo "hot-density $hd rc=$?"; python - <<PY
 import json
 for l in open("gpurun_out/ab_${TAG}_$hd.json"):
@@ -15,7 +14,7 @@ for l in open("gpurun_out/ab_${TAG}_$hd.json"):
 PY
   tail -3 gpurun_out/ab_${TAG}_$hd.err
 done
-CMD="python bench.py --steps 3 --warmup 3 --no-cpu-baseline"
+CMD="python bench.py --steps 3 --warmup 3 --no-cpu-baseline --hot-density ${NCU_HD:-0.03}"
 ncu --metrics gpu__time_duration.sum --clock-control none --nvtx --nvtx-include "spmf_timed/" --csv \
     --log-file gpurun_out/launches_$TAG.csv $CMD > gpurun_out/ncu_list.log 2>&1
 echo "ncu list rc=$?"

@@ -124,8 +124,13 @@ hot_ev_tiles_kernel(const float* __restrict__ EV, const float* __restrict__ PH, 
 }
 
 // ---- the fused tile kernel --------------------------------------------------------------------------
+// 256 threads: warp w works on tensor-memory lanes 32*(w&3).. (the rows of the tile) and on column
+// half (w>>2) of the chunk, so the element-wise phase has eight warps of ILP per CTA; two CTAs per SM
+// interleave their MMA and CUDA-core phases.
+constexpr int kTileThreads = 256;
+
 template <int KP, int SV>
-__global__ void __launch_bounds__(128, 2)
+__global__ void __launch_bounds__(kTileThreads, 2)
 hot_tile_kernel(const unsigned char* __restrict__ xhot, const unsigned char* __restrict__ EVt,
                 const float* __restrict__ z, int nrows, int D, int H, int nch,
                 float* __restrict__ dzacc, float* __restrict__ rowacc, float* __restrict__ GEV,
@@ -139,33 +144,38 @@ hot_tile_kernel(const unsigned char* __restrict__ xhot, const unsigned char* __r
   __shared__ uint32_t tmem_slot;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int rt = tid & 127;                 // row of the tile = tensor-memory lane
+  const int hcol = tid >> 7;                // column half of the chunk this thread works on
+  const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
   const int mt = blockIdx.x, s = blockIdx.y;
   const int q = s / SV, sv = s - q * SV;
-  const int m0 = mt * 128;
-  const int row = m0 + tid;
+  const int row = mt * 128 + rt;
 
-  // shared-memory map
-  const uint32_t sStage[2] = {sbase, sbase + (uint32_t)T::STAGE};
-  const uint32_t sZ[2] = {sbase + 2u * T::STAGE, sbase + 2u * T::STAGE + (uint32_t)T::Z_TILE};       // hi, lo
-  const uint32_t sW[2] = {sZ[1] + (uint32_t)T::Z_TILE, sZ[1] + (uint32_t)T::Z_TILE + (uint32_t)T::W_TILE};
-  unsigned char* pStage[2] = {sp, sp + T::STAGE};
-  unsigned char* pZ[2] = {sp + 2 * T::STAGE, sp + 2 * T::STAGE + T::Z_TILE};
-  unsigned char* pW[2] = {pZ[1] + T::Z_TILE, pZ[1] + T::Z_TILE + T::W_TILE};
+  // shared-memory map: [stage 0 | stage 1 | Z hi | Z lo | W hi | W lo]
+  const uint32_t sStage0 = sbase;
+  const uint32_t sZ0 = sbase + 2u * T::STAGE, sZ1 = sZ0 + (uint32_t)T::Z_TILE;
+  const uint32_t sW0 = sZ1 + (uint32_t)T::Z_TILE, sW1 = sW0 + (uint32_t)T::W_TILE;
+  unsigned char* const pZ0 = sp + 2 * T::STAGE;
+  unsigned char* const pZ1 = pZ0 + T::Z_TILE;
+  unsigned char* const pW0 = pZ1 + T::Z_TILE;
+  unsigned char* const pW1 = pW0 + T::W_TILE;
 
-  const uint32_t full[2] = {smem_u32(&mbar_store[0]), smem_u32(&mbar_store[1])};
+  const uint32_t full0 = smem_u32(&mbar_store[0]), full1 = smem_u32(&mbar_store[1]);
   const uint32_t bar_s = smem_u32(&mbar_store[2]), bar_g = smem_u32(&mbar_store[3]);
   if (tid == 0) {
-    mbar_init(full[0], 1); mbar_init(full[1], 1); mbar_init(bar_s, 1); mbar_init(bar_g, 1);
+    mbar_init(full0, 1); mbar_init(full1, 1); mbar_init(bar_s, 1);
+    mbar_init(bar_g, 2);          // P2 and P3 are issued (and committed) by two different threads
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 2) {
+  if (warp == 3) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)),
                  "r"((uint32_t)T::TM_COLS)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
 
-  // ---- Z_s tile: this draw's z of the 128 rows as two bf16 terms + the ones column
+  // ---- Z_s tile: this draw's z of the 128 rows as two bf16 terms + the ones column.  The two
+  // thread halves write alternate 16-byte chunks of the row.
   {
     float zr[KK + 8];
 #pragma unroll
@@ -181,6 +191,7 @@ hot_tile_kernel(const unsigned char* __restrict__ xhot, const unsigned char* __r
     zr[KK] = 1.f;                               // W^T . 1 = column sums of w  (Gphi)
 #pragma unroll
     for (int j = 0; j < T::ZCPR; ++j) {
+      if ((j & 1) != hcol) continue;
       uint32_t hi[4], lo[4];
 #pragma unroll
       for (int p = 0; p < 4; ++p) {
@@ -188,9 +199,9 @@ hot_tile_kernel(const unsigned char* __restrict__ xhot, const unsigned char* __r
         hi[p] = pack_bf16(a, b);
         lo[p] = pack_bf16(a - bf16_lo(hi[p]), b - bf16_hi(hi[p]));
       }
-      const uint32_t o = core_off_g(tid, j, T::ZCPR);
-      *reinterpret_cast<uint4*>(pZ[0] + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-      *reinterpret_cast<uint4*>(pZ[1] + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      const uint32_t o = core_off_g(rt, j, T::ZCPR);
+      *reinterpret_cast<uint4*>(pZ0 + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<uint4*>(pZ1 + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
     }
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -203,67 +214,78 @@ hot_tile_kernel(const unsigned char* __restrict__ xhot, const unsigned char* __r
   const unsigned char* esrc = EVt + (size_t)s * nch * T::EV_BLOCK;
   auto issue_load = [&](int chunk) {
     const int st = chunk & 1;
-    mbar_expect_tx(full[st], (uint32_t)T::STAGE);
-    tma_bulk_g2s(sStage[st], xsrc + (size_t)chunk * T::X_TILE, T::X_TILE, full[st]);
-    tma_bulk_g2s(sStage[st] + T::X_TILE, esrc + (size_t)chunk * T::EV_BLOCK, T::EV_BLOCK, full[st]);
+    const uint32_t fb = st ? full1 : full0, dst = sStage0 + (uint32_t)(st * T::STAGE);
+    mbar_expect_tx(fb, (uint32_t)T::STAGE);
+    tma_bulk_g2s(dst, xsrc + (size_t)chunk * T::X_TILE, T::X_TILE, fb);
+    tma_bulk_g2s(dst + T::X_TILE, esrc + (size_t)chunk * T::EV_BLOCK, T::EV_BLOCK, fb);
   };
+  // Descriptors are loop invariants up to the stage: build them once (the start-address field is
+  // the low 14 bits in 16-byte units, so stepping an operand is one 64-bit add), and spread the MMA
+  // issue over three threads -- a lone thread retires ~1 instruction per 4 clocks.
+  //   warp 0 lane 0: P2        warp 1 lane 0: P3        warp 2 lane 0: P1 of the next chunk
+  //   warp 3 lane 0: TMA for chunk i+2
+  constexpr uint64_t kStageStep = (uint64_t)(T::STAGE >> 4);
   // P1: S = Z . EV^T   (both K-major), terms hi.hi, hi.lo, lo.hi
   auto issue_p1 = [&](int st) {
     constexpr uint32_t ID = umma_idesc_bf16(128, 64, 0, 0);
-    const uint32_t sEV = sStage[st] + T::X_TILE;
+    const uint64_t dZk[2] = {umma_desc(sZ0, 128, T::ZCPR * 128), umma_desc(sZ1, 128, T::ZCPR * 128)};
+    const uint64_t dEk[2] = {umma_desc(sStage0 + T::X_TILE, 128, T::CPR * 128),
+                             umma_desc(sStage0 + T::X_TILE + T::EV_TILE, 128, T::CPR * 128)};
 #pragma unroll
     for (int t = 0; t < 3; ++t) {
-      const uint32_t a = sZ[t == 2 ? 1 : 0], b = sEV + (t == 1 ? T::EV_TILE : 0);
+      const uint64_t a = dZk[t == 2 ? 1 : 0], b = dEk[t == 1 ? 1 : 0] + (uint64_t)st * kStageStep;
 #pragma unroll
       for (int j = 0; j < KK / 16; ++j)
-        umma_bf16(tm + T::TM_S, umma_desc(a + j * 256, 128, T::ZCPR * 128), umma_desc(b + j * 256, 128, T::CPR * 128),
-                  ID, (t | j) ? 1u : 0u);
+        umma_bf16(tm + T::TM_S, a + (uint64_t)(j * 16), b + (uint64_t)(j * 16), ID, (t | j) ? 1u : 0u);
     }
     umma_commit(bar_s);
   };
-  if (tid == 0) {
+  if (tid == 96) {
     issue_load(0);
     if (nch > 1) issue_load(1);
-    mbar_wait(full[0], 0u);
+  }
+  if (tid == 64) {
+    mbar_wait(full0, 0u);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     issue_p1(0);
   }
 
-  float xlog2 = 0.f;
-  int bad = 0;
+  float xlog2 = 0.f, badacc = 0.f;
   for (int i = 0; i < nch; ++i) {
     const int st = i & 1;
-    mbar_wait(full[st], (uint32_t)((i >> 1) & 1));        // TMA data visible to this thread
-    mbar_wait(bar_s, (uint32_t)(i & 1));                  // S ready in tensor memory
+    mbar_wait(st ? full1 : full0, (uint32_t)((i >> 1) & 1));   // TMA data visible to this thread
+    mbar_wait(bar_s, (uint32_t)(i & 1));                       // S ready in tensor memory
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
-    // ---- E: lambda, w = x / lambda, x log lambda ; W -> shared memory as two bf16 terms
-    const unsigned char* xt = pStage[st];
-    const float* ph = reinterpret_cast<const float*>(pStage[st] + T::X_TILE + 2 * T::EV_TILE);
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
+    // ---- E: lambda, w = x / lambda, x log lambda for 32 columns of this thread's row;
+    //      W -> shared memory as two bf16 terms.  The rate is clamped into the positive finite range
+    //      instead of branching (poisson.py:606-616 guards non-finite rates): a clamped entry with a
+    //      nonzero count is flagged through `badacc`.
+    {
+      const unsigned char* xt = sp + st * T::STAGE;
+      const float* ph = reinterpret_cast<const float*>(xt + T::X_TILE + 2 * T::EV_TILE) + 32 * hcol;
       float lam[32];
-      tmem_ld<32>(tm + ((uint32_t)(warp * 32) << 16) + T::TM_S + 32 * h, lam);
+      tmem_ld<32>(tm + lane_base + T::TM_S + 32 * hcol, lam);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {          // 4 chunks of 8 columns
-        const uint4 xp = *reinterpret_cast<const uint4*>(xt + core_off(tid, 4 * h + j));
+        const uint32_t o = core_off(rt, 4 * hcol + j);
+        const uint4 xp = *reinterpret_cast<const uint4*>(xt + o);
         const uint32_t xw[4] = {xp.x, xp.y, xp.z, xp.w};
-        const float4 p0 = *reinterpret_cast<const float4*>(ph + 32 * h + 8 * j);
-        const float4 p1 = *reinterpret_cast<const float4*>(ph + 32 * h + 8 * j + 4);
+        const float4 p0 = *reinterpret_cast<const float4*>(ph + 8 * j);
+        const float4 p1 = *reinterpret_cast<const float4*>(ph + 8 * j + 4);
         const float phv[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
         float w[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           const float x = (e & 1) ? bf16_hi(xw[e >> 1]) : bf16_lo(xw[e >> 1]);
           const float l = lam[8 * j + e] + phv[e];                 // poisson.py:177
-          const bool ok = rate_ok_t(l);
+          const float lc = fminf(fmaxf(l, 1e-30f), 3.0e38f);
           float lg, rc;
-          asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(l));
-          asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(l));
-          const bool nz = x > 0.f;
-          w[e] = (nz && ok) ? x * rc : 0.f;
-          xlog2 = fmaf(x, (nz && ok) ? lg : 0.f, xlog2);
-          bad += (nz && !ok) ? 1 : 0;
+          asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(lc));
+          asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(lc));
+          w[e] = x * rc;
+          xlog2 = fmaf(x, lg, xlog2);
+          badacc = fmaf(x, fabsf(l - lc), badacc);                 // 0 unless the rate left (0, inf)
         }
         uint32_t hi[4], lo[4];
 #pragma unroll
@@ -271,9 +293,8 @@ hot_tile_kernel(const unsigned char* __restrict__ xhot, const unsigned char* __r
           hi[p] = pack_bf16(w[2 * p], w[2 * p + 1]);
           lo[p] = pack_bf16(w[2 * p] - bf16_lo(hi[p]), w[2 * p + 1] - bf16_hi(hi[p]));
         }
-        const uint32_t o = core_off(tid, 4 * h + j);
-        *reinterpret_cast<uint4*>(pW[0] + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-        *reinterpret_cast<uint4*>(pW[1] + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        *reinterpret_cast<uint4*>(pW0 + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(pW1 + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
       }
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -281,89 +302,118 @@ hot_tile_kernel(const unsigned char* __restrict__ xhot, const unsigned char* __r
     __syncthreads();
 
     if (tid == 0) {
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t sEV = sStage[st] + T::X_TILE;
       // P2: dZ += W . EV      A = W K-major [128 x 64], B = EV MN-major (N = latent, K = 64 columns)
-      {
-        constexpr uint32_t ID = umma_idesc_bf16(128, KK, 0, 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      constexpr uint32_t ID = umma_idesc_bf16(128, KK, 0, 1);
+      const uint64_t dWk[2] = {umma_desc(sW0, 128, 1024), umma_desc(sW1, 128, 1024)};
+      const uint64_t dEn[2] = {umma_desc(sStage0 + T::X_TILE, T::CPR * 128, 128),
+                               umma_desc(sStage0 + T::X_TILE + T::EV_TILE, T::CPR * 128, 128)};
 #pragma unroll
-        for (int t = 0; t < 3; ++t) {
-          const uint32_t a = sW[t == 2 ? 1 : 0], b = sEV + (t == 1 ? T::EV_TILE : 0);
+      for (int t = 0; t < 3; ++t) {
+        const uint64_t a = dWk[t == 2 ? 1 : 0], b = dEn[t == 1 ? 1 : 0] + (uint64_t)st * kStageStep;
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            umma_bf16(tm + T::TM_DZ, umma_desc(a + j * 256, 128, 1024),
-                      umma_desc(b + j * (2 * T::CPR * 128), T::CPR * 128, 128), ID, (i | t | j) ? 1u : 0u);
-        }
-      }
-      // P3: GEV = W^T . [Z | 1]   A = W MN-major (M = 64 columns, K = 128 rows), B = Z MN-major (N = NZ)
-      {
-        constexpr uint32_t ID = umma_idesc_bf16(64, T::NZ, 1, 1);
-#pragma unroll
-        for (int t = 0; t < 3; ++t) {
-          const uint32_t a = sW[t == 2 ? 1 : 0], b = sZ[t == 1 ? 1 : 0];
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            umma_bf16(tm + T::TM_GEV, umma_desc(a + j * 2048, 1024, 128),
-                      umma_desc(b + j * (2 * T::ZCPR * 128), T::ZCPR * 128, 128), ID, (t | j) ? 1u : 0u);
-        }
+        for (int j = 0; j < 4; ++j)
+          umma_bf16(tm + T::TM_DZ, a + (uint64_t)(j * 16), b + (uint64_t)(j * (2 * T::CPR * 128 / 16)), ID,
+                    (i | t | j) ? 1u : 0u);
       }
       umma_commit(bar_g);
-      if (i + 1 < nch) {                                  // keep the tensor core busy during the flush
-        mbar_wait(full[(i + 1) & 1], (uint32_t)(((i + 1) >> 1) & 1));
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        issue_p1((i + 1) & 1);
+    } else if (tid == 32) {
+      // P3: GEV = W^T . [Z | 1]   A = W MN-major (M = 64 columns, K = 128 rows), B = Z MN-major (N = NZ)
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      constexpr uint32_t ID = umma_idesc_bf16(64, T::NZ, 1, 1);
+      const uint64_t dWn[2] = {umma_desc(sW0, 1024, 128), umma_desc(sW1, 1024, 128)};
+      const uint64_t dZn[2] = {umma_desc(sZ0, T::ZCPR * 128, 128), umma_desc(sZ1, T::ZCPR * 128, 128)};
+#pragma unroll
+      for (int t = 0; t < 3; ++t) {
+        const uint64_t a = dWn[t == 2 ? 1 : 0], b = dZn[t == 1 ? 1 : 0];
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          umma_bf16(tm + T::TM_GEV, a + (uint64_t)(j * (2048 / 16)), b + (uint64_t)(j * (2 * T::ZCPR * 128 / 16)), ID,
+                    (t | j) ? 1u : 0u);
       }
+      umma_commit(bar_g);
+    } else if (tid == 64 && i + 1 < nch) {
+      // P1 of the next chunk keeps the tensor core busy during the flush below
+      mbar_wait(((i + 1) & 1) ? full1 : full0, (uint32_t)(((i + 1) >> 1) & 1));
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      issue_p1((i + 1) & 1);
     }
     __syncwarp();
     mbar_wait(bar_g, (uint32_t)(i & 1));
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    if (tid == 0 && i + 2 < nch) issue_load(i + 2);       // this stage's inputs are fully consumed
+    if (tid == 96 && i + 2 < nch) issue_load(i + 2);      // this stage's inputs are fully consumed
 
-    // ---- flush GEV / Gphi of the chunk: accumulator row m sits in lane (m/16)*32 + m%16
+    // ---- flush GEV / Gphi of the chunk: accumulator row m sits in lane (m/16)*32 + m%16; the two
+    //      thread halves take the two halves of the latent range (the second also the ones column)
     {
-      float g[T::NZ];
-      const uint32_t ta = tm + ((uint32_t)(warp * 32) << 16) + T::TM_GEV;
+      const int c = i * 64 + (warp & 3) * 16 + lane;
+      const bool act = lane < 16 && c < H;
+      float* ge = GEV + ((size_t)q * D + c) * REC;
+      const uint32_t ta = tm + lane_base + T::TM_GEV;
       if constexpr (KK == 32) {
-        tmem_ld<32>(ta, g);
-        tmem_ld<8>(ta + 32, g + 32);
-      } else {
-        tmem_ld<16>(ta, g);
-        tmem_ld<8>(ta + 16, g + 16);
-      }
-      const int c = i * 64 + warp * 16 + lane;
-      if (lane < 16 && c < H) {
-        float* ge = GEV + ((size_t)q * D + c) * REC;
+        float g[24];
+        if (hcol == 0) {
+          tmem_ld<16>(ta, g);
+          if (act) {
 #pragma unroll
-        for (int k = 0; k < KP; k += 4)
-          atomicAdd(reinterpret_cast<float4*>(ge + rec_pos(KP, SV, sv, k)), make_float4(g[k], g[k + 1], g[k + 2], g[k + 3]));
-        atomicAdd(Gphi + ((size_t)q * D + c) * SV + sv, g[KK]);
+            for (int k = 0; k < 16; k += 4)
+              if (k < KP) atomicAdd(reinterpret_cast<float4*>(ge + rec_pos(KP, SV, sv, k)), make_float4(g[k], g[k + 1], g[k + 2], g[k + 3]));
+          }
+        } else {
+          tmem_ld<16>(ta + 16, g);
+          tmem_ld<8>(ta + 32, g + 16);
+          if (act) {
+#pragma unroll
+            for (int k = 0; k < 16; k += 4)
+              if (16 + k < KP) atomicAdd(reinterpret_cast<float4*>(ge + rec_pos(KP, SV, sv, 16 + k)), make_float4(g[k], g[k + 1], g[k + 2], g[k + 3]));
+            atomicAdd(Gphi + ((size_t)q * D + c) * SV + sv, g[16]);
+          }
+        }
+      } else {              // KK == 16: latent dims in columns [0,16), the ones column at 16
+        float g[16];
+        if (hcol == 0) {
+          tmem_ld<16>(ta, g);
+          if (act) {
+#pragma unroll
+            for (int k = 0; k < KP; k += 4)
+              atomicAdd(reinterpret_cast<float4*>(ge + rec_pos(KP, SV, sv, k)), make_float4(g[k], g[k + 1], g[k + 2], g[k + 3]));
+          }
+        } else {
+          tmem_ld<8>(ta + 16, g);
+          if (act) atomicAdd(Gphi + ((size_t)q * D + c) * SV + sv, g[0]);
+        }
       }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   }
 
-  // ---- dZ of the 128 rows (this CTA is the only writer of its (rows, draw) slice) and row scalars
+  // ---- dZ of the 128 rows (this CTA is the only writer of its (rows, draw) slice; the two thread
+  //      halves own the two halves of the latent range) and the row scalars
   {
-    float dzv[KK];
-    const uint32_t ta = tm + ((uint32_t)(warp * 32) << 16) + T::TM_DZ;
-    if constexpr (KK == 32) tmem_ld<32>(ta, dzv); else tmem_ld<16>(ta, dzv);
+    constexpr int HK = KK / 2;
+    float dzv[HK];
+    const uint32_t ta = tm + lane_base + T::TM_DZ + HK * hcol;
+    if constexpr (HK == 16) tmem_ld<16>(ta, dzv); else tmem_ld<8>(ta, dzv);
     if (row < nrows) {
       float* dp = dzacc + ((size_t)q * nrows + row) * REC;
 #pragma unroll
-      for (int k = 0; k < KP; k += 4) {
-        float4* p = reinterpret_cast<float4*>(dp + rec_pos(KP, SV, sv, k));
-        float4 v = *p;
-        v.x += dzv[k]; v.y += dzv[k + 1]; v.z += dzv[k + 2]; v.w += dzv[k + 3];
-        *p = v;
+      for (int k = 0; k < HK; k += 4) {
+        const int kk = HK * hcol + k;
+        if (kk < KP) {
+          float4* p = reinterpret_cast<float4*>(dp + rec_pos(KP, SV, sv, kk));
+          float4 v = *p;
+          v.x += dzv[k]; v.y += dzv[k + 1]; v.z += dzv[k + 2]; v.w += dzv[k + 3];
+          *p = v;
+        }
       }
       float* ra = rowacc + ((size_t)q * nrows + row) * 4 * SV;
-      ra[0 * SV + sv] += xlog2 * 0.6931471805599453f;
-      ra[3 * SV + sv] += (float)bad;
+      atomicAdd(ra + 0 * SV + sv, xlog2 * 0.6931471805599453f);          // two threads per row
+      if (badacc != 0.f) atomicAdd(ra + 3 * SV + sv, 1.0f);              // (also true for NaN)
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 2) {
+  if (warp == 3) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm), "r"((uint32_t)T::TM_COLS) : "memory");
   }
 }
@@ -423,7 +473,7 @@ static int launch_hot_tile(const void* xhot, const void* EVt, const float* z, in
     attr = true;
   }
   dim3 grid((nrows + 127) / 128, S);
-  hot_tile_kernel<KP, SV><<<grid, 128, T::SMEM, st>>>((const unsigned char*)xhot, (const unsigned char*)EVt, z, nrows, D,
+  hot_tile_kernel<KP, SV><<<grid, kTileThreads, T::SMEM, st>>>((const unsigned char*)xhot, (const unsigned char*)EVt, z, nrows, D,
                                                      H, (H + 63) / 64, dzacc, rowacc, GEV, Gphi);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? SPMF_OK : (int)e;
