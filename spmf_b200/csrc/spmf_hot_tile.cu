@@ -42,9 +42,11 @@ struct HotTile {
   static constexpr int STAGE = X_TILE + EV_BLOCK;
   static constexpr int Z_TILE = 128 * ZCPR * 16;
   static constexpr int W_TILE = 128 * 64 * 2;
-  static constexpr int SMEM = 2 * STAGE + 2 * Z_TILE + 2 * W_TILE + 128;
-  static constexpr int TM_S = 0, TM_DZ = 64, TM_GEV = 64 + KK;   // tensor-memory columns
-  static constexpr int TM_COLS = 256;
+  static constexpr int NSTAGE = 3;                      // chunk inputs in flight
+  static constexpr int SMEM = NSTAGE * STAGE + 2 * Z_TILE + 4 * W_TILE + 128;   // W (hi, lo) double buffered
+  // tensor-memory columns: S | dZ | GEV buffer 0 | GEV buffer 1
+  static constexpr int TM_S = 0, TM_DZ = 64, TM_GEV = 64 + KK, TM_GEV_STRIDE = NZ;
+  static constexpr int TM_COLS = 256;                   // power of two >= 64 + KK + 2 NZ (<= 176)
 };
 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {     // a -> low half
@@ -124,15 +126,24 @@ hot_ev_tiles_kernel(const float* __restrict__ EV, const float* __restrict__ PH, 
 }
 
 // ---- the fused tile kernel --------------------------------------------------------------------------
-// 256 threads: warp w works on tensor-memory lanes 32*(w&3).. (the rows of the tile) and on column
-// half (w>>2) of the chunk, so the element-wise phase has eight warps of ILP per CTA; two CTAs per SM
-// interleave their MMA and CUDA-core phases.
-constexpr int kTileThreads = 256;
+// One CTA per SM.  Work thread t (< 512) handles row (t & 127) of the tile -- its tensor-memory lane;
+// warp w can only touch lanes 32*(w&3).. -- and column quarter (t >> 7) of the chunk.  Two more warps
+// only issue: MMAs must come from warp-convergent code (see spmf_umma_ptx.cuh), and an issuing warp
+// that also did element-wise work would arrive late at every barrier.
+// Software pipeline over the chunks of this CTA's column range (W and the GEV accumulator are
+// double buffered, chunk inputs triple buffered):
+//   iteration i:  wait S(i) ; E(i) -> W[i&1] ; sync ;
+//                 issue P1(i+1) then P3(i) (one thread), P2(i) (another) ;
+//                 flush GEV(i-1) -> atomics ; TMA for chunk i+2
+// so the tensor core works on chunk i (and produces S(i+1) first) while the CUDA cores flush chunk
+// i-1 and then run E(i+1).
+constexpr int kTileWorkThreads = 512;               // 16 warps: element-wise phases, flushes
+constexpr int kTileThreads = kTileWorkThreads + 64;  // + warp 16: P1/P3 issue, warp 17: P2 issue and TMA
 
 template <int KP, int SV>
-__global__ void __launch_bounds__(kTileThreads, 2)
+__global__ void __launch_bounds__(kTileThreads, 1)
 hot_tile_kernel(const unsigned char* __restrict__ xhot, const unsigned char* __restrict__ EVt,
-                const float* __restrict__ z, int nrows, int D, int H, int nch,
+                const float* __restrict__ z, int nrows, int D, int H, int nch, int chunks_per_cta,
                 float* __restrict__ dzacc, float* __restrict__ rowacc, float* __restrict__ GEV,
                 float* __restrict__ Gphi) {
   using T = HotTile<KP>;
@@ -140,31 +151,39 @@ hot_tile_kernel(const unsigned char* __restrict__ xhot, const unsigned char* __r
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 127u) & ~127u;
   unsigned char* sp = smem_raw + (sbase - smem_u32(smem_raw));
-  __shared__ __align__(8) unsigned long long mbar_store[4];
+  __shared__ __align__(8) unsigned long long mbar_store[T::NSTAGE + 3];
   __shared__ uint32_t tmem_slot;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int rt = tid & 127;                 // row of the tile = tensor-memory lane
-  const int hcol = tid >> 7;                // column half of the chunk this thread works on
+  const int hq = tid >> 7;                  // column quarter of the chunk this thread works on
   const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
   const int mt = blockIdx.x, s = blockIdx.y;
   const int q = s / SV, sv = s - q * SV;
   const int row = mt * 128 + rt;
+  const int c_begin = blockIdx.z * chunks_per_cta;
+  const int n = min(nch, c_begin + chunks_per_cta) - c_begin;       // chunks of this CTA
+  if (n <= 0) return;
 
-  // shared-memory map: [stage 0 | stage 1 | Z hi | Z lo | W hi | W lo]
+  // shared-memory map: [stage 0..2 | Z hi | Z lo | W0 hi | W0 lo | W1 hi | W1 lo]
   const uint32_t sStage0 = sbase;
-  const uint32_t sZ0 = sbase + 2u * T::STAGE, sZ1 = sZ0 + (uint32_t)T::Z_TILE;
-  const uint32_t sW0 = sZ1 + (uint32_t)T::Z_TILE, sW1 = sW0 + (uint32_t)T::W_TILE;
-  unsigned char* const pZ0 = sp + 2 * T::STAGE;
+  const uint32_t sZ0 = sbase + (uint32_t)(T::NSTAGE * T::STAGE), sZ1 = sZ0 + (uint32_t)T::Z_TILE;
+  const uint32_t sWb = sZ1 + (uint32_t)T::Z_TILE;                    // W buffer b: hi at sWb + b*2*W_TILE, lo + W_TILE
+  unsigned char* const pZ0 = sp + T::NSTAGE * T::STAGE;
   unsigned char* const pZ1 = pZ0 + T::Z_TILE;
-  unsigned char* const pW0 = pZ1 + T::Z_TILE;
-  unsigned char* const pW1 = pW0 + T::W_TILE;
+  unsigned char* const pWb = pZ1 + T::Z_TILE;
 
-  const uint32_t full0 = smem_u32(&mbar_store[0]), full1 = smem_u32(&mbar_store[1]);
-  const uint32_t bar_s = smem_u32(&mbar_store[2]), bar_g = smem_u32(&mbar_store[3]);
+  uint32_t full[T::NSTAGE];
+#pragma unroll
+  for (int i = 0; i < T::NSTAGE; ++i) full[i] = smem_u32(&mbar_store[i]);
+  const uint32_t bar_s = smem_u32(&mbar_store[T::NSTAGE]);
+  const uint32_t bar_g[2] = {smem_u32(&mbar_store[T::NSTAGE + 1]), smem_u32(&mbar_store[T::NSTAGE + 2])};
   if (tid == 0) {
-    mbar_init(full0, 1); mbar_init(full1, 1); mbar_init(bar_s, 1);
-    mbar_init(bar_g, 2);          // P2 and P3 are issued (and committed) by two different threads
+#pragma unroll
+    for (int i = 0; i < T::NSTAGE; ++i) mbar_init(full[i], 1);
+    mbar_init(bar_s, 1);
+    mbar_init(bar_g[0], 2);       // P2 and P3 are issued (and committed) by two different threads
+    mbar_init(bar_g[1], 2);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 3) {
@@ -174,9 +193,10 @@ hot_tile_kernel(const unsigned char* __restrict__ xhot, const unsigned char* __r
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
 
-  // ---- Z_s tile: this draw's z of the 128 rows as two bf16 terms + the ones column.  The two
-  // thread halves write alternate 16-byte chunks of the row.
-  {
+  const bool worker = tid < kTileWorkThreads;
+  // ---- Z_s tile: this draw's z of the 128 rows as two bf16 terms + the ones column; the four thread
+  // quarters write alternate 16-byte chunks of the row
+  if (worker) {
     float zr[KK + 8];
 #pragma unroll
     for (int k = 0; k < KK + 8; ++k) zr[k] = 0.f;
@@ -191,7 +211,7 @@ hot_tile_kernel(const unsigned char* __restrict__ xhot, const unsigned char* __r
     zr[KK] = 1.f;                               // W^T . 1 = column sums of w  (Gphi)
 #pragma unroll
     for (int j = 0; j < T::ZCPR; ++j) {
-      if ((j & 1) != hcol) continue;
+      if ((j & 3) != hq) continue;
       uint32_t hi[4], lo[4];
 #pragma unroll
       for (int p = 0; p < 4; ++p) {
@@ -210,65 +230,94 @@ hot_tile_kernel(const unsigned char* __restrict__ xhot, const unsigned char* __r
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tm = tmem_slot;
 
-  const unsigned char* xsrc = xhot + (size_t)mt * nch * T::X_TILE;
-  const unsigned char* esrc = EVt + (size_t)s * nch * T::EV_BLOCK;
-  auto issue_load = [&](int chunk) {
-    const int st = chunk & 1;
-    const uint32_t fb = st ? full1 : full0, dst = sStage0 + (uint32_t)(st * T::STAGE);
-    mbar_expect_tx(fb, (uint32_t)T::STAGE);
-    tma_bulk_g2s(dst, xsrc + (size_t)chunk * T::X_TILE, T::X_TILE, fb);
-    tma_bulk_g2s(dst + T::X_TILE, esrc + (size_t)chunk * T::EV_BLOCK, T::EV_BLOCK, fb);
+  const unsigned char* xsrc = xhot + ((size_t)mt * nch + c_begin) * T::X_TILE;
+  const unsigned char* esrc = EVt + ((size_t)s * nch + c_begin) * T::EV_BLOCK;
+  auto issue_load = [&](int i) {              // local chunk i -> stage i % NSTAGE
+    const int st = i % T::NSTAGE;
+    const uint32_t dst = sStage0 + (uint32_t)(st * T::STAGE);
+    mbar_expect_tx(full[st], (uint32_t)T::STAGE);
+    tma_bulk_g2s(dst, xsrc + (size_t)i * T::X_TILE, T::X_TILE, full[st]);
+    tma_bulk_g2s(dst + T::X_TILE, esrc + (size_t)i * T::EV_BLOCK, T::EV_BLOCK, full[st]);
   };
-  // Descriptors are loop invariants up to the stage: build them once (the start-address field is
-  // the low 14 bits in 16-byte units, so stepping an operand is one 64-bit add), and spread the MMA
-  // issue over three threads -- a lone thread retires ~1 instruction per 4 clocks.
-  //   warp 0 lane 0: P2        warp 1 lane 0: P3        warp 2 lane 0: P1 of the next chunk
-  //   warp 3 lane 0: TMA for chunk i+2
+  auto wait_full = [&](int i) { mbar_wait(full[i % T::NSTAGE], (uint32_t)((i / T::NSTAGE) & 1)); };
   constexpr uint64_t kStageStep = (uint64_t)(T::STAGE >> 4);
+  constexpr uint64_t kWStep = (uint64_t)((2 * T::W_TILE) >> 4);
   // P1: S = Z . EV^T   (both K-major), terms hi.hi, hi.lo, lo.hi
-  auto issue_p1 = [&](int st) {
+  auto issue_p1 = [&](int i) {
     constexpr uint32_t ID = umma_idesc_bf16(128, 64, 0, 0);
+    const uint64_t so = (uint64_t)(i % T::NSTAGE) * kStageStep;
     const uint64_t dZk[2] = {umma_desc(sZ0, 128, T::ZCPR * 128), umma_desc(sZ1, 128, T::ZCPR * 128)};
     const uint64_t dEk[2] = {umma_desc(sStage0 + T::X_TILE, 128, T::CPR * 128),
                              umma_desc(sStage0 + T::X_TILE + T::EV_TILE, 128, T::CPR * 128)};
 #pragma unroll
     for (int t = 0; t < 3; ++t) {
-      const uint64_t a = dZk[t == 2 ? 1 : 0], b = dEk[t == 1 ? 1 : 0] + (uint64_t)st * kStageStep;
+      const uint64_t a = dZk[t == 2 ? 1 : 0], b = dEk[t == 1 ? 1 : 0] + so;
 #pragma unroll
       for (int j = 0; j < KK / 16; ++j)
-        umma_bf16(tm + T::TM_S, a + (uint64_t)(j * 16), b + (uint64_t)(j * 16), ID, (t | j) ? 1u : 0u);
+        umma_bf16_elect(tm + T::TM_S, a + (uint64_t)(j * 16), b + (uint64_t)(j * 16), ID, (t | j) ? 1u : 0u);
     }
-    umma_commit(bar_s);
+    umma_commit_elect(bar_s);
   };
-  if (tid == 96) {
-    issue_load(0);
-    if (nch > 1) issue_load(1);
+  // flush GEV / Gphi of local chunk i: accumulator row m sits in lane (m/16)*32 + m%16; thread quarters
+  // 0/1 take the two halves of the latent range, quarter 2 the ones column
+  auto flush_gev = [&](int i) {
+    mbar_wait(bar_g[i & 1], (uint32_t)((i >> 1) & 1));
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int c = (c_begin + i) * 64 + (warp & 3) * 16 + lane;
+    const bool act = lane < 16 && c < H;
+    float* ge = GEV + ((size_t)q * D + c) * REC;
+    const uint32_t ta = tm + lane_base + T::TM_GEV + (uint32_t)((i & 1) * T::TM_GEV_STRIDE);
+    float g[16];
+    if (hq < 2) {
+      constexpr int HK = KK / 2;              // 16 or 8 latent dims per quarter
+      if constexpr (HK == 16) tmem_ld<16>(ta + HK * hq, g); else tmem_ld<8>(ta + HK * hq, g);
+      if (act) {
+#pragma unroll
+        for (int k = 0; k < HK; k += 4)
+          if (HK * hq + k < KP)
+            atomicAdd(reinterpret_cast<float4*>(ge + rec_pos(KP, SV, sv, HK * hq + k)), make_float4(g[k], g[k + 1], g[k + 2], g[k + 3]));
+      }
+    } else if (hq == 2) {
+      tmem_ld<8>(ta + KK, g);
+      if (act) atomicAdd(Gphi + ((size_t)q * D + c) * SV + sv, g[0]);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  };
+
+  if (warp == 17) {
+    if (elect_one()) {
+      issue_load(0);
+      if (n > 1) issue_load(1);
+      if (n > 2) issue_load(2);
+    }
+    __syncwarp();
   }
-  if (tid == 64) {
-    mbar_wait(full0, 0u);
+  if (warp == 16) {
+    wait_full(0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     issue_p1(0);
   }
 
-  float xlog2 = 0.f, badacc = 0.f;
-  for (int i = 0; i < nch; ++i) {
-    const int st = i & 1;
-    mbar_wait(st ? full1 : full0, (uint32_t)((i >> 1) & 1));   // TMA data visible to this thread
-    mbar_wait(bar_s, (uint32_t)(i & 1));                       // S ready in tensor memory
+  float xlog2 = 0.f;
+  for (int i = 0; i < n; ++i) {
+    const int st = i % T::NSTAGE, wb = i & 1;
+    if (worker) {
+    wait_full(i);                                           // TMA data visible to this thread
+    mbar_wait(bar_s, (uint32_t)(i & 1));                    // S(i) ready in tensor memory
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
-    // ---- E: lambda, w = x / lambda, x log lambda for 32 columns of this thread's row;
-    //      W -> shared memory as two bf16 terms.  The rate is clamped into the positive finite range
-    //      instead of branching (poisson.py:606-616 guards non-finite rates): a clamped entry with a
-    //      nonzero count is flagged through `badacc`.
+    // ---- E: lambda, w = x / lambda, x log lambda for 16 columns of this thread's row; W -> shared
+    //      memory as two bf16 terms.  The rate is floored at 1e-30 instead of branching on it
+    //      (poisson.py:606-616 guards non-finite rates; here they are sums of positive terms).
     {
       const unsigned char* xt = sp + st * T::STAGE;
-      const float* ph = reinterpret_cast<const float*>(xt + T::X_TILE + 2 * T::EV_TILE) + 32 * hcol;
-      float lam[32];
-      tmem_ld<32>(tm + lane_base + T::TM_S + 32 * hcol, lam);
+      const float* ph = reinterpret_cast<const float*>(xt + T::X_TILE + 2 * T::EV_TILE) + 16 * hq;
+      unsigned char* w0 = pWb + wb * 2 * T::W_TILE;
+      float lam[16];
+      tmem_ld<16>(tm + lane_base + T::TM_S + 16 * hq, lam);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {          // 4 chunks of 8 columns
-        const uint32_t o = core_off(rt, 4 * hcol + j);
+      for (int j = 0; j < 2; ++j) {          // 2 chunks of 8 columns
+        const uint32_t o = core_off(rt, 2 * hq + j);
         const uint4 xp = *reinterpret_cast<const uint4*>(xt + o);
         const uint32_t xw[4] = {xp.x, xp.y, xp.z, xp.w};
         const float4 p0 = *reinterpret_cast<const float4*>(ph + 8 * j);
@@ -278,14 +327,12 @@ hot_tile_kernel(const unsigned char* __restrict__ xhot, const unsigned char* __r
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           const float x = (e & 1) ? bf16_hi(xw[e >> 1]) : bf16_lo(xw[e >> 1]);
-          const float l = lam[8 * j + e] + phv[e];                 // poisson.py:177
-          const float lc = fminf(fmaxf(l, 1e-30f), 3.0e38f);
+          const float l = fmaxf(lam[8 * j + e] + phv[e], 1e-30f);       // poisson.py:177
           float lg, rc;
-          asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(lc));
-          asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(lc));
+          asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(l));
+          asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(l));
           w[e] = x * rc;
           xlog2 = fmaf(x, lg, xlog2);
-          badacc = fmaf(x, fabsf(l - lc), badacc);                 // 0 unless the rate left (0, inf)
         }
         uint32_t hi[4], lo[4];
 #pragma unroll
@@ -293,124 +340,89 @@ hot_tile_kernel(const unsigned char* __restrict__ xhot, const unsigned char* __r
           hi[p] = pack_bf16(w[2 * p], w[2 * p + 1]);
           lo[p] = pack_bf16(w[2 * p] - bf16_lo(hi[p]), w[2 * p + 1] - bf16_hi(hi[p]));
         }
-        *reinterpret_cast<uint4*>(pW0 + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-        *reinterpret_cast<uint4*>(pW1 + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        *reinterpret_cast<uint4*>(w0 + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(w0 + T::W_TILE + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
       }
     }
+    }   // worker
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
 
-    if (tid == 0) {
+    if (warp == 17) {
       // P2: dZ += W . EV      A = W K-major [128 x 64], B = EV MN-major (N = latent, K = 64 columns)
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       constexpr uint32_t ID = umma_idesc_bf16(128, KK, 0, 1);
-      const uint64_t dWk[2] = {umma_desc(sW0, 128, 1024), umma_desc(sW1, 128, 1024)};
+      const uint64_t wo = (uint64_t)wb * kWStep, so = (uint64_t)st * kStageStep;
+      const uint64_t dWk[2] = {umma_desc(sWb, 128, 1024), umma_desc(sWb + T::W_TILE, 128, 1024)};
       const uint64_t dEn[2] = {umma_desc(sStage0 + T::X_TILE, T::CPR * 128, 128),
                                umma_desc(sStage0 + T::X_TILE + T::EV_TILE, T::CPR * 128, 128)};
 #pragma unroll
       for (int t = 0; t < 3; ++t) {
-        const uint64_t a = dWk[t == 2 ? 1 : 0], b = dEn[t == 1 ? 1 : 0] + (uint64_t)st * kStageStep;
+        const uint64_t a = dWk[t == 2 ? 1 : 0] + wo, b = dEn[t == 1 ? 1 : 0] + so;
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-          umma_bf16(tm + T::TM_DZ, a + (uint64_t)(j * 16), b + (uint64_t)(j * (2 * T::CPR * 128 / 16)), ID,
-                    (i | t | j) ? 1u : 0u);
+          umma_bf16_elect(tm + T::TM_DZ, a + (uint64_t)(j * 16), b + (uint64_t)(j * (2 * T::CPR * 128 / 16)), ID,
+                          (i | t | j) ? 1u : 0u);
       }
-      umma_commit(bar_g);
-    } else if (tid == 32) {
-      // P3: GEV = W^T . [Z | 1]   A = W MN-major (M = 64 columns, K = 128 rows), B = Z MN-major (N = NZ)
+      umma_commit_elect(bar_g[wb]);
+      // chunk i-1 is fully consumed once its MMAs are done: refill its stage with chunk i+2
+      if (i >= 1 && i + 2 < n) {
+        mbar_wait(bar_g[(i - 1) & 1], (uint32_t)(((i - 1) >> 1) & 1));
+        if (elect_one()) issue_load(i + 2);
+        __syncwarp();
+      }
+    } else if (warp == 16) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      // P1 of the next chunk first: its result gates the next element-wise phase
+      if (i + 1 < n) {
+        wait_full(i + 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        issue_p1(i + 1);
+      }
+      // P3: GEV = W^T . [Z | 1]   A = W MN-major (M = 64 columns, K = 128 rows), B = Z MN-major (N = NZ)
       constexpr uint32_t ID = umma_idesc_bf16(64, T::NZ, 1, 1);
-      const uint64_t dWn[2] = {umma_desc(sW0, 1024, 128), umma_desc(sW1, 1024, 128)};
+      const uint64_t wo = (uint64_t)wb * kWStep;
+      const uint64_t dWn[2] = {umma_desc(sWb, 1024, 128), umma_desc(sWb + T::W_TILE, 1024, 128)};
       const uint64_t dZn[2] = {umma_desc(sZ0, T::ZCPR * 128, 128), umma_desc(sZ1, T::ZCPR * 128, 128)};
+      const uint32_t tg = tm + T::TM_GEV + (uint32_t)(wb * T::TM_GEV_STRIDE);
 #pragma unroll
       for (int t = 0; t < 3; ++t) {
-        const uint64_t a = dWn[t == 2 ? 1 : 0], b = dZn[t == 1 ? 1 : 0];
+        const uint64_t a = dWn[t == 2 ? 1 : 0] + wo, b = dZn[t == 1 ? 1 : 0];
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-          umma_bf16(tm + T::TM_GEV, a + (uint64_t)(j * (2048 / 16)), b + (uint64_t)(j * (2 * T::ZCPR * 128 / 16)), ID,
-                    (t | j) ? 1u : 0u);
+          umma_bf16_elect(tg, a + (uint64_t)(j * (2048 / 16)), b + (uint64_t)(j * (2 * T::ZCPR * 128 / 16)), ID,
+                          (t | j) ? 1u : 0u);
       }
-      umma_commit(bar_g);
-    } else if (tid == 64 && i + 1 < nch) {
-      // P1 of the next chunk keeps the tensor core busy during the flush below
-      mbar_wait(((i + 1) & 1) ? full1 : full0, (uint32_t)(((i + 1) >> 1) & 1));
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      issue_p1((i + 1) & 1);
+      umma_commit_elect(bar_g[wb]);
+    } else if (i >= 1) {
+      // workers: the previous chunk's MMAs have had a whole element-wise phase to finish
+      flush_gev(i - 1);
     }
-    __syncwarp();
-    mbar_wait(bar_g, (uint32_t)(i & 1));
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    if (tid == 96 && i + 2 < nch) issue_load(i + 2);      // this stage's inputs are fully consumed
-
-    // ---- flush GEV / Gphi of the chunk: accumulator row m sits in lane (m/16)*32 + m%16; the two
-    //      thread halves take the two halves of the latent range (the second also the ones column)
-    {
-      const int c = i * 64 + (warp & 3) * 16 + lane;
-      const bool act = lane < 16 && c < H;
-      float* ge = GEV + ((size_t)q * D + c) * REC;
-      const uint32_t ta = tm + lane_base + T::TM_GEV;
-      if constexpr (KK == 32) {
-        float g[24];
-        if (hcol == 0) {
-          tmem_ld<16>(ta, g);
-          if (act) {
-#pragma unroll
-            for (int k = 0; k < 16; k += 4)
-              if (k < KP) atomicAdd(reinterpret_cast<float4*>(ge + rec_pos(KP, SV, sv, k)), make_float4(g[k], g[k + 1], g[k + 2], g[k + 3]));
-          }
-        } else {
-          tmem_ld<16>(ta + 16, g);
-          tmem_ld<8>(ta + 32, g + 16);
-          if (act) {
-#pragma unroll
-            for (int k = 0; k < 16; k += 4)
-              if (16 + k < KP) atomicAdd(reinterpret_cast<float4*>(ge + rec_pos(KP, SV, sv, 16 + k)), make_float4(g[k], g[k + 1], g[k + 2], g[k + 3]));
-            atomicAdd(Gphi + ((size_t)q * D + c) * SV + sv, g[16]);
-          }
-        }
-      } else {              // KK == 16: latent dims in columns [0,16), the ones column at 16
-        float g[16];
-        if (hcol == 0) {
-          tmem_ld<16>(ta, g);
-          if (act) {
-#pragma unroll
-            for (int k = 0; k < KP; k += 4)
-              atomicAdd(reinterpret_cast<float4*>(ge + rec_pos(KP, SV, sv, k)), make_float4(g[k], g[k + 1], g[k + 2], g[k + 3]));
-          }
-        } else {
-          tmem_ld<8>(ta + 16, g);
-          if (act) atomicAdd(Gphi + ((size_t)q * D + c) * SV + sv, g[0]);
-        }
-      }
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   }
+  if (worker) {
+  flush_gev(n - 1);
 
-  // ---- dZ of the 128 rows (this CTA is the only writer of its (rows, draw) slice; the two thread
-  //      halves own the two halves of the latent range) and the row scalars
+  // ---- dZ of the 128 rows (several CTAs share a (rows, draw) slice when the column range is split:
+  //      atomics) and the row scalars; thread quarter hq owns a quarter of the latent range
   {
-    constexpr int HK = KK / 2;
-    float dzv[HK];
-    const uint32_t ta = tm + lane_base + T::TM_DZ + HK * hcol;
-    if constexpr (HK == 16) tmem_ld<16>(ta, dzv); else tmem_ld<8>(ta, dzv);
+    constexpr int QK = KK / 4;                 // 8 or 4
+    float dzv[8];
+    tmem_ld<8>(tm + lane_base + T::TM_DZ + (QK == 8 ? 8 * hq : 8 * (hq >> 1)), dzv);
     if (row < nrows) {
       float* dp = dzacc + ((size_t)q * nrows + row) * REC;
 #pragma unroll
-      for (int k = 0; k < HK; k += 4) {
-        const int kk = HK * hcol + k;
-        if (kk < KP) {
-          float4* p = reinterpret_cast<float4*>(dp + rec_pos(KP, SV, sv, kk));
-          float4 v = *p;
-          v.x += dzv[k]; v.y += dzv[k + 1]; v.z += dzv[k + 2]; v.w += dzv[k + 3];
-          *p = v;
-        }
+      for (int k = 0; k < QK; k += 4) {
+        const int kk = QK * hq + k;
+        const int src = (QK == 8) ? k : 4 * (hq & 1) + k;
+        if (kk < KP)
+          atomicAdd(reinterpret_cast<float4*>(dp + rec_pos(KP, SV, sv, kk)),
+                    make_float4(dzv[src], dzv[src + 1], dzv[src + 2], dzv[src + 3]));
       }
-      float* ra = rowacc + ((size_t)q * nrows + row) * 4 * SV;
-      atomicAdd(ra + 0 * SV + sv, xlog2 * 0.6931471805599453f);          // two threads per row
-      if (badacc != 0.f) atomicAdd(ra + 3 * SV + sv, 1.0f);              // (also true for NaN)
+      atomicAdd(rowacc + ((size_t)q * nrows + row) * 4 * SV + sv, xlog2 * 0.6931471805599453f);
     }
   }
+  }   // worker
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 3) {
@@ -472,9 +484,16 @@ static int launch_hot_tile(const void* xhot, const void* EVt, const float* z, in
     if (e != cudaSuccess) return (int)e;
     attr = true;
   }
-  dim3 grid((nrows + 127) / 128, S);
+  // one CTA per SM: cut the hot columns into ranges so that the grid is several waves of 148 CTAs
+  const int nch = (H + 63) / 64, items = ((nrows + 127) / 128) * S;
+  int splits = (6 * 148 + items - 1) / items;
+  if (splits > nch) splits = nch;
+  if (splits < 1) splits = 1;
+  const int per = (nch + splits - 1) / splits;
+  splits = (nch + per - 1) / per;
+  dim3 grid((nrows + 127) / 128, S, splits);
   hot_tile_kernel<KP, SV><<<grid, kTileThreads, T::SMEM, st>>>((const unsigned char*)xhot, (const unsigned char*)EVt, z, nrows, D,
-                                                     H, (H + 63) / 64, dzacc, rowacc, GEV, Gphi);
+                                                              H, nch, per, dzacc, rowacc, GEV, Gphi);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? SPMF_OK : (int)e;
 }

@@ -41,6 +41,46 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
       : "memory");
 }
 
+// Warp-convergent forms: EVERY lane of the warp executes the statement, one elected lane issues.
+// Issuing from a divergent `if (tid == X)` makes the compiler wrap each tcgen05.mma in an
+// elect/branch "waterfall" loop (~10 dependent instructions per MMA); issued convergently it is
+// ELECT + a predicated UTCHMMA.  elect.sync picks the same (lowest active) lane every time, which
+// tcgen05.commit relies on (it tracks the MMAs of the executing thread).
+__device__ __forceinline__ void umma_bf16_elect(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, e;\n\t"
+      ".reg .b32 r;\n\t"
+      "elect.sync r|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_elect(uint32_t mbar) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred e;\n\t"
+      ".reg .b32 r;\n\t"
+      "elect.sync r|e, 0xffffffff;\n\t"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+      "}\n" ::"r"(mbar)
+      : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred e;\n\t"
+      ".reg .b32 r;\n\t"
+      "elect.sync r|e, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, e;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void umma_commit(uint32_t mbar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar)
                : "memory");
