@@ -43,7 +43,9 @@ struct HotTile {
   static constexpr int Z_TILE = 128 * ZCPR * 16;
   static constexpr int W_TILE = 128 * 64 * 2;
   static constexpr int NSTAGE = 3;                      // chunk inputs in flight
-  static constexpr int SMEM = NSTAGE * STAGE + 2 * Z_TILE + 4 * W_TILE + 128;   // W (hi, lo) double buffered
+  static constexpr int G_STRIDE = KK + 4;               // floats per staged GEV row (latent | 1 | pad): conflict-free
+  static constexpr int G_BYTES = 64 * G_STRIDE * 4;
+  static constexpr int SMEM = NSTAGE * STAGE + 2 * Z_TILE + 4 * W_TILE + G_BYTES + 128;   // W (hi, lo) double buffered
   // tensor-memory columns: S | dZ | GEV buffer 0 | GEV buffer 1
   static constexpr int TM_S = 0, TM_DZ = 64, TM_GEV = 64 + KK, TM_GEV_STRIDE = NZ;
   static constexpr int TM_COLS = 256;                   // power of two >= 64 + KK + 2 NZ (<= 176)
@@ -258,30 +260,42 @@ hot_tile_kernel(const unsigned char* __restrict__ xhot, const unsigned char* __r
     }
     umma_commit_elect(bar_s);
   };
-  // flush GEV / Gphi of local chunk i: accumulator row m sits in lane (m/16)*32 + m%16; thread quarters
-  // 0/1 take the two halves of the latent range, quarter 2 the ones column
+  // flush GEV / Gphi of local chunk i.  Accumulator row m (a column of the chunk) sits in tensor-memory
+  // lane (m/16)*32 + m%16, so a lane-owner store would scatter 16 lanes over 16 different records;
+  // instead the tile is staged through shared memory and written out by all 512 workers, 8
+  // consecutive threads per column (coalesced vector reductions).
+  float* const gst = reinterpret_cast<float*>(pWb + 4 * T::W_TILE);
   auto flush_gev = [&](int i) {
     mbar_wait(bar_g[i & 1], (uint32_t)((i >> 1) & 1));
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const int c = (c_begin + i) * 64 + (warp & 3) * 16 + lane;
-    const bool act = lane < 16 && c < H;
-    float* ge = GEV + ((size_t)q * D + c) * REC;
     const uint32_t ta = tm + lane_base + T::TM_GEV + (uint32_t)((i & 1) * T::TM_GEV_STRIDE);
+    const int m = (warp & 3) * 16 + lane;          // column of the chunk held by this lane (lane < 16)
     float g[16];
     if (hq < 2) {
       constexpr int HK = KK / 2;              // 16 or 8 latent dims per quarter
       if constexpr (HK == 16) tmem_ld<16>(ta + HK * hq, g); else tmem_ld<8>(ta + HK * hq, g);
-      if (act) {
+      if (lane < 16) {
 #pragma unroll
         for (int k = 0; k < HK; k += 4)
-          if (HK * hq + k < KP)
-            atomicAdd(reinterpret_cast<float4*>(ge + rec_pos(KP, SV, sv, HK * hq + k)), make_float4(g[k], g[k + 1], g[k + 2], g[k + 3]));
+          *reinterpret_cast<float4*>(gst + m * T::G_STRIDE + HK * hq + k) = make_float4(g[k], g[k + 1], g[k + 2], g[k + 3]);
       }
     } else if (hq == 2) {
       tmem_ld<8>(ta + KK, g);
-      if (act) atomicAdd(Gphi + ((size_t)q * D + c) * SV + sv, g[0]);
+      if (lane < 16) gst[m * T::G_STRIDE + KK] = g[0];
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    asm volatile("bar.sync 1, %0;" ::"n"(kTileWorkThreads) : "memory");
+    {
+      const int cl = tid >> 3, k = (tid & 7) * 4;          // 8 threads per column, 4 latent dims each
+      const int c = (c_begin + i) * 64 + cl;
+      if (c < H) {
+        if (k < KP) {
+          const float4 v = *reinterpret_cast<const float4*>(gst + cl * T::G_STRIDE + k);
+          atomicAdd(reinterpret_cast<float4*>(GEV + ((size_t)q * D + c) * REC + rec_pos(KP, SV, sv, k)), v);
+        }
+        if ((tid & 7) == 7) atomicAdd(Gphi + ((size_t)q * D + c) * SV + sv, gst[cl * T::G_STRIDE + KK]);
+      }
+    }
   };
 
   if (warp == 17) {
@@ -401,6 +415,7 @@ hot_tile_kernel(const unsigned char* __restrict__ xhot, const unsigned char* __r
     }
   }
   if (worker) {
+  asm volatile("bar.sync 1, %0;" ::"n"(kTileWorkThreads) : "memory");   // staging tile free (previous flush read out)
   flush_gev(n - 1);
 
   // ---- dZ of the 128 rows (several CTAs share a (rows, draw) slice when the column range is split:
