@@ -37,18 +37,22 @@ struct HotTile {
   static constexpr int ZCPR = CPR + 1;                  // Z rows carry one more chunk: the ones column
   static constexpr int NZ = KK + 8;                     // N of P3: latent dims | 1 | 7 zeros
   static constexpr int EV_TILE = 64 * KK * 2;           // bytes of one bf16 term
-  static constexpr int EV_BLOCK = 2 * EV_TILE + 256;    // hi | lo | phi[64] (fp32)
+  // EV block = one [64 columns][hi latent | lo latent] core-matrix tile (2*CPR chunks per row) + phi[64]:
+  // hi and lo side by side so that [hi | lo] is ONE MN-major operand of width 2*KK (term merging)
+  static constexpr int EV_BLOCK = 2 * EV_TILE + 256;
   static constexpr int X_TILE = kTileABytes;            // 128 x 64 bf16 counts
   static constexpr int STAGE = X_TILE + EV_BLOCK;
-  static constexpr int Z_TILE = 128 * ZCPR * 16;
+  static constexpr int Z_TILE = 128 * ZCPR * 16;        // per term; the two terms share rows: [hi | 1 | lo | 0]
+  static constexpr int ZCPR2 = 2 * ZCPR;                // chunks per row of the combined Z tile
   static constexpr int W_TILE = 128 * 64 * 2;
   static constexpr int NSTAGE = 3;                      // chunk inputs in flight
   static constexpr int G_STRIDE = KK + 4;               // floats per staged GEV row (latent | 1 | pad): conflict-free
   static constexpr int G_BYTES = 64 * G_STRIDE * 4;
   static constexpr int SMEM = NSTAGE * STAGE + 2 * Z_TILE + 4 * W_TILE + G_BYTES + 128;   // W (hi, lo) double buffered
-  // tensor-memory columns: S | dZ | GEV buffer 0 | GEV buffer 1
-  static constexpr int TM_S = 0, TM_DZ = 64, TM_GEV = 64 + KK, TM_GEV_STRIDE = NZ;
-  static constexpr int TM_COLS = 256;                   // power of two >= 64 + KK + 2 NZ (<= 176)
+  // tensor-memory columns: S | dZ (a | b) | GEV buffer 0 (a | b) | GEV buffer 1 (a | b); the "b" halves
+  // receive the hi.lo products of the merged MMAs and are added at read-out
+  static constexpr int TM_S = 0, TM_DZ = 64, TM_GEV = 64 + 2 * KK, TM_GEV_STRIDE = 2 * NZ;
+  static constexpr int TM_COLS = 512;                   // power of two >= 64 + 2 KK + 4 NZ (<= 288)
 };
 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {     // a -> low half
@@ -119,9 +123,8 @@ hot_ev_tiles_kernel(const float* __restrict__ EV, const float* __restrict__ PH, 
       hi[p] = pack_bf16(x[2 * p], x[2 * p + 1]);
       lo[p] = pack_bf16(x[2 * p] - bf16_lo(hi[p]), x[2 * p + 1] - bf16_hi(hi[p]));
     }
-    const uint32_t o = core_off_g(c, j, T::CPR);
-    *reinterpret_cast<uint4*>(blk + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-    *reinterpret_cast<uint4*>(blk + T::EV_TILE + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    *reinterpret_cast<uint4*>(blk + core_off_g(c, j, 2 * T::CPR)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(blk + core_off_g(c, T::CPR + j, 2 * T::CPR)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
     if (j == 0)     // padding columns get rate 1 (their counts are 0, so they contribute nothing)
       reinterpret_cast<float*>(blk + 2 * T::EV_TILE)[c] = d < H ? __ldg(PH + ((size_t)q * D + d) * SV + sv) : 1.f;
   }
@@ -169,11 +172,10 @@ hot_tile_kernel(const unsigned char* __restrict__ xhot, const unsigned char* __r
 
   // shared-memory map: [stage 0..2 | Z hi | Z lo | W0 hi | W0 lo | W1 hi | W1 lo]
   const uint32_t sStage0 = sbase;
-  const uint32_t sZ0 = sbase + (uint32_t)(T::NSTAGE * T::STAGE), sZ1 = sZ0 + (uint32_t)T::Z_TILE;
-  const uint32_t sWb = sZ1 + (uint32_t)T::Z_TILE;                    // W buffer b: hi at sWb + b*2*W_TILE, lo + W_TILE
+  const uint32_t sZ0 = sbase + (uint32_t)(T::NSTAGE * T::STAGE);      // combined Z tile, 2*Z_TILE bytes
+  const uint32_t sWb = sZ0 + 2u * (uint32_t)T::Z_TILE;               // W buffer b: hi at sWb + b*2*W_TILE, lo + W_TILE
   unsigned char* const pZ0 = sp + T::NSTAGE * T::STAGE;
-  unsigned char* const pZ1 = pZ0 + T::Z_TILE;
-  unsigned char* const pWb = pZ1 + T::Z_TILE;
+  unsigned char* const pWb = pZ0 + 2 * T::Z_TILE;
 
   uint32_t full[T::NSTAGE];
 #pragma unroll
@@ -221,9 +223,8 @@ hot_tile_kernel(const unsigned char* __restrict__ xhot, const unsigned char* __r
         hi[p] = pack_bf16(a, b);
         lo[p] = pack_bf16(a - bf16_lo(hi[p]), b - bf16_hi(hi[p]));
       }
-      const uint32_t o = core_off_g(rt, j, T::ZCPR);
-      *reinterpret_cast<uint4*>(pZ0 + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-      *reinterpret_cast<uint4*>(pZ1 + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      *reinterpret_cast<uint4*>(pZ0 + core_off_g(rt, j, T::ZCPR2)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<uint4*>(pZ0 + core_off_g(rt, T::ZCPR + j, T::ZCPR2)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
     }
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -248,9 +249,9 @@ hot_tile_kernel(const unsigned char* __restrict__ xhot, const unsigned char* __r
   auto issue_p1 = [&](int i) {
     constexpr uint32_t ID = umma_idesc_bf16(128, 64, 0, 0);
     const uint64_t so = (uint64_t)(i % T::NSTAGE) * kStageStep;
-    const uint64_t dZk[2] = {umma_desc(sZ0, 128, T::ZCPR * 128), umma_desc(sZ1, 128, T::ZCPR * 128)};
-    const uint64_t dEk[2] = {umma_desc(sStage0 + T::X_TILE, 128, T::CPR * 128),
-                             umma_desc(sStage0 + T::X_TILE + T::EV_TILE, 128, T::CPR * 128)};
+    const uint64_t dZk[2] = {umma_desc(sZ0, 128, T::ZCPR2 * 128), umma_desc(sZ0 + T::ZCPR * 128, 128, T::ZCPR2 * 128)};
+    const uint64_t dEk[2] = {umma_desc(sStage0 + T::X_TILE, 128, 2 * T::CPR * 128),
+                             umma_desc(sStage0 + T::X_TILE + T::CPR * 128, 128, 2 * T::CPR * 128)};
 #pragma unroll
     for (int t = 0; t < 3; ++t) {
       const uint64_t a = dZk[t == 2 ? 1 : 0], b = dEk[t == 1 ? 1 : 0] + so;
@@ -273,11 +274,19 @@ hot_tile_kernel(const unsigned char* __restrict__ xhot, const unsigned char* __r
     float g[16];
     if (hq < 2) {
       constexpr int HK = KK / 2;              // 16 or 8 latent dims per quarter
-      if constexpr (HK == 16) tmem_ld<16>(ta + HK * hq, g); else tmem_ld<8>(ta + HK * hq, g);
+      float gb[16];                           // the hi.lo half of the merged MMA
+      if constexpr (HK == 16) {
+        tmem_ld<16>(ta + HK * hq, g);
+        tmem_ld<16>(ta + T::NZ + HK * hq, gb);
+      } else {
+        tmem_ld<8>(ta + HK * hq, g);
+        tmem_ld<8>(ta + T::NZ + HK * hq, gb);
+      }
       if (lane < 16) {
 #pragma unroll
         for (int k = 0; k < HK; k += 4)
-          *reinterpret_cast<float4*>(gst + m * T::G_STRIDE + HK * hq + k) = make_float4(g[k], g[k + 1], g[k + 2], g[k + 3]);
+          *reinterpret_cast<float4*>(gst + m * T::G_STRIDE + HK * hq + k) =
+              make_float4(g[k] + gb[k], g[k + 1] + gb[k + 1], g[k + 2] + gb[k + 2], g[k + 3] + gb[k + 3]);
       }
     } else if (hq == 2) {
       tmem_ld<8>(ta + KK, g);
@@ -366,19 +375,19 @@ hot_tile_kernel(const unsigned char* __restrict__ xhot, const unsigned char* __r
     if (warp == 17) {
       // P2: dZ += W . EV      A = W K-major [128 x 64], B = EV MN-major (N = latent, K = 64 columns)
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      constexpr uint32_t ID = umma_idesc_bf16(128, KK, 0, 1);
+      // two MMAs per k-step instead of three: W_hi . [EV_hi | EV_lo] (N = 2 KK, second half -> dZ_b)
+      // and W_lo . EV_hi (N = KK, into dZ_a): the W operand is fetched twice, not three times
+      constexpr uint32_t IDa = umma_idesc_bf16(128, 2 * KK, 0, 1), IDb = umma_idesc_bf16(128, KK, 0, 1);
       const uint64_t wo = (uint64_t)wb * kWStep, so = (uint64_t)st * kStageStep;
-      const uint64_t dWk[2] = {umma_desc(sWb, 128, 1024), umma_desc(sWb + T::W_TILE, 128, 1024)};
-      const uint64_t dEn[2] = {umma_desc(sStage0 + T::X_TILE, T::CPR * 128, 128),
-                               umma_desc(sStage0 + T::X_TILE + T::EV_TILE, T::CPR * 128, 128)};
+      const uint64_t dWh = umma_desc(sWb, 128, 1024) + wo, dWl = umma_desc(sWb + T::W_TILE, 128, 1024) + wo;
+      const uint64_t dEn = umma_desc(sStage0 + T::X_TILE, 2 * T::CPR * 128, 128) + so;     // MN-major, k-group = 8 columns
+      constexpr uint64_t kEStep = (uint64_t)(2 * 2 * T::CPR * 128 / 16);                   // 16 columns
 #pragma unroll
-      for (int t = 0; t < 3; ++t) {
-        const uint64_t a = dWk[t == 2 ? 1 : 0] + wo, b = dEn[t == 1 ? 1 : 0] + so;
+      for (int j = 0; j < 4; ++j)
+        umma_bf16_elect(tm + T::TM_DZ, dWh + (uint64_t)(j * 16), dEn + j * kEStep, IDa, (i | j) ? 1u : 0u);
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          umma_bf16_elect(tm + T::TM_DZ, a + (uint64_t)(j * 16), b + (uint64_t)(j * (2 * T::CPR * 128 / 16)), ID,
-                          (i | t | j) ? 1u : 0u);
-      }
+      for (int j = 0; j < 4; ++j)
+        umma_bf16_elect(tm + T::TM_DZ, dWl + (uint64_t)(j * 16), dEn + j * kEStep, IDb, 1u);
       umma_commit_elect(bar_g[wb]);
       // chunk i-1 is fully consumed once its MMAs are done: refill its stage with chunk i+2
       if (i >= 1 && i + 2 < n) {
@@ -395,19 +404,19 @@ hot_tile_kernel(const unsigned char* __restrict__ xhot, const unsigned char* __r
         issue_p1(i + 1);
       }
       // P3: GEV = W^T . [Z | 1]   A = W MN-major (M = 64 columns, K = 128 rows), B = Z MN-major (N = NZ)
-      constexpr uint32_t ID = umma_idesc_bf16(64, T::NZ, 1, 1);
+      // merged the same way: W_hi^T . [Z_hi | 1 | Z_lo | 0] (N = 2 NZ) and W_lo^T . [Z_hi | 1] (N = NZ)
+      constexpr uint32_t IDa = umma_idesc_bf16(64, 2 * T::NZ, 1, 1), IDb = umma_idesc_bf16(64, T::NZ, 1, 1);
       const uint64_t wo = (uint64_t)wb * kWStep;
-      const uint64_t dWn[2] = {umma_desc(sWb, 1024, 128), umma_desc(sWb + T::W_TILE, 1024, 128)};
-      const uint64_t dZn[2] = {umma_desc(sZ0, T::ZCPR * 128, 128), umma_desc(sZ1, T::ZCPR * 128, 128)};
+      const uint64_t dWh = umma_desc(sWb, 1024, 128) + wo, dWl = umma_desc(sWb + T::W_TILE, 1024, 128) + wo;
+      const uint64_t dZn = umma_desc(sZ0, T::ZCPR2 * 128, 128);
+      constexpr uint64_t kZStep = (uint64_t)(2 * T::ZCPR2 * 128 / 16);                      // 16 rows
       const uint32_t tg = tm + T::TM_GEV + (uint32_t)(wb * T::TM_GEV_STRIDE);
 #pragma unroll
-      for (int t = 0; t < 3; ++t) {
-        const uint64_t a = dWn[t == 2 ? 1 : 0] + wo, b = dZn[t == 1 ? 1 : 0];
+      for (int j = 0; j < 8; ++j)
+        umma_bf16_elect(tg, dWh + (uint64_t)(j * (2048 / 16)), dZn + j * kZStep, IDa, j ? 1u : 0u);
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          umma_bf16_elect(tg, a + (uint64_t)(j * (2048 / 16)), b + (uint64_t)(j * (2 * T::ZCPR * 128 / 16)), ID,
-                          (t | j) ? 1u : 0u);
-      }
+      for (int j = 0; j < 8; ++j)
+        umma_bf16_elect(tg, dWl + (uint64_t)(j * (2048 / 16)), dZn + j * kZStep, IDb, 1u);
       umma_commit_elect(bar_g[wb]);
     } else if (i >= 1) {
       // workers: the previous chunk's MMAs have had a whole element-wise phase to finish
@@ -422,8 +431,11 @@ hot_tile_kernel(const unsigned char* __restrict__ xhot, const unsigned char* __r
   //      atomics) and the row scalars; thread quarter hq owns a quarter of the latent range
   {
     constexpr int QK = KK / 4;                 // 8 or 4
-    float dzv[8];
+    float dzv[8], dzb[8];
     tmem_ld<8>(tm + lane_base + T::TM_DZ + (QK == 8 ? 8 * hq : 8 * (hq >> 1)), dzv);
+    tmem_ld<8>(tm + lane_base + T::TM_DZ + KK + (QK == 8 ? 8 * hq : 8 * (hq >> 1)), dzb);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) dzv[k] += dzb[k];
     if (row < nrows) {
       float* dp = dzacc + ((size_t)q * nrows + row) * REC;
 #pragma unroll
