@@ -226,9 +226,18 @@ def main():
     batches = list(shard.iter_batches(B))
     eng = model._engine_for(S)
     hybrid = eng.hot_cols > 0 and eng.hybrid_ok
-    for b in batches:
+    prep_ms = None
+    for bi, b in enumerate(batches):
         if hybrid:
-            b.ensure_hot(eng.rank, eng.hot_cols)     # ranked CSR/CSC + dense bf16 hot block, built once
+            if bi == 2:                                # time one build of the hybrid form (after warm-up)
+                torch.cuda.synchronize()
+                p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                p0.record()
+            b.ensure_hot(eng.rank, eng.hot_cols, hot_csc=(eng.hot_mode != 2))   # ranked CSR/CSC + dense bf16 hot block
+            if bi == 2:
+                p1.record()
+                torch.cuda.synchronize()
+                prep_ms = p0.elapsed_time(p1)
         else:
             b.ensure_csc()
     eng.ws.ensure_rows(B)
@@ -289,7 +298,7 @@ def main():
         src = (hbatches[(start + i) % len(hbatches)] for i in range(n))
         prev = None
         tlast = time.perf_counter()
-        for i, db in enumerate(prefetch_to_device(src, dev, hot=(model.col_rank, model.hot_cols) if hybrid else None)):
+        for i, db in enumerate(prefetch_to_device(src, dev, hot=(model.col_rank, model.hot_cols, eng.hot_mode != 2) if hybrid else None)):
             if os.environ.get("BENCH_DEBUG"):
                 tnow = time.perf_counter()
                 print(f"e2e iter {i} host dt {1e3 * (tnow - tlast):.2f} ms", file=sys.stderr)
@@ -362,6 +371,7 @@ def main():
                 "kernels": {k: {"ms": v["ms"], "alg_GBps": v["bytes"] / (v["ms"] * 1e-3) / 1e9,
                                 "fp32_TFLOPs": v["flop"] / (v["ms"] * 1e-3) / 1e12} for k, v in kern.items()},
                 "hot_cols": int(eng.hot_cols) if hybrid else 0, "umma_gemm_gradA": None,
+                "hot_prepare_ms_per_batch": prep_ms, "hot_mode": int(eng.hot_mode) if hybrid else 0,
                 "note": "gather/FMA-bound SpMM+SDDMM at K*S=128 channels: per nonzero 8 B of HBM vs ~2 KB of "
                         "L2/L1 gather and 12*K*S flop; fp32 FMA peak 74.4 TFLOP/s (148 SM x 128 lanes x 2 x 1.965 GHz)"}
 

@@ -877,13 +877,47 @@ __device__ __forceinline__ bool hot_covered(int r, float x, int H) {   // rank i
   return r < H && x > 0.f && __uint_as_float(__float_as_uint(x) & 0xffff0000u) == x;
 }
 
+// xthot = UMMA-tiled X^T[H][Bp] from xhot = UMMA-tiled X[nrows][Hp]: one CTA per 128 x 64 tile of xhot,
+// transposed through shared memory; the result is two contiguous 8 KiB half-tiles of xthot.  Covers
+// every element of xthot (padding included), so no memset is needed.
+__global__ void __launch_bounds__(256)
+hot_transpose_kernel(const unsigned short* __restrict__ xhot, int hchunks, unsigned short* __restrict__ xthot,
+                     int bchunks, int xt_mtiles) {
+  __shared__ unsigned short t[128][66];                      // [row b][col h], padded
+  const int kcx = blockIdx.x, mtx = blockIdx.y;             // xhot tile: rows 128*mtx.., cols 64*kcx..
+  const unsigned short* src = xhot + ((size_t)mtx * hchunks + kcx) * (kTileABytes / 2);
+  // read the tile in its storage order (16-byte chunks), scatter into t[b][h]
+  for (int ch = threadIdx.x; ch < 1024; ch += blockDim.x) {
+    // (an odd number of column chunks: the grid is rounded up so the last m-tile of xthot is complete)
+    const uint4 v = kcx < hchunks ? *reinterpret_cast<const uint4*>(src + ch * 8) : make_uint4(0u, 0u, 0u, 0u);
+    const int rg = ch >> 6, kc8 = (ch >> 3) & 7, r = rg * 8 + (ch & 7);
+    const unsigned short* e = reinterpret_cast<const unsigned short*>(&v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t[r][kc8 * 8 + i] = e[i];
+  }
+  __syncthreads();
+  // xthot rows h = 64*kcx + (0..63) -> m-tile (64*kcx)/128, row offset (kcx & 1) * 64; k = b in chunks 2*mtx, 2*mtx+1
+  const int mt_t = kcx >> 1, rbase = (kcx & 1) * 64;
+  if (mt_t >= xt_mtiles) return;
+  for (int ch = threadIdx.x; ch < 1024; ch += blockDim.x) {   // 64 rows x 16 chunks of 8 k
+    const int hr = ch >> 4, kq = ch & 15;                     // local row h, 8-wide k group (b = 8*kq ..)
+    const int kc_t = 2 * mtx + (kq >> 3);
+    if (kc_t >= bchunks) continue;
+    unsigned short e[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) e[i] = t[kq * 8 + i][hr];
+    unsigned short* dst = xthot + ((size_t)mt_t * bchunks + kc_t) * (kTileABytes / 2) +
+                          (core_off(rbase + hr, kq & 7) >> 1);
+    *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(e);
+  }
+}
+
 __global__ void __launch_bounds__(128)
 hot_split_kernel(const long long* __restrict__ rowptr, const int* __restrict__ cols,
                  const float* __restrict__ vals, int nrows, const int* __restrict__ rank, int H,
                  long long* __restrict__ rowptr_out, int* __restrict__ cols_out,
                  float* __restrict__ vals_out, int* __restrict__ rowmid,
-                 unsigned short* __restrict__ xhot, long long hchunks, unsigned short* __restrict__ xthot,
-                 long long bchunks) {
+                 unsigned short* __restrict__ xhot, long long hchunks) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= nrows) return;
@@ -924,7 +958,6 @@ hot_split_kernel(const long long* __restrict__ rowptr, const int* __restrict__ c
       vals_out[o] = -x;
       const unsigned short hx = (unsigned short)(__float_as_uint(x) >> 16);
       xhot[tiledA_index(row, r, hchunks)] = hx;      // UMMA-tiled X[nrows][Hp]
-      xthot[tiledA_index(r, row, bchunks)] = hx;     // UMMA-tiled X^T[H][Bp]
     } else if (in) {
       const long long o = pu + __popc(mu & below);
       cols_out[o] = r;
@@ -1158,11 +1191,14 @@ int spmf_hot_split(const long long* rowptr, const int* cols, const float* vals, 
   cudaStream_t st = (cudaStream_t)stream;
   const long long hp = (H + 63) / 64 * 64, bp = ((long long)nrows + 63) / 64 * 64;
   cudaError_t e = cudaMemsetAsync(xhot, 0, (size_t)spmf_umma_tiled_a_elems(nrows, hp) * 2, st);
-  if (e == cudaSuccess) e = cudaMemsetAsync(xthot, 0, (size_t)spmf_umma_tiled_a_elems(H, bp) * 2, st);
   if (e != cudaSuccess) return (int)e;
   hot_split_kernel<<<(nrows + 3) / 4, 128, 0, st>>>(rowptr, cols, vals, nrows, rank, H, rowptr_out, cols_out,
-                                                    vals_out, rowmid, (unsigned short*)xhot, hp / 64,
-                                                    (unsigned short*)xthot, bp / 64);
+                                                    vals_out, rowmid, (unsigned short*)xhot, hp / 64);
+  SPMF_CHECK_LAUNCH();
+  // the transpose covers whole 128-row tiles of xhot: rows >= nrows are zero there (memset above)
+  dim3 tg((unsigned)((hp / 64 + 1) / 2 * 2), (unsigned)((nrows + 127) / 128));
+  hot_transpose_kernel<<<tg, 256, 0, st>>>((const unsigned short*)xhot, (int)(hp / 64), (unsigned short*)xthot,
+                                           (int)(bp / 64), (int)((H + 127) / 128));
   SPMF_CHECK_LAUNCH();
   return SPMF_OK;
 }

@@ -43,9 +43,10 @@ class HotSplit:
     colptr: torch.Tensor          # CSC of the entries NOT covered by the GEMMs: int32 [D+1]
     crows: torch.Tensor
     cvals: torch.Tensor
-    hcolptr: torch.Tensor         # CSC of the covered entries
+    hcolptr: torch.Tensor         # CSC of the covered entries (valid only if has_hot_csc)
     hcrows: torch.Tensor
     hcvals: torch.Tensor
+    has_hot_csc: bool = True
 
 
 @dataclass
@@ -64,10 +65,12 @@ class DeviceBatch:
     cvals: Optional[torch.Tensor] = None    # fp32 [nnz]
     hot: Optional[HotSplit] = None          # hybrid form (built for one (rank, H) ordering)
 
-    def ensure_hot(self, rank, H, bufs=None):
+    def ensure_hot(self, rank, H, bufs=None, hot_csc=True):
         """Build (once) the hybrid form for the column ordering `rank` (int32 [D] device tensor) with
-        H hot columns.  `bufs` may supply reusable staging (the streaming uploader)."""
-        if self.hot is not None and self.hot.H == H:
+        H hot columns.  `bufs` may supply reusable staging (the streaming uploader).  `hot_csc`: also
+        build the CSC copy of the covered entries (only the GEMM-only hybrid mode reads it; the tile
+        mode gets those gradients from the tensor-core kernel)."""
+        if self.hot is not None and self.hot.H == H and (self.hot.has_hot_csc or not hot_csc):
             return self.hot
         dev = self.vals.device
         n, nnz = self.nrows, self.nnz
@@ -93,13 +96,16 @@ class DeviceBatch:
                   _ptr(bufs["rowptr"]), _ptr(bufs["cols"]), _ptr(bufs["vals"]), _ptr(bufs["rowmid"]),
                   _ptr(bufs["xhot"]), _ptr(bufs["xthot"]), st)
         for part, pre in ((0, "h"), (1, "")):       # covered entries / the rest
+            if part == 0 and not hot_csc:
+                continue
             _abi.call("spmf_csr_to_csc_part", _ptr(bufs["rowptr"]), _ptr(bufs["rowmid"]), part, _ptr(bufs["cols"]),
                       _ptr(bufs["vals"]), n, self.D, _ptr(bufs[pre + "colptr"]), _ptr(bufs[pre + "crows"]),
                       _ptr(bufs[pre + "cvals"]), _ptr(bufs["scratch"]), st)
         self.hot = HotSplit(H=H, rowptr=bufs["rowptr"], cols=bufs["cols"], vals=bufs["vals"],
                             rowmid=bufs["rowmid"], xhot=bufs["xhot"], xthot=bufs["xthot"],
                             colptr=bufs["colptr"], crows=bufs["crows"], cvals=bufs["cvals"],
-                            hcolptr=bufs["hcolptr"], hcrows=bufs["hcrows"], hcvals=bufs["hcvals"])
+                            hcolptr=bufs["hcolptr"], hcrows=bufs["hcrows"], hcvals=bufs["hcvals"],
+                            has_hot_csc=bool(hot_csc))
         return self.hot
 
     def ensure_csc(self):
@@ -350,7 +356,9 @@ class BatchUploader:
 
     def __init__(self, device, D, max_rows=0, max_nnz=0, hot=None):
         self.device, self.D = torch.device(device), int(D)
-        self.hot = hot if (hot is not None and hot[0] is not None and hot[1] > 0) else None   # (rank, H)
+        # hot = (rank, H[, need_hot_csc])
+        self.hot = hot if (hot is not None and hot[0] is not None and hot[1] > 0) else None
+        self.hot_csc = bool(hot[2]) if (self.hot is not None and len(hot) > 2) else True
         self._alloc(max_rows, max_nnz)
 
     def _alloc(self, rows, nnz):
@@ -410,7 +418,7 @@ class BatchUploader:
                       _ptr(self.lgam), st)
             db = DeviceBatch(rowptr=self.rowptr[:n + 1], cols=self.cols, vals=self.vals, rowsum=self.rowsum[:n],
                              lgam=self.lgam[:n], nrows=n, nnz=nnz, D=self.D)
-            db.ensure_hot(self.hot[0], int(self.hot[1]), bufs=self.hot_bufs)
+            db.ensure_hot(self.hot[0], int(self.hot[1]), bufs=self.hot_bufs, hot_csc=self.hot_csc)
             return db
         _abi.call("spmf_prepare_batch", _ptr(c16), _ptr(v16), _ptr(self.rowptr), _ptr(self.cols),
                   _ptr(self.vals), n, nnz, self.D, _ptr(self.rowsum), _ptr(self.lgam), _ptr(self.colptr),
@@ -432,7 +440,7 @@ def prefetch_to_device(host_batches, device, depth=2, hot=None):
     # staging buffers and the copy stream persist across calls: no allocation once warmed up
     pool = _PREFETCH_POOL.setdefault(str(device), {"stream": torch.cuda.Stream(device=device), "ups": {}})
     copy, ups = pool["stream"], pool["ups"]
-    hot_key = None if hot is None or hot[0] is None or hot[1] <= 0 else (hot[0].data_ptr(), int(hot[1]))
+    hot_key = None if hot is None or hot[0] is None or hot[1] <= 0 else (hot[0].data_ptr(), int(hot[1]), tuple(hot[2:]))
     freed = [None] * depth
     queue = []
 

@@ -235,7 +235,7 @@ class AdviEngine:
             self._args = None
         hybrid = self.hot_cols > 0 and self.hybrid_ok and self.rank is not None and batch.nnz > 0
         if hybrid:
-            h = batch.ensure_hot(self.rank, self.hot_cols)
+            h = batch.ensure_hot(self.rank, self.hot_cols, hot_csc=(self.hot_mode != 2))
             if w.ensure_hybrid(self.hot_cols, batch.nrows):
                 self._args = None
         else:

@@ -200,6 +200,11 @@ class PoissonFactorization:
         self._choose_hot_columns(colnnz, float(nrows_all.item()))
         self._set_scales_from_stats(colsum.cpu(), colnnz.cpu())
 
+    def _hot_mode(self):
+        for eng in self._engines.values():
+            return eng.hot_mode
+        return int(os.environ.get("SPMF_HOT_MODE", "2"))
+
     def _choose_hot_columns(self, colnnz, nrows):
         """Column ordering for the hybrid step: features ranked by how many rows populate them; the
         H columns populated in >= hot_density of the rows form the tensor-core block.  Identical on
@@ -476,7 +481,7 @@ class PoissonFactorization:
         c = first[self.count_key] if isinstance(first, dict) else first
         if isinstance(c, HostCsrBatch):
             return prefetch_to_device((b[self.count_key] if isinstance(b, dict) else b for b in chained),
-                                      self.device, hot=(self.col_rank, self.hot_cols))
+                                      self.device, hot=(self.col_rank, self.hot_cols, self._hot_mode() != 2))
         return chained
 
     @staticmethod
