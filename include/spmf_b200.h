@@ -160,10 +160,11 @@ int spmf_umma_tile_a(const void* src_bf16, long long ld, int M, int Kd, void* ds
  * the others from rowmid[row] on) and the dense hot block as UMMA-tiled bf16: xhot = X[nrows][Hp] and
  * its transpose xthot = X^T[H][Bp] (Hp = ceil64(H), Bp = ceil64(nrows); sizes from
  * spmf_umma_tiled_a_elems; both zeroed here).  Covered = rank < H and the count is exactly
- * representable in bf16. */
+ * representable in bf16.  rowsum / lgam (both or neither): also emit the per-row constants of
+ * spmf_csr_row_consts in the same pass. */
 int spmf_hot_split(const long long* rowptr, const int* cols, const float* vals, int nrows, long long nnz,
                    const int* rank, int H, long long* rowptr_out, int* cols_out, float* vals_out, int* rowmid,
-                   void* xhot, void* xthot, void* stream);
+                   void* xhot, void* xthot, float* rowsum, float* lgam, void* stream);
 /* fp32 src[NQ][R][C] (row stride lds) -> UMMA-tiled B3 operand dst[NQ] with k = source row (i.e. the
  * transpose), hi+mid+lo = src to 24 bits; k in [R, Rpad) is written as zeros.  C % 32 == 0, Rpad % 64 == 0. */
 int spmf_split3_transpose(const float* src, long long lds, long long src_qstride, int R, int Rpad, int C,
@@ -281,6 +282,7 @@ typedef struct spmf_step_args {
    * (spmf_hot_tile) instead of the gather kernels; EVt = workspace of spmf_hot_tile_scratch_bytes */
   int hot_mode;
   void* EVt;
+  void *ev_tile0, *ev_tile1;       /* optional events around spmf_hot_tile (bench instrumentation) */
 } spmf_step_args;
 int spmf_advi_step(const spmf_step_args* args);
 /* widen a compact batch (either 16-bit source may be NULL), build its row constants and CSC copy */

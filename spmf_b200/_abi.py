@@ -77,7 +77,7 @@ _SIGS = {
     "spmf_umma_tiled_a_index": (i64, [i64, i64, i64]),
     "spmf_umma_tile_a": (i32, [p, i64, i32, i32, p, p]),
     "spmf_umma_probe": (i32, [p, i32, p, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, p, p]),
-    "spmf_hot_split": (i32, [p, p, p, i32, i64, p, i32, p, p, p, p, p, p, p]),
+    "spmf_hot_split": (i32, [p, p, p, i32, i64, p, i32, p, p, p, p, p, p, p, p, p]),
     "spmf_split3_transpose": (i32, [p, i64, i64, i32, i32, i32, p, i64, i32, p]),
     "spmf_umma_gemm3": (i32, [p, i64, i32, p, i64, p, i64, i64, i32, i32, i32, i32, p]),
     "spmf_csr_rows_hybrid": (i32, [p, p, p, p, p, p, f32, i32, i32, i32, i32, i32, p, p, p, p, p, p, p, p]),
@@ -115,7 +115,7 @@ class StepArgs(C.Structure):
         + [(n, p) for n in ("rowmid", "hot_colptr", "hot_crows", "hot_cvals", "xhot", "xthot", "ApT3", "dzrT3",
                             "ev_gemm0", "ev_gemm1", "aux_stream1", "aux_stream2", "ev_aux_fork", "ev_aux_join1",
                             "ev_aux_join2")]
-        + [("hot_mode", i32), ("EVt", p)]
+        + [("hot_mode", i32), ("EVt", p), ("ev_tile0", p), ("ev_tile1", p)]
     )
 
 

@@ -917,31 +917,59 @@ hot_split_kernel(const long long* __restrict__ rowptr, const int* __restrict__ c
                  const float* __restrict__ vals, int nrows, const int* __restrict__ rank, int H,
                  long long* __restrict__ rowptr_out, int* __restrict__ cols_out,
                  float* __restrict__ vals_out, int* __restrict__ rowmid,
-                 unsigned short* __restrict__ xhot, long long hchunks) {
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (row >= nrows) return;
+                 unsigned short* __restrict__ xhot, long long hchunks, float* __restrict__ rowsum,
+                 float* __restrict__ lgam) {
+  // one CTA per row; its four warps take four contiguous quarters of the row (the kernel is a chain
+  // of dependent gathers per 32 entries: more warps per row = more of them in flight)
+  __shared__ int s_cov[4];
+  __shared__ float s_sum[4], s_lg[4];
+  const int row = blockIdx.x;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const long long base = rowptr[0];
   const long long j0 = rowptr[row], j1 = rowptr[row + 1];
   const long long o0 = j0 - base;
-  if (lane == 0) {
+  if (threadIdx.x == 0) {
     rowptr_out[row] = o0;
     if (row == nrows - 1) rowptr_out[nrows] = j1 - base;
   }
-  // pass 1: number of covered entries
+  const long long n = j1 - j0;
+  const long long seg = (n + 127) / 128 * 32;               // entries per warp, a multiple of 32
+  const long long a0 = min(j1, j0 + w * seg), a1 = min(j1, a0 + seg);
+  // pass 1: covered entries of my quarter (and, if asked, the row constants of spmf_csr_row_consts)
   int ncov = 0;
-  for (long long j = j0 + lane; j < j1; j += 32) {
+  float rs = 0.f, rl = 0.f;
+  for (long long j = a0 + lane; j < a1; j += 32) {
     const int r = rank ? __ldg(rank + __ldg(cols + j)) : __ldg(cols + j);
-    ncov += hot_covered(r, __ldg(vals + j), H) ? 1 : 0;
+    const float x = __ldg(vals + j);
+    ncov += hot_covered(r, x, H) ? 1 : 0;
+    if (rowsum) { rs += x; rl += lgamma1p_count(x); }
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) ncov += __shfl_xor_sync(0xffffffffu, ncov, o);
-  if (lane == 0) rowmid[row] = ncov;
-  // pass 2: stable partition
-  long long pc = o0, pu = o0 + ncov;
-  for (long long jb = j0; jb < j1; jb += 32) {
+  for (int o = 16; o > 0; o >>= 1) {
+    ncov += __shfl_xor_sync(0xffffffffu, ncov, o);
+    rs += __shfl_xor_sync(0xffffffffu, rs, o);
+    rl += __shfl_xor_sync(0xffffffffu, rl, o);
+  }
+  if (lane == 0) { s_cov[w] = ncov; s_sum[w] = rs; s_lg[w] = rl; }
+  __syncthreads();
+  int cov_before = 0, cov_total = 0;
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    if (t < w) cov_before += s_cov[t];
+    cov_total += s_cov[t];
+  }
+  if (threadIdx.x == 0) {
+    rowmid[row] = cov_total;
+    if (rowsum) {
+      rowsum[row] = (s_sum[0] + s_sum[1]) + (s_sum[2] + s_sum[3]);
+      lgam[row] = (s_lg[0] + s_lg[1]) + (s_lg[2] + s_lg[3]);
+    }
+  }
+  // pass 2: stable partition -- covered entries first (negated), the others after cov_total
+  long long pc = o0 + cov_before, pu = o0 + cov_total + ((a0 - j0) - cov_before);
+  for (long long jb = a0; jb < a1; jb += 32) {
     const long long j = jb + lane;
-    const bool in = j < j1;
+    const bool in = j < a1;
     int r = 0;
     float x = 0.f;
     if (in) {
@@ -956,8 +984,7 @@ hot_split_kernel(const long long* __restrict__ rowptr, const int* __restrict__ c
       const long long o = pc + __popc(mc & below);
       cols_out[o] = r;
       vals_out[o] = -x;
-      const unsigned short hx = (unsigned short)(__float_as_uint(x) >> 16);
-      xhot[tiledA_index(row, r, hchunks)] = hx;      // UMMA-tiled X[nrows][Hp]
+      xhot[tiledA_index(row, r, hchunks)] = (unsigned short)(__float_as_uint(x) >> 16);   // UMMA-tiled X[nrows][Hp]
     } else if (in) {
       const long long o = pu + __popc(mu & below);
       cols_out[o] = r;
@@ -1184,16 +1211,17 @@ int spmf_csc_cols_hybrid(const int* hot_colptr, const int* hot_rows, const float
 // xhot[b][rank] / xthot[rank][b] receive the covered values (both pre-zeroed here).
 int spmf_hot_split(const long long* rowptr, const int* cols, const float* vals, int nrows, long long nnz,
                    const int* rank, int H, long long* rowptr_out, int* cols_out, float* vals_out, int* rowmid,
-                   void* xhot, void* xthot, void* stream) {
+                   void* xhot, void* xthot, float* rowsum, float* lgam, void* stream) {
   if (!rowptr || !cols || !vals || !rowptr_out || !cols_out || !vals_out || !rowmid || !xhot || !xthot)
     return SPMF_ERR_BAD_ARG;
+  if ((rowsum == nullptr) != (lgam == nullptr)) return SPMF_ERR_BAD_ARG;
   if (nrows <= 0 || nnz < 0 || H <= 0) return SPMF_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   const long long hp = (H + 63) / 64 * 64, bp = ((long long)nrows + 63) / 64 * 64;
   cudaError_t e = cudaMemsetAsync(xhot, 0, (size_t)spmf_umma_tiled_a_elems(nrows, hp) * 2, st);
   if (e != cudaSuccess) return (int)e;
-  hot_split_kernel<<<(nrows + 3) / 4, 128, 0, st>>>(rowptr, cols, vals, nrows, rank, H, rowptr_out, cols_out,
-                                                    vals_out, rowmid, (unsigned short*)xhot, hp / 64);
+  hot_split_kernel<<<nrows, 128, 0, st>>>(rowptr, cols, vals, nrows, rank, H, rowptr_out, cols_out,
+                                                    vals_out, rowmid, (unsigned short*)xhot, hp / 64, rowsum, lgam);
   SPMF_CHECK_LAUNCH();
   // the transpose covers whole 128-row tiles of xhot: rows >= nrows are zero there (memset above)
   dim3 tg((unsigned)((hp / 64 + 1) / 2 * 2), (unsigned)((nrows + 127) / 128));

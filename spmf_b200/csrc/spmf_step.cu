@@ -72,7 +72,9 @@ int spmf_advi_step(const spmf_step_args* a) {
       STEP_TRY(spmf_zero_col_grads(a->GAp, a->GEV, a->Gph, D, K, S, hot));
       STEP_TRY(spmf_csr_rows_cold(a->rowptr, a->cols, a->vals, a->rowmid, a->rowsum, a->inv_xi, a->scale_rows,
                                   a->nrows, D, K, S, a->Ap, a->EV, a->PH, a->z, a->dzr, a->rowacc, hot));
+      if (a->ev_tile0) CUDA_TRY(cudaEventRecord((cudaEvent_t)a->ev_tile0, hot));
       STEP_TRY(spmf_hot_tile(a->xhot, a->EVt, a->z, a->nrows, D, H, K, S, a->dzr, a->rowacc, a->GEV, a->Gph, hot));
+      if (a->ev_tile1) CUDA_TRY(cudaEventRecord((cudaEvent_t)a->ev_tile1, hot));
       STEP_TRY(spmf_rows_finish(a->rowsum, a->lgam, a->inv_xi, a->scale_rows, a->nrows, K, S, a->vsum, a->z, a->dzr,
                                 a->rowacc, hot));
     } else {

@@ -65,7 +65,7 @@ class DeviceBatch:
     cvals: Optional[torch.Tensor] = None    # fp32 [nnz]
     hot: Optional[HotSplit] = None          # hybrid form (built for one (rank, H) ordering)
 
-    def ensure_hot(self, rank, H, bufs=None, hot_csc=True):
+    def ensure_hot(self, rank, H, bufs=None, hot_csc=True, row_consts=False):
         """Build (once) the hybrid form for the column ordering `rank` (int32 [D] device tensor) with
         H hot columns.  `bufs` may supply reusable staging (the streaming uploader).  `hot_csc`: also
         build the CSC copy of the covered entries (only the GEMM-only hybrid mode reads it; the tile
@@ -94,7 +94,8 @@ class DeviceBatch:
         st = _stream()
         _abi.call("spmf_hot_split", _ptr(self.rowptr), _ptr(self.cols), _ptr(self.vals), n, nnz, _ptr(rank), H,
                   _ptr(bufs["rowptr"]), _ptr(bufs["cols"]), _ptr(bufs["vals"]), _ptr(bufs["rowmid"]),
-                  _ptr(bufs["xhot"]), _ptr(bufs["xthot"]), st)
+                  _ptr(bufs["xhot"]), _ptr(bufs["xthot"]),
+                  _ptr(self.rowsum) if row_consts else None, _ptr(self.lgam) if row_consts else None, st)
         for part, pre in ((0, "h"), (1, "")):       # covered entries / the rest
             if part == 0 and not hot_csc:
                 continue
@@ -414,11 +415,10 @@ class BatchUploader:
             # its CSC copy -- all on this (copy) stream, into persistent staging
             if c16 is not None or v16 is not None:
                 _abi.call("spmf_csr_unpack16", _ptr(c16), _ptr(v16), nnz, _ptr(self.cols), _ptr(self.vals), st)
-            _abi.call("spmf_csr_row_consts", _ptr(self.rowptr), _ptr(self.vals), n, _ptr(self.rowsum),
-                      _ptr(self.lgam), st)
             db = DeviceBatch(rowptr=self.rowptr[:n + 1], cols=self.cols, vals=self.vals, rowsum=self.rowsum[:n],
                              lgam=self.lgam[:n], nrows=n, nnz=nnz, D=self.D)
-            db.ensure_hot(self.hot[0], int(self.hot[1]), bufs=self.hot_bufs, hot_csc=self.hot_csc)
+            db.ensure_hot(self.hot[0], int(self.hot[1]), bufs=self.hot_bufs, hot_csc=self.hot_csc,
+                          row_consts=True)          # row constants come out of the split's first pass
             return db
         _abi.call("spmf_prepare_batch", _ptr(c16), _ptr(v16), _ptr(self.rowptr), _ptr(self.cols),
                   _ptr(self.vals), n, nnz, self.D, _ptr(self.rowsum), _ptr(self.lgam), _ptr(self.colptr),

@@ -266,7 +266,7 @@ class AdviEngine:
         a.caller_stream = _stream()
         ev = self.kernel_events
         if ev is not None:
-            tev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
+            tev = [torch.cuda.Event(enable_timing=True) for _ in range(8)]
             for e in tev:
                 e.record()
             a.ev_rows0, a.ev_rows1, a.ev_cols0, a.ev_cols1 = (e.cuda_event for e in tev[:4])
@@ -275,10 +275,16 @@ class AdviEngine:
             if hybrid:
                 a.ev_gemm0, a.ev_gemm1 = tev[4].cuda_event, tev[5].cuda_event
                 ev.setdefault("umma_gemm_gradA", []).append((tev[4], tev[5], batch.nnz, batch.nrows))
+                if self.hot_mode == 2:
+                    a.ev_tile0, a.ev_tile1 = tev[6].cuda_event, tev[7].cuda_event
+                    ev.setdefault("hot_tile", []).append((tev[6], tev[7], batch.nnz, batch.nrows))
+                else:
+                    a.ev_tile0 = a.ev_tile1 = None
             else:
-                a.ev_gemm0 = a.ev_gemm1 = None
+                a.ev_gemm0 = a.ev_gemm1 = a.ev_tile0 = a.ev_tile1 = None
         else:
             a.ev_rows0 = a.ev_rows1 = a.ev_cols0 = a.ev_cols1 = a.ev_gemm0 = a.ev_gemm1 = None
+            a.ev_tile0 = a.ev_tile1 = None
         _abi.call("spmf_advi_step", a)
         if fresh_noise:
             self.rng_step += 1

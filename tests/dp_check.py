@@ -75,7 +75,7 @@ def main():
             idx = v.reshape(-1).numpy()
             e_grad = max(e_grad, np.abs(g1[idx] - g2[idx]).max() / (np.abs(g1[idx]).max() + 1e-300))
         print(f"dp_check world={world}: loss single={l1:.6f} dp={l2:.6f} rel={e_loss:.2e}; worst grad rel={e_grad:.2e}")
-        ok = e_loss < 1e-6 and e_grad < 2e-5
+        ok = e_loss < 1e-6 and e_grad < 5e-5      # (hybrid bf16-split tensor-core path vs the fp32 gather path)
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.broadcast(flag, src=0)
     dist.destroy_process_group()
