@@ -458,32 +458,51 @@ hot_tile_kernel(const unsigned char* __restrict__ xhot, const unsigned char* __r
 }
 
 // ---- row finalisation after the cold row pass and the hot tile kernel have both added into dzr / rowacc
+// One warp per (row, draw group): lane l owns the 4 consecutive record floats [4l, 4l+4) -- one k-vector
+// of one draw (spmf_record.cuh) -- so the record is read and written with coalesced 16-byte accesses.
 template <int KP, int SV>
 __global__ void __launch_bounds__(128)
 rows_finish_kernel(const float* __restrict__ rowsum, const float* __restrict__ lgam, float inv_xi, int scale_rows,
                    int nrows, const double* __restrict__ vsum, const float* __restrict__ z,
                    float* __restrict__ dzr, float* __restrict__ rowacc) {
   constexpr int REC = SV * KP;
-  // one thread per (row, draw): KP latent dims
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  const int row = t / SV, sv = t - row * SV, q = blockIdx.y;
+  static_assert(KP >= 4 && REC <= 128, "rows_finish: one warp covers a record");
+  const RecMap rm = rec_map(KP);
+  const int row = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31, q = blockIdx.y;
   if (row >= nrows) return;
   const float r = scale_rows ? rowsum[row] * inv_xi : 1.f;
-  const float* zp = z + ((size_t)q * nrows + row) * REC;
-  float* dp = dzr + ((size_t)q * nrows + row) * REC;
-  const double* vs = vsum + (size_t)q * REC;
+  const bool act = lane * 4 < REC;
+  const int sv = act ? (lane / rm.RG) % SV : -1;            // draw of this lane's k-vector
   float zv = 0.f, z2 = 0.f;
-  for (int k = 0; k < KP; ++k) {
-    const int p = rec_pos(KP, SV, sv, k);
-    const float zz = zp[p], v = (float)vs[p];
-    zv = fmaf(zz, v, zv);
-    z2 = fmaf(zz, zz, z2);
-    dp[p] = r * (dp[p] - v - zz);          // dL/dz incl. the HalfNormal(1) z prior (poisson.py:599-604)
+  if (act) {
+    const size_t o = ((size_t)q * nrows + row) * REC + lane * 4;
+    const float4 zz = *reinterpret_cast<const float4*>(z + o);
+    float4 d = *reinterpret_cast<float4*>(dzr + o);
+    const double* vs = vsum + (size_t)q * REC + lane * 4;
+    const float v0 = (float)vs[0], v1 = (float)vs[1], v2 = (float)vs[2], v3 = (float)vs[3];
+    zv = zz.x * v0 + zz.y * v1 + zz.z * v2 + zz.w * v3;
+    z2 = zz.x * zz.x + zz.y * zz.y + zz.z * zz.z + zz.w * zz.w;
+    d.x = r * (d.x - v0 - zz.x);           // dL/dz incl. the HalfNormal(1) z prior (poisson.py:599-604)
+    d.y = r * (d.y - v1 - zz.y);
+    d.z = r * (d.z - v2 - zz.z);
+    d.w = r * (d.w - v3 - zz.w);
+    *reinterpret_cast<float4*>(dzr + o) = d;
   }
   float* ra = rowacc + ((size_t)q * nrows + row) * 4 * SV;
-  ra[0 * SV + sv] -= lgam[row];
-  ra[1 * SV + sv] = zv;
-  ra[2 * SV + sv] = z2;
+#pragma unroll
+  for (int s = 0; s < SV; ++s) {
+    float a = sv == s ? zv : 0.f, b = sv == s ? z2 : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, o);
+      b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    if (lane == 0) {
+      ra[0 * SV + s] -= lgam[row];
+      ra[1 * SV + s] = a;
+      ra[2 * SV + s] = b;
+    }
+  }
 }
 
 }  // namespace spmf
@@ -564,7 +583,7 @@ int spmf_rows_finish(const float* rowsum, const float* lgam, float inv_xi, int s
   if (!rowsum || !lgam || !vsum || !z || !dzr || !rowacc || nrows <= 0 || K <= 0 || K > SPMF_MAX_K || S <= 0)
     return SPMF_ERR_BAD_ARG;
   const int KP = spmf_kpad(K), SV = spmf_draw_vec(S), NQ = S / SV;
-  dim3 grid((unsigned)(((long long)nrows * SV + 127) / 128), NQ);
+  dim3 grid((unsigned)((nrows + 3) / 4), NQ);
   cudaStream_t st = (cudaStream_t)stream;
 #define CALL_RF(KPC, SVC) rows_finish_kernel<KPC, SVC><<<grid, 128, 0, st>>>(rowsum, lgam, inv_xi, scale_rows, nrows, vsum, z, dzr, rowacc)
   HT_DISPATCH(KP, SV, CALL_RF);
