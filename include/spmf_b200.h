@@ -111,6 +111,11 @@ int spmf_adam_step(float* params, const float* grads, float* m, float* v, long l
                    float beta1, float beta2, float eps, int step, float clip_value, float grad_scale,
                    void* stream);
 int spmf_sumsq(const float* g, long long n, float* tmp, double* out, double* scratch, void* stream);
+/* multi-GPU: after the all-reduce of the gradient block, fold the summed ('z','x') (hi,lo) float pairs
+ * in the block's scalar slack back into parts[S][16], recompute the per-draw loss ([15]), write the
+ * mean loss, zero the slack.  S <= 64. */
+int spmf_unpack_parts(float* comm_slack, int slack_floats, int S, float w_entropy, float w_prior, double* parts,
+                      double* loss_out, void* stream);
 int spmf_colsum(const float* in, long long n, int c, int q, double* out, double* scratch, void* stream);
 
 /* ---- data formats either side of the path ---- */

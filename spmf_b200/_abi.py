@@ -58,6 +58,7 @@ _SIGS = {
     "spmf_backward_params": (i32, [p, p, p, p, i32, i32, i32, p, p, p, p, p, p, f32, f32, f32, f32, f32,
                                    f32, i32, p, p, p, p, p]),
     "spmf_adam_step": (i32, [p, p, p, p, i64, f32, f32, f32, f32, i32, f32, f32, p]),
+    "spmf_unpack_parts": (i32, [p, i32, i32, f32, f32, p, p, p]),
     "spmf_sumsq": (i32, [p, i64, p, p, p, p]),
     "spmf_colsum": (i32, [p, i64, i32, i32, p, p, p]),
     "spmf_csr_colstats": (i32, [p, p, i64, i32, p, p, p]),

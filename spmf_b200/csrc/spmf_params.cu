@@ -347,6 +347,32 @@ __global__ void finalize_parts_kernel(int S, int SV, int K, const double* __rest
   }
 }
 
+// After the all-reduce of the gradient block: recombine the summed ('z','x') (hi,lo) pairs into
+// parts[s][13..14], recompute the per-draw loss, emit the mean loss, clear the scalar slack.
+__global__ void unpack_parts_kernel(int S, double w_entropy, double w_prior, float* __restrict__ comm, int slack,
+                                    double* __restrict__ parts, double* __restrict__ loss_out) {
+  __shared__ double sl[64];
+  const int s = threadIdx.x;
+  double l = 0.0;
+  if (s < S) {
+    double* o = parts + (long long)s * NUM_PARTS;
+    o[P_Z] = (double)comm[4 * s + 0] + (double)comm[4 * s + 1];
+    o[P_X] = (double)comm[4 * s + 2] + (double)comm[4 * s + 3];
+    double prior = 0.0;
+    for (int p = 0; p < P_LOGQ; ++p) prior += o[p];
+    l = w_entropy * o[P_LOGQ] - w_prior * prior - o[P_Z] - o[P_X];
+    o[15] = l;
+  }
+  if (s < 64) sl[s] = l;
+  __syncthreads();
+  for (int i = threadIdx.x; i < slack; i += blockDim.x) comm[i] = 0.f;
+  if (s == 0) {
+    double t = 0.0;
+    for (int i = 0; i < S && i < 64; ++i) t += sl[i];
+    *loss_out = t / (double)S;
+  }
+}
+
 // ------------------------------------------------------------------ Adam  [EXT L4]
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, long long n, float lr, float b1, float b2, float eps,
@@ -638,6 +664,15 @@ int spmf_adam_step(float* params, const float* grads, float* m, float* v, long l
   if (!params || !grads || !m || !v || n <= 0 || step <= 0) return SPMF_ERR_BAD_ARG;
   float bc1 = 1.f - powf(beta1, (float)step), bc2 = 1.f - powf(beta2, (float)step);
   adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(params, grads, m, v, n, lr, beta1, beta2, eps, bc1, bc2, clip_value, grad_scale);
+  SPMF_CHECK_LAUNCH();
+  return SPMF_OK;
+}
+
+int spmf_unpack_parts(float* comm_slack, int slack_floats, int S, float w_entropy, float w_prior, double* parts,
+                      double* loss_out, void* stream) {
+  if (!comm_slack || !parts || !loss_out || S <= 0 || S > 64 || slack_floats < 4 * S) return SPMF_ERR_BAD_ARG;
+  unpack_parts_kernel<<<1, 64, 0, (cudaStream_t)stream>>>(S, (double)w_entropy, (double)w_prior, comm_slack,
+                                                          slack_floats, parts, loss_out);
   SPMF_CHECK_LAUNCH();
   return SPMF_OK;
 }

@@ -46,5 +46,17 @@ def unpack_data_parts(eng, parts):
 def allreduce_step(eng, parts, group=None):
     """All-reduce gradients + data parts in one collective; returns the global loss (0-d tensor)."""
     dist.all_reduce(comm_block(eng), op=dist.ReduceOp.SUM, group=group)
+    dev = getattr(eng, "device", None)
+    if dev is not None and dev.type == "cuda" and eng.S <= 64:
+        # one launch instead of a handful of tiny tensor ops on the critical path between the
+        # collective and Adam
+        L = eng.layout
+        if getattr(eng, "_loss_buf", None) is None:
+            eng._loss_buf = torch.zeros(1, dtype=torch.float64, device=eng.device)
+        slack = eng.grads[L.comm_off: L.comm_off + L.comm_slack]
+        _abi.call("spmf_unpack_parts", slack.data_ptr(), L.comm_slack, eng.S, eng.entropy_weight, eng.prior_weight,
+                  parts.data_ptr(), eng._loss_buf.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        eng.launches += 1
+        return eng._loss_buf[0]
     unpack_data_parts(eng, parts)
     return parts[:, 15].mean()

@@ -101,7 +101,7 @@ class PoissonFactorization:
         # columns populated in at least this fraction of the rows form the dense "hot block" whose
         # count products and per-nonzero terms run on the tcgen05 tensor cores (0 = gather kernels only)
         if hot_density is None:
-            hot_density = float(os.environ.get("SPMF_HOT_DENSITY", "0.03"))
+            hot_density = float(os.environ.get("SPMF_HOT_DENSITY", "0.05"))
         self.hot_density = float(hot_density)
         self.col_rank = None        # int32 [D] device tensor: rank of each feature by population
         self.hot_cols = 0
