@@ -106,6 +106,20 @@ int spmf_backward_params(const float* params, const float* noise, const float* d
                          float w_entropy, float w_prior, int world_size, float* grads, double* parts,
                          float* scratch_f, double* scratch_d, void* stream);
 
+/* The same backward in two halves: `pre` = everything that does not depend on the data term (prior +
+ * entropy gradients of all 24 tensors, the loss parts) -- it can run on a side stream while the data
+ * term is being evaluated; `post` = the data half (u, v, w, s) + parts.  pre then post ==
+ * spmf_backward_params_ranked (the gradient is linear in the upstream data terms).  scr_d must not be
+ * shared with the reductions of the data term if the two run concurrently. */
+int spmf_backward_pre(const float* params, const float* noise, const float* dgda, const float* eta, int D, int K,
+                      int S, float batch_rows, float u_tau_scale, float s_tau_scale, float decay, float w_entropy,
+                      float w_prior, int world_size, float* grads, float* scr_f, double* scr_d, void* stream);
+int spmf_backward_post(const float* params, const float* noise, const float* eta, const int* rank, int D, int K,
+                       int S, const float* GAp, const float* GEVnz, const float* Gphinz, const double* zcolsum,
+                       const double* datasums, const double* phisum, float batch_rows, float u_tau_scale,
+                       float s_tau_scale, float decay, float w_entropy, float w_prior, int world_size,
+                       float* grads, double* parts, float* scr_f, const double* scr_d, void* stream);
+
 /* ---- optimiser [EXT L4: Adam + clip in bayesianquilts' batched_minimize] ---- */
 int spmf_adam_step(float* params, const float* grads, float* m, float* v, long long n, float lr,
                    float beta1, float beta2, float eps, int step, float clip_value, float grad_scale,
@@ -288,6 +302,11 @@ typedef struct spmf_step_args {
   int hot_mode;
   void* EVt;
   void *ev_tile0, *ev_tile1;       /* optional events around spmf_hot_tile (bench instrumentation) */
+  /* split backward: with scr_dpre (a second double scratch of spmf_backward_scratch_doubles) and
+   * ev_noise given, the data-independent half of the backward runs on the side stream under the data
+   * term; otherwise the one-pass backward runs after it */
+  double* scr_dpre;
+  void* ev_noise;
 } spmf_step_args;
 int spmf_advi_step(const spmf_step_args* args);
 /* widen a compact batch (either 16-bit source may be NULL), build its row constants and CSC copy */

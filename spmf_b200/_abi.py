@@ -57,6 +57,9 @@ _SIGS = {
     "spmf_gamma_draw_grad": (i32, [p, p, p, i32, i32, i32, u64, u32, p]),
     "spmf_backward_params": (i32, [p, p, p, p, i32, i32, i32, p, p, p, p, p, p, f32, f32, f32, f32, f32,
                                    f32, i32, p, p, p, p, p]),
+    "spmf_backward_pre": (i32, [p, p, p, p, i32, i32, i32, f32, f32, f32, f32, f32, f32, i32, p, p, p, p]),
+    "spmf_backward_post": (i32, [p, p, p, p, i32, i32, i32, p, p, p, p, p, p, f32, f32, f32, f32, f32, f32, i32,
+                                 p, p, p, p, p]),
     "spmf_adam_step": (i32, [p, p, p, p, i64, f32, f32, f32, f32, i32, f32, f32, p]),
     "spmf_unpack_parts": (i32, [p, i32, i32, f32, f32, p, p, p]),
     "spmf_sumsq": (i32, [p, i64, p, p, p, p]),
@@ -116,7 +119,7 @@ class StepArgs(C.Structure):
         + [(n, p) for n in ("rowmid", "hot_colptr", "hot_crows", "hot_cvals", "xhot", "xthot", "ApT3", "dzrT3",
                             "ev_gemm0", "ev_gemm1", "aux_stream1", "aux_stream2", "ev_aux_fork", "ev_aux_join1",
                             "ev_aux_join2")]
-        + [("hot_mode", i32), ("EVt", p), ("ev_tile0", p), ("ev_tile1", p)]
+        + [("hot_mode", i32), ("EVt", p), ("ev_tile0", p), ("ev_tile1", p), ("scr_dpre", p), ("ev_noise", p)]
     )
 
 

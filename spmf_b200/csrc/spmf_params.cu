@@ -149,7 +149,12 @@ __global__ void sample_kernel(Layout L, const float* __restrict__ P, const float
 // One warp per feature d, lanes over k: u, v, u_eta, u_eta_a.  Emits da[s][d] = sum_k GA' u / eta
 // (needed by the per-feature kernel), the per-(s,d,k) contribution to d prior_u / d u_tau, and
 // this feature's share of the prior / log q sums.
-template <int KK>
+// PRE = true: the data-independent half of the backward (prior + entropy terms of every tensor, all
+// loss parts) with the upstream data gradients taken as zero; it also stores, per (s,d,k), the three
+// factors the data half needs -- cu = a_d sigmoid'(u)/eta_d, cv = eta_d sigmoid'(v), uy = u/eta_d -- so
+// that backward_dk_post_kernel is a pure streaming pass.  The gradient is linear in the upstream
+// terms, so pre + post == the one-pass kernel.  PRE runs on the side stream under the data term.
+template <int KK, bool PRE>
 __global__ void __launch_bounds__(128, KK == 1 ? 6 : 3)
 backward_dk_kernel(Layout L, Hyper h, const float* __restrict__ P, const float* __restrict__ N,
                    const float* __restrict__ G, const float* __restrict__ eta,
@@ -157,11 +162,11 @@ backward_dk_kernel(Layout L, Hyper h, const float* __restrict__ P, const float* 
                    const float* __restrict__ GAp, const float* __restrict__ GEVnz,
                    const double* __restrict__ zcolsum, float* __restrict__ grads,
                    float* __restrict__ scr_utau, float* __restrict__ scr_parts,
-                   float* __restrict__ scr_da) {
+                   float* __restrict__ scr_da, float* __restrict__ fac) {
   const int lane = threadIdx.x & 31;
   const int d = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (d >= L.D) return;
-  const int dr = rank ? rank[d] : d;
+  const int dr = (!PRE && rank) ? rank[d] : d;
   LaneState<KK> st;
   lane_init<KK>(st, L, P, d, lane, h.decay);
   const NParam s0 = nparam_init(P[L.toff[S_LOC] + d], P[L.toff[S_RHO] + d]);
@@ -179,9 +184,24 @@ backward_dk_kernel(Layout L, Hyper h, const float* __restrict__ P, const float* 
         const int rp = rec_pos(KP, SV, sv, k);
         long long idx = ((long long)q * L.D + dr) * SV * KP + rp;
         DkUp up;
-        up.GAp = GAp[idx];
-        up.GEV = GEVnz[idx] - (float)zcolsum[(long long)q * SV * KP + rp];
+        if constexpr (PRE) {
+          up.GAp = 0.f;
+          up.GEV = 0.f;
+        } else {
+          up.GAp = GAp[idx];
+          up.GEV = GEVnz[idx] - (float)zcolsum[(long long)q * SV * KP + rp];
+        }
         DkOut o = lane_step<KK>(st, L, h, N, G, eta, d, lane, i, s, a_d, up);
+        if constexpr (PRE) {
+          const long long e = ((long long)s * L.D + d) * L.K + k;
+          const long long nsdk = (long long)L.S * L.D * L.K;
+          const NDraw ud = ndraw(st.u[i], N[L.noff[VAR_U] + e]);
+          const NDraw vd = ndraw(st.v[i], N[L.noff[VAR_V] + e]);
+          const float ieta = 1.f / eta[d];
+          fac[e] = a_d * ieta * ud.sg;
+          fac[nsdk + e] = eta[d] * vd.sg;
+          fac[2 * nsdk + e] = ud.y * ieta;
+        }
         da += o.da;
         scr_utau[((long long)s * L.D + d) * L.K + k] = o.dutau;
 #pragma unroll
@@ -192,7 +212,7 @@ backward_dk_kernel(Layout L, Hyper h, const float* __restrict__ P, const float* 
 #pragma unroll
     for (int j = 0; j < 5; ++j) pp[j] = warp_sum(pp[j]);
     if (lane == 0) {
-      scr_da[(long long)s * L.D + d] = da;
+      if constexpr (!PRE) scr_da[(long long)s * L.D + d] = da;
       float* o = scr_parts + ((long long)d * L.S + s) * NUM_PARTS;
 #pragma unroll
       for (int j = 0; j < NUM_PARTS; ++j) o[j] = 0.f;
@@ -214,6 +234,96 @@ backward_dk_kernel(Layout L, Hyper h, const float* __restrict__ P, const float* 
   }
 }
 
+// Data half of the (d,k) backward: u and v only.  grads += (1/S) sum_s of the upstream terms times the
+// stored factors (see PRE above); emits da[s][d] = sum_k GA' u / eta for the per-feature post kernel.
+template <int KK>
+__global__ void __launch_bounds__(128)
+backward_dk_post_kernel(Layout L, const float* __restrict__ P, const float* __restrict__ N,
+                        const int* __restrict__ rank, int SV, int KP, const float* __restrict__ GAp,
+                        const float* __restrict__ GEVnz, const double* __restrict__ zcolsum,
+                        const float* __restrict__ fac, float* __restrict__ grads, float* __restrict__ scr_da) {
+  const int lane = threadIdx.x & 31;
+  const int d = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (d >= L.D) return;
+  const int dr = rank ? rank[d] : d;
+  const long long nsdk = (long long)L.S * L.D * L.K;
+  float au[KK], aue[KK], av[KK], ave[KK];
+#pragma unroll
+  for (int i = 0; i < KK; ++i) { au[i] = 0.f; aue[i] = 0.f; av[i] = 0.f; ave[i] = 0.f; }
+  for (int s = 0; s < L.S; ++s) {
+    const int q = s / SV, sv = s - q * SV;
+    float da = 0.f;
+#pragma unroll
+    for (int i = 0; i < KK; ++i) {
+      const int k = lane + 32 * i;
+      if (k < L.K) {
+        const int rp = rec_pos(KP, SV, sv, k);
+        const long long idx = ((long long)q * L.D + dr) * SV * KP + rp;
+        const long long e = ((long long)s * L.D + d) * L.K + k;
+        const float ga = GAp[idx];
+        const float gv = GEVnz[idx] - (float)zcolsum[(long long)q * SV * KP + rp];
+        const float dtu = -ga * fac[e], dtv = -gv * fac[nsdk + e];
+        au[i] += dtu;
+        aue[i] = fmaf(dtu, N[L.noff[VAR_U] + e], aue[i]);
+        av[i] += dtv;
+        ave[i] = fmaf(dtv, N[L.noff[VAR_V] + e], ave[i]);
+        da = fmaf(ga, fac[2 * nsdk + e], da);
+      }
+    }
+    da = warp_sum(da);
+    if (lane == 0) scr_da[(long long)s * L.D + d] = da;
+  }
+  const float invS = 1.f / (float)L.S;
+#pragma unroll
+  for (int i = 0; i < KK; ++i) {
+    const int k = lane + 32 * i;
+    if (k < L.K) {
+      const long long e = (long long)d * L.K + k;
+      grads[L.toff[U_LOC] + e] += au[i] * invS;
+      grads[L.toff[U_RHO] + e] += aue[i] * invS * sigmoidf(P[L.toff[U_RHO] + e]);
+      grads[L.toff[V_LOC] + e] += av[i] * invS;
+      grads[L.toff[V_RHO] + e] += ave[i] * invS * sigmoidf(P[L.toff[V_RHO] + e]);
+    }
+  }
+}
+
+// Data half of the per-feature backward: w, s (poisson.py:661-663, 694-701 chain rule).
+__global__ void __launch_bounds__(128)
+backward_feat_post_kernel(Layout L, Hyper h, const float* __restrict__ P, const float* __restrict__ N,
+                          const float* __restrict__ eta, const int* __restrict__ rank, int SV,
+                          const float* __restrict__ Gphinz, const float* __restrict__ scr_da,
+                          float* __restrict__ grads) {
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= L.D) return;
+  const int dr = rank ? rank[d] : d;
+  const long long D = L.D;
+  FeatState f;
+  feat_init(f, L, P, d);
+  float aw = 0.f, awe = 0.f, a0 = 0.f, a0e = 0.f, a1 = 0.f, a1e = 0.f;
+  for (int s = 0; s < L.S; ++s) {
+    const int q = s / SV, sv = s - q * SV;
+    const FeatDraw fd = feat_draw(f, L, N, d, s);
+    const float da = scr_da[(long long)s * D + d];
+    const float Gphi = Gphinz[((long long)q * D + dr) * SV + sv] - h.batch_rows;     // d L / d phi_d
+    const float dw_data = eta[d] * fd.b * Gphi;                                     // phi = eta b w
+    const float db = eta[d] * fd.w.y * Gphi;
+    const float inv = 1.f / (fd.s0.y + fd.s1.y), inv2 = inv * inv;
+    const float ds0_data = (da - db) * fd.s1.y * inv2;
+    const float ds1_data = (db - da) * fd.s0.y * inv2;
+    const float tw = -dw_data * fd.w.sg, t0 = -ds0_data * fd.s0.sg, t1 = -ds1_data * fd.s1.sg;
+    aw += tw;  awe = fmaf(tw, N[L.noff[VAR_W] + s * D + d], awe);
+    a0 += t0;  a0e = fmaf(t0, N[L.noff[VAR_S] + s * 2 * D + d], a0e);
+    a1 += t1;  a1e = fmaf(t1, N[L.noff[VAR_S] + s * 2 * D + D + d], a1e);
+  }
+  const float invS = 1.f / (float)L.S;
+  grads[L.toff[W_LOC] + d] += aw * invS;
+  grads[L.toff[W_RHO] + d] += awe * invS * sigmoidf(P[L.toff[W_RHO] + d]);
+  grads[L.toff[S_LOC] + d] += a0 * invS;
+  grads[L.toff[S_RHO] + d] += a0e * invS * sigmoidf(P[L.toff[S_RHO] + d]);
+  grads[L.toff[S_LOC] + D + d] += a1 * invS;
+  grads[L.toff[S_RHO] + D + d] += a1e * invS * sigmoidf(P[L.toff[S_RHO] + D + d]);
+}
+
 // ------------------------------------------------------------------ backward, per-feature tensors
 // G = SV lanes per feature d, each taking every G-th draw: w, s, s_eta, s_tau, s_eta_a, s_tau_a
 // (runs after backward_dk_kernel).  Accumulators meet through a fixed xor butterfly.
@@ -226,20 +336,21 @@ backward_feat_kernel(Layout L, Hyper h, const float* __restrict__ P, const float
                      const float* __restrict__ G, const float* __restrict__ eta,
                      const int* __restrict__ rank, int SV,
                      const float* __restrict__ Gphinz, const float* __restrict__ scr_da,
-                     float* __restrict__ grads, float* __restrict__ scr_parts) {
+                     float* __restrict__ grads, float* __restrict__ scr_parts, int pre) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int dreal = t / SV, sg = t - dreal * SV;
   const bool valid = dreal < L.D;
   const int d = valid ? dreal : L.D - 1;           // out-of-range lanes shadow the last feature (no writes)
-  const int dr = rank ? rank[d] : d;
+  const int dr = (!pre && rank) ? rank[d] : d;
   FeatState f;
   feat_init(f, L, P, d);
   for (int s = sg; s < L.S; s += SV) {
     const int q = s / SV, sv = s - q * SV;
     FeatDraw fd = feat_draw(f, L, N, d, s);
     float fp[7];
-    feat_step(f, fd, L, h, N, G, eta, d, s, scr_da[(long long)s * L.D + d],
-              Gphinz[((long long)q * L.D + dr) * SV + sv], fp);
+    // pre: data-independent half (upstream da = 0, dL/dphi = 0); backward_feat_post_kernel adds the rest
+    feat_step(f, fd, L, h, N, G, eta, d, s, pre ? 0.f : scr_da[(long long)s * L.D + d],
+              pre ? h.batch_rows : Gphinz[((long long)q * L.D + dr) * SV + sv], fp);
     if (valid) {
       float* o = scr_parts + ((long long)d * L.S + s) * NUM_PARTS;
       o[P_W] = fp[0]; o[P_S] = fp[1]; o[P_SETA] = fp[2]; o[P_STAU] = fp[3];
@@ -629,10 +740,10 @@ int spmf_backward_params_ranked(const float* params, const float* noise, const f
   double* rscr = latparts + (long long)S * NUM_PARTS;
   float* scr_da = scr_lat + (long long)K * S * NUM_PARTS;
   dim3 grid((D + 3) / 4);
-  if (KP <= 32) backward_dk_kernel<1><<<grid, 128, 0, st>>>(L, h, params, noise, dgda, eta, rank, SV, KP, GAp, GEVnz, zcolsum, grads, scr_utau, scr_parts, scr_da);
-  else if (KP <= 64) backward_dk_kernel<2><<<grid, 128, 0, st>>>(L, h, params, noise, dgda, eta, rank, SV, KP, GAp, GEVnz, zcolsum, grads, scr_utau, scr_parts, scr_da);
-  else backward_dk_kernel<4><<<grid, 128, 0, st>>>(L, h, params, noise, dgda, eta, rank, SV, KP, GAp, GEVnz, zcolsum, grads, scr_utau, scr_parts, scr_da);
-  backward_feat_kernel<<<(int)(((long long)D * SV + 127) / 128), 128, 0, st>>>(L, h, params, noise, dgda, eta, rank, SV, Gphinz, scr_da, grads, scr_parts);
+  if (KP <= 32) backward_dk_kernel<1, false><<<grid, 128, 0, st>>>(L, h, params, noise, dgda, eta, rank, SV, KP, GAp, GEVnz, zcolsum, grads, scr_utau, scr_parts, scr_da, nullptr);
+  else if (KP <= 64) backward_dk_kernel<2, false><<<grid, 128, 0, st>>>(L, h, params, noise, dgda, eta, rank, SV, KP, GAp, GEVnz, zcolsum, grads, scr_utau, scr_parts, scr_da, nullptr);
+  else backward_dk_kernel<4, false><<<grid, 128, 0, st>>>(L, h, params, noise, dgda, eta, rank, SV, KP, GAp, GEVnz, zcolsum, grads, scr_utau, scr_parts, scr_da, nullptr);
+  backward_feat_kernel<<<(int)(((long long)D * SV + 127) / 128), 128, 0, st>>>(L, h, params, noise, dgda, eta, rank, SV, Gphinz, scr_da, grads, scr_parts, 0);
   SPMF_CHECK_LAUNCH();
   int rc = reduce_rows_pair(scr_utau, dutau, D, K, S, scr_parts, featparts, D, S * NUM_PARTS, 1, rscr, st);
   if (rc) return rc;
@@ -649,7 +760,70 @@ int spmf_backward_params_ranked(const float* params, const float* noise, const f
 }
 
 long long spmf_backward_scratch_floats(int D, int K, int S) {
-  return (long long)S * D * K + (long long)D * S * NUM_PARTS + (long long)K * S * NUM_PARTS + (long long)S * D;
+  // scr_utau | scr_parts | scr_lat | scr_da | fac (3 factors per (s,d,k), split backward only)
+  return 4LL * S * D * K + (long long)D * S * NUM_PARTS + (long long)K * S * NUM_PARTS + (long long)S * D;
+}
+
+/* Split backward: spmf_backward_pre = everything that does not depend on the data term (runs under it on
+ * a side stream), spmf_backward_post = the data half + the loss parts.  pre + post == spmf_backward_params. */
+int spmf_backward_pre(const float* params, const float* noise, const float* dgda, const float* eta, int D, int K,
+                      int S, float batch_rows, float u_tau_scale, float s_tau_scale, float decay, float w_entropy,
+                      float w_prior, int world_size, float* grads, float* scr_f, double* scr_d, void* stream) {
+  if (!params || !noise || !dgda || !eta || !grads || !scr_f || !scr_d) return SPMF_ERR_BAD_ARG;
+  if (D <= 0 || K <= 0 || S <= 0 || K > SPMF_MAX_K || world_size <= 0) return SPMF_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  Layout L = make_layout(D, K, S);
+  Hyper h = make_hyper(u_tau_scale, s_tau_scale, decay, w_entropy, w_prior, world_size, batch_rows);
+  const int KP = spmf_kpad(K), SV = spmf_draw_vec(S);
+  float* scr_utau = scr_f;
+  float* scr_parts = scr_utau + (long long)S * D * K;
+  float* scr_lat = scr_parts + (long long)D * S * NUM_PARTS;
+  float* scr_da = scr_lat + (long long)K * S * NUM_PARTS;
+  float* fac = scr_da + (long long)S * D;
+  double* dutau = scr_d;
+  double* featparts = dutau + (long long)S * K;
+  double* latparts = featparts + (long long)S * NUM_PARTS;
+  double* rscr = latparts + (long long)S * NUM_PARTS;
+  dim3 grid((D + 3) / 4);
+  if (KP <= 32) backward_dk_kernel<1, true><<<grid, 128, 0, st>>>(L, h, params, noise, dgda, eta, nullptr, SV, KP, nullptr, nullptr, nullptr, grads, scr_utau, scr_parts, scr_da, fac);
+  else if (KP <= 64) backward_dk_kernel<2, true><<<grid, 128, 0, st>>>(L, h, params, noise, dgda, eta, nullptr, SV, KP, nullptr, nullptr, nullptr, grads, scr_utau, scr_parts, scr_da, fac);
+  else backward_dk_kernel<4, true><<<grid, 128, 0, st>>>(L, h, params, noise, dgda, eta, nullptr, SV, KP, nullptr, nullptr, nullptr, grads, scr_utau, scr_parts, scr_da, fac);
+  backward_feat_kernel<<<(int)(((long long)D * SV + 127) / 128), 128, 0, st>>>(L, h, params, noise, dgda, eta, nullptr, SV, nullptr, nullptr, grads, scr_parts, 1);
+  SPMF_CHECK_LAUNCH();
+  int rc = reduce_rows_pair(scr_utau, dutau, D, K, S, scr_parts, featparts, D, S * NUM_PARTS, 1, rscr, st);
+  if (rc) return rc;
+  backward_lat_kernel<<<(K + 63) / 64, 64, 0, st>>>(L, h, params, noise, dgda, dutau, grads, scr_lat);
+  SPMF_CHECK_LAUNCH();
+  return reduce_rows<float>(scr_lat, latparts, rscr, K, S * NUM_PARTS, 1, st);
+}
+
+int spmf_backward_post(const float* params, const float* noise, const float* eta, const int* rank, int D, int K,
+                       int S, const float* GAp, const float* GEVnz, const float* Gphinz, const double* zcolsum,
+                       const double* datasums, const double* phisum, float batch_rows, float u_tau_scale,
+                       float s_tau_scale, float decay, float w_entropy, float w_prior, int world_size,
+                       float* grads, double* parts, float* scr_f, const double* scr_d, void* stream) {
+  if (!params || !noise || !eta || !GAp || !GEVnz || !Gphinz || !zcolsum || !datasums || !phisum || !grads ||
+      !parts || !scr_f || !scr_d)
+    return SPMF_ERR_BAD_ARG;
+  if (D <= 0 || K <= 0 || S <= 0 || K > SPMF_MAX_K || world_size <= 0) return SPMF_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  Layout L = make_layout(D, K, S);
+  Hyper h = make_hyper(u_tau_scale, s_tau_scale, decay, w_entropy, w_prior, world_size, batch_rows);
+  const int KP = spmf_kpad(K), SV = spmf_draw_vec(S);
+  float* scr_da = scr_f + (long long)S * D * K + (long long)D * S * NUM_PARTS + (long long)K * S * NUM_PARTS;
+  const float* fac = scr_da + (long long)S * D;
+  const double* featparts = scr_d + (long long)S * K;
+  const double* latparts = featparts + (long long)S * NUM_PARTS;
+  dim3 grid((D + 3) / 4);
+  if (KP <= 32) backward_dk_post_kernel<1><<<grid, 128, 0, st>>>(L, params, noise, rank, SV, KP, GAp, GEVnz, zcolsum, fac, grads, scr_da);
+  else if (KP <= 64) backward_dk_post_kernel<2><<<grid, 128, 0, st>>>(L, params, noise, rank, SV, KP, GAp, GEVnz, zcolsum, fac, grads, scr_da);
+  else backward_dk_post_kernel<4><<<grid, 128, 0, st>>>(L, params, noise, rank, SV, KP, GAp, GEVnz, zcolsum, fac, grads, scr_da);
+  backward_feat_post_kernel<<<(D + 127) / 128, 128, 0, st>>>(L, h, params, noise, eta, rank, SV, Gphinz, scr_da, grads);
+  finalize_parts_kernel<<<1, ((S + 31) / 32) * 32, 0, st>>>(S, SV, K, featparts, latparts, datasums, phisum,
+                                                           (double)batch_rows, (double)w_entropy, (double)w_prior,
+                                                           parts, grads + L.comm_off);
+  SPMF_CHECK_LAUNCH();
+  return SPMF_OK;
 }
 long long spmf_backward_scratch_doubles(int D, int K, int S) {
   long long c = (long long)S * NUM_PARTS;

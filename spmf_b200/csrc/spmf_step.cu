@@ -40,8 +40,6 @@ int spmf_advi_step(const spmf_step_args* a) {
     STEP_TRY(spmf_gamma_draw_grad(a->params, a->noise, a->dgda, D, K, S, a->seed, a->rng_step, side));
   else
     STEP_TRY(spmf_gamma_grad(a->params, a->noise, D, K, S, a->dgda, side));
-  if (side != hot) CUDA_TRY(cudaEventRecord((cudaEvent_t)a->ev_join, side));
-
   // ---- hot path
   const bool hybrid = a->hot_cols > 0;
   if (hybrid && (!a->rank || !a->rowmid || !a->xhot || !a->xthot || !a->ApT3 || !a->dzrT3 || !a->hot_colptr ||
@@ -49,6 +47,18 @@ int spmf_advi_step(const spmf_step_args* a) {
     return SPMF_ERR_BAD_ARG;
   if (a->fresh_noise)
     STEP_TRY(spmf_fill_noise(a->noise, a->params, D, K, S, a->seed, a->rng_step, SPMF_NOISE_NORMAL, hot));
+  // data-independent half of the backward: needs the noise only -> side stream, under the data term
+  const bool split_bwd = a->scr_dpre && (side == hot || a->ev_noise);
+  if (split_bwd) {
+    if (side != hot) {
+      CUDA_TRY(cudaEventRecord((cudaEvent_t)a->ev_noise, hot));
+      CUDA_TRY(cudaStreamWaitEvent(side, (cudaEvent_t)a->ev_noise, 0));
+    }
+    STEP_TRY(spmf_backward_pre(a->params, a->noise, a->dgda, a->eta, D, K, S, (float)a->nrows, a->u_tau_scale,
+                               a->s_tau_scale, a->decay, a->w_entropy, a->w_prior, a->world_size, a->grads,
+                               a->scr_f, a->scr_dpre, side));
+  }
+  if (side != hot) CUDA_TRY(cudaEventRecord((cudaEvent_t)a->ev_join, side));
   STEP_TRY(spmf_draw_operands_ranked(a->params, a->noise, a->eta, hybrid ? a->rank : nullptr, D, K, S, a->Ap, a->EV,
                                      a->PH, a->vsum, a->phisum, a->scr_d, hot));
   const int KP = spmf_kpad(K), SV = spmf_draw_vec(S), NQ = S / SV, REC = KP * SV;
@@ -125,10 +135,16 @@ int spmf_advi_step(const spmf_step_args* a) {
   }
   if (a->ev_cols1) CUDA_TRY(cudaEventRecord((cudaEvent_t)a->ev_cols1, hot));
   if (side != hot) CUDA_TRY(cudaStreamWaitEvent(hot, (cudaEvent_t)a->ev_join, 0));
-  STEP_TRY(spmf_backward_params_ranked(a->params, a->noise, a->dgda, a->eta, hybrid ? a->rank : nullptr, D, K, S,
-                                       a->GAp, a->GEV, a->Gph, a->zcolsum, a->datasums, a->phisum, (float)a->nrows,
-                                       a->u_tau_scale, a->s_tau_scale, a->decay, a->w_entropy, a->w_prior,
-                                       a->world_size, a->grads, a->parts, a->scr_f, a->scr_d, hot));
+  if (split_bwd)
+    STEP_TRY(spmf_backward_post(a->params, a->noise, a->eta, hybrid ? a->rank : nullptr, D, K, S, a->GAp, a->GEV,
+                                a->Gph, a->zcolsum, a->datasums, a->phisum, (float)a->nrows, a->u_tau_scale,
+                                a->s_tau_scale, a->decay, a->w_entropy, a->w_prior, a->world_size, a->grads,
+                                a->parts, a->scr_f, a->scr_dpre, hot));
+  else
+    STEP_TRY(spmf_backward_params_ranked(a->params, a->noise, a->dgda, a->eta, hybrid ? a->rank : nullptr, D, K, S,
+                                         a->GAp, a->GEV, a->Gph, a->zcolsum, a->datasums, a->phisum,
+                                         (float)a->nrows, a->u_tau_scale, a->s_tau_scale, a->decay, a->w_entropy,
+                                         a->w_prior, a->world_size, a->grads, a->parts, a->scr_f, a->scr_d, hot));
   if (a->adam_lr > 0.f) {
     if (a->world_size > 1) return SPMF_ERR_BAD_ARG;      // the all-reduce must come between backward and Adam
     // the scalar slack inside the gradient block is host-side bookkeeping, not a parameter gradient

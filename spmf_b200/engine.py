@@ -43,6 +43,7 @@ class StepWorkspace:
         nf, nd = _abi.backward_scratch(D, K, S)
         self.scr_f = torch.empty(nf, dtype=f32, device=device)
         self.scr_d = torch.empty(nd, dtype=f64, device=device)
+        self.scr_dpre = torch.empty(nd, dtype=f64, device=device)    # split backward: side-stream half
         self.parts = torch.zeros(S * _abi.NUM_PARTS, dtype=f64, device=device)
         self.ensure_rows(max_rows)
 
@@ -205,6 +206,8 @@ class AdviEngine:
             for name in ("Ap", "EV", "PH", "GAp", "GEV", "Gph", "scr_f", "vsum", "phisum", "zcolsum",
                          "datasums", "parts", "scr_d"):
                 setattr(a, name, _ptr(getattr(w, name)))
+            if os.environ.get("SPMF_SPLIT_BACKWARD", "1") != "0":
+                a.scr_dpre = _ptr(w.scr_dpre)
             if self.stream_mode == "prio":
                 self._hot = torch.cuda.Stream(device=self.device, priority=-1)
                 self._side = torch.cuda.Stream(device=self.device, priority=0)
@@ -213,6 +216,9 @@ class AdviEngine:
                     e.record()                       # materialise the cudaEvent_t handles
                 a.hot_stream, a.side_stream = self._hot.cuda_stream, self._side.cuda_stream
                 a.ev_fork, a.ev_join, a.ev_done = (e.cuda_event for e in self._sync_events)
+                self._ev_noise = torch.cuda.Event()
+                self._ev_noise.record()
+                a.ev_noise = self._ev_noise.cuda_event
                 # hybrid step: the GA' GEMM and the cold column pass run next to the hot column pass
                 self._aux = [torch.cuda.Stream(device=self.device, priority=-1) for _ in range(2)]
                 self._aux_events = [torch.cuda.Event() for _ in range(3)]
