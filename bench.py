@@ -110,7 +110,8 @@ def make_shard(wl, device, seed):
     from spmf_b200.data import CsrShard, synth_linear_dense, synth_noise_dense, synth_scrna_csr_device
     n = wl["rows"] * wl["nbatch"]
     if wl["kind"] == "scrna":
-        return synth_scrna_csr_device(n, wl["D"], wl["density"], seed=seed, device=device)
+        # one dataset, row-sharded: the gene profile is shared by all ranks, the cells are per rank
+        return synth_scrna_csr_device(n, wl["D"], wl["density"], seed=seed, device=device, gene_seed=1234 + 3)
     x = synth_linear_dense(n, wl["D"], seed=seed) if wl["kind"] == "linear" else synth_noise_dense(n, wl["D"], seed=seed)
     x[0, :] = x[0, :].clip(min=1)
     return CsrShard.from_dense(torch.from_numpy(x), device)

@@ -247,13 +247,17 @@ def synth_linear_dense(N, D, k_true=3, seed=0):
     return X
 
 
-def synth_scrna_csr_device(nrows, D, density=0.05, seed=0, device="cuda", sigma_gene=1.5, sigma_cell=0.5):
+def synth_scrna_csr_device(nrows, D, density=0.05, seed=0, device="cuda", sigma_gene=1.5, sigma_cell=0.5,
+                           gene_seed=None):
     """scRNA-seq shaped sparse counts on the device: x_bd ~ Poisson(c_b g_d),
     c_b ~ LogNormal(0, sigma_cell^2), g_d ~ LogNormal(m, sigma_gene^2) with m solved so the mean
-    P(x>0) equals `density`.  Returns a CsrShard.  Rows are generated in chunks to bound memory."""
+    P(x>0) equals `density`.  Returns a CsrShard.  Rows are generated in chunks to bound memory.
+    `gene_seed` fixes the gene profile g independently of `seed` (row shards of ONE dataset share
+    their genes: every rank passes the same gene_seed and its own seed)."""
     dev = torch.device(device)
     gen = torch.Generator(device=dev).manual_seed(int(seed))
-    g = torch.exp(sigma_gene * torch.randn(D, generator=gen, device=dev, dtype=torch.float64))
+    ggen = gen if gene_seed is None else torch.Generator(device=dev).manual_seed(int(gene_seed))
+    g = torch.exp(sigma_gene * torch.randn(D, generator=ggen, device=dev, dtype=torch.float64))
     c = torch.exp(sigma_cell * torch.randn(nrows, generator=gen, device=dev, dtype=torch.float64))
     # solve m: mean_{b,d} (1 - exp(-c_b g_d e^m)) = density on a subsample (bisection)
     cs = c[: min(nrows, 2048)]
