@@ -176,9 +176,9 @@ long long spmf_umma_tiled_a_index(long long row, long long k, long long Kd);
 int spmf_umma_tile_a(const void* src_bf16, long long ld, int M, int Kd, void* dst, void* stream); /* row-major -> tiled */
 /* CSR batch (original column ids) -> ranked + partitioned CSR (zero-based rowptr_out[nrows+1]; per row
  * the entries covered by the tensor-core products first, stored with a NEGATIVE value as their flag,
- * the others from rowmid[row] on) and the dense hot block as UMMA-tiled bf16: xhot = X[nrows][Hp] and
- * its transpose xthot = X^T[H][Bp] (Hp = ceil64(H), Bp = ceil64(nrows); sizes from
- * spmf_umma_tiled_a_elems; both zeroed here).  Covered = rank < H and the count is exactly
+ * the others from rowmid[row] on) and the dense hot block as UMMA-tiled bf16: xhot = X[nrows][Hp]
+ * (zeroed here) and, if xthot != NULL, its transpose xthot = X^T[H][Bp] (Hp = ceil64(H),
+ * Bp = ceil64(nrows); sizes from spmf_umma_tiled_a_elems).  The step itself needs xhot only.  Covered = rank < H and the count is exactly
  * representable in bf16.  rowsum / lgam (both or neither): also emit the per-row constants of
  * spmf_csr_row_consts in the same pass. */
 int spmf_hot_split(const long long* rowptr, const int* cols, const float* vals, int nrows, long long nnz,
@@ -193,6 +193,11 @@ int spmf_split3_transpose(const float* src, long long lds, long long src_qstride
  * `splits` = split-K factor (<= 0: automatic). */
 int spmf_umma_gemm3(const void* A, long long a_qstride, int M, const void* B3, long long b_qstride, float* C,
                     long long ldc, long long c_qstride, int N, int Kd, int NQ, int splits, void* stream);
+/* C[q][M][N] += X^T . (B3[q] hi+mid+lo)^T with X = the UMMA-tiled counts X[x_rows][x_kd] read as an
+ * MN-major operand (M = its columns, first M of them; K = its rows): GA' = X_hot^T . dzr without a
+ * transposed copy of the counts.  B3 is UMMA-tiled over k = rows of X, padded to a multiple of 128. */
+int spmf_umma_gemm3_at(const void* X, int x_kd, int x_rows, int M, const void* B3, long long b_qstride, float* C,
+                       long long ldc, long long c_qstride, int N, int NQ, int splits, void* stream);
 /* bring-up probe: one CTA, raw shared-memory operand images, explicit descriptor fields (major-ness,
  * leading / stride byte offsets, byte step per k=16 MMA); dumps the 128-lane x N-column fp32
  * accumulator block to out[128][N].  Pins the UMMA conventions the kernels rely on (tests only). */
@@ -290,7 +295,7 @@ typedef struct spmf_step_args {
   const int* rowmid;
   const int *hot_colptr, *hot_crows;   /* CSC of the covered entries (colptr/crows/cvals above: the rest) */
   const float* hot_cvals;
-  const void *xhot, *xthot;        /* UMMA-tiled bf16 hot block and its transpose (spmf_hot_split) */
+  const void *xhot, *xthot;        /* UMMA-tiled bf16 hot block (spmf_hot_split); xthot is unused (may be NULL) */
   void *ApT3, *dzrT3;              /* UMMA-tiled bf16 B3 workspaces, [NQ] x spmf_umma_tiled_b_elems */
   void *ev_gemm0, *ev_gemm1;       /* optional events around the tensor-core launches of the column side */
   /* optional: two more streams (+ three events) on which the GA' GEMM and the cold column pass run

@@ -1212,7 +1212,7 @@ int spmf_csc_cols_hybrid(const int* hot_colptr, const int* hot_rows, const float
 int spmf_hot_split(const long long* rowptr, const int* cols, const float* vals, int nrows, long long nnz,
                    const int* rank, int H, long long* rowptr_out, int* cols_out, float* vals_out, int* rowmid,
                    void* xhot, void* xthot, float* rowsum, float* lgam, void* stream) {
-  if (!rowptr || !cols || !vals || !rowptr_out || !cols_out || !vals_out || !rowmid || !xhot || !xthot)
+  if (!rowptr || !cols || !vals || !rowptr_out || !cols_out || !vals_out || !rowmid || !xhot)
     return SPMF_ERR_BAD_ARG;
   if ((rowsum == nullptr) != (lgam == nullptr)) return SPMF_ERR_BAD_ARG;
   if (nrows <= 0 || nnz < 0 || H <= 0) return SPMF_ERR_BAD_ARG;
@@ -1223,6 +1223,7 @@ int spmf_hot_split(const long long* rowptr, const int* cols, const float* vals, 
   hot_split_kernel<<<nrows, 128, 0, st>>>(rowptr, cols, vals, nrows, rank, H, rowptr_out, cols_out,
                                                     vals_out, rowmid, (unsigned short*)xhot, hp / 64, rowsum, lgam);
   SPMF_CHECK_LAUNCH();
+  if (!xthot) return SPMF_OK;      // (the GA' GEMM reads xhot itself as an MN-major operand)
   // the transpose covers whole 128-row tiles of xhot: rows >= nrows are zero there (memset above)
   dim3 tg((unsigned)((hp / 64 + 1) / 2 * 2), (unsigned)((nrows + 127) / 128));
   hot_transpose_kernel<<<tg, 256, 0, st>>>((const unsigned short*)xhot, (int)(hp / 64), (unsigned short*)xthot,

@@ -42,9 +42,8 @@ int spmf_advi_step(const spmf_step_args* a) {
     STEP_TRY(spmf_gamma_grad(a->params, a->noise, D, K, S, a->dgda, side));
   // ---- hot path
   const bool hybrid = a->hot_cols > 0;
-  if (hybrid && (!a->rank || !a->rowmid || !a->xhot || !a->xthot || !a->ApT3 || !a->dzrT3 || !a->hot_colptr ||
-                 !a->hot_crows || !a->hot_cvals))
-    return SPMF_ERR_BAD_ARG;
+  if (hybrid && (!a->rank || !a->rowmid || !a->xhot || !a->ApT3 || !a->dzrT3)) return SPMF_ERR_BAD_ARG;
+  if (hybrid && a->hot_mode != 2 && (!a->hot_colptr || !a->hot_crows || !a->hot_cvals)) return SPMF_ERR_BAD_ARG;
   if (a->fresh_noise)
     STEP_TRY(spmf_fill_noise(a->noise, a->params, D, K, S, a->seed, a->rng_step, SPMF_NOISE_NORMAL, hot));
   // data-independent half of the backward: needs the noise only -> side stream, under the data term
@@ -105,7 +104,7 @@ int spmf_advi_step(const spmf_step_args* a) {
     //   GA'[0:H] += X_hot^T . dzr                     -- tcgen05 GEMM, aux stream 1
     //   cold CSC (everything else): GEV, Gphi, GA'    -- gather kernel, aux stream 2
     const int H = a->hot_cols;
-    const int Bp = (a->nrows + 63) / 64 * 64;
+    const int Bp = (a->nrows + 127) / 128 * 128;     // whole 128-row tiles of the count block
     const bool fork = a->aux_stream1 && a->aux_stream2 && a->ev_aux_fork && a->ev_aux_join1 && a->ev_aux_join2;
     cudaStream_t s1 = fork ? (cudaStream_t)a->aux_stream1 : hot;
     cudaStream_t s2 = fork ? (cudaStream_t)a->aux_stream2 : hot;
@@ -118,8 +117,9 @@ int spmf_advi_step(const spmf_step_args* a) {
     if (a->ev_gemm0) CUDA_TRY(cudaEventRecord((cudaEvent_t)a->ev_gemm0, s1));
     STEP_TRY(spmf_split3_transpose(a->dzr, REC, (long long)a->nrows * REC, a->nrows, Bp, REC, a->dzrT3,
                                    a->t3_qstride, NQ, s1));
-    STEP_TRY(spmf_umma_gemm3(a->xthot, 0, H, a->dzrT3, a->t3_qstride, a->GAp, REC, (long long)D * REC, REC, Bp, NQ,
-                             a->gemm_splits, s1));
+    // X_hot^T is never built: the GEMM reads the X tiles as an MN-major operand
+    STEP_TRY(spmf_umma_gemm3_at(a->xhot, (H + 63) / 64 * 64, a->nrows, H, a->dzrT3, a->t3_qstride, a->GAp, REC,
+                                (long long)D * REC, REC, NQ, a->gemm_splits, s1));
     if (a->ev_gemm1) CUDA_TRY(cudaEventRecord((cudaEvent_t)a->ev_gemm1, s1));
     STEP_TRY(spmf_csc_cols_accum(a->colptr, a->crows, a->cvals, a->nnz, a->nrows, D, K, S, a->z, a->dzr, a->EV,
                                  a->PH, a->GAp, a->GEV, a->Gph, 0, s2));

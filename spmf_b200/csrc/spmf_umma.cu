@@ -97,27 +97,25 @@ umma_gemm3_kernel(const __nv_bfloat16* __restrict__ A, long long a_qstride, int 
       tma_bulk_g2s(sA, At + (long long)i * (SM::A_BYTES / 2), SM::A_BYTES, full[stage]);
       tma_bulk_g2s(sA + SM::A_BYTES, Bt + (long long)i * (SM::B_BYTES / 2), SM::B_BYTES, full[stage]);
     }
-  } else if (warp == 1 && lane == 0) {
-    // ===== MMA issuer =====
+  } else if (warp == 1) {
+    // ===== MMA issuer: the whole warp runs the loop, one elected lane issues (spmf_umma_ptx.cuh) =====
     constexpr uint32_t IDESC = umma_idesc_bf16(kGemmBM, N);
+    const uint64_t dA = umma_desc(sbase, 128, (kGemmBK / 8) * 128);
+    const uint64_t dB = umma_desc(sbase + SM::A_BYTES, 128, (kGemmBK / 8) * 128);
     for (int i = 0; i < nchunks; ++i) {
       const int stage = i % kGemmStages;
       mbar_wait(full[stage], (uint32_t)((i / kGemmStages) & 1));
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t sA = sbase + stage * SM::STAGE_BYTES;
+      const uint64_t so = (uint64_t)stage * (uint64_t)(SM::STAGE_BYTES >> 4);
 #pragma unroll
-      for (int t = 0; t < 3; ++t) {
-        const uint32_t sB = sA + SM::A_BYTES + t * (N * kGemmBK * 2);
+      for (int t = 0; t < 3; ++t)
 #pragma unroll
-        for (int j = 0; j < kGemmBK / 16; ++j) {
-          const uint64_t ad = umma_desc(sA + j * 256, 128, (kGemmBK / 8) * 128);
-          const uint64_t bd = umma_desc(sB + j * 256, 128, (kGemmBK / 8) * 128);
-          umma_bf16(tmem_acc, ad, bd, IDESC, (i | t | j) ? 1u : 0u);
-        }
-      }
-      umma_commit(empty[stage]);         // frees the stage once these MMAs have read it
+        for (int j = 0; j < kGemmBK / 16; ++j)
+          umma_bf16_elect(tmem_acc, dA + so + (uint64_t)(j * 16), dB + so + (uint64_t)(t * (N * kGemmBK * 2 / 16) + j * 16),
+                          IDESC, (i | t | j) ? 1u : 0u);
+      umma_commit_elect(empty[stage]);   // frees the stage once these MMAs have read it
     }
-    umma_commit(done);                   // commits retire in order: covers every MMA above
+    umma_commit_elect(done);             // commits retire in order: covers every MMA above
   }
   __syncwarp();
   mbar_wait(done, 0u);
@@ -242,6 +240,144 @@ umma_probe_kernel(const unsigned char* __restrict__ a_img, int a_bytes, const un
   if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tacc), "r"(256u) : "memory");
 }
 
+// GA'[d][c] += sum_b X[b][d] * (B_hi + B_mid + B_lo)[c][b]  with A = X^T taken straight from the X tiles:
+// a K-major [128 rows b][64 columns d] tile IS an MN-major operand with M = d (64), K = b, so no
+// transposed copy of the counts is ever built.  One CTA = one 64-column chunk (UMMA M = 64) and a
+// range of 64-row k-chunks; a stage = half an X tile (8 KiB, contiguous) + one B3 chunk.
+template <int N>
+struct GemmAtSmem {
+  static constexpr int A_BYTES = kTileABytes / 2;                 // 64 rows x 64 columns
+  static constexpr int B_BYTES = 3 * N * kGemmBK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int TOTAL = kGemmStages * STAGE_BYTES + 128;
+};
+
+template <int N>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+umma_gemm3_at_kernel(const __nv_bfloat16* __restrict__ X, int xchunks, int M,
+                     const __nv_bfloat16* __restrict__ B, long long b_qstride, float* __restrict__ C,
+                     long long ldc, long long c_qstride, int kchunks, int chunks_per_split) {
+  using SM = GemmAtSmem<N>;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 127u) & ~127u;
+  __shared__ __align__(8) unsigned long long mbar_store[2 * kGemmStages + 1];
+  __shared__ uint32_t tmem_base_slot;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int kc = blockIdx.x;                  // 64-column chunk of X = 64 rows of C
+  const int q = blockIdx.z;
+  const int c0 = blockIdx.y * chunks_per_split;
+  const int c1 = min(kchunks, c0 + chunks_per_split);
+  const int nchunks = c1 - c0;
+  if (nchunks <= 0) return;
+  B += (long long)q * b_qstride;
+  C += (long long)q * c_qstride;
+
+  uint32_t full[kGemmStages], empty[kGemmStages];
+#pragma unroll
+  for (int i = 0; i < kGemmStages; ++i) {
+    full[i] = smem_u32(&mbar_store[i]);
+    empty[i] = smem_u32(&mbar_store[kGemmStages + i]);
+  }
+  const uint32_t done = smem_u32(&mbar_store[2 * kGemmStages]);
+  if (tid == 0) {
+#pragma unroll
+    for (int i = 0; i < kGemmStages; ++i) { mbar_init(full[i], 1); mbar_init(empty[i], 1); }
+    mbar_init(done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                 "r"((uint32_t)N)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_acc = tmem_base_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      // k-chunk c (64 rows of X) = half (c & 1) of X tile (c >> 1, kc)
+      const __nv_bfloat16* Bt = B + (long long)c0 * (SM::B_BYTES / 2);
+      for (int i = 0; i < nchunks; ++i) {
+        const int stage = i % kGemmStages, c = c0 + i;
+        if (i >= kGemmStages) mbar_wait(empty[stage], (uint32_t)((i / kGemmStages - 1) & 1));
+        const uint32_t sA = sbase + stage * SM::STAGE_BYTES;
+        const __nv_bfloat16* At = X + ((long long)(c >> 1) * xchunks + kc) * (kTileABytes / 2) + (c & 1) * (SM::A_BYTES / 2);
+        mbar_expect_tx(full[stage], (uint32_t)SM::STAGE_BYTES);
+        tma_bulk_g2s(sA, At, SM::A_BYTES, full[stage]);
+        tma_bulk_g2s(sA + SM::A_BYTES, Bt + (long long)i * (SM::B_BYTES / 2), SM::B_BYTES, full[stage]);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    constexpr uint32_t IDESC = umma_idesc_bf16(64, N, 1, 0);                  // A MN-major, B K-major
+    const uint64_t dA = umma_desc(sbase, 1024, 128);                          // k-group = 8 rows of X, m-group = 8 columns
+    const uint64_t dB = umma_desc(sbase + SM::A_BYTES, 128, (kGemmBK / 8) * 128);
+    for (int i = 0; i < nchunks; ++i) {
+      const int stage = i % kGemmStages;
+      mbar_wait(full[stage], (uint32_t)((i / kGemmStages) & 1));
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint64_t so = (uint64_t)stage * (uint64_t)(SM::STAGE_BYTES >> 4);
+#pragma unroll
+      for (int t = 0; t < 3; ++t)
+#pragma unroll
+        for (int j = 0; j < kGemmBK / 16; ++j)
+          umma_bf16_elect(tmem_acc, dA + so + (uint64_t)(j * (2048 / 16)),
+                          dB + so + (uint64_t)(t * (N * kGemmBK * 2 / 16) + j * 16), IDESC, (i | t | j) ? 1u : 0u);
+      umma_commit_elect(empty[stage]);
+    }
+    umma_commit_elect(done);
+  }
+  __syncwarp();
+  mbar_wait(done, 0u);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+  // ---- epilogue: accumulator row m (M = 64) sits in tensor-memory lane (m/16)*32 + m%16
+  const int row = kc * 64 + warp * 16 + lane;
+  float* crow = C + (long long)row * ldc;
+#pragma unroll
+  for (int cb = 0; cb < N / 32; ++cb) {
+    float v[32];
+    tmem_ld32(tmem_acc + ((uint32_t)(warp * 32) << 16) + (uint32_t)(cb * 32), v);
+    if (lane < 16 && row < M) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4)
+        atomicAdd(reinterpret_cast<float4*>(crow + cb * 32 + j), make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"((uint32_t)N) : "memory");
+  }
+}
+
+template <int N>
+static int launch_gemm3_at(const __nv_bfloat16* X, int xchunks, int M, const __nv_bfloat16* B, long long bq, float* C,
+                           long long ldc, long long cq, int Kd, int NQ, int splits, cudaStream_t st) {
+  using SM = GemmAtSmem<N>;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(umma_gemm3_at_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL);
+    if (e != cudaSuccess) return (int)e;
+    attr = true;
+  }
+  const int kchunks = Kd / kGemmBK;
+  const int mchunks = (M + 63) / 64;
+  if (splits <= 0) splits = (2 * 148 + mchunks * NQ - 1) / (mchunks * NQ);
+  if (splits < 1) splits = 1;
+  if (splits > kchunks) splits = kchunks;
+  const int per = (kchunks + splits - 1) / splits;
+  splits = (kchunks + per - 1) / per;
+  dim3 grid(mchunks, splits, NQ);
+  umma_gemm3_at_kernel<N><<<grid, kGemmThreads, SM::TOTAL, st>>>(X, xchunks, M, B, bq, C, ldc, cq, kchunks, per);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? SPMF_OK : (int)e;
+}
+
 template <int N>
 static int launch_gemm3(const __nv_bfloat16* A, long long aq, int M, const __nv_bfloat16* B, long long bq, float* C,
                         long long ldc, long long cq, int Kd, int NQ, int splits, cudaStream_t st) {
@@ -306,6 +442,23 @@ int spmf_umma_gemm3(const void* A, long long a_qstride, int M, const void* B3, l
     case 32: return launch_gemm3<32>(a, a_qstride, M, b, b_qstride, C, ldc, c_qstride, Kd, NQ, splits, st);
     case 64: return launch_gemm3<64>(a, a_qstride, M, b, b_qstride, C, ldc, c_qstride, Kd, NQ, splits, st);
     case 128: return launch_gemm3<128>(a, a_qstride, M, b, b_qstride, C, ldc, c_qstride, Kd, NQ, splits, st);
+    default: return SPMF_ERR_UNSUPPORTED;
+  }
+}
+
+int spmf_umma_gemm3_at(const void* X, int x_kd, int x_rows, int M, const void* B3, long long b_qstride, float* C,
+                       long long ldc, long long c_qstride, int N, int NQ, int splits, void* stream) {
+  if (!X || !B3 || !C || M <= 0 || x_kd <= 0 || x_rows <= 0 || NQ <= 0) return SPMF_ERR_BAD_ARG;
+  if (x_kd % kGemmBK || M > x_kd || ldc % 4) return SPMF_ERR_BAD_ARG;
+  if (((uintptr_t)X | (uintptr_t)B3 | (uintptr_t)C) & 15) return SPMF_ERR_BAD_ARG;
+  const int Kd = (x_rows + 127) / 128 * 128;          // whole X tiles: rows beyond x_rows are zero there
+  cudaStream_t st = (cudaStream_t)stream;
+  const __nv_bfloat16* a = (const __nv_bfloat16*)X;
+  const __nv_bfloat16* b = (const __nv_bfloat16*)B3;
+  switch (N) {
+    case 32: return launch_gemm3_at<32>(a, x_kd / kGemmBK, M, b, b_qstride, C, ldc, c_qstride, Kd, NQ, splits, st);
+    case 64: return launch_gemm3_at<64>(a, x_kd / kGemmBK, M, b, b_qstride, C, ldc, c_qstride, Kd, NQ, splits, st);
+    case 128: return launch_gemm3_at<128>(a, x_kd / kGemmBK, M, b, b_qstride, C, ldc, c_qstride, Kd, NQ, splits, st);
     default: return SPMF_ERR_UNSUPPORTED;
   }
 }

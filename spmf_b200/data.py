@@ -39,7 +39,7 @@ class HotSplit:
     vals: torch.Tensor            # fp32 [nnz]    negative = covered by the tensor-core products
     rowmid: torch.Tensor          # int32 [nrows] first uncovered entry of each row (row-local)
     xhot: torch.Tensor            # bf16, UMMA-tiled X[nrows][ceil64(H)]   (see include/spmf_b200.h)
-    xthot: torch.Tensor           # bf16, UMMA-tiled X^T[H][ceil64(nrows)]
+    xthot: Optional[torch.Tensor] # bf16, UMMA-tiled X^T[H][ceil64(nrows)] (only on request; the step reads xhot)
     colptr: torch.Tensor          # CSC of the entries NOT covered by the GEMMs: int32 [D+1]
     crows: torch.Tensor
     cvals: torch.Tensor
@@ -65,7 +65,7 @@ class DeviceBatch:
     cvals: Optional[torch.Tensor] = None    # fp32 [nnz]
     hot: Optional[HotSplit] = None          # hybrid form (built for one (rank, H) ordering)
 
-    def ensure_hot(self, rank, H, bufs=None, hot_csc=True, row_consts=False):
+    def ensure_hot(self, rank, H, bufs=None, hot_csc=True, row_consts=False, build_xt=False):
         """Build (once) the hybrid form for the column ordering `rank` (int32 [D] device tensor) with
         H hot columns.  `bufs` may supply reusable staging (the streaming uploader).  `hot_csc`: also
         build the CSC copy of the covered entries (only the GEMM-only hybrid mode reads it; the tile
@@ -83,7 +83,7 @@ class DeviceBatch:
                         vals=torch.empty(m, dtype=torch.float32, device=dev),
                         rowmid=torch.empty(n, dtype=torch.int32, device=dev),
                         xhot=torch.empty(na, dtype=torch.bfloat16, device=dev),
-                        xthot=torch.empty(nt, dtype=torch.bfloat16, device=dev),
+                        xthot=torch.empty(nt, dtype=torch.bfloat16, device=dev) if build_xt else None,
                         colptr=torch.empty(self.D + 1, dtype=torch.int32, device=dev),
                         crows=torch.empty(m, dtype=torch.int32, device=dev),
                         cvals=torch.empty(m, dtype=torch.float32, device=dev),
@@ -94,7 +94,7 @@ class DeviceBatch:
         st = _stream()
         _abi.call("spmf_hot_split", _ptr(self.rowptr), _ptr(self.cols), _ptr(self.vals), n, nnz, _ptr(rank), H,
                   _ptr(bufs["rowptr"]), _ptr(bufs["cols"]), _ptr(bufs["vals"]), _ptr(bufs["rowmid"]),
-                  _ptr(bufs["xhot"]), _ptr(bufs["xthot"]),
+                  _ptr(bufs["xhot"]), _ptr(bufs.get("xthot")),
                   _ptr(self.rowsum) if row_consts else None, _ptr(self.lgam) if row_consts else None, st)
         for part, pre in ((0, "h"), (1, "")):       # covered entries / the rest
             if part == 0 and not hot_csc:
@@ -103,7 +103,7 @@ class DeviceBatch:
                       _ptr(bufs["vals"]), n, self.D, _ptr(bufs[pre + "colptr"]), _ptr(bufs[pre + "crows"]),
                       _ptr(bufs[pre + "cvals"]), _ptr(bufs["scratch"]), st)
         self.hot = HotSplit(H=H, rowptr=bufs["rowptr"], cols=bufs["cols"], vals=bufs["vals"],
-                            rowmid=bufs["rowmid"], xhot=bufs["xhot"], xthot=bufs["xthot"],
+                            rowmid=bufs["rowmid"], xhot=bufs["xhot"], xthot=bufs.get("xthot"),
                             colptr=bufs["colptr"], crows=bufs["crows"], cvals=bufs["cvals"],
                             hcolptr=bufs["hcolptr"], hcrows=bufs["hcrows"], hcvals=bufs["hcvals"],
                             has_hot_csc=bool(hot_csc))
@@ -391,7 +391,7 @@ class BatchUploader:
                                  vals=torch.empty(n, dtype=torch.float32, device=dev),
                                  rowmid=torch.empty(max(rows, 1), dtype=torch.int32, device=dev),
                                  xhot=torch.empty(na, dtype=torch.bfloat16, device=dev),
-                                 xthot=torch.empty(nt, dtype=torch.bfloat16, device=dev),
+                                 xthot=None,
                                  colptr=self.colptr, crows=self.crows, cvals=self.cvals,
                                  hcolptr=torch.empty(self.D + 1, dtype=torch.int32, device=dev),
                                  hcrows=torch.empty(n, dtype=torch.int32, device=dev),

@@ -50,7 +50,7 @@ class StepWorkspace:
     def ensure_hybrid(self, H, nrows):
         """bf16 three-term operands of the tcgen05 GEMMs (UMMA-tiled B3): ApT3 over the hot columns,
         dzrT3 over the batch rows; one block of `t3_qstride` elements per draw group."""
-        kd = max((int(H) + 63) // 64 * 64, (int(nrows) + 63) // 64 * 64)
+        kd = max((int(H) + 63) // 64 * 64, (int(nrows) + 127) // 128 * 128)
         if getattr(self, "t3_kd", 0) >= kd:
             return False
         self.t3_kd = kd

@@ -62,6 +62,23 @@ def test_umma_gemm3_matches_float64(M, N, Kd, NQ, splits):
     err = (C.cpu().double() - ref).abs().max() / ref.abs().max()
     assert float(err) < 2e-6, float(err)
 
+    # the transposed product straight from the same tiles (MN-major operand): Ct[q][Kd'][N] += A^T . Bt^T
+    # with k = the rows of A (padded to whole 128-row tiles)
+    Mp = (M + 127) // 128 * 128
+    Msel = min(Kd, 100)                                    # first Msel columns of A
+    Bt_src = torch.randn(NQ, M, N, generator=g)
+    qs2 = _abi._lib.spmf_umma_tiled_b_elems(N, Mp)
+    Bt3 = torch.zeros(NQ * qs2, dtype=torch.bfloat16, device=dev)
+    _abi.call("spmf_split3_transpose", _ptr(Bt_src.to(dev).contiguous()), N, M * N, M, Mp, N, _ptr(Bt3), qs2, NQ,
+              _stream())
+    Ct = torch.zeros(NQ, Msel, N, device=dev)
+    _abi.call("spmf_umma_gemm3_at", _ptr(Ad), Kd, M, Msel, _ptr(Bt3), qs2, _ptr(Ct), N, Msel * N, N, NQ, splits,
+              _stream())
+    torch.cuda.synchronize()
+    reft = torch.einsum("mk,qmn->qkn", A.double()[:, :Msel], Bt_src.double())
+    errt = (Ct.cpu().double() - reft).abs().max() / reft.abs().max()
+    assert float(errt) < 2e-6, float(errt)
+
 
 def test_hot_split_partitions_and_fills_dense_block():
     from spmf_b200 import _abi
@@ -77,7 +94,7 @@ def test_hot_split_partitions_and_fills_dense_block():
     rank = rng.permutation(D).astype(np.int32)
     sh = CsrShard.from_dense(torch.from_numpy(x), dev)
     b = sh.batch(0, B)
-    h = b.ensure_hot(torch.from_numpy(rank).to(dev), H)
+    h = b.ensure_hot(torch.from_numpy(rank).to(dev), H, build_xt=True)
     torch.cuda.synchronize()
     rp = h.rowptr.cpu().numpy()
     cols, vals, mid = h.cols.cpu().numpy(), h.vals.cpu().numpy(), h.rowmid.cpu().numpy()
