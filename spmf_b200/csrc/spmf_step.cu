@@ -69,16 +69,30 @@ int spmf_advi_step(const spmf_step_args* a) {
     // encode product of the hot block on the tensor cores: z = X_hot . A'[0:H]  (un-scaled)
     const int H = a->hot_cols;
     const int Hp = (H + 63) / 64 * 64;
+    // the EV / phi tile blocks and the zeroing of the column-gradient tables do not depend on the
+    // GEMM: run them next to it on an auxiliary stream when one is available
+    const bool pre_fork = a->hot_mode == 2 && a->EVt && a->aux_stream1 && a->ev_aux_fork && a->ev_aux_join1;
+    if (pre_fork) {
+      cudaStream_t s1 = (cudaStream_t)a->aux_stream1;
+      CUDA_TRY(cudaEventRecord((cudaEvent_t)a->ev_aux_fork, hot));
+      CUDA_TRY(cudaStreamWaitEvent(s1, (cudaEvent_t)a->ev_aux_fork, 0));
+      STEP_TRY(spmf_hot_ev_tiles(a->EV, a->PH, D, H, K, S, a->EVt, s1));
+      STEP_TRY(spmf_zero_col_grads(a->GAp, a->GEV, a->Gph, D, K, S, s1));
+      CUDA_TRY(cudaEventRecord((cudaEvent_t)a->ev_aux_join1, s1));
+    }
     STEP_TRY(spmf_split3_transpose(a->Ap, REC, (long long)D * REC, H, Hp, REC, a->ApT3, a->t3_qstride, NQ, hot));
     CUDA_TRY(cudaMemsetAsync(a->z, 0, (size_t)NQ * a->nrows * REC * sizeof(float), hot));
     STEP_TRY(spmf_umma_gemm3(a->xhot, 0, a->nrows, a->ApT3, a->t3_qstride, a->z, REC, (long long)a->nrows * REC,
                              REC, Hp, NQ, a->gemm_splits, hot));
+    if (pre_fork) CUDA_TRY(cudaStreamWaitEvent(hot, (cudaEvent_t)a->ev_aux_join1, 0));
     if (a->hot_mode == 2) {
       // per-nonzero terms of the hot block in the fused tcgen05 tile kernel; the gather kernel keeps
       // the uncovered entries only
       if (!a->EVt) return SPMF_ERR_BAD_ARG;
-      STEP_TRY(spmf_hot_ev_tiles(a->EV, a->PH, D, H, K, S, a->EVt, hot));
-      STEP_TRY(spmf_zero_col_grads(a->GAp, a->GEV, a->Gph, D, K, S, hot));
+      if (!pre_fork) {
+        STEP_TRY(spmf_hot_ev_tiles(a->EV, a->PH, D, H, K, S, a->EVt, hot));
+        STEP_TRY(spmf_zero_col_grads(a->GAp, a->GEV, a->Gph, D, K, S, hot));
+      }
       STEP_TRY(spmf_csr_rows_cold(a->rowptr, a->cols, a->vals, a->rowmid, a->rowsum, a->inv_xi, a->scale_rows,
                                   a->nrows, D, K, S, a->Ap, a->EV, a->PH, a->z, a->dzr, a->rowacc, hot));
       if (a->ev_tile0) CUDA_TRY(cudaEventRecord((cudaEvent_t)a->ev_tile0, hot));

@@ -296,7 +296,10 @@ class AdviEngine:
             self.rng_step += 1
         if do_adam:
             self.opt_step += 1
-        self.launches += 17 + (1 if do_adam else 0) + (5 if hybrid else 0)   # kernels issued by spmf_advi_step
+        # kernels issued by spmf_advi_step (counted against the ncu launch lists under profiles/):
+        # 18 in gather mode, +5 GEMM-hybrid (2 splits, 2 GEMMs, second column kernel), +7 tile-hybrid
+        # (2 splits, 2 GEMMs, EV tiles, tile kernel, row finalisation); +1 Adam
+        self.launches += 18 + (1 if do_adam else 0) + ((7 if self.hot_mode == 2 else 5) if hybrid else 0)
         return w.parts.view(self.S, _abi.NUM_PARTS)
 
     def loss_and_grad(self, batch: DeviceBatch, fresh_noise=True, variant=0):
