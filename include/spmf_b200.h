@@ -156,7 +156,9 @@ int spmf_dense_fill(const float* x, int nrows, int D, const long long* rowptr, i
  * populated columns; the per-nonzero terms (rate, x/rate) stay on the gather kernels.
  * Column order: `rank[d]` = table row of feature d (descending column population), so the hot block
  * is rows [0,H) of every operand table.  All *_ranked entry points take rank == NULL as identity. */
-int spmf_hybrid_supported(int K, int S); /* 1 if REC = KP*SV is 32, 64 or 128 with KP in {8,16,32} */
+/* 0: none; 2: GEMMs + fused tile kernel (KP in {8,16,32}, REC = KP*SV in {32,64,128});
+ * 1: GEMMs only (KP = 64 or 128, wider records run as blocks of 128 channels) */
+int spmf_hybrid_supported(int K, int S);
 int spmf_draw_operands_ranked(const float* params, const float* noise, const float* eta, const int* rank,
                               int D, int K, int S, float* Ap, float* EV, float* PH, double* vsum,
                               double* phisum, double* scratch, void* stream);
@@ -189,7 +191,7 @@ int spmf_hot_split(const long long* rowptr, const int* cols, const float* vals, 
 int spmf_split3_transpose(const float* src, long long lds, long long src_qstride, int R, int Rpad, int C,
                           void* dst3, long long dst_qstride, int NQ, void* stream);
 /* C[q][M][N] (fp32, row stride ldc, accumulated with atomics) += A[q] (UMMA-tiled, M x Kd)
- * * (B3[q] hi+mid+lo)^T (UMMA-tiled, N x Kd) on tcgen05; N in {32,64,128}, Kd % 64 == 0,
+ * * (B3[q] hi+mid+lo)^T (UMMA-tiled, N x Kd) on tcgen05; N in {32,64,128,256,512}, Kd % 64 == 0,
  * `splits` = split-K factor (<= 0: automatic). */
 int spmf_umma_gemm3(const void* A, long long a_qstride, int M, const void* B3, long long b_qstride, float* C,
                     long long ldc, long long c_qstride, int N, int Kd, int NQ, int splits, void* stream);

@@ -1118,13 +1118,24 @@ int spmf_csc_cols(const int* colptr, const int* rows, const float* vals, int nnz
     else if (KP == 16 && SV == 4) { CALL(16, 4); }                           \
     else if (KP == 16 && SV == 2) { CALL(16, 2); }                           \
     else if (KP == 8 && SV == 4) { CALL(8, 4); }                             \
+    else if (KP == 64 && SV == 4) { CALL(64, 4); }                           \
+    else if (KP == 64 && SV == 2) { CALL(64, 2); }                           \
+    else if (KP == 64 && SV == 1) { CALL(64, 1); }                           \
+    else if (KP == 128 && SV == 4) { CALL(128, 4); }                         \
+    else if (KP == 128 && SV == 2) { CALL(128, 2); }                         \
+    else if (KP == 128 && SV == 1) { CALL(128, 1); }                         \
     else return SPMF_ERR_UNSUPPORTED;                                        \
   } while (0)
 
+/* 0: gather kernels only; 2: tile-hybrid (KP <= 32: GEMMs + fused tile kernel); 1: GEMM-hybrid only
+ * (KP = 64, 128: the count products on tcgen05 in blocks of 128 channels, per-nonzero terms gathered) */
 int spmf_hybrid_supported(int K, int S) {
   if (K <= 0 || K > SPMF_MAX_K || S <= 0) return 0;
   const int KP = spmf_kpad(K), SV = spmf_draw_vec(S);
-  return (KP == 32 && (SV == 4 || SV == 2 || SV == 1)) || (KP == 16 && (SV == 4 || SV == 2)) || (KP == 8 && SV == 4);
+  if ((KP == 32 && (SV == 4 || SV == 2 || SV == 1)) || (KP == 16 && (SV == 4 || SV == 2)) || (KP == 8 && SV == 4))
+    return 2;
+  if (KP == 64 || KP == 128) return 1;
+  return 0;
 }
 
 int spmf_csr_rows_hybrid(const long long* rowptr, const int* cols, const float* vals, const int* rowmid,

@@ -38,11 +38,13 @@ struct GemmSmem {
 
 // C[q][M][N] += A[M][Kd] . (B3[q][0] + B3[q][1] + B3[q][2])[N][Kd]^T, operands UMMA-tiled (see above).
 // Warp 0 lane 0: TMA producer.  Warp 1 lane 0: MMA issuer.  All four warps: epilogue.
+// N = channels per CTA; the B3 operand may hold n_total = nblocks * N channels (record shapes wider than
+// one MMA): blockIdx.z = q * nblocks + nb, and a stage takes the nb-th N-row block of each term's tile.
 template <int N>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 umma_gemm3_kernel(const __nv_bfloat16* __restrict__ A, long long a_qstride, int M,
                   const __nv_bfloat16* __restrict__ B, long long b_qstride, float* __restrict__ C,
-                  long long ldc, long long c_qstride, int kchunks, int chunks_per_split) {
+                  long long ldc, long long c_qstride, int kchunks, int chunks_per_split, int nblocks) {
   using SM = GemmSmem<N>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 127u) & ~127u;
@@ -52,14 +54,15 @@ umma_gemm3_kernel(const __nv_bfloat16* __restrict__ A, long long a_qstride, int 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int mt = blockIdx.x;
   const int m0 = mt * kGemmBM;
-  const int q = blockIdx.z;
+  const int q = blockIdx.z / nblocks, nb = blockIdx.z - q * nblocks;
   const int c0 = blockIdx.y * chunks_per_split;
   const int c1 = min(kchunks, c0 + chunks_per_split);
   const int nchunks = c1 - c0;
   if (nchunks <= 0) return;
   A += (long long)q * a_qstride;
-  B += (long long)q * b_qstride;
-  C += (long long)q * c_qstride;
+  B += (long long)q * b_qstride + (long long)nb * (N * kGemmBK);      // N-row block inside every term tile
+  C += (long long)q * c_qstride + (long long)nb * N;
+  const long long b_term = (long long)nblocks * N * kGemmBK;          // elements between the terms of one k-chunk
 
   uint32_t full[kGemmStages], empty[kGemmStages];
 #pragma unroll
@@ -88,14 +91,21 @@ umma_gemm3_kernel(const __nv_bfloat16* __restrict__ A, long long a_qstride, int 
   if (warp == 0 && lane == 0) {
     // ===== TMA producer: two contiguous bulk copies per stage =====
     const __nv_bfloat16* At = A + ((long long)mt * kchunks + c0) * (SM::A_BYTES / 2);
-    const __nv_bfloat16* Bt = B + (long long)c0 * (SM::B_BYTES / 2);
+    const __nv_bfloat16* Bt = B + (long long)c0 * 3 * b_term;
     for (int i = 0; i < nchunks; ++i) {
       const int stage = i % kGemmStages;
       if (i >= kGemmStages) mbar_wait(empty[stage], (uint32_t)((i / kGemmStages - 1) & 1));
       const uint32_t sA = sbase + stage * SM::STAGE_BYTES;
       mbar_expect_tx(full[stage], (uint32_t)SM::STAGE_BYTES);
       tma_bulk_g2s(sA, At + (long long)i * (SM::A_BYTES / 2), SM::A_BYTES, full[stage]);
-      tma_bulk_g2s(sA + SM::A_BYTES, Bt + (long long)i * (SM::B_BYTES / 2), SM::B_BYTES, full[stage]);
+      if (nblocks == 1) {
+        tma_bulk_g2s(sA + SM::A_BYTES, Bt + (long long)i * 3 * b_term, SM::B_BYTES, full[stage]);
+      } else {
+#pragma unroll
+        for (int t = 0; t < 3; ++t)
+          tma_bulk_g2s(sA + SM::A_BYTES + t * (SM::B_BYTES / 3), Bt + ((long long)i * 3 + t) * b_term, SM::B_BYTES / 3,
+                       full[stage]);
+      }
     }
   } else if (warp == 1) {
     // ===== MMA issuer: the whole warp runs the loop, one elected lane issues (spmf_umma_ptx.cuh) =====
@@ -256,7 +266,7 @@ template <int N>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 umma_gemm3_at_kernel(const __nv_bfloat16* __restrict__ X, int xchunks, int M,
                      const __nv_bfloat16* __restrict__ B, long long b_qstride, float* __restrict__ C,
-                     long long ldc, long long c_qstride, int kchunks, int chunks_per_split) {
+                     long long ldc, long long c_qstride, int kchunks, int chunks_per_split, int nblocks) {
   using SM = GemmAtSmem<N>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 127u) & ~127u;
@@ -265,13 +275,14 @@ umma_gemm3_at_kernel(const __nv_bfloat16* __restrict__ X, int xchunks, int M,
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int kc = blockIdx.x;                  // 64-column chunk of X = 64 rows of C
-  const int q = blockIdx.z;
+  const int q = blockIdx.z / nblocks, nb = blockIdx.z - q * nblocks;
   const int c0 = blockIdx.y * chunks_per_split;
   const int c1 = min(kchunks, c0 + chunks_per_split);
   const int nchunks = c1 - c0;
   if (nchunks <= 0) return;
-  B += (long long)q * b_qstride;
-  C += (long long)q * c_qstride;
+  B += (long long)q * b_qstride + (long long)nb * (N * kGemmBK);
+  C += (long long)q * c_qstride + (long long)nb * N;
+  const long long b_term = (long long)nblocks * N * kGemmBK;
 
   uint32_t full[kGemmStages], empty[kGemmStages];
 #pragma unroll
@@ -300,7 +311,7 @@ umma_gemm3_at_kernel(const __nv_bfloat16* __restrict__ X, int xchunks, int M,
   if (warp == 0) {
     if (elect_one()) {
       // k-chunk c (64 rows of X) = half (c & 1) of X tile (c >> 1, kc)
-      const __nv_bfloat16* Bt = B + (long long)c0 * (SM::B_BYTES / 2);
+      const __nv_bfloat16* Bt = B + (long long)c0 * 3 * b_term;
       for (int i = 0; i < nchunks; ++i) {
         const int stage = i % kGemmStages, c = c0 + i;
         if (i >= kGemmStages) mbar_wait(empty[stage], (uint32_t)((i / kGemmStages - 1) & 1));
@@ -308,7 +319,14 @@ umma_gemm3_at_kernel(const __nv_bfloat16* __restrict__ X, int xchunks, int M,
         const __nv_bfloat16* At = X + ((long long)(c >> 1) * xchunks + kc) * (kTileABytes / 2) + (c & 1) * (SM::A_BYTES / 2);
         mbar_expect_tx(full[stage], (uint32_t)SM::STAGE_BYTES);
         tma_bulk_g2s(sA, At, SM::A_BYTES, full[stage]);
-        tma_bulk_g2s(sA + SM::A_BYTES, Bt + (long long)i * (SM::B_BYTES / 2), SM::B_BYTES, full[stage]);
+        if (nblocks == 1) {
+          tma_bulk_g2s(sA + SM::A_BYTES, Bt + (long long)i * 3 * b_term, SM::B_BYTES, full[stage]);
+        } else {
+#pragma unroll
+          for (int t = 0; t < 3; ++t)
+            tma_bulk_g2s(sA + SM::A_BYTES + t * (SM::B_BYTES / 3), Bt + ((long long)i * 3 + t) * b_term,
+                         SM::B_BYTES / 3, full[stage]);
+        }
       }
     }
     __syncwarp();
@@ -357,7 +375,7 @@ umma_gemm3_at_kernel(const __nv_bfloat16* __restrict__ X, int xchunks, int M,
 
 template <int N>
 static int launch_gemm3_at(const __nv_bfloat16* X, int xchunks, int M, const __nv_bfloat16* B, long long bq, float* C,
-                           long long ldc, long long cq, int Kd, int NQ, int splits, cudaStream_t st) {
+                           long long ldc, long long cq, int Kd, int NQ, int splits, int nblocks, cudaStream_t st) {
   using SM = GemmAtSmem<N>;
   static bool attr = false;
   if (!attr) {
@@ -367,20 +385,20 @@ static int launch_gemm3_at(const __nv_bfloat16* X, int xchunks, int M, const __n
   }
   const int kchunks = Kd / kGemmBK;
   const int mchunks = (M + 63) / 64;
-  if (splits <= 0) splits = (2 * 148 + mchunks * NQ - 1) / (mchunks * NQ);
+  if (splits <= 0) splits = (2 * 148 + mchunks * NQ * nblocks - 1) / (mchunks * NQ * nblocks);
   if (splits < 1) splits = 1;
   if (splits > kchunks) splits = kchunks;
   const int per = (kchunks + splits - 1) / splits;
   splits = (kchunks + per - 1) / per;
-  dim3 grid(mchunks, splits, NQ);
-  umma_gemm3_at_kernel<N><<<grid, kGemmThreads, SM::TOTAL, st>>>(X, xchunks, M, B, bq, C, ldc, cq, kchunks, per);
+  dim3 grid(mchunks, splits, NQ * nblocks);
+  umma_gemm3_at_kernel<N><<<grid, kGemmThreads, SM::TOTAL, st>>>(X, xchunks, M, B, bq, C, ldc, cq, kchunks, per, nblocks);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? SPMF_OK : (int)e;
 }
 
 template <int N>
 static int launch_gemm3(const __nv_bfloat16* A, long long aq, int M, const __nv_bfloat16* B, long long bq, float* C,
-                        long long ldc, long long cq, int Kd, int NQ, int splits, cudaStream_t st) {
+                        long long ldc, long long cq, int Kd, int NQ, int splits, int nblocks, cudaStream_t st) {
   using SM = GemmSmem<N>;
   static bool attr = false;
   if (!attr) {
@@ -390,13 +408,13 @@ static int launch_gemm3(const __nv_bfloat16* A, long long aq, int M, const __nv_
   }
   const int kchunks = Kd / kGemmBK;
   const int mtiles = (M + kGemmBM - 1) / kGemmBM;
-  if (splits <= 0) splits = (148 + mtiles * NQ - 1) / (mtiles * NQ);   // one resident CTA per SM
+  if (splits <= 0) splits = (148 + mtiles * NQ * nblocks - 1) / (mtiles * NQ * nblocks);   // one resident CTA per SM
   if (splits < 1) splits = 1;
   if (splits > kchunks) splits = kchunks;
   const int per = (kchunks + splits - 1) / splits;
   splits = (kchunks + per - 1) / per;
-  dim3 grid(mtiles, splits, NQ);
-  umma_gemm3_kernel<N><<<grid, kGemmThreads, SM::TOTAL, st>>>(A, aq, M, B, bq, C, ldc, cq, kchunks, per);
+  dim3 grid(mtiles, splits, NQ * nblocks);
+  umma_gemm3_kernel<N><<<grid, kGemmThreads, SM::TOTAL, st>>>(A, aq, M, B, bq, C, ldc, cq, kchunks, per, nblocks);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? SPMF_OK : (int)e;
 }
@@ -439,9 +457,10 @@ int spmf_umma_gemm3(const void* A, long long a_qstride, int M, const void* B3, l
   const __nv_bfloat16* a = (const __nv_bfloat16*)A;
   const __nv_bfloat16* b = (const __nv_bfloat16*)B3;
   switch (N) {
-    case 32: return launch_gemm3<32>(a, a_qstride, M, b, b_qstride, C, ldc, c_qstride, Kd, NQ, splits, st);
-    case 64: return launch_gemm3<64>(a, a_qstride, M, b, b_qstride, C, ldc, c_qstride, Kd, NQ, splits, st);
-    case 128: return launch_gemm3<128>(a, a_qstride, M, b, b_qstride, C, ldc, c_qstride, Kd, NQ, splits, st);
+    case 32: return launch_gemm3<32>(a, a_qstride, M, b, b_qstride, C, ldc, c_qstride, Kd, NQ, splits, 1, st);
+    case 64: return launch_gemm3<64>(a, a_qstride, M, b, b_qstride, C, ldc, c_qstride, Kd, NQ, splits, 1, st);
+    case 128: case 256: case 512:      // wider records: blocks of 128 channels
+      return launch_gemm3<128>(a, a_qstride, M, b, b_qstride, C, ldc, c_qstride, Kd, NQ, splits, N / 128, st);
     default: return SPMF_ERR_UNSUPPORTED;
   }
 }
@@ -456,9 +475,10 @@ int spmf_umma_gemm3_at(const void* X, int x_kd, int x_rows, int M, const void* B
   const __nv_bfloat16* a = (const __nv_bfloat16*)X;
   const __nv_bfloat16* b = (const __nv_bfloat16*)B3;
   switch (N) {
-    case 32: return launch_gemm3_at<32>(a, x_kd / kGemmBK, M, b, b_qstride, C, ldc, c_qstride, Kd, NQ, splits, st);
-    case 64: return launch_gemm3_at<64>(a, x_kd / kGemmBK, M, b, b_qstride, C, ldc, c_qstride, Kd, NQ, splits, st);
-    case 128: return launch_gemm3_at<128>(a, x_kd / kGemmBK, M, b, b_qstride, C, ldc, c_qstride, Kd, NQ, splits, st);
+    case 32: return launch_gemm3_at<32>(a, x_kd / kGemmBK, M, b, b_qstride, C, ldc, c_qstride, Kd, NQ, splits, 1, st);
+    case 64: return launch_gemm3_at<64>(a, x_kd / kGemmBK, M, b, b_qstride, C, ldc, c_qstride, Kd, NQ, splits, 1, st);
+    case 128: case 256: case 512:      // wider records: blocks of 128 channels
+      return launch_gemm3_at<128>(a, x_kd / kGemmBK, M, b, b_qstride, C, ldc, c_qstride, Kd, NQ, splits, N / 128, st);
     default: return SPMF_ERR_UNSUPPORTED;
   }
 }

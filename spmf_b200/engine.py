@@ -99,9 +99,14 @@ class AdviEngine:
         self.eta = torch.ones(D, dtype=torch.float32, device=self.device)
         self.rank = None          # int32 [D]: table row of each feature (hot-column ordering), or None
         self.hot_cols = 0         # H > 0 enables the hybrid (tensor-core hot block + gather) step
-        self.hybrid_ok = bool(_abi._lib.spmf_hybrid_supported(self.K, self.S))
+        cap = int(_abi._lib.spmf_hybrid_supported(self.K, self.S))
+        # cap 2: GEMMs + fused tile kernel (default on).  cap 1 (latent dims 64 / 128): only the count
+        # products have a tensor-core path; measured at K=128 it does not beat the gather kernels yet
+        # (5.43 vs 5.39 ms/step), so it is opt-in.
+        self.hybrid_ok = cap == 2 or (cap == 1 and os.environ.get("SPMF_WIDE_HYBRID", "0") == "1")
         # 1: tensor cores for the two count products only; 2: also the per-nonzero terms of the hot block
-        self.hot_mode = int(os.environ.get("SPMF_HOT_MODE", "2"))
+        # (fused tile kernel; latent dims <= 32 -- wider records use mode 1)
+        self.hot_mode = min(int(os.environ.get("SPMF_HOT_MODE", "2")), cap) if cap else 0
         self.inv_xi = 1.0
         self._ws = None
         self._side = None
