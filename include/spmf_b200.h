@@ -179,13 +179,19 @@ int spmf_umma_tile_a(const void* src_bf16, long long ld, int M, int Kd, void* ds
 /* CSR batch (original column ids) -> ranked + partitioned CSR (zero-based rowptr_out[nrows+1]; per row
  * the entries covered by the tensor-core products first, stored with a NEGATIVE value as their flag,
  * the others from rowmid[row] on) and the dense hot block as UMMA-tiled bf16: xhot = X[nrows][Hp]
- * (zeroed here) and, if xthot != NULL, its transpose xthot = X^T[H][Bp] (Hp = ceil64(H),
+ * (every element of the 128-row-padded block is written here) and, if xthot != NULL, its transpose xthot = X^T[H][Bp] (Hp = ceil64(H),
  * Bp = ceil64(nrows); sizes from spmf_umma_tiled_a_elems).  The step itself needs xhot only.  Covered = rank < H and the count is exactly
  * representable in bf16.  rowsum / lgam (both or neither): also emit the per-row constants of
  * spmf_csr_row_consts in the same pass. */
 int spmf_hot_split(const long long* rowptr, const int* cols, const float* vals, int nrows, long long nnz,
                    const int* rank, int H, long long* rowptr_out, int* cols_out, float* vals_out, int* rowmid,
                    void* xhot, void* xthot, float* rowsum, float* lgam, void* stream);
+/* the same, reading the compact upload format directly (spmf_csr_unpack16 fused in): exactly one of
+ * cols / cols16 and one of vals / vals16 is non-NULL */
+int spmf_hot_split_packed(const long long* rowptr, const int* cols, const unsigned short* cols16, const float* vals,
+                          const unsigned short* vals16, int nrows, long long nnz, const int* rank, int H,
+                          long long* rowptr_out, int* cols_out, float* vals_out, int* rowmid, void* xhot, void* xthot,
+                          float* rowsum, float* lgam, void* stream);
 /* fp32 src[NQ][R][C] (row stride lds) -> UMMA-tiled B3 operand dst[NQ] with k = source row (i.e. the
  * transpose), hi+mid+lo = src to 24 bits; k in [R, Rpad) is written as zeros.  C % 32 == 0, Rpad % 64 == 0. */
 int spmf_split3_transpose(const float* src, long long lds, long long src_qstride, int R, int Rpad, int C,

@@ -912,19 +912,39 @@ hot_transpose_kernel(const unsigned short* __restrict__ xhot, int hchunks, unsig
   }
 }
 
+// One CTA per row of the 128-row-padded batch.  STAGED: the row's dense hot vector (Hp bf16) is assembled
+// in shared memory and written out as whole 16-byte chunks -- zeros included, so xhot needs no memset and
+// the DRAM side sees full chunks instead of 2-byte read-modify-writes; rows >= nrows (tile padding) are
+// written as zeros.  !STAGED (very wide hot blocks): direct 2-byte scatter into a pre-zeroed xhot.
+constexpr int kSplitStash = 2048;     // (rank, value) pairs per row kept between the two passes
+
+// CT / VT: int / float, or unsigned short for the compact upload format (spmf_csr_unpack16 fused in).
+template <bool STAGED, typename CT, typename VT>
 __global__ void __launch_bounds__(128)
-hot_split_kernel(const long long* __restrict__ rowptr, const int* __restrict__ cols,
-                 const float* __restrict__ vals, int nrows, const int* __restrict__ rank, int H,
+hot_split_kernel(const long long* __restrict__ rowptr, const CT* __restrict__ cols,
+                 const VT* __restrict__ vals, int nrows, const int* __restrict__ rank, int H,
                  long long* __restrict__ rowptr_out, int* __restrict__ cols_out,
                  float* __restrict__ vals_out, int* __restrict__ rowmid,
                  unsigned short* __restrict__ xhot, long long hchunks, float* __restrict__ rowsum,
                  float* __restrict__ lgam) {
-  // one CTA per row; its four warps take four contiguous quarters of the row (the kernel is a chain
-  // of dependent gathers per 32 entries: more warps per row = more of them in flight)
+  extern __shared__ __align__(16) unsigned short xrow[];        // [Hp] when STAGED, then the stash
   __shared__ int s_cov[4];
   __shared__ float s_sum[4], s_lg[4];
   const int row = blockIdx.x;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int hp = (int)hchunks * 64;
+  if constexpr (STAGED) {
+    for (int i = threadIdx.x; i < hp / 8; i += blockDim.x) reinterpret_cast<uint4*>(xrow)[i] = make_uint4(0u, 0u, 0u, 0u);
+  }
+  if (row >= nrows) {                                            // padding row of the last 128-row tile
+    if constexpr (STAGED) {
+      for (int c = threadIdx.x; c < hp / 8; c += blockDim.x)
+        *reinterpret_cast<uint4*>(xhot + tiledA_index(row, 8LL * c, hchunks)) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    return;
+  }
+  // the four warps take four contiguous quarters of the row (the kernel is a chain of dependent gathers
+  // per 32 entries: more warps per row = more of them in flight)
   const long long base = rowptr[0];
   const long long j0 = rowptr[row], j1 = rowptr[row + 1];
   const long long o0 = j0 - base;
@@ -935,12 +955,18 @@ hot_split_kernel(const long long* __restrict__ rowptr, const int* __restrict__ c
   const long long n = j1 - j0;
   const long long seg = (n + 127) / 128 * 32;               // entries per warp, a multiple of 32
   const long long a0 = min(j1, j0 + w * seg), a1 = min(j1, a0 + seg);
-  // pass 1: covered entries of my quarter (and, if asked, the row constants of spmf_csr_row_consts)
+  // pass 1: covered entries of my quarter (and, if asked, the row constants of spmf_csr_row_consts);
+  // the (rank, value) pairs of the first kSplitStash entries of the row are kept in shared memory so
+  // that pass 2 does not repeat the two dependent gathers
+  int2* stash = reinterpret_cast<int2*>(xrow + (STAGED ? hp : 0));
   int ncov = 0;
   float rs = 0.f, rl = 0.f;
+#pragma unroll 4
   for (long long j = a0 + lane; j < a1; j += 32) {
-    const int r = rank ? __ldg(rank + __ldg(cols + j)) : __ldg(cols + j);
-    const float x = __ldg(vals + j);
+    const int c = (int)__ldg(cols + j);
+    const int r = rank ? __ldg(rank + c) : c;
+    const float x = (float)__ldg(vals + j);
+    if (j - j0 < kSplitStash) stash[j - j0] = make_int2(r, __float_as_int(x));
     ncov += hot_covered(r, x, H) ? 1 : 0;
     if (rowsum) { rs += x; rl += lgamma1p_count(x); }
   }
@@ -951,7 +977,7 @@ hot_split_kernel(const long long* __restrict__ rowptr, const int* __restrict__ c
     rl += __shfl_xor_sync(0xffffffffu, rl, o);
   }
   if (lane == 0) { s_cov[w] = ncov; s_sum[w] = rs; s_lg[w] = rl; }
-  __syncthreads();
+  __syncthreads();                                           // (also: xrow is zeroed)
   int cov_before = 0, cov_total = 0;
 #pragma unroll
   for (int t = 0; t < 4; ++t) {
@@ -973,8 +999,15 @@ hot_split_kernel(const long long* __restrict__ rowptr, const int* __restrict__ c
     int r = 0;
     float x = 0.f;
     if (in) {
-      r = rank ? __ldg(rank + __ldg(cols + j)) : __ldg(cols + j);
-      x = __ldg(vals + j);
+      if (j - j0 < kSplitStash) {                               // (written by this same lane in pass 1)
+        const int2 e = stash[j - j0];
+        r = e.x;
+        x = __int_as_float(e.y);
+      } else {
+        const int c = (int)__ldg(cols + j);
+        r = rank ? __ldg(rank + c) : c;
+        x = (float)__ldg(vals + j);
+      }
     }
     const bool cov = in && hot_covered(r, x, H);
     const unsigned mc = __ballot_sync(0xffffffffu, cov);
@@ -984,7 +1017,9 @@ hot_split_kernel(const long long* __restrict__ rowptr, const int* __restrict__ c
       const long long o = pc + __popc(mc & below);
       cols_out[o] = r;
       vals_out[o] = -x;
-      xhot[tiledA_index(row, r, hchunks)] = (unsigned short)(__float_as_uint(x) >> 16);   // UMMA-tiled X[nrows][Hp]
+      const unsigned short hx = (unsigned short)(__float_as_uint(x) >> 16);
+      if constexpr (STAGED) xrow[r] = hx;
+      else xhot[tiledA_index(row, r, hchunks)] = hx;           // UMMA-tiled X[nrows][Hp]
     } else if (in) {
       const long long o = pu + __popc(mu & below);
       cols_out[o] = r;
@@ -992,6 +1027,11 @@ hot_split_kernel(const long long* __restrict__ rowptr, const int* __restrict__ c
     }
     pc += __popc(mc);
     pu += __popc(mu);
+  }
+  if constexpr (STAGED) {
+    __syncthreads();
+    for (int c = threadIdx.x; c < hp / 8; c += blockDim.x)
+      *reinterpret_cast<uint4*>(xhot + tiledA_index(row, 8LL * c, hchunks)) = reinterpret_cast<const uint4*>(xrow)[c];
   }
 }
 
@@ -1220,27 +1260,73 @@ int spmf_csc_cols_hybrid(const int* hot_colptr, const int* hot_rows, const float
 // is exactly representable in bf16 (integer counts <= 256).  Per row, covered entries come first
 // (stored with a negative sign as their flag), the rest after rowmid[row]; column ids become ranks.
 // xhot[b][rank] / xthot[rank][b] receive the covered values (both pre-zeroed here).
-int spmf_hot_split(const long long* rowptr, const int* cols, const float* vals, int nrows, long long nnz,
-                   const int* rank, int H, long long* rowptr_out, int* cols_out, float* vals_out, int* rowmid,
-                   void* xhot, void* xthot, float* rowsum, float* lgam, void* stream) {
-  if (!rowptr || !cols || !vals || !rowptr_out || !cols_out || !vals_out || !rowmid || !xhot)
+}  // extern "C"
+
+template <typename CT, typename VT>
+static int launch_hot_split(const long long* rowptr, const CT* cols, const VT* vals, int nrows, const int* rank, int H,
+                            long long* rowptr_out, int* cols_out, float* vals_out, int* rowmid, void* xhot,
+                            float* rowsum, float* lgam, cudaStream_t st) {
+  const long long hp = (H + 63) / 64 * 64;
+  const size_t stash = (size_t)kSplitStash * sizeof(int2);
+  const size_t smem = (size_t)hp * 2 + stash;
+  if (smem <= 112 * 1024) {
+    // staged: every 16-byte chunk of the 128-row-padded block is written by the kernel (no memset)
+    static bool attr = false;
+    if (!attr) {
+      cudaError_t e = cudaFuncSetAttribute(hot_split_kernel<true, CT, VT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           112 * 1024);
+      if (e != cudaSuccess) return (int)e;
+      attr = true;
+    }
+    hot_split_kernel<true, CT, VT><<<(nrows + 127) / 128 * 128, 128, smem, st>>>(
+        rowptr, cols, vals, nrows, rank, H, rowptr_out, cols_out, vals_out, rowmid, (unsigned short*)xhot, hp / 64,
+        rowsum, lgam);
+  } else {
+    cudaError_t e = cudaMemsetAsync(xhot, 0, (size_t)spmf_umma_tiled_a_elems(nrows, hp) * 2, st);
+    if (e != cudaSuccess) return (int)e;
+    hot_split_kernel<false, CT, VT><<<nrows, 128, stash, st>>>(rowptr, cols, vals, nrows, rank, H, rowptr_out, cols_out,
+                                                          vals_out, rowmid, (unsigned short*)xhot, hp / 64, rowsum,
+                                                          lgam);
+  }
+  SPMF_CHECK_LAUNCH();
+  return SPMF_OK;
+}
+
+extern "C" {
+
+int spmf_hot_split_packed(const long long* rowptr, const int* cols, const unsigned short* cols16, const float* vals,
+                          const unsigned short* vals16, int nrows, long long nnz, const int* rank, int H,
+                          long long* rowptr_out, int* cols_out, float* vals_out, int* rowmid, void* xhot, void* xthot,
+                          float* rowsum, float* lgam, void* stream) {
+  if (!rowptr || (!cols == !cols16) || (!vals == !vals16) || !rowptr_out || !cols_out || !vals_out || !rowmid || !xhot)
     return SPMF_ERR_BAD_ARG;
   if ((rowsum == nullptr) != (lgam == nullptr)) return SPMF_ERR_BAD_ARG;
   if (nrows <= 0 || nnz < 0 || H <= 0) return SPMF_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   const long long hp = (H + 63) / 64 * 64, bp = ((long long)nrows + 63) / 64 * 64;
-  cudaError_t e = cudaMemsetAsync(xhot, 0, (size_t)spmf_umma_tiled_a_elems(nrows, hp) * 2, st);
-  if (e != cudaSuccess) return (int)e;
-  hot_split_kernel<<<nrows, 128, 0, st>>>(rowptr, cols, vals, nrows, rank, H, rowptr_out, cols_out,
-                                                    vals_out, rowmid, (unsigned short*)xhot, hp / 64, rowsum, lgam);
-  SPMF_CHECK_LAUNCH();
+  int rc;
+#define SPMF_SPLIT_ARGS nrows, rank, H, rowptr_out, cols_out, vals_out, rowmid, xhot, rowsum, lgam, st
+  if (cols && vals) rc = launch_hot_split(rowptr, cols, vals, SPMF_SPLIT_ARGS);
+  else if (cols) rc = launch_hot_split(rowptr, cols, vals16, SPMF_SPLIT_ARGS);
+  else if (vals) rc = launch_hot_split(rowptr, cols16, vals, SPMF_SPLIT_ARGS);
+  else rc = launch_hot_split(rowptr, cols16, vals16, SPMF_SPLIT_ARGS);
+#undef SPMF_SPLIT_ARGS
+  if (rc != SPMF_OK) return rc;
   if (!xthot) return SPMF_OK;      // (the GA' GEMM reads xhot itself as an MN-major operand)
-  // the transpose covers whole 128-row tiles of xhot: rows >= nrows are zero there (memset above)
+  // the transpose covers whole 128-row tiles of xhot: rows >= nrows are zero there (written by the split)
   dim3 tg((unsigned)((hp / 64 + 1) / 2 * 2), (unsigned)((nrows + 127) / 128));
   hot_transpose_kernel<<<tg, 256, 0, st>>>((const unsigned short*)xhot, (int)(hp / 64), (unsigned short*)xthot,
                                            (int)(bp / 64), (int)((H + 127) / 128));
   SPMF_CHECK_LAUNCH();
   return SPMF_OK;
+}
+
+int spmf_hot_split(const long long* rowptr, const int* cols, const float* vals, int nrows, long long nnz,
+                   const int* rank, int H, long long* rowptr_out, int* cols_out, float* vals_out, int* rowmid,
+                   void* xhot, void* xthot, float* rowsum, float* lgam, void* stream) {
+  if (!cols || !vals) return SPMF_ERR_BAD_ARG;
+  return spmf_hot_split_packed(rowptr, cols, nullptr, vals, nullptr, nrows, nnz, rank, H, rowptr_out, cols_out,
+                               vals_out, rowmid, xhot, xthot, rowsum, lgam, stream);
 }
 
 int spmf_csr_colstats(const int* cols, const float* vals, long long nnz, int D, double* colsum,

@@ -65,14 +65,15 @@ class DeviceBatch:
     cvals: Optional[torch.Tensor] = None    # fp32 [nnz]
     hot: Optional[HotSplit] = None          # hybrid form (built for one (rank, H) ordering)
 
-    def ensure_hot(self, rank, H, bufs=None, hot_csc=True, row_consts=False, build_xt=False):
+    def ensure_hot(self, rank, H, bufs=None, hot_csc=True, row_consts=False, build_xt=False, packed=None):
         """Build (once) the hybrid form for the column ordering `rank` (int32 [D] device tensor) with
         H hot columns.  `bufs` may supply reusable staging (the streaming uploader).  `hot_csc`: also
         build the CSC copy of the covered entries (only the GEMM-only hybrid mode reads it; the tile
-        mode gets those gradients from the tensor-core kernel)."""
+        mode gets those gradients from the tensor-core kernel).  `packed` = (cols16, vals16): read the
+        compact upload format instead of self.cols / self.vals (either may be None = use the wide array)."""
         if self.hot is not None and self.hot.H == H and (self.hot.has_hot_csc or not hot_csc):
             return self.hot
-        dev = self.vals.device
+        dev = self.rowptr.device
         n, nnz = self.nrows, self.nnz
         m = max(nnz, 1) + 8
         na = _abi._lib.spmf_umma_tiled_a_elems(n, _ceil64(H))
@@ -92,7 +93,9 @@ class DeviceBatch:
                         hcvals=torch.empty(m, dtype=torch.float32, device=dev),
                         scratch=torch.empty(_abi._lib.spmf_csc_scratch_ints(self.D), dtype=torch.int32, device=dev))
         st = _stream()
-        _abi.call("spmf_hot_split", _ptr(self.rowptr), _ptr(self.cols), _ptr(self.vals), n, nnz, _ptr(rank), H,
+        c16, v16 = packed if packed is not None else (None, None)
+        _abi.call("spmf_hot_split_packed", _ptr(self.rowptr), None if c16 is not None else _ptr(self.cols), _ptr(c16),
+                  None if v16 is not None else _ptr(self.vals), _ptr(v16), n, nnz, _ptr(rank), H,
                   _ptr(bufs["rowptr"]), _ptr(bufs["cols"]), _ptr(bufs["vals"]), _ptr(bufs["rowmid"]),
                   _ptr(bufs["xhot"]), _ptr(bufs.get("xthot")),
                   _ptr(self.rowsum) if row_consts else None, _ptr(self.lgam) if row_consts else None, st)
@@ -417,12 +420,14 @@ class BatchUploader:
         if self.hot is not None:
             # hybrid form: widen, row constants, then the ranked/partitioned CSR + dense bf16 block and
             # its CSC copy -- all on this (copy) stream, into persistent staging
-            if c16 is not None or v16 is not None:
-                _abi.call("spmf_csr_unpack16", _ptr(c16), _ptr(v16), nnz, _ptr(self.cols), _ptr(self.vals), st)
-            db = DeviceBatch(rowptr=self.rowptr[:n + 1], cols=self.cols, vals=self.vals, rowsum=self.rowsum[:n],
+            # (the split reads the compact arrays directly; the wide cols / vals of such a batch are not
+            # materialised -- the hybrid step reads the ranked copies only)
+            db = DeviceBatch(rowptr=self.rowptr[:n + 1], cols=None if c16 is not None else self.cols,
+                             vals=None if v16 is not None else self.vals, rowsum=self.rowsum[:n],
                              lgam=self.lgam[:n], nrows=n, nnz=nnz, D=self.D)
             db.ensure_hot(self.hot[0], int(self.hot[1]), bufs=self.hot_bufs, hot_csc=self.hot_csc,
-                          row_consts=True)          # row constants come out of the split's first pass
+                          row_consts=True,          # row constants come out of the split's first pass
+                          packed=(c16, v16))
             return db
         _abi.call("spmf_prepare_batch", _ptr(c16), _ptr(v16), _ptr(self.rowptr), _ptr(self.cols),
                   _ptr(self.vals), n, nnz, self.D, _ptr(self.rowsum), _ptr(self.lgam), _ptr(self.colptr),

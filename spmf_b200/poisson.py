@@ -30,6 +30,16 @@ from .engine import AdviEngine
 from .variables import VAR_LIST, NORMAL_VARS, var_shapes
 
 
+def waic_terms(ll):
+    """(lppd_i, pwaic_i) from per-observation log-likelihoods ll (S, n): log-mean-exp and the sample
+    variance over the S draws."""
+    ll = ll.to(torch.float64)
+    S = ll.shape[0]
+    lppd = torch.logsumexp(ll, 0) - math.log(S)
+    pwaic = ll.var(0, unbiased=True) if S > 1 else torch.zeros_like(lppd)
+    return lppd, pwaic
+
+
 class _SurrogateDistribution:
     """Stand-in for `self.surrogate_distribution` (a tfd.JointDistributionNamed in the reference,
     poisson.py:567-569): `.sample(n)` returns a dict of reference-shaped draws."""
@@ -106,6 +116,7 @@ class PoissonFactorization:
         self.col_rank = None        # int32 [D] device tensor: rank of each feature by population
         self.hot_cols = 0
         self.calibrated_expectations = {}
+        self._last_data_factory = None
         self._engines: Dict[int, AdviEngine] = {}
         self._params = None
         if initialize_distributions:
@@ -165,6 +176,7 @@ class PoissonFactorization:
     def compute_scales(self, data_factory, compute_normalization=True, n=None):
         """poisson.py:113-154.  `data_factory()` yields batches (dicts keyed by count_key); a
         `CsrShard` may be passed directly."""
+        self._last_data_factory = data_factory
         if not (self.scale_columns and compute_normalization):
             return
         print("Looping through the entire dataset once to get some stats")          # poisson.py:116
@@ -382,6 +394,61 @@ class PoissonFactorization:
             out['ll'] = out['log_likelihood'].sum((-1, -2))
         return out
 
+    def row_log_likelihood(self, data, sample_size=32, seed=None, **params):
+        """Per-row Poisson log-likelihood of every draw, shape (S, B): sum_d log Poisson(x_bd | lambda_sbd),
+        i.e. poisson.py:156-184's 'log_likelihood' summed over the feature axis, evaluated by the CUDA
+        row pass (sum x log lambda - lgamma(x+1) gathered over the nonzeros; sum_d lambda in closed
+        form) without materialising (S,B,D).  `params`: explicit draws of s, u, v, w with a leading
+        sample axis; default: `sample_size` draws of the surrogate posterior."""
+        if not params:
+            params = self.surrogate_distribution.sample(int(sample_size), seed=seed)
+        u = torch.as_tensor(params['u'])
+        S = u.shape[0] if u.dim() == 3 else 1
+        eng = self._engine_for(S)
+        c = data[self.count_key] if isinstance(data, dict) else data
+        b = c if isinstance(c, DeviceBatch) else as_device_batch(c, self.device, self.feature_dim)
+        if b.cols is None:
+            raise ValueError("row_log_likelihood needs a batch with its CSR arrays (not a hybrid-only upload)")
+        ws = eng.ws
+        ws.ensure_rows(b.nrows)
+        self._operands_from_theta(eng, params['u'], params['v'], params['w'], params['s'])
+        _abi.call("spmf_csr_rows", _ptr(b.rowptr), _ptr(b.cols), _ptr(b.vals), _ptr(b.rowsum), _ptr(b.lgam),
+                  eng.inv_xi, int(self.scale_rows), b.nrows, self.feature_dim, self.latent_dim, S,
+                  _ptr(ws.Ap), _ptr(ws.EV), _ptr(ws.PH), _ptr(ws.vsum), _ptr(ws.z), _ptr(ws.dzr),
+                  _ptr(ws.rowacc), 0, _stream())
+        ra = ws.rowacc[:ws.NQ * b.nrows * 4 * ws.SV].view(ws.NQ, b.nrows, 4, ws.SV).to(torch.float64)
+        ll = (ra[:, :, 0, :] - ra[:, :, 1, :]).permute(0, 2, 1).reshape(S, b.nrows)
+        return ll - ws.phisum.view(S, 1)
+
+    def waic(self, data=None, sample_size=32, batch_size=None, seed=12345):
+        """[EXT] BayesianModel.waic() (notebooks/factorizing_random_noise.ipynb:447-453): widely applicable
+        information criterion over the ROWS of `data` with `sample_size` surrogate draws (the same draws
+        for every batch): lppd_i = log mean_s exp(ll_si), pwaic_i = var_s(ll_si), waic = -2 sum_i
+        (lppd_i - pwaic_i), se = 2 sqrt(n var_i(lppd_i - pwaic_i)).  Returns the reference's dict
+        {'waic', 'se', 'lppd', 'pwaic'}.  `data`: a batch factory as for fit(), a CsrShard, or one
+        batch / array; default: the factory last given to fit() / compute_scales()."""
+        data = self._last_data_factory if data is None else data
+        if data is None:
+            raise ValueError("waic() needs data (none was seen by fit / compute_scales yet)")
+        draws = self.surrogate_distribution.sample(int(sample_size), seed=seed)
+        if isinstance(data, CsrShard):
+            batches = data.iter_batches(batch_size or min(data.nrows, 8192))
+        elif callable(data):
+            batches = iter(data())
+        else:
+            batches = [data]
+        acc = torch.zeros(4, dtype=torch.float64, device=self.device)     # lppd, pwaic, elpd, elpd^2
+        n = 0
+        for batch in batches:
+            ll = self.row_log_likelihood(batch, **draws)
+            stats = waic_terms(ll)
+            elpd = stats[0] - stats[1]
+            acc += torch.stack([stats[0].sum(), stats[1].sum(), elpd.sum(), (elpd * elpd).sum()])
+            n += ll.shape[1]
+        lppd, pwaic, e1, e2 = (float(t) for t in acc.cpu())
+        var = max(e2 / n - (e1 / n) ** 2, 0.0) * (n / (n - 1.0) if n > 1 else 1.0)
+        return {'waic': -2.0 * e1, 'se': 2.0 * math.sqrt(n * var), 'lppd': lppd, 'pwaic': pwaic}
+
     def unormalized_log_prob_list(self, *x):
         """poisson.py:703-709 (positional wrapper; needs `data` bound by the caller)."""
         return self.unormalized_log_prob(**{v: t for v, t in zip(self.var_list, x)})
@@ -415,6 +482,7 @@ class PoissonFactorization:
         snapshotted, on a plateau the learning rate decays by `lr_decay_factor` and the best
         snapshot is restored; stops on rel_tol / abs_tol / max_decay_steps / num_steps.
         Returns the list of epoch losses."""
+        self._last_data_factory = batched_data_factory
         S = int(sample_size) * int(sample_batches)
         eng = self._engine_for(S)
         losses, best, best_state = [], float('inf'), None

@@ -94,6 +94,8 @@ def test_hot_split_partitions_and_fills_dense_block():
     rank = rng.permutation(D).astype(np.int32)
     sh = CsrShard.from_dense(torch.from_numpy(x), dev)
     b = sh.batch(0, B)
+    junk = torch.full((1 << 22,), 1.5, dtype=torch.bfloat16, device=dev)   # dirty the allocator's free blocks:
+    del junk                                                              # the split must write every chunk of xhot
     h = b.ensure_hot(torch.from_numpy(rank).to(dev), H, build_xt=True)
     torch.cuda.synchronize()
     rp = h.rowptr.cpu().numpy()
@@ -104,7 +106,9 @@ def test_hot_split_partitions_and_fills_dense_block():
         rp_ = (rows + 127) // 128 * 128
         v = t[:rp_ * kd].view(rp_ // 128, kd // 64, 16, 8, 8, 8).float()      # mt, kc, r8, k8, r, k
         return v.permute(0, 2, 4, 1, 3, 5).reshape(rp_, kd).cpu().numpy()
-    xh = untile(h.xhot, B, Hp)[:B]
+    xh = untile(h.xhot, B, Hp)
+    assert (xh[B:] == 0).all()                                    # padding rows of the last 128-row tile
+    xh = xh[:B]
     xt = untile(h.xthot, H, Bp)
     assert (xt[H:] == 0).all()
     xt = xt[:Hp] if xt.shape[0] >= Hp else np.vstack([xt, np.zeros((Hp - xt.shape[0], Bp), np.float32)])

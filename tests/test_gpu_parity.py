@@ -154,6 +154,38 @@ def test_unormalized_log_prob_matches_oracle():
     assert set(parts) == set(oracle.var_list) | {'z', 'x'}          # poisson.py:582-621 dict keys
 
 
+def test_row_log_likelihood_and_waic_match_oracle():
+    """per-row log-likelihood of every draw from the CUDA row pass vs the oracle's dense
+    (S,B,D) log-likelihood (poisson.py:156-184) summed over features; WAIC over the rows from it."""
+    import spmf_b200
+    from spmf_b200.poisson import waic_terms
+    dev = torch.device("cuda:0")
+    D, K, B, S = 60, 4, 48, 8
+    x = make_counts(B, D, seed=6)
+    oracle = make_oracle(D, K, 400, x)
+    model = spmf_b200.PoissonFactorization(latent_dim=K, feature_dim=D, u_tau_scale=1.0 / np.sqrt(400 * D), device=dev)
+    model.compute_scales(lambda: [{'counts': x[:24]}, {'counts': x[24:]}])
+    th = model.surrogate_distribution.sample(S, seed=12345)
+    th64 = {k: v.cpu().double() for k, v in th.items()}
+    ref = oracle.log_likelihood_components(data={'counts': torch.tensor(x, dtype=torch.float64)},
+                                           **{k: th64[k] for k in 'suvw'})['log_likelihood'].sum(-1).numpy()
+    got = model.row_log_likelihood({'counts': x}, **th).cpu().numpy()
+    assert got.shape == (S, B)
+    np.testing.assert_allclose(got, ref, rtol=1e-5, atol=1e-3)
+    # WAIC with the same draws (seed 12345 is waic()'s default), streamed over the two batches
+    w = model.waic(sample_size=S)
+    lppd = np.log(np.exp(ref - ref.max(0)).mean(0)) + ref.max(0)
+    pw = ref.var(0, ddof=1)
+    elpd = lppd - pw
+    exp = {'waic': -2 * elpd.sum(), 'se': 2 * np.sqrt(B * elpd.var(ddof=1)), 'lppd': lppd.sum(), 'pwaic': pw.sum()}
+    assert set(w) == set(exp)                       # the reference's keys (notebook output)
+    for k in exp:
+        assert abs(w[k] - exp[k]) <= 1e-4 * abs(exp[k]) + 1e-3, (k, w[k], exp[k])
+    a, b = waic_terms(torch.tensor(ref))
+    np.testing.assert_allclose(a.numpy(), lppd, rtol=1e-12)
+    np.testing.assert_allclose(b.numpy(), pw, rtol=1e-12)
+
+
 def test_csr_csc_roundtrip_and_dense_compaction():
     import spmf_b200
     dev = torch.device("cuda:0")

@@ -61,3 +61,19 @@ def test_three_bf16_terms_carry_an_fp32_value_and_two_carry_16_bits():
     kept = xh.double() * yh.double() + xh.double() * yl.double() + xl.double() * yh.double()
     err = (kept - x.double() * y.double()).abs() / (x.double() * y.double()).abs().clamp_min(1e-300)
     assert float(err.max()) < 3 * 2.0 ** -16
+
+
+def test_waic_terms_formula():
+    """lppd_i = log mean_s exp(ll_si), pwaic_i = var_s(ll_si) (the pieces of PoissonFactorization.waic)."""
+    import math
+    import numpy as np
+    import torch
+    from spmf_b200.poisson import waic_terms
+    rng = np.random.default_rng(0)
+    ll = rng.normal(-50.0, 3.0, size=(6, 11))
+    lppd, pw = waic_terms(torch.tensor(ll, dtype=torch.float32).double())
+    exp_lppd = np.array([math.log(np.mean(np.exp(ll[:, i]))) for i in range(11)])
+    np.testing.assert_allclose(lppd.numpy(), exp_lppd, rtol=1e-6)
+    np.testing.assert_allclose(pw.numpy(), ll.var(0, ddof=1), rtol=1e-5)
+    one, zero = waic_terms(torch.tensor(ll[:1]))
+    assert np.allclose(one.numpy(), ll[0]) and (zero == 0).all()
