@@ -688,7 +688,8 @@ csc_block_hist_kernel(const long long* __restrict__ rowptr, const int* __restric
     for (int row = r0 + warp; row < r1; row += nwarp) {
       long long j0, j1;
       part_range(rowptr, rowmid, part, row, j0, j1);
-      for (long long j = j0 + lane; j < j1; j += 32) atomicAdd(&h[__ldg(cols + j)], 1);
+#pragma unroll 4
+      for (long long j = j0 + lane; j < j1; j += 32) atomicAdd(&h[__ldg(cols + j)], 1);   // (loads batched 4 deep)
     }
   }
   __syncthreads();
@@ -730,6 +731,7 @@ csc_block_scatter_kernel(const long long* __restrict__ rowptr, const int* __rest
   for (int row = r0 + warp; row < r1; row += nwarp) {
     long long j0, j1;
     part_range(rowptr, rowmid, part, row, j0, j1);
+#pragma unroll 4
     for (long long j = j0 + lane; j < j1; j += 32) {
       const int pos = atomicAdd(&cur[__ldg(cols + j)], 1);
       rows_out[pos] = row;
@@ -916,11 +918,12 @@ hot_transpose_kernel(const unsigned short* __restrict__ xhot, int hchunks, unsig
 // in shared memory and written out as whole 16-byte chunks -- zeros included, so xhot needs no memset and
 // the DRAM side sees full chunks instead of 2-byte read-modify-writes; rows >= nrows (tile padding) are
 // written as zeros.  !STAGED (very wide hot blocks): direct 2-byte scatter into a pre-zeroed xhot.
+constexpr int kSplitThreads = 256, kSplitWarps = kSplitThreads / 32;
 constexpr int kSplitStash = 2048;     // (rank, value) pairs per row kept between the two passes
 
 // CT / VT: int / float, or unsigned short for the compact upload format (spmf_csr_unpack16 fused in).
 template <bool STAGED, typename CT, typename VT>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(kSplitThreads, 2048 / kSplitThreads)
 hot_split_kernel(const long long* __restrict__ rowptr, const CT* __restrict__ cols,
                  const VT* __restrict__ vals, int nrows, const int* __restrict__ rank, int H,
                  long long* __restrict__ rowptr_out, int* __restrict__ cols_out,
@@ -928,8 +931,8 @@ hot_split_kernel(const long long* __restrict__ rowptr, const CT* __restrict__ co
                  unsigned short* __restrict__ xhot, long long hchunks, float* __restrict__ rowsum,
                  float* __restrict__ lgam) {
   extern __shared__ __align__(16) unsigned short xrow[];        // [Hp] when STAGED, then the stash
-  __shared__ int s_cov[4];
-  __shared__ float s_sum[4], s_lg[4];
+  __shared__ int s_cov[kSplitWarps];
+  __shared__ float s_sum[kSplitWarps], s_lg[kSplitWarps];
   const int row = blockIdx.x;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int hp = (int)hchunks * 64;
@@ -943,7 +946,7 @@ hot_split_kernel(const long long* __restrict__ rowptr, const CT* __restrict__ co
     }
     return;
   }
-  // the four warps take four contiguous quarters of the row (the kernel is a chain of dependent gathers
+  // the warps take contiguous, equal pieces of the row (the kernel is a chain of dependent gathers
   // per 32 entries: more warps per row = more of them in flight)
   const long long base = rowptr[0];
   const long long j0 = rowptr[row], j1 = rowptr[row + 1];
@@ -953,9 +956,9 @@ hot_split_kernel(const long long* __restrict__ rowptr, const CT* __restrict__ co
     if (row == nrows - 1) rowptr_out[nrows] = j1 - base;
   }
   const long long n = j1 - j0;
-  const long long seg = (n + 127) / 128 * 32;               // entries per warp, a multiple of 32
+  const long long seg = (n + kSplitThreads - 1) / kSplitThreads * 32;     // entries per warp, a multiple of 32
   const long long a0 = min(j1, j0 + w * seg), a1 = min(j1, a0 + seg);
-  // pass 1: covered entries of my quarter (and, if asked, the row constants of spmf_csr_row_consts);
+  // pass 1: covered entries of my piece (and, if asked, the row constants of spmf_csr_row_consts);
   // the (rank, value) pairs of the first kSplitStash entries of the row are kept in shared memory so
   // that pass 2 does not repeat the two dependent gathers
   int2* stash = reinterpret_cast<int2*>(xrow + (STAGED ? hp : 0));
@@ -979,16 +982,19 @@ hot_split_kernel(const long long* __restrict__ rowptr, const CT* __restrict__ co
   if (lane == 0) { s_cov[w] = ncov; s_sum[w] = rs; s_lg[w] = rl; }
   __syncthreads();                                           // (also: xrow is zeroed)
   int cov_before = 0, cov_total = 0;
+  float tsum = 0.f, tlg = 0.f;
 #pragma unroll
-  for (int t = 0; t < 4; ++t) {
+  for (int t = 0; t < kSplitWarps; ++t) {
     if (t < w) cov_before += s_cov[t];
     cov_total += s_cov[t];
+    tsum += s_sum[t];
+    tlg += s_lg[t];
   }
   if (threadIdx.x == 0) {
     rowmid[row] = cov_total;
     if (rowsum) {
-      rowsum[row] = (s_sum[0] + s_sum[1]) + (s_sum[2] + s_sum[3]);
-      lgam[row] = (s_lg[0] + s_lg[1]) + (s_lg[2] + s_lg[3]);
+      rowsum[row] = tsum;
+      lgam[row] = tlg;
     }
   }
   // pass 2: stable partition -- covered entries first (negated), the others after cov_total
@@ -1278,13 +1284,13 @@ static int launch_hot_split(const long long* rowptr, const CT* cols, const VT* v
       if (e != cudaSuccess) return (int)e;
       attr = true;
     }
-    hot_split_kernel<true, CT, VT><<<(nrows + 127) / 128 * 128, 128, smem, st>>>(
+    hot_split_kernel<true, CT, VT><<<(nrows + 127) / 128 * 128, kSplitThreads, smem, st>>>(
         rowptr, cols, vals, nrows, rank, H, rowptr_out, cols_out, vals_out, rowmid, (unsigned short*)xhot, hp / 64,
         rowsum, lgam);
   } else {
     cudaError_t e = cudaMemsetAsync(xhot, 0, (size_t)spmf_umma_tiled_a_elems(nrows, hp) * 2, st);
     if (e != cudaSuccess) return (int)e;
-    hot_split_kernel<false, CT, VT><<<nrows, 128, stash, st>>>(rowptr, cols, vals, nrows, rank, H, rowptr_out, cols_out,
+    hot_split_kernel<false, CT, VT><<<nrows, kSplitThreads, stash, st>>>(rowptr, cols, vals, nrows, rank, H, rowptr_out, cols_out,
                                                           vals_out, rowmid, (unsigned short*)xhot, hp / 64, rowsum,
                                                           lgam);
   }
