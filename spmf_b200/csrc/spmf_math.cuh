@@ -162,14 +162,18 @@ SPMF_HD float gamma_der_cf(float a, float psi, float x) {
   return x * (dans + ans * (SPMF_LOGF(x) - psi));
 }
 
-SPMF_HD void gamma_sample_der_alpha4(float a, float psi, const float (&x)[4], int n, float (&out)[4]) {
+// Series half: fills out[j] for the draws in the power-series regime and returns the mask of the draws
+// that need the continued fraction instead (gamma_der_cf).
+SPMF_HD unsigned gamma_der_series4(float a, float psi, const float (&x)[4], int n, float (&out)[4]) {
   bool ser[4];
   bool any_ser = false;
+  unsigned cf = 0u;
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     ser[j] = j < n && x[j] > 0.f && (x[j] <= 1.f || x[j] <= a + 1.f);
     any_ser = any_ser || ser[j];
     out[j] = 0.f;
+    if (j < n && !ser[j] && x[j] > 0.f) cf |= 1u << j;
   }
   if (any_ser) {
     float T[4], sT[4], sTH[4], xs[4];
@@ -194,9 +198,14 @@ SPMF_HD void gamma_sample_der_alpha4(float a, float psi, const float (&x)[4], in
     for (int j = 0; j < 4; ++j)
       if (ser[j]) out[j] = (x[j] / a) * (sTH[j] - (SPMF_LOGF(x[j]) - psi1) * sT[j]);
   }
+  return cf;
+}
+
+SPMF_HD void gamma_sample_der_alpha4(float a, float psi, const float (&x)[4], int n, float (&out)[4]) {
+  const unsigned cf = gamma_der_series4(a, psi, x, n, out);
 #pragma unroll
   for (int j = 0; j < 4; ++j)
-    if (j < n && !ser[j] && x[j] > 0.f) out[j] = gamma_der_cf(a, psi, x[j]);
+    if (cf & (1u << j)) out[j] = gamma_der_cf(a, psi, x[j]);
 }
 
 // ---------------------------------------------------------------------------

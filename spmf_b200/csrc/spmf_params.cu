@@ -53,39 +53,68 @@ __global__ void fill_normal_kernel(Layout L, float* __restrict__ noise, uint32_t
 // draws: g[s][e] ~ Gamma(softplus(conc_raw[e]), 1) (Philox stream keyed by s*nelem+e) when `draw`,
 // and dg/dalpha of every draw (implicit reparameterisation) -- it depends on (alpha, g) only, so
 // it is evaluated here, fully parallel, off the critical path of the data term.
+// The continued-fraction regime of the gradient (draws well above alpha, ~20 % of them) is not evaluated
+// in place -- that would run its long loop once per draw slot with a fifth of the lanes active -- but
+// queued in shared memory and worked off by the whole CTA with (nearly) full warps.
 __global__ void __launch_bounds__(128)
 gamma_kernel(Layout L, const float* __restrict__ P, float* __restrict__ N, float* __restrict__ G,
              int draw, int grad, uint32_t step, uint32_t k0, uint32_t k1) {
+  __shared__ float4 cfq[128 * 4];              // (alpha, digamma(alpha), draw, slot = draw index * 128 + thread)
+  __shared__ int cfn;
   const int v = VAR_UETA + blockIdx.y;
   const long long nelem = L.vsize[v];
-  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= nelem) return;
-  const float alpha = softplusf(P[L.toff[2 * v] + e]);
-  const float psi = grad ? digammaf_pos(alpha) : 0.f;
+  const long long e0 = (long long)blockIdx.x * blockDim.x;
+  const long long e = e0 + threadIdx.x;
+  const bool live = e < nelem;
+  if (threadIdx.x == 0) cfn = 0;
+  __syncthreads();
+  const float alpha = live ? softplusf(P[L.toff[2 * v] + e]) : 1.f;
+  const float psi = (grad && live) ? digammaf_pos(alpha) : 0.f;
   float* Nv = N + L.noff[v];
   float* Gv = G + L.noff[v];
   for (int s0 = 0; s0 < L.S; s0 += 4) {
     const int ns = L.S - s0 < 4 ? L.S - s0 : 4;
-    float g[4] = {1.f, 1.f, 1.f, 1.f}, o[4];
+    if (live) {
+      float g[4] = {1.f, 1.f, 1.f, 1.f}, o[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      if (j < ns) {
-        const long long i = (long long)(s0 + j) * nelem + e;
-        if (draw) {
-          // stream id folds the step so that (element, iteration) keep the whole counter space
-          g[j] = gamma_draw(alpha, (uint32_t)(i & 0xffffffffu), (uint32_t)(i >> 32),
-                            (uint32_t)v ^ (step * 0x9E3779B9u), k0, k1 ^ step);
-          Nv[i] = g[j];
-        } else {
-          g[j] = Nv[i];
+      for (int j = 0; j < 4; ++j) {
+        if (j < ns) {
+          const long long i = (long long)(s0 + j) * nelem + e;
+          if (draw) {
+            // stream id folds the step so that (element, iteration) keep the whole counter space
+            g[j] = gamma_draw(alpha, (uint32_t)(i & 0xffffffffu), (uint32_t)(i >> 32),
+                              (uint32_t)v ^ (step * 0x9E3779B9u), k0, k1 ^ step);
+            Nv[i] = g[j];
+          } else {
+            g[j] = Nv[i];
+          }
+        }
+      }
+      if (grad) {
+        const unsigned cf = gamma_der_series4(alpha, psi, g, ns, o);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (j < ns) {
+            if (cf & (1u << j)) {
+              cfq[atomicAdd(&cfn, 1)] = make_float4(alpha, psi, g[j], __int_as_float(j * 128 + (int)threadIdx.x));
+            } else {
+              Gv[(long long)(s0 + j) * nelem + e] = o[j];
+            }
+          }
         }
       }
     }
     if (grad) {
-      gamma_sample_der_alpha4(alpha, psi, g, ns, o);
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        if (j < ns) Gv[(long long)(s0 + j) * nelem + e] = o[j];
+      __syncthreads();
+      const int nq = cfn;
+      for (int t = threadIdx.x; t < nq; t += blockDim.x) {
+        const float4 q = cfq[t];
+        const int slot = __float_as_int(q.w);
+        Gv[(long long)(s0 + (slot >> 7)) * nelem + e0 + (slot & 127)] = gamma_der_cf(q.x, q.y, q.z);
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) cfn = 0;
+      __syncthreads();
     }
   }
 }
