@@ -162,6 +162,10 @@ int spmf_hybrid_supported(int K, int S);
 int spmf_draw_operands_ranked(const float* params, const float* noise, const float* eta, const int* rank,
                               int D, int K, int S, float* Ap, float* EV, float* PH, double* vsum,
                               double* phisum, double* scratch, void* stream);
+/* the reduction half of spmf_draw_operands(_ranked) on its own (pass vsum = phisum = NULL there):
+ * vsum[NQ][REC] = sum_d EV, phisum[NQ][SV] = sum_d PH in fp64 */
+int spmf_operand_sums(const float* EV, const float* PH, int D, int K, int S, double* vsum, double* phisum,
+                      double* scratch, void* stream);
 int spmf_backward_params_ranked(const float* params, const float* noise, const float* dgda, const float* eta,
                                 const int* rank, int D, int K, int S, const float* GAp, const float* GEVnz,
                                 const float* Gphinz, const double* zcolsum, const double* datasums,

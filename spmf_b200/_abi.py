@@ -74,6 +74,7 @@ _SIGS = {
     # hybrid path (tcgen05 hot block)
     "spmf_hybrid_supported": (i32, [i32, i32]),
     "spmf_draw_operands_ranked": (i32, [p, p, p, p, i32, i32, i32, p, p, p, p, p, p, p]),
+    "spmf_operand_sums": (i32, [p, p, i32, i32, i32, p, p, p, p]),
     "spmf_backward_params_ranked": (i32, [p, p, p, p, p, i32, i32, i32, p, p, p, p, p, p, f32, f32, f32, f32,
                                           f32, f32, i32, p, p, p, p, p]),
     "spmf_umma_tiled_a_elems": (i64, [i64, i64]),

@@ -263,14 +263,16 @@ backward_dk_kernel(Layout L, Hyper h, const float* __restrict__ P, const float* 
   }
 }
 
-// Data half of the (d,k) backward: u and v only.  grads += (1/S) sum_s of the upstream terms times the
-// stored factors (see PRE above); emits da[s][d] = sum_k GA' u / eta for the per-feature post kernel.
+// Data half of the backward: u and v per (d,k) -- grads += (1/S) sum_s of the upstream terms times the
+// stored factors (see PRE above) -- then, with da[s] = sum_k GA' u / eta still in registers, w and s of
+// the same feature.
 template <int KK>
 __global__ void __launch_bounds__(128)
-backward_dk_post_kernel(Layout L, const float* __restrict__ P, const float* __restrict__ N,
-                        const int* __restrict__ rank, int SV, int KP, const float* __restrict__ GAp,
-                        const float* __restrict__ GEVnz, const double* __restrict__ zcolsum,
-                        const float* __restrict__ fac, float* __restrict__ grads, float* __restrict__ scr_da) {
+backward_dk_post_kernel(Layout L, Hyper h, const float* __restrict__ P, const float* __restrict__ N,
+                        const float* __restrict__ eta, const int* __restrict__ rank, int SV, int KP,
+                        const float* __restrict__ GAp, const float* __restrict__ GEVnz,
+                        const float* __restrict__ Gphinz, const double* __restrict__ zcolsum,
+                        const float* __restrict__ fac, float* __restrict__ grads) {
   const int lane = threadIdx.x & 31;
   const int d = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (d >= L.D) return;
@@ -279,6 +281,7 @@ backward_dk_post_kernel(Layout L, const float* __restrict__ P, const float* __re
   float au[KK], aue[KK], av[KK], ave[KK];
 #pragma unroll
   for (int i = 0; i < KK; ++i) { au[i] = 0.f; aue[i] = 0.f; av[i] = 0.f; ave[i] = 0.f; }
+  float da_mine[2] = {0.f, 0.f};               // S <= 64 draws (checked by the launcher)
   for (int s = 0; s < L.S; ++s) {
     const int q = s / SV, sv = s - q * SV;
     float da = 0.f;
@@ -300,9 +303,45 @@ backward_dk_post_kernel(Layout L, const float* __restrict__ P, const float* __re
       }
     }
     da = warp_sum(da);
-    if (lane == 0) scr_da[(long long)s * L.D + d] = da;
+    if ((s & 31) == lane) da_mine[s >> 5] = da;       // lane s % 32 keeps draw s for the per-feature half below
   }
   const float invS = 1.f / (float)L.S;
+  // per-feature tensors w, s (poisson.py:661-663, 694-701 chain rule): lane s takes draw s, the six
+  // accumulators meet in a butterfly.  (Was a kernel of its own reading da[s][d] back.)
+  {
+    const long long D = L.D;
+    FeatState f;
+    f.w = nparam_init(P[L.toff[W_LOC] + d], P[L.toff[W_RHO] + d]);
+    f.s0 = nparam_init(P[L.toff[S_LOC] + d], P[L.toff[S_RHO] + d]);
+    f.s1 = nparam_init(P[L.toff[S_LOC] + D + d], P[L.toff[S_RHO] + D + d]);
+    float aw = 0.f, awe = 0.f, a0 = 0.f, a0e = 0.f, a1 = 0.f, a1e = 0.f;
+    for (int s = lane; s < L.S; s += 32) {
+      const int q = s / SV, sv = s - q * SV;
+      const FeatDraw fd = feat_draw(f, L, N, d, s);
+      const float da = da_mine[s >> 5];
+      const float Gphi = Gphinz[((long long)q * D + dr) * SV + sv] - h.batch_rows;     // d L / d phi_d
+      const float dw_data = eta[d] * fd.b * Gphi;                                     // phi = eta b w
+      const float db = eta[d] * fd.w.y * Gphi;
+      const float inv = 1.f / (fd.s0.y + fd.s1.y), inv2 = inv * inv;
+      const float ds0_data = (da - db) * fd.s1.y * inv2;
+      const float ds1_data = (db - da) * fd.s0.y * inv2;
+      const float tw = -dw_data * fd.w.sg, t0 = -ds0_data * fd.s0.sg, t1 = -ds1_data * fd.s1.sg;
+      aw += tw;  awe = fmaf(tw, N[L.noff[VAR_W] + s * D + d], awe);
+      a0 += t0;  a0e = fmaf(t0, N[L.noff[VAR_S] + s * 2 * D + d], a0e);
+      a1 += t1;  a1e = fmaf(t1, N[L.noff[VAR_S] + s * 2 * D + D + d], a1e);
+    }
+    aw = warp_sum(aw);  awe = warp_sum(awe);
+    a0 = warp_sum(a0);  a0e = warp_sum(a0e);
+    a1 = warp_sum(a1);  a1e = warp_sum(a1e);
+    if (lane == 0) {
+      grads[L.toff[W_LOC] + d] += aw * invS;
+      grads[L.toff[W_RHO] + d] += awe * invS * sigmoidf(P[L.toff[W_RHO] + d]);
+      grads[L.toff[S_LOC] + d] += a0 * invS;
+      grads[L.toff[S_RHO] + d] += a0e * invS * sigmoidf(P[L.toff[S_RHO] + d]);
+      grads[L.toff[S_LOC] + D + d] += a1 * invS;
+      grads[L.toff[S_RHO] + D + d] += a1e * invS * sigmoidf(P[L.toff[S_RHO] + D + d]);
+    }
+  }
 #pragma unroll
   for (int i = 0; i < KK; ++i) {
     const int k = lane + 32 * i;
@@ -314,43 +353,6 @@ backward_dk_post_kernel(Layout L, const float* __restrict__ P, const float* __re
       grads[L.toff[V_RHO] + e] += ave[i] * invS * sigmoidf(P[L.toff[V_RHO] + e]);
     }
   }
-}
-
-// Data half of the per-feature backward: w, s (poisson.py:661-663, 694-701 chain rule).
-__global__ void __launch_bounds__(128)
-backward_feat_post_kernel(Layout L, Hyper h, const float* __restrict__ P, const float* __restrict__ N,
-                          const float* __restrict__ eta, const int* __restrict__ rank, int SV,
-                          const float* __restrict__ Gphinz, const float* __restrict__ scr_da,
-                          float* __restrict__ grads) {
-  const int d = blockIdx.x * blockDim.x + threadIdx.x;
-  if (d >= L.D) return;
-  const int dr = rank ? rank[d] : d;
-  const long long D = L.D;
-  FeatState f;
-  feat_init(f, L, P, d);
-  float aw = 0.f, awe = 0.f, a0 = 0.f, a0e = 0.f, a1 = 0.f, a1e = 0.f;
-  for (int s = 0; s < L.S; ++s) {
-    const int q = s / SV, sv = s - q * SV;
-    const FeatDraw fd = feat_draw(f, L, N, d, s);
-    const float da = scr_da[(long long)s * D + d];
-    const float Gphi = Gphinz[((long long)q * D + dr) * SV + sv] - h.batch_rows;     // d L / d phi_d
-    const float dw_data = eta[d] * fd.b * Gphi;                                     // phi = eta b w
-    const float db = eta[d] * fd.w.y * Gphi;
-    const float inv = 1.f / (fd.s0.y + fd.s1.y), inv2 = inv * inv;
-    const float ds0_data = (da - db) * fd.s1.y * inv2;
-    const float ds1_data = (db - da) * fd.s0.y * inv2;
-    const float tw = -dw_data * fd.w.sg, t0 = -ds0_data * fd.s0.sg, t1 = -ds1_data * fd.s1.sg;
-    aw += tw;  awe = fmaf(tw, N[L.noff[VAR_W] + s * D + d], awe);
-    a0 += t0;  a0e = fmaf(t0, N[L.noff[VAR_S] + s * 2 * D + d], a0e);
-    a1 += t1;  a1e = fmaf(t1, N[L.noff[VAR_S] + s * 2 * D + D + d], a1e);
-  }
-  const float invS = 1.f / (float)L.S;
-  grads[L.toff[W_LOC] + d] += aw * invS;
-  grads[L.toff[W_RHO] + d] += awe * invS * sigmoidf(P[L.toff[W_RHO] + d]);
-  grads[L.toff[S_LOC] + d] += a0 * invS;
-  grads[L.toff[S_RHO] + d] += a0e * invS * sigmoidf(P[L.toff[S_RHO] + d]);
-  grads[L.toff[S_LOC] + D + d] += a1 * invS;
-  grads[L.toff[S_RHO] + D + d] += a1e * invS * sigmoidf(P[L.toff[S_RHO] + D + d]);
 }
 
 // ------------------------------------------------------------------ backward, per-feature tensors
@@ -377,7 +379,7 @@ backward_feat_kernel(Layout L, Hyper h, const float* __restrict__ P, const float
     const int q = s / SV, sv = s - q * SV;
     FeatDraw fd = feat_draw(f, L, N, d, s);
     float fp[7];
-    // pre: data-independent half (upstream da = 0, dL/dphi = 0); backward_feat_post_kernel adds the rest
+    // pre: data-independent half (upstream da = 0, dL/dphi = 0); the data half of backward_dk_post_kernel adds the rest
     feat_step(f, fd, L, h, N, G, eta, d, s, pre ? 0.f : scr_da[(long long)s * L.D + d],
               pre ? h.batch_rows : Gphinz[((long long)q * L.D + dr) * SV + sv], fp);
     if (valid) {
@@ -696,17 +698,28 @@ int spmf_draw_operands(const float* params, const float* noise, const float* eta
 int spmf_draw_operands_ranked(const float* params, const float* noise, const float* eta, const int* rank,
                               int D, int K, int S, float* Ap, float* EV, float* PH, double* vsum,
                               double* phisum, double* scratch, void* stream) {
-  if (!params || !noise || !eta || !Ap || !EV || !PH || !vsum || !phisum || !scratch) return SPMF_ERR_BAD_ARG;
+  if (!params || !noise || !eta || !Ap || !EV || !PH) return SPMF_ERR_BAD_ARG;
+  if ((vsum == nullptr) != (phisum == nullptr) || (vsum && !scratch)) return SPMF_ERR_BAD_ARG;
   if (D <= 0 || K <= 0 || S <= 0 || K > SPMF_MAX_K) return SPMF_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   Layout L = make_layout(D, K, S);
-  const int KP = spmf_kpad(K), SV = spmf_draw_vec(S), NQ = S / SV;
+  const int KP = spmf_kpad(K), SV = spmf_draw_vec(S);
   dim3 grid((D + 3) / 4);
   if (KP <= 32) draw_operands_kernel<1><<<grid, 128, 0, st>>>(L, params, noise, eta, rank, SV, KP, Ap, EV, PH);
   else if (KP <= 64) draw_operands_kernel<2><<<grid, 128, 0, st>>>(L, params, noise, eta, rank, SV, KP, Ap, EV, PH);
   else draw_operands_kernel<4><<<grid, 128, 0, st>>>(L, params, noise, eta, rank, SV, KP, Ap, EV, PH);
   SPMF_CHECK_LAUNCH();
-  return reduce_rows_pair(EV, vsum, D, KP * SV, NQ, PH, phisum, D, SV, NQ, scratch, st);
+  if (!vsum) return SPMF_OK;        // the caller runs spmf_operand_sums itself (on another stream)
+  return spmf_operand_sums(EV, PH, D, K, S, vsum, phisum, scratch, stream);
+}
+
+/* vsum[q][rec] = sum_d EV, phisum[q][sv] = sum_d PH (fp64): the closed-form -sum lambda terms. */
+int spmf_operand_sums(const float* EV, const float* PH, int D, int K, int S, double* vsum, double* phisum,
+                      double* scratch, void* stream) {
+  if (!EV || !PH || !vsum || !phisum || !scratch) return SPMF_ERR_BAD_ARG;
+  if (D <= 0 || K <= 0 || S <= 0 || K > SPMF_MAX_K) return SPMF_ERR_BAD_ARG;
+  const int KP = spmf_kpad(K), SV = spmf_draw_vec(S), NQ = S / SV;
+  return reduce_rows_pair(EV, vsum, D, KP * SV, NQ, PH, phisum, D, SV, NQ, scratch, (cudaStream_t)stream);
 }
 
 int spmf_gamma_grad(const float* params, const float* noise, int D, int K, int S, float* dgda,
@@ -844,10 +857,10 @@ int spmf_backward_post(const float* params, const float* noise, const float* eta
   const double* featparts = scr_d + (long long)S * K;
   const double* latparts = featparts + (long long)S * NUM_PARTS;
   dim3 grid((D + 3) / 4);
-  if (KP <= 32) backward_dk_post_kernel<1><<<grid, 128, 0, st>>>(L, params, noise, rank, SV, KP, GAp, GEVnz, zcolsum, fac, grads, scr_da);
-  else if (KP <= 64) backward_dk_post_kernel<2><<<grid, 128, 0, st>>>(L, params, noise, rank, SV, KP, GAp, GEVnz, zcolsum, fac, grads, scr_da);
-  else backward_dk_post_kernel<4><<<grid, 128, 0, st>>>(L, params, noise, rank, SV, KP, GAp, GEVnz, zcolsum, fac, grads, scr_da);
-  backward_feat_post_kernel<<<(D + 127) / 128, 128, 0, st>>>(L, h, params, noise, eta, rank, SV, Gphinz, scr_da, grads);
+  if (S > 64) return SPMF_ERR_BAD_ARG;
+  if (KP <= 32) backward_dk_post_kernel<1><<<grid, 128, 0, st>>>(L, h, params, noise, eta, rank, SV, KP, GAp, GEVnz, Gphinz, zcolsum, fac, grads);
+  else if (KP <= 64) backward_dk_post_kernel<2><<<grid, 128, 0, st>>>(L, h, params, noise, eta, rank, SV, KP, GAp, GEVnz, Gphinz, zcolsum, fac, grads);
+  else backward_dk_post_kernel<4><<<grid, 128, 0, st>>>(L, h, params, noise, eta, rank, SV, KP, GAp, GEVnz, Gphinz, zcolsum, fac, grads);
   finalize_parts_kernel<<<1, ((S + 31) / 32) * 32, 0, st>>>(S, SV, K, featparts, latparts, datasums, phisum,
                                                            (double)batch_rows, (double)w_entropy, (double)w_prior,
                                                            parts, grads + L.comm_off);

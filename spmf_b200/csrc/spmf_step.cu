@@ -58,8 +58,12 @@ int spmf_advi_step(const spmf_step_args* a) {
                                a->scr_f, a->scr_dpre, side));
   }
   if (side != hot) CUDA_TRY(cudaEventRecord((cudaEvent_t)a->ev_join, side));
+  // (tile mode with auxiliary streams: the fp64 operand sums are first read by spmf_rows_finish, so
+  // they leave the critical path and run next to the encode GEMM)
+  const bool pre_fork = hybrid && a->hot_mode == 2 && a->EVt && a->aux_stream1 && a->ev_aux_fork && a->ev_aux_join1;
   STEP_TRY(spmf_draw_operands_ranked(a->params, a->noise, a->eta, hybrid ? a->rank : nullptr, D, K, S, a->Ap, a->EV,
-                                     a->PH, a->vsum, a->phisum, a->scr_d, hot));
+                                     a->PH, pre_fork ? nullptr : a->vsum, pre_fork ? nullptr : a->phisum, a->scr_d,
+                                     hot));
   const int KP = spmf_kpad(K), SV = spmf_draw_vec(S), NQ = S / SV, REC = KP * SV;
   if (a->ev_rows0) CUDA_TRY(cudaEventRecord((cudaEvent_t)a->ev_rows0, hot));
   if (!hybrid) {
@@ -71,13 +75,13 @@ int spmf_advi_step(const spmf_step_args* a) {
     const int Hp = (H + 63) / 64 * 64;
     // the EV / phi tile blocks and the zeroing of the column-gradient tables do not depend on the
     // GEMM: run them next to it on an auxiliary stream when one is available
-    const bool pre_fork = a->hot_mode == 2 && a->EVt && a->aux_stream1 && a->ev_aux_fork && a->ev_aux_join1;
     if (pre_fork) {
       cudaStream_t s1 = (cudaStream_t)a->aux_stream1;
       CUDA_TRY(cudaEventRecord((cudaEvent_t)a->ev_aux_fork, hot));
       CUDA_TRY(cudaStreamWaitEvent(s1, (cudaEvent_t)a->ev_aux_fork, 0));
       STEP_TRY(spmf_hot_ev_tiles(a->EV, a->PH, D, H, K, S, a->EVt, s1));
       STEP_TRY(spmf_zero_col_grads(a->GAp, a->GEV, a->Gph, D, K, S, s1));
+      STEP_TRY(spmf_operand_sums(a->EV, a->PH, D, K, S, a->vsum, a->phisum, a->scr_d, s1));
       CUDA_TRY(cudaEventRecord((cudaEvent_t)a->ev_aux_join1, s1));
     }
     STEP_TRY(spmf_split3_transpose(a->Ap, REC, (long long)D * REC, H, Hp, REC, a->ApT3, a->t3_qstride, NQ, hot));
@@ -107,7 +111,10 @@ int spmf_advi_step(const spmf_step_args* a) {
     }
   }
   if (a->ev_rows1) CUDA_TRY(cudaEventRecord((cudaEvent_t)a->ev_rows1, hot));
-  STEP_TRY(spmf_batch_sums(a->z, a->rowacc, a->nrows, K, S, a->zcolsum, a->datasums, a->scr_d, hot));
+  // column sums of z and the batch totals: only the backward reads them -> next to the column side
+  const bool cols_fork = hybrid && a->aux_stream1 && a->aux_stream2 && a->ev_aux_fork && a->ev_aux_join1 && a->ev_aux_join2;
+  if (!cols_fork)
+    STEP_TRY(spmf_batch_sums(a->z, a->rowacc, a->nrows, K, S, a->zcolsum, a->datasums, a->scr_d, hot));
   if (a->ev_cols0) CUDA_TRY(cudaEventRecord((cudaEvent_t)a->ev_cols0, hot));
   if (!hybrid) {
     STEP_TRY(spmf_csc_cols(a->colptr, a->crows, a->cvals, a->nnz, a->nrows, D, K, S, a->z, a->dzr, a->EV, a->PH,
@@ -119,7 +126,7 @@ int spmf_advi_step(const spmf_step_args* a) {
     //   cold CSC (everything else): GEV, Gphi, GA'    -- gather kernel, aux stream 2
     const int H = a->hot_cols;
     const int Bp = (a->nrows + 127) / 128 * 128;     // whole 128-row tiles of the count block
-    const bool fork = a->aux_stream1 && a->aux_stream2 && a->ev_aux_fork && a->ev_aux_join1 && a->ev_aux_join2;
+    const bool fork = cols_fork;
     cudaStream_t s1 = fork ? (cudaStream_t)a->aux_stream1 : hot;
     cudaStream_t s2 = fork ? (cudaStream_t)a->aux_stream2 : hot;
     if (a->hot_mode != 2) STEP_TRY(spmf_zero_col_grads(a->GAp, a->GEV, a->Gph, D, K, S, hot));
@@ -128,6 +135,7 @@ int spmf_advi_step(const spmf_step_args* a) {
       CUDA_TRY(cudaStreamWaitEvent(s1, (cudaEvent_t)a->ev_aux_fork, 0));
       CUDA_TRY(cudaStreamWaitEvent(s2, (cudaEvent_t)a->ev_aux_fork, 0));
     }
+    if (fork) STEP_TRY(spmf_batch_sums(a->z, a->rowacc, a->nrows, K, S, a->zcolsum, a->datasums, a->scr_d, s1));
     if (a->ev_gemm0) CUDA_TRY(cudaEventRecord((cudaEvent_t)a->ev_gemm0, s1));
     STEP_TRY(spmf_split3_transpose(a->dzr, REC, (long long)a->nrows * REC, a->nrows, Bp, REC, a->dzrT3,
                                    a->t3_qstride, NQ, s1));

@@ -302,9 +302,11 @@ class AdviEngine:
         if do_adam:
             self.opt_step += 1
         # kernels issued by spmf_advi_step (counted against the ncu launch lists under profiles/):
-        # 18 in gather mode, +5 GEMM-hybrid (2 splits, 2 GEMMs, second column kernel), +7 tile-hybrid
-        # (2 splits, 2 GEMMs, EV tiles, tile kernel, row finalisation); +1 Adam
-        self.launches += 18 + (1 if do_adam else 0) + ((7 if self.hot_mode == 2 else 5) if hybrid else 0)
+        # 17 in gather mode with the split backward (16 with the one-pass backward), +5 GEMM-hybrid
+        # (2 splits, 2 GEMMs, second column kernel), +7 tile-hybrid (2 splits, 2 GEMMs, EV tiles, tile
+        # kernel, row finalisation); +1 Adam
+        base = 17 if a.scr_dpre else 16
+        self.launches += base + (1 if do_adam else 0) + ((7 if self.hot_mode == 2 else 5) if hybrid else 0)
         return w.parts.view(self.S, _abi.NUM_PARTS)
 
     def loss_and_grad(self, batch: DeviceBatch, fresh_noise=True, variant=0):
