@@ -151,7 +151,7 @@ __device__ __forceinline__ void ld_idx(const int* __restrict__ pc, const float* 
 constexpr int kRowsTrain = 0, kRowsEncode = 1, kRowsHybrid = 2, kRowsCold = 3;
 
 template <int KP, int SV, int MODE>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, (MODE == kRowsCold && KP * SV == 128) ? 5 : 1)
 csr_rows_kernel(const long long* __restrict__ rowptr, const int* __restrict__ cols,
                 const float* __restrict__ vals, const float* __restrict__ rowsum,
                 const float* __restrict__ lgam, float inv_xi, int scale_rows, int nrows, int D,
