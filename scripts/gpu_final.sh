@@ -14,5 +14,5 @@ ncu --metrics gpu__time_duration.sum --clock-control none --nvtx --nvtx-include 
     --log-file gpurun_out/launches_$TAG.csv $CMD > gpurun_out/ncu_list.log 2>&1
 echo "ncu list rc=$?"
 ncu --set full --clock-control none --import-source on --nvtx --nvtx-include "spmf_timed/" \
-    -k regex:'hot_tile_kernel|csr_rows_kernel|csc_cols_kernel|umma_gemm3_kernel|backward_dk_kernel' -c 6 -f -o gpurun_out/prof_$TAG $CMD > gpurun_out/ncu_full.log 2>&1
+    -k regex:'hot_tile_kernel|csr_rows_|csc_cols_kernel|umma_gemm3_kernel|backward_dk_kernel|gamma_kernel' -c 7 -f -o gpurun_out/prof_$TAG $CMD > gpurun_out/ncu_full.log 2>&1
 echo "ncu full rc=$?"; tail -2 gpurun_out/ncu_full.log
