@@ -12,6 +12,7 @@
 // nonzero at a time and gathers its record with VPL coalesced vector loads; every lane holds up to
 // 16 latent dims of one draw, so the k-contraction is in-lane FMAs plus log2(RG) shuffle steps.
 #include <cuda_runtime.h>
+#include <stdlib.h>
 #include <stdint.h>
 
 #include "../../include/spmf_b200.h"
@@ -1300,7 +1301,11 @@ static int launch_hot_split(const long long* rowptr, const CT* cols, const VT* v
   const long long hp = (H + 63) / 64 * 64;
   const size_t stash = (size_t)kSplitStash * sizeof(int2);
   const size_t smem = (size_t)hp * 2 + stash;
-  if (smem <= 112 * 1024) {
+  static const bool force_scatter = [] {           // test hook: exercise the wide-block fallback on small inputs
+    const char* e = getenv("SPMF_SPLIT_UNSTAGED");
+    return e && e[0] == '1';
+  }();
+  if (smem <= 112 * 1024 && !force_scatter) {
     // staged: every 16-byte chunk of the 128-row-padded block is written by the kernel (no memset)
     static bool attr = false;
     if (!attr) {

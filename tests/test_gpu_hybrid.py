@@ -80,6 +80,20 @@ def test_umma_gemm3_matches_float64(M, N, Kd, NQ, splits):
     assert float(errt) < 2e-6, float(errt)
 
 
+def test_hot_split_wide_block_fallback():
+    """The direct-scatter variant of the split (hot blocks too wide for shared-memory staging), forced
+    on a small input in a fresh process: same hybrid form as the staged kernel."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, SPMF_SPLIT_UNSTAGED="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", os.path.join(root, "tests", "test_gpu_hybrid.py"),
+                        "-k", "partitions_and_fills or fit_reduces"], env=env, cwd=root, capture_output=True,
+                       text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 def test_hot_split_partitions_and_fills_dense_block():
     from spmf_b200 import _abi
     from spmf_b200.data import CsrShard
