@@ -3,8 +3,9 @@
 Replaces, for `PoissonFactorization`, what bayesianquilts' `minibatch_fit_surrogate_posterior`
 does per batch in the reference stack [EXT L3/L4] (call site tests/spmf_test.py:35-43):
 draw S reparameterised samples, evaluate `log q - unormalized_log_prob` (poisson.py:575-621) and
-back-propagate to the 24 variational tensors -- as six fused CUDA launches instead of a
-TensorFlow graph, never materialising the (S,B,D) rate tensor of poisson.py:174-184.
+back-propagate to the 24 variational tensors -- as one native call (`spmf_advi_step`, ~25 kernel
+launches over five streams in hybrid mode) instead of a TensorFlow graph, never materialising the
+(S,B,D) rate tensor of poisson.py:174-184.
 """
 from __future__ import annotations
 
