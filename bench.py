@@ -434,7 +434,10 @@ def main():
                        "parallelism": f"dp{world} row-sharded, 1 all-reduce/step",
                        "l2": "inputs larger than L2 (16 distinct batches cycled; ~130 MB of CSR+CSC each, "
                              "plus ~260 MB of bf16 hot block in hybrid mode)",
-                       "variant": args.variant, "final_loss": final_loss},
+                       "variant": args.variant, "final_loss": final_loss,
+                       # work/t and work*S/t -- `value` counts each nonzero once per step;
+                       # every one is evaluated for all S draws
+                       "nnzK_times_draws_per_s": value * S},
             "e2e": {"value": e2e_value, "unit": "nonzeros*K/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": 8, "ms_per_step": float(t2.item()) / args.steps},
             "gpu_launches": launches,
