@@ -299,7 +299,7 @@ def main():
         src = (hbatches[(start + i) % len(hbatches)] for i in range(n))
         prev = None
         tlast = time.perf_counter()
-        for i, db in enumerate(prefetch_to_device(src, dev, hot=(model.col_rank, model.hot_cols, eng.hot_mode != 2) if hybrid else None)):
+        for i, db in enumerate(prefetch_to_device(src, dev, hot=model._hot_spec(eng) if hybrid else None)):
             if os.environ.get("BENCH_DEBUG"):
                 tnow = time.perf_counter()
                 print(f"e2e iter {i} host dt {1e3 * (tnow - tlast):.2f} ms", file=sys.stderr)

@@ -24,7 +24,7 @@ class SpmfError(RuntimeError):
 def _load():
     if not os.path.exists(LIB_PATH):
         raise ImportError(
-            f"{LIB_PATH} not found: build it with `python -m spmf_b200.build` "
+            f"{LIB_PATH} not found: build it with `python spmf_b200/build.py` "
             "(nvcc, sm_100a).  spmf_b200 has no CPU fallback.")
     return C.CDLL(LIB_PATH)
 

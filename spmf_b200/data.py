@@ -47,6 +47,7 @@ class HotSplit:
     hcrows: torch.Tensor
     hcvals: torch.Tensor
     has_hot_csc: bool = True
+    version: int = 0              # column-ordering version this form was built for
 
 
 @dataclass
@@ -65,13 +66,15 @@ class DeviceBatch:
     cvals: Optional[torch.Tensor] = None    # fp32 [nnz]
     hot: Optional[HotSplit] = None          # hybrid form (built for one (rank, H) ordering)
 
-    def ensure_hot(self, rank, H, bufs=None, hot_csc=True, row_consts=False, build_xt=False, packed=None):
+    def ensure_hot(self, rank, H, bufs=None, hot_csc=True, row_consts=False, build_xt=False, packed=None,
+                   version=0):
         """Build (once) the hybrid form for the column ordering `rank` (int32 [D] device tensor) with
         H hot columns.  `bufs` may supply reusable staging (the streaming uploader).  `hot_csc`: also
         build the CSC copy of the covered entries (only the GEMM-only hybrid mode reads it; the tile
         mode gets those gradients from the tensor-core kernel).  `packed` = (cols16, vals16): read the
         compact upload format instead of self.cols / self.vals (either may be None = use the wide array)."""
-        if self.hot is not None and self.hot.H == H and (self.hot.has_hot_csc or not hot_csc):
+        if (self.hot is not None and self.hot.H == H and self.hot.version == version
+                and (self.hot.has_hot_csc or not hot_csc)):
             return self.hot
         dev = self.rowptr.device
         n, nnz = self.nrows, self.nnz
@@ -109,7 +112,7 @@ class DeviceBatch:
                             rowmid=bufs["rowmid"], xhot=bufs["xhot"], xthot=bufs.get("xthot"),
                             colptr=bufs["colptr"], crows=bufs["crows"], cvals=bufs["cvals"],
                             hcolptr=bufs["hcolptr"], hcrows=bufs["hcrows"], hcvals=bufs["hcvals"],
-                            has_hot_csc=bool(hot_csc))
+                            has_hot_csc=bool(hot_csc), version=version)
         return self.hot
 
     def ensure_csc(self):
@@ -367,6 +370,7 @@ class BatchUploader:
         # hot = (rank, H[, need_hot_csc])
         self.hot = hot if (hot is not None and hot[0] is not None and hot[1] > 0) else None
         self.hot_csc = bool(hot[2]) if (self.hot is not None and len(hot) > 2) else True
+        self.hot_version = int(hot[3]) if (self.hot is not None and len(hot) > 3) else 0
         self._alloc(max_rows, max_nnz)
 
     def _alloc(self, rows, nnz):
@@ -427,7 +431,7 @@ class BatchUploader:
                              lgam=self.lgam[:n], nrows=n, nnz=nnz, D=self.D)
             db.ensure_hot(self.hot[0], int(self.hot[1]), bufs=self.hot_bufs, hot_csc=self.hot_csc,
                           row_consts=True,          # row constants come out of the split's first pass
-                          packed=(c16, v16))
+                          packed=(c16, v16), version=self.hot_version)
             return db
         _abi.call("spmf_prepare_batch", _ptr(c16), _ptr(v16), _ptr(self.rowptr), _ptr(self.cols),
                   _ptr(self.vals), n, nnz, self.D, _ptr(self.rowsum), _ptr(self.lgam), _ptr(self.colptr),

@@ -52,15 +52,20 @@ class StepWorkspace:
         """bf16 three-term operands of the tcgen05 GEMMs (UMMA-tiled B3): ApT3 over the hot columns,
         dzrT3 over the batch rows; one block of `t3_qstride` elements per draw group."""
         kd = max((int(H) + 63) // 64 * 64, (int(nrows) + 127) // 128 * 128)
-        if getattr(self, "t3_kd", 0) >= kd:
-            return False
-        self.t3_kd = kd
-        self.t3_qstride = int(_abi._lib.spmf_umma_tiled_b_elems(self.KP * self.SV, kd))
-        self.ApT3 = torch.zeros(self.NQ * self.t3_qstride, dtype=torch.bfloat16, device=self.device)
-        self.dzrT3 = torch.zeros(self.NQ * self.t3_qstride, dtype=torch.bfloat16, device=self.device)
-        self.EVt = torch.zeros(max(int(_abi._lib.spmf_hot_tile_scratch_bytes(int(H), self.K, self.S)), 16),
-                               dtype=torch.uint8, device=self.device)
-        return True
+        changed = False
+        if getattr(self, "t3_kd", 0) < kd:
+            self.t3_kd = kd
+            self.t3_qstride = int(_abi._lib.spmf_umma_tiled_b_elems(self.KP * self.SV, kd))
+            self.ApT3 = torch.zeros(self.NQ * self.t3_qstride, dtype=torch.bfloat16, device=self.device)
+            self.dzrT3 = torch.zeros(self.NQ * self.t3_qstride, dtype=torch.bfloat16, device=self.device)
+            changed = True
+        # the EV / phi tile workspace is sized by H alone (not by kd): track it separately
+        evt_bytes = max(int(_abi._lib.spmf_hot_tile_scratch_bytes(int(H), self.K, self.S)), 16)
+        if getattr(self, "evt_bytes", 0) < evt_bytes:
+            self.evt_bytes = evt_bytes
+            self.EVt = torch.zeros(evt_bytes, dtype=torch.uint8, device=self.device)
+            changed = True
+        return changed
 
     def ensure_rows(self, nrows):
         if nrows <= self.max_rows:
@@ -247,10 +252,14 @@ class AdviEngine:
             self._args = None
         hybrid = self.hot_cols > 0 and self.hybrid_ok and self.rank is not None and batch.nnz > 0
         if hybrid:
-            h = batch.ensure_hot(self.rank, self.hot_cols, hot_csc=(self.hot_mode != 2))
+            h = batch.ensure_hot(self.rank, self.hot_cols, hot_csc=(self.hot_mode != 2),
+                                 version=getattr(self, "rank_version", 0))
             if w.ensure_hybrid(self.hot_cols, batch.nrows):
                 self._args = None
         else:
+            if batch.cols is None or batch.vals is None:
+                raise _abi.SpmfError("this batch was uploaded in hybrid-only form (no CSR arrays) but the engine "
+                                     f"for S={self.S} runs the gather step; upload it without a hot split")
             batch.ensure_csc()
         a = self._step_args()
         a.z, a.dzr, a.rowacc = _ptr(w.z), _ptr(w.dzr), _ptr(w.rowacc)

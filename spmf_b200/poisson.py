@@ -51,7 +51,8 @@ class _SurrogateDistribution:
         m = self._m
         S = 1 if n is None else int(n)
         eng = m._engine_for(S)
-        eng.fill_noise(step=(seed if seed is not None else eng.rng_step))
+        # a sampling call must not move the training stream's Philox counter (fit continues where it was)
+        eng.fill_noise(step=(seed if seed is not None else eng.rng_step), advance=seed is None)
         out = {k: v.clone() for k, v in eng.samples().items()}
         if n is None:
             out = {k: v[0] for k, v in out.items()}
@@ -161,6 +162,7 @@ class PoissonFactorization:
         eng.inv_xi = 1.0 / xi if self.scale_rows else 1.0
         eng.scale_rows = bool(self.scale_rows)
         eng.rank, eng.hot_cols = self.col_rank, int(self.hot_cols)
+        eng.rank_version = getattr(self, "_rank_version", 0)
 
     @property
     def surrogate_vars(self):
@@ -212,17 +214,22 @@ class PoissonFactorization:
         self._choose_hot_columns(colnnz, float(nrows_all.item()))
         self._set_scales_from_stats(colsum.cpu(), colnnz.cpu())
 
-    def _hot_mode(self):
-        for eng in self._engines.values():
-            return eng.hot_mode
-        return int(os.environ.get("SPMF_HOT_MODE", "2"))
+    def _hot_spec(self, eng):
+        """(rank, H, need_hot_csc) for the streaming uploader, decided by the engine that will consume
+        the batches: the hybrid form is only built when THAT engine (its S decides KP*SV) runs the
+        hybrid step; otherwise batches keep their plain CSR + CSC form."""
+        if eng.hybrid_ok and eng.hot_cols > 0 and eng.rank is not None:
+            return (eng.rank, int(eng.hot_cols), eng.hot_mode != 2, getattr(eng, "rank_version", 0))
+        return None
 
     def _choose_hot_columns(self, colnnz, nrows):
         """Column ordering for the hybrid step: features ranked by how many rows populate them; the
         H columns populated in >= hot_density of the rows form the tensor-core block.  Identical on
         every rank (computed from the all-reduced counts)."""
         self.col_rank, self.hot_cols = None, 0
-        if self.hot_density <= 0 or nrows <= 0 or not _abi._lib.spmf_hybrid_supported(self.latent_dim, 4):
+        self._rank_version = getattr(self, "_rank_version", 0) + 1     # invalidates cached hybrid forms
+        # (whether a given engine uses the hot block is its own decision: hybrid_ok depends on S)
+        if self.hot_density <= 0 or nrows <= 0 or self.latent_dim > _abi.MAX_K:
             return
         order = torch.argsort(colnnz.to(torch.float64), descending=True, stable=True)
         H = int((colnnz.to(torch.float64) >= self.hot_density * nrows).sum().item())
@@ -490,7 +497,11 @@ class PoissonFactorization:
         for epoch in range(int(num_steps)):
             acc = torch.zeros((), dtype=torch.float64, device=self.device)
             nb, last = 0, None
-            for batch in self._device_batches(batched_data_factory()):
+            batches = batched_data_factory()
+            limit = self._common_batch_count(batches) if eng.world_size > 1 else None
+            for batch in self._device_batches(batches, eng):
+                if limit is not None and nb >= limit:
+                    break              # ranks must issue the same number of all-reduces per epoch
                 last = self.elbo_step(batch, S, learning_rate=lr, clip_value=clip_value)
                 acc += last
                 nb += 1
@@ -536,7 +547,22 @@ class PoissonFactorization:
 
     calibrate_advi = fit     # legacy name used by bin/factorize_csv.py:121-124
 
-    def _device_batches(self, batches):
+    def _common_batch_count(self, batches):
+        """Multi-GPU: every rank must run the same number of steps per epoch (one all-reduce each).  When
+        the per-rank batch count is known (`len()`), agree on the minimum across ranks and truncate;
+        iterables without a length must be balanced by the caller (e.g. drop_remainder sharding)."""
+        try:
+            n = len(batches)
+        except TypeError:
+            return None
+        t = torch.tensor([n, -n], dtype=torch.int64, device=self.device)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MIN, group=self.process_group)
+        lo, hi = int(t[0].item()), -int(t[1].item())
+        if lo != hi:
+            print(f"[spmf_b200] ranks hold {lo}..{hi} batches per epoch; truncating every rank to {lo}")
+        return lo
+
+    def _device_batches(self, batches, eng):
         """Host-resident CSR batches are uploaded one ahead on a copy stream; anything else passes through."""
         from .data import HostCsrBatch, prefetch_to_device
         it = iter(batches)
@@ -549,7 +575,7 @@ class PoissonFactorization:
         c = first[self.count_key] if isinstance(first, dict) else first
         if isinstance(c, HostCsrBatch):
             return prefetch_to_device((b[self.count_key] if isinstance(b, dict) else b for b in chained),
-                                      self.device, hot=(self.col_rank, self.hot_cols, self._hot_mode() != 2))
+                                      self.device, hot=self._hot_spec(eng))
         return chained
 
     @staticmethod

@@ -11,7 +11,11 @@ if ROOT not in sys.path:
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
     # The C-ABI library is a build artefact (git-ignored): make sure it exists before collection.
-    from spmf_b200 import build as _b
+    # (loaded by path: importing the package needs the library to exist already)
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_spmf_b200_build", os.path.join(ROOT, "spmf_b200", "build.py"))
+    _b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(_b)
     _b.build()
 
 
