@@ -55,8 +55,6 @@ def main(argv=None):
         sys.exit("You need to specify a csv file")
     if not os.path.exists(args.csv_file):
         sys.exit("File doesn't exist")
-    if args.log_transform:
-        sys.exit("--log-transform has no CUDA path in spmf_b200")
 
     import torch
     import spmf_b200
@@ -68,7 +66,7 @@ def main(argv=None):
 
     factor = spmf_b200.PoissonFactorization(
         latent_dim=args.dimension, feature_dim=columns, strategy=None, scale_columns=True,
-        scale_rows=bool(args.row_normalize), log_transform=False,
+        scale_rows=bool(args.row_normalize), log_transform=bool(args.log_transform),
         u_tau_scale=1.0 / np.sqrt(columns * N), device=dev)      # bin/factorize_csv.py:114-119
     factor.compute_scales(shard)                                 # column scales (:84-96 computes them inline)
 

@@ -12,7 +12,9 @@
  *  - no allocation, no global state, asynchronous on `stream` (a cudaStream_t passed as void*);
  *  - return 0 on success, a negative SPMF_ERR_* for bad arguments / unsupported configurations,
  *    or a positive cudaError_t if a launch failed;
- *  - there is NO CPU fallback: without a CUDA device every compute entry point fails.
+ *  - there is NO CPU fallback: without a CUDA device every compute entry point fails;
+ *  - `gs` (where present, may be NULL) = device guard state (see "dense evaluation" below): the row passes
+ *    raise its flag when they meet a non-finite log-likelihood, the backward / loss-part kernels read it.
  *
  * Device layouts (KP = spmf_kpad(K), SV = spmf_draw_vec(S), NQ = S/SV; draw s = q*SV + sv):
  *   params / grads / adam moments : flat fp32, tensor offsets from spmf_layout()
@@ -75,7 +77,7 @@ int spmf_csr_row_consts(const long long* rowptr, const float* vals, long long nr
 int spmf_csr_rows(const long long* rowptr, const int* cols, const float* vals, const float* rowsum,
                   const float* lgam, float inv_xi, int scale_rows, int nrows, int D, int K, int S,
                   const float* Ap, const float* EV, const float* PH, const double* vsum, float* z,
-                  float* dzr, float* rowacc, int variant, void* stream);
+                  float* dzr, float* rowacc, int variant, void* gs, void* stream);
 /* encode only (inference): z[NQ][B][SV][KP] */
 int spmf_csr_encode(const long long* rowptr, const int* cols, const float* vals, const float* rowsum,
                     float inv_xi, int scale_rows, int nrows, int D, int K, int S, const float* Ap,
@@ -104,7 +106,7 @@ int spmf_backward_params(const float* params, const float* noise, const float* d
                          const double* zcolsum, const double* datasums, const double* phisum,
                          float batch_rows, float u_tau_scale, float s_tau_scale, float decay,
                          float w_entropy, float w_prior, int world_size, float* grads, double* parts,
-                         float* scratch_f, double* scratch_d, void* stream);
+                         float* scratch_f, double* scratch_d, void* gs, void* stream);
 
 /* The same backward in two halves: `pre` = everything that does not depend on the data term (prior +
  * entropy gradients of all 24 tensors, the loss parts) -- it can run on a side stream while the data
@@ -118,7 +120,7 @@ int spmf_backward_post(const float* params, const float* noise, const float* eta
                        int S, const float* GAp, const float* GEVnz, const float* Gphinz, const double* zcolsum,
                        const double* datasums, const double* phisum, float batch_rows, float u_tau_scale,
                        float s_tau_scale, float decay, float w_entropy, float w_prior, int world_size,
-                       float* grads, double* parts, float* scr_f, const double* scr_d, void* stream);
+                       float* grads, double* parts, float* scr_f, const double* scr_d, void* gs, void* stream);
 
 /* ---- optimiser [EXT L4: Adam + clip in bayesianquilts' batched_minimize] ---- */
 int spmf_adam_step(float* params, const float* grads, float* m, float* v, long long n, float lr,
@@ -171,7 +173,7 @@ int spmf_backward_params_ranked(const float* params, const float* noise, const f
                                 const float* Gphinz, const double* zcolsum, const double* datasums,
                                 const double* phisum, float batch_rows, float u_tau_scale, float s_tau_scale,
                                 float decay, float w_entropy, float w_prior, int world_size, float* grads,
-                                double* parts, float* scr_f, double* scr_d, void* stream);
+                                double* parts, float* scr_f, double* scr_d, void* gs, void* stream);
 /* Operands of the tcgen05 GEMM live in global memory "UMMA-tiled": tile by tile in the byte order the
  * tensor core reads from shared memory (K-major, no swizzle), so that a pipeline stage is two
  * contiguous TMA bulk copies.  A (bf16 counts): tiles [row/128][k/64] of 128 x 64; B3 (three bf16
@@ -221,7 +223,7 @@ int spmf_umma_probe(const void* a_img, int a_bytes, const void* b_img, int b_byt
 int spmf_csr_rows_hybrid(const long long* rowptr, const int* cols, const float* vals, const int* rowmid,
                          const float* rowsum, const float* lgam, float inv_xi, int scale_rows, int nrows,
                          int D, int K, int S, const float* Ap, const float* EV, const float* PH,
-                         const double* vsum, float* z, float* dzr, float* rowacc, void* stream);
+                         const double* vsum, float* z, float* dzr, float* rowacc, void* gs, void* stream);
 /* column pass over the two CSC copies of a hot-split batch: `hot_*` holds the covered entries (GEV and
  * Gphi only -- their GA' comes from the GEMM), `cold_*` the rest (full column pass).  Zeroes the three
  * tables first.  nnz_bound >= either copy's count (the counts themselves are colptr[D], device side). */
@@ -241,11 +243,11 @@ int spmf_hot_ev_tiles(const float* EV, const float* PH, int D, int H, int K, int
 int spmf_csr_rows_cold(const long long* rowptr, const int* cols, const float* vals, const int* rowmid,
                        const float* rowsum, float inv_xi, int scale_rows, int nrows, int D, int K, int S,
                        const float* Ap, const float* EV, const float* PH, float* z, float* dzacc, float* rowacc,
-                       void* stream);
+                       void* gs, void* stream);
 int spmf_hot_tile(const void* xhot, const void* EVt, const float* z, int nrows, int D, int H, int K, int S,
-                  float* dzacc, float* rowacc, float* GEVnz, float* Gphinz, void* stream);
+                  float* dzacc, float* rowacc, float* GEVnz, float* Gphinz, void* gs, void* stream);
 int spmf_rows_finish(const float* rowsum, const float* lgam, float inv_xi, int scale_rows, int nrows, int K, int S,
-                     const double* vsum, const float* z, float* dzr, float* rowacc, void* stream);
+                     const double* vsum, const float* z, float* dzr, float* rowacc, void* gs, void* stream);
 /* the pieces of spmf_csc_cols_hybrid, for callers that overlap them on several streams: zero the three
  * column-gradient tables; accumulate (atomics) one CSC copy into them -- covered != 0: GEV and Gphi
  * only (hot copy), covered == 0: full column pass (cold copy). */
@@ -324,12 +326,69 @@ typedef struct spmf_step_args {
    * term; otherwise the one-pass backward runs after it */
   double* scr_dpre;
   void* ev_noise;
+  /* link function and exact guard: link = SPMF_LINK_*; gs = device guard state (spmf_guard_state_bytes());
+   * xdense = scratch of nrows*D floats (touched only when the guard fires, or every step by the dense
+   * links); xdense_in = optional dense fp32 [nrows][D] batch in feature order (dense links: used
+   * instead of scattering the CSR).  gs == NULL or xdense == NULL: non-finite entries are dropped and
+   * counted, not replaced.  `eta` above is [2][D] (decoder scale | encoder divisor). */
+  int link;
+  void* gs;
+  float* xdense;
+  const float* xdense_in;
 } spmf_step_args;
 int spmf_advi_step(const spmf_step_args* args);
 /* widen a compact batch (either 16-bit source may be NULL), build its row constants and CSC copy */
 int spmf_prepare_batch(const unsigned short* cols16, const unsigned short* vals16, const long long* rowptr,
                        int* cols, float* vals, int nrows, long long nnz, int D, float* rowsum, float* lgam,
                        int* colptr, int* crows, float* cvals, int* scratch, void* stream);
+
+/* ---- dense evaluation of the data term (csrc/spmf_dense.cu): link functions without a closed-form
+ *      sum(rate) and the exact non-finite guard of poisson.py:606-616 ----
+ * Links: linear Poisson (poisson.py:43,54,177-183), log_transform Poisson (poisson.py:41-42, 52-53),
+ * Bernoulli-logit (bernoulli.py:148) with either decoder.  xd = the batch as dense fp32 [nrows][D] in
+ * TABLE order (column = table row of the feature).  eta_enc[D] (table order) = the encoder divisor of
+ * the log link (log(x/eta + 1)); the linear encoder's 1/eta is folded into A'.
+ * The dense row pass finishes in place: dzr = r (dz - z), rowacc = (sum_d ll, 0, |z|^2, #non-finite);
+ * no closed-form terms remain downstream (spmf_backward_* / parts are told through the guard state).
+ * Guard state (spmf_guard_state_bytes() bytes on the device): flag bit 0 = a non-finite entry was met
+ * this step, bit 1 = dense-only link; nbad; (min finite log-likelihood, its entry).  Reset before every
+ * evaluation of the data term (spmf_guard_reset; the training step's last kernel does it for the next step). */
+#define SPMF_LINK_POISSON 0
+#define SPMF_LINK_POISSON_LOG 1
+#define SPMF_LINK_BERNOULLI 2
+#define SPMF_LINK_BERNOULLI_LOG 3
+#define SPMF_DENSE_OPTIMISTIC 0 /* value + gradient, non-finite entries dropped and flagged */
+#define SPMF_DENSE_STATS 1      /* count non-finite entries, find the smallest finite log-likelihood */
+#define SPMF_DENSE_GUARDED 2    /* value + gradient with the reference's replacement (needs the statistics) */
+int spmf_guard_state_bytes(void);
+int spmf_guard_reset(void* gs, int flag, void* stream);
+/* host-side decode of a copied-back guard state */
+int spmf_guard_decode(const void* gs_host, int* flag, int* nbad, float* min_ll);
+/* xd[nrows][D] = 0, then |vals| scattered at (row, cols[j]); cols must already be table rows */
+int spmf_dense_scatter(const long long* rowptr, const int* cols, const float* vals, int nrows, int D, float* xd,
+                       void* stream);
+/* z = r_b sum_d enc(x_bd) A'_d  (poisson.py:623-650 with either encoder) */
+int spmf_dense_encode(const float* xd, const float* eta_enc, const float* rowsum, float inv_xi, int scale_rows,
+                      int nrows, int D, int K, int S, int link, const float* Ap, float* z, void* stream);
+/* conditional != 0: the launch returns at once unless flag bit 0 is set */
+int spmf_dense_rows(const float* xd, const float* rowsum, const float* lgam, float inv_xi, int scale_rows, int nrows,
+                    int D, int K, int S, int link, int mode, int conditional, const float* EV, const float* PH,
+                    const float* z, float* dzr, float* rowacc, void* gs, void* stream);
+/* accumulates (atomics) GEV, Gphi and -- with_ga -- GA' = enc(x)^T . dzr into tables zeroed by the caller */
+int spmf_dense_cols(const float* xd, const float* eta_enc, int nrows, int D, int K, int S, int link, int with_ga,
+                    const float* z, const float* dzr, const float* EV, const float* PH, float* GAp, float* GEV,
+                    float* Gph, const void* gs, void* stream);
+/* The exact guard of the linear link as two conditional cooperative launches around the column side of
+ * the sparse / tensor-core step (both return at once unless flag bit 0 is set): rows fix = densify the
+ * batch into xd (scratch of nrows*D floats) -> statistics -> guarded dense row pass (overwrites dzr,
+ * rowacc); columns fix = zero GEV / Gphi -> guarded dense column pass.  GA' needs no fix: the column
+ * side computes it from the fixed dzr. */
+int spmf_guard_rows_fix(const long long* rowptr, const int* cols, const float* vals, const float* rowsum,
+                        const float* lgam, float inv_xi, int scale_rows, int nrows, int D, int K, int S,
+                        const float* EV, const float* PH, const float* z, float* dzr, float* rowacc, float* xd,
+                        void* gs, void* stream);
+int spmf_guard_cols_fix(int nrows, int D, int K, int S, const float* EV, const float* PH, const float* z,
+                        float* GEV, float* Gph, const float* xd, void* gs, void* stream);
 
 const char* spmf_version(void);
 

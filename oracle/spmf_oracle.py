@@ -345,8 +345,10 @@ class OraclePoissonFactorization:
         parts['z'] = halfnormal_log_prob(theta, torch.ones_like(theta)).sum((-1, -2))  # :599-604
         finite = torch.isfinite(ll)
         finite_portion = torch.where(finite, ll, torch.zeros_like(ll))               # :606-608
-        min_val = (finite_portion.min() - 10.).detach()                               # :609 (global min)
-        ll = torch.clamp(ll, min=float(min_val), max=0.)                              # :611
+        min_val = finite_portion.min() - 10.                                          # :609 (global min, differentiable)
+        # :611 tf.clip_by_value = maximum(minimum(t, max), min): the gradient of a clipped / NaN entry
+        # flows to min_val (and through reduce_min to the entry attaining the minimum)
+        ll = torch.maximum(torch.minimum(ll, torch.zeros_like(ll)), min_val)
         ll = torch.where(torch.isfinite(ll), ll, torch.ones_like(ll) * min_val)       # :612-616
         parts['x'] = ll.sum(-1).sum(-1)                                               # :617-619
         return parts

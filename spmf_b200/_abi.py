@@ -49,17 +49,17 @@ _SIGS = {
     "spmf_sample": (i32, [p, p, i32, i32, i32, p, p]),
     "spmf_draw_operands": (i32, [p, p, p, i32, i32, i32, p, p, p, p, p, p, p]),
     "spmf_csr_row_consts": (i32, [p, p, i64, p, p, p]),
-    "spmf_csr_rows": (i32, [p, p, p, p, p, f32, i32, i32, i32, i32, i32, p, p, p, p, p, p, p, i32, p]),
+    "spmf_csr_rows": (i32, [p, p, p, p, p, f32, i32, i32, i32, i32, i32, p, p, p, p, p, p, p, i32, p, p]),
     "spmf_csr_encode": (i32, [p, p, p, p, f32, i32, i32, i32, i32, i32, p, p, p]),
     "spmf_csc_cols": (i32, [p, p, p, i32, i32, i32, i32, i32, p, p, p, p, p, p, p, i32, p]),
     "spmf_batch_sums": (i32, [p, p, i32, i32, i32, p, p, p, p]),
     "spmf_gamma_grad": (i32, [p, p, i32, i32, i32, p, p]),
     "spmf_gamma_draw_grad": (i32, [p, p, p, i32, i32, i32, u64, u32, p]),
     "spmf_backward_params": (i32, [p, p, p, p, i32, i32, i32, p, p, p, p, p, p, f32, f32, f32, f32, f32,
-                                   f32, i32, p, p, p, p, p]),
+                                   f32, i32, p, p, p, p, p, p]),
     "spmf_backward_pre": (i32, [p, p, p, p, i32, i32, i32, f32, f32, f32, f32, f32, f32, i32, p, p, p, p]),
     "spmf_backward_post": (i32, [p, p, p, p, i32, i32, i32, p, p, p, p, p, p, f32, f32, f32, f32, f32, f32, i32,
-                                 p, p, p, p, p]),
+                                 p, p, p, p, p, p]),
     "spmf_adam_step": (i32, [p, p, p, p, i64, f32, f32, f32, f32, i32, f32, f32, p]),
     "spmf_unpack_parts": (i32, [p, i32, i32, f32, f32, p, p, p]),
     "spmf_sumsq": (i32, [p, i64, p, p, p, p]),
@@ -76,7 +76,7 @@ _SIGS = {
     "spmf_draw_operands_ranked": (i32, [p, p, p, p, i32, i32, i32, p, p, p, p, p, p, p]),
     "spmf_operand_sums": (i32, [p, p, i32, i32, i32, p, p, p, p]),
     "spmf_backward_params_ranked": (i32, [p, p, p, p, p, i32, i32, i32, p, p, p, p, p, p, f32, f32, f32, f32,
-                                          f32, f32, i32, p, p, p, p, p]),
+                                          f32, f32, i32, p, p, p, p, p, p]),
     "spmf_umma_tiled_a_elems": (i64, [i64, i64]),
     "spmf_umma_tiled_b_elems": (i64, [i32, i64]),
     "spmf_umma_tiled_a_index": (i64, [i64, i64, i64]),
@@ -87,13 +87,23 @@ _SIGS = {
     "spmf_hot_split_packed": (i32, [p, p, p, p, p, i32, i64, p, i32, p, p, p, p, p, p, p, p, p]),
     "spmf_split3_transpose": (i32, [p, i64, i64, i32, i32, i32, p, i64, i32, p]),
     "spmf_umma_gemm3": (i32, [p, i64, i32, p, i64, p, i64, i64, i32, i32, i32, i32, p]),
-    "spmf_csr_rows_hybrid": (i32, [p, p, p, p, p, p, f32, i32, i32, i32, i32, i32, p, p, p, p, p, p, p, p]),
+    "spmf_csr_rows_hybrid": (i32, [p, p, p, p, p, p, f32, i32, i32, i32, i32, i32, p, p, p, p, p, p, p, p, p]),
     "spmf_csc_cols_hybrid": (i32, [p, p, p, p, p, p, i32, i32, i32, i32, i32, p, p, p, p, p, p, p, p]),
     "spmf_hot_tile_scratch_bytes": (i64, [i32, i32, i32]),
     "spmf_hot_ev_tiles": (i32, [p, p, i32, i32, i32, i32, p, p]),
-    "spmf_csr_rows_cold": (i32, [p, p, p, p, p, f32, i32, i32, i32, i32, i32, p, p, p, p, p, p, p]),
-    "spmf_hot_tile": (i32, [p, p, p, i32, i32, i32, i32, i32, p, p, p, p, p]),
-    "spmf_rows_finish": (i32, [p, p, f32, i32, i32, i32, i32, p, p, p, p, p]),
+    "spmf_csr_rows_cold": (i32, [p, p, p, p, p, f32, i32, i32, i32, i32, i32, p, p, p, p, p, p, p, p]),
+    "spmf_hot_tile": (i32, [p, p, p, i32, i32, i32, i32, i32, p, p, p, p, p, p]),
+    "spmf_rows_finish": (i32, [p, p, f32, i32, i32, i32, i32, p, p, p, p, p, p]),
+    # dense evaluation of the data term: log / Bernoulli links, exact non-finite guard (spmf_dense.cu)
+    "spmf_guard_state_bytes": (i32, []),
+    "spmf_guard_reset": (i32, [p, i32, p]),
+    "spmf_guard_decode": (i32, [p, C.POINTER(i32), C.POINTER(i32), C.POINTER(f32)]),
+    "spmf_dense_scatter": (i32, [p, p, p, i32, i32, p, p]),
+    "spmf_dense_encode": (i32, [p, p, p, f32, i32, i32, i32, i32, i32, i32, p, p, p]),
+    "spmf_dense_rows": (i32, [p, p, p, f32, i32, i32, i32, i32, i32, i32, i32, i32, p, p, p, p, p, p, p]),
+    "spmf_dense_cols": (i32, [p, p, i32, i32, i32, i32, i32, i32, p, p, p, p, p, p, p, p, p]),
+    "spmf_guard_rows_fix": (i32, [p, p, p, p, p, f32, i32, i32, i32, i32, i32, p, p, p, p, p, p, p, p]),
+    "spmf_guard_cols_fix": (i32, [i32, i32, i32, i32, p, p, p, p, p, p, p, p]),
     "spmf_zero_col_grads": (i32, [p, p, p, i32, i32, i32, p]),
     "spmf_csc_cols_accum": (i32, [p, p, p, i32, i32, i32, i32, i32, p, p, p, p, p, p, p, i32, p]),
     "spmf_csr_to_csc_part": (i32, [p, p, i32, p, p, i32, i32, p, p, p, p, p]),
@@ -123,6 +133,7 @@ class StepArgs(C.Structure):
                             "ev_gemm0", "ev_gemm1", "aux_stream1", "aux_stream2", "ev_aux_fork", "ev_aux_join1",
                             "ev_aux_join2")]
         + [("hot_mode", i32), ("EVt", p), ("ev_tile0", p), ("ev_tile1", p), ("scr_dpre", p), ("ev_noise", p)]
+        + [("link", i32), ("gs", p), ("xdense", p), ("xdense_in", p)]
     )
 
 
@@ -146,6 +157,10 @@ def _check(rc, name):
 def call(name, *args):
     """Call an int-returning entry point and raise on a non-zero status."""
     _check(getattr(_lib, name)(*args), name)
+
+
+LINK_POISSON, LINK_POISSON_LOG, LINK_BERNOULLI, LINK_BERNOULLI_LOG = 0, 1, 2, 3
+DENSE_OPTIMISTIC, DENSE_STATS, DENSE_GUARDED = 0, 1, 2
 
 
 def kpad(K):

@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(kTileThreads, 1)
 hot_tile_kernel(const unsigned char* __restrict__ xhot, const unsigned char* __restrict__ EVt,
                 const float* __restrict__ z, int nrows, int D, int H, int nch, int chunks_per_cta,
                 float* __restrict__ dzacc, float* __restrict__ rowacc, float* __restrict__ GEV,
-                float* __restrict__ Gphi) {
+                float* __restrict__ Gphi, int* __restrict__ gflag) {
   using T = HotTile<KP>;
   constexpr int KK = T::KK, REC = SV * KP;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -322,7 +322,7 @@ hot_tile_kernel(const unsigned char* __restrict__ xhot, const unsigned char* __r
     issue_p1(0);
   }
 
-  float xlog2 = 0.f;
+  float xlog2 = 0.f, wmax = 0.f;
   for (int i = 0; i < n; ++i) {
     const int st = i % T::NSTAGE, wb = i & 1;
     if (worker) {
@@ -356,6 +356,7 @@ hot_tile_kernel(const unsigned char* __restrict__ xhot, const unsigned char* __r
           asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(l));
           asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(l));
           w[e] = x * rc;
+          wmax = fmaxf(wmax, w[e]);                 // a floored (zero / NaN) rate at a nonzero shows up as x * 1e30
           xlog2 = fmaf(x, lg, xlog2);
         }
         uint32_t hi[4], lo[4];
@@ -449,6 +450,9 @@ hot_tile_kernel(const unsigned char* __restrict__ xhot, const unsigned char* __r
       }
       atomicAdd(rowacc + ((size_t)q * nrows + row) * 4 * SV + sv, xlog2 * 0.6931471805599453f);
     }
+    // non-finite log-likelihood somewhere in this thread's entries (rate 0 / NaN at a nonzero, or an
+    // infinite rate): the exact guard of poisson.py:606-616 re-evaluates the step (spmf_dense.cu)
+    if (gflag && (!(wmax < 1e25f) || !(fabsf(xlog2) <= 3.402823466e38f))) atomicOr(gflag, 1);
   }
   }   // worker
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -465,7 +469,7 @@ template <int KP, int SV>
 __global__ void __launch_bounds__(128)
 rows_finish_kernel(const float* __restrict__ rowsum, const float* __restrict__ lgam, float inv_xi, int scale_rows,
                    int nrows, const double* __restrict__ vsum, const float* __restrict__ z,
-                   float* __restrict__ dzr, float* __restrict__ rowacc) {
+                   float* __restrict__ dzr, float* __restrict__ rowacc, int* __restrict__ gflag) {
   constexpr int REC = SV * KP;
   static_assert(KP >= 4 && REC <= 128, "rows_finish: one warp covers a record");
   const RecMap rm = rec_map(KP);
@@ -502,6 +506,8 @@ rows_finish_kernel(const float* __restrict__ rowsum, const float* __restrict__ l
       ra[0 * SV + s] -= lgam[row];
       ra[1 * SV + s] = a;
       ra[2 * SV + s] = b;
+      // closed-form sum_d rate of this row is not finite: some entry's rate is not (poisson.py:606-616)
+      if (gflag && !(fabsf(a) <= 3.402823466e38f)) atomicOr(gflag, 1);
     }
   }
 }
@@ -523,7 +529,7 @@ using namespace spmf;
 
 template <int KP, int SV>
 static int launch_hot_tile(const void* xhot, const void* EVt, const float* z, int nrows, int D, int H, int S,
-                           float* dzacc, float* rowacc, float* GEV, float* Gphi, cudaStream_t st) {
+                           float* dzacc, float* rowacc, float* GEV, float* Gphi, int* gflag, cudaStream_t st) {
   using T = HotTile<KP>;
   static bool attr = false;
   if (!attr) {
@@ -546,7 +552,7 @@ static int launch_hot_tile(const void* xhot, const void* EVt, const float* z, in
   splits = (nch + per - 1) / per;
   dim3 grid((nrows + 127) / 128, S, splits);
   hot_tile_kernel<KP, SV><<<grid, kTileThreads, T::SMEM, st>>>((const unsigned char*)xhot, (const unsigned char*)EVt, z, nrows, D,
-                                                              H, nch, per, dzacc, rowacc, GEV, Gphi);
+                                                              H, nch, per, dzacc, rowacc, GEV, Gphi, gflag);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? SPMF_OK : (int)e;
 }
@@ -573,26 +579,26 @@ int spmf_hot_ev_tiles(const float* EV, const float* PH, int D, int H, int K, int
 }
 
 int spmf_hot_tile(const void* xhot, const void* EVt, const float* z, int nrows, int D, int H, int K, int S,
-                  float* dzacc, float* rowacc, float* GEVnz, float* Gphinz, void* stream) {
+                  float* dzacc, float* rowacc, float* GEVnz, float* Gphinz, void* gs, void* stream) {
   if (!xhot || !EVt || !z || !dzacc || !rowacc || !GEVnz || !Gphinz) return SPMF_ERR_BAD_ARG;
   if (nrows <= 0 || D <= 0 || H <= 0 || H > D || K <= 0 || K > SPMF_MAX_K || S <= 0) return SPMF_ERR_BAD_ARG;
   const int KP = spmf_kpad(K), SV = spmf_draw_vec(S);
   cudaStream_t st = (cudaStream_t)stream;
   int rc = SPMF_OK;
-#define CALL_HT(KPC, SVC) rc = launch_hot_tile<KPC, SVC>(xhot, EVt, z, nrows, D, H, S, dzacc, rowacc, GEVnz, Gphinz, st)
+#define CALL_HT(KPC, SVC) rc = launch_hot_tile<KPC, SVC>(xhot, EVt, z, nrows, D, H, S, dzacc, rowacc, GEVnz, Gphinz, (int*)gs, st)
   HT_DISPATCH(KP, SV, CALL_HT);
 #undef CALL_HT
   return rc;
 }
 
 int spmf_rows_finish(const float* rowsum, const float* lgam, float inv_xi, int scale_rows, int nrows, int K, int S,
-                     const double* vsum, const float* z, float* dzr, float* rowacc, void* stream) {
+                     const double* vsum, const float* z, float* dzr, float* rowacc, void* gs, void* stream) {
   if (!rowsum || !lgam || !vsum || !z || !dzr || !rowacc || nrows <= 0 || K <= 0 || K > SPMF_MAX_K || S <= 0)
     return SPMF_ERR_BAD_ARG;
   const int KP = spmf_kpad(K), SV = spmf_draw_vec(S), NQ = S / SV;
   dim3 grid((unsigned)((nrows + 3) / 4), NQ);
   cudaStream_t st = (cudaStream_t)stream;
-#define CALL_RF(KPC, SVC) rows_finish_kernel<KPC, SVC><<<grid, 128, 0, st>>>(rowsum, lgam, inv_xi, scale_rows, nrows, vsum, z, dzr, rowacc)
+#define CALL_RF(KPC, SVC) rows_finish_kernel<KPC, SVC><<<grid, 128, 0, st>>>(rowsum, lgam, inv_xi, scale_rows, nrows, vsum, z, dzr, rowacc, (int*)gs)
   HT_DISPATCH(KP, SV, CALL_RF);
 #undef CALL_RF
   cudaError_t e = cudaGetLastError();

@@ -176,10 +176,13 @@ struct FeatState {
   GParam se0, se1, st, sea0, sea1, sta;
 };
 
+// `eta` everywhere below is [2][D]: row 0 = the decoder scale eta_i (EV = eta v, phi = eta b w), row 1 =
+// the encoder divisor (A' = a u / eta_enc): eta_i for the linear encoder x/eta, 1 under log_transform
+// (the encoder log(x/eta + 1) is then applied to the counts themselves; poisson.py:34-54).
 struct ModelPtrs {
   const float* params;   // flat
   const float* noise;    // flat
-  const float* eta;      // [D]
+  const float* eta;      // [2][D]
 };
 
 
@@ -236,7 +239,7 @@ SPMF_HD void lane_operands(const LaneState<KK>& st, const Layout& L, const float
   long long e = (long long)s * L.D * L.K + (long long)d * L.K + k;
   NDraw u = ndraw(st.u[i], N[L.noff[VAR_U] + e]);
   NDraw v = ndraw(st.v[i], N[L.noff[VAR_V] + e]);
-  *Ap = a_d * u.y / eta[d];
+  *Ap = a_d * u.y / eta[L.D + d];      // encoder divisor: eta_d, or 1 under log_transform (poisson.py:41-43)
   *EV = eta[d] * v.y;
   if (u_out) *u_out = u.y;
   if (v_out) *v_out = v.y;
@@ -267,7 +270,7 @@ SPMF_HD DkOut lane_step(LaneState<KK>& st, const Layout& L, const Hyper& h, cons
   float pv = halfnormal(v.y, 0.1f, &dv, &dtmp);                  // poisson.py:229-235
   float pue = sqrt_ig_half(ue.y, ua.y, &due, &dua);              // poisson.py:303-311
   float pua = ig_half(ua.y, 1.0f, &dua2);                        // poisson.py:312-322
-  float ieta = 1.f / eta[d];
+  float ieta = 1.f / eta[L.D + d];
   const float wpr = h.w_prior * h.rep_scale, wer = h.w_entropy * h.rep_scale;
   float Gy_u = -(wpr * du + up.GAp * a_d * ieta);
   float Gy_v = -(wpr * dv + eta[d] * up.GEV);

@@ -12,6 +12,7 @@
 #include <stdint.h>
 
 #include "../../include/spmf_b200.h"
+#include "spmf_guard.cuh"
 #include "spmf_model.cuh"
 #include "spmf_record.cuh"
 
@@ -191,11 +192,12 @@ backward_dk_kernel(Layout L, Hyper h, const float* __restrict__ P, const float* 
                    const float* __restrict__ GAp, const float* __restrict__ GEVnz,
                    const double* __restrict__ zcolsum, float* __restrict__ grads,
                    float* __restrict__ scr_utau, float* __restrict__ scr_parts,
-                   float* __restrict__ scr_da, float* __restrict__ fac) {
+                   float* __restrict__ scr_da, float* __restrict__ fac, const int* __restrict__ gflag) {
   const int lane = threadIdx.x & 31;
   const int d = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (d >= L.D) return;
   const int dr = (!PRE && rank) ? rank[d] : d;
+  const bool dense = !PRE && gflag && *gflag;      // dense data term: no closed-form -sum_b z_b in GEV
   LaneState<KK> st;
   lane_init<KK>(st, L, P, d, lane, h.decay);
   const NParam s0 = nparam_init(P[L.toff[S_LOC] + d], P[L.toff[S_RHO] + d]);
@@ -218,7 +220,7 @@ backward_dk_kernel(Layout L, Hyper h, const float* __restrict__ P, const float* 
           up.GEV = 0.f;
         } else {
           up.GAp = GAp[idx];
-          up.GEV = GEVnz[idx] - (float)zcolsum[(long long)q * SV * KP + rp];
+          up.GEV = GEVnz[idx] - (dense ? 0.f : (float)zcolsum[(long long)q * SV * KP + rp]);
         }
         DkOut o = lane_step<KK>(st, L, h, N, G, eta, d, lane, i, s, a_d, up);
         if constexpr (PRE) {
@@ -226,7 +228,7 @@ backward_dk_kernel(Layout L, Hyper h, const float* __restrict__ P, const float* 
           const long long nsdk = (long long)L.S * L.D * L.K;
           const NDraw ud = ndraw(st.u[i], N[L.noff[VAR_U] + e]);
           const NDraw vd = ndraw(st.v[i], N[L.noff[VAR_V] + e]);
-          const float ieta = 1.f / eta[d];
+          const float ieta = 1.f / eta[L.D + d];       // encoder divisor
           fac[e] = a_d * ieta * ud.sg;
           fac[nsdk + e] = eta[d] * vd.sg;
           fac[2 * nsdk + e] = ud.y * ieta;
@@ -272,11 +274,13 @@ backward_dk_post_kernel(Layout L, Hyper h, const float* __restrict__ P, const fl
                         const float* __restrict__ eta, const int* __restrict__ rank, int SV, int KP,
                         const float* __restrict__ GAp, const float* __restrict__ GEVnz,
                         const float* __restrict__ Gphinz, const double* __restrict__ zcolsum,
-                        const float* __restrict__ fac, float* __restrict__ grads) {
+                        const float* __restrict__ fac, float* __restrict__ grads, const int* __restrict__ gflag) {
   const int lane = threadIdx.x & 31;
   const int d = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (d >= L.D) return;
   const int dr = rank ? rank[d] : d;
+  const bool dense = gflag && *gflag;              // dense data term: no closed-form terms (-sum z, -B)
+  const float cf_rows = dense ? 0.f : h.batch_rows;
   const long long nsdk = (long long)L.S * L.D * L.K;
   float au[KK], aue[KK], av[KK], ave[KK];
 #pragma unroll
@@ -293,7 +297,7 @@ backward_dk_post_kernel(Layout L, Hyper h, const float* __restrict__ P, const fl
         const long long idx = ((long long)q * L.D + dr) * SV * KP + rp;
         const long long e = ((long long)s * L.D + d) * L.K + k;
         const float ga = GAp[idx];
-        const float gv = GEVnz[idx] - (float)zcolsum[(long long)q * SV * KP + rp];
+        const float gv = GEVnz[idx] - (dense ? 0.f : (float)zcolsum[(long long)q * SV * KP + rp]);
         const float dtu = -ga * fac[e], dtv = -gv * fac[nsdk + e];
         au[i] += dtu;
         aue[i] = fmaf(dtu, N[L.noff[VAR_U] + e], aue[i]);
@@ -319,7 +323,7 @@ backward_dk_post_kernel(Layout L, Hyper h, const float* __restrict__ P, const fl
       const int q = s / SV, sv = s - q * SV;
       const FeatDraw fd = feat_draw(f, L, N, d, s);
       const float da = da_mine[s >> 5];
-      const float Gphi = Gphinz[((long long)q * D + dr) * SV + sv] - h.batch_rows;     // d L / d phi_d
+      const float Gphi = Gphinz[((long long)q * D + dr) * SV + sv] - cf_rows;          // d L / d phi_d
       const float dw_data = eta[d] * fd.b * Gphi;                                     // phi = eta b w
       const float db = eta[d] * fd.w.y * Gphi;
       const float inv = 1.f / (fd.s0.y + fd.s1.y), inv2 = inv * inv;
@@ -367,7 +371,9 @@ backward_feat_kernel(Layout L, Hyper h, const float* __restrict__ P, const float
                      const float* __restrict__ G, const float* __restrict__ eta,
                      const int* __restrict__ rank, int SV,
                      const float* __restrict__ Gphinz, const float* __restrict__ scr_da,
-                     float* __restrict__ grads, float* __restrict__ scr_parts, int pre) {
+                     float* __restrict__ grads, float* __restrict__ scr_parts, int pre,
+                     const int* __restrict__ gflag) {
+  if (!pre && gflag && *gflag) h.batch_rows = 0.f;  // dense data term: Gphi carries no closed-form -B
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int dreal = t / SV, sg = t - dreal * SV;
   const bool valid = dreal < L.D;
@@ -467,15 +473,30 @@ __global__ void finalize_parts_kernel(int S, int SV, int K, const double* __rest
                                       const double* __restrict__ data, const double* __restrict__ phisum,
                                       double batch_rows, double w_entropy,
                                       double w_prior, double* __restrict__ parts_out,
-                                      float* __restrict__ comm) {
+                                      float* __restrict__ comm, GuardState* __restrict__ gs) {
   int s = threadIdx.x;
+  const int gflag = gs ? gs->flag : 0;
+  const double min_val = gs ? (double)guard_min_val(gs->minkey) : 0.0;
+  __syncthreads();
+  if (gs && threadIdx.x == 0) {        // last reader of the step: re-arm the guard for the next one
+    gs->flag = gflag & 2;              // (the dense-link bit is configuration, not state)
+    gs->nbad = 0;
+    gs->minkey = ~0ull;
+  }
   if (s >= S) return;
   double* o = parts_out + (long long)s * NUM_PARTS;
   for (int p = 0; p <= P_LOGQ; ++p) o[p] = featparts[s * NUM_PARTS + p] + latparts[s * NUM_PARTS + p];
   const int q = s / SV, sv = s - q * SV;
   const double* dd = data + ((long long)q * 4) * SV;   // data[q][4][SV]
   double xlog = dd[0 * SV + sv], zv = dd[1 * SV + sv], z2 = dd[2 * SV + sv];
-  o[P_X] = xlog - zv - batch_rows * phisum[q * SV + sv];
+  if (gflag) {
+    // dense data term: dd[0] already sums the finite entries; the others take min(finite) - 10
+    // (poisson.py:606-616)
+    const double nb = dd[3 * SV + sv];
+    o[P_X] = xlog + (nb > 0.0 ? nb * min_val : 0.0);
+  } else {
+    o[P_X] = xlog - zv - batch_rows * phisum[q * SV + sv];
+  }
   o[P_Z] = batch_rows * (double)K * (double)kHalfLog2OverPi - 0.5 * z2;
   double prior = 0.0;
   for (int p = 0; p < P_LOGQ; ++p) prior += o[p];
@@ -751,10 +772,10 @@ int spmf_backward_params(const float* params, const float* noise, const float* d
                          const double* zcolsum, const double* datasums, const double* phisum,
                          float batch_rows, float u_tau_scale, float s_tau_scale,
                          float decay, float w_entropy, float w_prior, int world_size, float* grads,
-                         double* parts, float* scr_f, double* scr_d, void* stream) {
+                         double* parts, float* scr_f, double* scr_d, void* gs, void* stream) {
   return spmf_backward_params_ranked(params, noise, dgda, eta, nullptr, D, K, S, GAp, GEVnz, Gphinz, zcolsum,
                                      datasums, phisum, batch_rows, u_tau_scale, s_tau_scale, decay, w_entropy,
-                                     w_prior, world_size, grads, parts, scr_f, scr_d, stream);
+                                     w_prior, world_size, grads, parts, scr_f, scr_d, gs, stream);
 }
 
 int spmf_backward_params_ranked(const float* params, const float* noise, const float* dgda, const float* eta,
@@ -762,7 +783,7 @@ int spmf_backward_params_ranked(const float* params, const float* noise, const f
                                 const float* Gphinz, const double* zcolsum, const double* datasums,
                                 const double* phisum, float batch_rows, float u_tau_scale, float s_tau_scale,
                                 float decay, float w_entropy, float w_prior, int world_size, float* grads,
-                                double* parts, float* scr_f, double* scr_d, void* stream) {
+                                double* parts, float* scr_f, double* scr_d, void* gs, void* stream) {
   if (!params || !noise || !dgda || !eta || !GAp || !GEVnz || !Gphinz || !zcolsum || !datasums ||
       !phisum || !grads || !parts || !scr_f || !scr_d)
     return SPMF_ERR_BAD_ARG;
@@ -782,10 +803,10 @@ int spmf_backward_params_ranked(const float* params, const float* noise, const f
   double* rscr = latparts + (long long)S * NUM_PARTS;
   float* scr_da = scr_lat + (long long)K * S * NUM_PARTS;
   dim3 grid((D + 3) / 4);
-  if (KP <= 32) backward_dk_kernel<1, false><<<grid, 128, 0, st>>>(L, h, params, noise, dgda, eta, rank, SV, KP, GAp, GEVnz, zcolsum, grads, scr_utau, scr_parts, scr_da, nullptr);
-  else if (KP <= 64) backward_dk_kernel<2, false><<<grid, 128, 0, st>>>(L, h, params, noise, dgda, eta, rank, SV, KP, GAp, GEVnz, zcolsum, grads, scr_utau, scr_parts, scr_da, nullptr);
-  else backward_dk_kernel<4, false><<<grid, 128, 0, st>>>(L, h, params, noise, dgda, eta, rank, SV, KP, GAp, GEVnz, zcolsum, grads, scr_utau, scr_parts, scr_da, nullptr);
-  backward_feat_kernel<<<(int)(((long long)D * SV + 127) / 128), 128, 0, st>>>(L, h, params, noise, dgda, eta, rank, SV, Gphinz, scr_da, grads, scr_parts, 0);
+  if (KP <= 32) backward_dk_kernel<1, false><<<grid, 128, 0, st>>>(L, h, params, noise, dgda, eta, rank, SV, KP, GAp, GEVnz, zcolsum, grads, scr_utau, scr_parts, scr_da, nullptr, (const int*)gs);
+  else if (KP <= 64) backward_dk_kernel<2, false><<<grid, 128, 0, st>>>(L, h, params, noise, dgda, eta, rank, SV, KP, GAp, GEVnz, zcolsum, grads, scr_utau, scr_parts, scr_da, nullptr, (const int*)gs);
+  else backward_dk_kernel<4, false><<<grid, 128, 0, st>>>(L, h, params, noise, dgda, eta, rank, SV, KP, GAp, GEVnz, zcolsum, grads, scr_utau, scr_parts, scr_da, nullptr, (const int*)gs);
+  backward_feat_kernel<<<(int)(((long long)D * SV + 127) / 128), 128, 0, st>>>(L, h, params, noise, dgda, eta, rank, SV, Gphinz, scr_da, grads, scr_parts, 0, (const int*)gs);
   SPMF_CHECK_LAUNCH();
   int rc = reduce_rows_pair(scr_utau, dutau, D, K, S, scr_parts, featparts, D, S * NUM_PARTS, 1, rscr, st);
   if (rc) return rc;
@@ -796,7 +817,7 @@ int spmf_backward_params_ranked(const float* params, const float* noise, const f
   finalize_parts_kernel<<<1, ((S + 31) / 32) * 32, 0, st>>>(S, SV, K, featparts, latparts, datasums, phisum,
                                                            (double)batch_rows,
                                                            (double)w_entropy, (double)w_prior, parts,
-                                                           grads + L.comm_off);
+                                                           grads + L.comm_off, (GuardState*)gs);
   SPMF_CHECK_LAUNCH();
   return SPMF_OK;
 }
@@ -827,10 +848,10 @@ int spmf_backward_pre(const float* params, const float* noise, const float* dgda
   double* latparts = featparts + (long long)S * NUM_PARTS;
   double* rscr = latparts + (long long)S * NUM_PARTS;
   dim3 grid((D + 3) / 4);
-  if (KP <= 32) backward_dk_kernel<1, true><<<grid, 128, 0, st>>>(L, h, params, noise, dgda, eta, nullptr, SV, KP, nullptr, nullptr, nullptr, grads, scr_utau, scr_parts, scr_da, fac);
-  else if (KP <= 64) backward_dk_kernel<2, true><<<grid, 128, 0, st>>>(L, h, params, noise, dgda, eta, nullptr, SV, KP, nullptr, nullptr, nullptr, grads, scr_utau, scr_parts, scr_da, fac);
-  else backward_dk_kernel<4, true><<<grid, 128, 0, st>>>(L, h, params, noise, dgda, eta, nullptr, SV, KP, nullptr, nullptr, nullptr, grads, scr_utau, scr_parts, scr_da, fac);
-  backward_feat_kernel<<<(int)(((long long)D * SV + 127) / 128), 128, 0, st>>>(L, h, params, noise, dgda, eta, nullptr, SV, nullptr, nullptr, grads, scr_parts, 1);
+  if (KP <= 32) backward_dk_kernel<1, true><<<grid, 128, 0, st>>>(L, h, params, noise, dgda, eta, nullptr, SV, KP, nullptr, nullptr, nullptr, grads, scr_utau, scr_parts, scr_da, fac, nullptr);
+  else if (KP <= 64) backward_dk_kernel<2, true><<<grid, 128, 0, st>>>(L, h, params, noise, dgda, eta, nullptr, SV, KP, nullptr, nullptr, nullptr, grads, scr_utau, scr_parts, scr_da, fac, nullptr);
+  else backward_dk_kernel<4, true><<<grid, 128, 0, st>>>(L, h, params, noise, dgda, eta, nullptr, SV, KP, nullptr, nullptr, nullptr, grads, scr_utau, scr_parts, scr_da, fac, nullptr);
+  backward_feat_kernel<<<(int)(((long long)D * SV + 127) / 128), 128, 0, st>>>(L, h, params, noise, dgda, eta, nullptr, SV, nullptr, nullptr, grads, scr_parts, 1, nullptr);
   SPMF_CHECK_LAUNCH();
   int rc = reduce_rows_pair(scr_utau, dutau, D, K, S, scr_parts, featparts, D, S * NUM_PARTS, 1, rscr, st);
   if (rc) return rc;
@@ -843,7 +864,7 @@ int spmf_backward_post(const float* params, const float* noise, const float* eta
                        int S, const float* GAp, const float* GEVnz, const float* Gphinz, const double* zcolsum,
                        const double* datasums, const double* phisum, float batch_rows, float u_tau_scale,
                        float s_tau_scale, float decay, float w_entropy, float w_prior, int world_size,
-                       float* grads, double* parts, float* scr_f, const double* scr_d, void* stream) {
+                       float* grads, double* parts, float* scr_f, const double* scr_d, void* gs, void* stream) {
   if (!params || !noise || !eta || !GAp || !GEVnz || !Gphinz || !zcolsum || !datasums || !phisum || !grads ||
       !parts || !scr_f || !scr_d)
     return SPMF_ERR_BAD_ARG;
@@ -858,12 +879,12 @@ int spmf_backward_post(const float* params, const float* noise, const float* eta
   const double* latparts = featparts + (long long)S * NUM_PARTS;
   dim3 grid((D + 3) / 4);
   if (S > 64) return SPMF_ERR_BAD_ARG;
-  if (KP <= 32) backward_dk_post_kernel<1><<<grid, 128, 0, st>>>(L, h, params, noise, eta, rank, SV, KP, GAp, GEVnz, Gphinz, zcolsum, fac, grads);
-  else if (KP <= 64) backward_dk_post_kernel<2><<<grid, 128, 0, st>>>(L, h, params, noise, eta, rank, SV, KP, GAp, GEVnz, Gphinz, zcolsum, fac, grads);
-  else backward_dk_post_kernel<4><<<grid, 128, 0, st>>>(L, h, params, noise, eta, rank, SV, KP, GAp, GEVnz, Gphinz, zcolsum, fac, grads);
+  if (KP <= 32) backward_dk_post_kernel<1><<<grid, 128, 0, st>>>(L, h, params, noise, eta, rank, SV, KP, GAp, GEVnz, Gphinz, zcolsum, fac, grads, (const int*)gs);
+  else if (KP <= 64) backward_dk_post_kernel<2><<<grid, 128, 0, st>>>(L, h, params, noise, eta, rank, SV, KP, GAp, GEVnz, Gphinz, zcolsum, fac, grads, (const int*)gs);
+  else backward_dk_post_kernel<4><<<grid, 128, 0, st>>>(L, h, params, noise, eta, rank, SV, KP, GAp, GEVnz, Gphinz, zcolsum, fac, grads, (const int*)gs);
   finalize_parts_kernel<<<1, ((S + 31) / 32) * 32, 0, st>>>(S, SV, K, featparts, latparts, datasums, phisum,
                                                            (double)batch_rows, (double)w_entropy, (double)w_prior,
-                                                           parts, grads + L.comm_off);
+                                                           parts, grads + L.comm_off, (GuardState*)gs);
   SPMF_CHECK_LAUNCH();
   return SPMF_OK;
 }

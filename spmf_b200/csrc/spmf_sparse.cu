@@ -159,7 +159,7 @@ csr_rows_body(const long long* __restrict__ rowptr, const int* __restrict__ cols
               const float* __restrict__ Ap, const float* __restrict__ EV,
               const float* __restrict__ PH, const double* __restrict__ vsum,
               float* __restrict__ z, float* __restrict__ dzr, float* __restrict__ rowacc,
-              const int* __restrict__ rowmid) {
+              const int* __restrict__ rowmid, int* __restrict__ gflag) {
   constexpr bool ENCODE_ONLY = (MODE == kRowsEncode);
   constexpr bool COLD = (MODE == kRowsCold);
   constexpr bool ZIN = (MODE == kRowsHybrid) || COLD;     // z holds the GEMM's hot block on entry
@@ -415,6 +415,7 @@ csr_rows_body(const long long* __restrict__ rowptr, const int* __restrict__ cols
       ra[1 * SV + s] = 0.f;
       ra[2 * SV + s] = 0.f;
       ra[3 * SV + s] = fbad;
+      if (gflag && fbad > 0.f) atomicOr(gflag, 1);     // exact guard (poisson.py:606-616) takes over this step
     }
     return;
   }
@@ -441,6 +442,9 @@ csr_rows_body(const long long* __restrict__ rowptr, const int* __restrict__ cols
     ra[1 * SV + s] = zv;
     ra[2 * SV + s] = z2;
     ra[3 * SV + s] = fbad;
+    // a non-finite entry among the nonzeros, or a non-finite closed-form sum(rate) of this row (some
+    // zero entry's rate is not finite): the exact guard of poisson.py:606-616 takes over this step
+    if (gflag && (fbad > 0.f || !(fabsf(zv) <= 3.402823466e38f))) atomicOr(gflag, 1);
   }
 }
 
@@ -449,9 +453,9 @@ csr_rows_body(const long long* __restrict__ rowptr, const int* __restrict__ cols
       const float *__restrict__ rowsum, const float *__restrict__ lgam, float inv_xi, int scale_rows, int nrows, \
       int D, const float *__restrict__ Ap, const float *__restrict__ EV, const float *__restrict__ PH,          \
       const double *__restrict__ vsum, float *__restrict__ z, float *__restrict__ dzr,                          \
-      float *__restrict__ rowacc, const int *__restrict__ rowmid
+      float *__restrict__ rowacc, const int *__restrict__ rowmid, int *__restrict__ gflag
 #define SPMF_ROWS_ARGS \
-  rowptr, cols, vals, rowsum, lgam, inv_xi, scale_rows, nrows, D, Ap, EV, PH, vsum, z, dzr, rowacc, rowmid
+  rowptr, cols, vals, rowsum, lgam, inv_xi, scale_rows, nrows, D, Ap, EV, PH, vsum, z, dzr, rowacc, rowmid, gflag
 
 template <int KP, int SV, int MODE>
 __global__ void __launch_bounds__(128) csr_rows_kernel(SPMF_ROWS_PARAMS) {
@@ -1069,14 +1073,14 @@ static int launch_rows(const long long* rowptr, const int* cols, const float* va
                        const float* rowsum, const float* lgam, float inv_xi, int scale_rows, int nrows,
                        int D, int NQ, const float* Ap, const float* EV, const float* PH,
                        const double* vsum, float* z, float* dzr, float* rowacc, const int* rowmid,
-                       cudaStream_t st) {
+                       int* gflag, cudaStream_t st) {
   dim3 grid(nrows, NQ);
   if constexpr (MODE == kRowsCold && KP * SV == 128)
     csr_rows_cold5_kernel<KP, SV><<<grid, 128, 0, st>>>(
-        rowptr, cols, vals, rowsum, lgam, inv_xi, scale_rows, nrows, D, Ap, EV, PH, vsum, z, dzr, rowacc, rowmid);
+        rowptr, cols, vals, rowsum, lgam, inv_xi, scale_rows, nrows, D, Ap, EV, PH, vsum, z, dzr, rowacc, rowmid, gflag);
   else
     csr_rows_kernel<KP, SV, MODE><<<grid, 128, 0, st>>>(
-        rowptr, cols, vals, rowsum, lgam, inv_xi, scale_rows, nrows, D, Ap, EV, PH, vsum, z, dzr, rowacc, rowmid);
+        rowptr, cols, vals, rowsum, lgam, inv_xi, scale_rows, nrows, D, Ap, EV, PH, vsum, z, dzr, rowacc, rowmid, gflag);
   SPMF_CHECK_LAUNCH();
   return SPMF_OK;
 }
@@ -1132,7 +1136,7 @@ int spmf_csr_row_consts(const long long* rowptr, const float* vals, long long nr
 int spmf_csr_rows(const long long* rowptr, const int* cols, const float* vals, const float* rowsum,
                   const float* lgam, float inv_xi, int scale_rows, int nrows, int D, int K, int S,
                   const float* Ap, const float* EV, const float* PH, const double* vsum, float* z,
-                  float* dzr, float* rowacc, int variant, void* stream) {
+                  float* dzr, float* rowacc, int variant, void* gs, void* stream) {
   if (!rowptr || !cols || !vals || !rowsum || !lgam || !Ap || !EV || !PH || !vsum || !z || !dzr || !rowacc)
     return SPMF_ERR_BAD_ARG;
   if (nrows <= 0 || D <= 0 || K <= 0 || K > SPMF_MAX_K || S <= 0) return SPMF_ERR_BAD_ARG;
@@ -1140,7 +1144,7 @@ int spmf_csr_rows(const long long* rowptr, const int* cols, const float* vals, c
   const int KP = spmf_kpad(K), SV = spmf_draw_vec(S), NQ = S / SV;
   cudaStream_t st = (cudaStream_t)stream;
   int rc = SPMF_OK;
-#define CALL_ROWS(KPC, SVC) rc = launch_rows<KPC, SVC, kRowsTrain>(rowptr, cols, vals, rowsum, lgam, inv_xi, scale_rows, nrows, D, NQ, Ap, EV, PH, vsum, z, dzr, rowacc, nullptr, st)
+#define CALL_ROWS(KPC, SVC) rc = launch_rows<KPC, SVC, kRowsTrain>(rowptr, cols, vals, rowsum, lgam, inv_xi, scale_rows, nrows, D, NQ, Ap, EV, PH, vsum, z, dzr, rowacc, nullptr, (int*)gs, st)
   SPMF_DISPATCH_KP_SV(KP, SV, CALL_ROWS);
 #undef CALL_ROWS
   return rc;
@@ -1154,7 +1158,7 @@ int spmf_csr_encode(const long long* rowptr, const int* cols, const float* vals,
   const int KP = spmf_kpad(K), SV = spmf_draw_vec(S), NQ = S / SV;
   cudaStream_t st = (cudaStream_t)stream;
   int rc = SPMF_OK;
-#define CALL_ENC(KPC, SVC) rc = launch_rows<KPC, SVC, kRowsEncode>(rowptr, cols, vals, rowsum, nullptr, inv_xi, scale_rows, nrows, D, NQ, Ap, nullptr, nullptr, nullptr, z, nullptr, nullptr, nullptr, st)
+#define CALL_ENC(KPC, SVC) rc = launch_rows<KPC, SVC, kRowsEncode>(rowptr, cols, vals, rowsum, nullptr, inv_xi, scale_rows, nrows, D, NQ, Ap, nullptr, nullptr, nullptr, z, nullptr, nullptr, nullptr, nullptr, st)
   SPMF_DISPATCH_KP_SV(KP, SV, CALL_ENC);
 #undef CALL_ENC
   return rc;
@@ -1213,14 +1217,14 @@ int spmf_hybrid_supported(int K, int S) {
 int spmf_csr_rows_hybrid(const long long* rowptr, const int* cols, const float* vals, const int* rowmid,
                          const float* rowsum, const float* lgam, float inv_xi, int scale_rows, int nrows,
                          int D, int K, int S, const float* Ap, const float* EV, const float* PH,
-                         const double* vsum, float* z, float* dzr, float* rowacc, void* stream) {
+                         const double* vsum, float* z, float* dzr, float* rowacc, void* gs, void* stream) {
   if (!rowptr || !cols || !vals || !rowmid || !rowsum || !lgam || !Ap || !EV || !PH || !vsum || !z || !dzr || !rowacc)
     return SPMF_ERR_BAD_ARG;
   if (nrows <= 0 || D <= 0 || K <= 0 || K > SPMF_MAX_K || S <= 0) return SPMF_ERR_BAD_ARG;
   const int KP = spmf_kpad(K), SV = spmf_draw_vec(S), NQ = S / SV;
   cudaStream_t st = (cudaStream_t)stream;
   int rc = SPMF_OK;
-#define CALL_ROWS_H(KPC, SVC) rc = launch_rows<KPC, SVC, kRowsHybrid>(rowptr, cols, vals, rowsum, lgam, inv_xi, scale_rows, nrows, D, NQ, Ap, EV, PH, vsum, z, dzr, rowacc, rowmid, st)
+#define CALL_ROWS_H(KPC, SVC) rc = launch_rows<KPC, SVC, kRowsHybrid>(rowptr, cols, vals, rowsum, lgam, inv_xi, scale_rows, nrows, D, NQ, Ap, EV, PH, vsum, z, dzr, rowacc, rowmid, (int*)gs, st)
   SPMF_DISPATCH_HYBRID(KP, SV, CALL_ROWS_H);
 #undef CALL_ROWS_H
   return rc;
@@ -1229,14 +1233,14 @@ int spmf_csr_rows_hybrid(const long long* rowptr, const int* cols, const float* 
 int spmf_csr_rows_cold(const long long* rowptr, const int* cols, const float* vals, const int* rowmid,
                        const float* rowsum, float inv_xi, int scale_rows, int nrows, int D, int K, int S,
                        const float* Ap, const float* EV, const float* PH, float* z, float* dzacc, float* rowacc,
-                       void* stream) {
+                       void* gs, void* stream) {
   if (!rowptr || !cols || !vals || !rowmid || !rowsum || !Ap || !EV || !PH || !z || !dzacc || !rowacc)
     return SPMF_ERR_BAD_ARG;
   if (nrows <= 0 || D <= 0 || K <= 0 || K > SPMF_MAX_K || S <= 0) return SPMF_ERR_BAD_ARG;
   const int KP = spmf_kpad(K), SV = spmf_draw_vec(S), NQ = S / SV;
   cudaStream_t st = (cudaStream_t)stream;
   int rc = SPMF_OK;
-#define CALL_ROWS_C(KPC, SVC) rc = launch_rows<KPC, SVC, kRowsCold>(rowptr, cols, vals, rowsum, nullptr, inv_xi, scale_rows, nrows, D, NQ, Ap, EV, PH, nullptr, z, dzacc, rowacc, rowmid, st)
+#define CALL_ROWS_C(KPC, SVC) rc = launch_rows<KPC, SVC, kRowsCold>(rowptr, cols, vals, rowsum, nullptr, inv_xi, scale_rows, nrows, D, NQ, Ap, EV, PH, nullptr, z, dzacc, rowacc, rowmid, (int*)gs, st)
   SPMF_DISPATCH_HYBRID(KP, SV, CALL_ROWS_C);
 #undef CALL_ROWS_C
   return rc;

@@ -66,9 +66,34 @@ int spmf_advi_step(const spmf_step_args* a) {
                                      hot));
   const int KP = spmf_kpad(K), SV = spmf_draw_vec(S), NQ = S / SV, REC = KP * SV;
   if (a->ev_rows0) CUDA_TRY(cudaEventRecord((cudaEvent_t)a->ev_rows0, hot));
+  const bool dense_link = a->link != SPMF_LINK_POISSON;
+  if (dense_link) {
+    // links without a closed-form sum(rate) (log_transform / Bernoulli): the whole data term runs in the
+    // dense CUDA-core kernels of spmf_dense.cu; tables stay in feature order
+    if (hybrid || !a->gs || !a->xdense) return SPMF_ERR_BAD_ARG;
+    const float* xd = a->xdense_in ? a->xdense_in : a->xdense;
+    if (!a->xdense_in) STEP_TRY(spmf_dense_scatter(a->rowptr, a->cols, a->vals, a->nrows, D, a->xdense, hot));
+    STEP_TRY(spmf_dense_encode(xd, a->eta, a->rowsum, a->inv_xi, a->scale_rows, a->nrows, D, K, S, a->link, a->Ap,
+                               a->z, hot));
+    STEP_TRY(spmf_dense_rows(xd, a->rowsum, a->lgam, a->inv_xi, a->scale_rows, a->nrows, D, K, S, a->link,
+                             SPMF_DENSE_OPTIMISTIC, 0, a->EV, a->PH, a->z, a->dzr, a->rowacc, a->gs, hot));
+    // non-finite entries met: count them / find the smallest finite log-likelihood, then redo the row pass
+    // with the reference's replacement (both launches return at once otherwise)
+    STEP_TRY(spmf_dense_rows(xd, a->rowsum, a->lgam, a->inv_xi, a->scale_rows, a->nrows, D, K, S, a->link,
+                             SPMF_DENSE_STATS, 1, a->EV, a->PH, a->z, a->dzr, a->rowacc, a->gs, hot));
+    STEP_TRY(spmf_dense_rows(xd, a->rowsum, a->lgam, a->inv_xi, a->scale_rows, a->nrows, D, K, S, a->link,
+                             SPMF_DENSE_GUARDED, 1, a->EV, a->PH, a->z, a->dzr, a->rowacc, a->gs, hot));
+    if (a->ev_rows1) CUDA_TRY(cudaEventRecord((cudaEvent_t)a->ev_rows1, hot));
+    STEP_TRY(spmf_batch_sums(a->z, a->rowacc, a->nrows, K, S, a->zcolsum, a->datasums, a->scr_d, hot));
+    if (a->ev_cols0) CUDA_TRY(cudaEventRecord((cudaEvent_t)a->ev_cols0, hot));
+    STEP_TRY(spmf_zero_col_grads(a->GAp, a->GEV, a->Gph, D, K, S, hot));
+    STEP_TRY(spmf_dense_cols(xd, a->eta, a->nrows, D, K, S, a->link, 1, a->z, a->dzr, a->EV, a->PH, a->GAp, a->GEV,
+                             a->Gph, a->gs, hot));
+    if (a->ev_cols1) CUDA_TRY(cudaEventRecord((cudaEvent_t)a->ev_cols1, hot));
+  } else {
   if (!hybrid) {
     STEP_TRY(spmf_csr_rows(a->rowptr, a->cols, a->vals, a->rowsum, a->lgam, a->inv_xi, a->scale_rows, a->nrows,
-                           D, K, S, a->Ap, a->EV, a->PH, a->vsum, a->z, a->dzr, a->rowacc, 0, hot));
+                           D, K, S, a->Ap, a->EV, a->PH, a->vsum, a->z, a->dzr, a->rowacc, 0, a->gs, hot));
   } else {
     // encode product of the hot block on the tensor cores: z = X_hot . A'[0:H]  (un-scaled)
     const int H = a->hot_cols;
@@ -98,18 +123,26 @@ int spmf_advi_step(const spmf_step_args* a) {
         STEP_TRY(spmf_zero_col_grads(a->GAp, a->GEV, a->Gph, D, K, S, hot));
       }
       STEP_TRY(spmf_csr_rows_cold(a->rowptr, a->cols, a->vals, a->rowmid, a->rowsum, a->inv_xi, a->scale_rows,
-                                  a->nrows, D, K, S, a->Ap, a->EV, a->PH, a->z, a->dzr, a->rowacc, hot));
+                                  a->nrows, D, K, S, a->Ap, a->EV, a->PH, a->z, a->dzr, a->rowacc, a->gs, hot));
       if (a->ev_tile0) CUDA_TRY(cudaEventRecord((cudaEvent_t)a->ev_tile0, hot));
-      STEP_TRY(spmf_hot_tile(a->xhot, a->EVt, a->z, a->nrows, D, H, K, S, a->dzr, a->rowacc, a->GEV, a->Gph, hot));
+      STEP_TRY(spmf_hot_tile(a->xhot, a->EVt, a->z, a->nrows, D, H, K, S, a->dzr, a->rowacc, a->GEV, a->Gph, a->gs,
+                             hot));
       if (a->ev_tile1) CUDA_TRY(cudaEventRecord((cudaEvent_t)a->ev_tile1, hot));
       STEP_TRY(spmf_rows_finish(a->rowsum, a->lgam, a->inv_xi, a->scale_rows, a->nrows, K, S, a->vsum, a->z, a->dzr,
-                                a->rowacc, hot));
+                                a->rowacc, a->gs, hot));
     } else {
       STEP_TRY(spmf_csr_rows_hybrid(a->rowptr, a->cols, a->vals, a->rowmid, a->rowsum, a->lgam, a->inv_xi,
                                     a->scale_rows, a->nrows, D, K, S, a->Ap, a->EV, a->PH, a->vsum, a->z, a->dzr,
-                                    a->rowacc, hot));
+                                    a->rowacc, a->gs, hot));
     }
   }
+  // exact guard of poisson.py:606-616: if a row pass met a non-finite log-likelihood, the data term of
+  // this step is re-evaluated densely with the reference's replacement semantics (conditional launch:
+  // returns at once otherwise); dzr / rowacc are rewritten BEFORE the column side reads them
+  const bool guard = a->gs && a->xdense;
+  if (guard)
+    STEP_TRY(spmf_guard_rows_fix(a->rowptr, a->cols, a->vals, a->rowsum, a->lgam, a->inv_xi, a->scale_rows, a->nrows,
+                                 D, K, S, a->EV, a->PH, a->z, a->dzr, a->rowacc, a->xdense, a->gs, hot));
   if (a->ev_rows1) CUDA_TRY(cudaEventRecord((cudaEvent_t)a->ev_rows1, hot));
   // column sums of z and the batch totals: only the backward reads them -> next to the column side
   const bool cols_fork = hybrid && a->aux_stream1 && a->aux_stream2 && a->ev_aux_fork && a->ev_aux_join1 && a->ev_aux_join2;
@@ -155,18 +188,22 @@ int spmf_advi_step(const spmf_step_args* a) {
       CUDA_TRY(cudaStreamWaitEvent(hot, (cudaEvent_t)a->ev_aux_join2, 0));
     }
   }
+  if (guard)        // ... and GEV / Gphi after it (GA' was computed from the fixed dzr)
+    STEP_TRY(spmf_guard_cols_fix(a->nrows, D, K, S, a->EV, a->PH, a->z, a->GEV, a->Gph, a->xdense, a->gs, hot));
   if (a->ev_cols1) CUDA_TRY(cudaEventRecord((cudaEvent_t)a->ev_cols1, hot));
+  }   // sparse / tensor-core data term
   if (side != hot) CUDA_TRY(cudaStreamWaitEvent(hot, (cudaEvent_t)a->ev_join, 0));
   if (split_bwd)
     STEP_TRY(spmf_backward_post(a->params, a->noise, a->eta, hybrid ? a->rank : nullptr, D, K, S, a->GAp, a->GEV,
                                 a->Gph, a->zcolsum, a->datasums, a->phisum, (float)a->nrows, a->u_tau_scale,
                                 a->s_tau_scale, a->decay, a->w_entropy, a->w_prior, a->world_size, a->grads,
-                                a->parts, a->scr_f, a->scr_dpre, hot));
+                                a->parts, a->scr_f, a->scr_dpre, a->gs, hot));
   else
     STEP_TRY(spmf_backward_params_ranked(a->params, a->noise, a->dgda, a->eta, hybrid ? a->rank : nullptr, D, K, S,
                                          a->GAp, a->GEV, a->Gph, a->zcolsum, a->datasums, a->phisum,
                                          (float)a->nrows, a->u_tau_scale, a->s_tau_scale, a->decay, a->w_entropy,
-                                         a->w_prior, a->world_size, a->grads, a->parts, a->scr_f, a->scr_d, hot));
+                                         a->w_prior, a->world_size, a->grads, a->parts, a->scr_f, a->scr_d, a->gs,
+                                         hot));
   if (a->adam_lr > 0.f) {
     if (a->world_size > 1) return SPMF_ERR_BAD_ARG;      // the all-reduce must come between backward and Adam
     // the scalar slack inside the gradient block is host-side bookkeeping, not a parameter gradient

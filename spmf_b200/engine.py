@@ -67,6 +67,15 @@ class StepWorkspace:
             changed = True
         return changed
 
+    def ensure_dense(self, nrows):
+        """fp32 [nrows][D] scratch of the dense evaluation (spmf_dense.cu): every step for the links without
+        a closed-form sum(rate), only when the non-finite guard fires for the default link."""
+        need = int(nrows) * self.D
+        if getattr(self, "xdense", None) is None or self.xdense.numel() < need:
+            self.xdense = torch.empty(max(need, 1), dtype=torch.float32, device=self.device)
+            return True
+        return False
+
     def ensure_rows(self, nrows):
         if nrows <= self.max_rows:
             return False
@@ -80,8 +89,12 @@ class StepWorkspace:
 class AdviEngine:
     """ELBO + gradient of one minibatch; optimiser state; everything stays on the device."""
 
+    # exact guard scratch is nrows*D floats; above this many bytes the guard degrades to drop-and-count
+    GUARD_SCRATCH_LIMIT = 16 << 30
+
     def __init__(self, D, K, S, device, u_tau_scale, s_tau_scale, decay, scale_rows=True,
-                 entropy_weight=1.0, prior_weight=1.0, world_size=1, seed=0, max_rows=0):
+                 entropy_weight=1.0, prior_weight=1.0, world_size=1, seed=0, max_rows=0, link=0,
+                 exact_guard=True):
         if K > _abi.MAX_K:
             raise _abi.SpmfError(f"latent_dim {K} > {_abi.MAX_K} is not supported by the CUDA path")
         self.D, self.K, self.S = int(D), int(K), int(S)
@@ -102,10 +115,18 @@ class AdviEngine:
         self.adam_v = torch.zeros_like(self.params)
         self.noise = torch.empty(L.n_noise, dtype=torch.float32, device=self.device)
         self.dgda = torch.zeros(L.n_noise, dtype=torch.float32, device=self.device)
-        self.eta = torch.ones(D, dtype=torch.float32, device=self.device)
+        # [2][D]: decoder scale eta_i | encoder divisor (eta_i, or 1 under log_transform) -- spmf_model.cuh
+        self.eta = torch.ones(2 * D, dtype=torch.float32, device=self.device)
+        # link function (SPMF_LINK_*): 0 = linear Poisson (sparse / tensor-core path with closed-form sum(rate));
+        # log_transform / Bernoulli run the dense CUDA-core path of spmf_dense.cu
+        self.link = int(link)
+        self.exact_guard = bool(exact_guard)
+        # device guard state (poisson.py:606-616): flag | nbad | (min finite log-likelihood, entry)
+        self.gs = torch.zeros(int(_abi._lib.spmf_guard_state_bytes()), dtype=torch.uint8, device=self.device)
+        self.reset_guard()
         self.rank = None          # int32 [D]: table row of each feature (hot-column ordering), or None
         self.hot_cols = 0         # H > 0 enables the hybrid (tensor-core hot block + gather) step
-        cap = int(_abi._lib.spmf_hybrid_supported(self.K, self.S))
+        cap = int(_abi._lib.spmf_hybrid_supported(self.K, self.S)) if self.link == 0 else 0
         # cap 2: GEMMs + fused tile kernel (default on).  cap 1 (latent dims 64 / 128): only the count
         # products have a tensor-core path; measured at K=128 it does not beat the gather kernels yet
         # (5.43 vs 5.39 ms/step), so it is opt-in.
@@ -133,6 +154,28 @@ class AdviEngine:
     # ------------------------------------------------------------------ pieces
     NOISE_NORMAL, NOISE_GAMMA = 1, 2
 
+    def reset_guard(self):
+        """Re-arm the guard state (the training step's last kernel does this itself; the API paths that
+        stop after the data term call it explicitly)."""
+        _abi.call("spmf_guard_reset", _ptr(self.gs), 2 if self.link != 0 else 0, _stream())
+
+    def guard_report(self):
+        """(flag, nbad, replacement value min(finite) - 10) of the last data-term evaluation (host sync)."""
+        import ctypes as C
+        raw = bytes(self.gs.cpu().numpy().tobytes())
+        buf = C.create_string_buffer(raw, len(raw))
+        flag, nbad, mv = C.c_int(), C.c_int(), C.c_float()
+        _abi.call("spmf_guard_decode", C.cast(buf, C.c_void_p), C.byref(flag), C.byref(nbad), C.byref(mv))
+        return flag.value, nbad.value, mv.value
+
+    def _guard_scratch(self, nrows):
+        """Dense scratch pointer for the exact guard / dense links, or None (guard degrades to drop-and-count)."""
+        w = self.ws
+        if self.link == 0 and (not self.exact_guard or 4 * int(nrows) * self.D > self.GUARD_SCRATCH_LIMIT):
+            return None
+        w.ensure_dense(max(int(nrows), w.max_rows))
+        return w.xdense
+
     def fill_noise(self, step=None, which=3, advance=True):
         """Philox draws for `step`: N(0,1) for v,w,u,s (which&1), Gamma(alpha,1) for the rest (which&2)."""
         step = self.rng_step if step is None else step
@@ -150,10 +193,18 @@ class AdviEngine:
         self.launches += 5
 
     def data_term(self, b: DeviceBatch, variant=0):
+        """Row pass + batch sums + column pass of `b` for the operands currently in the workspace (API
+        path: unormalized_log_prob_parts; the training step issues the same sequence natively), including
+        the exact non-finite guard / the dense links."""
         w = self.ws
         w.ensure_rows(b.nrows)
-        b.ensure_csc()
         st = _stream()
+        self.reset_guard()
+        xd = self._guard_scratch(b.nrows)
+        if self.link != 0:
+            self.dense_data_term(b, xd)
+            return
+        b.ensure_csc()
         ev = self.kernel_events
         if ev is not None:
             e0, e1, e2, e3 = (torch.cuda.Event(enable_timing=True) for _ in range(4))
@@ -161,7 +212,19 @@ class AdviEngine:
         _abi.call("spmf_csr_rows", _ptr(b.rowptr), _ptr(b.cols), _ptr(b.vals), _ptr(b.rowsum),
                   _ptr(b.lgam), self.inv_xi, int(self.scale_rows), b.nrows, self.D, self.K, self.S,
                   _ptr(w.Ap), _ptr(w.EV), _ptr(w.PH), _ptr(w.vsum), _ptr(w.z), _ptr(w.dzr),
-                  _ptr(w.rowacc), variant, st)
+                  _ptr(w.rowacc), variant, _ptr(self.gs), st)
+        if xd is not None and self.world_size > 1 and torch.distributed.is_initialized():
+            # rows are sharded: if ANY rank met a non-finite entry, every rank needs its dense statistics
+            # (the replacement value is the minimum over the whole batch, poisson.py:609)
+            mine = self.guard_report()[0] & 1
+            t = torch.tensor([float(mine)], device=self.device)
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX, group=getattr(self, "process_group", None))
+            if t.item() > 0 and not mine:
+                _abi.call("spmf_guard_reset", _ptr(self.gs), 1, st)
+        if xd is not None:
+            _abi.call("spmf_guard_rows_fix", _ptr(b.rowptr), _ptr(b.cols), _ptr(b.vals), _ptr(b.rowsum), _ptr(b.lgam),
+                      self.inv_xi, int(self.scale_rows), b.nrows, self.D, self.K, self.S, _ptr(w.EV), _ptr(w.PH),
+                      _ptr(w.z), _ptr(w.dzr), _ptr(w.rowacc), _ptr(xd), _ptr(self.gs), st)
         if ev is not None:
             e1.record()
         _abi.call("spmf_batch_sums", _ptr(w.z), _ptr(w.rowacc), b.nrows, self.K, self.S,
@@ -171,11 +234,44 @@ class AdviEngine:
         _abi.call("spmf_csc_cols", _ptr(b.colptr), _ptr(b.crows), _ptr(b.cvals), b.nnz, b.nrows,
                   self.D, self.K, self.S, _ptr(w.z), _ptr(w.dzr), _ptr(w.EV), _ptr(w.PH), _ptr(w.GAp),
                   _ptr(w.GEV), _ptr(w.Gph), variant, st)
+        if xd is not None:
+            _abi.call("spmf_guard_cols_fix", b.nrows, self.D, self.K, self.S, _ptr(w.EV), _ptr(w.PH), _ptr(w.z),
+                      _ptr(w.GEV), _ptr(w.Gph), _ptr(xd), _ptr(self.gs), st)
         if ev is not None:
             e3.record()
             ev.setdefault("csr_rows", []).append((e0, e1, b.nnz, b.nrows))
             ev.setdefault("csc_cols", []).append((e2, e3, b.nnz, b.nrows))
-        self.launches += 1 + 4 + 1 + 3   # rows, 4 reduce launches, cols (+3 memsets)
+        self.launches += 1 + 4 + 1 + 3 + (2 if xd is not None else 0)   # rows, 4 reduce launches, cols (+3 memsets), guard
+
+    def dense_scatter(self, b: DeviceBatch, xd):
+        if b.cols is None:
+            raise _abi.SpmfError("the dense links need the batch's CSR arrays (not a hybrid-only upload)")
+        _abi.call("spmf_dense_scatter", _ptr(b.rowptr), _ptr(b.cols), _ptr(b.vals), b.nrows, self.D, _ptr(xd), _stream())
+
+    def dense_encode(self, b: DeviceBatch, xd):
+        w = self.ws
+        _abi.call("spmf_dense_encode", _ptr(xd), _ptr(self.eta), _ptr(b.rowsum), self.inv_xi, int(self.scale_rows),
+                  b.nrows, self.D, self.K, self.S, self.link, _ptr(w.Ap), _ptr(w.z), _stream())
+
+    def dense_data_term(self, b: DeviceBatch, xd, forward_only=False):
+        """Data term of the links without a closed-form sum(rate) (log_transform / Bernoulli), spmf_dense.cu."""
+        w, st = self.ws, _stream()
+        self.dense_scatter(b, xd)
+        self.dense_encode(b, xd)
+        for mode, cond in ((_abi.DENSE_OPTIMISTIC, 0), (_abi.DENSE_STATS, 1), (_abi.DENSE_GUARDED, 1)):
+            _abi.call("spmf_dense_rows", _ptr(xd), _ptr(b.rowsum), _ptr(b.lgam), self.inv_xi, int(self.scale_rows),
+                      b.nrows, self.D, self.K, self.S, self.link, mode, cond, _ptr(w.EV), _ptr(w.PH), _ptr(w.z),
+                      _ptr(w.dzr), _ptr(w.rowacc), _ptr(self.gs), st)
+        _abi.call("spmf_batch_sums", _ptr(w.z), _ptr(w.rowacc), b.nrows, self.K, self.S,
+                  _ptr(w.zcolsum), _ptr(w.datasums), _ptr(w.scr_d), st)
+        self.launches += 2 + 2 + 3 + 2
+        if forward_only:
+            return
+        _abi.call("spmf_zero_col_grads", _ptr(w.GAp), _ptr(w.GEV), _ptr(w.Gph), self.D, self.K, self.S, st)
+        _abi.call("spmf_dense_cols", _ptr(xd), _ptr(self.eta), b.nrows, self.D, self.K, self.S, self.link, 1,
+                  _ptr(w.z), _ptr(w.dzr), _ptr(w.EV), _ptr(w.PH), _ptr(w.GAp), _ptr(w.GEV), _ptr(w.Gph),
+                  _ptr(self.gs), st)
+        self.launches += 4
 
     def gamma_grad(self):
         _abi.call("spmf_gamma_grad", _ptr(self.params), _ptr(self.noise), self.D, self.K, self.S,
@@ -189,7 +285,7 @@ class AdviEngine:
                   _ptr(w.datasums), _ptr(w.phisum), float(batch_rows), self.u_tau_scale,
                   self.s_tau_scale, self.decay, self.entropy_weight, self.prior_weight,
                   self.world_size, _ptr(self.grads), _ptr(w.parts), _ptr(w.scr_f), _ptr(w.scr_d),
-                  _stream())
+                  _ptr(self.gs), _stream())
         self.launches += 9
 
     def _mark(self, name, start):
@@ -250,7 +346,8 @@ class AdviEngine:
         if batch.nrows > w.max_rows:
             w.ensure_rows(batch.nrows)
             self._args = None
-        hybrid = self.hot_cols > 0 and self.hybrid_ok and self.rank is not None and batch.nnz > 0
+        hybrid = (self.link == 0 and self.hot_cols > 0 and self.hybrid_ok and self.rank is not None
+                  and batch.nnz > 0)
         if hybrid:
             h = batch.ensure_hot(self.rank, self.hot_cols, hot_csc=(self.hot_mode != 2),
                                  version=getattr(self, "rank_version", 0))
@@ -260,8 +357,11 @@ class AdviEngine:
             if batch.cols is None or batch.vals is None:
                 raise _abi.SpmfError("this batch was uploaded in hybrid-only form (no CSR arrays) but the engine "
                                      f"for S={self.S} runs the gather step; upload it without a hot split")
-            batch.ensure_csc()
+            if self.link == 0:
+                batch.ensure_csc()
+        xd = self._guard_scratch(batch.nrows)
         a = self._step_args()
+        a.link, a.gs, a.xdense, a.xdense_in = self.link, _ptr(self.gs), _ptr(xd), None
         a.z, a.dzr, a.rowacc = _ptr(w.z), _ptr(w.dzr), _ptr(w.rowacc)
         a.inv_xi, a.scale_rows = self.inv_xi, int(self.scale_rows)
         a.fresh_noise, a.rng_step = int(fresh_noise), self.rng_step
@@ -316,6 +416,10 @@ class AdviEngine:
         # (2 splits, 2 GEMMs, second column kernel), +7 tile-hybrid (2 splits, 2 GEMMs, EV tiles, tile
         # kernel, row finalisation); +1 Adam
         base = 17 if a.scr_dpre else 16
+        if self.link != 0:
+            base += 6              # scatter (2), encode, two conditional row passes, zeroing -- minus nothing
+        elif xd is not None:
+            base += 2              # the two conditional guard launches
         self.launches += base + (1 if do_adam else 0) + ((7 if self.hot_mode == 2 else 5) if hybrid else 0)
         return w.parts.view(self.S, _abi.NUM_PARTS)
 

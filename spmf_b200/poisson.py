@@ -11,8 +11,13 @@ Differences that are deliberate:
     float64 oracle is checked at 1e-4 relative;
   * batches may be dense arrays (compacted to CSR by a kernel), scipy.sparse matrices, or
     device-resident `DeviceBatch`es cut from a `CsrShard`;
-  * `log_transform=True`, `horshoe_plus=False` and custom encoder/decoder callables have no CUDA
-    path yet and raise (no silent fallback).
+  * `log_transform=True` (poisson.py:41-42, 52-53) has no closed-form sum(rate): it runs the dense
+    CUDA-core kernels of csrc/spmf_dense.cu over every (draw, row, feature) entry;
+  * the non-finite guard of poisson.py:606-616 is exact: a step that meets a non-finite
+    log-likelihood is re-evaluated densely with the reference's min(finite) - 10 replacement;
+  * `horshoe_plus=False` (the reference's own branch fails at construction: misplaced kwarg at
+    poisson.py:388) and arbitrary Python encoder/decoder callables (a CUDA kernel cannot run them)
+    raise -- no silent fallback.
 """
 from __future__ import annotations
 
@@ -67,6 +72,51 @@ class _SurrogateDistribution:
         return self._m.surrogate_vars
 
 
+class _PriorDistribution:
+    """Stand-in for `self.prior_distribution` (tfd.JointDistributionNamed, poisson.py:400-401): the
+    horseshoe+ hierarchy of poisson.py:228-377.  `log_prob_parts` is what the energy calls
+    (poisson.py:590); `sample` draws ancestrally (diagnostics only -- the training step never samples
+    the prior)."""
+
+    def __init__(self, model):
+        self._m = model
+
+    def log_prob_parts(self, params):
+        return self._m._prior_parts_torch(params)
+
+    def log_prob(self, params=None, **kw):
+        return sum(self.log_prob_parts(params if params is not None else kw).values())
+
+    def sample(self, n=None, seed=None):
+        m = self._m
+        D, K = m.feature_dim, m.latent_dim
+        shp = () if n is None else (int(n),)
+        gen = torch.Generator(device=m.device)
+        gen.manual_seed(int(seed) if seed is not None else 0)
+        f64 = dict(device=m.device, dtype=torch.float64)
+
+        def half_normal(scale, shape):
+            return (torch.randn(*shp, *shape, generator=gen, **f64) * scale).abs()
+
+        def inv_gamma(conc, scale, shape):            # 1 / Gamma(conc, rate=scale)
+            g = torch._standard_gamma(torch.full(shp + shape, conc, **f64), generator=gen)
+            return scale / g
+
+        ck = m.symmetry_breaking_decay ** torch.arange(K, **f64)[None, :]
+        out = {}
+        out['u_eta_a'] = inv_gamma(0.5, 1.0, (D, K))
+        out['u_tau_a'] = inv_gamma(0.5, 1.0 / m.u_tau_scale ** 2, (1, K))
+        out['s_eta_a'] = inv_gamma(0.5, 1.0, (2, D))
+        out['s_tau_a'] = inv_gamma(0.5, 1.0 / m.s_tau_scale ** 2, (1, D))
+        for name, a in (('u_eta', 'u_eta_a'), ('u_tau', 'u_tau_a'), ('s_eta', 's_eta_a'), ('s_tau', 's_tau_a')):
+            out[name] = inv_gamma(0.5, 1.0 / out[a], tuple(out[a].shape[len(shp):])).sqrt()   # SqrtInverseGamma
+        out['u'] = half_normal(out['u_eta'] * out['u_tau'] * ck, ())
+        out['s'] = half_normal(out['s_eta'] * out['s_tau'], ())
+        out['v'] = half_normal(0.1, (K, D))
+        out['w'] = half_normal(1.0, (1, D))
+        return out
+
+
 class PoissonFactorization:
     """Sparse (horseshoe) Poisson matrix factorisation, ADVI on B200."""
 
@@ -80,13 +130,14 @@ class PoissonFactorization:
                  horshoe_plus=True, column_norms=None, count_key='counts',
                  initialize_distributions=True, dtype=torch.float32, device=None,
                  entropy_weight=1.0, prior_weight=1.0, seed=0, process_group=None, hot_density=None,
-                 **kwargs):
+                 exact_guard=True, **kwargs):
         if encoder_function is not None or decoder_function is not None:
-            raise _abi.SpmfError("custom encoder/decoder callables have no CUDA path")
-        if log_transform:
-            raise _abi.SpmfError("log_transform=True has no CUDA path yet (needs the dense rate)")
+            raise _abi.SpmfError("custom encoder/decoder callables have no CUDA path (the linear and "
+                                 "log_transform pairs of poisson.py:34-54 are built in)")
         if not horshoe_plus:
-            raise _abi.SpmfError("horshoe_plus=False (AbsHorseshoe priors) has no CUDA path yet")
+            raise _abi.SpmfError("horshoe_plus=False (AbsHorseshoe priors) has no CUDA path")
+        self.link = self._link_id(bool(log_transform))
+        self.exact_guard = bool(exact_guard)
         if feature_dim is None:
             raise ValueError("feature_dim is required")
         self.scale_rows = scale_rows                      # poisson.py:85-92
@@ -124,6 +175,11 @@ class PoissonFactorization:
             self.create_distributions()
         print(f"Feature dim: {self.feature_dim} -> Latent dim {self.latent_dim}")   # poisson.py:110-111
 
+    @staticmethod
+    def _link_id(log_transform):
+        """SPMF_LINK_* of this model class (poisson.py:34-54, 177-183)."""
+        return _abi.LINK_POISSON_LOG if log_transform else _abi.LINK_POISSON
+
     # ------------------------------------------------------------------ distributions
     def create_distributions(self):
         """poisson.py:212-573: (re)initialise the 24 variational tensors; priors are implicit in
@@ -135,7 +191,7 @@ class PoissonFactorization:
         eng = self._engine_for(1)
         self._params = eng.params
         self.surrogate_distribution = _SurrogateDistribution(self)
-        self.prior_distribution = None
+        self.prior_distribution = _PriorDistribution(self)
         self.set_calibration_expectations()
 
     def _engine_for(self, S) -> AdviEngine:
@@ -147,7 +203,9 @@ class PoissonFactorization:
                 world = torch.distributed.get_world_size(self.process_group)
             eng = AdviEngine(self.feature_dim, self.latent_dim, S, self.device, self.u_tau_scale,
                              self.s_tau_scale, self.symmetry_breaking_decay, self.scale_rows,
-                             self.entropy_weight, self.prior_weight, world, self.seed)
+                             self.entropy_weight, self.prior_weight, world, self.seed, link=self.link,
+                             exact_guard=self.exact_guard)
+            eng.process_group = self.process_group
             if self._params is not None:                # engines share parameters / optimiser state
                 first = next(iter(self._engines.values()))
                 eng.params, eng.grads = first.params, first.grads
@@ -157,7 +215,13 @@ class PoissonFactorization:
         return self._engines[S]
 
     def _push_scales(self, eng):
-        eng.eta.copy_(self.eta_i.reshape(-1).to(torch.float32))
+        D = self.feature_dim
+        eta = self.eta_i.reshape(-1).to(torch.float32)
+        eng.eta[:D].copy_(eta)                                  # decoder scale (poisson.py:52-54)
+        if self.log_transform:
+            eng.eta[D:].fill_(1.0)                              # encoder log(x/eta + 1) acts on the counts
+        else:
+            eng.eta[D:].copy_(eta)                              # encoder x/eta folded into A'
         xi = float(self.xi_u_global)
         eng.inv_xi = 1.0 / xi if self.scale_rows else 1.0
         eng.scale_rows = bool(self.scale_rows)
@@ -227,6 +291,8 @@ class PoissonFactorization:
         H columns populated in >= hot_density of the rows form the tensor-core block.  Identical on
         every rank (computed from the all-reduced counts)."""
         self.col_rank, self.hot_cols = None, 0
+        if self.link != _abi.LINK_POISSON:
+            return                      # dense links: no closed form, no hot / cold split
         self._rank_version = getattr(self, "_rank_version", 0) + 1     # invalidates cached hybrid forms
         # (whether a given engine uses the hot block is its own decision: hybrid_ok depends on S)
         if self.hot_density <= 0 or nrows <= 0 or self.latent_dim > _abi.MAX_K:
@@ -285,7 +351,8 @@ class PoissonFactorization:
             u, v, w, s = u[None], v[None], w[None], s[None]
         a = s[:, 0, :] / (s[:, 0, :] + s[:, 1, :])
         b = 1.0 - a
-        Ap = a[:, :, None] * u / eta[None, :, None]                  # (S,D,K)
+        eta_enc = torch.ones_like(eta) if self.log_transform else eta
+        Ap = a[:, :, None] * u / eta_enc[None, :, None]              # (S,D,K)
         EV = eta[None, :, None] * v.transpose(-1, -2)                # (S,D,K)
         PH = eta[None, :] * b * w[:, 0, :]                           # (S,D)
 
@@ -324,8 +391,13 @@ class PoissonFactorization:
         zeros_w = torch.zeros((S, 1, D) if batched else (1, D), device=self.device)
         self._operands_from_theta(eng, u, zeros_v, zeros_w, s)
         ws = eng.ws
-        _abi.call("spmf_csr_encode", _ptr(b.rowptr), _ptr(b.cols), _ptr(b.vals), _ptr(b.rowsum),
-                  eng.inv_xi, int(self.scale_rows), b.nrows, D, K, S, _ptr(ws.Ap), _ptr(ws.z), _stream())
+        if self.link & 1:              # log(x/eta + 1) encoder: dense kernel (spmf_dense.cu)
+            xd = eng._guard_scratch(b.nrows)
+            eng.dense_scatter(b, xd)
+            eng.dense_encode(b, xd)
+        else:
+            _abi.call("spmf_csr_encode", _ptr(b.rowptr), _ptr(b.cols), _ptr(b.vals), _ptr(b.rowsum),
+                      eng.inv_xi, int(self.scale_rows), b.nrows, D, K, S, _ptr(ws.Ap), _ptr(ws.z), _stream())
         z = self._unpack_rows(eng, ws.z, b.nrows).clone()
         return z if batched else z[0]
 
@@ -338,15 +410,35 @@ class PoissonFactorization:
         b = as_device_batch(data[self.count_key] if isinstance(data, dict) else data, self.device)
         self._operands_from_theta(eng, params['u'], params['v'], params['w'], params['s'])
         eng.data_term(b)
-        ws = eng.ws
-        ds = ws.datasums.view(ws.NQ, 4, ws.SV).permute(0, 2, 1).reshape(S, 4)
-        ph = ws.phisum.view(S)
-        x_part = ds[:, 0] - ds[:, 1] - b.nrows * ph
-        z_part = b.nrows * self.latent_dim * 0.5 * math.log(2.0 / math.pi) - 0.5 * ds[:, 2]
+        x_part, z_part = self._data_parts(eng, b.nrows)
         parts = {k: v * prior_weight for k, v in self._prior_parts_torch(params).items()}
         parts['z'] = z_part
         parts['x'] = x_part
         return parts
+
+    def _data_parts(self, eng, nrows):
+        """('x', 'z') parts of the last eng.data_term(): closed-form assembly, or -- if the exact guard
+        fired or the link is dense -- sum over the finite entries + (#non-finite) * (min(finite) - 10)
+        (poisson.py:606-619).  Multi-rank: rows are sharded, so sums / counts are all-reduced and the
+        minimum is the GLOBAL one, as the reference's single (S,B,D) tensor would give."""
+        ws, S = eng.ws, eng.S
+        ds = ws.datasums.view(ws.NQ, 4, ws.SV).permute(0, 2, 1).reshape(S, 4).clone()
+        flag, nbad, min_val = eng.guard_report()
+        dist_on = torch.distributed.is_available() and torch.distributed.is_initialized() and eng.world_size > 1
+        rows = torch.tensor([float(nrows)], dtype=torch.float64, device=self.device)
+        if dist_on:
+            t = torch.tensor([float(flag != 0), -float(min_val)], dtype=torch.float64, device=self.device)
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX, group=self.process_group)
+            min_val = -float(t[1].item())        # (eng.data_term made the flag collective already)
+            torch.distributed.all_reduce(ds, group=self.process_group)
+            torch.distributed.all_reduce(rows, group=self.process_group)
+        n = float(rows.item())
+        if flag:
+            x_part = ds[:, 0] + ds[:, 3] * min_val
+        else:
+            x_part = ds[:, 0] - ds[:, 1] - n * ws.phisum.view(S)
+        z_part = n * self.latent_dim * 0.5 * math.log(2.0 / math.pi) - 0.5 * ds[:, 2]
+        return x_part, z_part
 
     def unormalized_log_prob(self, data=None, prior_weight=1., **params):
         # poisson.py:575-580 -- the caller's prior_weight is discarded there; kept for parity.
@@ -389,9 +481,14 @@ class PoissonFactorization:
         f32 = dict(device=self.device, dtype=torch.float32)
         s, u, v, w = (torch.as_tensor(t).to(**f32) for t in (s, u, v, w))
         z = self.encode(x, u, s)
-        rate = torch.matmul(z, v) * self.eta_i.to(**f32) + self.intercept_matrix(w, s)
-        ll = torch.xlogy(x, rate) - rate - torch.lgamma(x + 1.0)
-        return {'log_likelihood': ll, 'rate': rate}
+        lin = torch.matmul(z, v) * self.eta_i.to(**f32)
+        rate = (torch.expm1(lin) if self.log_transform else lin) + self.intercept_matrix(w, s)   # :52-54, :177
+        return {'log_likelihood': self._log_prob(x, rate), 'rate': rate}
+
+    @staticmethod
+    def _log_prob(x, rate):
+        """tfd.Poisson(rate).log_prob(x)  (poisson.py:178-183)."""
+        return torch.xlogy(x, rate) - rate - torch.lgamma(x + 1.0)
 
     def predictive_distribution(self, s, u, v, w, data, *args, **kwargs):
         """poisson.py:187-210 (the reference reduces a key 'll' that does not exist; here 'll' is
@@ -419,10 +516,15 @@ class PoissonFactorization:
         ws = eng.ws
         ws.ensure_rows(b.nrows)
         self._operands_from_theta(eng, params['u'], params['v'], params['w'], params['s'])
+        if self.link != _abi.LINK_POISSON:        # dense links: per-row sums over every entry (spmf_dense.cu)
+            eng.reset_guard()
+            eng.dense_data_term(b, eng._guard_scratch(b.nrows), forward_only=True)
+            ra = ws.rowacc[:ws.NQ * b.nrows * 4 * ws.SV].view(ws.NQ, b.nrows, 4, ws.SV).to(torch.float64)
+            return ra[:, :, 0, :].permute(0, 2, 1).reshape(S, b.nrows)
         _abi.call("spmf_csr_rows", _ptr(b.rowptr), _ptr(b.cols), _ptr(b.vals), _ptr(b.rowsum), _ptr(b.lgam),
                   eng.inv_xi, int(self.scale_rows), b.nrows, self.feature_dim, self.latent_dim, S,
                   _ptr(ws.Ap), _ptr(ws.EV), _ptr(ws.PH), _ptr(ws.vsum), _ptr(ws.z), _ptr(ws.dzr),
-                  _ptr(ws.rowacc), 0, _stream())
+                  _ptr(ws.rowacc), 0, None, _stream())
         ra = ws.rowacc[:ws.NQ * b.nrows * 4 * ws.SV].view(ws.NQ, b.nrows, 4, ws.SV).to(torch.float64)
         ll = (ra[:, :, 0, :] - ra[:, :, 1, :]).permute(0, 2, 1).reshape(S, b.nrows)
         return ll - ws.phisum.view(S, 1)
@@ -455,6 +557,10 @@ class PoissonFactorization:
         lppd, pwaic, e1, e2 = (float(t) for t in acc.cpu())
         var = max(e2 / n - (e1 / n) ** 2, 0.0) * (n / (n - 1.0) if n > 1 else 1.0)
         return {'waic': -2.0 * e1, 'se': 2.0 * math.sqrt(n * var), 'lppd': lppd, 'pwaic': pwaic}
+
+    def sample(self, n=None, seed=None):
+        """[EXT] BayesianModel.sample: draws of every latent variable from the surrogate posterior."""
+        return self.surrogate_distribution.sample(n, seed=seed)
 
     def unormalized_log_prob_list(self, *x):
         """poisson.py:703-709 (positional wrapper; needs `data` bound by the caller)."""
@@ -595,13 +701,18 @@ class PoissonFactorization:
                           u_tau_scale=self.u_tau_scale, s_tau_scale=self.s_tau_scale,
                           symmetry_breaking_decay=self.symmetry_breaking_decay,
                           scale_columns=self.scale_columns, scale_rows=self.scale_rows,
-                          count_key=self.count_key),
+                          log_transform=self.log_transform, count_key=self.count_key),
         }
 
     def save(self, filename):
-        """[EXT] BayesianModel.save (dill pickle in the reference; bin/factorize_csv.py:136-139)."""
+        """[EXT] BayesianModel.save (a dill pickle in the reference; bin/factorize_csv.py:136-139).  The
+        state is plain tensors / floats, so the file loads with either dill or pickle."""
+        try:
+            import dill as _pk
+        except ImportError:          # pragma: no cover - dill ships with the image
+            _pk = pickle
         with open(filename, 'wb') as f:
-            pickle.dump(self.state(), f)
+            _pk.dump(self.state(), f)
 
     def reconstitute(self, state):
         """poisson.py:711-717: re-create distributions, then assign the saved tensors in order."""

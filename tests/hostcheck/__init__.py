@@ -132,9 +132,15 @@ def pack_noise(noise, D, K, S):
     return flat
 
 
+def _eta2(eta, D):
+    """[2][D] scale table of the kernels: decoder scale | encoder divisor (both eta_i for the linear link)."""
+    e = np.ascontiguousarray(eta, np.float32).reshape(-1)
+    return np.ascontiguousarray(np.concatenate([e, e]) if e.size == D else e, np.float32)
+
+
 def draw_operands(P, N, eta, D, K, S):
     Ap = np.zeros((S, D, K), np.float32); EV = np.zeros((S, D, K), np.float32); PH = np.zeros((S, D), np.float32)
-    lib.hc_draw_operands(P, N, np.ascontiguousarray(eta, np.float32), D, K, S, Ap, EV, PH)
+    lib.hc_draw_operands(P, N, _eta2(eta, D), D, K, S, Ap, EV, PH)
     return Ap, EV, PH
 
 
@@ -142,7 +148,7 @@ def backward_params(P, N, eta, D, K, S, GAp, GEV, Gphinz, batch_rows, u_tau_scal
                     w_entropy=1.0, w_prior=1.0, world=1):
     grads = np.zeros_like(P)
     parts = np.zeros((S, 16), np.float64)
-    lib.hc_backward_params(P, N, np.ascontiguousarray(eta, np.float32), D, K, S,
+    lib.hc_backward_params(P, N, _eta2(eta, D), D, K, S,
                            np.ascontiguousarray(GAp, np.float32), np.ascontiguousarray(GEV, np.float32),
                            np.ascontiguousarray(Gphinz, np.float32), batch_rows, u_tau_scale,
                            s_tau_scale, decay, w_entropy, w_prior, world, grads, parts)

@@ -59,7 +59,10 @@ def test_bad_arguments_are_rejected():
     with pytest.raises(_abi.SpmfError):       # null pointers
         _abi.call("spmf_fill_noise", None, None, 10, 2, 1, 0, 0, 3, None)
     with pytest.raises(_abi.SpmfError):
-        _abi.call("spmf_csr_rows", *([None] * 5), 1.0, 1, 4, 10, 2, 1, *([None] * 7), 0, None)
+        _abi.call("spmf_csr_rows", *([None] * 5), 1.0, 1, 4, 10, 2, 1, *([None] * 7), 0, None, None)
+    with pytest.raises(_abi.SpmfError):       # dense-link entry points validate the same way
+        _abi.call("spmf_dense_rows", *([None] * 3), 1.0, 1, 4, 10, 2, 1, 1, 0, 0, *([None] * 7))
+    assert _abi._lib.spmf_guard_state_bytes() == 16
 
 
 def test_no_cpu_fallback():

@@ -1,0 +1,215 @@
+"""GPU parity of (1) the exact non-finite guard of poisson.py:606-616 and (2) the log_transform link of
+poisson.py:41-42, 52-53 -- both evaluated by the dense CUDA-core kernels of csrc/spmf_dense.cu.
+
+Guard: one feature is forced to rate exactly 0 (v and w of that column at loc = -1000: softplus
+underflows to 0 in float32 AND float64), so every nonzero count in that column has log-likelihood
+-inf.  The reference replaces those entries by min(finite entries of the whole (S,B,D) tensor) - 10.
+  * value: `unormalized_log_prob_parts` vs the oracle (oracle/spmf_oracle.py:340-352);
+  * training step: loss, parts and all 24 gradients vs autograd of the same guarded energy.  The
+    reference's OWN autograd gradient is NaN in this regime (0 * d log(rate)/d rate at rate = 0, in TF
+    as in torch), so the comparison uses a restatement that differs from the oracle in exactly one
+    respect: log() of a non-finite entry's rate is not back-propagated (tests/util-free, below).
+"""
+import numpy as np
+import pytest
+import torch
+
+from tests.util import make_counts, make_oracle, perturbed_params, rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL, TOL_IG = 1e-4, 5e-4
+
+
+def _load(eng, params):
+    views = eng.layout.views(eng.params)
+    for k, v in params.items():
+        views[k].copy_(v.to(device=eng.device, dtype=torch.float32))
+
+
+def _kill_column(params, d0):
+    """rate of feature d0 == 0 for every row and draw (in fp32 and fp64)."""
+    p = {k: v.clone() for k, v in params.items()}
+    p['v/loc'][:, d0] = -1000.0
+    p['w/loc'][:, d0] = -1000.0
+    return p
+
+
+def _guarded_loss_safe(oracle, params, noise, x):
+    """mean_s[log q - energy] with the guard of poisson.py:606-616, autograd-safe: identical to
+    OraclePoissonFactorization.loss except that the rate of a non-finite entry is detached to 1 before
+    log(), so that its (zero-weight) branch does not inject 0 * inf = NaN into the gradient."""
+    from oracle.spmf_oracle import halfnormal_log_prob
+    theta, logq = oracle.sample(params, noise)
+    parts = oracle.prior_log_prob_parts(theta)
+    xt = torch.as_tensor(x, dtype=torch.float64)
+    z = oracle.encode(xt, theta['u'], theta['s'])
+    rate = oracle.decoder_function(torch.matmul(z, theta['v'])) + oracle.intercept_matrix(theta['w'], theta['s'])
+    bad = ~torch.isfinite(torch.where(xt == 0, torch.zeros_like(rate), xt * torch.log(rate)) - rate)
+    rs = torch.where(bad, torch.ones_like(rate), rate)
+    ll = torch.where(xt == 0, torch.zeros_like(rs), xt * torch.log(rs)) - torch.lgamma(xt + 1.0) - rs
+    min_val = torch.where(bad, torch.zeros_like(ll), ll).min() - 10.0
+    ll = torch.where(bad, torch.ones_like(ll) * min_val, ll)
+    parts['x'] = ll.sum((-1, -2))
+    parts['z'] = halfnormal_log_prob(z, torch.ones_like(z)).sum((-1, -2))
+    return (logq - sum(parts.values())).mean(), logq, parts, int(bad.sum())
+
+
+@pytest.mark.parametrize("D,K,B,S,kind,hot", [
+    (40, 4, 64, 4, "noise", False),        # gather path (K=4 has no tensor-core form)
+    (160, 16, 192, 4, "noise", True),      # every column hot: tcgen05 tile kernel raises the flag
+    (300, 32, 96, 4, "sparse", True),      # hot + cold columns; the dead column is a hot one
+    (48, 64, 40, 2, "noise", False),       # wide latent space: 2 lanes per row in the dense kernels
+])
+def test_guard_training_step_matches_guarded_autograd(D, K, B, S, kind, hot):
+    import spmf_b200
+    from oracle.spmf_oracle import draw_noise
+    dev = torch.device("cuda:0")
+    x = make_counts(B, D, seed=4, kind=kind)
+    N = 10 * B
+    oracle = make_oracle(D, K, N, x)
+    d0 = 0 if kind == "sparse" else D // 3          # a populated column (column 0 is forced non-empty)
+    assert (x[:, d0] > 0).sum() > 0
+    params = _kill_column(perturbed_params(oracle, 0.3, seed=1), d0)
+    noise = draw_noise(oracle, params, S, seed=2)
+    leaves = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    loss, logq, parts, nbad = _guarded_loss_safe(oracle, leaves, noise, x)
+    assert nbad == S * int((x[:, d0] > 0).sum())
+    names = oracle.param_names()
+    ref_grads = dict(zip(names, torch.autograd.grad(loss, [leaves[n] for n in names])))
+    assert all(bool(torch.isfinite(g).all()) for g in ref_grads.values())
+    # the oracle proper agrees on the VALUE (its gradient is NaN here, like the reference's)
+    _, _, oparts = oracle.loss_parts(params, noise, {'counts': torch.tensor(x, dtype=torch.float64)})
+    np.testing.assert_allclose(oparts['x'].numpy(), parts['x'].detach().numpy(), rtol=1e-12)
+
+    model = spmf_b200.PoissonFactorization(latent_dim=K, feature_dim=D, u_tau_scale=1.0 / np.sqrt(N * D), device=dev)
+    model.compute_scales(lambda: [{'counts': x}])
+    eng = model._engine_for(S)
+    assert (eng.hot_cols > 0 and eng.hybrid_ok) == hot
+    _load(eng, params)
+    eng.set_noise_from(noise)
+    batch = spmf_b200.as_device_batch(x, dev)
+    p = eng.loss_and_grad(batch, fresh_noise=False)
+    torch.cuda.synchronize()
+    got_loss = float(eng.loss_value(p).item())
+    ref_loss = float(loss.detach())
+    assert abs(got_loss - ref_loss) <= TOL * abs(ref_loss), (got_loss, ref_loss)
+    pd = eng.parts_dict()
+    for name in ('x', 'z'):
+        ref = parts[name].detach().numpy()
+        assert np.abs(pd[name].numpy() - ref).max() <= TOL * np.abs(ref).max(), (name, pd[name].numpy(), ref)
+    grads = eng.layout.views(eng.grads)
+    for k, g in ref_grads.items():
+        tol = TOL if k.split('/')[0] in ('v', 'w', 'u', 's') else TOL_IG
+        e = rel_err(grads[k].cpu().numpy(), g.numpy())
+        assert e <= tol, (k, e)
+    # the guard re-armed itself: a clean step afterwards takes the fast path and matches the oracle
+    clean = perturbed_params(oracle, 0.3, seed=1)
+    _load(eng, clean)
+    p = eng.loss_and_grad(batch, fresh_noise=False)
+    ref_loss2, ref_grads2, _ = oracle.loss_and_grads(clean, noise, {'counts': torch.tensor(x, dtype=torch.float64)})
+    assert abs(float(eng.loss_value(p).item()) - ref_loss2) <= TOL * abs(ref_loss2)
+    assert rel_err(eng.layout.views(eng.grads)['u/loc'].cpu().numpy(), ref_grads2['u/loc'].numpy()) <= TOL
+
+
+def test_guard_value_through_the_energy_api():
+    """unormalized_log_prob_parts (poisson.py:582-621) with non-finite entries: all 14 parts vs the oracle."""
+    import spmf_b200
+    from oracle.spmf_oracle import draw_noise
+    dev = torch.device("cuda:0")
+    D, K, B, S = 50, 8, 70, 3
+    x = make_counts(B, D, seed=9)
+    N = 10 * B
+    oracle = make_oracle(D, K, N, x)
+    params = _kill_column(perturbed_params(oracle, 0.3, seed=3), 7)
+    noise = draw_noise(oracle, params, S, seed=5)
+    theta, _ = oracle.sample(params, noise)
+    ref = oracle.unormalized_log_prob_parts({'counts': torch.tensor(x, dtype=torch.float64)}, **theta)
+    model = spmf_b200.PoissonFactorization(latent_dim=K, feature_dim=D, u_tau_scale=1.0 / np.sqrt(N * D), device=dev)
+    model.compute_scales(lambda: [{'counts': x}])
+    got = model.unormalized_log_prob_parts({'counts': x}, **{k: v.to(dev) for k, v in theta.items()})
+    assert set(got) == set(ref)
+    for k in ref:
+        r = ref[k].detach().numpy()
+        assert np.abs(got[k].cpu().numpy() - r).max() <= TOL * max(np.abs(r).max(), 1.0), (k, got[k], r)
+    flag, nbad, min_val = model._engine_for(S).guard_report()
+    assert flag & 1 and nbad == S * int((x[:, 7] > 0).sum()) and min_val < -10.0
+    # with exact_guard=False the non-finite entries are dropped and counted (round-1 behaviour)
+    m2 = spmf_b200.PoissonFactorization(latent_dim=K, feature_dim=D, u_tau_scale=1.0 / np.sqrt(N * D), device=dev,
+                                        exact_guard=False)
+    m2.compute_scales(lambda: [{'counts': x}])
+    g2 = m2.unormalized_log_prob_parts({'counts': x}, **{k: v.to(dev) for k, v in theta.items()})
+    assert bool(torch.isfinite(g2['x']).all()) and float((g2['x'].cpu() - ref['x']).abs().max()) > 1.0
+
+
+# ------------------------------------------------------------------------------------------------
+# log_transform=True (poisson.py:41-42, 52-53)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("D,K,B,S,kind", [
+    (64, 8, 96, 4, "noise"),
+    (100, 2, 130, 4, "noise"),        # C1-shaped, K=2
+    (90, 16, 70, 2, "linear"),
+    (40, 64, 33, 1, "sparse"),        # wide latent space
+])
+def test_log_transform_step_matches_oracle(D, K, B, S, kind):
+    import spmf_b200
+    from oracle.spmf_oracle import draw_noise
+    dev = torch.device("cuda:0")
+    x = make_counts(B, D, seed=6, kind=kind)
+    N = 10 * B
+    oracle = make_oracle(D, K, N, x, log_transform=True)
+    params = perturbed_params(oracle, 0.3, seed=2)
+    noise = draw_noise(oracle, params, S, seed=3)
+    data = {'counts': torch.tensor(x, dtype=torch.float64)}
+    ref_loss, ref_grads, ref_parts = oracle.loss_and_grads(params, noise, data)
+    model = spmf_b200.PoissonFactorization(latent_dim=K, feature_dim=D, u_tau_scale=1.0 / np.sqrt(N * D),
+                                           log_transform=True, device=dev)
+    model.compute_scales(lambda: [{'counts': x}])
+    assert rel_err(model.eta_i.numpy(), oracle.eta_i.numpy()) < 1e-12
+    eng = model._engine_for(S)
+    assert eng.link == 1 and not (eng.hot_cols > 0 and eng.hybrid_ok)
+    _load(eng, params)
+    eng.set_noise_from(noise)
+    batch = spmf_b200.as_device_batch(x, dev)
+    p = eng.loss_and_grad(batch, fresh_noise=False)
+    torch.cuda.synchronize()
+    loss = float(eng.loss_value(p).item())
+    assert abs(loss - ref_loss) <= TOL * abs(ref_loss), (loss, ref_loss)
+    pd = eng.parts_dict()
+    for name in ref_parts:
+        ref = ref_parts[name].numpy()
+        assert np.abs(pd[name].numpy() - ref).max() <= TOL * max(np.abs(ref).max(), 1.0), (name, pd[name].numpy(), ref)
+    grads = eng.layout.views(eng.grads)
+    for k, g in ref_grads.items():
+        tol = TOL if k.split('/')[0] in ('v', 'w', 'u', 's') else TOL_IG
+        e = rel_err(grads[k].cpu().numpy(), g.numpy())
+        assert e <= tol, (k, e)
+    # encoder / energy / likelihood surface with the log link
+    th = model.surrogate_distribution.sample(2, seed=4)
+    thc = {k: v.cpu().double() for k, v in th.items()}
+    z = model.encode(x, th['u'], th['s']).cpu().double().numpy()
+    assert rel_err(z, oracle.encode(data['counts'], thc['u'], thc['s']).numpy()) < 1e-5
+    got = model.unormalized_log_prob_parts({'counts': x}, **th)
+    ref = oracle.unormalized_log_prob_parts(data, **thc)
+    for k in ref:
+        r = ref[k].numpy()
+        assert np.abs(got[k].cpu().numpy() - r).max() <= TOL * max(np.abs(r).max(), 1.0), (k,)
+    llc = model.log_likelihood_components(data={'counts': x}, **{k: th[k] for k in ('s', 'u', 'v', 'w')})
+    ollc = oracle.log_likelihood_components(data=data, **{k: thc[k] for k in ('s', 'u', 'v', 'w')})
+    assert rel_err(llc['rate'].cpu().double().numpy(), ollc['rate'].numpy()) < 1e-4
+
+
+def test_log_transform_fit_decreases_loss_and_waic_runs():
+    import spmf_b200
+    from spmf_b200.data import synth_linear_dense
+    dev = torch.device("cuda:0")
+    x = synth_linear_dense(512, 60, seed=1)
+    x[0, :] = x[0, :].clip(min=1)
+    model = spmf_b200.PoissonFactorization(latent_dim=4, feature_dim=60, u_tau_scale=1.0 / np.sqrt(512 * 60),
+                                           log_transform=True, device=dev, seed=3)
+    factory = lambda: [{'counts': x[i:i + 128]} for i in range(0, 512, 128)]
+    model.compute_scales(factory)
+    losses = model.fit(factory, num_steps=30, learning_rate=0.05, sample_size=4, verbose=False, rel_tol=None)
+    assert np.isfinite(losses).all() and losses[-1] < losses[0]
+    w = model.waic(factory, sample_size=8)
+    assert np.isfinite(w['waic']) and w['pwaic'] >= 0
