@@ -321,16 +321,15 @@ __device__ void phase_rows(const DenseBatch& b, const DenseGeom& g, const float*
     }
     return;
   }
+  float z2 = 0.f;
+#pragma unroll
+  for (int j = 0; j < KC; ++j) z2 = fmaf(zr[j], zr[j], z2);
+  z2 = lanes_sum(z2, g.NKQ);          // (full-warp shuffle: before any lane leaves)
   if (!live) return;
   const float r = b.scale_rows ? b.rowsum[row] * b.inv_xi : 1.f;
-  float z2 = 0.f;
   float* dq = dzr + ((size_t)q * b.nrows + row) * g.REC;
 #pragma unroll
-  for (int j = 0; j < KC; ++j) {
-    z2 = fmaf(zr[j], zr[j], z2);
-    dq[rec_pos(g.KP, g.SV, sv, kq * KC + j)] = r * (dz[j] - zr[j]);
-  }
-  z2 = lanes_sum(z2, g.NKQ);
+  for (int j = 0; j < KC; ++j) dq[rec_pos(g.KP, g.SV, sv, kq * KC + j)] = r * (dz[j] - zr[j]);
   if (kq == 0) {
     float* ra = rowacc + ((size_t)q * b.nrows + row) * 4 * g.SV;
     // Poisson: sum over the finite entries of -lgamma(x+1) = -(row total) + (the bad entries' share)

@@ -96,7 +96,8 @@ class _PriorDistribution:
         f64 = dict(device=m.device, dtype=torch.float64)
 
         def half_normal(scale, shape):
-            return (torch.randn(*shp, *shape, generator=gen, **f64) * scale).abs()
+            shape = tuple(scale.shape) if torch.is_tensor(scale) else shp + tuple(shape)
+            return (torch.randn(*shape, generator=gen, **f64) * scale).abs()
 
         def inv_gamma(conc, scale, shape):            # 1 / Gamma(conc, rate=scale)
             g = torch._standard_gamma(torch.full(shp + shape, conc, **f64), generator=gen)
@@ -701,7 +702,8 @@ class PoissonFactorization:
                           u_tau_scale=self.u_tau_scale, s_tau_scale=self.s_tau_scale,
                           symmetry_breaking_decay=self.symmetry_breaking_decay,
                           scale_columns=self.scale_columns, scale_rows=self.scale_rows,
-                          log_transform=self.log_transform, count_key=self.count_key),
+                          log_transform=self.log_transform, count_key=self.count_key, seed=self.seed,
+                          entropy_weight=self.entropy_weight, prior_weight=self.prior_weight),
         }
 
     def save(self, filename):

@@ -37,8 +37,8 @@ def _kill_column(params, d0):
 
 def _guarded_loss_safe(oracle, params, noise, x):
     """mean_s[log q - energy] with the guard of poisson.py:606-616, autograd-safe: identical to
-    OraclePoissonFactorization.loss except that the rate of a non-finite entry is detached to 1 before
-    log(), so that its (zero-weight) branch does not inject 0 * inf = NaN into the gradient."""
+    OraclePoissonFactorization.loss except that log(rate) is only formed where it is used (finite
+    entries with x > 0), so that the zero-weight branches do not inject 0 * inf = NaN into the gradient."""
     from oracle.spmf_oracle import halfnormal_log_prob
     theta, logq = oracle.sample(params, noise)
     parts = oracle.prior_log_prob_parts(theta)
@@ -47,7 +47,8 @@ def _guarded_loss_safe(oracle, params, noise, x):
     rate = oracle.decoder_function(torch.matmul(z, theta['v'])) + oracle.intercept_matrix(theta['w'], theta['s'])
     bad = ~torch.isfinite(torch.where(xt == 0, torch.zeros_like(rate), xt * torch.log(rate)) - rate)
     rs = torch.where(bad, torch.ones_like(rate), rate)
-    ll = torch.where(xt == 0, torch.zeros_like(rs), xt * torch.log(rs)) - torch.lgamma(xt + 1.0) - rs
+    rlog = torch.where(bad | (xt == 0), torch.ones_like(rate), rate)     # log() only where it is used
+    ll = torch.where(xt == 0, torch.zeros_like(rs), xt * torch.log(rlog)) - torch.lgamma(xt + 1.0) - rs
     min_val = torch.where(bad, torch.zeros_like(ll), ll).min() - 10.0
     ll = torch.where(bad, torch.ones_like(ll) * min_val, ll)
     parts['x'] = ll.sum((-1, -2))
