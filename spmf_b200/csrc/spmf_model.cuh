@@ -65,6 +65,27 @@ struct Hyper {
   float batch_rows;  // rows in this rank's minibatch (closed-form -B term of dphi)
 };
 
+// ---------------- Adam [EXT L4: tf.optimizers.Adam in bayesianquilts' loop] ----------------
+// Applied by whichever kernel FINISHES a gradient (the backward kernels below), so that the step needs no
+// separate pass over the 24 tensors: m, v = first / second moments; bc1, bc2 = 1 - beta^t; a non-finite
+// gradient is dropped, `clip` > 0 clips the gradient by value.  lr <= 0: off.
+struct AdamCfg {
+  float lr, b1, b2, eps, bc1, bc2, clip, grad_scale;
+  float* p;     // parameters (same flat layout as the gradients)
+  float* m;
+  float* v;
+};
+SPMF_HD void adam_apply(const AdamCfg& a, long long i, float g) {
+  g *= a.grad_scale;
+  if (!(fabsf(g) <= 3.402823466e38f)) g = 0.f;
+  if (a.clip > 0.f) g = fminf(fmaxf(g, -a.clip), a.clip);
+  const float mi = a.b1 * a.m[i] + (1.f - a.b1) * g;
+  const float vi = a.b2 * a.v[i] + (1.f - a.b2) * g * g;
+  a.m[i] = mi;
+  a.v[i] = vi;
+  a.p[i] -= a.lr * (mi / a.bc1) / (sqrtf(vi / a.bc2) + a.eps);
+}
+
 // ---------------- Normal-based factor:  y = softplus(loc + softplus(rho) * eps) ----------------
 struct NParam { float loc, sig, logsig, acc_dt, acc_dte; };
 struct NDraw { float t, y, sg, oms, lsg; };   // pre-softplus t, softplus, sigmoid, 1-sigmoid, log sigmoid

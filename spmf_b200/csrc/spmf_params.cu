@@ -121,6 +121,9 @@ gamma_kernel(Layout L, const float* __restrict__ P, float* __restrict__ N, float
 }
 
 // ------------------------------------------------------------------ draw -> operands
+// Only the four Normal-based variables enter the operands (u, v per (d,k); w, s per feature), so this
+// kernel initialises just those -- no lgamma / digamma of the InverseGamma factors (that was 80 % of
+// its instructions) -- and needs softplus(t) alone, not its derivatives.
 template <int KK>
 __global__ void __launch_bounds__(128)
 draw_operands_kernel(Layout L, const float* __restrict__ P, const float* __restrict__ N,
@@ -130,25 +133,46 @@ draw_operands_kernel(Layout L, const float* __restrict__ P, const float* __restr
   const int d = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (d >= L.D) return;
   const int dr = rank ? rank[d] : d;      // table row of feature d (hot-column ordering)
-  LaneState<KK> st;
-  FeatState f;
-  lane_init<KK>(st, L, P, d, lane);
-  feat_init(f, L, P, d);
+  const long long D = L.D, DK = (long long)L.D * L.K;
+  float ul[KK], us[KK], vl[KK], vs[KK];
+#pragma unroll
+  for (int i = 0; i < KK; ++i) {
+    const int k = lane + 32 * i;
+    ul[i] = us[i] = vl[i] = vs[i] = 0.f;
+    if (k < L.K) {
+      const long long e = (long long)d * L.K + k;
+      ul[i] = P[L.toff[U_LOC] + e]; us[i] = softplusf(P[L.toff[U_RHO] + e]);
+      vl[i] = P[L.toff[V_LOC] + e]; vs[i] = softplusf(P[L.toff[V_RHO] + e]);
+    }
+  }
+  const float wl = P[L.toff[W_LOC] + d], wsg = softplusf(P[L.toff[W_RHO] + d]);
+  const float s0l = P[L.toff[S_LOC] + d], s0s = softplusf(P[L.toff[S_RHO] + d]);
+  const float s1l = P[L.toff[S_LOC] + D + d], s1s = softplusf(P[L.toff[S_RHO] + D + d]);
+  const float eta_dec = eta[d], ieta_enc = 1.f / eta[D + d];
   for (int s = 0; s < L.S; ++s) {
     const int q = s / SV, sv = s - q * SV;
-    FeatDraw fd = feat_draw(f, L, N, d, s);
+    const float y0 = softplus4(fmaf(s0s, N[L.noff[VAR_S] + (long long)s * 2 * D + d], s0l)).y;
+    const float y1 = softplus4(fmaf(s1s, N[L.noff[VAR_S] + (long long)s * 2 * D + D + d], s1l)).y;
+    const float inv = 1.f / (y0 + y1);
+    const float a_d = y0 * inv, b_d = y1 * inv;                 // poisson.py:661-663, 694-697
 #pragma unroll
     for (int i = 0; i < KK; ++i) {
-      int k = lane + 32 * i;
+      const int k = lane + 32 * i;
       if (k < KP) {
         float ap = 0.f, ev = 0.f;
-        if (k < L.K) lane_operands<KK>(st, L, N, eta, d, lane, i, s, fd.a, &ap, &ev, nullptr, nullptr);
-        long long idx = ((long long)q * L.D + dr) * SV * KP + rec_pos(KP, SV, sv, k);
+        if (k < L.K) {
+          const long long e = (long long)s * DK + (long long)d * L.K + k;
+          ap = a_d * softplus4(fmaf(us[i], N[L.noff[VAR_U] + e], ul[i])).y * ieta_enc;   // A' (poisson.py:665, 43)
+          ev = eta_dec * softplus4(fmaf(vs[i], N[L.noff[VAR_V] + e], vl[i])).y;          // eta v (poisson.py:54)
+        }
+        const long long idx = ((long long)q * D + dr) * SV * KP + rec_pos(KP, SV, sv, k);
         Ap[idx] = ap;
         EV[idx] = ev;
       }
     }
-    if (lane == 0) PH[((long long)q * L.D + dr) * SV + sv] = eta[d] * fd.b * fd.w.y;  // poisson.py:701
+    if (lane == 0)
+      PH[((long long)q * D + dr) * SV + sv] =
+          eta_dec * b_d * softplus4(fmaf(wsg, N[L.noff[VAR_W] + (long long)s * D + d], wl)).y;   // poisson.py:701
   }
 }
 
@@ -192,7 +216,8 @@ backward_dk_kernel(Layout L, Hyper h, const float* __restrict__ P, const float* 
                    const float* __restrict__ GAp, const float* __restrict__ GEVnz,
                    const double* __restrict__ zcolsum, float* __restrict__ grads,
                    float* __restrict__ scr_utau, float* __restrict__ scr_parts,
-                   float* __restrict__ scr_da, float* __restrict__ fac, const int* __restrict__ gflag) {
+                   float* __restrict__ scr_da, float* __restrict__ fac, const int* __restrict__ gflag,
+                   AdamCfg adam, int adam_data) {
   const int lane = threadIdx.x & 31;
   const int d = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (d >= L.D) return;
@@ -261,6 +286,17 @@ backward_dk_kernel(Layout L, Hyper h, const float* __restrict__ P, const float* 
       nparam_finish(st.v[i], P[L.toff[V_RHO] + e], invS, wer, &grads[L.toff[V_LOC] + e], &grads[L.toff[V_RHO] + e]);
       gparam_finish(st.ue[i], P[L.toff[UETA_C] + e], P[L.toff[UETA_B] + e], invS, &grads[L.toff[UETA_C] + e], &grads[L.toff[UETA_B] + e]);
       gparam_finish(st.ua[i], P[L.toff[UETAA_C] + e], P[L.toff[UETAA_B] + e], invS, &grads[L.toff[UETAA_C] + e], &grads[L.toff[UETAA_B] + e]);
+      if (adam.lr > 0.f) {
+        // u_eta, u_eta_a see prior / entropy terms only: their gradients are final here
+        const int ig[4] = {UETA_C, UETA_B, UETAA_C, UETAA_B};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) adam_apply(adam, L.toff[ig[j]] + e, grads[L.toff[ig[j]] + e]);
+        if (!PRE && adam_data) {                   // one-pass backward: u, v are final as well
+          const int dt[4] = {U_LOC, U_RHO, V_LOC, V_RHO};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) adam_apply(adam, L.toff[dt[j]] + e, grads[L.toff[dt[j]] + e]);
+        }
+      }
     }
   }
 }
@@ -274,7 +310,8 @@ backward_dk_post_kernel(Layout L, Hyper h, const float* __restrict__ P, const fl
                         const float* __restrict__ eta, const int* __restrict__ rank, int SV, int KP,
                         const float* __restrict__ GAp, const float* __restrict__ GEVnz,
                         const float* __restrict__ Gphinz, const double* __restrict__ zcolsum,
-                        const float* __restrict__ fac, float* __restrict__ grads, const int* __restrict__ gflag) {
+                        const float* __restrict__ fac, float* __restrict__ grads, const int* __restrict__ gflag,
+                        AdamCfg adam) {
   const int lane = threadIdx.x & 31;
   const int d = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (d >= L.D) return;
@@ -344,6 +381,12 @@ backward_dk_post_kernel(Layout L, Hyper h, const float* __restrict__ P, const fl
       grads[L.toff[S_RHO] + d] += a0e * invS * sigmoidf(P[L.toff[S_RHO] + d]);
       grads[L.toff[S_LOC] + D + d] += a1 * invS;
       grads[L.toff[S_RHO] + D + d] += a1e * invS * sigmoidf(P[L.toff[S_RHO] + D + d]);
+      if (adam.lr > 0.f) {                          // w, s of this feature are final: optimiser step in place
+        const long long ix[6] = {L.toff[W_LOC] + d, L.toff[W_RHO] + d, L.toff[S_LOC] + d, L.toff[S_RHO] + d,
+                                 L.toff[S_LOC] + D + d, L.toff[S_RHO] + D + d};
+#pragma unroll
+        for (int j = 0; j < 6; ++j) adam_apply(adam, ix[j], grads[ix[j]]);
+      }
     }
   }
 #pragma unroll
@@ -355,6 +398,11 @@ backward_dk_post_kernel(Layout L, Hyper h, const float* __restrict__ P, const fl
       grads[L.toff[U_RHO] + e] += aue[i] * invS * sigmoidf(P[L.toff[U_RHO] + e]);
       grads[L.toff[V_LOC] + e] += av[i] * invS;
       grads[L.toff[V_RHO] + e] += ave[i] * invS * sigmoidf(P[L.toff[V_RHO] + e]);
+      if (adam.lr > 0.f) {
+        const int dt[4] = {U_LOC, U_RHO, V_LOC, V_RHO};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) adam_apply(adam, L.toff[dt[j]] + e, grads[L.toff[dt[j]] + e]);
+      }
     }
   }
 }
@@ -372,7 +420,7 @@ backward_feat_kernel(Layout L, Hyper h, const float* __restrict__ P, const float
                      const int* __restrict__ rank, int SV,
                      const float* __restrict__ Gphinz, const float* __restrict__ scr_da,
                      float* __restrict__ grads, float* __restrict__ scr_parts, int pre,
-                     const int* __restrict__ gflag) {
+                     const int* __restrict__ gflag, AdamCfg adam, int adam_data) {
   if (!pre && gflag && *gflag) h.batch_rows = 0.f;  // dense data term: Gphi carries no closed-form -B
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int dreal = t / SV, sg = t - dreal * SV;
@@ -413,13 +461,26 @@ backward_feat_kernel(Layout L, Hyper h, const float* __restrict__ P, const float
   gparam_finish(f.sea0, P[L.toff[SETAA_C] + d], P[L.toff[SETAA_B] + d], invS, &grads[L.toff[SETAA_C] + d], &grads[L.toff[SETAA_B] + d]);
   gparam_finish(f.sea1, P[L.toff[SETAA_C] + D + d], P[L.toff[SETAA_B] + D + d], invS, &grads[L.toff[SETAA_C] + D + d], &grads[L.toff[SETAA_B] + D + d]);
   gparam_finish(f.sta, P[L.toff[STAUA_C] + d], P[L.toff[STAUA_B] + d], invS, &grads[L.toff[STAUA_C] + d], &grads[L.toff[STAUA_B] + d]);
+  if (adam.lr > 0.f) {
+    const long long ig[12] = {L.toff[SETA_C] + d, L.toff[SETA_B] + d, L.toff[SETA_C] + D + d, L.toff[SETA_B] + D + d,
+                              L.toff[STAU_C] + d, L.toff[STAU_B] + d, L.toff[SETAA_C] + d, L.toff[SETAA_B] + d,
+                              L.toff[SETAA_C] + D + d, L.toff[SETAA_B] + D + d, L.toff[STAUA_C] + d, L.toff[STAUA_B] + d};
+#pragma unroll
+    for (int j = 0; j < 12; ++j) adam_apply(adam, ig[j], grads[ig[j]]);
+    if (!pre && adam_data) {
+      const long long dt[6] = {L.toff[W_LOC] + d, L.toff[W_RHO] + d, L.toff[S_LOC] + d, L.toff[S_RHO] + d,
+                               L.toff[S_LOC] + D + d, L.toff[S_RHO] + D + d};
+#pragma unroll
+      for (int j = 0; j < 6; ++j) adam_apply(adam, dt[j], grads[dt[j]]);
+    }
+  }
 }
 
 // ------------------------------------------------------------------ backward (per latent k)
 __global__ void backward_lat_kernel(Layout L, Hyper h, const float* __restrict__ P,
                                     const float* __restrict__ N, const float* __restrict__ G,
                                     const double* __restrict__ dutau,
-                                    float* __restrict__ grads, float* __restrict__ scr_lat) {
+                                    float* __restrict__ grads, float* __restrict__ scr_lat, AdamCfg adam) {
   int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= L.K) return;
   LatState t;
@@ -434,6 +495,11 @@ __global__ void backward_lat_kernel(Layout L, Hyper h, const float* __restrict__
   const float invS = 1.f / (float)L.S;
   gparam_finish(t.ut, P[L.toff[UTAU_C] + k], P[L.toff[UTAU_B] + k], invS, &grads[L.toff[UTAU_C] + k], &grads[L.toff[UTAU_B] + k]);
   gparam_finish(t.uta, P[L.toff[UTAUA_C] + k], P[L.toff[UTAUA_B] + k], invS, &grads[L.toff[UTAUA_C] + k], &grads[L.toff[UTAUA_B] + k]);
+  if (adam.lr > 0.f) {
+    const long long ig[4] = {L.toff[UTAU_C] + k, L.toff[UTAU_B] + k, L.toff[UTAUA_C] + k, L.toff[UTAUA_B] + k};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) adam_apply(adam, ig[j], grads[ig[j]]);
+  }
 }
 
 // ------------------------------------------------------------------ deterministic reductions
@@ -536,6 +602,37 @@ __global__ void unpack_parts_kernel(int S, double w_entropy, double w_prior, flo
   }
 }
 
+// blocks [0, n/256): Adam over the all-reduced gradient block; the extra last block: unpack_parts_kernel's job
+__global__ void unpack_adam_kernel(int S, double w_entropy, double w_prior, float* __restrict__ comm, int slack,
+                                   double* __restrict__ parts, double* __restrict__ loss_out,
+                                   const float* __restrict__ g, long long n, AdamCfg adam) {
+  if (blockIdx.x + 1 < gridDim.x) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && adam.lr > 0.f) adam_apply(adam, i, g[i]);
+    return;
+  }
+  __shared__ double sl[64];
+  const int s = threadIdx.x;
+  double l = 0.0;
+  if (s < S) {
+    double* o = parts + (long long)s * NUM_PARTS;
+    o[P_Z] = (double)comm[4 * s + 0] + (double)comm[4 * s + 1];
+    o[P_X] = (double)comm[4 * s + 2] + (double)comm[4 * s + 3];
+    double prior = 0.0;
+    for (int p = 0; p < P_LOGQ; ++p) prior += o[p];
+    l = w_entropy * o[P_LOGQ] - w_prior * prior - o[P_Z] - o[P_X];
+    o[15] = l;
+  }
+  if (s < 64) sl[s] = l;
+  __syncthreads();
+  for (int i = threadIdx.x; i < slack; i += blockDim.x) comm[i] = 0.f;
+  if (s == 0) {
+    double t = 0.0;
+    for (int i = 0; i < S && i < 64; ++i) t += sl[i];
+    *loss_out = t / (double)S;
+  }
+}
+
 // ------------------------------------------------------------------ Adam  [EXT L4]
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, long long n, float lr, float b1, float b2, float eps,
@@ -572,6 +669,18 @@ static Hyper make_hyper(float u_tau_scale, float s_tau_scale, float decay, float
   h.rep_scale = 1.f / (float)world;
   h.batch_rows = batch_rows;
   return h;
+}
+
+static AdamCfg make_adam(const spmf_adam_args* a) {
+  AdamCfg c{};
+  if (!a || !(a->lr > 0.f) || !a->params || !a->m || !a->v || a->step <= 0) return c;     // lr = 0: off
+  c.lr = a->lr; c.b1 = a->beta1; c.b2 = a->beta2; c.eps = a->eps;
+  c.bc1 = 1.f - powf(a->beta1, (float)a->step);
+  c.bc2 = 1.f - powf(a->beta2, (float)a->step);
+  c.clip = a->clip_value;
+  c.grad_scale = a->grad_scale > 0.f ? a->grad_scale : 1.f;
+  c.p = a->params; c.m = a->m; c.v = a->v;
+  return c;
 }
 
 static int nsplit_for(long long n) {
@@ -772,10 +881,11 @@ int spmf_backward_params(const float* params, const float* noise, const float* d
                          const double* zcolsum, const double* datasums, const double* phisum,
                          float batch_rows, float u_tau_scale, float s_tau_scale,
                          float decay, float w_entropy, float w_prior, int world_size, float* grads,
-                         double* parts, float* scr_f, double* scr_d, void* gs, void* stream) {
+                         double* parts, float* scr_f, double* scr_d, void* gs, const spmf_adam_args* adam,
+                         void* stream) {
   return spmf_backward_params_ranked(params, noise, dgda, eta, nullptr, D, K, S, GAp, GEVnz, Gphinz, zcolsum,
                                      datasums, phisum, batch_rows, u_tau_scale, s_tau_scale, decay, w_entropy,
-                                     w_prior, world_size, grads, parts, scr_f, scr_d, gs, stream);
+                                     w_prior, world_size, grads, parts, scr_f, scr_d, gs, adam, stream);
 }
 
 int spmf_backward_params_ranked(const float* params, const float* noise, const float* dgda, const float* eta,
@@ -783,7 +893,10 @@ int spmf_backward_params_ranked(const float* params, const float* noise, const f
                                 const float* Gphinz, const double* zcolsum, const double* datasums,
                                 const double* phisum, float batch_rows, float u_tau_scale, float s_tau_scale,
                                 float decay, float w_entropy, float w_prior, int world_size, float* grads,
-                                double* parts, float* scr_f, double* scr_d, void* gs, void* stream) {
+                                double* parts, float* scr_f, double* scr_d, void* gs,
+                                const spmf_adam_args* adam, void* stream) {
+  const AdamCfg ad = make_adam(adam);
+  const int ad_data = adam ? !adam->defer_data : 0;
   if (!params || !noise || !dgda || !eta || !GAp || !GEVnz || !Gphinz || !zcolsum || !datasums ||
       !phisum || !grads || !parts || !scr_f || !scr_d)
     return SPMF_ERR_BAD_ARG;
@@ -803,14 +916,14 @@ int spmf_backward_params_ranked(const float* params, const float* noise, const f
   double* rscr = latparts + (long long)S * NUM_PARTS;
   float* scr_da = scr_lat + (long long)K * S * NUM_PARTS;
   dim3 grid((D + 3) / 4);
-  if (KP <= 32) backward_dk_kernel<1, false><<<grid, 128, 0, st>>>(L, h, params, noise, dgda, eta, rank, SV, KP, GAp, GEVnz, zcolsum, grads, scr_utau, scr_parts, scr_da, nullptr, (const int*)gs);
-  else if (KP <= 64) backward_dk_kernel<2, false><<<grid, 128, 0, st>>>(L, h, params, noise, dgda, eta, rank, SV, KP, GAp, GEVnz, zcolsum, grads, scr_utau, scr_parts, scr_da, nullptr, (const int*)gs);
-  else backward_dk_kernel<4, false><<<grid, 128, 0, st>>>(L, h, params, noise, dgda, eta, rank, SV, KP, GAp, GEVnz, zcolsum, grads, scr_utau, scr_parts, scr_da, nullptr, (const int*)gs);
-  backward_feat_kernel<<<(int)(((long long)D * SV + 127) / 128), 128, 0, st>>>(L, h, params, noise, dgda, eta, rank, SV, Gphinz, scr_da, grads, scr_parts, 0, (const int*)gs);
+  if (KP <= 32) backward_dk_kernel<1, false><<<grid, 128, 0, st>>>(L, h, params, noise, dgda, eta, rank, SV, KP, GAp, GEVnz, zcolsum, grads, scr_utau, scr_parts, scr_da, nullptr, (const int*)gs, ad, ad_data);
+  else if (KP <= 64) backward_dk_kernel<2, false><<<grid, 128, 0, st>>>(L, h, params, noise, dgda, eta, rank, SV, KP, GAp, GEVnz, zcolsum, grads, scr_utau, scr_parts, scr_da, nullptr, (const int*)gs, ad, ad_data);
+  else backward_dk_kernel<4, false><<<grid, 128, 0, st>>>(L, h, params, noise, dgda, eta, rank, SV, KP, GAp, GEVnz, zcolsum, grads, scr_utau, scr_parts, scr_da, nullptr, (const int*)gs, ad, ad_data);
+  backward_feat_kernel<<<(int)(((long long)D * SV + 127) / 128), 128, 0, st>>>(L, h, params, noise, dgda, eta, rank, SV, Gphinz, scr_da, grads, scr_parts, 0, (const int*)gs, ad, ad_data);
   SPMF_CHECK_LAUNCH();
   int rc = reduce_rows_pair(scr_utau, dutau, D, K, S, scr_parts, featparts, D, S * NUM_PARTS, 1, rscr, st);
   if (rc) return rc;
-  backward_lat_kernel<<<(K + 63) / 64, 64, 0, st>>>(L, h, params, noise, dgda, dutau, grads, scr_lat);
+  backward_lat_kernel<<<(K + 63) / 64, 64, 0, st>>>(L, h, params, noise, dgda, dutau, grads, scr_lat, ad);
   SPMF_CHECK_LAUNCH();
   rc = reduce_rows<float>(scr_lat, latparts, rscr, K, S * NUM_PARTS, 1, st);
   if (rc) return rc;
@@ -831,7 +944,9 @@ long long spmf_backward_scratch_floats(int D, int K, int S) {
  * a side stream), spmf_backward_post = the data half + the loss parts.  pre + post == spmf_backward_params. */
 int spmf_backward_pre(const float* params, const float* noise, const float* dgda, const float* eta, int D, int K,
                       int S, float batch_rows, float u_tau_scale, float s_tau_scale, float decay, float w_entropy,
-                      float w_prior, int world_size, float* grads, float* scr_f, double* scr_d, void* stream) {
+                      float w_prior, int world_size, float* grads, float* scr_f, double* scr_d,
+                      const spmf_adam_args* adam, void* stream) {
+  const AdamCfg ad = make_adam(adam);
   if (!params || !noise || !dgda || !eta || !grads || !scr_f || !scr_d) return SPMF_ERR_BAD_ARG;
   if (D <= 0 || K <= 0 || S <= 0 || K > SPMF_MAX_K || world_size <= 0) return SPMF_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
@@ -848,14 +963,14 @@ int spmf_backward_pre(const float* params, const float* noise, const float* dgda
   double* latparts = featparts + (long long)S * NUM_PARTS;
   double* rscr = latparts + (long long)S * NUM_PARTS;
   dim3 grid((D + 3) / 4);
-  if (KP <= 32) backward_dk_kernel<1, true><<<grid, 128, 0, st>>>(L, h, params, noise, dgda, eta, nullptr, SV, KP, nullptr, nullptr, nullptr, grads, scr_utau, scr_parts, scr_da, fac, nullptr);
-  else if (KP <= 64) backward_dk_kernel<2, true><<<grid, 128, 0, st>>>(L, h, params, noise, dgda, eta, nullptr, SV, KP, nullptr, nullptr, nullptr, grads, scr_utau, scr_parts, scr_da, fac, nullptr);
-  else backward_dk_kernel<4, true><<<grid, 128, 0, st>>>(L, h, params, noise, dgda, eta, nullptr, SV, KP, nullptr, nullptr, nullptr, grads, scr_utau, scr_parts, scr_da, fac, nullptr);
-  backward_feat_kernel<<<(int)(((long long)D * SV + 127) / 128), 128, 0, st>>>(L, h, params, noise, dgda, eta, nullptr, SV, nullptr, nullptr, grads, scr_parts, 1, nullptr);
+  if (KP <= 32) backward_dk_kernel<1, true><<<grid, 128, 0, st>>>(L, h, params, noise, dgda, eta, nullptr, SV, KP, nullptr, nullptr, nullptr, grads, scr_utau, scr_parts, scr_da, fac, nullptr, ad, 0);
+  else if (KP <= 64) backward_dk_kernel<2, true><<<grid, 128, 0, st>>>(L, h, params, noise, dgda, eta, nullptr, SV, KP, nullptr, nullptr, nullptr, grads, scr_utau, scr_parts, scr_da, fac, nullptr, ad, 0);
+  else backward_dk_kernel<4, true><<<grid, 128, 0, st>>>(L, h, params, noise, dgda, eta, nullptr, SV, KP, nullptr, nullptr, nullptr, grads, scr_utau, scr_parts, scr_da, fac, nullptr, ad, 0);
+  backward_feat_kernel<<<(int)(((long long)D * SV + 127) / 128), 128, 0, st>>>(L, h, params, noise, dgda, eta, nullptr, SV, nullptr, nullptr, grads, scr_parts, 1, nullptr, ad, 0);
   SPMF_CHECK_LAUNCH();
   int rc = reduce_rows_pair(scr_utau, dutau, D, K, S, scr_parts, featparts, D, S * NUM_PARTS, 1, rscr, st);
   if (rc) return rc;
-  backward_lat_kernel<<<(K + 63) / 64, 64, 0, st>>>(L, h, params, noise, dgda, dutau, grads, scr_lat);
+  backward_lat_kernel<<<(K + 63) / 64, 64, 0, st>>>(L, h, params, noise, dgda, dutau, grads, scr_lat, ad);
   SPMF_CHECK_LAUNCH();
   return reduce_rows<float>(scr_lat, latparts, rscr, K, S * NUM_PARTS, 1, st);
 }
@@ -864,7 +979,10 @@ int spmf_backward_post(const float* params, const float* noise, const float* eta
                        int S, const float* GAp, const float* GEVnz, const float* Gphinz, const double* zcolsum,
                        const double* datasums, const double* phisum, float batch_rows, float u_tau_scale,
                        float s_tau_scale, float decay, float w_entropy, float w_prior, int world_size,
-                       float* grads, double* parts, float* scr_f, const double* scr_d, void* gs, void* stream) {
+                       float* grads, double* parts, float* scr_f, const double* scr_d, void* gs,
+                       const spmf_adam_args* adam, void* stream) {
+  AdamCfg ad = make_adam(adam);
+  if (adam && adam->defer_data) ad.lr = 0.f;       // multi-GPU: v, w, u, s wait for the all-reduce
   if (!params || !noise || !eta || !GAp || !GEVnz || !Gphinz || !zcolsum || !datasums || !phisum || !grads ||
       !parts || !scr_f || !scr_d)
     return SPMF_ERR_BAD_ARG;
@@ -879,9 +997,9 @@ int spmf_backward_post(const float* params, const float* noise, const float* eta
   const double* latparts = featparts + (long long)S * NUM_PARTS;
   dim3 grid((D + 3) / 4);
   if (S > 64) return SPMF_ERR_BAD_ARG;
-  if (KP <= 32) backward_dk_post_kernel<1><<<grid, 128, 0, st>>>(L, h, params, noise, eta, rank, SV, KP, GAp, GEVnz, Gphinz, zcolsum, fac, grads, (const int*)gs);
-  else if (KP <= 64) backward_dk_post_kernel<2><<<grid, 128, 0, st>>>(L, h, params, noise, eta, rank, SV, KP, GAp, GEVnz, Gphinz, zcolsum, fac, grads, (const int*)gs);
-  else backward_dk_post_kernel<4><<<grid, 128, 0, st>>>(L, h, params, noise, eta, rank, SV, KP, GAp, GEVnz, Gphinz, zcolsum, fac, grads, (const int*)gs);
+  if (KP <= 32) backward_dk_post_kernel<1><<<grid, 128, 0, st>>>(L, h, params, noise, eta, rank, SV, KP, GAp, GEVnz, Gphinz, zcolsum, fac, grads, (const int*)gs, ad);
+  else if (KP <= 64) backward_dk_post_kernel<2><<<grid, 128, 0, st>>>(L, h, params, noise, eta, rank, SV, KP, GAp, GEVnz, Gphinz, zcolsum, fac, grads, (const int*)gs, ad);
+  else backward_dk_post_kernel<4><<<grid, 128, 0, st>>>(L, h, params, noise, eta, rank, SV, KP, GAp, GEVnz, Gphinz, zcolsum, fac, grads, (const int*)gs, ad);
   finalize_parts_kernel<<<1, ((S + 31) / 32) * 32, 0, st>>>(S, SV, K, featparts, latparts, datasums, phisum,
                                                            (double)batch_rows, (double)w_entropy, (double)w_prior,
                                                            parts, grads + L.comm_off, (GuardState*)gs);
@@ -901,6 +1019,21 @@ int spmf_adam_step(float* params, const float* grads, float* m, float* v, long l
   if (!params || !grads || !m || !v || n <= 0 || step <= 0) return SPMF_ERR_BAD_ARG;
   float bc1 = 1.f - powf(beta1, (float)step), bc2 = 1.f - powf(beta2, (float)step);
   adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(params, grads, m, v, n, lr, beta1, beta2, eps, bc1, bc2, clip_value, grad_scale);
+  SPMF_CHECK_LAUNCH();
+  return SPMF_OK;
+}
+
+/* Multi-GPU tail of a step in one launch: fold the all-reduced ('z','x') pairs back into parts / the mean
+ * loss (spmf_unpack_parts) and apply Adam to the all-reduced block grads[0, n_data) = v, w, u, s. */
+int spmf_unpack_adam(float* comm_slack, int slack_floats, int S, float w_entropy, float w_prior, double* parts,
+                     double* loss_out, const float* grads, long long n_data, const spmf_adam_args* adam,
+                     void* stream) {
+  if (!comm_slack || !parts || !loss_out || !grads || S <= 0 || S > 64 || slack_floats < 4 * S || n_data <= 0)
+    return SPMF_ERR_BAD_ARG;
+  const AdamCfg ad = make_adam(adam);
+  const unsigned nblk = (unsigned)((n_data + 255) / 256);
+  unpack_adam_kernel<<<nblk + 1, 256, 0, (cudaStream_t)stream>>>(S, (double)w_entropy, (double)w_prior, comm_slack,
+                                                                slack_floats, parts, loss_out, grads, n_data, ad);
   SPMF_CHECK_LAUNCH();
   return SPMF_OK;
 }

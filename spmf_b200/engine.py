@@ -285,7 +285,7 @@ class AdviEngine:
                   _ptr(w.datasums), _ptr(w.phisum), float(batch_rows), self.u_tau_scale,
                   self.s_tau_scale, self.decay, self.entropy_weight, self.prior_weight,
                   self.world_size, _ptr(self.grads), _ptr(w.parts), _ptr(w.scr_f), _ptr(w.scr_d),
-                  _ptr(self.gs), _stream())
+                  _ptr(self.gs), None, _stream())
         self.launches += 9
 
     def _mark(self, name, start):
@@ -380,7 +380,9 @@ class AdviEngine:
             a.rowptr, a.cols, a.vals = _ptr(batch.rowptr), _ptr(batch.cols), _ptr(batch.vals)
             a.colptr, a.crows, a.cvals = _ptr(batch.colptr), _ptr(batch.crows), _ptr(batch.cvals)
             a.rank, a.hot_cols = None, 0
-        do_adam = lr is not None and self.world_size == 1
+        # Adam runs inside the backward kernels; with several ranks the all-reduced block (v, w, u, s) is
+        # stepped after the collective (finish_step) while the 16 replicated tensors are stepped here
+        do_adam = lr is not None
         a.adam_lr = float(lr) if do_adam else 0.0
         a.adam_beta1, a.adam_beta2, a.adam_eps, a.clip_value = beta1, beta2, eps, float(clip_value)
         a.adam_t = self.opt_step + 1
@@ -415,12 +417,13 @@ class AdviEngine:
         # 17 in gather mode with the split backward (16 with the one-pass backward), +5 GEMM-hybrid
         # (2 splits, 2 GEMMs, second column kernel), +7 tile-hybrid (2 splits, 2 GEMMs, EV tiles, tile
         # kernel, row finalisation); +1 Adam
+        self._last_adam = (float(lr), beta1, beta2, eps, float(clip_value)) if do_adam else None
         base = 17 if a.scr_dpre else 16
         if self.link != 0:
             base += 6              # scatter (2), encode, two conditional row passes, zeroing -- minus nothing
         elif xd is not None:
             base += 2              # the two conditional guard launches
-        self.launches += base + (1 if do_adam else 0) + ((7 if self.hot_mode == 2 else 5) if hybrid else 0)
+        self.launches += base + ((7 if self.hot_mode == 2 else 5) if hybrid else 0)
         return w.parts.view(self.S, _abi.NUM_PARTS)
 
     def loss_and_grad(self, batch: DeviceBatch, fresh_noise=True, variant=0):
@@ -432,6 +435,15 @@ class AdviEngine:
         """mean_s [ w_e log q - w_p prior - z - x ]  as a 0-d device tensor."""
         parts = self.ws.parts.view(self.S, _abi.NUM_PARTS) if parts is None else parts
         return parts[:, 15].mean()
+
+    def adam_args(self, n_step=None, defer_data=False):
+        """spmf_adam_args of the optimiser step the last `step(lr=...)` call took (multi-GPU tail)."""
+        lr, b1, b2, eps, clip = self._last_adam
+        a = _abi.AdamArgs()
+        a.lr, a.beta1, a.beta2, a.eps, a.clip_value, a.grad_scale = lr, b1, b2, eps, clip, 1.0
+        a.step, a.defer_data = int(self.opt_step if n_step is None else n_step), int(defer_data)
+        a.params, a.m, a.v = _ptr(self.params), _ptr(self.adam_m), _ptr(self.adam_v)
+        return a
 
     def adam_step(self, lr, beta1=0.9, beta2=0.999, eps=1e-7, clip_value=0.0, grad_scale=1.0):
         self.opt_step += 1

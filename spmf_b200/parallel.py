@@ -43,10 +43,24 @@ def unpack_data_parts(eng, parts):
     return parts
 
 
-def allreduce_step(eng, parts, group=None):
-    """All-reduce gradients + data parts in one collective; returns the global loss (0-d tensor)."""
+def allreduce_step(eng, parts, group=None, adam=False):
+    """All-reduce gradients + data parts in one collective; returns the global loss (0-d tensor).
+    adam=True: the optimiser step of the all-reduced block (v, w, u, s) rides in the same launch as the
+    post-collective bookkeeping (the 16 replicated tensors were stepped inside the backward kernels)."""
     dist.all_reduce(comm_block(eng), op=dist.ReduceOp.SUM, group=group)
     dev = getattr(eng, "device", None)
+    if adam and dev is not None and dev.type == "cuda" and eng.S <= 64:
+        import ctypes as C
+        L = eng.layout
+        if getattr(eng, "_loss_buf", None) is None:
+            eng._loss_buf = torch.zeros(1, dtype=torch.float64, device=eng.device)
+        slack = eng.grads[L.comm_off: L.comm_off + L.comm_slack]
+        a = eng.adam_args()
+        _abi.call("spmf_unpack_adam", slack.data_ptr(), L.comm_slack, eng.S, eng.entropy_weight, eng.prior_weight,
+                  parts.data_ptr(), eng._loss_buf.data_ptr(), eng.grads.data_ptr(), L.comm_off, C.byref(a),
+                  torch.cuda.current_stream().cuda_stream)
+        eng.launches += 1
+        return eng._loss_buf[0]
     if dev is not None and dev.type == "cuda" and eng.S <= 64:
         # one launch instead of a handful of tiny tensor ops on the critical path between the
         # collective and Adam

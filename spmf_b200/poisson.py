@@ -575,10 +575,8 @@ class PoissonFactorization:
         b = as_device_batch(c, self.device)
         if eng.world_size > 1:
             from .parallel import allreduce_step
-            parts = eng.step(b, lr=None)
-            loss = allreduce_step(eng, parts, self.process_group)
-            if learning_rate is not None:
-                eng.adam_step(learning_rate, clip_value=clip_value)
+            parts = eng.step(b, lr=learning_rate, clip_value=clip_value)
+            loss = allreduce_step(eng, parts, self.process_group, adam=learning_rate is not None)
         else:
             parts = eng.step(b, lr=learning_rate, clip_value=clip_value)   # one native call, Adam included
             loss = eng.loss_value(parts)

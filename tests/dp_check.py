@@ -76,8 +76,49 @@ def main():
             e_grad = max(e_grad, np.abs(g1[idx] - g2[idx]).max() / (np.abs(g1[idx]).max() + 1e-300))
         print(f"dp_check world={world}: loss single={l1:.6f} dp={l2:.6f} rel={e_loss:.2e}; worst grad rel={e_grad:.2e}")
         ok = e_loss < 1e-6 and e_grad < 5e-5      # (hybrid bf16-split tensor-core path vs the fp32 gather path)
+    # ---- three optimiser steps: Adam fused into the backward kernels (replicated tensors) and into the
+    #      post-collective launch (all-reduced block) vs the single-GPU step on the whole batch
+    lr = 0.02
+    for _ in range(3):
+        model.elbo_step({'counts': shard.batch(0, hi - lo)}, S, learning_rate=lr, clip_value=2.5)
+    torch.cuda.synchronize()
+    p_dp = eng.params.clone()
+    ref = p_dp.clone()
+    dist.broadcast(ref, src=0)
+    assert torch.equal(ref, p_dp), "replicas diverged after Adam"
+    if rank == 0:
+        single.params.copy_(p_before)
+        single.adam_m.zero_(); single.adam_v.zero_()
+        single.opt_step, single.rng_step = 0, 1
+        for _ in range(3):
+            single.step(full.batch(0, B), lr=lr, clip_value=2.5)
+        torch.cuda.synchronize()
+        upd_ref = (single.params - p_before).double()
+        upd_dp = (p_dp - p_before).double()
+        L = eng.layout
+        mask = torch.ones(L.n_params, dtype=torch.bool, device=dev)
+        mask[L.comm_off:L.comm_off + L.comm_slack] = False        # scalar slack is not a parameter
+        e_adam = float((upd_ref - upd_dp)[mask].abs().max() / upd_ref[mask].abs().max())
+        print(f"dp_check world={world}: 3 Adam steps, worst update rel={e_adam:.2e}")
+        ok = ok and e_adam < 2e-3 and float(upd_ref[mask].abs().max()) > 0.5 * lr
+    # ---- exact guard across ranks: a dead column; the replacement value is the GLOBAL minimum
+    from tests.test_gpu_links import _kill_column
+    from tests.util import make_oracle, perturbed_params
+    from oracle.spmf_oracle import draw_noise
+    oracle = make_oracle(D, K, B, x)
+    oracle.u_tau_scale = model.u_tau_scale
+    prm = _kill_column(perturbed_params(oracle, 0.3, seed=1), 0)
+    nz = draw_noise(oracle, prm, S, seed=2)
+    theta, _ = oracle.sample(prm, nz)
+    refp = oracle.unormalized_log_prob_parts({'counts': torch.tensor(x, dtype=torch.float64)}, **theta)
+    got = model.unormalized_log_prob_parts({'counts': shard.batch(0, hi - lo)}, **{k: v.to(dev) for k, v in theta.items()})
+    e_x = float((got['x'].cpu() - refp['x']).abs().max() / refp['x'].abs().max())
+    e_z = float((got['z'].cpu() - refp['z']).abs().max() / refp['z'].abs().max())
+    if rank == 0:
+        print(f"dp_check world={world}: guarded energy parts over {world} shards: x rel={e_x:.2e} z rel={e_z:.2e}")
+    ok = ok and e_x < 1e-4 and e_z < 1e-4
     flag = torch.tensor([1 if ok else 0], device=dev)
-    dist.broadcast(flag, src=0)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     dist.destroy_process_group()
     if not bool(flag.item()):
         sys.exit(1)
