@@ -234,7 +234,7 @@ def main():
                 torch.cuda.synchronize()
                 p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 p0.record()
-            b.ensure_hot(eng.rank, eng.hot_cols, hot_csc=(eng.hot_mode != 2))   # ranked CSR/CSC + dense bf16 hot block
+            eng.prepare_batch(b)                       # ranked CSR/CSC + dense bf16 hot block
             if bi == 2:
                 p1.record()
                 torch.cuda.synchronize()

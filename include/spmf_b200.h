@@ -91,15 +91,12 @@ int spmf_csc_cols(const int* colptr, const int* rows, const float* vals, int nnz
 int spmf_batch_sums(const float* z, const float* rowacc, int nrows, int K, int S, double* zcolsum,
                     double* datasums, double* scratch, void* stream);
 
-/* Adam fused into the backward [EXT L4: tf.optimizers.Adam + clip in bayesianquilts' loop]: every backward
- * kernel applies the optimiser step to the tensors whose gradient it FINISHES (the 16 InverseGamma-family
- * tensors in the data-independent half, v / w / u / s in the data half), so a training step has no
- * separate pass over the parameters.  NULL or lr <= 0: gradients only.  defer_data != 0 (multi-GPU): v, w,
- * u, s are left to spmf_unpack_adam after the all-reduce. */
+/* Optimiser step arguments [EXT L4: tf.optimizers.Adam + clip in bayesianquilts' loop] of the fused
+ * multi-GPU tail (spmf_unpack_adam). */
 typedef struct spmf_adam_args {
   float lr, beta1, beta2, eps, clip_value, grad_scale;
   int step;          /* 1-based optimiser step (bias correction) */
-  int defer_data;
+  int reserved;
   float *params, *m, *v;
 } spmf_adam_args;
 
@@ -118,7 +115,7 @@ int spmf_backward_params(const float* params, const float* noise, const float* d
                          const double* zcolsum, const double* datasums, const double* phisum,
                          float batch_rows, float u_tau_scale, float s_tau_scale, float decay,
                          float w_entropy, float w_prior, int world_size, float* grads, double* parts,
-                         float* scratch_f, double* scratch_d, void* gs, const spmf_adam_args* adam, void* stream);
+                         float* scratch_f, double* scratch_d, void* gs, void* stream);
 
 /* The same backward in two halves: `pre` = everything that does not depend on the data term (prior +
  * entropy gradients of all 24 tensors, the loss parts) -- it can run on a side stream while the data
@@ -127,14 +124,12 @@ int spmf_backward_params(const float* params, const float* noise, const float* d
  * shared with the reductions of the data term if the two run concurrently. */
 int spmf_backward_pre(const float* params, const float* noise, const float* dgda, const float* eta, int D, int K,
                       int S, float batch_rows, float u_tau_scale, float s_tau_scale, float decay, float w_entropy,
-                      float w_prior, int world_size, float* grads, float* scr_f, double* scr_d,
-                      const spmf_adam_args* adam, void* stream);
+                      float w_prior, int world_size, float* grads, float* scr_f, double* scr_d, void* stream);
 int spmf_backward_post(const float* params, const float* noise, const float* eta, const int* rank, int D, int K,
                        int S, const float* GAp, const float* GEVnz, const float* Gphinz, const double* zcolsum,
                        const double* datasums, const double* phisum, float batch_rows, float u_tau_scale,
                        float s_tau_scale, float decay, float w_entropy, float w_prior, int world_size,
-                       float* grads, double* parts, float* scr_f, const double* scr_d, void* gs,
-                       const spmf_adam_args* adam, void* stream);
+                       float* grads, double* parts, float* scr_f, const double* scr_d, void* gs, void* stream);
 
 /* ---- optimiser [EXT L4: Adam + clip in bayesianquilts' batched_minimize] ---- */
 int spmf_adam_step(float* params, const float* grads, float* m, float* v, long long n, float lr,
@@ -146,7 +141,7 @@ int spmf_sumsq(const float* g, long long n, float* tmp, double* out, double* scr
  * mean loss, zero the slack.  S <= 64. */
 int spmf_unpack_parts(float* comm_slack, int slack_floats, int S, float w_entropy, float w_prior, double* parts,
                       double* loss_out, void* stream);
-/* the same plus Adam over the all-reduced gradient block grads[0, n_data) (v, w, u, s), one launch */
+/* the same plus Adam over grads[0, n_data) (the whole flat buffer), one launch: the multi-GPU tail */
 int spmf_unpack_adam(float* comm_slack, int slack_floats, int S, float w_entropy, float w_prior, double* parts,
                      double* loss_out, const float* grads, long long n_data, const spmf_adam_args* adam,
                      void* stream);
@@ -191,8 +186,7 @@ int spmf_backward_params_ranked(const float* params, const float* noise, const f
                                 const float* Gphinz, const double* zcolsum, const double* datasums,
                                 const double* phisum, float batch_rows, float u_tau_scale, float s_tau_scale,
                                 float decay, float w_entropy, float w_prior, int world_size, float* grads,
-                                double* parts, float* scr_f, double* scr_d, void* gs, const spmf_adam_args* adam,
-                                void* stream);
+                                double* parts, float* scr_f, double* scr_d, void* gs, void* stream);
 /* Operands of the tcgen05 GEMM live in global memory "UMMA-tiled": tile by tile in the byte order the
  * tensor core reads from shared memory (K-major, no swizzle), so that a pipeline stage is two
  * contiguous TMA bulk copies.  A (bf16 counts): tiles [row/128][k/64] of 128 x 64; B3 (three bf16
@@ -313,8 +307,8 @@ typedef struct spmf_step_args {
   const int *colptr, *crows;
   const float* cvals;
   int nrows, nnz;
-  /* optimiser: adam_lr > 0 applies Adam inside the backward kernels (world_size > 1: to the 16 replicated
-   * tensors only -- v, w, u, s follow the all-reduce through spmf_unpack_adam) */
+  /* optimiser: adam_lr > 0 (world_size == 1 only) ends the step with spmf_adam_step; with several ranks
+   * the caller all-reduces the gradient block first and then calls spmf_unpack_adam */
   float adam_lr, adam_beta1, adam_beta2, adam_eps, clip_value;
   int adam_t;
   /* streams / events (cudaStream_t / cudaEvent_t) */

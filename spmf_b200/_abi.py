@@ -56,10 +56,10 @@ _SIGS = {
     "spmf_gamma_grad": (i32, [p, p, i32, i32, i32, p, p]),
     "spmf_gamma_draw_grad": (i32, [p, p, p, i32, i32, i32, u64, u32, p]),
     "spmf_backward_params": (i32, [p, p, p, p, i32, i32, i32, p, p, p, p, p, p, f32, f32, f32, f32, f32,
-                                   f32, i32, p, p, p, p, p, p, p]),
-    "spmf_backward_pre": (i32, [p, p, p, p, i32, i32, i32, f32, f32, f32, f32, f32, f32, i32, p, p, p, p, p]),
+                                   f32, i32, p, p, p, p, p, p]),
+    "spmf_backward_pre": (i32, [p, p, p, p, i32, i32, i32, f32, f32, f32, f32, f32, f32, i32, p, p, p, p]),
     "spmf_backward_post": (i32, [p, p, p, p, i32, i32, i32, p, p, p, p, p, p, f32, f32, f32, f32, f32, f32, i32,
-                                 p, p, p, p, p, p, p]),
+                                 p, p, p, p, p, p]),
     "spmf_unpack_adam": (i32, [p, i32, i32, f32, f32, p, p, p, i64, p, p]),
     "spmf_adam_step": (i32, [p, p, p, p, i64, f32, f32, f32, f32, i32, f32, f32, p]),
     "spmf_unpack_parts": (i32, [p, i32, i32, f32, f32, p, p, p]),
@@ -77,7 +77,7 @@ _SIGS = {
     "spmf_draw_operands_ranked": (i32, [p, p, p, p, i32, i32, i32, p, p, p, p, p, p, p]),
     "spmf_operand_sums": (i32, [p, p, i32, i32, i32, p, p, p, p]),
     "spmf_backward_params_ranked": (i32, [p, p, p, p, p, i32, i32, i32, p, p, p, p, p, p, f32, f32, f32, f32,
-                                          f32, f32, i32, p, p, p, p, p, p, p]),
+                                          f32, f32, i32, p, p, p, p, p, p]),
     "spmf_umma_tiled_a_elems": (i64, [i64, i64]),
     "spmf_umma_tiled_b_elems": (i64, [i32, i64]),
     "spmf_umma_tiled_a_index": (i64, [i64, i64, i64]),
@@ -115,7 +115,7 @@ _SIGS = {
 class AdamArgs(C.Structure):
     """Mirror of `spmf_adam_args` (include/spmf_b200.h)."""
     _fields_ = ([(n, f32) for n in ("lr", "beta1", "beta2", "eps", "clip_value", "grad_scale")]
-                + [("step", i32), ("defer_data", i32), ("params", p), ("m", p), ("v", p)])
+                + [("step", i32), ("reserved", i32), ("params", p), ("m", p), ("v", p)])
 
 
 class StepArgs(C.Structure):

@@ -19,7 +19,6 @@
 // by the whole CTA (coalesced global reads, broadcast / conflict-free shared reads).  This is the
 // "x tile in shared memory, rate recomputed in registers, dL/drate feeding dz and dv in the same
 // pass" formulation; it is FMA-bound (2*K FMAs per entry and pass against K/4 + 1 shared loads).
-#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <float.h>
 #include <stdint.h>
@@ -27,8 +26,6 @@
 #include "../../include/spmf_b200.h"
 #include "spmf_guard.cuh"
 #include "spmf_record.cuh"
-
-namespace cg = cooperative_groups;
 
 namespace spmf {
 
@@ -457,10 +454,55 @@ dense_cols_kernel(DenseBatch b, DenseGeom g, const float* __restrict__ EV, const
                        min(b.nrows, r0 + rows_per_split));
 }
 
-// ... and the exact-guard slow path of the linear link as TWO conditional cooperative launches (they
-// return at once unless gs->flag is set, so a step that meets no non-finite entry pays two empty
-// launches): rows fix = densify -> statistics -> guarded row pass; columns fix = zero GEV / Gphi ->
+// ... and the exact-guard slow path of the linear link as TWO conditional launches (they return at once
+// unless gs->flag is set, so a step that meets no non-finite entry pays two empty launches of one CTA
+// per SM): rows fix = densify -> statistics -> guarded row pass; columns fix = zero GEV / Gphi ->
 // guarded column pass.  GA' needs no fix of its own: it is computed from the (fixed) dzr afterwards.
+// The phases of one launch are separated by a grid barrier.  These are ordinary launches of at most
+// one CTA per SM (a cooperative launch would make every step wait for the whole grid to be
+// co-resident, i.e. drain the kernels of the other streams, even when the guard does not fire -- measured
+// +70 us per step); the barrier is a monotonic arrival counter in the guard state: all CTAs become
+// resident as soon as the kernels running beside them finish (nothing those kernels wait for is
+// produced here), and a bounded spin turns a barrier that could not complete into a flagged error
+// instead of a hang.
+__device__ __forceinline__ bool grid_barrier(GuardState* gs, unsigned nblocks, unsigned phase) {
+  __shared__ int ok_s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(&gs->bar, 1u);
+    const unsigned target = (phase + 1u) * nblocks;
+    int ok = 0;
+    for (long long spin = 0; spin < (1ll << 24); ++spin) {          // ~10 s at 0.5 us per poll
+      if (*(volatile unsigned*)&gs->bar >= target) { ok = 1; break; }
+      __nanosleep(500);
+    }
+    __threadfence();
+    ok_s = ok;
+  }
+  __syncthreads();
+  return ok_s != 0;
+}
+// last CTA out re-arms the barrier for the next launch
+__device__ __forceinline__ void grid_leave(GuardState* gs, unsigned nblocks) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(&gs->done, 1u) == nblocks - 1u) {
+      gs->bar = 0u;
+      gs->done = 0u;
+      __threadfence();
+    }
+  }
+}
+#define GRID_BARRIER_OR_FAIL(gs, phase)                       \
+  do {                                                        \
+    if (!grid_barrier(gs, gridDim.x, phase)) {                \
+      if (threadIdx.x == 0) atomicOr(&(gs)->flag, 4);         \
+      grid_leave(gs, gridDim.x);                              \
+      return;                                                 \
+    }                                                         \
+  } while (0)
 struct GuardFixArgs {
   DenseBatch b;
   DenseGeom g;
@@ -476,22 +518,22 @@ template <int KC>
 __global__ void __launch_bounds__(128)
 guard_rows_fix_kernel(GuardFixArgs a) {
   extern __shared__ __align__(16) float dsm[];
-  if (!(a.gs->flag & 1)) return;                             // uniform over the grid
-  cg::grid_group grid = cg::this_grid();
+  if (!(a.gs->flag & 1)) return;                             // uniform over the grid (nobody writes it here)
   const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
   if (tid == 0) { a.gs->nbad = 0; a.gs->minkey = ~0ull; }
   phase_zero(a.xd, (long long)a.b.nrows * a.b.D, tid, nth);
-  grid.sync();
+  GRID_BARRIER_OR_FAIL(a.gs, 0u);
   phase_scatter(a.rowptr, a.cols, a.vals, a.b.nrows, a.b.D, a.xd, tid >> 5, nth >> 5, threadIdx.x & 31);
-  grid.sync();
+  GRID_BARRIER_OR_FAIL(a.gs, 1u);
   DenseBatch b = a.b;
   b.xd = a.xd;
   const int ntile = (b.nrows + a.g.OB - 1) / a.g.OB;
-  for (int mode = MODE_STATS; mode <= MODE_GUARD; ++mode) {
-    for (int w = blockIdx.x; w < ntile * a.g.NQ; w += gridDim.x)
-      phase_rows<KC, LINK_POIS_LIN>(b, a.g, a.EV, a.PH, a.z, a.dzr, a.rowacc, a.gs, mode, dsm, w % ntile, w / ntile);
-    grid.sync();
-  }
+  for (int w = blockIdx.x; w < ntile * a.g.NQ; w += gridDim.x)
+    phase_rows<KC, LINK_POIS_LIN>(b, a.g, a.EV, a.PH, a.z, a.dzr, a.rowacc, a.gs, MODE_STATS, dsm, w % ntile, w / ntile);
+  GRID_BARRIER_OR_FAIL(a.gs, 2u);
+  for (int w = blockIdx.x; w < ntile * a.g.NQ; w += gridDim.x)
+    phase_rows<KC, LINK_POIS_LIN>(b, a.g, a.EV, a.PH, a.z, a.dzr, a.rowacc, a.gs, MODE_GUARD, dsm, w % ntile, w / ntile);
+  grid_leave(a.gs, gridDim.x);
 }
 
 template <int KC>
@@ -499,11 +541,10 @@ __global__ void __launch_bounds__(128)
 guard_cols_fix_kernel(GuardFixArgs a) {
   extern __shared__ __align__(16) float dsm[];
   if (!(a.gs->flag & 1)) return;
-  cg::grid_group grid = cg::this_grid();
   const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
   phase_zero(a.GEV, (long long)a.g.NQ * a.b.D * a.g.REC, tid, nth);
   phase_zero(a.Gph, (long long)a.g.NQ * a.b.D * a.g.SV, tid, nth);
-  grid.sync();
+  GRID_BARRIER_OR_FAIL(a.gs, 0u);
   DenseBatch b = a.b;
   b.xd = a.xd;
   const int nct = (b.D + a.g.OB - 1) / a.g.OB;
@@ -515,12 +556,15 @@ guard_cols_fix_kernel(GuardFixArgs a) {
     phase_cols<KC, LINK_POIS_LIN>(b, a.g, a.EV, a.PH, a.z, nullptr, nullptr, a.GEV, a.Gph, a.gs, 0, dsm, ct, q, r0,
                                   min(b.nrows, r0 + a.rows_per_split));
   }
+  grid_leave(a.gs, gridDim.x);
 }
 
 __global__ void guard_reset_kernel(GuardState* gs, int flag) {
   gs->flag = flag;
   gs->nbad = 0;
   gs->minkey = ~0ull;
+  gs->bar = 0u;
+  gs->done = 0u;
 }
 
 static size_t rows_smem(const DenseGeom& g) {
@@ -689,24 +733,20 @@ int spmf_dense_cols(const float* xd, const float* eta_enc, int nrows, int D, int
 // nrows*D floats, touched only when the guard fires.
 template <int KC, typename Kern>
 static int launch_fix(Kern kern, GuardFixArgs& a, size_t sm, cudaStream_t st) {
-  static size_t cached_sm = ~(size_t)0;          // per instantiation: grid of the last shared-memory size
+  static size_t cached_sm = ~(size_t)0;          // per instantiation: set the shared-memory attribute once per size
   static int cached_grid = 0;
   if (cached_sm != sm) {
     int rc = set_smem(kern, sm);
     if (rc) return rc;
-    int per_sm = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, sm);
-    if (e != cudaSuccess) return (int)e;
     int dev = 0, sms = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (per_sm < 1 || sms < 1) return SPMF_ERR_UNSUPPORTED;
-    if (per_sm > 2) per_sm = 2;                  // leave room for the kernels of the other streams
-    cached_grid = sms * per_sm;
+    if (sms < 1) return SPMF_ERR_UNSUPPORTED;
+    cached_grid = sms;                           // one CTA per SM: always able to become co-resident
     cached_sm = sm;
   }
-  void* args[] = {&a};
-  cudaError_t e = cudaLaunchCooperativeKernel((const void*)kern, dim3(cached_grid), dim3(128), args, sm, st);
+  kern<<<cached_grid, 128, sm, st>>>(a);
+  cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? SPMF_OK : (int)e;
 }
 

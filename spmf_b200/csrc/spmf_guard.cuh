@@ -16,6 +16,8 @@ struct GuardState {
   int flag;
   int nbad;
   unsigned long long minkey;
+  unsigned bar;        // arrival counter of the slow path's grid barrier (0 between launches)
+  unsigned done;       // blocks that have left the slow-path kernel
 };
 
 #if defined(__CUDACC__)

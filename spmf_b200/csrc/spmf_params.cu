@@ -149,8 +149,16 @@ draw_operands_kernel(Layout L, const float* __restrict__ P, const float* __restr
   const float s0l = P[L.toff[S_LOC] + d], s0s = softplusf(P[L.toff[S_RHO] + d]);
   const float s1l = P[L.toff[S_LOC] + D + d], s1s = softplusf(P[L.toff[S_RHO] + D + d]);
   const float eta_dec = eta[d], ieta_enc = 1.f / eta[D + d];
-  for (int s = 0; s < L.S; ++s) {
-    const int q = s / SV, sv = s - q * SV;
+  // position of (sv, k) inside a record = position of (0, k) + sv * RG * VW  (spmf_record.cuh): the
+  // integer divisions of rec_pos leave the draw loop
+  const RecMap rm = rec_map(KP);
+  const int sv_stride = rm.RG * rm.VW;
+  int pos0[KK];
+#pragma unroll
+  for (int i = 0; i < KK; ++i) pos0[i] = (lane + 32 * i) < KP ? rec_pos(KP, SV, 0, lane + 32 * i) : 0;
+  int q = 0, sv = 0;
+  for (int s = 0; s < L.S; ++s, ++sv) {
+    if (sv == SV) { sv = 0; ++q; }
     const float y0 = softplus4(fmaf(s0s, N[L.noff[VAR_S] + (long long)s * 2 * D + d], s0l)).y;
     const float y1 = softplus4(fmaf(s1s, N[L.noff[VAR_S] + (long long)s * 2 * D + D + d], s1l)).y;
     const float inv = 1.f / (y0 + y1);
@@ -165,7 +173,7 @@ draw_operands_kernel(Layout L, const float* __restrict__ P, const float* __restr
           ap = a_d * softplus4(fmaf(us[i], N[L.noff[VAR_U] + e], ul[i])).y * ieta_enc;   // A' (poisson.py:665, 43)
           ev = eta_dec * softplus4(fmaf(vs[i], N[L.noff[VAR_V] + e], vl[i])).y;          // eta v (poisson.py:54)
         }
-        const long long idx = ((long long)q * D + dr) * SV * KP + rec_pos(KP, SV, sv, k);
+        const long long idx = ((long long)q * D + dr) * SV * KP + pos0[i] + sv * sv_stride;
         Ap[idx] = ap;
         EV[idx] = ev;
       }
@@ -216,8 +224,7 @@ backward_dk_kernel(Layout L, Hyper h, const float* __restrict__ P, const float* 
                    const float* __restrict__ GAp, const float* __restrict__ GEVnz,
                    const double* __restrict__ zcolsum, float* __restrict__ grads,
                    float* __restrict__ scr_utau, float* __restrict__ scr_parts,
-                   float* __restrict__ scr_da, float* __restrict__ fac, const int* __restrict__ gflag,
-                   AdamCfg adam, int adam_data) {
+                   float* __restrict__ scr_da, float* __restrict__ fac, const int* __restrict__ gflag) {
   const int lane = threadIdx.x & 31;
   const int d = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (d >= L.D) return;
@@ -227,6 +234,11 @@ backward_dk_kernel(Layout L, Hyper h, const float* __restrict__ P, const float* 
   lane_init<KK>(st, L, P, d, lane, h.decay);
   const NParam s0 = nparam_init(P[L.toff[S_LOC] + d], P[L.toff[S_RHO] + d]);
   const NParam s1 = nparam_init(P[L.toff[S_LOC] + L.D + d], P[L.toff[S_RHO] + L.D + d]);
+  const RecMap rmap = rec_map(KP);                 // rec_pos(sv, k) = rec_pos(0, k) + sv * RG * VW
+  const int sv_stride = rmap.RG * rmap.VW;
+  int pos0[KK];
+#pragma unroll
+  for (int i = 0; i < KK; ++i) pos0[i] = (lane + 32 * i) < KP ? rec_pos(KP, SV, 0, lane + 32 * i) : 0;
   for (int s = 0; s < L.S; ++s) {
     const int q = s / SV, sv = s - q * SV;
     const float y0 = ndraw(s0, N[L.noff[VAR_S] + (long long)s * 2 * L.D + d]).y;
@@ -237,7 +249,7 @@ backward_dk_kernel(Layout L, Hyper h, const float* __restrict__ P, const float* 
     for (int i = 0; i < KK; ++i) {
       int k = lane + 32 * i;
       if (k < L.K) {
-        const int rp = rec_pos(KP, SV, sv, k);
+        const int rp = pos0[i] + sv * sv_stride;
         long long idx = ((long long)q * L.D + dr) * SV * KP + rp;
         DkUp up;
         if constexpr (PRE) {
@@ -286,17 +298,6 @@ backward_dk_kernel(Layout L, Hyper h, const float* __restrict__ P, const float* 
       nparam_finish(st.v[i], P[L.toff[V_RHO] + e], invS, wer, &grads[L.toff[V_LOC] + e], &grads[L.toff[V_RHO] + e]);
       gparam_finish(st.ue[i], P[L.toff[UETA_C] + e], P[L.toff[UETA_B] + e], invS, &grads[L.toff[UETA_C] + e], &grads[L.toff[UETA_B] + e]);
       gparam_finish(st.ua[i], P[L.toff[UETAA_C] + e], P[L.toff[UETAA_B] + e], invS, &grads[L.toff[UETAA_C] + e], &grads[L.toff[UETAA_B] + e]);
-      if (adam.lr > 0.f) {
-        // u_eta, u_eta_a see prior / entropy terms only: their gradients are final here
-        const int ig[4] = {UETA_C, UETA_B, UETAA_C, UETAA_B};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) adam_apply(adam, L.toff[ig[j]] + e, grads[L.toff[ig[j]] + e]);
-        if (!PRE && adam_data) {                   // one-pass backward: u, v are final as well
-          const int dt[4] = {U_LOC, U_RHO, V_LOC, V_RHO};
-#pragma unroll
-          for (int j = 0; j < 4; ++j) adam_apply(adam, L.toff[dt[j]] + e, grads[L.toff[dt[j]] + e]);
-        }
-      }
     }
   }
 }
@@ -310,8 +311,7 @@ backward_dk_post_kernel(Layout L, Hyper h, const float* __restrict__ P, const fl
                         const float* __restrict__ eta, const int* __restrict__ rank, int SV, int KP,
                         const float* __restrict__ GAp, const float* __restrict__ GEVnz,
                         const float* __restrict__ Gphinz, const double* __restrict__ zcolsum,
-                        const float* __restrict__ fac, float* __restrict__ grads, const int* __restrict__ gflag,
-                        AdamCfg adam) {
+                        const float* __restrict__ fac, float* __restrict__ grads, const int* __restrict__ gflag) {
   const int lane = threadIdx.x & 31;
   const int d = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (d >= L.D) return;
@@ -323,6 +323,11 @@ backward_dk_post_kernel(Layout L, Hyper h, const float* __restrict__ P, const fl
 #pragma unroll
   for (int i = 0; i < KK; ++i) { au[i] = 0.f; aue[i] = 0.f; av[i] = 0.f; ave[i] = 0.f; }
   float da_mine[2] = {0.f, 0.f};               // S <= 64 draws (checked by the launcher)
+  const RecMap rmap = rec_map(KP);                 // rec_pos(sv, k) = rec_pos(0, k) + sv * RG * VW
+  const int sv_stride = rmap.RG * rmap.VW;
+  int pos0[KK];
+#pragma unroll
+  for (int i = 0; i < KK; ++i) pos0[i] = (lane + 32 * i) < KP ? rec_pos(KP, SV, 0, lane + 32 * i) : 0;
   for (int s = 0; s < L.S; ++s) {
     const int q = s / SV, sv = s - q * SV;
     float da = 0.f;
@@ -330,7 +335,7 @@ backward_dk_post_kernel(Layout L, Hyper h, const float* __restrict__ P, const fl
     for (int i = 0; i < KK; ++i) {
       const int k = lane + 32 * i;
       if (k < L.K) {
-        const int rp = rec_pos(KP, SV, sv, k);
+        const int rp = pos0[i] + sv * sv_stride;
         const long long idx = ((long long)q * L.D + dr) * SV * KP + rp;
         const long long e = ((long long)s * L.D + d) * L.K + k;
         const float ga = GAp[idx];
@@ -381,12 +386,6 @@ backward_dk_post_kernel(Layout L, Hyper h, const float* __restrict__ P, const fl
       grads[L.toff[S_RHO] + d] += a0e * invS * sigmoidf(P[L.toff[S_RHO] + d]);
       grads[L.toff[S_LOC] + D + d] += a1 * invS;
       grads[L.toff[S_RHO] + D + d] += a1e * invS * sigmoidf(P[L.toff[S_RHO] + D + d]);
-      if (adam.lr > 0.f) {                          // w, s of this feature are final: optimiser step in place
-        const long long ix[6] = {L.toff[W_LOC] + d, L.toff[W_RHO] + d, L.toff[S_LOC] + d, L.toff[S_RHO] + d,
-                                 L.toff[S_LOC] + D + d, L.toff[S_RHO] + D + d};
-#pragma unroll
-        for (int j = 0; j < 6; ++j) adam_apply(adam, ix[j], grads[ix[j]]);
-      }
     }
   }
 #pragma unroll
@@ -398,11 +397,6 @@ backward_dk_post_kernel(Layout L, Hyper h, const float* __restrict__ P, const fl
       grads[L.toff[U_RHO] + e] += aue[i] * invS * sigmoidf(P[L.toff[U_RHO] + e]);
       grads[L.toff[V_LOC] + e] += av[i] * invS;
       grads[L.toff[V_RHO] + e] += ave[i] * invS * sigmoidf(P[L.toff[V_RHO] + e]);
-      if (adam.lr > 0.f) {
-        const int dt[4] = {U_LOC, U_RHO, V_LOC, V_RHO};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) adam_apply(adam, L.toff[dt[j]] + e, grads[L.toff[dt[j]] + e]);
-      }
     }
   }
 }
@@ -420,7 +414,7 @@ backward_feat_kernel(Layout L, Hyper h, const float* __restrict__ P, const float
                      const int* __restrict__ rank, int SV,
                      const float* __restrict__ Gphinz, const float* __restrict__ scr_da,
                      float* __restrict__ grads, float* __restrict__ scr_parts, int pre,
-                     const int* __restrict__ gflag, AdamCfg adam, int adam_data) {
+                     const int* __restrict__ gflag) {
   if (!pre && gflag && *gflag) h.batch_rows = 0.f;  // dense data term: Gphi carries no closed-form -B
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int dreal = t / SV, sg = t - dreal * SV;
@@ -461,26 +455,13 @@ backward_feat_kernel(Layout L, Hyper h, const float* __restrict__ P, const float
   gparam_finish(f.sea0, P[L.toff[SETAA_C] + d], P[L.toff[SETAA_B] + d], invS, &grads[L.toff[SETAA_C] + d], &grads[L.toff[SETAA_B] + d]);
   gparam_finish(f.sea1, P[L.toff[SETAA_C] + D + d], P[L.toff[SETAA_B] + D + d], invS, &grads[L.toff[SETAA_C] + D + d], &grads[L.toff[SETAA_B] + D + d]);
   gparam_finish(f.sta, P[L.toff[STAUA_C] + d], P[L.toff[STAUA_B] + d], invS, &grads[L.toff[STAUA_C] + d], &grads[L.toff[STAUA_B] + d]);
-  if (adam.lr > 0.f) {
-    const long long ig[12] = {L.toff[SETA_C] + d, L.toff[SETA_B] + d, L.toff[SETA_C] + D + d, L.toff[SETA_B] + D + d,
-                              L.toff[STAU_C] + d, L.toff[STAU_B] + d, L.toff[SETAA_C] + d, L.toff[SETAA_B] + d,
-                              L.toff[SETAA_C] + D + d, L.toff[SETAA_B] + D + d, L.toff[STAUA_C] + d, L.toff[STAUA_B] + d};
-#pragma unroll
-    for (int j = 0; j < 12; ++j) adam_apply(adam, ig[j], grads[ig[j]]);
-    if (!pre && adam_data) {
-      const long long dt[6] = {L.toff[W_LOC] + d, L.toff[W_RHO] + d, L.toff[S_LOC] + d, L.toff[S_RHO] + d,
-                               L.toff[S_LOC] + D + d, L.toff[S_RHO] + D + d};
-#pragma unroll
-      for (int j = 0; j < 6; ++j) adam_apply(adam, dt[j], grads[dt[j]]);
-    }
-  }
 }
 
 // ------------------------------------------------------------------ backward (per latent k)
 __global__ void backward_lat_kernel(Layout L, Hyper h, const float* __restrict__ P,
                                     const float* __restrict__ N, const float* __restrict__ G,
                                     const double* __restrict__ dutau,
-                                    float* __restrict__ grads, float* __restrict__ scr_lat, AdamCfg adam) {
+                                    float* __restrict__ grads, float* __restrict__ scr_lat) {
   int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= L.K) return;
   LatState t;
@@ -495,11 +476,6 @@ __global__ void backward_lat_kernel(Layout L, Hyper h, const float* __restrict__
   const float invS = 1.f / (float)L.S;
   gparam_finish(t.ut, P[L.toff[UTAU_C] + k], P[L.toff[UTAU_B] + k], invS, &grads[L.toff[UTAU_C] + k], &grads[L.toff[UTAU_B] + k]);
   gparam_finish(t.uta, P[L.toff[UTAUA_C] + k], P[L.toff[UTAUA_B] + k], invS, &grads[L.toff[UTAUA_C] + k], &grads[L.toff[UTAUA_B] + k]);
-  if (adam.lr > 0.f) {
-    const long long ig[4] = {L.toff[UTAU_C] + k, L.toff[UTAU_B] + k, L.toff[UTAUA_C] + k, L.toff[UTAUA_B] + k};
-#pragma unroll
-    for (int j = 0; j < 4; ++j) adam_apply(adam, ig[j], grads[ig[j]]);
-  }
 }
 
 // ------------------------------------------------------------------ deterministic reductions
@@ -545,7 +521,8 @@ __global__ void finalize_parts_kernel(int S, int SV, int K, const double* __rest
   const double min_val = gs ? (double)guard_min_val(gs->minkey) : 0.0;
   __syncthreads();
   if (gs && threadIdx.x == 0) {        // last reader of the step: re-arm the guard for the next one
-    gs->flag = gflag & 2;              // (the dense-link bit is configuration, not state)
+    gs->flag = gflag & 2;              // (the dense-link bit is configuration, not state; bit 2 = barrier
+                                       //  failure of the slow path, sticky in the reports only)
     gs->nbad = 0;
     gs->minkey = ~0ull;
   }
@@ -608,7 +585,8 @@ __global__ void unpack_adam_kernel(int S, double w_entropy, double w_prior, floa
                                    const float* __restrict__ g, long long n, AdamCfg adam) {
   if (blockIdx.x + 1 < gridDim.x) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n && adam.lr > 0.f) adam_apply(adam, i, g[i]);
+    const long long c0 = comm - g;                       // the scalar slack is bookkeeping, not a gradient
+    if (i < n && adam.lr > 0.f && !(i >= c0 && i < c0 + slack)) adam_apply(adam, i, g[i]);
     return;
   }
   __shared__ double sl[64];
@@ -881,11 +859,10 @@ int spmf_backward_params(const float* params, const float* noise, const float* d
                          const double* zcolsum, const double* datasums, const double* phisum,
                          float batch_rows, float u_tau_scale, float s_tau_scale,
                          float decay, float w_entropy, float w_prior, int world_size, float* grads,
-                         double* parts, float* scr_f, double* scr_d, void* gs, const spmf_adam_args* adam,
-                         void* stream) {
+                         double* parts, float* scr_f, double* scr_d, void* gs, void* stream) {
   return spmf_backward_params_ranked(params, noise, dgda, eta, nullptr, D, K, S, GAp, GEVnz, Gphinz, zcolsum,
                                      datasums, phisum, batch_rows, u_tau_scale, s_tau_scale, decay, w_entropy,
-                                     w_prior, world_size, grads, parts, scr_f, scr_d, gs, adam, stream);
+                                     w_prior, world_size, grads, parts, scr_f, scr_d, gs, stream);
 }
 
 int spmf_backward_params_ranked(const float* params, const float* noise, const float* dgda, const float* eta,
@@ -893,10 +870,7 @@ int spmf_backward_params_ranked(const float* params, const float* noise, const f
                                 const float* Gphinz, const double* zcolsum, const double* datasums,
                                 const double* phisum, float batch_rows, float u_tau_scale, float s_tau_scale,
                                 float decay, float w_entropy, float w_prior, int world_size, float* grads,
-                                double* parts, float* scr_f, double* scr_d, void* gs,
-                                const spmf_adam_args* adam, void* stream) {
-  const AdamCfg ad = make_adam(adam);
-  const int ad_data = adam ? !adam->defer_data : 0;
+                                double* parts, float* scr_f, double* scr_d, void* gs, void* stream) {
   if (!params || !noise || !dgda || !eta || !GAp || !GEVnz || !Gphinz || !zcolsum || !datasums ||
       !phisum || !grads || !parts || !scr_f || !scr_d)
     return SPMF_ERR_BAD_ARG;
@@ -916,14 +890,14 @@ int spmf_backward_params_ranked(const float* params, const float* noise, const f
   double* rscr = latparts + (long long)S * NUM_PARTS;
   float* scr_da = scr_lat + (long long)K * S * NUM_PARTS;
   dim3 grid((D + 3) / 4);
-  if (KP <= 32) backward_dk_kernel<1, false><<<grid, 128, 0, st>>>(L, h, params, noise, dgda, eta, rank, SV, KP, GAp, GEVnz, zcolsum, grads, scr_utau, scr_parts, scr_da, nullptr, (const int*)gs, ad, ad_data);
-  else if (KP <= 64) backward_dk_kernel<2, false><<<grid, 128, 0, st>>>(L, h, params, noise, dgda, eta, rank, SV, KP, GAp, GEVnz, zcolsum, grads, scr_utau, scr_parts, scr_da, nullptr, (const int*)gs, ad, ad_data);
-  else backward_dk_kernel<4, false><<<grid, 128, 0, st>>>(L, h, params, noise, dgda, eta, rank, SV, KP, GAp, GEVnz, zcolsum, grads, scr_utau, scr_parts, scr_da, nullptr, (const int*)gs, ad, ad_data);
-  backward_feat_kernel<<<(int)(((long long)D * SV + 127) / 128), 128, 0, st>>>(L, h, params, noise, dgda, eta, rank, SV, Gphinz, scr_da, grads, scr_parts, 0, (const int*)gs, ad, ad_data);
+  if (KP <= 32) backward_dk_kernel<1, false><<<grid, 128, 0, st>>>(L, h, params, noise, dgda, eta, rank, SV, KP, GAp, GEVnz, zcolsum, grads, scr_utau, scr_parts, scr_da, nullptr, (const int*)gs);
+  else if (KP <= 64) backward_dk_kernel<2, false><<<grid, 128, 0, st>>>(L, h, params, noise, dgda, eta, rank, SV, KP, GAp, GEVnz, zcolsum, grads, scr_utau, scr_parts, scr_da, nullptr, (const int*)gs);
+  else backward_dk_kernel<4, false><<<grid, 128, 0, st>>>(L, h, params, noise, dgda, eta, rank, SV, KP, GAp, GEVnz, zcolsum, grads, scr_utau, scr_parts, scr_da, nullptr, (const int*)gs);
+  backward_feat_kernel<<<(int)(((long long)D * SV + 127) / 128), 128, 0, st>>>(L, h, params, noise, dgda, eta, rank, SV, Gphinz, scr_da, grads, scr_parts, 0, (const int*)gs);
   SPMF_CHECK_LAUNCH();
   int rc = reduce_rows_pair(scr_utau, dutau, D, K, S, scr_parts, featparts, D, S * NUM_PARTS, 1, rscr, st);
   if (rc) return rc;
-  backward_lat_kernel<<<(K + 63) / 64, 64, 0, st>>>(L, h, params, noise, dgda, dutau, grads, scr_lat, ad);
+  backward_lat_kernel<<<(K + 63) / 64, 64, 0, st>>>(L, h, params, noise, dgda, dutau, grads, scr_lat);
   SPMF_CHECK_LAUNCH();
   rc = reduce_rows<float>(scr_lat, latparts, rscr, K, S * NUM_PARTS, 1, st);
   if (rc) return rc;
@@ -944,9 +918,7 @@ long long spmf_backward_scratch_floats(int D, int K, int S) {
  * a side stream), spmf_backward_post = the data half + the loss parts.  pre + post == spmf_backward_params. */
 int spmf_backward_pre(const float* params, const float* noise, const float* dgda, const float* eta, int D, int K,
                       int S, float batch_rows, float u_tau_scale, float s_tau_scale, float decay, float w_entropy,
-                      float w_prior, int world_size, float* grads, float* scr_f, double* scr_d,
-                      const spmf_adam_args* adam, void* stream) {
-  const AdamCfg ad = make_adam(adam);
+                      float w_prior, int world_size, float* grads, float* scr_f, double* scr_d, void* stream) {
   if (!params || !noise || !dgda || !eta || !grads || !scr_f || !scr_d) return SPMF_ERR_BAD_ARG;
   if (D <= 0 || K <= 0 || S <= 0 || K > SPMF_MAX_K || world_size <= 0) return SPMF_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
@@ -963,14 +935,14 @@ int spmf_backward_pre(const float* params, const float* noise, const float* dgda
   double* latparts = featparts + (long long)S * NUM_PARTS;
   double* rscr = latparts + (long long)S * NUM_PARTS;
   dim3 grid((D + 3) / 4);
-  if (KP <= 32) backward_dk_kernel<1, true><<<grid, 128, 0, st>>>(L, h, params, noise, dgda, eta, nullptr, SV, KP, nullptr, nullptr, nullptr, grads, scr_utau, scr_parts, scr_da, fac, nullptr, ad, 0);
-  else if (KP <= 64) backward_dk_kernel<2, true><<<grid, 128, 0, st>>>(L, h, params, noise, dgda, eta, nullptr, SV, KP, nullptr, nullptr, nullptr, grads, scr_utau, scr_parts, scr_da, fac, nullptr, ad, 0);
-  else backward_dk_kernel<4, true><<<grid, 128, 0, st>>>(L, h, params, noise, dgda, eta, nullptr, SV, KP, nullptr, nullptr, nullptr, grads, scr_utau, scr_parts, scr_da, fac, nullptr, ad, 0);
-  backward_feat_kernel<<<(int)(((long long)D * SV + 127) / 128), 128, 0, st>>>(L, h, params, noise, dgda, eta, nullptr, SV, nullptr, nullptr, grads, scr_parts, 1, nullptr, ad, 0);
+  if (KP <= 32) backward_dk_kernel<1, true><<<grid, 128, 0, st>>>(L, h, params, noise, dgda, eta, nullptr, SV, KP, nullptr, nullptr, nullptr, grads, scr_utau, scr_parts, scr_da, fac, nullptr);
+  else if (KP <= 64) backward_dk_kernel<2, true><<<grid, 128, 0, st>>>(L, h, params, noise, dgda, eta, nullptr, SV, KP, nullptr, nullptr, nullptr, grads, scr_utau, scr_parts, scr_da, fac, nullptr);
+  else backward_dk_kernel<4, true><<<grid, 128, 0, st>>>(L, h, params, noise, dgda, eta, nullptr, SV, KP, nullptr, nullptr, nullptr, grads, scr_utau, scr_parts, scr_da, fac, nullptr);
+  backward_feat_kernel<<<(int)(((long long)D * SV + 127) / 128), 128, 0, st>>>(L, h, params, noise, dgda, eta, nullptr, SV, nullptr, nullptr, grads, scr_parts, 1, nullptr);
   SPMF_CHECK_LAUNCH();
   int rc = reduce_rows_pair(scr_utau, dutau, D, K, S, scr_parts, featparts, D, S * NUM_PARTS, 1, rscr, st);
   if (rc) return rc;
-  backward_lat_kernel<<<(K + 63) / 64, 64, 0, st>>>(L, h, params, noise, dgda, dutau, grads, scr_lat, ad);
+  backward_lat_kernel<<<(K + 63) / 64, 64, 0, st>>>(L, h, params, noise, dgda, dutau, grads, scr_lat);
   SPMF_CHECK_LAUNCH();
   return reduce_rows<float>(scr_lat, latparts, rscr, K, S * NUM_PARTS, 1, st);
 }
@@ -979,10 +951,7 @@ int spmf_backward_post(const float* params, const float* noise, const float* eta
                        int S, const float* GAp, const float* GEVnz, const float* Gphinz, const double* zcolsum,
                        const double* datasums, const double* phisum, float batch_rows, float u_tau_scale,
                        float s_tau_scale, float decay, float w_entropy, float w_prior, int world_size,
-                       float* grads, double* parts, float* scr_f, const double* scr_d, void* gs,
-                       const spmf_adam_args* adam, void* stream) {
-  AdamCfg ad = make_adam(adam);
-  if (adam && adam->defer_data) ad.lr = 0.f;       // multi-GPU: v, w, u, s wait for the all-reduce
+                       float* grads, double* parts, float* scr_f, const double* scr_d, void* gs, void* stream) {
   if (!params || !noise || !eta || !GAp || !GEVnz || !Gphinz || !zcolsum || !datasums || !phisum || !grads ||
       !parts || !scr_f || !scr_d)
     return SPMF_ERR_BAD_ARG;
@@ -997,9 +966,9 @@ int spmf_backward_post(const float* params, const float* noise, const float* eta
   const double* latparts = featparts + (long long)S * NUM_PARTS;
   dim3 grid((D + 3) / 4);
   if (S > 64) return SPMF_ERR_BAD_ARG;
-  if (KP <= 32) backward_dk_post_kernel<1><<<grid, 128, 0, st>>>(L, h, params, noise, eta, rank, SV, KP, GAp, GEVnz, Gphinz, zcolsum, fac, grads, (const int*)gs, ad);
-  else if (KP <= 64) backward_dk_post_kernel<2><<<grid, 128, 0, st>>>(L, h, params, noise, eta, rank, SV, KP, GAp, GEVnz, Gphinz, zcolsum, fac, grads, (const int*)gs, ad);
-  else backward_dk_post_kernel<4><<<grid, 128, 0, st>>>(L, h, params, noise, eta, rank, SV, KP, GAp, GEVnz, Gphinz, zcolsum, fac, grads, (const int*)gs, ad);
+  if (KP <= 32) backward_dk_post_kernel<1><<<grid, 128, 0, st>>>(L, h, params, noise, eta, rank, SV, KP, GAp, GEVnz, Gphinz, zcolsum, fac, grads, (const int*)gs);
+  else if (KP <= 64) backward_dk_post_kernel<2><<<grid, 128, 0, st>>>(L, h, params, noise, eta, rank, SV, KP, GAp, GEVnz, Gphinz, zcolsum, fac, grads, (const int*)gs);
+  else backward_dk_post_kernel<4><<<grid, 128, 0, st>>>(L, h, params, noise, eta, rank, SV, KP, GAp, GEVnz, Gphinz, zcolsum, fac, grads, (const int*)gs);
   finalize_parts_kernel<<<1, ((S + 31) / 32) * 32, 0, st>>>(S, SV, K, featparts, latparts, datasums, phisum,
                                                            (double)batch_rows, (double)w_entropy, (double)w_prior,
                                                            parts, grads + L.comm_off, (GuardState*)gs);
@@ -1024,7 +993,7 @@ int spmf_adam_step(float* params, const float* grads, float* m, float* v, long l
 }
 
 /* Multi-GPU tail of a step in one launch: fold the all-reduced ('z','x') pairs back into parts / the mean
- * loss (spmf_unpack_parts) and apply Adam to the all-reduced block grads[0, n_data) = v, w, u, s. */
+ * loss (spmf_unpack_parts) and apply Adam to grads[0, n) (the whole flat parameter buffer). */
 int spmf_unpack_adam(float* comm_slack, int slack_floats, int S, float w_entropy, float w_prior, double* parts,
                      double* loss_out, const float* grads, long long n_data, const spmf_adam_args* adam,
                      void* stream) {

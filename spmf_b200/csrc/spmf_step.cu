@@ -29,13 +29,6 @@ int spmf_advi_step(const spmf_step_args* a) {
   const bool multi = (hot != caller) || (side != hot);
   if (multi && (!a->ev_fork || !a->ev_join || !a->ev_done)) return SPMF_ERR_BAD_ARG;
   const int D = a->D, K = a->K, S = a->S;
-  // Adam is applied by the backward kernels themselves (no separate pass over the parameters)
-  spmf_adam_args adam{};
-  adam.lr = a->adam_lr; adam.beta1 = a->adam_beta1; adam.beta2 = a->adam_beta2; adam.eps = a->adam_eps;
-  adam.clip_value = a->clip_value; adam.grad_scale = 1.f; adam.step = a->adam_t;
-  adam.defer_data = a->world_size > 1;
-  adam.params = a->params; adam.m = a->adam_m; adam.v = a->adam_v;
-  const spmf_adam_args* adamp = a->adam_lr > 0.f ? &adam : nullptr;
 
   if (multi) {
     CUDA_TRY(cudaEventRecord((cudaEvent_t)a->ev_fork, caller));
@@ -62,7 +55,7 @@ int spmf_advi_step(const spmf_step_args* a) {
     }
     STEP_TRY(spmf_backward_pre(a->params, a->noise, a->dgda, a->eta, D, K, S, (float)a->nrows, a->u_tau_scale,
                                a->s_tau_scale, a->decay, a->w_entropy, a->w_prior, a->world_size, a->grads,
-                               a->scr_f, a->scr_dpre, adamp, side));
+                               a->scr_f, a->scr_dpre, side));
   }
   if (side != hot) CUDA_TRY(cudaEventRecord((cudaEvent_t)a->ev_join, side));
   // (tile mode with auxiliary streams: the fp64 operand sums are first read by spmf_rows_finish, so
@@ -204,13 +197,20 @@ int spmf_advi_step(const spmf_step_args* a) {
     STEP_TRY(spmf_backward_post(a->params, a->noise, a->eta, hybrid ? a->rank : nullptr, D, K, S, a->GAp, a->GEV,
                                 a->Gph, a->zcolsum, a->datasums, a->phisum, (float)a->nrows, a->u_tau_scale,
                                 a->s_tau_scale, a->decay, a->w_entropy, a->w_prior, a->world_size, a->grads,
-                                a->parts, a->scr_f, a->scr_dpre, a->gs, adamp, hot));
+                                a->parts, a->scr_f, a->scr_dpre, a->gs, hot));
   else
     STEP_TRY(spmf_backward_params_ranked(a->params, a->noise, a->dgda, a->eta, hybrid ? a->rank : nullptr, D, K, S,
                                          a->GAp, a->GEV, a->Gph, a->zcolsum, a->datasums, a->phisum,
                                          (float)a->nrows, a->u_tau_scale, a->s_tau_scale, a->decay, a->w_entropy,
                                          a->w_prior, a->world_size, a->grads, a->parts, a->scr_f, a->scr_d, a->gs,
-                                         adamp, hot));
+                                         hot));
+  if (a->adam_lr > 0.f) {
+    if (a->world_size > 1) return SPMF_ERR_BAD_ARG;      // the all-reduce must come between backward and Adam
+    // the scalar slack inside the gradient block is host-side bookkeeping, not a parameter gradient
+    CUDA_TRY(cudaMemsetAsync(a->grads + a->comm_off, 0, (size_t)a->comm_slack * sizeof(float), hot));
+    STEP_TRY(spmf_adam_step(a->params, a->grads, a->adam_m, a->adam_v, a->n_params, a->adam_lr, a->adam_beta1,
+                            a->adam_beta2, a->adam_eps, a->adam_t, a->clip_value, 1.0f, hot));
+  }
   if (hot != caller) {
     CUDA_TRY(cudaEventRecord((cudaEvent_t)a->ev_done, hot));
     CUDA_TRY(cudaStreamWaitEvent(caller, (cudaEvent_t)a->ev_done, 0));

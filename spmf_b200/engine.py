@@ -285,7 +285,7 @@ class AdviEngine:
                   _ptr(w.datasums), _ptr(w.phisum), float(batch_rows), self.u_tau_scale,
                   self.s_tau_scale, self.decay, self.entropy_weight, self.prior_weight,
                   self.world_size, _ptr(self.grads), _ptr(w.parts), _ptr(w.scr_f), _ptr(w.scr_d),
-                  _ptr(self.gs), None, _stream())
+                  _ptr(self.gs), _stream())
         self.launches += 9
 
     def _mark(self, name, start):
@@ -337,6 +337,19 @@ class AdviEngine:
             self._args = a
         return self._args
 
+    def prepare_batch(self, batch: DeviceBatch):
+        """Build (once) the form of `batch` this engine's step reads: the hybrid form (ranked CSR/CSC + dense
+        bf16 hot block) or the plain CSC copy.  step() does it on first use; resident training loops call
+        this up front so that no step pays for it."""
+        hybrid = (self.link == 0 and self.hot_cols > 0 and self.hybrid_ok and self.rank is not None
+                  and batch.nnz > 0)
+        if hybrid:
+            batch.ensure_hot(self.rank, self.hot_cols, hot_csc=(self.hot_mode != 2),
+                             version=getattr(self, "rank_version", 0))
+        elif self.link == 0:
+            batch.ensure_csc()
+        return hybrid
+
     def step(self, batch: DeviceBatch, fresh_noise=True, lr=None, clip_value=0.0, beta1=0.9, beta2=0.999,
              eps=1e-7):
         """ONE native call: noise -> operands -> row pass -> column pass -> backward (-> Adam when `lr`
@@ -380,10 +393,9 @@ class AdviEngine:
             a.rowptr, a.cols, a.vals = _ptr(batch.rowptr), _ptr(batch.cols), _ptr(batch.vals)
             a.colptr, a.crows, a.cvals = _ptr(batch.colptr), _ptr(batch.crows), _ptr(batch.cvals)
             a.rank, a.hot_cols = None, 0
-        # Adam runs inside the backward kernels; with several ranks the all-reduced block (v, w, u, s) is
-        # stepped after the collective (finish_step) while the 16 replicated tensors are stepped here
+        # one rank: Adam ends the native step; several ranks: it follows the all-reduce (parallel.allreduce_step)
         do_adam = lr is not None
-        a.adam_lr = float(lr) if do_adam else 0.0
+        a.adam_lr = float(lr) if (do_adam and self.world_size == 1) else 0.0
         a.adam_beta1, a.adam_beta2, a.adam_eps, a.clip_value = beta1, beta2, eps, float(clip_value)
         a.adam_t = self.opt_step + 1
         a.caller_stream = _stream()
@@ -423,7 +435,7 @@ class AdviEngine:
             base += 6              # scatter (2), encode, two conditional row passes, zeroing -- minus nothing
         elif xd is not None:
             base += 2              # the two conditional guard launches
-        self.launches += base + ((7 if self.hot_mode == 2 else 5) if hybrid else 0)
+        self.launches += base + (1 if a.adam_lr > 0 else 0) + ((7 if self.hot_mode == 2 else 5) if hybrid else 0)
         return w.parts.view(self.S, _abi.NUM_PARTS)
 
     def loss_and_grad(self, batch: DeviceBatch, fresh_noise=True, variant=0):
@@ -436,12 +448,12 @@ class AdviEngine:
         parts = self.ws.parts.view(self.S, _abi.NUM_PARTS) if parts is None else parts
         return parts[:, 15].mean()
 
-    def adam_args(self, n_step=None, defer_data=False):
+    def adam_args(self, n_step=None):
         """spmf_adam_args of the optimiser step the last `step(lr=...)` call took (multi-GPU tail)."""
         lr, b1, b2, eps, clip = self._last_adam
         a = _abi.AdamArgs()
         a.lr, a.beta1, a.beta2, a.eps, a.clip_value, a.grad_scale = lr, b1, b2, eps, clip, 1.0
-        a.step, a.defer_data = int(self.opt_step if n_step is None else n_step), int(defer_data)
+        a.step = int(self.opt_step if n_step is None else n_step)
         a.params, a.m, a.v = _ptr(self.params), _ptr(self.adam_m), _ptr(self.adam_v)
         return a
 

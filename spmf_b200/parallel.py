@@ -45,8 +45,8 @@ def unpack_data_parts(eng, parts):
 
 def allreduce_step(eng, parts, group=None, adam=False):
     """All-reduce gradients + data parts in one collective; returns the global loss (0-d tensor).
-    adam=True: the optimiser step of the all-reduced block (v, w, u, s) rides in the same launch as the
-    post-collective bookkeeping (the 16 replicated tensors were stepped inside the backward kernels)."""
+    adam=True: the optimiser step (all 24 tensors; the 16 replicated ones are bit-identical on every rank)
+    rides in the same launch as the post-collective bookkeeping."""
     dist.all_reduce(comm_block(eng), op=dist.ReduceOp.SUM, group=group)
     dev = getattr(eng, "device", None)
     if adam and dev is not None and dev.type == "cuda" and eng.S <= 64:
@@ -57,7 +57,7 @@ def allreduce_step(eng, parts, group=None, adam=False):
         slack = eng.grads[L.comm_off: L.comm_off + L.comm_slack]
         a = eng.adam_args()
         _abi.call("spmf_unpack_adam", slack.data_ptr(), L.comm_slack, eng.S, eng.entropy_weight, eng.prior_weight,
-                  parts.data_ptr(), eng._loss_buf.data_ptr(), eng.grads.data_ptr(), L.comm_off, C.byref(a),
+                  parts.data_ptr(), eng._loss_buf.data_ptr(), eng.grads.data_ptr(), L.n_params, C.byref(a),
                   torch.cuda.current_stream().cuda_stream)
         eng.launches += 1
         return eng._loss_buf[0]

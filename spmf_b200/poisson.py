@@ -131,13 +131,15 @@ class PoissonFactorization:
                  horshoe_plus=True, column_norms=None, count_key='counts',
                  initialize_distributions=True, dtype=torch.float32, device=None,
                  entropy_weight=1.0, prior_weight=1.0, seed=0, process_group=None, hot_density=None,
-                 exact_guard=True, **kwargs):
+                 exact_guard=None, **kwargs):
         if encoder_function is not None or decoder_function is not None:
             raise _abi.SpmfError("custom encoder/decoder callables have no CUDA path (the linear and "
                                  "log_transform pairs of poisson.py:34-54 are built in)")
         if not horshoe_plus:
             raise _abi.SpmfError("horshoe_plus=False (AbsHorseshoe priors) has no CUDA path")
         self.link = self._link_id(bool(log_transform))
+        if exact_guard is None:
+            exact_guard = os.environ.get("SPMF_EXACT_GUARD", "1") != "0"
         self.exact_guard = bool(exact_guard)
         if feature_dim is None:
             raise ValueError("feature_dim is required")

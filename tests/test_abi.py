@@ -62,7 +62,7 @@ def test_bad_arguments_are_rejected():
         _abi.call("spmf_csr_rows", *([None] * 5), 1.0, 1, 4, 10, 2, 1, *([None] * 7), 0, None, None)
     with pytest.raises(_abi.SpmfError):       # dense-link entry points validate the same way
         _abi.call("spmf_dense_rows", *([None] * 3), 1.0, 1, 4, 10, 2, 1, 1, 0, 0, *([None] * 7))
-    assert _abi._lib.spmf_guard_state_bytes() == 16
+    assert _abi._lib.spmf_guard_state_bytes() == 24
 
 
 def test_no_cpu_fallback():
