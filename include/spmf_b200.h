@@ -274,6 +274,24 @@ int spmf_csr_to_csc_part(const long long* rowptr, const int* rowmid, int part, c
                          int nrows, int D, int* colptr, int* rows_out, float* vals_out, int* scratch,
                          void* stream);
 
+/* ---- per-step scalars on the device (CUDA-graph replay of a step) ----
+ * A captured step freezes its kernel arguments, so what changes per step (Philox step, Adam step / rates)
+ * is read from a small device struct (spmf_step_state_bytes()) by the `_dev` variants below; a NULL state
+ * means "use the arguments".  spmf_step_state_set is the kernel that writes it. */
+int spmf_step_state_bytes(void);
+int spmf_step_state_set(void* step_state, unsigned int rng_step, int adam_t, float lr, float beta1, float beta2,
+                        float eps, float clip_value, void* stream);
+const void* spmf_step_state_kernel_ptr(void);
+int spmf_step_state_value(unsigned int rng_step, int adam_t, float lr, float beta1, float beta2, float eps,
+                          float clip_value, void* out36);
+int spmf_fill_noise_dev(float* noise, const float* params, int D, int K, int S, unsigned long long seed,
+                        unsigned int step, int which, const void* step_state, void* stream);
+int spmf_gamma_draw_grad_dev(const float* params, float* noise, float* dgda, int D, int K, int S,
+                             unsigned long long seed, unsigned int step, const void* step_state, void* stream);
+int spmf_adam_step_dev(float* params, const float* grads, float* m, float* v, long long n, float lr, float beta1,
+                       float beta2, float eps, int step, float clip_value, float grad_scale,
+                       const void* step_state, void* stream);
+
 /* ---- one call per step / per uploaded batch ----
  * spmf_advi_step issues the whole sequence above (noise, Gamma gradients, operands, row pass, sums,
  * column pass, backward, optional Adam) from native code.  Streams: `caller_stream` is the stream
@@ -349,8 +367,19 @@ typedef struct spmf_step_args {
   void* gs;
   float* xdense;
   const float* xdense_in;
+  /* optional device step state (spmf_step_state_bytes()): when given, the step starts by writing
+   * (rng_step, adam_t, adam_*) into it and the noise / Adam kernels read it -- required for graph replay */
+  void* step_state;
 } spmf_step_args;
 int spmf_advi_step(const spmf_step_args* args);
+/* Replay of a whole step as ONE CUDA graph launch (all streams, events and kernels of spmf_advi_step):
+ * create captures the sequence for one argument block (pointers, sizes and flags are frozen; args->step_state
+ * must be set; kernel-timing events must be NULL), launch updates the per-step scalars and replays it
+ * on `stream`.  The handle is owned by the caller.  Typical use: one graph per resident batch. */
+int spmf_step_graph_create(const spmf_step_args* args, void** handle);
+int spmf_step_graph_launch(void* handle, unsigned int rng_step, int adam_t, float lr, float beta1, float beta2,
+                           float eps, float clip_value, void* stream);
+int spmf_step_graph_destroy(void* handle);
 /* widen a compact batch (either 16-bit source may be NULL), build its row constants and CSC copy */
 int spmf_prepare_batch(const unsigned short* cols16, const unsigned short* vals16, const long long* rowptr,
                        int* cols, float* vals, int nrows, long long nnz, int D, float* rowsum, float* lgam,

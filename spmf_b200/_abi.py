@@ -140,11 +140,21 @@ class StepArgs(C.Structure):
                             "ev_gemm0", "ev_gemm1", "aux_stream1", "aux_stream2", "ev_aux_fork", "ev_aux_join1",
                             "ev_aux_join2")]
         + [("hot_mode", i32), ("EVt", p), ("ev_tile0", p), ("ev_tile1", p), ("scr_dpre", p), ("ev_noise", p)]
-        + [("link", i32), ("gs", p), ("xdense", p), ("xdense_in", p)]
+        + [("link", i32), ("gs", p), ("xdense", p), ("xdense_in", p), ("step_state", p)]
     )
 
 
 _SIGS["spmf_advi_step"] = (i32, [C.POINTER(StepArgs)])
+_SIGS["spmf_step_graph_create"] = (i32, [C.POINTER(StepArgs), C.POINTER(p)])
+_SIGS["spmf_step_graph_launch"] = (i32, [p, u32, i32, f32, f32, f32, f32, f32, p])
+_SIGS["spmf_step_graph_destroy"] = (i32, [p])
+_SIGS["spmf_step_state_bytes"] = (i32, [])
+_SIGS["spmf_step_state_set"] = (i32, [p, u32, i32, f32, f32, f32, f32, f32, p])
+_SIGS["spmf_step_state_kernel_ptr"] = (p, [])
+_SIGS["spmf_step_state_value"] = (i32, [u32, i32, f32, f32, f32, f32, f32, p])
+_SIGS["spmf_fill_noise_dev"] = (i32, [p, p, i32, i32, i32, u64, u32, i32, p, p])
+_SIGS["spmf_gamma_draw_grad_dev"] = (i32, [p, p, p, i32, i32, i32, u64, u32, p, p])
+_SIGS["spmf_adam_step_dev"] = (i32, [p, p, p, p, i64, f32, f32, f32, f32, i32, f32, f32, p, p])
 _SIGS["spmf_prepare_batch"] = (i32, [p, p, p, p, p, i32, i64, i32, p, p, p, p, p, p, p])
 
 EXPORTS = tuple(_SIGS)

@@ -65,6 +65,17 @@ struct Hyper {
   float batch_rows;  // rows in this rank's minibatch (closed-form -B term of dphi)
 };
 
+// ---------------- per-step scalars on the device ----------------
+// What changes from one step to the next (Philox step, optimiser step and rates) lives in device memory
+// when the step is replayed as a CUDA graph: kernel arguments of a graph are frozen at capture, so the
+// kernels read these from `StepState` instead (written by the first node of the graph, whose argument is
+// the only thing updated per launch).  NULL state pointer = use the launch arguments.
+struct StepState {
+  unsigned rng_step;
+  int adam_t;
+  float lr, b1, b2, eps, bc1, bc2, clip;
+};
+
 // ---------------- Adam [EXT L4: tf.optimizers.Adam in bayesianquilts' loop] ----------------
 // m, v = first / second moments; bc1, bc2 = 1 - beta^t; a non-finite gradient is dropped, `clip` > 0 clips
 // the gradient by value.  lr <= 0: off.  (Fusing this into the backward kernels was tried in round 2

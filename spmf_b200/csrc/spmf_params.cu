@@ -10,6 +10,7 @@
 //   tf.GradientTape backward + Adam             [EXT L4]
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 
 #include "../../include/spmf_b200.h"
 #include "spmf_guard.cuh"
@@ -33,7 +34,8 @@ __device__ __forceinline__ float warp_sum(float v) {
 // ------------------------------------------------------------------ noise
 // Normal variables (blockIdx.y = v,w,u,s): 4 normals per Philox call; element e -> (call e/4, slot e%4).
 __global__ void fill_normal_kernel(Layout L, float* __restrict__ noise, uint32_t step, uint32_t k0,
-                                   uint32_t k1) {
+                                   uint32_t k1, const StepState* __restrict__ sst) {
+  if (sst) step = sst->rng_step;
   const int v = blockIdx.y;
   const long long n = L.vsize[v] * L.S;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -59,7 +61,8 @@ __global__ void fill_normal_kernel(Layout L, float* __restrict__ noise, uint32_t
 // queued in shared memory and worked off by the whole CTA with (nearly) full warps.
 __global__ void __launch_bounds__(128)
 gamma_kernel(Layout L, const float* __restrict__ P, float* __restrict__ N, float* __restrict__ G,
-             int draw, int grad, uint32_t step, uint32_t k0, uint32_t k1) {
+             int draw, int grad, uint32_t step, uint32_t k0, uint32_t k1, const StepState* __restrict__ sst) {
+  if (sst) step = sst->rng_step;
   __shared__ float4 cfq[128 * 4];              // (alpha, digamma(alpha), draw, slot = draw index * 128 + thread)
   __shared__ int cfn;
   const int v = VAR_UETA + blockIdx.y;
@@ -614,9 +617,11 @@ __global__ void unpack_adam_kernel(int S, double w_entropy, double w_prior, floa
 // ------------------------------------------------------------------ Adam  [EXT L4]
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, long long n, float lr, float b1, float b2, float eps,
-                            float bc1, float bc2, float clip_value, float grad_scale) {
+                            float bc1, float bc2, float clip_value, float grad_scale,
+                            const StepState* __restrict__ sst) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  if (sst) { lr = sst->lr; b1 = sst->b1; b2 = sst->b2; eps = sst->eps; bc1 = sst->bc1; bc2 = sst->bc2; clip_value = sst->clip; }
   float gi = g[i] * grad_scale;
   if (!isfinite(gi)) gi = 0.f;                 // non-finite gradients are dropped, not propagated
   if (clip_value > 0.f) gi = fminf(fmaxf(gi, -clip_value), clip_value);
@@ -626,6 +631,8 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   v[i] = vi;
   p[i] -= lr * (mi / bc1) / (sqrtf(vi / bc2) + eps);
 }
+
+__global__ void step_state_kernel(StepState* dst, StepState v) { *dst = v; }
 
 // sum of squares (double) of a float vector, deterministic two-stage via reduce_rows
 __global__ void square_kernel(const float* __restrict__ g, float* __restrict__ out, long long n) {
@@ -767,6 +774,12 @@ int spmf_layout(int D, int K, int S, long long* tensor_offsets, long long* noise
 
 int spmf_fill_noise(float* noise, const float* params, int D, int K, int S, unsigned long long seed,
                     unsigned int step, int which, void* stream) {
+  return spmf_fill_noise_dev(noise, params, D, K, S, seed, step, which, nullptr, stream);
+}
+
+int spmf_fill_noise_dev(float* noise, const float* params, int D, int K, int S, unsigned long long seed,
+                        unsigned int step, int which, const void* step_state, void* stream) {
+  const StepState* sst = (const StepState*)step_state;
   if (!noise || !params || D <= 0 || K <= 0 || S <= 0 || K > SPMF_MAX_K || !(which & 3)) return SPMF_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   Layout L = make_layout(D, K, S);
@@ -775,12 +788,12 @@ int spmf_fill_noise(float* noise, const float* params, int D, int K, int S, unsi
   if (nmax < 2LL * D * S) nmax = 2LL * D * S;
   if (which & SPMF_NOISE_NORMAL) {
     dim3 grid((unsigned)(((nmax + 3) / 4 + 255) / 256), VAR_S + 1);
-    fill_normal_kernel<<<grid, 256, 0, st>>>(L, noise, step, k0, k1);
+    fill_normal_kernel<<<grid, 256, 0, st>>>(L, noise, step, k0, k1, sst);
   }
   if (which & SPMF_NOISE_GAMMA) {
     long long emax = (long long)D * K > 2LL * D ? (long long)D * K : 2LL * D;
     dim3 grid((unsigned)((emax + 127) / 128), NUM_VARS - VAR_UETA);
-    gamma_kernel<<<grid, 128, 0, st>>>(L, params, noise, noise, 1, 0, step, k0, k1);
+    gamma_kernel<<<grid, 128, 0, st>>>(L, params, noise, noise, 1, 0, step, k0, k1, sst);
   }
   SPMF_CHECK_LAUNCH();
   return SPMF_OK;
@@ -836,7 +849,7 @@ int spmf_gamma_grad(const float* params, const float* noise, int D, int K, int S
   Layout L = make_layout(D, K, S);
   long long emax = (long long)D * K > 2LL * D ? (long long)D * K : 2LL * D;
   dim3 grid((unsigned)((emax + 127) / 128), NUM_VARS - VAR_UETA);
-  gamma_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(L, params, const_cast<float*>(noise), dgda, 0, 1, 0, 0, 0);
+  gamma_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(L, params, const_cast<float*>(noise), dgda, 0, 1, 0, 0, 0, nullptr);
   SPMF_CHECK_LAUNCH();
   return SPMF_OK;
 }
@@ -844,12 +857,18 @@ int spmf_gamma_grad(const float* params, const float* noise, int D, int K, int S
 /* Gamma draws and their implicit gradients in one pass (what a training step uses). */
 int spmf_gamma_draw_grad(const float* params, float* noise, float* dgda, int D, int K, int S,
                          unsigned long long seed, unsigned int step, void* stream) {
+  return spmf_gamma_draw_grad_dev(params, noise, dgda, D, K, S, seed, step, nullptr, stream);
+}
+
+int spmf_gamma_draw_grad_dev(const float* params, float* noise, float* dgda, int D, int K, int S,
+                             unsigned long long seed, unsigned int step, const void* step_state, void* stream) {
   if (!params || !noise || !dgda || D <= 0 || K <= 0 || S <= 0 || K > SPMF_MAX_K) return SPMF_ERR_BAD_ARG;
   Layout L = make_layout(D, K, S);
   long long emax = (long long)D * K > 2LL * D ? (long long)D * K : 2LL * D;
   dim3 grid((unsigned)((emax + 127) / 128), NUM_VARS - VAR_UETA);
   gamma_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(L, params, noise, dgda, 1, 1, step,
-                                                      (uint32_t)(seed & 0xffffffffu), (uint32_t)(seed >> 32));
+                                                      (uint32_t)(seed & 0xffffffffu), (uint32_t)(seed >> 32),
+                                                      (const StepState*)step_state);
   SPMF_CHECK_LAUNCH();
   return SPMF_OK;
 }
@@ -985,9 +1004,47 @@ long long spmf_backward_scratch_doubles(int D, int K, int S) {
 int spmf_adam_step(float* params, const float* grads, float* m, float* v, long long n, float lr,
                    float beta1, float beta2, float eps, int step, float clip_value, float grad_scale,
                    void* stream) {
-  if (!params || !grads || !m || !v || n <= 0 || step <= 0) return SPMF_ERR_BAD_ARG;
-  float bc1 = 1.f - powf(beta1, (float)step), bc2 = 1.f - powf(beta2, (float)step);
-  adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(params, grads, m, v, n, lr, beta1, beta2, eps, bc1, bc2, clip_value, grad_scale);
+  return spmf_adam_step_dev(params, grads, m, v, n, lr, beta1, beta2, eps, step, clip_value, grad_scale, nullptr, stream);
+}
+
+int spmf_step_state_bytes(void) { return (int)sizeof(StepState); }
+
+/* host-side value of the per-step device scalars (what the first node of a step graph writes) */
+static StepState make_step_state(unsigned rng_step, int adam_t, float lr, float b1, float b2, float eps, float clip) {
+  StepState v;
+  v.rng_step = rng_step; v.adam_t = adam_t; v.lr = lr; v.b1 = b1; v.b2 = b2; v.eps = eps; v.clip = clip;
+  const int t = adam_t > 0 ? adam_t : 1;
+  v.bc1 = 1.f - powf(b1, (float)t);
+  v.bc2 = 1.f - powf(b2, (float)t);
+  return v;
+}
+
+int spmf_step_state_set(void* step_state, unsigned int rng_step, int adam_t, float lr, float beta1, float beta2,
+                        float eps, float clip_value, void* stream) {
+  if (!step_state) return SPMF_ERR_BAD_ARG;
+  step_state_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((StepState*)step_state,
+                                                       make_step_state(rng_step, adam_t, lr, beta1, beta2, eps, clip_value));
+  SPMF_CHECK_LAUNCH();
+  return SPMF_OK;
+}
+
+/* the kernel and the argument image of spmf_step_state_set, for graph node updates (spmf_step.cu) */
+const void* spmf_step_state_kernel_ptr(void) { return (const void*)step_state_kernel; }
+int spmf_step_state_value(unsigned int rng_step, int adam_t, float lr, float beta1, float beta2, float eps,
+                          float clip_value, void* out36) {
+  if (!out36) return SPMF_ERR_BAD_ARG;
+  const StepState v = make_step_state(rng_step, adam_t, lr, beta1, beta2, eps, clip_value);
+  memcpy(out36, &v, sizeof(v));
+  return SPMF_OK;
+}
+
+int spmf_adam_step_dev(float* params, const float* grads, float* m, float* v, long long n, float lr,
+                       float beta1, float beta2, float eps, int step, float clip_value, float grad_scale,
+                       const void* step_state, void* stream) {
+  if (!params || !grads || !m || !v || n <= 0 || (step <= 0 && !step_state)) return SPMF_ERR_BAD_ARG;
+  const int t = step > 0 ? step : 1;
+  float bc1 = 1.f - powf(beta1, (float)t), bc2 = 1.f - powf(beta2, (float)t);
+  adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(params, grads, m, v, n, lr, beta1, beta2, eps, bc1, bc2, clip_value, grad_scale, (const StepState*)step_state);
   SPMF_CHECK_LAUNCH();
   return SPMF_OK;
 }

@@ -30,6 +30,10 @@ int spmf_advi_step(const spmf_step_args* a) {
   if (multi && (!a->ev_fork || !a->ev_join || !a->ev_done)) return SPMF_ERR_BAD_ARG;
   const int D = a->D, K = a->K, S = a->S;
 
+  // per-step scalars to the device first (graph replay updates this one node's argument)
+  if (a->step_state)
+    STEP_TRY(spmf_step_state_set(a->step_state, a->rng_step, a->adam_t, a->adam_lr, a->adam_beta1, a->adam_beta2,
+                                 a->adam_eps, a->clip_value, caller));
   if (multi) {
     CUDA_TRY(cudaEventRecord((cudaEvent_t)a->ev_fork, caller));
     if (hot != caller) CUDA_TRY(cudaStreamWaitEvent(hot, (cudaEvent_t)a->ev_fork, 0));
@@ -37,7 +41,7 @@ int spmf_advi_step(const spmf_step_args* a) {
   }
   // ---- Gamma draws + implicit gradients: only the backward needs them (side stream)
   if (a->fresh_noise)
-    STEP_TRY(spmf_gamma_draw_grad(a->params, a->noise, a->dgda, D, K, S, a->seed, a->rng_step, side));
+    STEP_TRY(spmf_gamma_draw_grad_dev(a->params, a->noise, a->dgda, D, K, S, a->seed, a->rng_step, a->step_state, side));
   else
     STEP_TRY(spmf_gamma_grad(a->params, a->noise, D, K, S, a->dgda, side));
   // ---- hot path
@@ -45,7 +49,8 @@ int spmf_advi_step(const spmf_step_args* a) {
   if (hybrid && (!a->rank || !a->rowmid || !a->xhot || !a->ApT3 || !a->dzrT3)) return SPMF_ERR_BAD_ARG;
   if (hybrid && a->hot_mode != 2 && (!a->hot_colptr || !a->hot_crows || !a->hot_cvals)) return SPMF_ERR_BAD_ARG;
   if (a->fresh_noise)
-    STEP_TRY(spmf_fill_noise(a->noise, a->params, D, K, S, a->seed, a->rng_step, SPMF_NOISE_NORMAL, hot));
+    STEP_TRY(spmf_fill_noise_dev(a->noise, a->params, D, K, S, a->seed, a->rng_step, SPMF_NOISE_NORMAL, a->step_state,
+                                 hot));
   // data-independent half of the backward: needs the noise only -> side stream, under the data term
   const bool split_bwd = a->scr_dpre && (side == hot || a->ev_noise);
   if (split_bwd) {
@@ -208,13 +213,92 @@ int spmf_advi_step(const spmf_step_args* a) {
     if (a->world_size > 1) return SPMF_ERR_BAD_ARG;      // the all-reduce must come between backward and Adam
     // the scalar slack inside the gradient block is host-side bookkeeping, not a parameter gradient
     CUDA_TRY(cudaMemsetAsync(a->grads + a->comm_off, 0, (size_t)a->comm_slack * sizeof(float), hot));
-    STEP_TRY(spmf_adam_step(a->params, a->grads, a->adam_m, a->adam_v, a->n_params, a->adam_lr, a->adam_beta1,
-                            a->adam_beta2, a->adam_eps, a->adam_t, a->clip_value, 1.0f, hot));
+    STEP_TRY(spmf_adam_step_dev(a->params, a->grads, a->adam_m, a->adam_v, a->n_params, a->adam_lr, a->adam_beta1,
+                                a->adam_beta2, a->adam_eps, a->adam_t, a->clip_value, 1.0f, a->step_state, hot));
   }
   if (hot != caller) {
     CUDA_TRY(cudaEventRecord((cudaEvent_t)a->ev_done, hot));
     CUDA_TRY(cudaStreamWaitEvent(caller, (cudaEvent_t)a->ev_done, 0));
   }
+  return SPMF_OK;
+}
+
+// ---- graph replay ------------------------------------------------------------------------------------
+struct StepGraph {
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  cudaGraphNode_t state_node = nullptr;
+  cudaKernelNodeParams state_params{};
+  void* state_dst = nullptr;
+};
+
+int spmf_step_graph_create(const spmf_step_args* a, void** handle) {
+  if (!a || !handle || !a->step_state || !a->caller_stream) return SPMF_ERR_BAD_ARG;
+  if (a->ev_rows0 || a->ev_rows1 || a->ev_cols0 || a->ev_cols1 || a->ev_gemm0 || a->ev_gemm1 || a->ev_tile0 ||
+      a->ev_tile1)
+    return SPMF_ERR_BAD_ARG;                      // timing events are recorded outside graphs only
+  cudaStream_t caller = (cudaStream_t)a->caller_stream;
+  StepGraph* g = new StepGraph();
+  cudaError_t e = cudaStreamBeginCapture(caller, cudaStreamCaptureModeThreadLocal);
+  if (e != cudaSuccess) { delete g; return (int)e; }
+  const int rc = spmf_advi_step(a);
+  e = cudaStreamEndCapture(caller, &g->graph);
+  if (rc != SPMF_OK || e != cudaSuccess || !g->graph) {
+    if (g->graph) cudaGraphDestroy(g->graph);
+    delete g;
+    cudaGetLastError();
+    return rc != SPMF_OK ? rc : (e != cudaSuccess ? (int)e : SPMF_ERR_UNSUPPORTED);
+  }
+  // the node that writes the per-step scalars: the only one whose argument changes between launches
+  size_t n = 0;
+  cudaGraphGetNodes(g->graph, nullptr, &n);
+  cudaGraphNode_t* nodes = new cudaGraphNode_t[n ? n : 1];
+  cudaGraphGetNodes(g->graph, nodes, &n);
+  const void* want = spmf_step_state_kernel_ptr();
+  for (size_t i = 0; i < n && !g->state_node; ++i) {
+    cudaGraphNodeType t;
+    if (cudaGraphNodeGetType(nodes[i], &t) != cudaSuccess || t != cudaGraphNodeTypeKernel) continue;
+    cudaKernelNodeParams p{};
+    if (cudaGraphKernelNodeGetParams(nodes[i], &p) == cudaSuccess && p.func == want) {
+      g->state_node = nodes[i];
+      g->state_params = p;
+    }
+  }
+  delete[] nodes;
+  g->state_dst = a->step_state;
+  e = g->state_node ? cudaGraphInstantiate(&g->exec, g->graph, 0) : cudaErrorInvalidValue;
+  if (e != cudaSuccess) {
+    cudaGraphDestroy(g->graph);
+    delete g;
+    cudaGetLastError();
+    return (int)e;
+  }
+  *handle = g;
+  return SPMF_OK;
+}
+
+int spmf_step_graph_launch(void* handle, unsigned int rng_step, int adam_t, float lr, float beta1, float beta2,
+                           float eps, float clip_value, void* stream) {
+  StepGraph* g = (StepGraph*)handle;
+  if (!g || !g->exec) return SPMF_ERR_BAD_ARG;
+  alignas(8) unsigned char value[64];
+  STEP_TRY(spmf_step_state_value(rng_step, adam_t, lr, beta1, beta2, eps, clip_value, value));
+  void* dst = g->state_dst;
+  void* kargs[2] = {&dst, value};
+  cudaKernelNodeParams p = g->state_params;
+  p.kernelParams = kargs;
+  p.extra = nullptr;
+  CUDA_TRY(cudaGraphExecKernelNodeSetParams(g->exec, g->state_node, &p));
+  CUDA_TRY(cudaGraphLaunch(g->exec, (cudaStream_t)stream));
+  return SPMF_OK;
+}
+
+int spmf_step_graph_destroy(void* handle) {
+  StepGraph* g = (StepGraph*)handle;
+  if (!g) return SPMF_OK;
+  if (g->exec) cudaGraphExecDestroy(g->exec);
+  if (g->graph) cudaGraphDestroy(g->graph);
+  delete g;
   return SPMF_OK;
 }
 

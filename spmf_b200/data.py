@@ -185,6 +185,7 @@ class CsrShard:
                         nrows=int(nrows), nnz=nnz, D=self.D)
         if cache:
             self._batches[key] = b
+            b._resident = True          # same object / device arrays every epoch: its step may be replayed as a graph
         return b
 
     def num_batches(self, batch_rows, drop_remainder=False):

@@ -86,6 +86,25 @@ class StepWorkspace:
         self.rowacc = torch.empty(self.NQ * nrows * 4 * self.SV, dtype=torch.float32, device=self.device)
 
 
+class _StepGraphs:
+    """CUDA-graph replays of the native step for ONE resident batch (spmf_step_graph_*): key -> handle.
+    Handles are destroyed with the batch."""
+
+    def __init__(self):
+        self.handles = {}
+
+    def drop(self, keep_gen):
+        for key in [k for k in self.handles if k[1] != keep_gen]:
+            _abi._lib.spmf_step_graph_destroy(self.handles.pop(key))
+
+    def __del__(self):
+        try:
+            for h in self.handles.values():
+                _abi._lib.spmf_step_graph_destroy(h)
+        except Exception:
+            pass
+
+
 class AdviEngine:
     """ELBO + gradient of one minibatch; optimiser state; everything stays on the device."""
 
@@ -124,6 +143,14 @@ class AdviEngine:
         # device guard state (poisson.py:606-616): flag | nbad | (min finite log-likelihood, entry)
         self.gs = torch.zeros(int(_abi._lib.spmf_guard_state_bytes()), dtype=torch.uint8, device=self.device)
         self.reset_guard()
+        # per-step scalars on the device (Philox step, Adam step / rates): what a replayed graph reads
+        self.step_state = torch.zeros(max(int(_abi._lib.spmf_step_state_bytes()), 64), dtype=torch.uint8,
+                                      device=self.device)
+        # replay resident batches as ONE CUDA graph launch per step (SPMF_GRAPHS=0: always launch eagerly)
+        self.use_graphs = os.environ.get("SPMF_GRAPHS", "1") != "0"
+        self._ws_gen = 0                  # bumped whenever a workspace buffer moves: invalidates graphs
+        self._warm_cfgs = set()
+        self.graph_launches = 0
         self.rank = None          # int32 [D]: table row of each feature (hot-column ordering), or None
         self.hot_cols = 0         # H > 0 enables the hybrid (tensor-core hot block + gather) step
         cap = int(_abi._lib.spmf_hybrid_supported(self.K, self.S)) if self.link == 0 else 0
@@ -359,6 +386,7 @@ class AdviEngine:
         if batch.nrows > w.max_rows:
             w.ensure_rows(batch.nrows)
             self._args = None
+            self._ws_gen += 1
         hybrid = (self.link == 0 and self.hot_cols > 0 and self.hybrid_ok and self.rank is not None
                   and batch.nnz > 0)
         if hybrid:
@@ -366,14 +394,19 @@ class AdviEngine:
                                  version=getattr(self, "rank_version", 0))
             if w.ensure_hybrid(self.hot_cols, batch.nrows):
                 self._args = None
+                self._ws_gen += 1
         else:
             if batch.cols is None or batch.vals is None:
                 raise _abi.SpmfError("this batch was uploaded in hybrid-only form (no CSR arrays) but the engine "
                                      f"for S={self.S} runs the gather step; upload it without a hot split")
             if self.link == 0:
                 batch.ensure_csc()
+        xd_before = getattr(w, "xdense", None)
         xd = self._guard_scratch(batch.nrows)
+        if xd is not xd_before:
+            self._ws_gen += 1
         a = self._step_args()
+        a.step_state = _ptr(self.step_state)
         a.link, a.gs, a.xdense, a.xdense_in = self.link, _ptr(self.gs), _ptr(xd), None
         a.z, a.dzr, a.rowacc = _ptr(w.z), _ptr(w.dzr), _ptr(w.rowacc)
         a.inv_xi, a.scale_rows = self.inv_xi, int(self.scale_rows)
@@ -420,7 +453,7 @@ class AdviEngine:
         else:
             a.ev_rows0 = a.ev_rows1 = a.ev_cols0 = a.ev_cols1 = a.ev_gemm0 = a.ev_gemm1 = None
             a.ev_tile0 = a.ev_tile1 = None
-        _abi.call("spmf_advi_step", a)
+        self._launch_step(a, batch, ev is None, hybrid, fresh_noise)
         if fresh_noise:
             self.rng_step += 1
         if do_adam:
@@ -437,6 +470,33 @@ class AdviEngine:
             base += 2              # the two conditional guard launches
         self.launches += base + (1 if a.adam_lr > 0 else 0) + ((7 if self.hot_mode == 2 else 5) if hybrid else 0)
         return w.parts.view(self.S, _abi.NUM_PARTS)
+
+    def _launch_step(self, a, batch, graphable, hybrid, fresh_noise):
+        """Eager native step, or -- for a RESIDENT batch (cut from a CsrShard: same object, same device
+        arrays every epoch) -- one CUDA graph launch (spmf_step_graph_launch).  The first step of every
+        configuration runs eagerly: it performs the kernels' lazy one-time initialisation, which must
+        not happen under stream capture."""
+        cfg = (int(fresh_noise), a.adam_lr > 0, bool(hybrid), int(self.hot_mode), int(self.link))
+        warm = cfg in self._warm_cfgs
+        if not (self.use_graphs and graphable and warm and getattr(batch, "_resident", False)):
+            _abi.call("spmf_advi_step", a)
+            self._warm_cfgs.add(cfg)
+            return
+        import ctypes as C
+        cache = batch.__dict__.get("_step_graphs")
+        if cache is None:
+            cache = batch.__dict__["_step_graphs"] = _StepGraphs()
+        key = (id(self), self._ws_gen) + cfg + (batch.nrows, batch.nnz, getattr(self, "rank_version", 0),
+                                                  a.inv_xi, a.scale_rows)
+        h = cache.handles.get(key)
+        if h is None:
+            cache.drop(self._ws_gen)
+            hp = C.c_void_p()
+            _abi.call("spmf_step_graph_create", a, C.byref(hp))
+            h = cache.handles[key] = hp.value
+        _abi.call("spmf_step_graph_launch", h, a.rng_step, a.adam_t, a.adam_lr, a.adam_beta1, a.adam_beta2,
+                  a.adam_eps, a.clip_value, a.caller_stream)
+        self.graph_launches += 1
 
     def loss_and_grad(self, batch: DeviceBatch, fresh_noise=True, variant=0):
         """Fills self.grads and self.ws.parts for `batch`; returns the (S,16) parts tensor (device,
