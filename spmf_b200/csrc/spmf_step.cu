@@ -232,8 +232,16 @@ struct StepGraph {
   void* state_dst = nullptr;
 };
 
-int spmf_step_graph_create(const spmf_step_args* a, void** handle) {
-  if (!a || !handle || !a->step_state || !a->caller_stream) return SPMF_ERR_BAD_ARG;
+int spmf_step_graph_create(const spmf_step_args* a_in, void** handle) {
+  if (!a_in || !handle || !a_in->step_state) return SPMF_ERR_BAD_ARG;
+  // the legacy default stream (0) cannot be captured: record the sequence with the hot stream as its
+  // origin instead (the replay may still be launched into any stream, the default one included)
+  spmf_step_args copy = *a_in;
+  if (!copy.caller_stream) {
+    if (!copy.hot_stream) return SPMF_ERR_UNSUPPORTED;
+    copy.caller_stream = copy.hot_stream;
+  }
+  const spmf_step_args* a = &copy;
   if (a->ev_rows0 || a->ev_rows1 || a->ev_cols0 || a->ev_cols1 || a->ev_gemm0 || a->ev_gemm1 || a->ev_tile0 ||
       a->ev_tile1)
     return SPMF_ERR_BAD_ARG;                      // timing events are recorded outside graphs only

@@ -146,8 +146,10 @@ class AdviEngine:
         # per-step scalars on the device (Philox step, Adam step / rates): what a replayed graph reads
         self.step_state = torch.zeros(max(int(_abi._lib.spmf_step_state_bytes()), 64), dtype=torch.uint8,
                                       device=self.device)
-        # replay resident batches as ONE CUDA graph launch per step (SPMF_GRAPHS=0: always launch eagerly)
-        self.use_graphs = os.environ.get("SPMF_GRAPHS", "1") != "0"
+        # SPMF_GRAPHS=1: replay resident batches as ONE CUDA graph launch per step.  Opt-in: measured on B200
+        # (profiles/r2_graph_replay_sweep.jsonl) the replay is no faster at C4 / C1 (the step is not
+        # launch-bound) and slower at C2 / C3, so the eager multi-stream launch stays the default.
+        self.use_graphs = os.environ.get("SPMF_GRAPHS", "0") == "1"
         self._ws_gen = 0                  # bumped whenever a workspace buffer moves: invalidates graphs
         self._warm_cfgs = set()
         self.graph_launches = 0
@@ -492,7 +494,12 @@ class AdviEngine:
         if h is None:
             cache.drop(self._ws_gen)
             hp = C.c_void_p()
-            _abi.call("spmf_step_graph_create", a, C.byref(hp))
+            rc = _abi._lib.spmf_step_graph_create(C.byref(a), C.byref(hp))
+            if rc != 0:                      # not capturable in this configuration: stay eager for good
+                self.use_graphs = False
+                self.graph_error = rc
+                _abi.call("spmf_advi_step", a)
+                return
             h = cache.handles[key] = hp.value
         _abi.call("spmf_step_graph_launch", h, a.rng_step, a.adam_t, a.adam_lr, a.adam_beta1, a.adam_beta2,
                   a.adam_eps, a.clip_value, a.caller_stream)
