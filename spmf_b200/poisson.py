@@ -425,7 +425,7 @@ class PoissonFactorization:
         (poisson.py:606-619).  Multi-rank: rows are sharded, so sums / counts are all-reduced and the
         minimum is the GLOBAL one, as the reference's single (S,B,D) tensor would give."""
         ws, S = eng.ws, eng.S
-        ds = ws.datasums.view(ws.NQ, 4, ws.SV).permute(0, 2, 1).reshape(S, 4).clone()
+        ds = ws.datasums.view(ws.NQ, 4, ws.SV).permute(0, 2, 1).reshape(S, 4).contiguous().clone()
         flag, nbad, min_val = eng.guard_report()
         dist_on = torch.distributed.is_available() and torch.distributed.is_initialized() and eng.world_size > 1
         rows = torch.tensor([float(nrows)], dtype=torch.float64, device=self.device)

@@ -98,9 +98,13 @@ def main():
         L = eng.layout
         mask = torch.ones(L.n_params, dtype=torch.bool, device=dev)
         mask[L.comm_off:L.comm_off + L.comm_slack] = False        # scalar slack is not a parameter
-        e_adam = float((upd_ref - upd_dp)[mask].abs().max() / upd_ref[mask].abs().max())
-        print(f"dp_check world={world}: 3 Adam steps, worst update rel={e_adam:.2e}")
-        ok = ok and e_adam < 2e-3 and float(upd_ref[mask].abs().max()) > 0.5 * lr
+        # Adam's first steps are sign-like (update ~ lr * g/|g|): an entry whose gradient is ~0 may flip between
+        # two summation orders, so compare robustly: almost all entries within 1 % of a step, none far off in bulk
+        diff = (upd_ref - upd_dp)[mask].abs()
+        frac_off = float((diff > 1e-2 * lr).double().mean())
+        e_adam = float(diff.median() / upd_ref[mask].abs().median())
+        print(f"dp_check world={world}: 3 Adam steps, median update rel={e_adam:.2e}, entries off by >1% of a step: {frac_off:.2e}")
+        ok = ok and e_adam < 1e-4 and frac_off < 1e-3 and float(upd_ref[mask].abs().max()) > 0.5 * lr
     # ---- exact guard across ranks: a dead column; the replacement value is the GLOBAL minimum
     from tests.test_gpu_links import _kill_column
     from tests.util import make_oracle, perturbed_params
