@@ -370,6 +370,7 @@ typedef struct spmf_step_args {
   /* optional device step state (spmf_step_state_bytes()): when given, the step starts by writing
    * (rng_step, adam_t, adam_*) into it and the noise / Adam kernels read it -- required for graph replay */
   void* step_state;
+  int model;          /* SPMF_MODEL_* */
 } spmf_step_args;
 int spmf_advi_step(const spmf_step_args* args);
 /* Replay of a whole step as ONE CUDA graph launch (all streams, events and kernels of spmf_advi_step):
@@ -384,6 +385,35 @@ int spmf_step_graph_destroy(void* handle);
 int spmf_prepare_batch(const unsigned short* cols16, const unsigned short* vals16, const long long* rowptr,
                        int* cols, float* vals, int nrows, long long nnz, int D, float* rowsum, float* lgam,
                        int* colptr, int* crows, float* cvals, int* scratch, void* stream);
+
+/* ---- model variants ----
+ * SPMF_MODEL_BERNOULLI = BernoulliFactorization (bernoulli.py:31-649): v and w use an Identity bijector and
+ * Normal(0, 0.1) / Normal(0, 1) priors (bernoulli.py:186-215) instead of Softplus + HalfNormal; everything
+ * else (horseshoe+ hierarchy on u and s, surrogate families, var_list order) is shared.  The `_m`
+ * variants take the model id; the plain entry points are the Poisson model. */
+#define SPMF_MODEL_POISSON 0
+#define SPMF_MODEL_BERNOULLI 1
+int spmf_sample_m(const float* params, const float* noise, int D, int K, int S, float* samples, int model,
+                  void* stream);
+int spmf_draw_operands_ranked_m(const float* params, const float* noise, const float* eta, const int* rank,
+                                int D, int K, int S, float* Ap, float* EV, float* PH, double* vsum,
+                                double* phisum, double* scratch, int model, void* stream);
+int spmf_backward_params_ranked_m(const float* params, const float* noise, const float* dgda, const float* eta,
+                                  const int* rank, int D, int K, int S, const float* GAp, const float* GEVnz,
+                                  const float* Gphinz, const double* zcolsum, const double* datasums,
+                                  const double* phisum, float batch_rows, float u_tau_scale, float s_tau_scale,
+                                  float decay, float w_entropy, float w_prior, int world_size, float* grads,
+                                  double* parts, float* scr_f, double* scr_d, void* gs, int model, void* stream);
+int spmf_backward_pre_m(const float* params, const float* noise, const float* dgda, const float* eta, int D, int K,
+                        int S, float batch_rows, float u_tau_scale, float s_tau_scale, float decay, float w_entropy,
+                        float w_prior, int world_size, float* grads, float* scr_f, double* scr_d, int model,
+                        void* stream);
+int spmf_backward_post_m(const float* params, const float* noise, const float* eta, const int* rank, int D, int K,
+                         int S, const float* GAp, const float* GEVnz, const float* Gphinz, const double* zcolsum,
+                         const double* datasums, const double* phisum, float batch_rows, float u_tau_scale,
+                         float s_tau_scale, float decay, float w_entropy, float w_prior, int world_size,
+                         float* grads, double* parts, float* scr_f, const double* scr_d, void* gs, int model,
+                         void* stream);
 
 /* ---- dense evaluation of the data term (csrc/spmf_dense.cu): link functions without a closed-form
  *      sum(rate) and the exact non-finite guard of poisson.py:606-616 ----

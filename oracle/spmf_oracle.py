@@ -256,6 +256,9 @@ class OraclePoissonFactorization:
                                  torch.ones_like(colmeans_nonzero))       # :142-149
         self.xi_u_global = rowmean_nonzero if self.scale_rows else torch.tensor(1.0, dtype=DTYPE)
 
+    # variables behind an Identity bijector (none here; v, w in OracleBernoulliFactorization)
+    IDENTITY_VARS = ()
+
     # ----- surrogate draws + log q  [EXT L3] -----
     def sample(self, params, noise):
         """noise[var]: (S,*shape) -- N(0,1) draws for Normal vars, standard-Gamma(alpha) draws
@@ -275,6 +278,10 @@ class OraclePoissonFactorization:
                 g = _GammaDraw.apply(conc.expand(S, *conc.shape), noise[k].to(DTYPE))
                 t = beta / g                              # tfd.InverseGamma sample = 1/Gamma(c, rate=scale)
                 base = inverse_gamma_log_prob(t, conc, beta)
+            if k in self.IDENTITY_VARS:                   # tfb.Identity: y = t, no Jacobian term
+                theta[k] = t
+                logq = logq + base.sum((-1, -2))
+                continue
             theta[k] = torch.nn.functional.softplus(t)
             logq = logq + (base - torch.nn.functional.logsigmoid(t)).sum((-1, -2))
         return theta, logq
@@ -328,6 +335,10 @@ class OraclePoissonFactorization:
             z = z * (x.sum(-1, keepdim=True) / self.xi_u_global)                  # :644-649
         return z
 
+    @staticmethod
+    def observation_log_prob(x, rate):
+        return poisson_log_prob(x, rate)                         # :178-183
+
     def log_likelihood_components(self, s, u, v, w, data, **_):
         x = torch.as_tensor(data[self.count_key]).to(DTYPE)
         theta_u = self.encode(x, u, s)                           # :170
@@ -335,7 +346,7 @@ class OraclePoissonFactorization:
         B = self.decoding_matrix(v)                              # :172
         theta_beta = self.decoder_function(torch.matmul(theta_u, B))   # :174-175
         rate = theta_beta + phi                                  # :177
-        return {'log_likelihood': poisson_log_prob(x, rate), 'rate': rate}   # :178-184
+        return {'log_likelihood': self.observation_log_prob(x, rate), 'rate': rate}   # :178-184
 
     def unormalized_log_prob_parts(self, data, prior_weight=1., **params):
         parts = self.prior_log_prob_parts(params)                # :590
@@ -378,6 +389,37 @@ class OraclePoissonFactorization:
         grads = torch.autograd.grad(loss, [leaves[n] for n in names])
         return (float(loss.detach()), {n: g for n, g in zip(names, grads)},
                 {'logq': logq.detach(), **{k: v.detach() for k, v in parts.items()}})
+
+
+def normal_log_prob(y, scale):
+    return -HALF_LOG_2PI - torch.log(scale) - 0.5 * (y / scale) ** 2
+
+
+class OracleBernoulliFactorization(OraclePoissonFactorization):
+    """Float64 restatement of mederrata_spmf/bernoulli.py::BernoulliFactorization (bernoulli.py:31-649):
+    Bernoulli-logit likelihood (:148-156), v and w behind Identity bijectors (:186-195) with Normal(0, 0.1) /
+    Normal(0, 1) priors (:200-215), encode without row scaling (:580-593), eta_i = 1 unless column norms are
+    given (:105-109).  Everything else is inherited, as in the reference."""
+
+    IDENTITY_VARS = ('v', 'w')
+
+    def __init__(self, latent_dim, feature_dim, u_tau_scale=0.01, s_tau_scale=1., symmetry_breaking_decay=0.99,
+                 log_transform=False, column_norms=None, count_key='counts'):
+        super().__init__(latent_dim, feature_dim, u_tau_scale=u_tau_scale, s_tau_scale=s_tau_scale,
+                         symmetry_breaking_decay=symmetry_breaking_decay, scale_columns=True, scale_rows=False,
+                         log_transform=log_transform, column_norms=column_norms, count_key=count_key)
+
+    def prior_log_prob_parts(self, th):
+        parts = super().prior_log_prob_parts(th)
+        red = lambda t: t.sum((-1, -2))
+        parts['v'] = red(normal_log_prob(th['v'], torch.tensor(0.1, dtype=DTYPE)))       # bernoulli.py:200-208
+        parts['w'] = red(normal_log_prob(th['w'], torch.tensor(1.0, dtype=DTYPE)))       # bernoulli.py:209-215
+        return parts
+
+    @staticmethod
+    def observation_log_prob(x, rate):
+        """[EXT] tfd.Bernoulli(logits).log_prob(x) = -sigmoid_cross_entropy(labels=x, logits) = x*l - softplus(l)."""
+        return x * rate - torch.nn.functional.softplus(rate)
 
 
 def draw_noise(model: OraclePoissonFactorization, params, S, seed=0):

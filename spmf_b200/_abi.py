@@ -140,7 +140,7 @@ class StepArgs(C.Structure):
                             "ev_gemm0", "ev_gemm1", "aux_stream1", "aux_stream2", "ev_aux_fork", "ev_aux_join1",
                             "ev_aux_join2")]
         + [("hot_mode", i32), ("EVt", p), ("ev_tile0", p), ("ev_tile1", p), ("scr_dpre", p), ("ev_noise", p)]
-        + [("link", i32), ("gs", p), ("xdense", p), ("xdense_in", p), ("step_state", p)]
+        + [("link", i32), ("gs", p), ("xdense", p), ("xdense_in", p), ("step_state", p), ("model", i32)]
     )
 
 
@@ -155,6 +155,13 @@ _SIGS["spmf_step_state_value"] = (i32, [u32, i32, f32, f32, f32, f32, f32, p])
 _SIGS["spmf_fill_noise_dev"] = (i32, [p, p, i32, i32, i32, u64, u32, i32, p, p])
 _SIGS["spmf_gamma_draw_grad_dev"] = (i32, [p, p, p, i32, i32, i32, u64, u32, p, p])
 _SIGS["spmf_adam_step_dev"] = (i32, [p, p, p, p, i64, f32, f32, f32, f32, i32, f32, f32, p, p])
+_SIGS["spmf_sample_m"] = (i32, [p, p, i32, i32, i32, p, i32, p])
+_SIGS["spmf_draw_operands_ranked_m"] = (i32, [p, p, p, p, i32, i32, i32, p, p, p, p, p, p, i32, p])
+_SIGS["spmf_backward_params_ranked_m"] = (i32, [p, p, p, p, p, i32, i32, i32, p, p, p, p, p, p, f32, f32, f32, f32,
+                                                 f32, f32, i32, p, p, p, p, p, i32, p])
+_SIGS["spmf_backward_pre_m"] = (i32, [p, p, p, p, i32, i32, i32, f32, f32, f32, f32, f32, f32, i32, p, p, p, i32, p])
+_SIGS["spmf_backward_post_m"] = (i32, [p, p, p, p, i32, i32, i32, p, p, p, p, p, p, f32, f32, f32, f32, f32, f32, i32,
+                                        p, p, p, p, p, i32, p])
 _SIGS["spmf_prepare_batch"] = (i32, [p, p, p, p, p, i32, i64, i32, p, p, p, p, p, p, p])
 
 EXPORTS = tuple(_SIGS)
@@ -177,6 +184,7 @@ def call(name, *args):
 
 
 LINK_POISSON, LINK_POISSON_LOG, LINK_BERNOULLI, LINK_BERNOULLI_LOG = 0, 1, 2, 3
+MODEL_POISSON, MODEL_BERNOULLI = 0, 1
 DENSE_OPTIMISTIC, DENSE_STATS, DENSE_GUARDED = 0, 1, 2
 
 

@@ -56,6 +56,7 @@ inline Layout make_layout(int D, int K, int S) {
 }
 
 struct Hyper {
+  int vw_identity;   // BernoulliFactorization: v, w use an Identity bijector and Normal priors (bernoulli.py:186-215)
   float u_tau_b;     // 1/u_tau_scale^2   (poisson.py:339)
   float s_tau_b;     // 1/s_tau_scale^2   (poisson.py:375)
   float decay;       // symmetry_breaking_decay (poisson.py:225)
@@ -113,6 +114,14 @@ SPMF_HD NDraw ndraw(const NParam& p, float eps) {
   d.y = f.y; d.sg = f.sg; d.oms = f.oms; d.lsg = f.lsg;
   return d;
 }
+// Identity bijector (v, w of BernoulliFactorization, bernoulli.py:186-195): y = t, no Jacobian term
+SPMF_HD NDraw ndraw_id(const NParam& p, float eps) {
+  NDraw d;
+  d.t = fmaf(p.sig, eps, p.loc);
+  d.y = d.t; d.sg = 1.f; d.oms = 0.f; d.lsg = 0.f;
+  return d;
+}
+SPMF_HD NDraw ndraw_sel(const NParam& p, float eps, int identity) { return identity ? ndraw_id(p, eps) : ndraw(p, eps); }
 // log q(y) = log N(t; loc, sig) - log sigmoid(t)     [EXT tfb.Softplus fldj]
 SPMF_HD float nlogq(const NParam& p, const NDraw& d, float eps) {
   return -0.5f * eps * eps - p.logsig - kHalfLog2Pi - d.lsg;
@@ -178,6 +187,12 @@ SPMF_HD float halfnormal(float y, float sigma, float* dy, float* dsigma) {
   *dy = -r * is;
   *dsigma = (r * r - 1.f) * is;
   return kHalfLog2OverPi - SPMF_LOGF(sigma) - 0.5f * r * r;
+}
+// Normal(y; 0, sigma): value, d/dy   (priors of v, w in bernoulli.py:200-215)
+SPMF_HD float normal0(float y, float sigma, float* dy) {
+  float is = SPMF_RCPF(sigma), r = y * is;
+  *dy = -r * is;
+  return -kHalfLog2Pi - SPMF_LOGF(sigma) - 0.5f * r * r;
 }
 // SqrtInverseGamma(y; 0.5, scale = 1/a): value, d/dy, d/da
 SPMF_HD float sqrt_ig_half(float y, float a, float* dy, float* da) {
@@ -251,10 +266,10 @@ SPMF_HD void feat_init(FeatState& f, const Layout& L, const float* P, int d) {
 
 // Draws of the per-feature variables needed by every lane (a_d, b_d and the draws themselves).
 struct FeatDraw { NDraw w, s0, s1; float a, b; };
-SPMF_HD FeatDraw feat_draw(const FeatState& f, const Layout& L, const float* N, int d, int s) {
+SPMF_HD FeatDraw feat_draw(const FeatState& f, const Layout& L, const float* N, int d, int s, int vw_identity = 0) {
   FeatDraw r;
   const long long D = L.D;
-  r.w = ndraw(f.w, N[L.noff[VAR_W] + s * D + d]);
+  r.w = ndraw_sel(f.w, N[L.noff[VAR_W] + s * D + d], vw_identity);
   r.s0 = ndraw(f.s0, N[L.noff[VAR_S] + s * 2 * D + d]);
   r.s1 = ndraw(f.s1, N[L.noff[VAR_S] + s * 2 * D + D + d]);
   float inv = 1.f / (r.s0.y + r.s1.y);
@@ -267,11 +282,11 @@ SPMF_HD FeatDraw feat_draw(const FeatState& f, const Layout& L, const float* N, 
 template <int KK>
 SPMF_HD void lane_operands(const LaneState<KK>& st, const Layout& L, const float* N, const float* eta,
                            int d, int lane, int i, int s, float a_d, float* Ap, float* EV,
-                           float* u_out, float* v_out) {
+                           float* u_out, float* v_out, int vw_identity = 0) {
   int k = lane + 32 * i;
   long long e = (long long)s * L.D * L.K + (long long)d * L.K + k;
   NDraw u = ndraw(st.u[i], N[L.noff[VAR_U] + e]);
-  NDraw v = ndraw(st.v[i], N[L.noff[VAR_V] + e]);
+  NDraw v = ndraw_sel(st.v[i], N[L.noff[VAR_V] + e], vw_identity);
   *Ap = a_d * u.y / eta[L.D + d];      // encoder divisor: eta_d, or 1 under log_transform (poisson.py:41-43)
   *EV = eta[d] * v.y;
   if (u_out) *u_out = u.y;
@@ -292,7 +307,7 @@ SPMF_HD DkOut lane_step(LaneState<KK>& st, const Layout& L, const Hyper& h, cons
   long long e = (long long)s * DK + (long long)d * L.K + k;
   float eps_u = N[L.noff[VAR_U] + e], eps_v = N[L.noff[VAR_V] + e];
   NDraw u = ndraw(st.u[i], eps_u);
-  NDraw v = ndraw(st.v[i], eps_v);
+  NDraw v = ndraw_sel(st.v[i], eps_v, h.vw_identity);
   GDraw ue = gdraw(st.ue[i], N[L.noff[VAR_UETA] + e]);
   GDraw ua = gdraw(st.ua[i], N[L.noff[VAR_UETAA] + e]);
   GDraw ut = gdraw(st.ut[i], N[L.noff[VAR_UTAU] + (long long)s * L.K + k]);
@@ -300,7 +315,8 @@ SPMF_HD DkOut lane_step(LaneState<KK>& st, const Layout& L, const Hyper& h, cons
   float sigma = ue.y * ut.y * ck;
   float du, dsig, dv, dtmp, due, dua, dua2;
   float pu = halfnormal(u.y, sigma, &du, &dsig);                 // poisson.py:247-251
-  float pv = halfnormal(v.y, 0.1f, &dv, &dtmp);                  // poisson.py:229-235
+  float pv = h.vw_identity ? normal0(v.y, 0.1f, &dv)             // bernoulli.py:200-208
+                           : halfnormal(v.y, 0.1f, &dv, &dtmp);  // poisson.py:229-235
   float pue = sqrt_ig_half(ue.y, ua.y, &due, &dua);              // poisson.py:303-311
   float pua = ig_half(ua.y, 1.0f, &dua2);                        // poisson.py:312-322
   float ieta = 1.f / eta[L.D + d];
@@ -347,7 +363,8 @@ SPMF_HD void feat_step(FeatState& f, const FeatDraw& fd, const Layout& L, const 
   float ds1_data = (db - da) * fd.s0.y * inv2;
 
   float dw, dtmp, d_s0, dsig0, d_s1, dsig1;
-  float pw = halfnormal(fd.w.y, 1.0f, &dw, &dtmp);             // poisson.py:236-242
+  float pw = h.vw_identity ? normal0(fd.w.y, 1.0f, &dw)        // bernoulli.py:209-215
+                           : halfnormal(fd.w.y, 1.0f, &dw, &dtmp);   // poisson.py:236-242
   float ps0 = halfnormal(fd.s0.y, se0.y * st.y, &d_s0, &dsig0);  // poisson.py:273-277
   float ps1 = halfnormal(fd.s1.y, se1.y * st.y, &d_s1, &dsig1);
   float dse0, dsea0, dse1, dsea1, dst, dsta, dsea0b, dsea1b, dstab;

@@ -131,7 +131,7 @@ template <int KK>
 __global__ void __launch_bounds__(128)
 draw_operands_kernel(Layout L, const float* __restrict__ P, const float* __restrict__ N,
                      const float* __restrict__ eta, const int* __restrict__ rank, int SV, int KP,
-                     float* __restrict__ Ap, float* __restrict__ EV, float* __restrict__ PH) {
+                     float* __restrict__ Ap, float* __restrict__ EV, float* __restrict__ PH, int vw_identity) {
   const int lane = threadIdx.x & 31;
   const int d = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (d >= L.D) return;
@@ -174,23 +174,25 @@ draw_operands_kernel(Layout L, const float* __restrict__ P, const float* __restr
         if (k < L.K) {
           const long long e = (long long)s * DK + (long long)d * L.K + k;
           ap = a_d * softplus4(fmaf(us[i], N[L.noff[VAR_U] + e], ul[i])).y * ieta_enc;   // A' (poisson.py:665, 43)
-          ev = eta_dec * softplus4(fmaf(vs[i], N[L.noff[VAR_V] + e], vl[i])).y;          // eta v (poisson.py:54)
+          const float tv = fmaf(vs[i], N[L.noff[VAR_V] + e], vl[i]);
+          ev = eta_dec * (vw_identity ? tv : softplus4(tv).y);                         // eta v (poisson.py:54)
         }
         const long long idx = ((long long)q * D + dr) * SV * KP + pos0[i] + sv * sv_stride;
         Ap[idx] = ap;
         EV[idx] = ev;
       }
     }
-    if (lane == 0)
-      PH[((long long)q * D + dr) * SV + sv] =
-          eta_dec * b_d * softplus4(fmaf(wsg, N[L.noff[VAR_W] + (long long)s * D + d], wl)).y;   // poisson.py:701
+    if (lane == 0) {
+      const float tw = fmaf(wsg, N[L.noff[VAR_W] + (long long)s * D + d], wl);
+      PH[((long long)q * D + dr) * SV + sv] = eta_dec * b_d * (vw_identity ? tw : softplus4(tw).y);   // poisson.py:701
+    }
   }
 }
 
 // Optional: materialise the draws themselves (API surface: surrogate_distribution.sample()).
 // out[var][s][elem] in the same layout as the noise buffer.
 __global__ void sample_kernel(Layout L, const float* __restrict__ P, const float* __restrict__ N,
-                              float* __restrict__ out) {
+                              float* __restrict__ out, int vw_identity) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   for (int v = 0; v < NUM_VARS; ++v) {
     long long n = L.vsize[v] * L.S;
@@ -201,7 +203,7 @@ __global__ void sample_kernel(Layout L, const float* __restrict__ P, const float
       float y;
       if (v <= VAR_S) {
         NParam p = nparam_init(a, b);
-        y = ndraw(p, nz).y;
+        y = ndraw_sel(p, nz, vw_identity && (v == VAR_V || v == VAR_W)).y;
       } else {
         y = softplusf(softplusf(b) / nz);
       }
@@ -267,7 +269,7 @@ backward_dk_kernel(Layout L, Hyper h, const float* __restrict__ P, const float* 
           const long long e = ((long long)s * L.D + d) * L.K + k;
           const long long nsdk = (long long)L.S * L.D * L.K;
           const NDraw ud = ndraw(st.u[i], N[L.noff[VAR_U] + e]);
-          const NDraw vd = ndraw(st.v[i], N[L.noff[VAR_V] + e]);
+          const NDraw vd = ndraw_sel(st.v[i], N[L.noff[VAR_V] + e], h.vw_identity);
           const float ieta = 1.f / eta[L.D + d];       // encoder divisor
           fac[e] = a_d * ieta * ud.sg;
           fac[nsdk + e] = eta[d] * vd.sg;
@@ -366,7 +368,7 @@ backward_dk_post_kernel(Layout L, Hyper h, const float* __restrict__ P, const fl
     float aw = 0.f, awe = 0.f, a0 = 0.f, a0e = 0.f, a1 = 0.f, a1e = 0.f;
     for (int s = lane; s < L.S; s += 32) {
       const int q = s / SV, sv = s - q * SV;
-      const FeatDraw fd = feat_draw(f, L, N, d, s);
+      const FeatDraw fd = feat_draw(f, L, N, d, s, h.vw_identity);
       const float da = da_mine[s >> 5];
       const float Gphi = Gphinz[((long long)q * D + dr) * SV + sv] - cf_rows;          // d L / d phi_d
       const float dw_data = eta[d] * fd.b * Gphi;                                     // phi = eta b w
@@ -428,7 +430,7 @@ backward_feat_kernel(Layout L, Hyper h, const float* __restrict__ P, const float
   feat_init(f, L, P, d);
   for (int s = sg; s < L.S; s += SV) {
     const int q = s / SV, sv = s - q * SV;
-    FeatDraw fd = feat_draw(f, L, N, d, s);
+    FeatDraw fd = feat_draw(f, L, N, d, s, h.vw_identity);
     float fp[7];
     // pre: data-independent half (upstream da = 0, dL/dphi = 0); the data half of backward_dk_post_kernel adds the rest
     feat_step(f, fd, L, h, N, G, eta, d, s, pre ? 0.f : scr_da[(long long)s * L.D + d],
@@ -644,8 +646,9 @@ __global__ void square_kernel(const float* __restrict__ g, float* __restrict__ o
 }
 
 static Hyper make_hyper(float u_tau_scale, float s_tau_scale, float decay, float w_entropy,
-                        float w_prior, int world, float batch_rows) {
+                        float w_prior, int world, float batch_rows, int model = 0) {
   Hyper h;
+  h.vw_identity = model == SPMF_MODEL_BERNOULLI;
   h.u_tau_b = 1.f / (u_tau_scale * u_tau_scale);
   h.s_tau_b = 1.f / (s_tau_scale * s_tau_scale);
   h.decay = decay;
@@ -801,11 +804,16 @@ int spmf_fill_noise_dev(float* noise, const float* params, int D, int K, int S, 
 
 int spmf_sample(const float* params, const float* noise, int D, int K, int S, float* samples,
                 void* stream) {
+  return spmf_sample_m(params, noise, D, K, S, samples, SPMF_MODEL_POISSON, stream);
+}
+
+int spmf_sample_m(const float* params, const float* noise, int D, int K, int S, float* samples, int model,
+                  void* stream) {
   if (!params || !noise || !samples || K > SPMF_MAX_K) return SPMF_ERR_BAD_ARG;
   Layout L = make_layout(D, K, S);
   long long nmax = (long long)D * K * S;
   if (nmax < 2LL * D * S) nmax = 2LL * D * S;
-  sample_kernel<<<(unsigned)((nmax + 255) / 256), 256, 0, (cudaStream_t)stream>>>(L, params, noise, samples);
+  sample_kernel<<<(unsigned)((nmax + 255) / 256), 256, 0, (cudaStream_t)stream>>>(L, params, noise, samples, model == SPMF_MODEL_BERNOULLI);
   SPMF_CHECK_LAUNCH();
   return SPMF_OK;
 }
@@ -819,6 +827,14 @@ int spmf_draw_operands(const float* params, const float* noise, const float* eta
 int spmf_draw_operands_ranked(const float* params, const float* noise, const float* eta, const int* rank,
                               int D, int K, int S, float* Ap, float* EV, float* PH, double* vsum,
                               double* phisum, double* scratch, void* stream) {
+  return spmf_draw_operands_ranked_m(params, noise, eta, rank, D, K, S, Ap, EV, PH, vsum, phisum, scratch,
+                                     SPMF_MODEL_POISSON, stream);
+}
+
+int spmf_draw_operands_ranked_m(const float* params, const float* noise, const float* eta, const int* rank,
+                                int D, int K, int S, float* Ap, float* EV, float* PH, double* vsum,
+                                double* phisum, double* scratch, int model, void* stream) {
+  const int vwid = model == SPMF_MODEL_BERNOULLI;
   if (!params || !noise || !eta || !Ap || !EV || !PH) return SPMF_ERR_BAD_ARG;
   if ((vsum == nullptr) != (phisum == nullptr) || (vsum && !scratch)) return SPMF_ERR_BAD_ARG;
   if (D <= 0 || K <= 0 || S <= 0 || K > SPMF_MAX_K) return SPMF_ERR_BAD_ARG;
@@ -826,9 +842,9 @@ int spmf_draw_operands_ranked(const float* params, const float* noise, const flo
   Layout L = make_layout(D, K, S);
   const int KP = spmf_kpad(K), SV = spmf_draw_vec(S);
   dim3 grid((D + 3) / 4);
-  if (KP <= 32) draw_operands_kernel<1><<<grid, 128, 0, st>>>(L, params, noise, eta, rank, SV, KP, Ap, EV, PH);
-  else if (KP <= 64) draw_operands_kernel<2><<<grid, 128, 0, st>>>(L, params, noise, eta, rank, SV, KP, Ap, EV, PH);
-  else draw_operands_kernel<4><<<grid, 128, 0, st>>>(L, params, noise, eta, rank, SV, KP, Ap, EV, PH);
+  if (KP <= 32) draw_operands_kernel<1><<<grid, 128, 0, st>>>(L, params, noise, eta, rank, SV, KP, Ap, EV, PH, vwid);
+  else if (KP <= 64) draw_operands_kernel<2><<<grid, 128, 0, st>>>(L, params, noise, eta, rank, SV, KP, Ap, EV, PH, vwid);
+  else draw_operands_kernel<4><<<grid, 128, 0, st>>>(L, params, noise, eta, rank, SV, KP, Ap, EV, PH, vwid);
   SPMF_CHECK_LAUNCH();
   if (!vsum) return SPMF_OK;        // the caller runs spmf_operand_sums itself (on another stream)
   return spmf_operand_sums(EV, PH, D, K, S, vsum, phisum, scratch, stream);
@@ -890,13 +906,24 @@ int spmf_backward_params_ranked(const float* params, const float* noise, const f
                                 const double* phisum, float batch_rows, float u_tau_scale, float s_tau_scale,
                                 float decay, float w_entropy, float w_prior, int world_size, float* grads,
                                 double* parts, float* scr_f, double* scr_d, void* gs, void* stream) {
+  return spmf_backward_params_ranked_m(params, noise, dgda, eta, rank, D, K, S, GAp, GEVnz, Gphinz, zcolsum, datasums,
+                                       phisum, batch_rows, u_tau_scale, s_tau_scale, decay, w_entropy, w_prior,
+                                       world_size, grads, parts, scr_f, scr_d, gs, SPMF_MODEL_POISSON, stream);
+}
+
+int spmf_backward_params_ranked_m(const float* params, const float* noise, const float* dgda, const float* eta,
+                                  const int* rank, int D, int K, int S, const float* GAp, const float* GEVnz,
+                                  const float* Gphinz, const double* zcolsum, const double* datasums,
+                                  const double* phisum, float batch_rows, float u_tau_scale, float s_tau_scale,
+                                  float decay, float w_entropy, float w_prior, int world_size, float* grads,
+                                  double* parts, float* scr_f, double* scr_d, void* gs, int model, void* stream) {
   if (!params || !noise || !dgda || !eta || !GAp || !GEVnz || !Gphinz || !zcolsum || !datasums ||
       !phisum || !grads || !parts || !scr_f || !scr_d)
     return SPMF_ERR_BAD_ARG;
   if (D <= 0 || K <= 0 || S <= 0 || K > SPMF_MAX_K || world_size <= 0) return SPMF_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   Layout L = make_layout(D, K, S);
-  Hyper h = make_hyper(u_tau_scale, s_tau_scale, decay, w_entropy, w_prior, world_size, batch_rows);
+  Hyper h = make_hyper(u_tau_scale, s_tau_scale, decay, w_entropy, w_prior, world_size, batch_rows, model);
   const int KP = spmf_kpad(K), SV = spmf_draw_vec(S);
   // float scratch: scr_utau [S][D][K] | scr_parts [D][S*16] | scr_lat [K][S*16] | scr_da [S][D]
   float* scr_utau = scr_f;
@@ -938,11 +965,19 @@ long long spmf_backward_scratch_floats(int D, int K, int S) {
 int spmf_backward_pre(const float* params, const float* noise, const float* dgda, const float* eta, int D, int K,
                       int S, float batch_rows, float u_tau_scale, float s_tau_scale, float decay, float w_entropy,
                       float w_prior, int world_size, float* grads, float* scr_f, double* scr_d, void* stream) {
+  return spmf_backward_pre_m(params, noise, dgda, eta, D, K, S, batch_rows, u_tau_scale, s_tau_scale, decay, w_entropy,
+                             w_prior, world_size, grads, scr_f, scr_d, SPMF_MODEL_POISSON, stream);
+}
+
+int spmf_backward_pre_m(const float* params, const float* noise, const float* dgda, const float* eta, int D, int K,
+                        int S, float batch_rows, float u_tau_scale, float s_tau_scale, float decay, float w_entropy,
+                        float w_prior, int world_size, float* grads, float* scr_f, double* scr_d, int model,
+                        void* stream) {
   if (!params || !noise || !dgda || !eta || !grads || !scr_f || !scr_d) return SPMF_ERR_BAD_ARG;
   if (D <= 0 || K <= 0 || S <= 0 || K > SPMF_MAX_K || world_size <= 0) return SPMF_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   Layout L = make_layout(D, K, S);
-  Hyper h = make_hyper(u_tau_scale, s_tau_scale, decay, w_entropy, w_prior, world_size, batch_rows);
+  Hyper h = make_hyper(u_tau_scale, s_tau_scale, decay, w_entropy, w_prior, world_size, batch_rows, model);
   const int KP = spmf_kpad(K), SV = spmf_draw_vec(S);
   float* scr_utau = scr_f;
   float* scr_parts = scr_utau + (long long)S * D * K;
@@ -971,13 +1006,24 @@ int spmf_backward_post(const float* params, const float* noise, const float* eta
                        const double* datasums, const double* phisum, float batch_rows, float u_tau_scale,
                        float s_tau_scale, float decay, float w_entropy, float w_prior, int world_size,
                        float* grads, double* parts, float* scr_f, const double* scr_d, void* gs, void* stream) {
+  return spmf_backward_post_m(params, noise, eta, rank, D, K, S, GAp, GEVnz, Gphinz, zcolsum, datasums, phisum,
+                              batch_rows, u_tau_scale, s_tau_scale, decay, w_entropy, w_prior, world_size, grads,
+                              parts, scr_f, scr_d, gs, SPMF_MODEL_POISSON, stream);
+}
+
+int spmf_backward_post_m(const float* params, const float* noise, const float* eta, const int* rank, int D, int K,
+                         int S, const float* GAp, const float* GEVnz, const float* Gphinz, const double* zcolsum,
+                         const double* datasums, const double* phisum, float batch_rows, float u_tau_scale,
+                         float s_tau_scale, float decay, float w_entropy, float w_prior, int world_size,
+                         float* grads, double* parts, float* scr_f, const double* scr_d, void* gs, int model,
+                         void* stream) {
   if (!params || !noise || !eta || !GAp || !GEVnz || !Gphinz || !zcolsum || !datasums || !phisum || !grads ||
       !parts || !scr_f || !scr_d)
     return SPMF_ERR_BAD_ARG;
   if (D <= 0 || K <= 0 || S <= 0 || K > SPMF_MAX_K || world_size <= 0) return SPMF_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   Layout L = make_layout(D, K, S);
-  Hyper h = make_hyper(u_tau_scale, s_tau_scale, decay, w_entropy, w_prior, world_size, batch_rows);
+  Hyper h = make_hyper(u_tau_scale, s_tau_scale, decay, w_entropy, w_prior, world_size, batch_rows, model);
   const int KP = spmf_kpad(K), SV = spmf_draw_vec(S);
   float* scr_da = scr_f + (long long)S * D * K + (long long)D * S * NUM_PARTS + (long long)K * S * NUM_PARTS;
   const float* fac = scr_da + (long long)S * D;

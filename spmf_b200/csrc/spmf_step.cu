@@ -58,17 +58,17 @@ int spmf_advi_step(const spmf_step_args* a) {
       CUDA_TRY(cudaEventRecord((cudaEvent_t)a->ev_noise, hot));
       CUDA_TRY(cudaStreamWaitEvent(side, (cudaEvent_t)a->ev_noise, 0));
     }
-    STEP_TRY(spmf_backward_pre(a->params, a->noise, a->dgda, a->eta, D, K, S, (float)a->nrows, a->u_tau_scale,
-                               a->s_tau_scale, a->decay, a->w_entropy, a->w_prior, a->world_size, a->grads,
-                               a->scr_f, a->scr_dpre, side));
+    STEP_TRY(spmf_backward_pre_m(a->params, a->noise, a->dgda, a->eta, D, K, S, (float)a->nrows, a->u_tau_scale,
+                                 a->s_tau_scale, a->decay, a->w_entropy, a->w_prior, a->world_size, a->grads,
+                                 a->scr_f, a->scr_dpre, a->model, side));
   }
   if (side != hot) CUDA_TRY(cudaEventRecord((cudaEvent_t)a->ev_join, side));
   // (tile mode with auxiliary streams: the fp64 operand sums are first read by spmf_rows_finish, so
   // they leave the critical path and run next to the encode GEMM)
   const bool pre_fork = hybrid && a->hot_mode == 2 && a->EVt && a->aux_stream1 && a->ev_aux_fork && a->ev_aux_join1;
-  STEP_TRY(spmf_draw_operands_ranked(a->params, a->noise, a->eta, hybrid ? a->rank : nullptr, D, K, S, a->Ap, a->EV,
-                                     a->PH, pre_fork ? nullptr : a->vsum, pre_fork ? nullptr : a->phisum, a->scr_d,
-                                     hot));
+  STEP_TRY(spmf_draw_operands_ranked_m(a->params, a->noise, a->eta, hybrid ? a->rank : nullptr, D, K, S, a->Ap,
+                                       a->EV, a->PH, pre_fork ? nullptr : a->vsum, pre_fork ? nullptr : a->phisum,
+                                       a->scr_d, a->model, hot));
   const int KP = spmf_kpad(K), SV = spmf_draw_vec(S), NQ = S / SV, REC = KP * SV;
   if (a->ev_rows0) CUDA_TRY(cudaEventRecord((cudaEvent_t)a->ev_rows0, hot));
   const bool dense_link = a->link != SPMF_LINK_POISSON;
@@ -199,16 +199,16 @@ int spmf_advi_step(const spmf_step_args* a) {
   }   // sparse / tensor-core data term
   if (side != hot) CUDA_TRY(cudaStreamWaitEvent(hot, (cudaEvent_t)a->ev_join, 0));
   if (split_bwd)
-    STEP_TRY(spmf_backward_post(a->params, a->noise, a->eta, hybrid ? a->rank : nullptr, D, K, S, a->GAp, a->GEV,
-                                a->Gph, a->zcolsum, a->datasums, a->phisum, (float)a->nrows, a->u_tau_scale,
-                                a->s_tau_scale, a->decay, a->w_entropy, a->w_prior, a->world_size, a->grads,
-                                a->parts, a->scr_f, a->scr_dpre, a->gs, hot));
+    STEP_TRY(spmf_backward_post_m(a->params, a->noise, a->eta, hybrid ? a->rank : nullptr, D, K, S, a->GAp, a->GEV,
+                                  a->Gph, a->zcolsum, a->datasums, a->phisum, (float)a->nrows, a->u_tau_scale,
+                                  a->s_tau_scale, a->decay, a->w_entropy, a->w_prior, a->world_size, a->grads,
+                                  a->parts, a->scr_f, a->scr_dpre, a->gs, a->model, hot));
   else
-    STEP_TRY(spmf_backward_params_ranked(a->params, a->noise, a->dgda, a->eta, hybrid ? a->rank : nullptr, D, K, S,
-                                         a->GAp, a->GEV, a->Gph, a->zcolsum, a->datasums, a->phisum,
-                                         (float)a->nrows, a->u_tau_scale, a->s_tau_scale, a->decay, a->w_entropy,
-                                         a->w_prior, a->world_size, a->grads, a->parts, a->scr_f, a->scr_d, a->gs,
-                                         hot));
+    STEP_TRY(spmf_backward_params_ranked_m(a->params, a->noise, a->dgda, a->eta, hybrid ? a->rank : nullptr, D, K, S,
+                                           a->GAp, a->GEV, a->Gph, a->zcolsum, a->datasums, a->phisum,
+                                           (float)a->nrows, a->u_tau_scale, a->s_tau_scale, a->decay, a->w_entropy,
+                                           a->w_prior, a->world_size, a->grads, a->parts, a->scr_f, a->scr_d, a->gs,
+                                           a->model, hot));
   if (a->adam_lr > 0.f) {
     if (a->world_size > 1) return SPMF_ERR_BAD_ARG;      // the all-reduce must come between backward and Adam
     // the scalar slack inside the gradient block is host-side bookkeeping, not a parameter gradient

@@ -113,7 +113,7 @@ class AdviEngine:
 
     def __init__(self, D, K, S, device, u_tau_scale, s_tau_scale, decay, scale_rows=True,
                  entropy_weight=1.0, prior_weight=1.0, world_size=1, seed=0, max_rows=0, link=0,
-                 exact_guard=True):
+                 exact_guard=True, model=0):
         if K > _abi.MAX_K:
             raise _abi.SpmfError(f"latent_dim {K} > {_abi.MAX_K} is not supported by the CUDA path")
         self.D, self.K, self.S = int(D), int(K), int(S)
@@ -139,6 +139,7 @@ class AdviEngine:
         # link function (SPMF_LINK_*): 0 = linear Poisson (sparse / tensor-core path with closed-form sum(rate));
         # log_transform / Bernoulli run the dense CUDA-core path of spmf_dense.cu
         self.link = int(link)
+        self.model = int(model)           # SPMF_MODEL_*: Bernoulli = Identity bijector + Normal priors on v, w
         self.exact_guard = bool(exact_guard)
         # device guard state (poisson.py:606-616): flag | nbad | (min finite log-likelihood, entry)
         self.gs = torch.zeros(int(_abi._lib.spmf_guard_state_bytes()), dtype=torch.uint8, device=self.device)
@@ -216,9 +217,9 @@ class AdviEngine:
 
     def draw_operands(self):
         w = self.ws
-        _abi.call("spmf_draw_operands", _ptr(self.params), _ptr(self.noise), _ptr(self.eta), self.D,
+        _abi.call("spmf_draw_operands_ranked_m", _ptr(self.params), _ptr(self.noise), _ptr(self.eta), None, self.D,
                   self.K, self.S, _ptr(w.Ap), _ptr(w.EV), _ptr(w.PH), _ptr(w.vsum), _ptr(w.phisum),
-                  _ptr(w.scr_d), _stream())
+                  _ptr(w.scr_d), self.model, _stream())
         self.launches += 5
 
     def data_term(self, b: DeviceBatch, variant=0):
@@ -309,12 +310,12 @@ class AdviEngine:
 
     def backward_params(self, batch_rows):
         w = self.ws
-        _abi.call("spmf_backward_params", _ptr(self.params), _ptr(self.noise), _ptr(self.dgda),
-                  _ptr(self.eta), self.D, self.K, self.S, _ptr(w.GAp), _ptr(w.GEV), _ptr(w.Gph), _ptr(w.zcolsum),
+        _abi.call("spmf_backward_params_ranked_m", _ptr(self.params), _ptr(self.noise), _ptr(self.dgda),
+                  _ptr(self.eta), None, self.D, self.K, self.S, _ptr(w.GAp), _ptr(w.GEV), _ptr(w.Gph), _ptr(w.zcolsum),
                   _ptr(w.datasums), _ptr(w.phisum), float(batch_rows), self.u_tau_scale,
                   self.s_tau_scale, self.decay, self.entropy_weight, self.prior_weight,
                   self.world_size, _ptr(self.grads), _ptr(w.parts), _ptr(w.scr_f), _ptr(w.scr_d),
-                  _ptr(self.gs), _stream())
+                  _ptr(self.gs), self.model, _stream())
         self.launches += 9
 
     def _mark(self, name, start):
@@ -410,6 +411,7 @@ class AdviEngine:
         a = self._step_args()
         a.step_state = _ptr(self.step_state)
         a.link, a.gs, a.xdense, a.xdense_in = self.link, _ptr(self.gs), _ptr(xd), None
+        a.model = self.model
         a.z, a.dzr, a.rowacc = _ptr(w.z), _ptr(w.dzr), _ptr(w.rowacc)
         a.inv_xi, a.scale_rows = self.inv_xi, int(self.scale_rows)
         a.fresh_noise, a.rng_step = int(fresh_noise), self.rng_step
@@ -553,6 +555,6 @@ class AdviEngine:
 
     def samples(self):
         out = torch.empty_like(self.noise)
-        _abi.call("spmf_sample", _ptr(self.params), _ptr(self.noise), self.D, self.K, self.S,
-                  _ptr(out), _stream())
+        _abi.call("spmf_sample_m", _ptr(self.params), _ptr(self.noise), self.D, self.K, self.S,
+                  _ptr(out), self.model, _stream())
         return {name: self.layout.noise_view(out, name) for name in self.layout.shapes}

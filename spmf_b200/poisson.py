@@ -115,6 +115,9 @@ class _PriorDistribution:
         out['s'] = half_normal(out['s_eta'] * out['s_tau'], ())
         out['v'] = half_normal(0.1, (K, D))
         out['w'] = half_normal(1.0, (1, D))
+        if m._model_id == _abi.MODEL_BERNOULLI:       # Normal, not HalfNormal (bernoulli.py:200-215)
+            for k in ('v', 'w'):
+                out[k] = out[k] * (torch.randint(0, 2, out[k].shape, generator=gen, device=m.device) * 2 - 1)
         return out
 
 
@@ -124,6 +127,7 @@ class PoissonFactorization:
     bijectors = None
     var_list = []
     s_tau_scale = 1
+    _model_id = _abi.MODEL_POISSON
 
     def __init__(self, latent_dim=None, feature_dim=None, u_tau_scale=0.01, s_tau_scale=1.,
                  symmetry_breaking_decay=0.99, strategy=None, encoder_function=None,
@@ -207,7 +211,7 @@ class PoissonFactorization:
             eng = AdviEngine(self.feature_dim, self.latent_dim, S, self.device, self.u_tau_scale,
                              self.s_tau_scale, self.symmetry_breaking_decay, self.scale_rows,
                              self.entropy_weight, self.prior_weight, world, self.seed, link=self.link,
-                             exact_guard=self.exact_guard)
+                             exact_guard=self.exact_guard, model=self._model_id)
             eng.process_group = self.process_group
             if self._params is not None:                # engines share parameters / optimiser state
                 first = next(iter(self._engines.values()))
@@ -462,7 +466,7 @@ class PoissonFactorization:
         sig = lambda y, c, b: ig(y * y, c, b) + torch.log(2 * y)
         one = torch.ones((), **f64)
         return {
-            'v': red(hn(th['v'], 0.1 * one)), 'w': red(hn(th['w'], one)),
+            'v': red(self._vw_prior(th['v'], 0.1 * one)), 'w': red(self._vw_prior(th['w'], one)),
             'u': red(hn(th['u'], th['u_eta'] * th['u_tau'] * ck)),
             'u_eta': red(sig(th['u_eta'], 0.5, 1.0 / th['u_eta_a'])),
             'u_tau': red(sig(th['u_tau'], 0.5, 1.0 / th['u_tau_a'])),
@@ -474,6 +478,11 @@ class PoissonFactorization:
             's_eta_a': red(ig(th['s_eta_a'], 0.5, one)),
             's_tau_a': red(ig(th['s_tau_a'], 0.5, one / self.s_tau_scale ** 2)),
         }
+
+    @staticmethod
+    def _vw_prior(y, sc):
+        """HalfNormal(scale) log-density of v and w (poisson.py:229-242)."""
+        return 0.5 * math.log(2.0 / math.pi) - torch.log(sc) - 0.5 * (y / sc) ** 2
 
     def log_likelihood_components(self, s, u, v, w, data, *args, **kwargs):
         """poisson.py:156-184: {'log_likelihood','rate'}, both (S,B,D) -- dense by definition, so

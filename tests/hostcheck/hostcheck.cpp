@@ -89,6 +89,7 @@ void hc_backward_params(const float* P, const float* N, const float* eta, int D,
                         float w_prior, int world, float* grads, double* parts /*[S][16]*/) {
   Layout L = make_layout(D, K, S);
   Hyper h;
+  h.vw_identity = 0;
   h.u_tau_b = 1.f / (u_tau_scale * u_tau_scale);
   h.s_tau_b = 1.f / (s_tau_scale * s_tau_scale);
   h.decay = decay; h.w_entropy = w_entropy; h.w_prior = w_prior;

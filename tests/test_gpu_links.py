@@ -214,3 +214,78 @@ def test_log_transform_fit_decreases_loss_and_waic_runs():
     assert np.isfinite(losses).all() and losses[-1] < losses[0]
     w = model.waic(factory, sample_size=8)
     assert np.isfinite(w['waic']) and w['pwaic'] >= 0
+
+
+# ------------------------------------------------------------------------------------------------
+# BernoulliFactorization (bernoulli.py): Bernoulli-logit link, Identity bijectors / Normal priors on v, w
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("D,K,B,S,log_transform", [
+    (64, 8, 96, 4, False),
+    (50, 3, 70, 2, False),
+    (40, 16, 48, 4, True),
+])
+def test_bernoulli_step_matches_oracle(D, K, B, S, log_transform):
+    import spmf_b200
+    from oracle.spmf_oracle import OracleBernoulliFactorization, draw_noise
+    dev = torch.device("cuda:0")
+    x = (make_counts(B, D, seed=12) > 1).astype(np.float32)            # binary observations
+    x[:, 0] = 1.0
+    x[0, :] = 1.0
+    N = 10 * B
+    oracle = OracleBernoulliFactorization(K, D, u_tau_scale=1.0 / np.sqrt(N * D), log_transform=log_transform)
+    params = perturbed_params(oracle, 0.3, seed=4)
+    # v, w are unconstrained here: move them off the Poisson initialisation so that logits of both signs occur
+    g = torch.Generator().manual_seed(9)
+    params['v/loc'] = (0.3 * torch.randn(params['v/loc'].shape, generator=g, dtype=torch.float64)).float().double()
+    params['w/loc'] = (0.5 * torch.randn(params['w/loc'].shape, generator=g, dtype=torch.float64)).float().double()
+    params['u/loc'] = params['u/loc'] + 4.0
+    noise = draw_noise(oracle, params, S, seed=5)
+    data = {'counts': torch.tensor(x, dtype=torch.float64)}
+    ref_loss, ref_grads, ref_parts = oracle.loss_and_grads(params, noise, data)
+    model = spmf_b200.BernoulliFactorization(latent_dim=K, feature_dim=D, u_tau_scale=1.0 / np.sqrt(N * D),
+                                             log_transform=log_transform, device=dev)
+    assert model.bijectors['v'] == 'identity' and model.var_list == oracle.var_list
+    eng = model._engine_for(S)
+    assert eng.link in (2, 3) and eng.model == 1 and not eng.scale_rows
+    _load(eng, params)
+    eng.set_noise_from(noise)
+    batch = spmf_b200.as_device_batch(x, dev)
+    p = eng.loss_and_grad(batch, fresh_noise=False)
+    torch.cuda.synchronize()
+    loss = float(eng.loss_value(p).item())
+    assert abs(loss - ref_loss) <= TOL * abs(ref_loss), (loss, ref_loss)
+    pd = eng.parts_dict()
+    for name in ref_parts:
+        ref = ref_parts[name].numpy()
+        assert np.abs(pd[name].numpy() - ref).max() <= TOL * max(np.abs(ref).max(), 1.0), (name, pd[name].numpy(), ref)
+    grads = eng.layout.views(eng.grads)
+    for k, gr in ref_grads.items():
+        tol = TOL if k.split('/')[0] in ('v', 'w', 'u', 's') else TOL_IG
+        e = rel_err(grads[k].cpu().numpy(), gr.numpy())
+        assert e <= tol, (k, e)
+    # draws of v, w are signed; the energy API and the likelihood surface agree with the oracle
+    th = model.sample(3, seed=6)
+    assert bool((th['v'] < 0).any()) and bool((th['u'] > 0).all())
+    thc = {k: v.cpu().double() for k, v in th.items()}
+    got = model.unormalized_log_prob_parts({'counts': x}, **th)
+    ref = oracle.unormalized_log_prob_parts(data, **thc)
+    for k in ref:
+        r = ref[k].numpy()
+        assert np.abs(got[k].cpu().numpy() - r).max() <= TOL * max(np.abs(r).max(), 1.0), (k,)
+    llc = model.log_likelihood_components(data={'counts': x}, **{k: th[k] for k in ('s', 'u', 'v', 'w')})
+    ollc = oracle.log_likelihood_components(data=data, **{k: thc[k] for k in ('s', 'u', 'v', 'w')})
+    assert rel_err(llc['log_likelihood'].cpu().double().numpy(), ollc['log_likelihood'].numpy()) < 1e-4
+
+
+def test_bernoulli_fit_decreases_loss():
+    import spmf_b200
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(0)
+    z = rng.random((400, 3)) < 0.3
+    w = rng.random((3, 40)) < 0.4
+    x = ((z.astype(np.float32) @ w.astype(np.float32)) > 0).astype(np.float32)
+    x[0, :] = 1.0
+    m = spmf_b200.BernoulliFactorization(latent_dim=3, feature_dim=40, u_tau_scale=1e-2, device=dev, seed=2)
+    factory = lambda: [{'counts': x[i:i + 100]} for i in range(0, 400, 100)]
+    losses = m.fit(factory, num_steps=40, learning_rate=0.05, sample_size=4, verbose=False, rel_tol=None)
+    assert np.isfinite(losses).all() and losses[-1] < losses[0]
