@@ -258,6 +258,9 @@ def main():
 
     # ------------------------------------------------ device-resident: `value`
     run_steps(args.warmup, lambda i: batches[i % len(batches)], args.lr)
+    # every resident batch replays its step as one CUDA graph: capture them all before the timed region
+    # (training does this once per batch in its first epoch)
+    primed = sum(bool(eng.prime_graph(b, lr=args.lr)) for b in batches)
     barrier()
     clocks = ClockSampler(local) if rank == 0 else None
     if clocks:
@@ -474,7 +477,7 @@ def main():
                        "nnzK_times_draws_per_s": value * S},
             "e2e": {"value": e2e_value, "unit": "nonzeros*K/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": 8, "ms_per_step": float(t2.item()) / args.steps},
-            "gpu_launches": launches, "graph_replays": graph_replays,
+            "gpu_launches": launches, "graph_replays": graph_replays, "graphs_primed": primed,
             "clocks": clk, "roofline": roofline, "cpu_baseline": cpu,
         }))
     if world > 1:

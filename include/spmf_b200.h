@@ -371,6 +371,7 @@ typedef struct spmf_step_args {
    * (rng_step, adam_t, adam_*) into it and the noise / Adam kernels read it -- required for graph replay */
   void* step_state;
   int model;          /* SPMF_MODEL_* */
+  int state_preset;   /* != 0: step_state was already written on the stream (graph replay); leave 0 otherwise */
 } spmf_step_args;
 int spmf_advi_step(const spmf_step_args* args);
 /* Replay of a whole step as ONE CUDA graph launch (all streams, events and kernels of spmf_advi_step):

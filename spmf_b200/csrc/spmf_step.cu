@@ -31,7 +31,7 @@ int spmf_advi_step(const spmf_step_args* a) {
   const int D = a->D, K = a->K, S = a->S;
 
   // per-step scalars to the device first (graph replay updates this one node's argument)
-  if (a->step_state)
+  if (a->step_state && !a->state_preset)
     STEP_TRY(spmf_step_state_set(a->step_state, a->rng_step, a->adam_t, a->adam_lr, a->adam_beta1, a->adam_beta2,
                                  a->adam_eps, a->clip_value, caller));
   if (multi) {
@@ -224,11 +224,13 @@ int spmf_advi_step(const spmf_step_args* a) {
 }
 
 // ---- graph replay ------------------------------------------------------------------------------------
+// The captured graph holds every kernel / memset / cross-stream dependency of one step EXCEPT the kernel
+// that writes the per-step scalars: that one is launched eagerly right before each replay, so the
+// executable graph itself is never modified (updating a kernel node's arguments before every launch
+// made the replay re-upload the graph and was slower than the eager multi-stream launch).
 struct StepGraph {
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t exec = nullptr;
-  cudaGraphNode_t state_node = nullptr;
-  cudaKernelNodeParams state_params{};
   void* state_dst = nullptr;
 };
 
@@ -237,6 +239,7 @@ int spmf_step_graph_create(const spmf_step_args* a_in, void** handle) {
   // the legacy default stream (0) cannot be captured: record the sequence with the hot stream as its
   // origin instead (the replay may still be launched into any stream, the default one included)
   spmf_step_args copy = *a_in;
+  copy.state_preset = 1;
   if (!copy.caller_stream) {
     if (!copy.hot_stream) return SPMF_ERR_UNSUPPORTED;
     copy.caller_stream = copy.hot_stream;
@@ -257,24 +260,8 @@ int spmf_step_graph_create(const spmf_step_args* a_in, void** handle) {
     cudaGetLastError();
     return rc != SPMF_OK ? rc : (e != cudaSuccess ? (int)e : SPMF_ERR_UNSUPPORTED);
   }
-  // the node that writes the per-step scalars: the only one whose argument changes between launches
-  size_t n = 0;
-  cudaGraphGetNodes(g->graph, nullptr, &n);
-  cudaGraphNode_t* nodes = new cudaGraphNode_t[n ? n : 1];
-  cudaGraphGetNodes(g->graph, nodes, &n);
-  const void* want = spmf_step_state_kernel_ptr();
-  for (size_t i = 0; i < n && !g->state_node; ++i) {
-    cudaGraphNodeType t;
-    if (cudaGraphNodeGetType(nodes[i], &t) != cudaSuccess || t != cudaGraphNodeTypeKernel) continue;
-    cudaKernelNodeParams p{};
-    if (cudaGraphKernelNodeGetParams(nodes[i], &p) == cudaSuccess && p.func == want) {
-      g->state_node = nodes[i];
-      g->state_params = p;
-    }
-  }
-  delete[] nodes;
   g->state_dst = a->step_state;
-  e = g->state_node ? cudaGraphInstantiate(&g->exec, g->graph, 0) : cudaErrorInvalidValue;
+  e = cudaGraphInstantiate(&g->exec, g->graph, 0);
   if (e != cudaSuccess) {
     cudaGraphDestroy(g->graph);
     delete g;
@@ -289,14 +276,7 @@ int spmf_step_graph_launch(void* handle, unsigned int rng_step, int adam_t, floa
                            float eps, float clip_value, void* stream) {
   StepGraph* g = (StepGraph*)handle;
   if (!g || !g->exec) return SPMF_ERR_BAD_ARG;
-  alignas(8) unsigned char value[64];
-  STEP_TRY(spmf_step_state_value(rng_step, adam_t, lr, beta1, beta2, eps, clip_value, value));
-  void* dst = g->state_dst;
-  void* kargs[2] = {&dst, value};
-  cudaKernelNodeParams p = g->state_params;
-  p.kernelParams = kargs;
-  p.extra = nullptr;
-  CUDA_TRY(cudaGraphExecKernelNodeSetParams(g->exec, g->state_node, &p));
+  STEP_TRY(spmf_step_state_set(g->state_dst, rng_step, adam_t, lr, beta1, beta2, eps, clip_value, stream));
   CUDA_TRY(cudaGraphLaunch(g->exec, (cudaStream_t)stream));
   return SPMF_OK;
 }

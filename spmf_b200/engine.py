@@ -147,10 +147,11 @@ class AdviEngine:
         # per-step scalars on the device (Philox step, Adam step / rates): what a replayed graph reads
         self.step_state = torch.zeros(max(int(_abi._lib.spmf_step_state_bytes()), 64), dtype=torch.uint8,
                                       device=self.device)
-        # SPMF_GRAPHS=1: replay resident batches as ONE CUDA graph launch per step.  Opt-in: measured on B200
-        # (profiles/r2_graph_replay_sweep.jsonl) the replay is no faster at C4 / C1 (the step is not
-        # launch-bound) and slower at C2 / C3, so the eager multi-stream launch stays the default.
-        self.use_graphs = os.environ.get("SPMF_GRAPHS", "0") == "1"
+        # Resident batches (cut from a CsrShard) replay their step as ONE CUDA graph launch (SPMF_GRAPHS=0:
+        # always launch eagerly).  Measured on B200 with captures outside the timed region
+        # (profiles/r2_graph_replay.txt): C1 0.137 -> 0.114, C2 0.202 -> 0.170, C3 0.282 -> 0.250,
+        # C4 1.104 -> 1.096 ms/step.  A capture + instantiation costs ~2 ms per (batch, configuration).
+        self.use_graphs = os.environ.get("SPMF_GRAPHS", "1") != "0"
         self._ws_gen = 0                  # bumped whenever a workspace buffer moves: invalidates graphs
         self._warm_cfgs = set()
         self.graph_launches = 0
@@ -380,8 +381,16 @@ class AdviEngine:
             batch.ensure_csc()
         return hybrid
 
+    def prime_graph(self, batch: DeviceBatch, fresh_noise=True, lr=None, clip_value=0.0):
+        """Capture (without running it) the CUDA graph of this batch's step for the given configuration, so
+        that no later step pays the ~ms capture + instantiation.  Needs one eager step of the same
+        configuration before (any batch); returns True if a graph is now cached."""
+        if not (self.use_graphs and getattr(batch, "_resident", False)):
+            return False
+        return bool(self.step(batch, fresh_noise=fresh_noise, lr=lr, clip_value=clip_value, _capture_only=True))
+
     def step(self, batch: DeviceBatch, fresh_noise=True, lr=None, clip_value=0.0, beta1=0.9, beta2=0.999,
-             eps=1e-7):
+             eps=1e-7, _capture_only=False):
         """ONE native call: noise -> operands -> row pass -> column pass -> backward (-> Adam when `lr`
         is given and world_size == 1).  Gamma draws / implicit gradients run on a low-priority side
         stream underneath the gather-bound data-term kernels (stream_mode "prio")."""
@@ -457,6 +466,8 @@ class AdviEngine:
         else:
             a.ev_rows0 = a.ev_rows1 = a.ev_cols0 = a.ev_cols1 = a.ev_gemm0 = a.ev_gemm1 = None
             a.ev_tile0 = a.ev_tile1 = None
+        if _capture_only:
+            return self._launch_step(a, batch, ev is None, hybrid, fresh_noise, capture_only=True)
         self._launch_step(a, batch, ev is None, hybrid, fresh_noise)
         if fresh_noise:
             self.rng_step += 1
@@ -475,7 +486,7 @@ class AdviEngine:
         self.launches += base + (1 if a.adam_lr > 0 else 0) + ((7 if self.hot_mode == 2 else 5) if hybrid else 0)
         return w.parts.view(self.S, _abi.NUM_PARTS)
 
-    def _launch_step(self, a, batch, graphable, hybrid, fresh_noise):
+    def _launch_step(self, a, batch, graphable, hybrid, fresh_noise, capture_only=False):
         """Eager native step, or -- for a RESIDENT batch (cut from a CsrShard: same object, same device
         arrays every epoch) -- one CUDA graph launch (spmf_step_graph_launch).  The first step of every
         configuration runs eagerly: it performs the kernels' lazy one-time initialisation, which must
@@ -483,6 +494,8 @@ class AdviEngine:
         cfg = (int(fresh_noise), a.adam_lr > 0, bool(hybrid), int(self.hot_mode), int(self.link))
         warm = cfg in self._warm_cfgs
         if not (self.use_graphs and graphable and warm and getattr(batch, "_resident", False)):
+            if capture_only:
+                return False
             _abi.call("spmf_advi_step", a)
             self._warm_cfgs.add(cfg)
             return
@@ -500,9 +513,13 @@ class AdviEngine:
             if rc != 0:                      # not capturable in this configuration: stay eager for good
                 self.use_graphs = False
                 self.graph_error = rc
+                if capture_only:
+                    return False
                 _abi.call("spmf_advi_step", a)
                 return
             h = cache.handles[key] = hp.value
+        if capture_only:
+            return True
         _abi.call("spmf_step_graph_launch", h, a.rng_step, a.adam_t, a.adam_lr, a.adam_beta1, a.adam_beta2,
                   a.adam_eps, a.clip_value, a.caller_stream)
         self.graph_launches += 1
