@@ -272,38 +272,44 @@ hot_tile_kernel(const unsigned char* __restrict__ xhot, const unsigned char* __r
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t ta = tm + lane_base + T::TM_GEV + (uint32_t)((i & 1) * T::TM_GEV_STRIDE);
     const int m = (warp & 3) * 16 + lane;          // column of the chunk held by this lane (lane < 16)
-    float g[16];
-    if (hq < 2) {
-      constexpr int HK = KK / 2;              // 16 or 8 latent dims per quarter
-      float gb[16];                           // the hi.lo half of the merged MMA
-      if constexpr (HK == 16) {
-        tmem_ld<16>(ta + HK * hq, g);
-        tmem_ld<16>(ta + T::NZ + HK * hq, gb);
-      } else {
-        tmem_ld<8>(ta + HK * hq, g);
-        tmem_ld<8>(ta + T::NZ + HK * hq, gb);
-      }
+    // NQD thread quarters read HK latent dims each (16 per quarter, 8 at KK = 16); the ones column
+    // (Gphi) goes to a quarter with spare registers
+    constexpr int NQD = KK >= 64 ? 4 : 2;
+    constexpr int HK = KK / NQD;
+    constexpr int ONES_Q = NQD == 4 ? 0 : 2;
+    if (hq < NQD) {
+      float g[HK], gb[HK];                    // gb: the hi.lo half of the merged MMA
+      tmem_ld<HK>(ta + HK * hq, g);
+      tmem_ld<HK>(ta + T::NZ + HK * hq, gb);
       if (lane < 16) {
 #pragma unroll
         for (int k = 0; k < HK; k += 4)
           *reinterpret_cast<float4*>(gst + m * T::G_STRIDE + HK * hq + k) =
               make_float4(g[k] + gb[k], g[k + 1] + gb[k + 1], g[k + 2] + gb[k + 2], g[k + 3] + gb[k + 3]);
       }
-    } else if (hq == 2) {
-      tmem_ld<8>(ta + KK, g);
-      if (lane < 16) gst[m * T::G_STRIDE + KK] = g[0];
+    }
+    if (hq == ONES_Q) {
+      float g1[8];
+      tmem_ld<8>(ta + KK, g1);
+      if (lane < 16) gst[m * T::G_STRIDE + KK] = g1[0];
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     asm volatile("bar.sync 1, %0;" ::"n"(kTileWorkThreads) : "memory");
     {
-      const int cl = tid >> 3, k = (tid & 7) * 4;          // 8 threads per column, 4 latent dims each
-      const int c = (c_begin + i) * 64 + cl;
-      if (c < H) {
-        if (k < KP) {
-          const float4 v = *reinterpret_cast<const float4*>(gst + cl * T::G_STRIDE + k);
-          atomicAdd(reinterpret_cast<float4*>(GEV + ((size_t)q * D + c) * REC + rec_pos(KP, SV, sv, k)), v);
+      constexpr int TPC = KK / 4;                          // threads per column, 4 latent dims each
+      constexpr int PASSES = 64 * TPC / kTileWorkThreads;  // 1 (KK <= 32) or 2 (KK = 64)
+#pragma unroll
+      for (int ps = 0; ps < (PASSES < 1 ? 1 : PASSES); ++ps) {
+        const int idx = ps * kTileWorkThreads + tid;
+        const int cl = idx / TPC, k = (idx % TPC) * 4;
+        const int c = (c_begin + i) * 64 + cl;
+        if (cl < 64 && c < H) {
+          if (k < KP) {
+            const float4 v = *reinterpret_cast<const float4*>(gst + cl * T::G_STRIDE + k);
+            atomicAdd(reinterpret_cast<float4*>(GEV + ((size_t)q * D + c) * REC + rec_pos(KP, SV, sv, k)), v);
+          }
+          if ((idx % TPC) == TPC - 1) atomicAdd(Gphi + ((size_t)q * D + c) * SV + sv, gst[cl * T::G_STRIDE + KK]);
         }
-        if ((tid & 7) == 7) atomicAdd(Gphi + ((size_t)q * D + c) * SV + sv, gst[cl * T::G_STRIDE + KK]);
       }
     }
   };
@@ -432,18 +438,20 @@ hot_tile_kernel(const unsigned char* __restrict__ xhot, const unsigned char* __r
   // ---- dZ of the 128 rows (several CTAs share a (rows, draw) slice when the column range is split:
   //      atomics) and the row scalars; thread quarter hq owns a quarter of the latent range
   {
-    constexpr int QK = KK / 4;                 // 8 or 4
-    float dzv[8], dzb[8];
-    tmem_ld<8>(tm + lane_base + T::TM_DZ + (QK == 8 ? 8 * hq : 8 * (hq >> 1)), dzv);
-    tmem_ld<8>(tm + lane_base + T::TM_DZ + KK + (QK == 8 ? 8 * hq : 8 * (hq >> 1)), dzb);
+    constexpr int QK = KK / 4;                 // latent dims per thread quarter: 4, 8 or 16
+    constexpr int LD = QK < 8 ? 8 : QK;        // tensor-memory columns read per quarter (>= 8 per load)
+    float dzv[LD], dzb[LD];
+    const int col0 = QK >= 8 ? QK * hq : 8 * (hq >> 1);
+    tmem_ld<LD>(tm + lane_base + T::TM_DZ + col0, dzv);
+    tmem_ld<LD>(tm + lane_base + T::TM_DZ + KK + col0, dzb);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) dzv[k] += dzb[k];
+    for (int k = 0; k < LD; ++k) dzv[k] += dzb[k];
     if (row < nrows) {
       float* dp = dzacc + ((size_t)q * nrows + row) * REC;
 #pragma unroll
       for (int k = 0; k < QK; k += 4) {
         const int kk = QK * hq + k;
-        const int src = (QK == 8) ? k : 4 * (hq & 1) + k;
+        const int src = (QK >= 8) ? k : 4 * (hq & 1) + k;
         if (kk < KP)
           atomicAdd(reinterpret_cast<float4*>(dp + rec_pos(KP, SV, sv, kk)),
                     make_float4(dzv[src], dzv[src + 1], dzv[src + 2], dzv[src + 3]));
@@ -471,32 +479,43 @@ rows_finish_kernel(const float* __restrict__ rowsum, const float* __restrict__ l
                    int nrows, const double* __restrict__ vsum, const float* __restrict__ z,
                    float* __restrict__ dzr, float* __restrict__ rowacc, int* __restrict__ gflag) {
   constexpr int REC = SV * KP;
-  static_assert(KP >= 4 && REC <= 128, "rows_finish: one warp covers a record");
+  static_assert(KP >= 4, "rows_finish: float4 k-vectors");
+  constexpr int NCH = (REC + 127) / 128;               // a warp covers 128 record floats per pass
   const RecMap rm = rec_map(KP);
   const int row = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31, q = blockIdx.y;
   if (row >= nrows) return;
   const float r = scale_rows ? rowsum[row] * inv_xi : 1.f;
-  const bool act = lane * 4 < REC;
-  const int sv = act ? (lane / rm.RG) % SV : -1;            // draw of this lane's k-vector
-  float zv = 0.f, z2 = 0.f;
-  if (act) {
-    const size_t o = ((size_t)q * nrows + row) * REC + lane * 4;
-    const float4 zz = *reinterpret_cast<const float4*>(z + o);
-    float4 d = *reinterpret_cast<float4*>(dzr + o);
-    const double* vs = vsum + (size_t)q * REC + lane * 4;
-    const float v0 = (float)vs[0], v1 = (float)vs[1], v2 = (float)vs[2], v3 = (float)vs[3];
-    zv = zz.x * v0 + zz.y * v1 + zz.z * v2 + zz.w * v3;
-    z2 = zz.x * zz.x + zz.y * zz.y + zz.z * zz.z + zz.w * zz.w;
-    d.x = r * (d.x - v0 - zz.x);           // dL/dz incl. the HalfNormal(1) z prior (poisson.py:599-604)
-    d.y = r * (d.y - v1 - zz.y);
-    d.z = r * (d.z - v2 - zz.z);
-    d.w = r * (d.w - v3 - zz.w);
-    *reinterpret_cast<float4*>(dzr + o) = d;
+  float zv[SV], z2[SV];
+#pragma unroll
+  for (int s = 0; s < SV; ++s) { zv[s] = 0.f; z2[s] = 0.f; }
+#pragma unroll
+  for (int ch = 0; ch < NCH; ++ch) {
+    const int p = ch * 128 + lane * 4;                 // first record float of this lane's k-vector
+    if (p < REC) {
+      const int sv = (p / (4 * rm.RG)) % SV;            // draw of the k-vector (spmf_record.cuh)
+      const size_t o = ((size_t)q * nrows + row) * REC + p;
+      const float4 zz = *reinterpret_cast<const float4*>(z + o);
+      float4 d = *reinterpret_cast<float4*>(dzr + o);
+      const double* vs = vsum + (size_t)q * REC + p;
+      const float v0 = (float)vs[0], v1 = (float)vs[1], v2 = (float)vs[2], v3 = (float)vs[3];
+      const float a = zz.x * v0 + zz.y * v1 + zz.z * v2 + zz.w * v3;
+      const float b = zz.x * zz.x + zz.y * zz.y + zz.z * zz.z + zz.w * zz.w;
+#pragma unroll
+      for (int s = 0; s < SV; ++s) {
+        zv[s] += sv == s ? a : 0.f;
+        z2[s] += sv == s ? b : 0.f;
+      }
+      d.x = r * (d.x - v0 - zz.x);           // dL/dz incl. the HalfNormal(1) z prior (poisson.py:599-604)
+      d.y = r * (d.y - v1 - zz.y);
+      d.z = r * (d.z - v2 - zz.z);
+      d.w = r * (d.w - v3 - zz.w);
+      *reinterpret_cast<float4*>(dzr + o) = d;
+    }
   }
   float* ra = rowacc + ((size_t)q * nrows + row) * 4 * SV;
 #pragma unroll
   for (int s = 0; s < SV; ++s) {
-    float a = sv == s ? zv : 0.f, b = sv == s ? z2 : 0.f;
+    float a = zv[s], b = z2[s];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       a += __shfl_xor_sync(0xffffffffu, a, o);
@@ -524,6 +543,9 @@ using namespace spmf;
     else if (KP == 16 && SV == 4) { CALL(16, 4); }                  \
     else if (KP == 16 && SV == 2) { CALL(16, 2); }                  \
     else if (KP == 8 && SV == 4) { CALL(8, 4); }                    \
+    else if (KP == 64 && SV == 4) { CALL(64, 4); }                  \
+    else if (KP == 64 && SV == 2) { CALL(64, 2); }                  \
+    else if (KP == 64 && SV == 1) { CALL(64, 1); }                  \
     else return SPMF_ERR_UNSUPPORTED;                               \
   } while (0)
 
