@@ -46,14 +46,26 @@ struct HotTile {
   static constexpr int Z_TILE = 128 * ZCPR * 16;        // per term; the two terms share rows: [hi | 1 | lo | 0]
   static constexpr int ZCPR2 = 2 * ZCPR;                // chunks per row of the combined Z tile
   static constexpr int W_TILE = 128 * 64 * 2;
-  static constexpr int NSTAGE = 3;                      // chunk inputs in flight
+  // 128 latent dims do not fit the fully pipelined plan (shared memory: 227 KB, tensor memory: 512
+  // columns): two input stages instead of three, one W buffer instead of two (the element-wise phase of
+  // chunk i+1 then waits for the MMAs of chunk i -- at K = 128 the kernel is MMA-bound anyway), the GEV
+  // flush staged in two halves, and no merged [hi | lo] MMAs (their "b" accumulator halves would need
+  // 864 tensor-memory columns): three MMAs per product into one accumulator instead.
+  static constexpr bool WIDE = KK > 64;
+  static constexpr bool MERGED = !WIDE;
+  static constexpr int NSTAGE = WIDE ? 2 : 3;           // chunk inputs in flight
+  static constexpr int WBUF = WIDE ? 1 : 2;             // W (hi, lo) buffers
+  static constexpr int GHALF = WIDE ? 2 : 1;            // GEV flush: staged 64 / GHALF columns at a time
   static constexpr int G_STRIDE = KK + 4;               // floats per staged GEV row (latent | 1 | pad): conflict-free
-  static constexpr int G_BYTES = 64 * G_STRIDE * 4;
-  static constexpr int SMEM = NSTAGE * STAGE + 2 * Z_TILE + 4 * W_TILE + G_BYTES + 128;   // W (hi, lo) double buffered
+  static constexpr int G_BYTES = (64 / GHALF) * G_STRIDE * 4;
+  static constexpr int SMEM = NSTAGE * STAGE + 2 * Z_TILE + 2 * WBUF * W_TILE + G_BYTES + 128;
   // tensor-memory columns: S | dZ (a | b) | GEV buffer 0 (a | b) | GEV buffer 1 (a | b); the "b" halves
-  // receive the hi.lo products of the merged MMAs and are added at read-out
-  static constexpr int TM_S = 0, TM_DZ = 64, TM_GEV = 64 + 2 * KK, TM_GEV_STRIDE = 2 * NZ;
-  static constexpr int TM_COLS = 512;                   // power of two >= 64 + 2 KK + 4 NZ (<= 288)
+  // (MERGED only) receive the hi.lo products of the merged MMAs and are added at read-out
+  static constexpr int ACC = MERGED ? 2 : 1;
+  static constexpr int TM_S = 0, TM_DZ = 64, TM_GEV = 64 + ACC * KK, TM_GEV_STRIDE = ACC * NZ;
+  static constexpr int TM_COLS = 512;                   // power of two >= 64 + ACC (KK + 2 NZ)  (<= 480)
+  static_assert(TM_GEV + 2 * TM_GEV_STRIDE <= 512, "tensor memory");
+  static_assert(SMEM <= 227 * 1024, "shared memory");
 };
 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {     // a -> low half
@@ -202,25 +214,27 @@ hot_tile_kernel(const unsigned char* __restrict__ xhot, const unsigned char* __r
   // ---- Z_s tile: this draw's z of the 128 rows as two bf16 terms + the ones column; the four thread
   // quarters write alternate 16-byte chunks of the row
   if (worker) {
-    float zr[KK + 8];
-#pragma unroll
-    for (int k = 0; k < KK + 8; ++k) zr[k] = 0.f;
-    if (row < nrows) {
-      const float* zp = z + ((size_t)q * nrows + row) * REC;
-#pragma unroll
-      for (int k = 0; k < KP; k += 4) {
-        const float4 v = __ldg(reinterpret_cast<const float4*>(zp + rec_pos(KP, SV, sv, k)));
-        zr[k] = v.x; zr[k + 1] = v.y; zr[k + 2] = v.z; zr[k + 3] = v.w;
-      }
-    }
-    zr[KK] = 1.f;                               // W^T . 1 = column sums of w  (Gphi)
+    const float* zp = z + ((size_t)q * nrows + (row < nrows ? row : 0)) * REC;
 #pragma unroll
     for (int j = 0; j < T::ZCPR; ++j) {
       if ((j & 3) != hq) continue;
+      float zr[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) zr[e] = 0.f;
+      if (8 * j < KP && row < nrows) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          if (8 * j + 4 * h < KP) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(zp + rec_pos(KP, SV, sv, 8 * j + 4 * h)));
+            zr[4 * h] = v.x; zr[4 * h + 1] = v.y; zr[4 * h + 2] = v.z; zr[4 * h + 3] = v.w;
+          }
+        }
+      }
+      if (8 * j == KK) zr[0] = 1.f;               // W^T . 1 = column sums of w  (Gphi)
       uint32_t hi[4], lo[4];
 #pragma unroll
       for (int p = 0; p < 4; ++p) {
-        const float a = zr[8 * j + 2 * p], b = zr[8 * j + 2 * p + 1];
+        const float a = zr[2 * p], b = zr[2 * p + 1];
         hi[p] = pack_bf16(a, b);
         lo[p] = pack_bf16(a - bf16_lo(hi[p]), b - bf16_hi(hi[p]));
       }
@@ -266,44 +280,56 @@ hot_tile_kernel(const unsigned char* __restrict__ xhot, const unsigned char* __r
   // lane (m/16)*32 + m%16, so a lane-owner store would scatter 16 lanes over 16 different records;
   // instead the tile is staged through shared memory and written out by all 512 workers, 8
   // consecutive threads per column (coalesced vector reductions).
-  float* const gst = reinterpret_cast<float*>(pWb + 4 * T::W_TILE);
+  float* const gst = reinterpret_cast<float*>(pWb + 2 * T::WBUF * T::W_TILE);
   auto flush_gev = [&](int i) {
     mbar_wait(bar_g[i & 1], (uint32_t)((i >> 1) & 1));
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t ta = tm + lane_base + T::TM_GEV + (uint32_t)((i & 1) * T::TM_GEV_STRIDE);
     const int m = (warp & 3) * 16 + lane;          // column of the chunk held by this lane (lane < 16)
-    // NQD thread quarters read HK latent dims each (16 per quarter, 8 at KK = 16); the ones column
-    // (Gphi) goes to a quarter with spare registers
+    // NQD thread quarters read HK latent dims each; the ones column (Gphi) goes to one of them
     constexpr int NQD = KK >= 64 ? 4 : 2;
-    constexpr int HK = KK / NQD;
+    constexpr int HK = KK / NQD;                    // 8, 16 or 32
     constexpr int ONES_Q = NQD == 4 ? 0 : 2;
+    float g[HK], g1 = 0.f;
     if (hq < NQD) {
-      float g[HK], gb[HK];                    // gb: the hi.lo half of the merged MMA
       tmem_ld<HK>(ta + HK * hq, g);
-      tmem_ld<HK>(ta + T::NZ + HK * hq, gb);
-      if (lane < 16) {
+      if constexpr (T::MERGED) {                    // + the hi.lo half of the merged MMA
+        float gb[HK];
+        tmem_ld<HK>(ta + T::NZ + HK * hq, gb);
 #pragma unroll
-        for (int k = 0; k < HK; k += 4)
-          *reinterpret_cast<float4*>(gst + m * T::G_STRIDE + HK * hq + k) =
-              make_float4(g[k] + gb[k], g[k + 1] + gb[k + 1], g[k + 2] + gb[k + 2], g[k + 3] + gb[k + 3]);
+        for (int k = 0; k < HK; ++k) g[k] += gb[k];
       }
     }
     if (hq == ONES_Q) {
-      float g1[8];
-      tmem_ld<8>(ta + KK, g1);
-      if (lane < 16) gst[m * T::G_STRIDE + KK] = g1[0];
+      float t8[8];
+      tmem_ld<8>(ta + KK, t8);
+      g1 = t8[0];
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    asm volatile("bar.sync 1, %0;" ::"n"(kTileWorkThreads) : "memory");
-    {
-      constexpr int TPC = KK / 4;                          // threads per column, 4 latent dims each
-      constexpr int PASSES = 64 * TPC / kTileWorkThreads;  // 1 (KK <= 32) or 2 (KK = 64)
+    // staged through shared memory 64 / GHALF columns at a time: tensor-memory lanes 0-15 of warps with
+    // (warp & 3) = w hold columns 16 w .. 16 w + 15
+    constexpr int CPH = 64 / T::GHALF;              // columns per half
 #pragma unroll
-      for (int ps = 0; ps < (PASSES < 1 ? 1 : PASSES); ++ps) {
+    for (int half = 0; half < T::GHALF; ++half) {
+      if (half > 0) asm volatile("bar.sync 1, %0;" ::"n"(kTileWorkThreads) : "memory");   // staging free again
+      const int ml = m - half * CPH;
+      if (lane < 16 && ml >= 0 && ml < CPH) {
+        if (hq < NQD) {
+#pragma unroll
+          for (int k = 0; k < HK; k += 4)
+            *reinterpret_cast<float4*>(gst + ml * T::G_STRIDE + HK * hq + k) = make_float4(g[k], g[k + 1], g[k + 2], g[k + 3]);
+        }
+        if (hq == ONES_Q) gst[ml * T::G_STRIDE + KK] = g1;
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(kTileWorkThreads) : "memory");
+      constexpr int TPC = KK / 4;                          // threads per column, 4 latent dims each
+      constexpr int PASSES = (CPH * TPC + kTileWorkThreads - 1) / kTileWorkThreads;
+#pragma unroll
+      for (int ps = 0; ps < PASSES; ++ps) {
         const int idx = ps * kTileWorkThreads + tid;
         const int cl = idx / TPC, k = (idx % TPC) * 4;
-        const int c = (c_begin + i) * 64 + cl;
-        if (cl < 64 && c < H) {
+        const int c = (c_begin + i) * 64 + half * CPH + cl;
+        if (cl < CPH && c < H) {
           if (k < KP) {
             const float4 v = *reinterpret_cast<const float4*>(gst + cl * T::G_STRIDE + k);
             atomicAdd(reinterpret_cast<float4*>(GEV + ((size_t)q * D + c) * REC + rec_pos(KP, SV, sv, k)), v);
@@ -318,7 +344,7 @@ hot_tile_kernel(const unsigned char* __restrict__ xhot, const unsigned char* __r
     if (elect_one()) {
       issue_load(0);
       if (n > 1) issue_load(1);
-      if (n > 2) issue_load(2);
+      if (T::NSTAGE > 2 && n > 2) issue_load(2);
     }
     __syncwarp();
   }
@@ -330,10 +356,12 @@ hot_tile_kernel(const unsigned char* __restrict__ xhot, const unsigned char* __r
 
   float xlog2 = 0.f, wmax = 0.f;
   for (int i = 0; i < n; ++i) {
-    const int st = i % T::NSTAGE, wb = i & 1;
+    const int st = i % T::NSTAGE, wb = T::WBUF == 1 ? 0 : (i & 1), gb_ = i & 1;
     if (worker) {
     wait_full(i);                                           // TMA data visible to this thread
     mbar_wait(bar_s, (uint32_t)(i & 1));                    // S(i) ready in tensor memory
+    if (T::WBUF == 1 && i >= 1)                             // one W buffer: chunk i-1's MMAs must have read it
+      mbar_wait(bar_g[(i - 1) & 1], (uint32_t)(((i - 1) >> 1) & 1));
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
     // ---- E: lambda, w = x / lambda, x log lambda for 16 columns of this thread's row; W -> shared
@@ -383,24 +411,39 @@ hot_tile_kernel(const unsigned char* __restrict__ xhot, const unsigned char* __r
     if (warp == 17) {
       // P2: dZ += W . EV      A = W K-major [128 x 64], B = EV MN-major (N = latent, K = 64 columns)
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      // two MMAs per k-step instead of three: W_hi . [EV_hi | EV_lo] (N = 2 KK, second half -> dZ_b)
-      // and W_lo . EV_hi (N = KK, into dZ_a): the W operand is fetched twice, not three times
-      constexpr uint32_t IDa = umma_idesc_bf16(128, 2 * KK, 0, 1), IDb = umma_idesc_bf16(128, KK, 0, 1);
       const uint64_t wo = (uint64_t)wb * kWStep, so = (uint64_t)st * kStageStep;
       const uint64_t dWh = umma_desc(sWb, 128, 1024) + wo, dWl = umma_desc(sWb + T::W_TILE, 128, 1024) + wo;
       const uint64_t dEn = umma_desc(sStage0 + T::X_TILE, 2 * T::CPR * 128, 128) + so;     // MN-major, k-group = 8 columns
       constexpr uint64_t kEStep = (uint64_t)(2 * 2 * T::CPR * 128 / 16);                   // 16 columns
+      if constexpr (T::MERGED) {
+        // two MMAs per k-step instead of three: W_hi . [EV_hi | EV_lo] (N = 2 KK, second half -> dZ_b)
+        // and W_lo . EV_hi (N = KK, into dZ_a): the W operand is fetched twice, not three times
+        constexpr uint32_t IDa = umma_idesc_bf16(128, 2 * KK, 0, 1), IDb = umma_idesc_bf16(128, KK, 0, 1);
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
-        umma_bf16_elect(tm + T::TM_DZ, dWh + (uint64_t)(j * 16), dEn + j * kEStep, IDa, (i | j) ? 1u : 0u);
+        for (int j = 0; j < 4; ++j)
+          umma_bf16_elect(tm + T::TM_DZ, dWh + (uint64_t)(j * 16), dEn + j * kEStep, IDa, (i | j) ? 1u : 0u);
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
-        umma_bf16_elect(tm + T::TM_DZ, dWl + (uint64_t)(j * 16), dEn + j * kEStep, IDb, 1u);
-      umma_commit_elect(bar_g[wb]);
-      // chunk i-1 is fully consumed once its MMAs are done: refill its stage with chunk i+2
-      if (i >= 1 && i + 2 < n) {
+        for (int j = 0; j < 4; ++j)
+          umma_bf16_elect(tm + T::TM_DZ, dWl + (uint64_t)(j * 16), dEn + j * kEStep, IDb, 1u);
+      } else {
+        // 128 latent dims: hi.hi, hi.lo, lo.hi as three MMAs of N = KK into ONE accumulator
+        constexpr uint32_t ID = umma_idesc_bf16(128, KK, 0, 1);
+        const uint64_t dEl = umma_desc(sStage0 + T::X_TILE + T::CPR * 128, 2 * T::CPR * 128, 128) + so;   // lo latent chunks
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          umma_bf16_elect(tm + T::TM_DZ, dWh + (uint64_t)(j * 16), dEn + j * kEStep, ID, (i | j) ? 1u : 0u);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          umma_bf16_elect(tm + T::TM_DZ, dWh + (uint64_t)(j * 16), dEl + j * kEStep, ID, 1u);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          umma_bf16_elect(tm + T::TM_DZ, dWl + (uint64_t)(j * 16), dEn + j * kEStep, ID, 1u);
+      }
+      umma_commit_elect(bar_g[gb_]);
+      // chunk i-1 is fully consumed once its MMAs are done: refill its stage with chunk i + NSTAGE - 1
+      if (i >= 1 && i + T::NSTAGE - 1 < n) {
         mbar_wait(bar_g[(i - 1) & 1], (uint32_t)(((i - 1) >> 1) & 1));
-        if (elect_one()) issue_load(i + 2);
+        if (elect_one()) issue_load(i + T::NSTAGE - 1);
         __syncwarp();
       }
     } else if (warp == 16) {
@@ -412,20 +455,35 @@ hot_tile_kernel(const unsigned char* __restrict__ xhot, const unsigned char* __r
         issue_p1(i + 1);
       }
       // P3: GEV = W^T . [Z | 1]   A = W MN-major (M = 64 columns, K = 128 rows), B = Z MN-major (N = NZ)
-      // merged the same way: W_hi^T . [Z_hi | 1 | Z_lo | 0] (N = 2 NZ) and W_lo^T . [Z_hi | 1] (N = NZ)
-      constexpr uint32_t IDa = umma_idesc_bf16(64, 2 * T::NZ, 1, 1), IDb = umma_idesc_bf16(64, T::NZ, 1, 1);
       const uint64_t wo = (uint64_t)wb * kWStep;
       const uint64_t dWh = umma_desc(sWb, 1024, 128) + wo, dWl = umma_desc(sWb + T::W_TILE, 1024, 128) + wo;
       const uint64_t dZn = umma_desc(sZ0, T::ZCPR2 * 128, 128);
       constexpr uint64_t kZStep = (uint64_t)(2 * T::ZCPR2 * 128 / 16);                      // 16 rows
-      const uint32_t tg = tm + T::TM_GEV + (uint32_t)(wb * T::TM_GEV_STRIDE);
+      const uint32_t tg = tm + T::TM_GEV + (uint32_t)(gb_ * T::TM_GEV_STRIDE);
+      if constexpr (T::MERGED) {
+        // merged the same way: W_hi^T . [Z_hi | 1 | Z_lo | 0] (N = 2 NZ) and W_lo^T . [Z_hi | 1] (N = NZ)
+        constexpr uint32_t IDa = umma_idesc_bf16(64, 2 * T::NZ, 1, 1), IDb = umma_idesc_bf16(64, T::NZ, 1, 1);
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        umma_bf16_elect(tg, dWh + (uint64_t)(j * (2048 / 16)), dZn + j * kZStep, IDa, j ? 1u : 0u);
+        for (int j = 0; j < 8; ++j)
+          umma_bf16_elect(tg, dWh + (uint64_t)(j * (2048 / 16)), dZn + j * kZStep, IDa, j ? 1u : 0u);
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        umma_bf16_elect(tg, dWl + (uint64_t)(j * (2048 / 16)), dZn + j * kZStep, IDb, 1u);
-      umma_commit_elect(bar_g[wb]);
+        for (int j = 0; j < 8; ++j)
+          umma_bf16_elect(tg, dWl + (uint64_t)(j * (2048 / 16)), dZn + j * kZStep, IDb, 1u);
+      } else {
+        // three MMAs of N = NZ into one accumulator: W_hi^T.[Z_hi | 1], W_hi^T.[Z_lo | 0], W_lo^T.[Z_hi | 1]
+        constexpr uint32_t ID = umma_idesc_bf16(64, T::NZ, 1, 1);
+        const uint64_t dZl = umma_desc(sZ0 + T::ZCPR * 128, T::ZCPR2 * 128, 128);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          umma_bf16_elect(tg, dWh + (uint64_t)(j * (2048 / 16)), dZn + j * kZStep, ID, j ? 1u : 0u);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          umma_bf16_elect(tg, dWh + (uint64_t)(j * (2048 / 16)), dZl + j * kZStep, ID, 1u);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          umma_bf16_elect(tg, dWl + (uint64_t)(j * (2048 / 16)), dZn + j * kZStep, ID, 1u);
+      }
+      umma_commit_elect(bar_g[gb_]);
     } else if (i >= 1) {
       // workers: the previous chunk's MMAs have had a whole element-wise phase to finish
       flush_gev(i - 1);
@@ -438,14 +496,17 @@ hot_tile_kernel(const unsigned char* __restrict__ xhot, const unsigned char* __r
   // ---- dZ of the 128 rows (several CTAs share a (rows, draw) slice when the column range is split:
   //      atomics) and the row scalars; thread quarter hq owns a quarter of the latent range
   {
-    constexpr int QK = KK / 4;                 // latent dims per thread quarter: 4, 8 or 16
+    constexpr int QK = KK / 4;                 // latent dims per thread quarter: 4, 8, 16 or 32
     constexpr int LD = QK < 8 ? 8 : QK;        // tensor-memory columns read per quarter (>= 8 per load)
-    float dzv[LD], dzb[LD];
+    float dzv[LD];
     const int col0 = QK >= 8 ? QK * hq : 8 * (hq >> 1);
     tmem_ld<LD>(tm + lane_base + T::TM_DZ + col0, dzv);
-    tmem_ld<LD>(tm + lane_base + T::TM_DZ + KK + col0, dzb);
+    if constexpr (T::MERGED) {
+      float dzb[LD];
+      tmem_ld<LD>(tm + lane_base + T::TM_DZ + KK + col0, dzb);
 #pragma unroll
-    for (int k = 0; k < LD; ++k) dzv[k] += dzb[k];
+      for (int k = 0; k < LD; ++k) dzv[k] += dzb[k];
+    }
     if (row < nrows) {
       float* dp = dzacc + ((size_t)q * nrows + row) * REC;
 #pragma unroll
@@ -546,6 +607,9 @@ using namespace spmf;
     else if (KP == 64 && SV == 4) { CALL(64, 4); }                  \
     else if (KP == 64 && SV == 2) { CALL(64, 2); }                  \
     else if (KP == 64 && SV == 1) { CALL(64, 1); }                  \
+    else if (KP == 128 && SV == 4) { CALL(128, 4); }                \
+    else if (KP == 128 && SV == 2) { CALL(128, 2); }                \
+    else if (KP == 128 && SV == 1) { CALL(128, 1); }                \
     else return SPMF_ERR_UNSUPPORTED;                               \
   } while (0)
 

@@ -1210,8 +1210,7 @@ int spmf_hybrid_supported(int K, int S) {
   const int KP = spmf_kpad(K), SV = spmf_draw_vec(S);
   if ((KP == 32 && (SV == 4 || SV == 2 || SV == 1)) || (KP == 16 && (SV == 4 || SV == 2)) || (KP == 8 && SV == 4))
     return 2;
-  if (KP == 64) return 2;              // fused tile kernel with 64 latent dims (spmf_hot_tile.cu)
-  if (KP == 128) return 1;
+  if (KP == 64 || KP == 128) return 2;     // fused tile kernel with 64 / 128 latent dims (spmf_hot_tile.cu)
   return 0;
 }
 

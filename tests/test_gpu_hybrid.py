@@ -175,7 +175,8 @@ def _step(model, eng, params, noise, batch):
     (96, 8, 130, 4, "linear", False),      # REC=32
     (160, 32, 70, 2, "noise", True),       # SV=2 -> REC=64
     (130, 20, 300, 8, "sparse", False),    # K padded to 32, two draw groups
-    (150, 128, 140, 2, "sparse", True),    # K=128 (C5): REC=256 -> GEMMs in two blocks of 128 channels, no tile kernel
+    (150, 128, 140, 2, "sparse", True),    # K=128 (C5): REC=256 -> GEMMs in two blocks of 128 channels; wide tile kernel
+    (320, 128, 200, 4, "sparse", False),   # K=128, S=4 (REC=512): 5 column chunks over 2 input stages, ragged row tiles
     (100, 64, 96, 4, "noise", False),      # K=64, REC=256: fused tile kernel with 64 latent dims
     (300, 64, 200, 4, "sparse", True),     # K=64: hot + cold columns, ragged row tiles, 5 column chunks
     (140, 50, 130, 2, "linear", False),    # K padded to 64, SV=2 -> REC=128
@@ -200,15 +201,14 @@ def test_hybrid_step_matches_oracle_and_gather_path(D, K, B, S, kind, big):
     # tile: per-nonzero terms of the hot block in the fused tcgen05 kernel; hybrid: tensor cores for the
     # two count products only; gather: CUDA-core kernels only
     for name, dens, mode in (("tile", 0.03, 2), ("hybrid", 0.03, 1), ("gather", 0.0, 0)):
-        if name == "tile" and K > 64:
-            continue                      # the fused tile kernel covers latent dims <= 64
+        if name == "tile" and K > 128:
+            continue                      # the fused tile kernel covers latent dims <= 128
         model = spmf_b200.PoissonFactorization(latent_dim=K, feature_dim=D, u_tau_scale=1.0 / np.sqrt(N * D),
                                                device=dev, hot_density=dens)
         model.compute_scales(lambda: [{'counts': x}])
         eng = model._engine_for(S)
         eng.hot_mode = mode
-        if K > 64 and name == "hybrid":
-            eng.hybrid_ok = True              # K = 128: the GEMM-only hybrid is opt-in (SPMF_WIDE_HYBRID=1)
+        eng.hybrid_ok = eng.hybrid_ok or name == "hybrid"
         if name != "gather":
             assert eng.hot_cols >= 64 and eng.hybrid_ok, (eng.hot_cols, eng.hybrid_ok)
         else:
