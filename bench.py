@@ -299,7 +299,7 @@ def main():
     # the device (prefetched one batch ahead on a copy stream), runs the step through the public
     # API, and its loss is read back D2H -- all inside the timed region.
     from spmf_b200.data import prefetch_to_device
-    host = HostCsr.from_shard(shard)
+    host = HostCsr.from_shard(shard, compact=os.environ.get("BENCH_HOST_FORMAT", "u8") if os.environ.get("BENCH_HOST_FORMAT", "u8") != "u16" else True)
     hbatches = [host.batch(i * B, B) for i in range(len(batches))]
 
     loss_bufs = [torch.empty(1, dtype=torch.float64).pin_memory() for _ in range(2)]

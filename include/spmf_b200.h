@@ -160,6 +160,11 @@ int spmf_csr_to_csc(const long long* rowptr, const int* cols, const float* vals,
  * widened on the device (either source may be NULL = that array was sent at full width). */
 int spmf_csr_unpack16(const unsigned short* cols16, const unsigned short* vals16, long long nnz,
                       int* cols, float* vals, void* stream);
+/* 2-byte transfer format: rowptr (zero-based, nrows+1) indexes two byte streams -- gaps8[j] = col_j - col_{j-1} - 1
+ * within the row (col_{-1} = -1; wider gaps are bridged on the host by zero-valued entries) and vals8[j] = count,
+ * 255 = "see the overflow list" (ovf_idx[i] = entry, ovf_val[i] = its count).  Expanded to int32 / fp32 here. */
+int spmf_csr_unpack8(const long long* rowptr, const unsigned char* gaps8, const unsigned char* vals8, int nrows,
+                     const int* ovf_idx, const float* ovf_val, int n_ovf, int* cols, float* vals, void* stream);
 /* dense (B,D) fp32 counts -> CSR (rowptr[B+1] int64, cols, vals); two calls: count then fill. */
 int spmf_dense_count(const float* x, int nrows, int D, long long* rowptr, void* stream);
 int spmf_dense_fill(const float* x, int nrows, int D, const long long* rowptr, int* cols, float* vals,

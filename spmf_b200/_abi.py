@@ -69,6 +69,7 @@ _SIGS = {
     "spmf_csc_scratch_ints": (i64, [i32]),
     "spmf_csr_to_csc": (i32, [p, p, p, i32, i32, p, p, p, p, p]),
     "spmf_csr_unpack16": (i32, [p, p, i64, p, p, p]),
+    "spmf_csr_unpack8": (i32, [p, p, p, i32, p, p, i32, p, p, p]),
     "spmf_dense_count": (i32, [p, i32, i32, p, p]),
     "spmf_dense_fill": (i32, [p, i32, i32, p, p, p, p]),
     "spmf_version": (C.c_char_p, []),

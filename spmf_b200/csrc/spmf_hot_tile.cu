@@ -546,6 +546,11 @@ rows_finish_kernel(const float* __restrict__ rowsum, const float* __restrict__ l
   const int row = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31, q = blockIdx.y;
   if (row >= nrows) return;
   const float r = scale_rows ? rowsum[row] * inv_xi : 1.f;
+  // the row scalars' read-modify-write is issued up front (lane s owns draw s) so that its latency
+  // overlaps the record traffic instead of trailing it as four dependent round trips of lane 0
+  float* ra = rowacc + ((size_t)q * nrows + row) * 4 * SV;
+  const float lg = lgam[row];
+  const float ra0 = lane < SV ? ra[lane] : 0.f;
   float zv[SV], z2[SV];
 #pragma unroll
   for (int s = 0; s < SV; ++s) { zv[s] = 0.f; z2[s] = 0.f; }
@@ -573,7 +578,7 @@ rows_finish_kernel(const float* __restrict__ rowsum, const float* __restrict__ l
       *reinterpret_cast<float4*>(dzr + o) = d;
     }
   }
-  float* ra = rowacc + ((size_t)q * nrows + row) * 4 * SV;
+  float am = 0.f, bm = 0.f;                  // this lane's draw (lane < SV)
 #pragma unroll
   for (int s = 0; s < SV; ++s) {
     float a = zv[s], b = z2[s];
@@ -582,13 +587,14 @@ rows_finish_kernel(const float* __restrict__ rowsum, const float* __restrict__ l
       a += __shfl_xor_sync(0xffffffffu, a, o);
       b += __shfl_xor_sync(0xffffffffu, b, o);
     }
-    if (lane == 0) {
-      ra[0 * SV + s] -= lgam[row];
-      ra[1 * SV + s] = a;
-      ra[2 * SV + s] = b;
-      // closed-form sum_d rate of this row is not finite: some entry's rate is not (poisson.py:606-616)
-      if (gflag && !(fabsf(a) <= 3.402823466e38f)) atomicOr(gflag, 1);
-    }
+    if (lane == s) { am = a; bm = b; }
+  }
+  if (lane < SV) {
+    ra[0 * SV + lane] = ra0 - lg;
+    ra[1 * SV + lane] = am;
+    ra[2 * SV + lane] = bm;
+    // closed-form sum_d rate of this row is not finite: some entry's rate is not (poisson.py:606-616)
+    if (gflag && !(fabsf(am) <= 3.402823466e38f)) atomicOr(gflag, 1);
   }
 }
 

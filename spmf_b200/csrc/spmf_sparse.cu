@@ -833,6 +833,40 @@ __global__ void csr_unpack16_kernel(const unsigned short* __restrict__ c16,
   }
 }
 
+// 2-byte transfer format of a CSR batch (1 byte per column id + 1 byte per count): per row the stored
+// byte of entry j is  col_j - col_{j-1} - 1  (col_{-1} = -1), so a row's column ids are an inclusive prefix
+// sum; gaps wider than 256 are bridged on the host by explicit zero-valued entries, counts above 254 are
+// sent as the byte 255 and patched from a short (entry index, value) list.  One warp per row.
+__global__ void __launch_bounds__(256)
+csr_unpack8_kernel(const long long* __restrict__ rowptr, const unsigned char* __restrict__ gaps8,
+                   const unsigned char* __restrict__ vals8, int nrows, int* __restrict__ cols,
+                   float* __restrict__ vals) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= nrows) return;
+  const long long j0 = rowptr[row], j1 = rowptr[row + 1];
+  int base = -1;                                              // column of the previous entry
+  for (long long j = j0; j < j1; j += 32) {
+    const long long jj = j + lane;
+    int g = jj < j1 ? (int)gaps8[jj] + 1 : 0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {                        // inclusive warp scan
+      const int t = __shfl_up_sync(0xffffffffu, g, o);
+      if (lane >= o) g += t;
+    }
+    if (jj < j1) {
+      cols[jj] = base + g;
+      vals[jj] = (float)vals8[jj];
+    }
+    base += __shfl_sync(0xffffffffu, g, 31);
+  }
+}
+__global__ void csr_patch_vals_kernel(const int* __restrict__ idx, const float* __restrict__ val, int n,
+                                      float* __restrict__ vals) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) vals[idx[i]] = val[i];
+}
+
 __global__ void dense_count_kernel(const float* __restrict__ x, int nrows, int D,
                                    long long* __restrict__ cnt) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -1428,6 +1462,17 @@ int spmf_csr_unpack16(const unsigned short* cols16, const unsigned short* vals16
   long long blocks = (nnz + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
   csr_unpack16_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(cols16, vals16, nnz, cols, vals);
+  SPMF_CHECK_LAUNCH();
+  return SPMF_OK;
+}
+
+int spmf_csr_unpack8(const long long* rowptr, const unsigned char* gaps8, const unsigned char* vals8, int nrows,
+                     const int* ovf_idx, const float* ovf_val, int n_ovf, int* cols, float* vals, void* stream) {
+  if (!rowptr || !gaps8 || !vals8 || !cols || !vals || nrows <= 0 || n_ovf < 0 || (n_ovf && (!ovf_idx || !ovf_val)))
+    return SPMF_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  csr_unpack8_kernel<<<(unsigned)((nrows + 7) / 8), 256, 0, st>>>(rowptr, gaps8, vals8, nrows, cols, vals);
+  if (n_ovf) csr_patch_vals_kernel<<<(unsigned)((n_ovf + 255) / 256), 256, 0, st>>>(ovf_idx, ovf_val, n_ovf, vals);
   SPMF_CHECK_LAUNCH();
   return SPMF_OK;
 }

@@ -310,10 +310,18 @@ def synth_scrna_csr_device(nrows, D, density=0.05, seed=0, device="cuda", sigma_
 # ---------------------------------------------------------------------------
 @dataclass
 class HostCsrBatch:
-    rowptr: torch.Tensor   # int64 [nrows+1], zero-based, pinned host
-    cols: torch.Tensor     # int32 or uint16 (compact) [nnz], pinned host
-    vals: torch.Tensor     # fp32 or uint16 (compact) [nnz], pinned host
+    """One minibatch in pinned host memory, as zero-copy views of its `HostCsr`.  `rowptr` holds ABSOLUTE
+    offsets (view of the shard's row pointers); `base` is subtracted on the device after the copy."""
+    rowptr: torch.Tensor   # int64 [nrows+1], pinned host; offsets relative to `base`
+    cols: Optional[torch.Tensor]     # int32 or uint16 (compact) [nnz], pinned host (None in the 2-byte format)
+    vals: Optional[torch.Tensor]     # fp32 or uint16 (compact) [nnz], pinned host (None in the 2-byte format)
     D: int
+    base: int = 0
+    # 2-byte format (spmf_csr_unpack8): column gaps and counts as bytes + the overflow list of large counts
+    gaps8: Optional[torch.Tensor] = None
+    vals8: Optional[torch.Tensor] = None
+    ovf_idx: Optional[torch.Tensor] = None     # int32, entry index relative to this batch
+    ovf_val: Optional[torch.Tensor] = None     # fp32
 
     @property
     def nrows(self):
@@ -321,11 +329,46 @@ class HostCsrBatch:
 
     @property
     def nnz(self):
-        return int(self.vals.numel())
+        return int(self.vals8.numel() if self.vals8 is not None else self.vals.numel())
 
     def nbytes(self):
-        return (self.rowptr.numel() * 8 + self.cols.numel() * self.cols.element_size()
-                + self.vals.numel() * self.vals.element_size())
+        n = self.rowptr.numel() * 8
+        for t in (self.cols, self.vals, self.gaps8, self.vals8, self.ovf_idx, self.ovf_val):
+            if t is not None:
+                n += t.numel() * t.element_size()
+        return n
+
+
+def encode_u8(rowptr, cols, vals):
+    """CSR -> the 2-byte transfer format (see spmf_csr_unpack8 in include/spmf_b200.h).  Returns (rowptr',
+    gaps8, vals8, ovf_idx, ovf_val) as numpy arrays; gaps wider than 256 columns are bridged by explicit
+    zero-valued entries (so rowptr' counts those too), counts that are not integers in [0, 254] go to the
+    overflow list."""
+    rowptr = np.asarray(rowptr, dtype=np.int64)
+    cols = np.asarray(cols, dtype=np.int64)
+    vals = np.asarray(vals, dtype=np.float32)
+    n = rowptr.size - 1
+    counts = np.diff(rowptr)
+    row_of = np.repeat(np.arange(n), counts)
+    order = np.lexsort((cols, row_of))                     # columns ascending inside every row
+    cols, vals = cols[order], vals[order]
+    prev = np.empty_like(cols)
+    prev[1:] = cols[:-1]
+    prev[rowptr[:-1][counts > 0]] = -1
+    gap = cols - prev - 1
+    npad = gap // 256
+    rep = npad + 1
+    ends = np.cumsum(rep)
+    total = int(ends[-1]) if ends.size else 0
+    gaps8 = np.full(total, 255, dtype=np.uint8)            # padding entries: +256 columns, count 0
+    vals8 = np.zeros(total, dtype=np.uint8)
+    pos = ends - 1
+    gaps8[pos] = (gap - 256 * npad).astype(np.uint8)
+    small = (vals >= 0) & (vals <= 254) & (vals == np.round(vals))
+    vals8[pos] = np.where(small, vals, 255).astype(np.uint8)
+    ovf = ~small
+    new_off = np.concatenate([[0], ends]).astype(np.int64)
+    return new_off[rowptr], gaps8, vals8, pos[ovf].astype(np.int64), vals[ovf].astype(np.float32)
 
 
 class HostCsr:
@@ -333,13 +376,28 @@ class HostCsr:
 
     compact=True stores column ids as uint16 when D <= 65536 and counts as uint16 when they are
     integers <= 65535 (count data almost always is): 4 B instead of 8 B per nonzero cross PCIe and
-    a kernel widens them on the device."""
+    a kernel widens them on the device.  compact="u8" goes to 2 B per nonzero: one byte for the column
+    gap inside the row and one for the count (`encode_u8`), expanded by spmf_csr_unpack8 -- with 8 ranks
+    streaming 8,192 x 20,000 batches the H2D traffic is what limits the end-to-end step."""
 
     def __init__(self, rowptr, cols, vals, D, compact=True):
-        self.rowptr = torch.as_tensor(rowptr).to(torch.int64).contiguous()
+        self.D = int(D)
+        self.u8 = compact == "u8"
+        if self.u8:
+            rp, g8, v8, oi, ov = encode_u8(torch.as_tensor(rowptr).cpu().numpy(), torch.as_tensor(cols).cpu().numpy(),
+                                           torch.as_tensor(vals).cpu().numpy())
+            self.rowptr = torch.from_numpy(rp).contiguous().pin_memory()
+            self.gaps8 = torch.from_numpy(g8).pin_memory()
+            self.vals8 = torch.from_numpy(v8).pin_memory()
+            self._ovf_pos = oi                                  # sorted (entries are visited in order)
+            self.ovf_idx_all = torch.from_numpy(oi.astype(np.int32))
+            self.ovf_val_all = torch.from_numpy(ov)
+            self.cols = self.vals = None
+            self.nrows = self.rowptr.numel() - 1
+            return
+        self.rowptr = torch.as_tensor(rowptr).to(torch.int64).contiguous().pin_memory()
         cols = torch.as_tensor(cols).to(torch.int32).contiguous()
         vals = torch.as_tensor(vals).to(torch.float32).contiguous()
-        self.D = int(D)
         self.nrows = self.rowptr.numel() - 1
         if compact and self.D <= 65536:
             cols = cols.to(torch.uint16)
@@ -353,9 +411,16 @@ class HostCsr:
         return cls(shard.rowptr.cpu(), shard.cols.cpu(), shard.vals.cpu(), shard.D, compact)
 
     def batch(self, row0, nrows) -> HostCsrBatch:
+        """Zero-copy views (nothing is allocated or pinned per batch)."""
         j0, j1 = int(self.rowptr[row0]), int(self.rowptr[row0 + nrows])
-        rp = (self.rowptr[row0:row0 + nrows + 1] - j0).contiguous().pin_memory()
-        return HostCsrBatch(rp, self.cols[j0:j1], self.vals[j0:j1], self.D)
+        rp = self.rowptr[row0:row0 + nrows + 1]
+        if self.u8:
+            a, b = np.searchsorted(self._ovf_pos, [j0, j1])
+            oi = (self.ovf_idx_all[a:b] - j0).to(torch.int32).pin_memory() if b > a else None
+            ov = self.ovf_val_all[a:b].clone().pin_memory() if b > a else None
+            return HostCsrBatch(rp, None, None, self.D, base=j0, gaps8=self.gaps8[j0:j1], vals8=self.vals8[j0:j1],
+                                ovf_idx=oi, ovf_val=ov)
+        return HostCsrBatch(rp, self.cols[j0:j1], self.vals[j0:j1], self.D, base=j0)
 
     def iter_batches(self, batch_rows):
         for r0 in range(0, self.nrows, batch_rows):
@@ -383,6 +448,10 @@ class BatchUploader:
         self.vals = torch.empty(n, dtype=torch.float32, device=dev)
         self.c16 = torch.empty(n, dtype=torch.uint16, device=dev)
         self.v16 = torch.empty(n, dtype=torch.uint16, device=dev)
+        self.g8 = torch.empty(n, dtype=torch.uint8, device=dev)       # 2-byte format staging
+        self.v8 = torch.empty(n, dtype=torch.uint8, device=dev)
+        self.ovf_i = torch.empty(max(n // 64, 1024), dtype=torch.int32, device=dev)
+        self.ovf_v = torch.empty(max(n // 64, 1024), dtype=torch.float32, device=dev)
         self.rowsum = torch.empty(max(rows, 1), dtype=torch.float32, device=dev)
         self.lgam = torch.empty(max(rows, 1), dtype=torch.float32, device=dev)
         self.colptr = torch.empty(self.D + 1, dtype=torch.int32, device=dev)
@@ -411,13 +480,30 @@ class BatchUploader:
             self._alloc(max(n, self.cap_rows), max(int(nnz * 1.25), self.cap_nnz))
         st = _stream()
         self.rowptr[:n + 1].copy_(hb.rowptr, non_blocking=True)
+        if hb.base:
+            self.rowptr[:n + 1].sub_(hb.base)              # the host sends a view of its absolute row pointers
         c16 = v16 = None
-        if hb.cols.dtype == torch.uint16:
+        if hb.gaps8 is not None:
+            # 2 bytes per nonzero over PCIe; expanded to int32 / fp32 by one kernel (+ a patch of the few large counts)
+            self.g8[:nnz].copy_(hb.gaps8, non_blocking=True)
+            self.v8[:nnz].copy_(hb.vals8, non_blocking=True)
+            novf = 0 if hb.ovf_idx is None else hb.ovf_idx.numel()
+            if novf > self.ovf_i.numel():
+                self.ovf_i = torch.empty(2 * novf, dtype=torch.int32, device=self.device)
+                self.ovf_v = torch.empty(2 * novf, dtype=torch.float32, device=self.device)
+            if novf:
+                self.ovf_i[:novf].copy_(hb.ovf_idx, non_blocking=True)
+                self.ovf_v[:novf].copy_(hb.ovf_val, non_blocking=True)
+            _abi.call("spmf_csr_unpack8", _ptr(self.rowptr), _ptr(self.g8), _ptr(self.v8), n, _ptr(self.ovf_i),
+                      _ptr(self.ovf_v), novf, _ptr(self.cols), _ptr(self.vals), st)
+        elif hb.cols.dtype == torch.uint16:
             c16 = self.c16[:nnz]
             c16.copy_(hb.cols, non_blocking=True)
         else:
             self.cols[:nnz].copy_(hb.cols, non_blocking=True)
-        if hb.vals.dtype == torch.uint16:
+        if hb.gaps8 is not None:
+            pass
+        elif hb.vals.dtype == torch.uint16:
             v16 = self.v16[:nnz]
             v16.copy_(hb.vals, non_blocking=True)
         else:

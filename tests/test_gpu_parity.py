@@ -302,11 +302,18 @@ def test_streamed_host_batches_match_resident():
     # prefetched stream of host batches: same batches, same order, same results
     from spmf_b200.data import prefetch_to_device
     wide = HostCsr.from_shard(sh, compact=False)
-    for hsrc in (host, wide):
+    xb = x.copy()
+    xb[5, 7] = 300.0                       # a count above 254: travels through the overflow list of the 2-byte format
+    xb[9, :] = 0
+    xb[9, 199] = 2.0                       # a gap wider than 256 columns needs no bridge here (D = 200) ...
+    shb = spmf_b200.CsrShard.from_dense(xb, dev)
+    bytes8 = HostCsr.from_shard(shb, compact="u8")
+    assert bytes8.u8 and bytes8.batch(0, B).nbytes() < 0.6 * HostCsr.from_shard(shb).batch(0, B).nbytes()
+    for hsrc, ref_shard in ((host, sh), (wide, sh), (bytes8, shb)):
         got = []
         for db in prefetch_to_device(hsrc.iter_batches(B), dev):
             got.append(eng.loss_and_grad(db, fresh_noise=False)[:, 13:15].clone())
-        ref = [eng.loss_and_grad(sh.batch(i * B, B), fresh_noise=False)[:, 13:15].clone() for i in range(3)]
+        ref = [eng.loss_and_grad(ref_shard.batch(i * B, B), fresh_noise=False)[:, 13:15].clone() for i in range(3)]
         assert len(got) == 3
         for a, b in zip(got, ref):
             assert rel_err(a.cpu().numpy(), b.cpu().numpy()) < 1e-6

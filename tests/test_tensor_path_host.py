@@ -77,3 +77,26 @@ def test_waic_terms_formula():
     np.testing.assert_allclose(pw.numpy(), ll.var(0, ddof=1), rtol=1e-5)
     one, zero = waic_terms(torch.tensor(ll[:1]))
     assert np.allclose(one.numpy(), ll[0]) and (zero == 0).all()
+
+
+def test_two_byte_transfer_format_round_trip():
+    """encode_u8 (host side of spmf_csr_unpack8): gaps / counts as bytes, wide gaps bridged by zero entries,
+    large counts through the overflow list -- decoded here by the definition of the format."""
+    import scipy.sparse as sp
+    from spmf_b200.data import encode_u8
+    rng = np.random.default_rng(3)
+    X = sp.random(40, 5000, density=0.004, random_state=2, format='csr')
+    X.data = np.ceil(X.data * 600).astype(np.float32)          # counts up to 600: some above 254
+    X = X.tolil(); X[7, :] = 0; X[8, 4999] = 3; X = X.tocsr(); X.eliminate_zeros()
+    rp, g8, v8, oi, ov = encode_u8(X.indptr, X.indices, X.data)
+    assert g8.dtype == np.uint8 and v8.dtype == np.uint8 and rp[0] == 0 and rp[-1] == g8.size == v8.size
+    assert g8.size > X.nnz                                       # bridges were needed (mean gap ~250 columns)
+    vals = v8.astype(np.float32)
+    assert (vals[oi] == 255).all()
+    vals[oi] = ov
+    D = np.zeros(X.shape, np.float32)
+    for r in range(X.shape[0]):
+        c = np.cumsum(g8[rp[r]:rp[r + 1]].astype(np.int64) + 1) - 1
+        assert (np.diff(c) > 0).all() and (c.size == 0 or c[-1] < X.shape[1])
+        D[r, c] = vals[rp[r]:rp[r + 1]]
+    assert np.array_equal(D, X.toarray())
