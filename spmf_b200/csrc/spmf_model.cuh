@@ -246,7 +246,10 @@ SPMF_HD void lane_init(LaneState<KK>& st, const Layout& L, const float* P, int d
       st.v[i] = nparam_init(P[L.toff[V_LOC] + e], P[L.toff[V_RHO] + e]);
       st.ue[i] = gparam_init(P[L.toff[UETA_C] + e], P[L.toff[UETA_B] + e]);
       st.ua[i] = gparam_init(P[L.toff[UETAA_C] + e], P[L.toff[UETAA_B] + e]);
-      st.ut[i] = gparam_init(P[L.toff[UTAU_C] + k], P[L.toff[UTAU_B] + k]);
+      // u_tau[k] enters the (d,k) program through its draw y = softplus(beta / g) only: beta is all it needs
+      // (its own gradient / log q terms are backward_lat_kernel's) -- no lgamma / digamma per (d,k)
+      st.ut[i].beta = softplusf(P[L.toff[UTAU_B] + k]);
+      st.ut[i].alpha = 0.f; st.ut[i].psi = 0.f; st.ut[i].c0 = 0.f; st.ut[i].acc_da = 0.f; st.ut[i].acc_db = 0.f;
     }
   }
 }

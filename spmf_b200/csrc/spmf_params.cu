@@ -159,32 +159,41 @@ draw_operands_kernel(Layout L, const float* __restrict__ P, const float* __restr
   int pos0[KK];
 #pragma unroll
   for (int i = 0; i < KK; ++i) pos0[i] = (lane + 32 * i) < KP ? rec_pos(KP, SV, 0, lane + 32 * i) : 0;
-  int q = 0, sv = 0;
-  for (int s = 0; s < L.S; ++s, ++sv) {
-    if (sv == SV) { sv = 0; ++q; }
-    const float y0 = softplus4(fmaf(s0s, N[L.noff[VAR_S] + (long long)s * 2 * D + d], s0l)).y;
-    const float y1 = softplus4(fmaf(s1s, N[L.noff[VAR_S] + (long long)s * 2 * D + D + d], s1l)).y;
-    const float inv = 1.f / (y0 + y1);
-    const float a_d = y0 * inv, b_d = y1 * inv;                 // poisson.py:661-663, 694-697
-#pragma unroll
-    for (int i = 0; i < KK; ++i) {
-      const int k = lane + 32 * i;
-      if (k < KP) {
-        float ap = 0.f, ev = 0.f;
-        if (k < L.K) {
-          const long long e = (long long)s * DK + (long long)d * L.K + k;
-          ap = a_d * softplus4(fmaf(us[i], N[L.noff[VAR_U] + e], ul[i])).y * ieta_enc;   // A' (poisson.py:665, 43)
-          const float tv = fmaf(vs[i], N[L.noff[VAR_V] + e], vl[i]);
-          ev = eta_dec * (vw_identity ? tv : softplus4(tv).y);                         // eta v (poisson.py:54)
-        }
-        const long long idx = ((long long)q * D + dr) * SV * KP + pos0[i] + sv * sv_stride;
-        Ap[idx] = ap;
-        EV[idx] = ev;
-      }
+  // per-feature quantities of draw s (a_d, b_d, phi) are computed by lane s % 32 and broadcast, not by all
+  // 32 lanes redundantly (two softplus and a division per draw were a third of this kernel's instructions)
+  for (int s0 = 0; s0 < L.S; s0 += 32) {
+    const int sm = s0 + lane;
+    float a_mine = 0.f;
+    if (sm < L.S) {
+      const float y0 = softplus4(fmaf(s0s, N[L.noff[VAR_S] + (long long)sm * 2 * D + d], s0l)).y;
+      const float y1 = softplus4(fmaf(s1s, N[L.noff[VAR_S] + (long long)sm * 2 * D + D + d], s1l)).y;
+      const float inv = 1.f / (y0 + y1);
+      a_mine = y0 * inv;                                         // poisson.py:661-663
+      const float tw = fmaf(wsg, N[L.noff[VAR_W] + (long long)sm * D + d], wl);
+      const int qm = sm / SV, svm = sm - qm * SV;
+      PH[((long long)qm * D + dr) * SV + svm] = eta_dec * (y1 * inv) * (vw_identity ? tw : softplus4(tw).y);   // poisson.py:694-701
     }
-    if (lane == 0) {
-      const float tw = fmaf(wsg, N[L.noff[VAR_W] + (long long)s * D + d], wl);
-      PH[((long long)q * D + dr) * SV + sv] = eta_dec * b_d * (vw_identity ? tw : softplus4(tw).y);   // poisson.py:701
+    const int ns = min(32, L.S - s0);
+    for (int j = 0; j < ns; ++j) {
+      const int s = s0 + j;
+      const int q = s / SV, sv = s - q * SV;
+      const float a_d = __shfl_sync(0xffffffffu, a_mine, j);
+#pragma unroll
+      for (int i = 0; i < KK; ++i) {
+        const int k = lane + 32 * i;
+        if (k < KP) {
+          float ap = 0.f, ev = 0.f;
+          if (k < L.K) {
+            const long long e = (long long)s * DK + (long long)d * L.K + k;
+            ap = a_d * softplus4(fmaf(us[i], N[L.noff[VAR_U] + e], ul[i])).y * ieta_enc;   // A' (poisson.py:665, 43)
+            const float tv = fmaf(vs[i], N[L.noff[VAR_V] + e], vl[i]);
+            ev = eta_dec * (vw_identity ? tv : softplus4(tv).y);                         // eta v (poisson.py:54)
+          }
+          const long long idx = ((long long)q * D + dr) * SV * KP + pos0[i] + sv * sv_stride;
+          Ap[idx] = ap;
+          EV[idx] = ev;
+        }
+      }
     }
   }
 }
@@ -244,11 +253,26 @@ backward_dk_kernel(Layout L, Hyper h, const float* __restrict__ P, const float* 
   int pos0[KK];
 #pragma unroll
   for (int i = 0; i < KK; ++i) pos0[i] = (lane + 32 * i) < KP ? rec_pos(KP, SV, 0, lane + 32 * i) : 0;
+  float a_mine[2] = {0.f, 0.f};                    // a_d of draws lane, lane + 32 (S <= 64 on this path)
+#pragma unroll
+  for (int h2 = 0; h2 < 2; ++h2) {
+    const int sm = lane + 32 * h2;
+    if (sm < L.S) {
+      const float y0 = ndraw(s0, N[L.noff[VAR_S] + (long long)sm * 2 * L.D + d]).y;
+      const float y1 = ndraw(s1, N[L.noff[VAR_S] + (long long)sm * 2 * L.D + L.D + d]).y;
+      a_mine[h2] = y0 / (y0 + y1);                          // poisson.py:661-663
+    }
+  }
   for (int s = 0; s < L.S; ++s) {
     const int q = s / SV, sv = s - q * SV;
-    const float y0 = ndraw(s0, N[L.noff[VAR_S] + (long long)s * 2 * L.D + d]).y;
-    const float y1 = ndraw(s1, N[L.noff[VAR_S] + (long long)s * 2 * L.D + L.D + d]).y;
-    const float a_d = y0 / (y0 + y1);                       // poisson.py:661-663
+    float a_d;
+    if (L.S <= 64) {
+      a_d = __shfl_sync(0xffffffffu, s < 32 ? a_mine[0] : a_mine[1], s & 31);
+    } else {
+      const float y0 = ndraw(s0, N[L.noff[VAR_S] + (long long)s * 2 * L.D + d]).y;
+      const float y1 = ndraw(s1, N[L.noff[VAR_S] + (long long)s * 2 * L.D + L.D + d]).y;
+      a_d = y0 / (y0 + y1);
+    }
     float da = 0.f, pp[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int i = 0; i < KK; ++i) {
@@ -413,7 +437,7 @@ __device__ __forceinline__ void group_add(float& v, int G) {
   for (int o = G >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
 }
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 4)
 backward_feat_kernel(Layout L, Hyper h, const float* __restrict__ P, const float* __restrict__ N,
                      const float* __restrict__ G, const float* __restrict__ eta,
                      const int* __restrict__ rank, int SV,

@@ -29,6 +29,25 @@ def _ceil64(n):
     return (int(n) + 63) // 64 * 64
 
 
+class StepGraphs:
+    """CUDA-graph replays of the native step for ONE resident batch (spmf_step_graph_*): key -> handle.
+    Handles are destroyed with the batch."""
+
+    def __init__(self):
+        self.handles = {}
+
+    def drop(self, keep_gen):
+        for key in [k for k in self.handles if k[1] != keep_gen]:
+            _abi._lib.spmf_step_graph_destroy(self.handles.pop(key))
+
+    def __del__(self):
+        try:
+            for h in self.handles.values():
+                _abi._lib.spmf_step_graph_destroy(h)
+        except Exception:
+            pass
+
+
 @dataclass
 class HotSplit:
     """Hybrid form of a minibatch (spmf_hot_split): ranked + partitioned CSR, its CSC copy, and the
@@ -437,10 +456,12 @@ class BatchUploader:
         self.hot = hot if (hot is not None and hot[0] is not None and hot[1] > 0) else None
         self.hot_csc = bool(hot[2]) if (self.hot is not None and len(hot) > 2) else True
         self.hot_version = int(hot[3]) if (self.hot is not None and len(hot) > 3) else 0
+        self.graphs = StepGraphs()          # CUDA-graph replays of the step on this staging slot (engine.py)
         self._alloc(max_rows, max_nnz)
 
     def _alloc(self, rows, nnz):
         dev = self.device
+        self.graphs.drop(None)              # captured graphs point into the old staging buffers
         self.cap_rows, self.cap_nnz = int(rows), int(nnz)
         n = max(nnz, 1) + 8
         self.rowptr = torch.empty(rows + 1, dtype=torch.int64, device=dev)
@@ -519,6 +540,8 @@ class BatchUploader:
             db.ensure_hot(self.hot[0], int(self.hot[1]), bufs=self.hot_bufs, hot_csc=self.hot_csc,
                           row_consts=True,          # row constants come out of the split's first pass
                           packed=(c16, v16), version=self.hot_version)
+            # same device arrays for every batch through this slot: the step may be replayed as a graph
+            db._resident, db._step_graphs, db._nnz_bound = True, self.graphs, self.cap_nnz
             return db
         _abi.call("spmf_prepare_batch", _ptr(c16), _ptr(v16), _ptr(self.rowptr), _ptr(self.cols),
                   _ptr(self.vals), n, nnz, self.D, _ptr(self.rowsum), _ptr(self.lgam), _ptr(self.colptr),

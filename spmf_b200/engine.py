@@ -15,7 +15,7 @@ from typing import Optional
 import torch
 
 from . import _abi
-from .data import DeviceBatch, _ptr, _stream
+from .data import DeviceBatch, StepGraphs as _StepGraphs, _ptr, _stream
 from .variables import VariableLayout, PART_NAMES
 
 
@@ -84,25 +84,6 @@ class StepWorkspace:
         self.z = torch.empty(self.NQ * nrows * C, dtype=torch.float32, device=self.device)
         self.dzr = torch.empty(self.NQ * nrows * C, dtype=torch.float32, device=self.device)
         self.rowacc = torch.empty(self.NQ * nrows * 4 * self.SV, dtype=torch.float32, device=self.device)
-
-
-class _StepGraphs:
-    """CUDA-graph replays of the native step for ONE resident batch (spmf_step_graph_*): key -> handle.
-    Handles are destroyed with the batch."""
-
-    def __init__(self):
-        self.handles = {}
-
-    def drop(self, keep_gen):
-        for key in [k for k in self.handles if k[1] != keep_gen]:
-            _abi._lib.spmf_step_graph_destroy(self.handles.pop(key))
-
-    def __del__(self):
-        try:
-            for h in self.handles.values():
-                _abi._lib.spmf_step_graph_destroy(h)
-        except Exception:
-            pass
 
 
 class AdviEngine:
@@ -425,7 +406,9 @@ class AdviEngine:
         a.inv_xi, a.scale_rows = self.inv_xi, int(self.scale_rows)
         a.fresh_noise, a.rng_step = int(fresh_noise), self.rng_step
         a.rowsum, a.lgam = _ptr(batch.rowsum), _ptr(batch.lgam)
-        a.nrows, a.nnz = batch.nrows, batch.nnz
+        # (a streamed batch lives in persistent staging: its kernels are sized by the staging capacity so that
+        # the captured graph of one slot serves every batch that passes through it; counts are device-side)
+        a.nrows, a.nnz = batch.nrows, int(getattr(batch, "_nnz_bound", batch.nnz))
         if hybrid:
             a.rowptr, a.cols, a.vals = _ptr(h.rowptr), _ptr(h.cols), _ptr(h.vals)
             a.colptr, a.crows, a.cvals = _ptr(h.colptr), _ptr(h.crows), _ptr(h.cvals)
@@ -503,8 +486,8 @@ class AdviEngine:
         cache = batch.__dict__.get("_step_graphs")
         if cache is None:
             cache = batch.__dict__["_step_graphs"] = _StepGraphs()
-        key = (id(self), self._ws_gen) + cfg + (batch.nrows, batch.nnz, getattr(self, "rank_version", 0),
-                                                  a.inv_xi, a.scale_rows)
+        key = (id(self), self._ws_gen) + cfg + (batch.nrows, int(a.nnz), getattr(self, "rank_version", 0),
+                                                  a.inv_xi, a.scale_rows, a.rowptr, a.xhot)
         h = cache.handles.get(key)
         if h is None:
             cache.drop(self._ws_gen)
