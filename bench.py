@@ -117,7 +117,9 @@ def make_shard(wl, device, seed):
         return synth_scrna_csr_device(n, wl["D"], wl["density"], seed=seed, device=device, gene_seed=1234 + 3)
     x = synth_linear_dense(n, wl["D"], seed=seed) if wl["kind"] == "linear" else synth_noise_dense(n, wl["D"], seed=seed)
     x[0, :] = x[0, :].clip(min=1)
-    return CsrShard.from_dense(torch.from_numpy(x), device)
+    sh = CsrShard.from_dense(torch.from_numpy(x), device)
+    sh._dense_host = x                      # dense-origin workload: the e2e leg streams the dense slabs themselves
+    return sh
 
 
 def oracle_step_time(wl, rows, steps, warmup, seed=0):
@@ -299,7 +301,15 @@ def main():
     # the device (prefetched one batch ahead on a copy stream), runs the step through the public
     # API, and its loss is read back D2H -- all inside the timed region.
     from spmf_b200.data import prefetch_to_device
-    host = HostCsr.from_shard(shard, compact=os.environ.get("BENCH_HOST_FORMAT", "u8") if os.environ.get("BENCH_HOST_FORMAT", "u8") != "u16" else True)
+    fmt = os.environ.get("BENCH_HOST_FORMAT", "auto")
+    x_host = getattr(shard, "_dense_host", None)
+    if fmt in ("auto", "dense") and x_host is not None and hybrid and eng.hot_mode == 2:
+        # dense-origin counts (C2 / C3): the uint8 slab itself travels and goes straight to the hybrid form
+        from spmf_b200.data import HostDense
+        host, fmt = HostDense(x_host), "dense-" + str(HostDense(x_host[:1]).x.dtype).replace("torch.", "")
+    else:
+        fmt = "u8" if fmt in ("auto", "dense") else fmt
+        host = HostCsr.from_shard(shard, compact=fmt if fmt != "u16" else True)
     hbatches = [host.batch(i * B, B) for i in range(len(batches))]
 
     loss_bufs = [torch.empty(1, dtype=torch.float64).pin_memory() for _ in range(2)]
@@ -476,7 +486,7 @@ def main():
                        # every one is evaluated for all S draws
                        "nnzK_times_draws_per_s": value * S},
             "e2e": {"value": e2e_value, "unit": "nonzeros*K/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": 8, "ms_per_step": float(t2.item()) / args.steps},
+                    "d2h_bytes_per_step": 8, "ms_per_step": float(t2.item()) / args.steps, "host_format": fmt},
             "gpu_launches": launches, "graph_replays": graph_replays, "graphs_primed": primed,
             "clocks": clk, "roofline": roofline, "cpu_baseline": cpu,
         }))

@@ -216,6 +216,16 @@ int spmf_hot_split_packed(const long long* rowptr, const int* cols, const unsign
                           const unsigned short* vals16, int nrows, long long nnz, const int* rank, int H,
                           long long* rowptr_out, int* cols_out, float* vals_out, int* rowmid, void* xhot, void* xthot,
                           float* rowsum, float* lgam, void* stream);
+/* Direct dense ingest: a dense [nrows][D] batch of counts in FEATURE order (dtype SPMF_DENSE_*) -> the hybrid
+ * form without a CSR round trip: xhot = the UMMA-tiled bf16 block of the H hot columns (rank order), the row
+ * constants, and the UNCOVERED nonzeros only (cold column, or a count not exact in bf16) as a ranked CSR with
+ * rowmid = 0 -- what the tile-hybrid step reads.  cols_out / vals_out must hold the batch's nonzero count. */
+#define SPMF_DENSE_U8 1
+#define SPMF_DENSE_U16 2
+#define SPMF_DENSE_F32 4
+int spmf_dense_hot_split(const void* x, int dtype, int nrows, int D, const int* rank, int H, long long* rowptr_out,
+                         int* cols_out, float* vals_out, int* rowmid, void* xhot, float* rowsum, float* lgam,
+                         void* stream);
 /* fp32 src[NQ][R][C] (row stride lds) -> UMMA-tiled B3 operand dst[NQ] with k = source row (i.e. the
  * transpose), hi+mid+lo = src to 24 bits; k in [R, Rpad) is written as zeros.  C % 32 == 0, Rpad % 64 == 0. */
 int spmf_split3_transpose(const float* src, long long lds, long long src_qstride, int R, int Rpad, int C,
@@ -377,6 +387,10 @@ typedef struct spmf_step_args {
   void* step_state;
   int model;          /* SPMF_MODEL_* */
   int state_preset;   /* != 0: step_state was already written on the stream (graph replay); leave 0 otherwise */
+  /* batch ingested dense (spmf_dense_hot_split): rowptr / cols / vals hold the uncovered entries only, the raw
+   * upload (feature order) is what the guard densifies from */
+  const void* dense_raw;
+  int dense_raw_dtype;
 } spmf_step_args;
 int spmf_advi_step(const spmf_step_args* args);
 /* Replay of a whole step as ONE CUDA graph launch (all streams, events and kernels of spmf_advi_step):
@@ -466,6 +480,12 @@ int spmf_guard_rows_fix(const long long* rowptr, const int* cols, const float* v
                         const float* lgam, float inv_xi, int scale_rows, int nrows, int D, int K, int S,
                         const float* EV, const float* PH, const float* z, float* dzr, float* rowacc, float* xd,
                         void* gs, void* stream);
+/* the same for a batch that was ingested dense (spmf_dense_hot_split): the batch is densified from the raw
+ * dense upload (feature order, permuted by rank) instead of from a CSR */
+int spmf_guard_rows_fix_dense(const void* raw, int raw_dtype, const int* rank, const float* rowsum, const float* lgam,
+                              float inv_xi, int scale_rows, int nrows, int D, int K, int S, const float* EV,
+                              const float* PH, const float* z, float* dzr, float* rowacc, float* xd, void* gs,
+                              void* stream);
 int spmf_guard_cols_fix(int nrows, int D, int K, int S, const float* EV, const float* PH, const float* z,
                         float* GEV, float* Gph, const float* xd, void* gs, void* stream);
 

@@ -6,11 +6,11 @@ spmf_b200/csrc; there is no CPU fallback.
 """
 from . import _abi
 from ._abi import SpmfError, version
-from .data import CsrShard, DeviceBatch, as_device_batch
+from .data import CsrShard, DeviceBatch, HostCsr, HostDense, as_device_batch
 from .engine import AdviEngine
 from .poisson import PoissonFactorization
 from .bernoulli import BernoulliFactorization
 from .variables import VAR_LIST, VariableLayout
 
-__all__ = ["PoissonFactorization", "BernoulliFactorization", "AdviEngine", "CsrShard", "DeviceBatch", "as_device_batch",
+__all__ = ["PoissonFactorization", "BernoulliFactorization", "AdviEngine", "CsrShard", "DeviceBatch", "HostCsr", "HostDense", "as_device_batch",
            "VariableLayout", "VAR_LIST", "SpmfError", "version"]

@@ -106,6 +106,8 @@ _SIGS = {
     "spmf_dense_cols": (i32, [p, p, i32, i32, i32, i32, i32, i32, p, p, p, p, p, p, p, p, p]),
     "spmf_guard_rows_fix": (i32, [p, p, p, p, p, f32, i32, i32, i32, i32, i32, p, p, p, p, p, p, p, p]),
     "spmf_guard_cols_fix": (i32, [i32, i32, i32, i32, p, p, p, p, p, p, p, p]),
+    "spmf_guard_rows_fix_dense": (i32, [p, i32, p, p, p, f32, i32, i32, i32, i32, i32, p, p, p, p, p, p, p, p]),
+    "spmf_dense_hot_split": (i32, [p, i32, i32, i32, p, i32, p, p, p, p, p, p, p, p]),
     "spmf_zero_col_grads": (i32, [p, p, p, i32, i32, i32, p]),
     "spmf_csc_cols_accum": (i32, [p, p, p, i32, i32, i32, i32, i32, p, p, p, p, p, p, p, i32, p]),
     "spmf_csr_to_csc_part": (i32, [p, p, i32, p, p, i32, i32, p, p, p, p, p]),
@@ -141,7 +143,7 @@ class StepArgs(C.Structure):
                             "ev_gemm0", "ev_gemm1", "aux_stream1", "aux_stream2", "ev_aux_fork", "ev_aux_join1",
                             "ev_aux_join2")]
         + [("hot_mode", i32), ("EVt", p), ("ev_tile0", p), ("ev_tile1", p), ("scr_dpre", p), ("ev_noise", p)]
-        + [("link", i32), ("gs", p), ("xdense", p), ("xdense_in", p), ("step_state", p), ("model", i32), ("state_preset", i32)]
+        + [("link", i32), ("gs", p), ("xdense", p), ("xdense_in", p), ("step_state", p), ("model", i32), ("state_preset", i32), ("dense_raw", p), ("dense_raw_dtype", i32)]
     )
 
 
@@ -186,6 +188,7 @@ def call(name, *args):
 
 LINK_POISSON, LINK_POISSON_LOG, LINK_BERNOULLI, LINK_BERNOULLI_LOG = 0, 1, 2, 3
 MODEL_POISSON, MODEL_BERNOULLI = 0, 1
+DENSE_U8, DENSE_U16, DENSE_F32 = 1, 2, 4
 DENSE_OPTIMISTIC, DENSE_STATS, DENSE_GUARDED = 0, 1, 2
 
 

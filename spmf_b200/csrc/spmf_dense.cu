@@ -158,6 +158,18 @@ __device__ void phase_scatter(const long long* __restrict__ rowptr, const int* _
   }
 }
 
+// densify from the raw dense upload (feature order) of a dense-ingested batch
+template <typename T>
+__device__ void phase_scatter_raw(const T* __restrict__ raw, const int* __restrict__ rank, int nrows, int D,
+                                  float* __restrict__ xd, long long tid, long long nth) {
+  const long long n = (long long)nrows * D;
+  for (long long i = tid; i < n; i += nth) {
+    const long long row = i / D;
+    const int d = (int)(i - row * D);
+    xd[row * D + (rank ? rank[d] : d)] = (float)raw[i];
+  }
+}
+
 __global__ void dense_zero_kernel(float* __restrict__ p, long long n, const GuardState* __restrict__ gs, int cond) {
   if (cond && !(gs && (gs->flag & 1))) return;
   phase_zero(p, n, (long long)blockIdx.x * blockDim.x + threadIdx.x, (long long)gridDim.x * blockDim.x);
@@ -507,6 +519,7 @@ struct GuardFixArgs {
   DenseBatch b;
   DenseGeom g;
   const long long* rowptr; const int* cols; const float* vals;      // CSR in table order (|vals|)
+  const void* raw; int raw_dtype; const int* rank;                   // or: the raw dense upload (feature order)
   float* xd;
   const float *EV, *PH, *z;
   float *dzr, *rowacc, *GEV, *Gph;
@@ -521,9 +534,15 @@ guard_rows_fix_kernel(GuardFixArgs a) {
   if (!(a.gs->flag & 1)) return;                             // uniform over the grid (nobody writes it here)
   const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
   if (tid == 0) { a.gs->nbad = 0; a.gs->minkey = ~0ull; }
-  phase_zero(a.xd, (long long)a.b.nrows * a.b.D, tid, nth);
+  if (a.raw) {                       // every element is written: no zero fill needed
+    if (a.raw_dtype == SPMF_DENSE_U8) phase_scatter_raw((const unsigned char*)a.raw, a.rank, a.b.nrows, a.b.D, a.xd, tid, nth);
+    else if (a.raw_dtype == SPMF_DENSE_U16) phase_scatter_raw((const unsigned short*)a.raw, a.rank, a.b.nrows, a.b.D, a.xd, tid, nth);
+    else phase_scatter_raw((const float*)a.raw, a.rank, a.b.nrows, a.b.D, a.xd, tid, nth);
+  } else {
+    phase_zero(a.xd, (long long)a.b.nrows * a.b.D, tid, nth);
+  }
   GRID_BARRIER_OR_FAIL(a.gs, 0u);
-  phase_scatter(a.rowptr, a.cols, a.vals, a.b.nrows, a.b.D, a.xd, tid >> 5, nth >> 5, threadIdx.x & 31);
+  if (!a.raw) phase_scatter(a.rowptr, a.cols, a.vals, a.b.nrows, a.b.D, a.xd, tid >> 5, nth >> 5, threadIdx.x & 31);
   GRID_BARRIER_OR_FAIL(a.gs, 1u);
   DenseBatch b = a.b;
   b.xd = a.xd;
@@ -752,17 +771,42 @@ static int launch_fix(Kern kern, GuardFixArgs& a, size_t sm, cudaStream_t st) {
 
 extern "C" {
 
+static int guard_rows_fix_impl(const long long* rowptr, const int* cols, const float* vals, const void* raw,
+                               int raw_dtype, const int* rank, const float* rowsum, const float* lgam, float inv_xi,
+                               int scale_rows, int nrows, int D, int K, int S, const float* EV, const float* PH,
+                               const float* z, float* dzr, float* rowacc, float* xd, void* gs, void* stream);
+
 int spmf_guard_rows_fix(const long long* rowptr, const int* cols, const float* vals, const float* rowsum,
                         const float* lgam, float inv_xi, int scale_rows, int nrows, int D, int K, int S,
                         const float* EV, const float* PH, const float* z, float* dzr, float* rowacc, float* xd,
                         void* gs, void* stream) {
-  if (!rowptr || !cols || !vals || !rowsum || !lgam || !EV || !PH || !z || !dzr || !rowacc || !xd || !gs ||
+  if (!rowptr || !cols || !vals) return SPMF_ERR_BAD_ARG;
+  return guard_rows_fix_impl(rowptr, cols, vals, nullptr, 0, nullptr, rowsum, lgam, inv_xi, scale_rows, nrows, D, K, S,
+                             EV, PH, z, dzr, rowacc, xd, gs, stream);
+}
+
+int spmf_guard_rows_fix_dense(const void* raw, int raw_dtype, const int* rank, const float* rowsum, const float* lgam,
+                              float inv_xi, int scale_rows, int nrows, int D, int K, int S, const float* EV,
+                              const float* PH, const float* z, float* dzr, float* rowacc, float* xd, void* gs,
+                              void* stream) {
+  if (!raw || (raw_dtype != SPMF_DENSE_U8 && raw_dtype != SPMF_DENSE_U16 && raw_dtype != SPMF_DENSE_F32))
+    return SPMF_ERR_BAD_ARG;
+  return guard_rows_fix_impl(nullptr, nullptr, nullptr, raw, raw_dtype, rank, rowsum, lgam, inv_xi, scale_rows, nrows,
+                             D, K, S, EV, PH, z, dzr, rowacc, xd, gs, stream);
+}
+
+static int guard_rows_fix_impl(const long long* rowptr, const int* cols, const float* vals, const void* raw,
+                               int raw_dtype, const int* rank, const float* rowsum, const float* lgam, float inv_xi,
+                               int scale_rows, int nrows, int D, int K, int S, const float* EV, const float* PH,
+                               const float* z, float* dzr, float* rowacc, float* xd, void* gs, void* stream) {
+  if (false || !rowsum || !lgam || !EV || !PH || !z || !dzr || !rowacc || !xd || !gs ||
       !dense_shape_ok(nrows, D, K, S))
     return SPMF_ERR_BAD_ARG;
   const int KP = spmf_kpad(K), SV = spmf_draw_vec(S), NQ = S / SV;
   GuardFixArgs a{};
   a.b = DenseBatch{xd, rowsum, lgam, nullptr, inv_xi, scale_rows, nrows, D};
   a.rowptr = rowptr; a.cols = cols; a.vals = vals; a.xd = xd;
+  a.raw = raw; a.raw_dtype = raw_dtype; a.rank = rank;
   a.EV = EV; a.PH = PH; a.z = z; a.dzr = dzr; a.rowacc = rowacc; a.gs = (GuardState*)gs;
   cudaStream_t st = (cudaStream_t)stream;
   int rc = SPMF_OK;

@@ -1101,6 +1101,114 @@ hot_split_kernel(const long long* __restrict__ rowptr, const CT* __restrict__ co
   }
 }
 
+// ---- direct dense ingest: dense (B,D) counts in feature order -> hybrid form, no CSR round trip ------------
+// For dense-origin workloads (BASELINE C2 / C3: every column is hot) the batch arrives as a dense matrix
+// of small integers; going through CSR would write and re-read 8 B per nonzero only to scatter it back
+// into the dense block.  Kernel 1: one CTA per row assembles the row's hot vector (bf16, rank order) in
+// shared memory from the dense row, writes it as whole 16-byte chunks of the UMMA-tiled block, and emits
+// the row constants and the number of UNCOVERED nonzeros (cold column, or a count that is not exact in
+// bf16).  Kernel 2 (after a scan of those counts): the uncovered entries as a ranked CSR -- all the gather
+// kernels of the tile-hybrid step read (rowmid = 0: the covered part of the CSR is never visited there).
+template <typename T>
+__global__ void __launch_bounds__(kSplitThreads, 2048 / kSplitThreads)
+dense_hot_rows_kernel(const T* __restrict__ x, int nrows, int D, const int* __restrict__ rank, int H,
+                      unsigned short* __restrict__ xhot, long long hchunks, float* __restrict__ rowsum,
+                      float* __restrict__ lgam, long long* __restrict__ uncount, int* __restrict__ rowmid) {
+  extern __shared__ __align__(16) unsigned short xrow[];        // [Hp]
+  __shared__ int s_unc[kSplitWarps];
+  __shared__ float s_sum[kSplitWarps], s_lg[kSplitWarps];
+  const int row = blockIdx.x;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int hp = (int)hchunks * 64;
+  for (int i = threadIdx.x; i < hp / 8; i += blockDim.x) reinterpret_cast<uint4*>(xrow)[i] = make_uint4(0u, 0u, 0u, 0u);
+  if (row >= nrows) {                                            // padding row of the last 128-row tile
+    for (int c = threadIdx.x; c < hp / 8; c += blockDim.x)
+      *reinterpret_cast<uint4*>(xhot + tiledA_index(row, 8LL * c, hchunks)) = make_uint4(0u, 0u, 0u, 0u);
+    return;
+  }
+  __syncthreads();
+  const T* xr = x + (size_t)row * D;
+  int nunc = 0;
+  float rs = 0.f, rl = 0.f;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    const float v = (float)xr[d];
+    if (v != 0.f) {
+      const int r = rank ? __ldg(rank + d) : d;
+      rs += v;
+      rl += lgamma1p_count(v);
+      if (hot_covered(r, v, H)) xrow[r] = (unsigned short)(__float_as_uint(v) >> 16);
+      else ++nunc;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    nunc += __shfl_xor_sync(0xffffffffu, nunc, o);
+    rs += __shfl_xor_sync(0xffffffffu, rs, o);
+    rl += __shfl_xor_sync(0xffffffffu, rl, o);
+  }
+  if (lane == 0) { s_unc[w] = nunc; s_sum[w] = rs; s_lg[w] = rl; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int tu = 0;
+    float ts = 0.f, tl = 0.f;
+#pragma unroll
+    for (int t = 0; t < kSplitWarps; ++t) { tu += s_unc[t]; ts += s_sum[t]; tl += s_lg[t]; }
+    uncount[row + 1] = tu;
+    if (row == 0) uncount[0] = 0;
+    rowsum[row] = ts;
+    lgam[row] = tl;
+    rowmid[row] = 0;
+  }
+  for (int c = threadIdx.x; c < hp / 8; c += blockDim.x)
+    *reinterpret_cast<uint4*>(xhot + tiledA_index(row, 8LL * c, hchunks)) = reinterpret_cast<const uint4*>(xrow)[c];
+}
+
+template <typename T>
+__global__ void dense_uncovered_fill_kernel(const T* __restrict__ x, int nrows, int D, const int* __restrict__ rank,
+                                            int H, const long long* __restrict__ rowptr, int* __restrict__ cols,
+                                            float* __restrict__ vals) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= nrows) return;
+  if (rowptr[row + 1] == rowptr[row]) return;                    // (the common case for dense-origin counts)
+  long long pos = rowptr[row];
+  const T* xr = x + (size_t)row * D;
+  for (int d0 = 0; d0 < D; d0 += 32) {
+    const int d = d0 + lane;
+    const float v = d < D ? (float)xr[d] : 0.f;
+    const int r = (d < D && v != 0.f) ? (rank ? __ldg(rank + d) : d) : 0;
+    const bool unc = v != 0.f && !hot_covered(r, v, H);
+    const unsigned m = __ballot_sync(0xffffffffu, unc);
+    if (unc) {
+      const long long o = pos + __popc(m & ((1u << lane) - 1u));
+      cols[o] = r;
+      vals[o] = v;
+    }
+    pos += __popc(m);
+  }
+}
+
+template <typename T>
+static int launch_dense_hot_split(const T* x, int nrows, int D, const int* rank, int H, long long* rowptr_out,
+                                  int* cols_out, float* vals_out, int* rowmid, void* xhot, float* rowsum, float* lgam,
+                                  cudaStream_t st) {
+  const long long hp = (H + 63) / 64 * 64;
+  const size_t smem = (size_t)hp * 2;
+  if (smem > 200 * 1024) return SPMF_ERR_UNSUPPORTED;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(dense_hot_rows_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return (int)e;
+    attr = true;
+  }
+  dense_hot_rows_kernel<T><<<(nrows + 127) / 128 * 128, kSplitThreads, smem, st>>>(
+      x, nrows, D, rank, H, (unsigned short*)xhot, hp / 64, rowsum, lgam, rowptr_out, rowmid);
+  incscan_ll_kernel<<<1, 1024, 0, st>>>(rowptr_out, nrows);
+  dense_uncovered_fill_kernel<T><<<(nrows + 7) / 8, 256, 0, st>>>(x, nrows, D, rank, H, rowptr_out, cols_out, vals_out);
+  SPMF_CHECK_LAUNCH();
+  return SPMF_OK;
+}
+
 // ------------------------------------------------------------------ dispatch
 template <int KP, int SV, int MODE>
 static int launch_rows(const long long* rowptr, const int* cols, const float* vals,
@@ -1494,6 +1602,20 @@ int spmf_dense_fill(const float* x, int nrows, int D, const long long* rowptr, i
   return SPMF_OK;
 }
 
-const char* spmf_version(void) { return "spmf_b200 0.1 (sm_100a)"; }
+int spmf_dense_hot_split(const void* x, int dtype, int nrows, int D, const int* rank, int H, long long* rowptr_out,
+                         int* cols_out, float* vals_out, int* rowmid, void* xhot, float* rowsum, float* lgam,
+                         void* stream) {
+  if (!x || !rowptr_out || !cols_out || !vals_out || !rowmid || !xhot || !rowsum || !lgam) return SPMF_ERR_BAD_ARG;
+  if (nrows <= 0 || D <= 0 || H <= 0 || H > D) return SPMF_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (dtype) {
+    case SPMF_DENSE_U8: return launch_dense_hot_split<unsigned char>((const unsigned char*)x, nrows, D, rank, H, rowptr_out, cols_out, vals_out, rowmid, xhot, rowsum, lgam, st);
+    case SPMF_DENSE_U16: return launch_dense_hot_split<unsigned short>((const unsigned short*)x, nrows, D, rank, H, rowptr_out, cols_out, vals_out, rowmid, xhot, rowsum, lgam, st);
+    case SPMF_DENSE_F32: return launch_dense_hot_split<float>((const float*)x, nrows, D, rank, H, rowptr_out, cols_out, vals_out, rowmid, xhot, rowsum, lgam, st);
+    default: return SPMF_ERR_BAD_ARG;
+  }
+}
+
+const char* spmf_version(void) { return "spmf_b200 0.2 (sm_100a)"; }
 
 }  // extern "C"

@@ -145,7 +145,11 @@ int spmf_advi_step(const spmf_step_args* a) {
   // this step is re-evaluated densely with the reference's replacement semantics (conditional launch:
   // returns at once otherwise); dzr / rowacc are rewritten BEFORE the column side reads them
   const bool guard = a->gs && a->xdense;
-  if (guard)
+  if (guard && a->dense_raw)
+    STEP_TRY(spmf_guard_rows_fix_dense(a->dense_raw, a->dense_raw_dtype, hybrid ? a->rank : nullptr, a->rowsum, a->lgam,
+                                       a->inv_xi, a->scale_rows, a->nrows, D, K, S, a->EV, a->PH, a->z, a->dzr,
+                                       a->rowacc, a->xdense, a->gs, hot));
+  else if (guard)
     STEP_TRY(spmf_guard_rows_fix(a->rowptr, a->cols, a->vals, a->rowsum, a->lgam, a->inv_xi, a->scale_rows, a->nrows,
                                  D, K, S, a->EV, a->PH, a->z, a->dzr, a->rowacc, a->xdense, a->gs, hot));
   if (a->ev_rows1) CUDA_TRY(cudaEventRecord((cudaEvent_t)a->ev_rows1, hot));

@@ -84,6 +84,8 @@ class DeviceBatch:
     crows: Optional[torch.Tensor] = None    # int32 [nnz] batch-local rows
     cvals: Optional[torch.Tensor] = None    # fp32 [nnz]
     hot: Optional[HotSplit] = None          # hybrid form (built for one (rank, H) ordering)
+    dense_raw: Optional[torch.Tensor] = None   # dense-ingested batch: the raw [nrows][D] upload (feature order)
+    dense_dtype: int = 0                       # SPMF_DENSE_* of dense_raw
 
     def ensure_hot(self, rank, H, bufs=None, hot_csc=True, row_consts=False, build_xt=False, packed=None,
                    version=0):
@@ -237,7 +239,7 @@ def as_device_batch(counts, device, D=None) -> DeviceBatch:
     dense torch/numpy array, or a scipy.sparse matrix."""
     if isinstance(counts, DeviceBatch):
         return counts
-    if isinstance(counts, HostCsrBatch):
+    if isinstance(counts, (HostCsrBatch, HostDenseBatch)):
         up = _UPLOADERS.get((str(device), counts.D))
         if up is None:
             up = _UPLOADERS[(str(device), counts.D)] = BatchUploader(device, counts.D)
@@ -446,6 +448,50 @@ class HostCsr:
             yield self.batch(r0, min(batch_rows, self.nrows - r0))
 
 
+_DENSE_CODE = {torch.uint8: _abi.DENSE_U8, torch.uint16: _abi.DENSE_U16, torch.float32: _abi.DENSE_F32}
+
+
+@dataclass
+class HostDenseBatch:
+    """Rows [row0, row0 + nrows) of a `HostDense`: a zero-copy view of the pinned dense matrix."""
+    x: torch.Tensor        # [nrows, D] uint8 / uint16 / float32, pinned host, contiguous
+    D: int
+    nnz: int               # number of nonzeros (sizes the device staging of the uncovered entries)
+
+    @property
+    def nrows(self):
+        return self.x.shape[0]
+
+    def nbytes(self):
+        return self.x.numel() * self.x.element_size()
+
+
+class HostDense:
+    """A dense count matrix kept in pinned host memory in the narrowest integer type that holds it (uint8 /
+    uint16, else float32): what a dense-origin workload (BASELINE C2 / C3; the reference's dense tf.data
+    batches, tests/spmf_test.py:17-27) streams.  On the device a batch goes straight to the hybrid form
+    (spmf_dense_hot_split) -- no CSR round trip."""
+
+    def __init__(self, x):
+        x = torch.as_tensor(x)
+        xf = x.to(torch.float32)
+        self.nrows, self.D = int(x.shape[0]), int(x.shape[1])
+        integral = bool((xf == xf.round()).all()) and float(xf.min()) >= 0
+        mx = float(xf.max()) if xf.numel() else 0.0
+        dt = torch.uint8 if (integral and mx <= 255) else torch.uint16 if (integral and mx <= 65535) else torch.float32
+        self.x = xf.to(dt).contiguous().pin_memory()
+        nz = (xf != 0).sum(1).to(torch.int64)
+        self._nnz_prefix = torch.cat([torch.zeros(1, dtype=torch.int64), torch.cumsum(nz, 0)])
+
+    def batch(self, row0, nrows) -> HostDenseBatch:
+        return HostDenseBatch(self.x[row0:row0 + nrows], self.D,
+                              int(self._nnz_prefix[row0 + nrows] - self._nnz_prefix[row0]))
+
+    def iter_batches(self, batch_rows):
+        for r0 in range(0, self.nrows, batch_rows):
+            yield self.batch(r0, min(batch_rows, self.nrows - r0))
+
+
 class BatchUploader:
     """Reusable device staging for host batches: async H2D of (rowptr, cols, vals), widening of the
     compact format, then the row constants and the CSC copy are built by kernels on the same stream."""
@@ -495,7 +541,42 @@ class BatchUploader:
                                  hcrows=torch.empty(n, dtype=torch.int32, device=dev),
                                  hcvals=torch.empty(n, dtype=torch.float32, device=dev), scratch=self.cursor)
 
-    def upload(self, hb: HostCsrBatch) -> DeviceBatch:
+    def upload_dense(self, hb: HostDenseBatch) -> DeviceBatch:
+        """Dense batch: one H2D copy of the slab, then straight to the hybrid form (tile-hybrid engines), or
+        to CSR on the device (everything else)."""
+        n, nnz = hb.nrows, hb.nnz
+        if n > self.cap_rows or nnz > self.cap_nnz:
+            self._alloc(max(n, self.cap_rows), max(int(nnz * 1.25), self.cap_nnz))
+        dt = hb.x.dtype
+        raw = getattr(self, "raw", None)
+        if raw is None or raw.dtype != dt or raw.numel() < self.cap_rows * self.D:
+            self.raw = raw = torch.empty(max(self.cap_rows, n) * self.D, dtype=dt, device=self.device)
+            self.graphs.drop(None)
+        rawv = raw[:n * self.D].view(n, self.D)
+        rawv.copy_(hb.x, non_blocking=True)
+        if self.hot is None or self.hot_csc:
+            # no fused tile kernel on the consuming engine: compact to CSR on the device (host sync for nnz)
+            sh = CsrShard.from_dense(rawv, self.device)
+            return sh.batch(0, n, cache=False)
+        H, hb_ = int(self.hot[1]), self.hot_bufs
+        _abi.call("spmf_dense_hot_split", _ptr(raw), _DENSE_CODE[dt], n, self.D, _ptr(self.hot[0]), H,
+                  _ptr(hb_["rowptr"]), _ptr(hb_["cols"]), _ptr(hb_["vals"]), _ptr(hb_["rowmid"]), _ptr(hb_["xhot"]),
+                  _ptr(self.rowsum), _ptr(self.lgam), _stream())
+        _abi.call("spmf_csr_to_csc_part", _ptr(hb_["rowptr"]), _ptr(hb_["rowmid"]), 1, _ptr(hb_["cols"]),
+                  _ptr(hb_["vals"]), n, self.D, _ptr(hb_["colptr"]), _ptr(hb_["crows"]), _ptr(hb_["cvals"]),
+                  _ptr(hb_["scratch"]), _stream())
+        db = DeviceBatch(rowptr=None, cols=None, vals=None, rowsum=self.rowsum[:n], lgam=self.lgam[:n], nrows=n,
+                         nnz=nnz, D=self.D, dense_raw=raw, dense_dtype=_DENSE_CODE[dt])
+        db.hot = HotSplit(H=H, rowptr=hb_["rowptr"], cols=hb_["cols"], vals=hb_["vals"], rowmid=hb_["rowmid"],
+                          xhot=hb_["xhot"], xthot=None, colptr=hb_["colptr"], crows=hb_["crows"], cvals=hb_["cvals"],
+                          hcolptr=hb_["hcolptr"], hcrows=hb_["hcrows"], hcvals=hb_["hcvals"], has_hot_csc=False,
+                          version=self.hot_version)
+        db._resident, db._step_graphs, db._nnz_bound = True, self.graphs, self.cap_nnz
+        return db
+
+    def upload(self, hb) -> DeviceBatch:
+        if isinstance(hb, HostDenseBatch):
+            return self.upload_dense(hb)
         n, nnz = hb.nrows, hb.nnz
         if n > self.cap_rows or nnz > self.cap_nnz:
             self._alloc(max(n, self.cap_rows), max(int(nnz * 1.25), self.cap_nnz))
@@ -572,7 +653,7 @@ def prefetch_to_device(host_batches, device, depth=2, hot=None):
             hb = next(it)
         except StopIteration:
             return False
-        if not isinstance(hb, HostCsrBatch):
+        if not isinstance(hb, (HostCsrBatch, HostDenseBatch)):
             hb = hb["counts"] if isinstance(hb, dict) else hb
         key = (slot, hb.D, hot_key)
         if key not in ups:

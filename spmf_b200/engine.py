@@ -389,6 +389,9 @@ class AdviEngine:
                 self._args = None
                 self._ws_gen += 1
         else:
+            if batch.dense_raw is not None:
+                raise _abi.SpmfError("this batch was ingested dense for the tile-hybrid step, but the engine for "
+                                     f"S={self.S} does not run it; upload it through an uploader made for this engine")
             if batch.cols is None or batch.vals is None:
                 raise _abi.SpmfError("this batch was uploaded in hybrid-only form (no CSR arrays) but the engine "
                                      f"for S={self.S} runs the gather step; upload it without a hot split")
@@ -402,6 +405,7 @@ class AdviEngine:
         a.step_state = _ptr(self.step_state)
         a.link, a.gs, a.xdense, a.xdense_in = self.link, _ptr(self.gs), _ptr(xd), None
         a.model = self.model
+        a.dense_raw, a.dense_raw_dtype = _ptr(batch.dense_raw), int(batch.dense_dtype)
         a.z, a.dzr, a.rowacc = _ptr(w.z), _ptr(w.dzr), _ptr(w.rowacc)
         a.inv_xi, a.scale_rows = self.inv_xi, int(self.scale_rows)
         a.fresh_noise, a.rng_step = int(fresh_noise), self.rng_step

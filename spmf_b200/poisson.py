@@ -680,7 +680,7 @@ class PoissonFactorization:
 
     def _device_batches(self, batches, eng):
         """Host-resident CSR batches are uploaded one ahead on a copy stream; anything else passes through."""
-        from .data import HostCsrBatch, prefetch_to_device
+        from .data import HostCsrBatch, HostDenseBatch, prefetch_to_device
         it = iter(batches)
         try:
             first = next(it)
@@ -689,7 +689,7 @@ class PoissonFactorization:
         import itertools
         chained = itertools.chain([first], it)
         c = first[self.count_key] if isinstance(first, dict) else first
-        if isinstance(c, HostCsrBatch):
+        if isinstance(c, (HostCsrBatch, HostDenseBatch)):
             return prefetch_to_device((b[self.count_key] if isinstance(b, dict) else b for b in chained),
                                       self.device, hot=self._hot_spec(eng))
         return chained

@@ -262,3 +262,81 @@ def test_hybrid_fit_reduces_loss_and_streams():
     a, b = run(False), run(True)
     assert a[-1] < a[0]
     assert np.allclose(a, b, rtol=1e-5), (a, b)
+
+
+@pytest.mark.parametrize("D,K,B,S,kind,big", [
+    (160, 16, 192, 4, "noise", False),     # dense-origin counts: every column hot, nothing uncovered
+    (300, 32, 200, 4, "sparse", False),    # hot + cold columns: the cold nonzeros go to the ranked CSR
+    (192, 32, 130, 4, "linear", True),     # counts that bf16 cannot hold (uint16 transfer) stay out of the block
+])
+def test_dense_ingest_matches_csr_path(D, K, B, S, kind, big):
+    """HostDense -> one H2D of the slab -> spmf_dense_hot_split: the same hybrid form and the same step as the
+    CSR upload of the same rows (bit-identical arrays, step equal up to fp32 atomics)."""
+    import spmf_b200
+    from spmf_b200.data import CsrShard, HostDense, HostDenseBatch, prefetch_to_device
+    dev = torch.device("cuda:0")
+    x = make_counts(3 * B, D, seed=8, kind=kind)
+    if big:
+        x[3, 5], x[B + 7, 11], x[2 * B + 1, 0] = 1001.0, 257.0, 40000.0
+    sh = CsrShard.from_dense(x, dev)
+    model = spmf_b200.PoissonFactorization(latent_dim=K, feature_dim=D, u_tau_scale=1.0 / np.sqrt(x.size),
+                                           device=dev, seed=3)
+    model.compute_scales(sh)
+    eng = model._engine_for(S)
+    assert eng.hot_mode == 2 and eng.hot_cols > 0
+    host = HostDense(x)
+    assert host.x.dtype == (torch.uint16 if big else torch.uint8)
+    assert isinstance(host.batch(0, B), HostDenseBatch) and host.batch(0, B).nnz == int((x[:B] != 0).sum())
+    eng.fill_noise(step=0)
+    hot = model._hot_spec(eng)
+    got = []
+    for i, db in enumerate(prefetch_to_device(host.iter_batches(B), dev, hot=hot)):
+        assert db.dense_raw is not None and db.cols is None
+        ref_b = sh.batch(i * B, B, cache=False)
+        h_ref = ref_b.ensure_hot(eng.rank, eng.hot_cols, hot_csc=False, version=getattr(eng, "rank_version", 0))
+        h = db.hot
+        torch.cuda.synchronize()
+        n_unc = int(h.rowptr[B].item())
+        assert torch.equal(h.xhot[:h_ref.xhot.numel()].view(torch.int16), h_ref.xhot.view(torch.int16))
+        assert torch.equal(db.rowsum, ref_b.rowsum) and torch.allclose(db.lgam, ref_b.lgam, rtol=1e-6)
+        assert torch.equal(h.colptr, h_ref.colptr)            # CSC of the uncovered entries: same column counts
+        nu = int(h.colptr[-1].item())
+        assert nu == n_unc
+        # (the order inside a column follows the atomic cursor of the CSC build: compare as sorted (col, row, value))
+        def entries(hh):
+            col = torch.repeat_interleave(torch.arange(D, device=dev), (hh.colptr[1:] - hh.colptr[:-1]).long())
+            key = col * B + hh.crows[:nu].long()
+            o = torch.argsort(key)
+            return key[o], hh.cvals[:nu][o]
+        (k1, v1), (k2, v2) = entries(h), entries(h_ref)
+        assert torch.equal(k1, k2) and torch.equal(v1, v2)
+        p = eng.loss_and_grad(db, fresh_noise=False).clone()
+        g = eng.grads.clone()
+        p0 = eng.loss_and_grad(ref_b, fresh_noise=False).clone()
+        assert rel_err(p.cpu().numpy(), p0.cpu().numpy()) < 1e-6
+        assert rel_err(g.cpu().numpy(), eng.grads.cpu().numpy()) < 2e-5
+        got.append(p)
+    assert len(got) == 3
+
+
+def test_dense_ingest_fit_and_gather_fallback():
+    """fit() over HostDense batches == fit() over the resident shard, for a tile-hybrid engine (direct ingest)
+    and for a gather-only one (K = 4: the uploader compacts the slab to CSR on the device)."""
+    import spmf_b200
+    from spmf_b200.data import CsrShard, HostDense
+    dev = torch.device("cuda:0")
+    B, D = 256, 192
+    x = make_counts(4 * B, D, seed=2, kind="linear")
+    sh = CsrShard.from_dense(x, dev)
+    host = HostDense(x)
+    for K in (16, 4):
+        def run(stream):
+            model = spmf_b200.PoissonFactorization(latent_dim=K, feature_dim=D, u_tau_scale=1.0 / np.sqrt(x.size),
+                                                   device=dev, seed=3)
+            model.compute_scales(sh)
+            fac = (lambda: ({'counts': hb} for hb in host.iter_batches(B))) if stream else \
+                  (lambda: ({'counts': b} for b in sh.iter_batches(B)))
+            return model.fit(fac, num_steps=4, learning_rate=0.05, sample_size=4, verbose=False, rel_tol=None)
+        a, b = run(False), run(True)
+        assert a[-1] < a[0]
+        assert np.allclose(a, b, rtol=1e-5), (K, a, b)
