@@ -210,6 +210,12 @@ int spmf_umma_tile_a(const void* src_bf16, long long ld, int M, int Kd, void* ds
 int spmf_hot_split(const long long* rowptr, const int* cols, const float* vals, int nrows, long long nnz,
                    const int* rank, int H, long long* rowptr_out, int* cols_out, float* vals_out, int* rowmid,
                    void* xhot, void* xthot, float* rowsum, float* lgam, void* stream);
+/* the same, reading the 2-byte transfer format directly (spmf_csr_unpack8 fused in: column-gap bytes, count
+ * bytes, sorted overflow list; entry indices relative to rowptr[0]) */
+int spmf_hot_split_u8(const long long* rowptr, const unsigned char* gaps8, const unsigned char* vals8,
+                      const int* ovf_idx, const float* ovf_val, int novf, int nrows, const int* rank, int H,
+                      long long* rowptr_out, int* cols_out, float* vals_out, int* rowmid, void* xhot, float* rowsum,
+                      float* lgam, void* stream);
 /* the same, reading the compact upload format directly (spmf_csr_unpack16 fused in): exactly one of
  * cols / cols16 and one of vals / vals16 is non-NULL */
 int spmf_hot_split_packed(const long long* rowptr, const int* cols, const unsigned short* cols16, const float* vals,

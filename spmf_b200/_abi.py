@@ -86,6 +86,7 @@ _SIGS = {
     "spmf_umma_gemm3_at": (i32, [p, i32, i32, i32, p, i64, p, i64, i64, i32, i32, i32, p]),
     "spmf_umma_probe": (i32, [p, i32, p, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, p, p]),
     "spmf_hot_split": (i32, [p, p, p, i32, i64, p, i32, p, p, p, p, p, p, p, p, p]),
+    "spmf_hot_split_u8": (i32, [p, p, p, p, p, i32, i32, p, i32, p, p, p, p, p, p, p, p]),
     "spmf_hot_split_packed": (i32, [p, p, p, p, p, i32, i64, p, i32, p, p, p, p, p, p, p, p, p]),
     "spmf_split3_transpose": (i32, [p, i64, i64, i32, i32, i32, p, i64, i32, p]),
     "spmf_umma_gemm3": (i32, [p, i64, i32, p, i64, p, i64, i64, i32, i32, i32, i32, p]),

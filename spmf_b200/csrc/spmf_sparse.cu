@@ -981,17 +981,35 @@ hot_transpose_kernel(const unsigned short* __restrict__ xhot, int hchunks, unsig
 constexpr int kSplitThreads = 256, kSplitWarps = kSplitThreads / 32;
 constexpr int kSplitStash = 2048;     // (rank, value) pairs per row kept between the two passes
 
+// count of entry e of the 2-byte format: the byte, or (byte 255) its value in the sorted overflow list
+__device__ __forceinline__ float u8_count(const unsigned char* __restrict__ vals8, long long e,
+                                          const int* __restrict__ ovf_idx, const float* __restrict__ ovf_val, int novf) {
+  const unsigned b = vals8[e];
+  if (b != 255u) return (float)b;
+  int lo = 0, hi = novf - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(ovf_idx + mid) < (int)e) lo = mid + 1; else hi = mid;
+  }
+  return (novf > 0 && __ldg(ovf_idx + lo) == (int)e) ? __ldg(ovf_val + lo) : 255.f;
+}
+
 // CT / VT: int / float, or unsigned short for the compact upload format (spmf_csr_unpack16 fused in).
-template <bool STAGED, typename CT, typename VT>
+// GAPS (CT = VT = unsigned char): the 2-byte format of spmf_csr_unpack8 fused in -- `cols` holds the column
+// gaps (a row's column ids are their inclusive prefix sum: warp scans, chained across the warps' pieces),
+// `vals` the count bytes with the overflow list beside them; entry indices are relative to rowptr[0].
+template <bool STAGED, typename CT, typename VT, bool GAPS = false>
 __global__ void __launch_bounds__(kSplitThreads, 2048 / kSplitThreads)
 hot_split_kernel(const long long* __restrict__ rowptr, const CT* __restrict__ cols,
                  const VT* __restrict__ vals, int nrows, const int* __restrict__ rank, int H,
                  long long* __restrict__ rowptr_out, int* __restrict__ cols_out,
                  float* __restrict__ vals_out, int* __restrict__ rowmid,
                  unsigned short* __restrict__ xhot, long long hchunks, float* __restrict__ rowsum,
-                 float* __restrict__ lgam) {
+                 float* __restrict__ lgam, const int* __restrict__ ovf_idx = nullptr,
+                 const float* __restrict__ ovf_val = nullptr, int novf = 0) {
   extern __shared__ __align__(16) unsigned short xrow[];        // [Hp] when STAGED, then the stash
   __shared__ int s_cov[kSplitWarps];
+  __shared__ int s_gap[kSplitWarps];
   __shared__ float s_sum[kSplitWarps], s_lg[kSplitWarps];
   const int row = blockIdx.x;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -1024,14 +1042,45 @@ hot_split_kernel(const long long* __restrict__ rowptr, const CT* __restrict__ co
   int2* stash = reinterpret_cast<int2*>(xrow + (STAGED ? hp : 0));
   int ncov = 0;
   float rs = 0.f, rl = 0.f;
+  int cstart = -1;                                              // GAPS: column before my piece's first entry
+  if constexpr (GAPS) {
+    int gs = 0;
+    for (long long j = a0 + lane; j < a1; j += 32) gs += (int)cols[j] + 1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) gs += __shfl_xor_sync(0xffffffffu, gs, o);
+    if (lane == 0) s_gap[w] = gs;
+    __syncthreads();
+    for (int t = 0; t < w; ++t) cstart += s_gap[t];
+    int cbase = cstart;
+    for (long long jb = a0; jb < a1; jb += 32) {
+      const long long j = jb + lane;
+      const bool in = j < a1;
+      int g = in ? (int)cols[j] + 1 : 0;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {                         // inclusive warp scan of the gaps
+        const int t = __shfl_up_sync(0xffffffffu, g, o);
+        if (lane >= o) g += t;
+      }
+      const int c = cbase + g;
+      cbase += __shfl_sync(0xffffffffu, g, 31);
+      if (in) {
+        const int r = rank ? __ldg(rank + c) : c;
+        const float x = u8_count(reinterpret_cast<const unsigned char*>(vals), j - base, ovf_idx, ovf_val, novf);
+        if (j - j0 < kSplitStash) stash[j - j0] = make_int2(r, __float_as_int(x));
+        ncov += hot_covered(r, x, H) ? 1 : 0;
+        if (rowsum) { rs += x; rl += lgamma1p_count(x); }
+      }
+    }
+  } else {
 #pragma unroll 4
-  for (long long j = a0 + lane; j < a1; j += 32) {
-    const int c = (int)__ldg(cols + j);
-    const int r = rank ? __ldg(rank + c) : c;
-    const float x = (float)__ldg(vals + j);
-    if (j - j0 < kSplitStash) stash[j - j0] = make_int2(r, __float_as_int(x));
-    ncov += hot_covered(r, x, H) ? 1 : 0;
-    if (rowsum) { rs += x; rl += lgamma1p_count(x); }
+    for (long long j = a0 + lane; j < a1; j += 32) {
+      const int c = (int)__ldg(cols + j);
+      const int r = rank ? __ldg(rank + c) : c;
+      const float x = (float)__ldg(vals + j);
+      if (j - j0 < kSplitStash) stash[j - j0] = make_int2(r, __float_as_int(x));
+      ncov += hot_covered(r, x, H) ? 1 : 0;
+      if (rowsum) { rs += x; rl += lgamma1p_count(x); }
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -1059,16 +1108,34 @@ hot_split_kernel(const long long* __restrict__ rowptr, const CT* __restrict__ co
   }
   // pass 2: stable partition -- covered entries first (negated), the others after cov_total
   long long pc = o0 + cov_before, pu = o0 + cov_total + ((a0 - j0) - cov_before);
+  const bool rescan = GAPS && n > kSplitStash;                  // (CTA-uniform) rows longer than the stash
+  int cbase2 = cstart;
   for (long long jb = a0; jb < a1; jb += 32) {
     const long long j = jb + lane;
     const bool in = j < a1;
     int r = 0;
     float x = 0.f;
+    int cscan = 0;
+    if constexpr (GAPS) {
+      if (rescan) {
+        int g = in ? (int)cols[j] + 1 : 0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int t = __shfl_up_sync(0xffffffffu, g, o);
+          if (lane >= o) g += t;
+        }
+        cscan = cbase2 + g;
+        cbase2 += __shfl_sync(0xffffffffu, g, 31);
+      }
+    }
     if (in) {
       if (j - j0 < kSplitStash) {                               // (written by this same lane in pass 1)
         const int2 e = stash[j - j0];
         r = e.x;
         x = __int_as_float(e.y);
+      } else if constexpr (GAPS) {
+        r = rank ? __ldg(rank + cscan) : cscan;
+        x = u8_count(reinterpret_cast<const unsigned char*>(vals), j - base, ovf_idx, ovf_val, novf);
       } else {
         const int c = (int)__ldg(cols + j);
         r = rank ? __ldg(rank + c) : c;
@@ -1474,7 +1541,47 @@ static int launch_hot_split(const long long* rowptr, const CT* cols, const VT* v
   return SPMF_OK;
 }
 
+static int launch_hot_split8(const long long* rowptr, const unsigned char* gaps8, const unsigned char* vals8,
+                             const int* ovf_idx, const float* ovf_val, int novf, int nrows, const int* rank, int H,
+                             long long* rowptr_out, int* cols_out, float* vals_out, int* rowmid, void* xhot,
+                             float* rowsum, float* lgam, cudaStream_t st) {
+  const long long hp = (H + 63) / 64 * 64;
+  const size_t stash = (size_t)kSplitStash * sizeof(int2);
+  const size_t smem = (size_t)hp * 2 + stash;
+  if (smem <= 112 * 1024) {
+    static bool attr = false;
+    if (!attr) {
+      cudaError_t e = cudaFuncSetAttribute(hot_split_kernel<true, unsigned char, unsigned char, true>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+      if (e != cudaSuccess) return (int)e;
+      attr = true;
+    }
+    hot_split_kernel<true, unsigned char, unsigned char, true><<<(nrows + 127) / 128 * 128, kSplitThreads, smem, st>>>(
+        rowptr, gaps8, vals8, nrows, rank, H, rowptr_out, cols_out, vals_out, rowmid, (unsigned short*)xhot, hp / 64,
+        rowsum, lgam, ovf_idx, ovf_val, novf);
+  } else {
+    cudaError_t e = cudaMemsetAsync(xhot, 0, (size_t)spmf_umma_tiled_a_elems(nrows, hp) * 2, st);
+    if (e != cudaSuccess) return (int)e;
+    hot_split_kernel<false, unsigned char, unsigned char, true><<<nrows, kSplitThreads, stash, st>>>(
+        rowptr, gaps8, vals8, nrows, rank, H, rowptr_out, cols_out, vals_out, rowmid, (unsigned short*)xhot, hp / 64,
+        rowsum, lgam, ovf_idx, ovf_val, novf);
+  }
+  SPMF_CHECK_LAUNCH();
+  return SPMF_OK;
+}
+
 extern "C" {
+
+int spmf_hot_split_u8(const long long* rowptr, const unsigned char* gaps8, const unsigned char* vals8,
+                      const int* ovf_idx, const float* ovf_val, int novf, int nrows, const int* rank, int H,
+                      long long* rowptr_out, int* cols_out, float* vals_out, int* rowmid, void* xhot, float* rowsum,
+                      float* lgam, void* stream) {
+  if (!rowptr || !gaps8 || !vals8 || !rowptr_out || !cols_out || !vals_out || !rowmid || !xhot) return SPMF_ERR_BAD_ARG;
+  if ((rowsum == nullptr) != (lgam == nullptr) || novf < 0 || (novf > 0 && (!ovf_idx || !ovf_val))) return SPMF_ERR_BAD_ARG;
+  if (nrows <= 0 || H <= 0) return SPMF_ERR_BAD_ARG;
+  return launch_hot_split8(rowptr, gaps8, vals8, ovf_idx, ovf_val, novf, nrows, rank, H, rowptr_out, cols_out, vals_out,
+                           rowmid, xhot, rowsum, lgam, (cudaStream_t)stream);
+}
 
 int spmf_hot_split_packed(const long long* rowptr, const int* cols, const unsigned short* cols16, const float* vals,
                           const unsigned short* vals16, int nrows, long long nnz, const int* rank, int H,

@@ -11,6 +11,8 @@ from __future__ import annotations
 from dataclasses import dataclass, field
 from typing import Dict, Optional
 
+import os
+
 import numpy as np
 import torch
 
@@ -117,12 +119,21 @@ class DeviceBatch:
                         hcvals=torch.empty(m, dtype=torch.float32, device=dev),
                         scratch=torch.empty(_abi._lib.spmf_csc_scratch_ints(self.D), dtype=torch.int32, device=dev))
         st = _stream()
-        c16, v16 = packed if packed is not None else (None, None)
-        _abi.call("spmf_hot_split_packed", _ptr(self.rowptr), None if c16 is not None else _ptr(self.cols), _ptr(c16),
-                  None if v16 is not None else _ptr(self.vals), _ptr(v16), n, nnz, _ptr(rank), H,
-                  _ptr(bufs["rowptr"]), _ptr(bufs["cols"]), _ptr(bufs["vals"]), _ptr(bufs["rowmid"]),
-                  _ptr(bufs["xhot"]), _ptr(bufs.get("xthot")),
-                  _ptr(self.rowsum) if row_consts else None, _ptr(self.lgam) if row_consts else None, st)
+        rs, lg = (_ptr(self.rowsum), _ptr(self.lgam)) if row_consts else (None, None)
+        if packed is not None and len(packed) == 5:
+            # 2-byte transfer format: (gaps8, vals8, ovf_idx, ovf_val, novf) -- expanded inside the split
+            g8, v8, oi, ov, novf = packed
+            if bufs.get("xthot") is not None:
+                raise _abi.SpmfError("the 2-byte split does not build the transposed block")
+            _abi.call("spmf_hot_split_u8", _ptr(self.rowptr), _ptr(g8), _ptr(v8), _ptr(oi) if novf else None,
+                      _ptr(ov) if novf else None, int(novf), n, _ptr(rank), H, _ptr(bufs["rowptr"]), _ptr(bufs["cols"]),
+                      _ptr(bufs["vals"]), _ptr(bufs["rowmid"]), _ptr(bufs["xhot"]), rs, lg, st)
+        else:
+            c16, v16 = packed if packed is not None else (None, None)
+            _abi.call("spmf_hot_split_packed", _ptr(self.rowptr), None if c16 is not None else _ptr(self.cols), _ptr(c16),
+                      None if v16 is not None else _ptr(self.vals), _ptr(v16), n, nnz, _ptr(rank), H,
+                      _ptr(bufs["rowptr"]), _ptr(bufs["cols"]), _ptr(bufs["vals"]), _ptr(bufs["rowmid"]),
+                      _ptr(bufs["xhot"]), _ptr(bufs.get("xthot")), rs, lg, st)
         for part, pre in ((0, "h"), (1, "")):       # covered entries / the rest
             if part == 0 and not hot_csc:
                 continue
@@ -584,7 +595,7 @@ class BatchUploader:
         self.rowptr[:n + 1].copy_(hb.rowptr, non_blocking=True)
         if hb.base:
             self.rowptr[:n + 1].sub_(hb.base)              # the host sends a view of its absolute row pointers
-        c16 = v16 = None
+        c16 = v16 = packed8 = None
         if hb.gaps8 is not None:
             # 2 bytes per nonzero over PCIe; expanded to int32 / fp32 by one kernel (+ a patch of the few large counts)
             self.g8[:nnz].copy_(hb.gaps8, non_blocking=True)
@@ -596,8 +607,11 @@ class BatchUploader:
             if novf:
                 self.ovf_i[:novf].copy_(hb.ovf_idx, non_blocking=True)
                 self.ovf_v[:novf].copy_(hb.ovf_val, non_blocking=True)
-            _abi.call("spmf_csr_unpack8", _ptr(self.rowptr), _ptr(self.g8), _ptr(self.v8), n, _ptr(self.ovf_i),
-                      _ptr(self.ovf_v), novf, _ptr(self.cols), _ptr(self.vals), st)
+            if self.hot is not None and os.environ.get("SPMF_FUSED_UNPACK8", "1") != "0":
+                packed8 = (self.g8, self.v8, self.ovf_i, self.ovf_v, novf)       # ... inside the hot split
+            else:
+                _abi.call("spmf_csr_unpack8", _ptr(self.rowptr), _ptr(self.g8), _ptr(self.v8), n, _ptr(self.ovf_i),
+                          _ptr(self.ovf_v), novf, _ptr(self.cols), _ptr(self.vals), st)
         elif hb.cols.dtype == torch.uint16:
             c16 = self.c16[:nnz]
             c16.copy_(hb.cols, non_blocking=True)
@@ -615,12 +629,12 @@ class BatchUploader:
             # its CSC copy -- all on this (copy) stream, into persistent staging
             # (the split reads the compact arrays directly; the wide cols / vals of such a batch are not
             # materialised -- the hybrid step reads the ranked copies only)
-            db = DeviceBatch(rowptr=self.rowptr[:n + 1], cols=None if c16 is not None else self.cols,
-                             vals=None if v16 is not None else self.vals, rowsum=self.rowsum[:n],
+            db = DeviceBatch(rowptr=self.rowptr[:n + 1], cols=None if (c16 is not None or packed8) else self.cols,
+                             vals=None if (v16 is not None or packed8) else self.vals, rowsum=self.rowsum[:n],
                              lgam=self.lgam[:n], nrows=n, nnz=nnz, D=self.D)
             db.ensure_hot(self.hot[0], int(self.hot[1]), bufs=self.hot_bufs, hot_csc=self.hot_csc,
                           row_consts=True,          # row constants come out of the split's first pass
-                          packed=(c16, v16), version=self.hot_version)
+                          packed=packed8 or (c16, v16), version=self.hot_version)
             # same device arrays for every batch through this slot: the step may be replayed as a graph
             db._resident, db._step_graphs, db._nnz_bound = True, self.graphs, self.cap_nnz
             return db

@@ -340,3 +340,40 @@ def test_dense_ingest_fit_and_gather_fallback():
         a, b = run(False), run(True)
         assert a[-1] < a[0]
         assert np.allclose(a, b, rtol=1e-5), (K, a, b)
+
+
+@pytest.mark.parametrize("D,K,B", [(300, 32, 200), (2600, 16, 130)])
+def test_u8_format_fused_into_the_split(D, K, B):
+    """2-byte transfer format read by the hot split itself (spmf_hot_split_u8): same hybrid form and step as the
+    CSR upload.  Covers counts above 254 (overflow list), zero-valued bridge entries (gaps > 256 columns) and a
+    row longer than the split's shared-memory stash (its columns are re-scanned in the second pass)."""
+    import spmf_b200
+    from spmf_b200.data import CsrShard, HostCsr, prefetch_to_device
+    dev = torch.device("cuda:0")
+    S = 4
+    x = make_counts(2 * B, D, seed=9, kind="sparse")
+    x[0, :] = np.maximum(x[0, :], 1.0)              # a full row (D = 2600: longer than the 2048-entry stash)
+    x[0, D - 3], x[5, 1], x[B + 2, D // 2] = 700.0, 255.0, 3000.0
+    x[7, :] = 0
+    x[7, 0], x[7, D - 1] = 2.0, 1.0                 # D = 2600: a gap of 2598 columns -> bridge entries
+    sh = CsrShard.from_dense(x, dev)
+    model = spmf_b200.PoissonFactorization(latent_dim=K, feature_dim=D, u_tau_scale=1.0 / np.sqrt(x.size),
+                                           device=dev, seed=3)
+    model.compute_scales(sh)
+    eng = model._engine_for(S)
+    assert eng.hot_mode == 2 and 0 < eng.hot_cols
+    host = HostCsr.from_shard(sh, compact="u8")
+    eng.fill_noise(step=0)
+    for i, db in enumerate(prefetch_to_device(host.iter_batches(B), dev, hot=model._hot_spec(eng))):
+        assert db.cols is None and db.hot is not None           # never widened to int32 / fp32 feature-order arrays
+        ref_b = sh.batch(i * B, B, cache=False)
+        h_ref = ref_b.ensure_hot(eng.rank, eng.hot_cols, hot_csc=False, version=getattr(eng, "rank_version", 0))
+        h = db.hot
+        assert torch.equal(h.xhot[:h_ref.xhot.numel()].view(torch.int16), h_ref.xhot.view(torch.int16))
+        assert torch.equal(db.rowsum, ref_b.rowsum) and torch.allclose(db.lgam, ref_b.lgam, rtol=1e-6)
+        assert torch.equal(h.rowmid[:B], h_ref.rowmid[:B])
+        p = eng.loss_and_grad(db, fresh_noise=False).clone()
+        g = eng.grads.clone()
+        p0 = eng.loss_and_grad(ref_b, fresh_noise=False).clone()
+        assert rel_err(p.cpu().numpy(), p0.cpu().numpy()) < 1e-6
+        assert rel_err(g.cpu().numpy(), eng.grads.cpu().numpy()) < 2e-5

@@ -289,3 +289,33 @@ def test_bernoulli_fit_decreases_loss():
     factory = lambda: [{'counts': x[i:i + 100]} for i in range(0, 400, 100)]
     losses = m.fit(factory, num_steps=40, learning_rate=0.05, sample_size=4, verbose=False, rel_tol=None)
     assert np.isfinite(losses).all() and losses[-1] < losses[0]
+
+
+def test_guard_on_a_dense_ingested_batch():
+    """A batch that arrived as a dense slab (HostDense) has no feature-order CSR on the device: the guard's slow
+    path rebuilds its dense working copy from the raw slab (spmf_guard_rows_fix_dense) and must give the same
+    step as the CSR-uploaded batch (which test_guard_training_step_matches_guarded_autograd pins to autograd)."""
+    import spmf_b200
+    from spmf_b200.data import BatchUploader, HostDense
+    dev = torch.device("cuda:0")
+    D, K, B, S = 160, 16, 192, 4
+    x = make_counts(B, D, seed=4, kind="noise")
+    oracle = make_oracle(D, K, 10 * B, x)
+    params = _kill_column(perturbed_params(oracle, 0.3, seed=1), D // 3)
+    from oracle.spmf_oracle import draw_noise
+    noise = draw_noise(oracle, params, S, seed=2)
+    model = spmf_b200.PoissonFactorization(latent_dim=K, feature_dim=D, u_tau_scale=1.0 / np.sqrt(10 * B * D), device=dev)
+    model.compute_scales(lambda: [{'counts': x}])
+    eng = model._engine_for(S)
+    assert eng.hot_mode == 2
+    _load(eng, params)
+    eng.set_noise_from(noise)
+    p_ref = eng.loss_and_grad(spmf_b200.as_device_batch(x, dev), fresh_noise=False).clone()
+    g_ref = eng.grads.clone()
+    assert bool(torch.isfinite(p_ref).all()) and bool(torch.isfinite(g_ref).all())
+    db = BatchUploader(dev, D, hot=model._hot_spec(eng)).upload(HostDense(x).batch(0, B))
+    assert db.dense_raw is not None
+    p = eng.loss_and_grad(db, fresh_noise=False).clone()
+    torch.cuda.synchronize()
+    assert abs(float(eng.loss_value(p).item()) - float(eng.loss_value(p_ref).item())) <= 1e-6 * abs(float(eng.loss_value(p_ref).item()))
+    assert rel_err(eng.grads.cpu().numpy(), g_ref.cpu().numpy()) < 2e-5
