@@ -312,31 +312,36 @@ def main():
         host = HostCsr.from_shard(shard, compact=fmt if fmt != "u16" else True)
     hbatches = [host.batch(i * B, B) for i in range(len(batches))]
 
-    loss_bufs = [torch.empty(1, dtype=torch.float64).pin_memory() for _ in range(2)]
+    LOOKAHEAD = 2            # the host blocks on the loss of step i-2: two steps are always enqueued behind it
+    loss_bufs = [torch.empty(1, dtype=torch.float64).pin_memory() for _ in range(LOOKAHEAD + 1)]
     losses_read = []
 
     def run_e2e(n, start):
-        # each step's loss is copied D2H asynchronously right behind the step; the host blocks on the
-        # PREVIOUS step's copy only, so launches for step i+1 are issued while step i runs
+        # each step's loss is copied D2H asynchronously right behind the step and read by the host LOOKAHEAD
+        # steps later, so launches for the next steps are issued while this one runs; every loss is read
+        # inside the timed region
         src = (hbatches[(start + i) % len(hbatches)] for i in range(n))
-        prev = None
+        pending = []
         tlast = time.perf_counter()
-        for i, db in enumerate(prefetch_to_device(src, dev, hot=model._hot_spec(eng) if hybrid else None)):
+        for i, db in enumerate(prefetch_to_device(src, dev, depth=LOOKAHEAD + 1,
+                                                  hot=model._hot_spec(eng) if hybrid else None)):
             if os.environ.get("BENCH_DEBUG"):
                 tnow = time.perf_counter()
                 print(f"e2e iter {i} host dt {1e3 * (tnow - tlast):.2f} ms", file=sys.stderr)
                 tlast = tnow
             loss = model.elbo_step({"counts": db}, S, learning_rate=args.lr, variant=args.variant)
-            buf = loss_bufs[i & 1]
+            buf = loss_bufs[i % (LOOKAHEAD + 1)]
             buf.copy_(loss.reshape(1), non_blocking=True)             # D2H read of this step's result
             ev = torch.cuda.Event()
             ev.record()
-            if prev is not None:
-                prev[0].synchronize()
-                losses_read.append(float(prev[1][0]))
-            prev = (ev, buf)
-        prev[0].synchronize()
-        losses_read.append(float(prev[1][0]))
+            pending.append((ev, buf))
+            if len(pending) > LOOKAHEAD:
+                e0, b0 = pending.pop(0)
+                e0.synchronize()
+                losses_read.append(float(b0[0]))
+        for e0, b0 in pending:
+            e0.synchronize()
+            losses_read.append(float(b0[0]))
 
     run_e2e(args.warmup, 0)
     barrier()
@@ -354,6 +359,11 @@ def main():
     e2e_value = nnz_all * K / (float(t2.item()) * 1e-3)
     h2d = sum(hbatches[(args.warmup + i) % len(hbatches)].nbytes() for i in range(args.steps)) / args.steps
     clk = clocks.stop() if clocks else None
+    exchange = None
+    if world > 1:
+        from spmf_b200.parallel import check_exchange, exchange_kind
+        check_exchange(eng)                 # raises if a rank ever gave up waiting for a peer
+        exchange = exchange_kind(eng)
 
     # ------------------------------------------------ roofline of the dominant kernel
     peaks = {}
@@ -478,7 +488,8 @@ def main():
             "data": "synthetic",
             "config": {"workload": wl["desc"], "rows_per_gpu_per_step": B, "shard_rows_per_gpu": shard.nrows,
                        "nnz_per_gpu_per_step": nnz_all / world / args.steps, "D": D, "K": K, "S": S,
-                       "parallelism": f"dp{world} row-sharded, 1 all-reduce/step",
+                       "parallelism": (f"dp{world} row-sharded, 1 exchange/step ({exchange})" if world > 1
+                                       else "dp1 (single GPU: no exchange)"),
                        "l2": "inputs larger than L2 (16 distinct batches cycled; ~130 MB of CSR+CSC each, "
                              "plus ~260 MB of bf16 hot block in hybrid mode)",
                        "variant": args.variant, "final_loss": final_loss,

@@ -37,6 +37,7 @@ extern "C" {
 #define SPMF_OK 0
 #define SPMF_ERR_BAD_ARG (-1)
 #define SPMF_ERR_UNSUPPORTED (-2)
+#define SPMF_ERR_PEER_TIMEOUT (-3)   /* a peer rank never reached the step's exchange (spmf_p2p_status) */
 #define SPMF_MAX_K 128
 #define SPMF_NUM_TENSORS 24
 #define SPMF_NUM_VARS 12
@@ -146,6 +147,41 @@ int spmf_unpack_adam(float* comm_slack, int slack_floats, int S, float w_entropy
                      double* loss_out, const float* grads, long long n_data, const spmf_adam_args* adam,
                      void* stream);
 int spmf_colsum(const float* in, long long n, int c, int q, double* out, double* scratch, void* stream);
+
+/* ---- multi-GPU tail over NVLink peer memory (net-new; replaces ncclAllReduce -> spmf_unpack_adam) ----
+ * One process per GPU.  Gradient, parameter and flag buffers come from spmf_p2p_alloc (cudaMalloc, zeroed) and
+ * are mapped into the peers with CUDA IPC: spmf_p2p_export fills a 64-byte handle, the host exchanges the
+ * handles once, spmf_p2p_open maps a peer's buffer (peer access enabled lazily).
+ * spmf_p2p_reduce_adam -- ONE kernel per step and rank: wait for every rank's gradients; for this rank's 1/world
+ * slice of the block [0, comm_off) add the world partial gradients in rank order (16-byte peer loads), apply Adam
+ * (moments live on the owner only) and store the new values into every rank's parameter buffer; Adam on the
+ * replicated tensors [n_block, n_params) locally; fold the ('z','x') (hi,lo) pairs of all ranks into parts /
+ * loss_out (as spmf_unpack_parts); leave when every peer's stores have landed, then zero the local slack.
+ * `epoch` must increase by one per call (same value on every rank).  Waits are bounded (~2 s): a missing peer
+ * sets a status word (spmf_p2p_status -> SPMF_ERR_PEER_TIMEOUT) instead of hanging the device. */
+#define SPMF_P2P_MAX_WORLD 8
+#define SPMF_P2P_HANDLE_BYTES 64
+typedef struct spmf_p2p_args {
+  int world, rank, S, slack;           /* slack = floats of bookkeeping at the end of the reduced block */
+  unsigned int epoch;
+  int reserved;
+  long long n_params, n_block, comm_off;   /* n_block = comm_off + slack */
+  double w_entropy, w_prior;
+  float* grads[SPMF_P2P_MAX_WORLD];    /* [q] = rank q's gradient buffer as mapped in THIS process */
+  float* params[SPMF_P2P_MAX_WORLD];
+  void* flags[SPMF_P2P_MAX_WORLD];     /* spmf_p2p_flag_bytes() each, zeroed once before the first call */
+  double* parts;                       /* [S][16] local */
+  double* loss_out;
+  const spmf_adam_args* adam;          /* params = params[rank]; lr = 0: reduce + parts only */
+} spmf_p2p_args;
+int spmf_p2p_alloc(long long bytes, void** ptr);
+int spmf_p2p_free(void* ptr);
+int spmf_p2p_export(void* ptr, unsigned char* handle64);
+int spmf_p2p_open(const unsigned char* handle64, void** ptr);
+int spmf_p2p_close(void* ptr);
+long long spmf_p2p_flag_bytes(void);
+int spmf_p2p_status(const void* flags, void* stream);
+int spmf_p2p_reduce_adam(const spmf_p2p_args* args, void* stream);
 
 /* ---- data formats either side of the path ---- */
 /* compute_scales (poisson.py:113-154): colsum[D] (double) and colnnz[D] (float, as the reference

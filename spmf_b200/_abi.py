@@ -122,6 +122,18 @@ class AdamArgs(C.Structure):
                 + [("step", i32), ("reserved", i32), ("params", p), ("m", p), ("v", p)])
 
 
+P2P_MAX_WORLD, P2P_HANDLE_BYTES = 8, 64
+
+
+class P2PArgs(C.Structure):
+    """Mirror of `spmf_p2p_args` (include/spmf_b200.h)."""
+    _fields_ = ([(n, i32) for n in ("world", "rank", "S", "slack")] + [("epoch", u32), ("reserved", i32)]
+                + [(n, i64) for n in ("n_params", "n_block", "comm_off")]
+                + [("w_entropy", C.c_double), ("w_prior", C.c_double)]
+                + [("grads", p * P2P_MAX_WORLD), ("params", p * P2P_MAX_WORLD), ("flags", p * P2P_MAX_WORLD)]
+                + [("parts", p), ("loss_out", p), ("adam", C.POINTER(AdamArgs))])
+
+
 class StepArgs(C.Structure):
     """Mirror of `spmf_step_args` (include/spmf_b200.h), field for field."""
     _fields_ = (
@@ -168,6 +180,15 @@ _SIGS["spmf_backward_post_m"] = (i32, [p, p, p, p, i32, i32, i32, p, p, p, p, p,
                                         p, p, p, p, p, i32, p])
 _SIGS["spmf_prepare_batch"] = (i32, [p, p, p, p, p, i32, i64, i32, p, p, p, p, p, p, p])
 
+_SIGS["spmf_p2p_alloc"] = (i32, [i64, p])
+_SIGS["spmf_p2p_free"] = (i32, [p])
+_SIGS["spmf_p2p_export"] = (i32, [p, p])
+_SIGS["spmf_p2p_open"] = (i32, [p, p])
+_SIGS["spmf_p2p_close"] = (i32, [p])
+_SIGS["spmf_p2p_flag_bytes"] = (i64, [])
+_SIGS["spmf_p2p_status"] = (i32, [p, p])
+_SIGS["spmf_p2p_reduce_adam"] = (i32, [p, p])
+
 EXPORTS = tuple(_SIGS)
 
 for _name, (_res, _args) in _SIGS.items():
@@ -178,7 +199,8 @@ for _name, (_res, _args) in _SIGS.items():
 
 def _check(rc, name):
     if rc != 0:
-        kind = {-1: "bad argument", -2: "unsupported configuration"}.get(rc, f"CUDA error {rc}")
+        kind = {-1: "bad argument", -2: "unsupported configuration",
+                -3: "a peer rank never reached the exchange"}.get(rc, f"CUDA error {rc}")
         raise SpmfError(f"{name} failed: {kind}")
 
 

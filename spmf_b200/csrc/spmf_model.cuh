@@ -99,6 +99,21 @@ SPMF_HD void adam_apply(const AdamCfg& a, long long i, float g) {
   a.p[i] -= a.lr * (mi / a.bc1) / (sqrtf(vi / a.bc2) + a.eps);
 }
 
+#ifdef SPMF_B200_H
+// host: C-ABI optimiser arguments -> kernel configuration (lr = 0: off)
+inline AdamCfg make_adam_cfg(const spmf_adam_args* a) {
+  AdamCfg c{};
+  if (!a || !(a->lr > 0.f) || !a->params || !a->m || !a->v || a->step <= 0) return c;
+  c.lr = a->lr; c.b1 = a->beta1; c.b2 = a->beta2; c.eps = a->eps;
+  c.bc1 = 1.f - powf(a->beta1, (float)a->step);
+  c.bc2 = 1.f - powf(a->beta2, (float)a->step);
+  c.clip = a->clip_value;
+  c.grad_scale = a->grad_scale > 0.f ? a->grad_scale : 1.f;
+  c.p = a->params; c.m = a->m; c.v = a->v;
+  return c;
+}
+#endif
+
 // ---------------- Normal-based factor:  y = softplus(loc + softplus(rho) * eps) ----------------
 struct NParam { float loc, sig, logsig, acc_dt, acc_dte; };
 struct NDraw { float t, y, sg, oms, lsg; };   // pre-softplus t, softplus, sigmoid, 1-sigmoid, log sigmoid

@@ -715,7 +715,7 @@ csc_block_hist_kernel(const long long* __restrict__ rowptr, const int* __restric
       long long j0, j1;
       part_range(rowptr, rowmid, part, row, j0, j1);
 #pragma unroll 4
-      for (long long j = j0 + lane; j < j1; j += 32) atomicAdd(&h[__ldg(cols + j)], 1);   // (loads batched 4 deep)
+      for (long long j = j0 + lane; j < j1; j += 32) atomicAdd(&h[__ldcs(cols + j)], 1);   // (loads batched 4 deep)
     }
   }
   __syncthreads();
@@ -759,9 +759,11 @@ csc_block_scatter_kernel(const long long* __restrict__ rowptr, const int* __rest
     part_range(rowptr, rowmid, part, row, j0, j1);
 #pragma unroll 4
     for (long long j = j0 + lane; j < j1; j += 32) {
-      const int pos = atomicAdd(&cur[__ldg(cols + j)], 1);
-      rows_out[pos] = row;
-      vals_out[pos] = fabsf(__ldg(vals + j));     // the sign is the hot-split coverage flag
+      // (streaming hints: this build runs on the copy stream under the previous step, whose gather kernels
+      // live off the L2-resident operand tables)
+      const int pos = atomicAdd(&cur[__ldcs(cols + j)], 1);
+      __stcs(rows_out + pos, row);
+      __stcs(vals_out + pos, fabsf(__ldcs(vals + j)));     // the sign is the hot-split coverage flag
     }
   }
 }
@@ -984,7 +986,7 @@ constexpr int kSplitStash = 2048;     // (rank, value) pairs per row kept betwee
 // count of entry e of the 2-byte format: the byte, or (byte 255) its value in the sorted overflow list
 __device__ __forceinline__ float u8_count(const unsigned char* __restrict__ vals8, long long e,
                                           const int* __restrict__ ovf_idx, const float* __restrict__ ovf_val, int novf) {
-  const unsigned b = vals8[e];
+  const unsigned b = __ldcs(vals8 + e);
   if (b != 255u) return (float)b;
   int lo = 0, hi = novf - 1;
   while (lo < hi) {
@@ -1045,7 +1047,7 @@ hot_split_kernel(const long long* __restrict__ rowptr, const CT* __restrict__ co
   int cstart = -1;                                              // GAPS: column before my piece's first entry
   if constexpr (GAPS) {
     int gs = 0;
-    for (long long j = a0 + lane; j < a1; j += 32) gs += (int)cols[j] + 1;
+    for (long long j = a0 + lane; j < a1; j += 32) gs += (int)__ldcs(cols + j) + 1;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) gs += __shfl_xor_sync(0xffffffffu, gs, o);
     if (lane == 0) s_gap[w] = gs;
@@ -1055,7 +1057,7 @@ hot_split_kernel(const long long* __restrict__ rowptr, const CT* __restrict__ co
     for (long long jb = a0; jb < a1; jb += 32) {
       const long long j = jb + lane;
       const bool in = j < a1;
-      int g = in ? (int)cols[j] + 1 : 0;
+      int g = in ? (int)__ldcs(cols + j) + 1 : 0;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {                         // inclusive warp scan of the gaps
         const int t = __shfl_up_sync(0xffffffffu, g, o);
@@ -1074,9 +1076,9 @@ hot_split_kernel(const long long* __restrict__ rowptr, const CT* __restrict__ co
   } else {
 #pragma unroll 4
     for (long long j = a0 + lane; j < a1; j += 32) {
-      const int c = (int)__ldg(cols + j);
+      const int c = (int)__ldcs(cols + j);
       const int r = rank ? __ldg(rank + c) : c;
-      const float x = (float)__ldg(vals + j);
+      const float x = (float)__ldcs(vals + j);
       if (j - j0 < kSplitStash) stash[j - j0] = make_int2(r, __float_as_int(x));
       ncov += hot_covered(r, x, H) ? 1 : 0;
       if (rowsum) { rs += x; rl += lgamma1p_count(x); }
@@ -1118,7 +1120,7 @@ hot_split_kernel(const long long* __restrict__ rowptr, const CT* __restrict__ co
     int cscan = 0;
     if constexpr (GAPS) {
       if (rescan) {
-        int g = in ? (int)cols[j] + 1 : 0;
+        int g = in ? (int)__ldcs(cols + j) + 1 : 0;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
           const int t = __shfl_up_sync(0xffffffffu, g, o);
@@ -1137,9 +1139,9 @@ hot_split_kernel(const long long* __restrict__ rowptr, const CT* __restrict__ co
         r = rank ? __ldg(rank + cscan) : cscan;
         x = u8_count(reinterpret_cast<const unsigned char*>(vals), j - base, ovf_idx, ovf_val, novf);
       } else {
-        const int c = (int)__ldg(cols + j);
+        const int c = (int)__ldcs(cols + j);
         r = rank ? __ldg(rank + c) : c;
-        x = (float)__ldg(vals + j);
+        x = (float)__ldcs(vals + j);
       }
     }
     const bool cov = in && hot_covered(r, x, H);
@@ -1148,15 +1150,15 @@ hot_split_kernel(const long long* __restrict__ rowptr, const CT* __restrict__ co
     const unsigned below = (1u << lane) - 1u;
     if (cov) {
       const long long o = pc + __popc(mc & below);
-      cols_out[o] = r;
-      vals_out[o] = -x;
+      __stcs(cols_out + o, r);
+      __stcs(vals_out + o, -x);
       const unsigned short hx = (unsigned short)(__float_as_uint(x) >> 16);
       if constexpr (STAGED) xrow[r] = hx;
       else xhot[tiledA_index(row, r, hchunks)] = hx;           // UMMA-tiled X[nrows][Hp]
     } else if (in) {
       const long long o = pu + __popc(mu & below);
-      cols_out[o] = r;
-      vals_out[o] = x;
+      __stcs(cols_out + o, r);
+      __stcs(vals_out + o, x);
     }
     pc += __popc(mc);
     pu += __popc(mu);
@@ -1164,7 +1166,7 @@ hot_split_kernel(const long long* __restrict__ rowptr, const CT* __restrict__ co
   if constexpr (STAGED) {
     __syncthreads();
     for (int c = threadIdx.x; c < hp / 8; c += blockDim.x)
-      *reinterpret_cast<uint4*>(xhot + tiledA_index(row, 8LL * c, hchunks)) = reinterpret_cast<const uint4*>(xrow)[c];
+      __stcs(reinterpret_cast<uint4*>(xhot + tiledA_index(row, 8LL * c, hchunks)), reinterpret_cast<const uint4*>(xrow)[c]);
   }
 }
 

@@ -108,11 +108,16 @@ class AdviEngine:
         self.world_size = int(world_size)
         self.seed = int(seed)
         L = self.layout
-        self.params = torch.zeros(L.n_params, dtype=torch.float32, device=self.device)
+        from . import p2p
+        if self.world_size > 1 and p2p.enabled():
+            # data-parallel: parameters / gradients live in memory the peer GPUs can map (csrc/spmf_p2p.cu)
+            self.params, self.grads = p2p.peer_zeros(L.n_params, self.device), p2p.peer_zeros(L.n_params, self.device)
+        else:
+            self.params = torch.zeros(L.n_params, dtype=torch.float32, device=self.device)
+            self.grads = torch.zeros(L.n_params, dtype=torch.float32, device=self.device)
         L.fill_initial(self.params, self.u_tau_scale, self.s_tau_scale)
-        self.grads = torch.zeros_like(self.params)
-        self.adam_m = torch.zeros_like(self.params)
-        self.adam_v = torch.zeros_like(self.params)
+        self.adam_m = torch.zeros(L.n_params, dtype=torch.float32, device=self.device)
+        self.adam_v = torch.zeros(L.n_params, dtype=torch.float32, device=self.device)
         self.noise = torch.empty(L.n_noise, dtype=torch.float32, device=self.device)
         self.dgda = torch.zeros(L.n_noise, dtype=torch.float32, device=self.device)
         # [2][D]: decoder scale eta_i | encoder divisor (eta_i, or 1 under log_transform) -- spmf_model.cuh

@@ -43,17 +43,54 @@ def unpack_data_parts(eng, parts):
     return parts
 
 
+_LINKS = {}
+
+
+def peer_link(eng, group=None):
+    """The PeerLink of this engine's (shared) parameter buffer, set up on first use -- a collective call: every
+    rank reaches it at its first optimiser step.  None when the buffers cannot be peer-mapped on this node
+    (decided collectively; the NCCL all-reduce path is used instead) or SPMF_P2P=0."""
+    from . import p2p
+    if not p2p.enabled():
+        return None
+    key = (eng.params.data_ptr(), eng.grads.data_ptr())
+    if key not in _LINKS:
+        _LINKS[key] = p2p.PeerLink(eng.params, eng.grads, eng.device, group)
+    link = _LINKS[key]
+    return link if link.ok else None
+
+
+def check_exchange(eng):
+    """Raise if a peer-memory exchange of this engine gave up waiting for a rank (host sync; fit calls it once
+    per epoch next to its loss read-back)."""
+    link = _LINKS.get((eng.params.data_ptr(), eng.grads.data_ptr()))
+    if link is not None and link.ok:
+        link.check()
+
+
+def exchange_kind(eng):
+    link = _LINKS.get((eng.params.data_ptr(), eng.grads.data_ptr()))
+    return "p2p-kernel" if (link is not None and link.ok) else "nccl-allreduce"
+
+
 def allreduce_step(eng, parts, group=None, adam=False):
     """All-reduce gradients + data parts in one collective; returns the global loss (0-d tensor).
     adam=True: the optimiser step (all 24 tensors; the 16 replicated ones are bit-identical on every rank)
     rides in the same launch as the post-collective bookkeeping."""
-    dist.all_reduce(comm_block(eng), op=dist.ReduceOp.SUM, group=group)
     dev = getattr(eng, "device", None)
+    if adam and dev is not None and dev.type == "cuda" and eng.S <= 64:
+        link = peer_link(eng, group)
+        if getattr(eng, "_loss_buf", None) is None:
+            eng._loss_buf = torch.zeros(1, dtype=torch.float64, device=eng.device)
+        if link is not None:
+            # ONE kernel per rank over NVLink peer memory: reduce-scatter -> Adam -> all-gather (no NCCL call)
+            link.reduce_adam(eng, parts, eng.adam_args(), eng._loss_buf)
+            eng.launches += 1
+            return eng._loss_buf[0]
+    dist.all_reduce(comm_block(eng), op=dist.ReduceOp.SUM, group=group)
     if adam and dev is not None and dev.type == "cuda" and eng.S <= 64:
         import ctypes as C
         L = eng.layout
-        if getattr(eng, "_loss_buf", None) is None:
-            eng._loss_buf = torch.zeros(1, dtype=torch.float64, device=eng.device)
         slack = eng.grads[L.comm_off: L.comm_off + L.comm_slack]
         a = eng.adam_args()
         _abi.call("spmf_unpack_adam", slack.data_ptr(), L.comm_slack, eng.S, eng.entropy_weight, eng.prior_weight,

@@ -215,6 +215,10 @@ class PoissonFactorization:
             eng.process_group = self.process_group
             if self._params is not None:                # engines share parameters / optimiser state
                 first = next(iter(self._engines.values()))
+                if eng.params.data_ptr() != first.params.data_ptr():
+                    from . import p2p
+                    p2p.release(eng.params)
+                    p2p.release(eng.grads)
                 eng.params, eng.grads = first.params, first.grads
                 eng.adam_m, eng.adam_v = first.adam_m, first.adam_v
             self._engines[S] = eng
@@ -624,6 +628,9 @@ class PoissonFactorization:
             if nb == 0:
                 raise ValueError("batched_data_factory() yielded no batches")
             mean_loss = float(acc.item()) / nb                 # one host sync per epoch
+            if eng.world_size > 1:
+                from .parallel import check_exchange
+                check_exchange(eng)
             losses.append(mean_loss)
             if verbose:
                 print(f"Epoch {epoch}: average-batch loss: {mean_loss} last batch loss: {float(last.item())}")

@@ -82,6 +82,12 @@ def main():
     for _ in range(3):
         model.elbo_step({'counts': shard.batch(0, hi - lo)}, S, learning_rate=lr, clip_value=2.5)
     torch.cuda.synchronize()
+    from spmf_b200.parallel import check_exchange, exchange_kind
+    check_exchange(eng)
+    want = "nccl-allreduce" if os.environ.get("SPMF_P2P", "1") == "0" else os.environ.get("DP_CHECK_EXPECT", "p2p-kernel")
+    assert exchange_kind(eng) == want, (exchange_kind(eng), want)
+    if rank == 0:
+        print(f"dp_check world={world}: optimiser-step exchange = {exchange_kind(eng)}")
     p_dp = eng.params.clone()
     ref = p_dp.clone()
     dist.broadcast(ref, src=0)

@@ -107,7 +107,7 @@ def test_step_args_struct_matches_header(tmp_path):
     from spmf_b200 import _abi
     src = tmp_path / "sz.c"
     fields = ["seed", "params", "n_params", "vsum", "rowptr", "nrows", "adam_lr", "adam_t", "caller_stream", "ev_cols1",
-              "rank", "hot_cols", "t3_qstride", "rowmid", "hot_cvals", "dzrT3", "ev_gemm1", "aux_stream2", "ev_aux_join2", "hot_mode", "EVt", "ev_tile1", "scr_dpre", "ev_noise"]
+              "rank", "hot_cols", "t3_qstride", "rowmid", "hot_cvals", "dzrT3", "ev_gemm1", "aux_stream2", "ev_aux_join2", "hot_mode", "EVt", "ev_tile1", "scr_dpre", "ev_noise", "step_state", "dense_raw", "dense_raw_dtype"]
     prints = "".join(f'printf("%zu\\n", offsetof(spmf_step_args, {f}));' for f in fields)
     src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "%s"\nint main(){printf("%%zu\\n", sizeof(spmf_step_args));%s return 0;}\n'
                    % (HEADER, prints))
@@ -117,3 +117,21 @@ def test_step_args_struct_matches_header(tmp_path):
     assert out[0] == ctypes.sizeof(_abi.StepArgs)
     for f, off in zip(fields, out[1:]):
         assert getattr(_abi.StepArgs, f).offset == off, f
+
+
+def test_p2p_args_struct_matches_header(tmp_path):
+    """ctypes mirrors of spmf_p2p_args / spmf_adam_args have the C layout (gcc)."""
+    import subprocess
+    from spmf_b200 import _abi
+    src = tmp_path / "sz.c"
+    fields = ["epoch", "n_params", "comm_off", "w_prior", "grads", "params", "flags", "parts", "loss_out", "adam"]
+    prints = "".join(f'printf("%zu\\n", offsetof(spmf_p2p_args, {f}));' for f in fields)
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "%s"\nint main(){printf("%%zu\\n%%zu\\n", '
+                   'sizeof(spmf_p2p_args), sizeof(spmf_adam_args));%s return 0;}\n' % (HEADER, prints))
+    exe = tmp_path / "sz"
+    subprocess.check_call(["gcc", "-o", str(exe), str(src)])
+    out = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    assert out[0] == ctypes.sizeof(_abi.P2PArgs) and out[1] == ctypes.sizeof(_abi.AdamArgs)
+    for f, off in zip(fields, out[2:]):
+        assert getattr(_abi.P2PArgs, f).offset == off, f
+    assert _abi.P2P_MAX_WORLD == 8 and _abi.P2P_HANDLE_BYTES == 64
