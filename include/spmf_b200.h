@@ -164,7 +164,7 @@ int spmf_colsum(const float* in, long long n, int c, int q, double* out, double*
 typedef struct spmf_p2p_args {
   int world, rank, S, slack;           /* slack = floats of bookkeeping at the end of the reduced block */
   unsigned int epoch;
-  int reserved;
+  int skip_tail;                       /* 1: the replicated tensors were already stepped (adam_tail_early) */
   long long n_params, n_block, comm_off;   /* n_block = comm_off + slack */
   double w_entropy, w_prior;
   float* grads[SPMF_P2P_MAX_WORLD];    /* [q] = rank q's gradient buffer as mapped in THIS process */
@@ -433,6 +433,12 @@ typedef struct spmf_step_args {
    * upload (feature order) is what the guard densifies from */
   const void* dense_raw;
   int dense_raw_dtype;
+  /* 1: Adam on the tensors that never see a data term ([comm_off + comm_slack, n_params): their gradient is
+   * final after the data-independent half of the backward) runs on the side stream under the data term; the
+   * closing Adam then covers [0, comm_off) only.  Needs the split backward (scr_dpre) and adam_lr > 0.  With
+   * world_size > 1 this is the only Adam the step applies -- the block [0, comm_off) belongs to the exchange
+   * (spmf_p2p_reduce_adam with skip_tail = 1, or all-reduce + spmf_unpack_adam over n_data = comm_off + slack). */
+  int adam_tail_early;
 } spmf_step_args;
 int spmf_advi_step(const spmf_step_args* args);
 /* Replay of a whole step as ONE CUDA graph launch (all streams, events and kernels of spmf_advi_step):

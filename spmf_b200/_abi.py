@@ -127,7 +127,7 @@ P2P_MAX_WORLD, P2P_HANDLE_BYTES = 8, 64
 
 class P2PArgs(C.Structure):
     """Mirror of `spmf_p2p_args` (include/spmf_b200.h)."""
-    _fields_ = ([(n, i32) for n in ("world", "rank", "S", "slack")] + [("epoch", u32), ("reserved", i32)]
+    _fields_ = ([(n, i32) for n in ("world", "rank", "S", "slack")] + [("epoch", u32), ("skip_tail", i32)]
                 + [(n, i64) for n in ("n_params", "n_block", "comm_off")]
                 + [("w_entropy", C.c_double), ("w_prior", C.c_double)]
                 + [("grads", p * P2P_MAX_WORLD), ("params", p * P2P_MAX_WORLD), ("flags", p * P2P_MAX_WORLD)]
@@ -156,7 +156,7 @@ class StepArgs(C.Structure):
                             "ev_gemm0", "ev_gemm1", "aux_stream1", "aux_stream2", "ev_aux_fork", "ev_aux_join1",
                             "ev_aux_join2")]
         + [("hot_mode", i32), ("EVt", p), ("ev_tile0", p), ("ev_tile1", p), ("scr_dpre", p), ("ev_noise", p)]
-        + [("link", i32), ("gs", p), ("xdense", p), ("xdense_in", p), ("step_state", p), ("model", i32), ("state_preset", i32), ("dense_raw", p), ("dense_raw_dtype", i32)]
+        + [("link", i32), ("gs", p), ("xdense", p), ("xdense_in", p), ("step_state", p), ("model", i32), ("state_preset", i32), ("dense_raw", p), ("dense_raw_dtype", i32), ("adam_tail_early", i32)]
     )
 
 

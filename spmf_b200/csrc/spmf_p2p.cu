@@ -12,7 +12,8 @@
 //      order, one owner per element: replicas cannot diverge), applies Adam to its local (params, m, v)
 //      -- the moments of an element live on its owner only -- and stores the new parameter value into
 //      EVERY rank's parameter buffer,
-//   3. applies Adam to the replicated tensors locally (deterministic kernels => bit-identical everywhere),
+//   3. applies Adam to the replicated tensors locally (deterministic kernels => bit-identical everywhere;
+//      skipped when the step already did it under its data term: spmf_step_args.adam_tail_early),
 //   4. folds the per-draw ('z','x') partial sums of all ranks into the loss parts (all ranks, rank order),
 //   5. signals "my stores are out" and leaves when every peer has said the same: from then on this
 //      rank's parameter buffer is complete and its gradient buffer is free to be overwritten.
@@ -55,6 +56,7 @@ __device__ __forceinline__ bool reached(unsigned flag, unsigned epoch) { return 
 struct P2PArgs {
   int world, rank, S, slack;
   unsigned epoch;
+  int skip_tail;
   long long n_params, n_block, comm_off;      // floats: whole buffer, reduced block (slack at its end), slack offset
   double w_entropy, w_prior;
   float* grads[SPMF_P2P_MAX_WORLD];
@@ -126,7 +128,7 @@ p2p_reduce_adam_kernel(const P2PArgs a) {
         if (q < W && q != a.rank) reinterpret_cast<float4*>(a.params[q])[i] = p;
     }
     // ---- 3. replicated tensors: local Adam
-    if (a.adam.lr > 0.f)
+    if (a.adam.lr > 0.f && !a.skip_tail)
       for (long long i = a.n_block + tid; i < a.n_params; i += nthr) adam_apply(a.adam, i, a.grads[a.rank][i]);
     // ---- 4. loss parts: ('z','x') as (hi, lo) float pairs, summed over the ranks in rank order
     if (blockIdx.x == gridDim.x - 1) {
@@ -236,7 +238,7 @@ int spmf_p2p_reduce_adam(const spmf_p2p_args* x, void* stream) {
       x->n_block != x->comm_off + x->slack || x->n_params < x->n_block || !x->parts || !x->loss_out || !x->adam)
     return SPMF_ERR_BAD_ARG;
   P2PArgs a{};
-  a.world = x->world; a.rank = x->rank; a.S = x->S; a.slack = x->slack; a.epoch = x->epoch;
+  a.world = x->world; a.rank = x->rank; a.S = x->S; a.slack = x->slack; a.epoch = x->epoch; a.skip_tail = x->skip_tail;
   a.n_params = x->n_params; a.n_block = x->n_block; a.comm_off = x->comm_off;
   a.w_entropy = x->w_entropy; a.w_prior = x->w_prior;
   for (int q = 0; q < x->world; ++q) {

@@ -62,6 +62,17 @@ int spmf_advi_step(const spmf_step_args* a) {
                                  a->s_tau_scale, a->decay, a->w_entropy, a->w_prior, a->world_size, a->grads,
                                  a->scr_f, a->scr_dpre, a->model, side));
   }
+  // Adam on the tensors without a data term: their gradients are final now, nothing later in the step reads
+  // their parameters (the data half of the backward touches v, w, u, s only) -> off the critical path
+  const long long n_block = a->comm_off + a->comm_slack;
+  const bool tail_early = a->adam_tail_early && a->adam_lr > 0.f;
+  if (tail_early) {
+    if (!split_bwd || !a->step_state || n_block <= 0 || n_block > a->n_params) return SPMF_ERR_BAD_ARG;
+    if (a->n_params > n_block)
+      STEP_TRY(spmf_adam_step_dev(a->params + n_block, a->grads + n_block, a->adam_m + n_block, a->adam_v + n_block,
+                                  a->n_params - n_block, a->adam_lr, a->adam_beta1, a->adam_beta2, a->adam_eps,
+                                  a->adam_t, a->clip_value, 1.0f, a->step_state, side));
+  }
   if (side != hot) CUDA_TRY(cudaEventRecord((cudaEvent_t)a->ev_join, side));
   // (tile mode with auxiliary streams: the fp64 operand sums are first read by spmf_rows_finish, so
   // they leave the critical path and run next to the encode GEMM)
@@ -213,12 +224,16 @@ int spmf_advi_step(const spmf_step_args* a) {
                                            (float)a->nrows, a->u_tau_scale, a->s_tau_scale, a->decay, a->w_entropy,
                                            a->w_prior, a->world_size, a->grads, a->parts, a->scr_f, a->scr_d, a->gs,
                                            a->model, hot));
-  if (a->adam_lr > 0.f) {
-    if (a->world_size > 1) return SPMF_ERR_BAD_ARG;      // the all-reduce must come between backward and Adam
+  if (a->adam_lr > 0.f && a->world_size > 1) {
+    // the exchange must come between the backward and the Adam step of the data-touched block: only the
+    // early tail step may run inside this call
+    if (!tail_early) return SPMF_ERR_BAD_ARG;
+  } else if (a->adam_lr > 0.f) {
     // the scalar slack inside the gradient block is host-side bookkeeping, not a parameter gradient
     CUDA_TRY(cudaMemsetAsync(a->grads + a->comm_off, 0, (size_t)a->comm_slack * sizeof(float), hot));
-    STEP_TRY(spmf_adam_step_dev(a->params, a->grads, a->adam_m, a->adam_v, a->n_params, a->adam_lr, a->adam_beta1,
-                                a->adam_beta2, a->adam_eps, a->adam_t, a->clip_value, 1.0f, a->step_state, hot));
+    STEP_TRY(spmf_adam_step_dev(a->params, a->grads, a->adam_m, a->adam_v, tail_early ? a->comm_off : a->n_params,
+                                a->adam_lr, a->adam_beta1, a->adam_beta2, a->adam_eps, a->adam_t, a->clip_value, 1.0f,
+                                a->step_state, hot));
   }
   if (hot != caller) {
     CUDA_TRY(cudaEventRecord((cudaEvent_t)a->ev_done, hot));

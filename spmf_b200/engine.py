@@ -156,8 +156,13 @@ class AdviEngine:
         self._side = None
         self._args = None
         self.stream_mode = os.environ.get("SPMF_STREAMS", "prio")
+        # Adam of the data-free tensors under the data term (spmf_step_args.adam_tail_early): needs the split
+        # backward on its side stream
+        self.adam_early = (os.environ.get("SPMF_ADAM_EARLY", "1") != "0" and self.stream_mode == "prio"
+                           and os.environ.get("SPMF_SPLIT_BACKWARD", "1") != "0")
         self._max_rows = max_rows
         self.opt_step = 0
+        self.tail_stepped = False
         self.rng_step = 0
         self.launches = 0     # CUDA kernel launches issued through the ABI (bench's gpu_launches)
         self.kernel_events = None   # when a dict: name -> [(start,end) CUDA events] around the hot kernels
@@ -433,7 +438,11 @@ class AdviEngine:
             a.rank, a.hot_cols = None, 0
         # one rank: Adam ends the native step; several ranks: it follows the all-reduce (parallel.allreduce_step)
         do_adam = lr is not None
-        a.adam_lr = float(lr) if (do_adam and self.world_size == 1) else 0.0
+        # the tensors that never see a data term are stepped under the data term (side stream); with several
+        # ranks that is the only Adam inside the native step -- the data-touched block belongs to the exchange
+        early = do_adam and self.adam_early and bool(a.scr_dpre)
+        a.adam_tail_early = int(early)
+        a.adam_lr = float(lr) if (do_adam and (self.world_size == 1 or early)) else 0.0
         a.adam_beta1, a.adam_beta2, a.adam_eps, a.clip_value = beta1, beta2, eps, float(clip_value)
         a.adam_t = self.opt_step + 1
         a.caller_stream = _stream()
@@ -470,12 +479,14 @@ class AdviEngine:
         # (2 splits, 2 GEMMs, second column kernel), +7 tile-hybrid (2 splits, 2 GEMMs, EV tiles, tile
         # kernel, row finalisation); +1 Adam
         self._last_adam = (float(lr), beta1, beta2, eps, float(clip_value)) if do_adam else None
+        self.tail_stepped = bool(a.adam_tail_early)     # (multi-GPU tail: the exchange skips those tensors)
         base = 17 if a.scr_dpre else 16
         if self.link != 0:
             base += 6              # scatter (2), encode, two conditional row passes, zeroing -- minus nothing
         elif xd is not None:
             base += 2              # the two conditional guard launches
-        self.launches += base + (1 if a.adam_lr > 0 else 0) + ((7 if self.hot_mode == 2 else 5) if hybrid else 0)
+        n_adam = (1 if (a.adam_lr > 0 and self.world_size == 1) else 0) + (1 if a.adam_tail_early else 0)
+        self.launches += base + n_adam + ((7 if self.hot_mode == 2 else 5) if hybrid else 0)
         return w.parts.view(self.S, _abi.NUM_PARTS)
 
     def _launch_step(self, a, batch, graphable, hybrid, fresh_noise, capture_only=False):
@@ -483,7 +494,7 @@ class AdviEngine:
         arrays every epoch) -- one CUDA graph launch (spmf_step_graph_launch).  The first step of every
         configuration runs eagerly: it performs the kernels' lazy one-time initialisation, which must
         not happen under stream capture."""
-        cfg = (int(fresh_noise), a.adam_lr > 0, bool(hybrid), int(self.hot_mode), int(self.link))
+        cfg = (int(fresh_noise), a.adam_lr > 0, bool(hybrid), int(self.hot_mode), int(self.link), int(a.adam_tail_early))
         warm = cfg in self._warm_cfgs
         if not (self.use_graphs and graphable and warm and getattr(batch, "_resident", False)):
             if capture_only:

@@ -128,13 +128,14 @@ class PeerLink:
                 pass
         self.opened = []
 
-    def reduce_adam(self, eng, parts, adam_args, loss_buf):
+    def reduce_adam(self, eng, parts, adam_args, loss_buf, skip_tail=False):
         """The step's exchange: one launch on the current stream."""
         L = eng.layout
         self.epoch += 1
         a = _abi.P2PArgs()
         a.world, a.rank, a.S, a.slack = self.world, self.rank, eng.S, L.comm_slack
         a.epoch = self.epoch & 0xFFFFFFFF
+        a.skip_tail = int(bool(skip_tail))
         a.n_params, a.n_block, a.comm_off = L.n_params, L.n_data_block, L.comm_off
         a.w_entropy, a.w_prior = eng.entropy_weight, eng.prior_weight
         for q in range(self.world):

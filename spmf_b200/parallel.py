@@ -84,7 +84,7 @@ def allreduce_step(eng, parts, group=None, adam=False):
             eng._loss_buf = torch.zeros(1, dtype=torch.float64, device=eng.device)
         if link is not None:
             # ONE kernel per rank over NVLink peer memory: reduce-scatter -> Adam -> all-gather (no NCCL call)
-            link.reduce_adam(eng, parts, eng.adam_args(), eng._loss_buf)
+            link.reduce_adam(eng, parts, eng.adam_args(), eng._loss_buf, skip_tail=eng.tail_stepped)
             eng.launches += 1
             return eng._loss_buf[0]
     dist.all_reduce(comm_block(eng), op=dist.ReduceOp.SUM, group=group)
@@ -94,7 +94,8 @@ def allreduce_step(eng, parts, group=None, adam=False):
         slack = eng.grads[L.comm_off: L.comm_off + L.comm_slack]
         a = eng.adam_args()
         _abi.call("spmf_unpack_adam", slack.data_ptr(), L.comm_slack, eng.S, eng.entropy_weight, eng.prior_weight,
-                  parts.data_ptr(), eng._loss_buf.data_ptr(), eng.grads.data_ptr(), L.n_params, C.byref(a),
+                  parts.data_ptr(), eng._loss_buf.data_ptr(), eng.grads.data_ptr(),
+                  L.n_data_block if eng.tail_stepped else L.n_params, C.byref(a),
                   torch.cuda.current_stream().cuda_stream)
         eng.launches += 1
         return eng._loss_buf[0]
