@@ -400,7 +400,7 @@ def main():
     # per-launch DRAM traffic of the dominant kernels from the committed `ncu --set full` capture
     traffic = {}
     try:
-        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r2_traffic.json")) as f:
             traffic = json.load(f)
     except Exception:
         pass
