@@ -127,6 +127,7 @@ class AdviEngine:
         self.link = int(link)
         self.model = int(model)           # SPMF_MODEL_*: Bernoulli = Identity bijector + Normal priors on v, w
         self.exact_guard = bool(exact_guard)
+        self.custom_link = None           # (encoder, decoder) torch callables: data term in torch (see custom_forward)
         # device guard state (poisson.py:606-616): flag | nbad | (min finite log-likelihood, entry)
         self.gs = torch.zeros(int(_abi._lib.spmf_guard_state_bytes()), dtype=torch.uint8, device=self.device)
         self.reset_guard()
@@ -223,6 +224,9 @@ class AdviEngine:
         st = _stream()
         self.reset_guard()
         xd = self._guard_scratch(b.nrows)
+        if self.custom_link is not None:
+            self.custom_data_term(b, xd, forward_only=True)
+            return
         if self.link != 0:
             self.dense_data_term(b, xd)
             return
@@ -294,6 +298,105 @@ class AdviEngine:
                   _ptr(w.z), _ptr(w.dzr), _ptr(w.EV), _ptr(w.PH), _ptr(w.GAp), _ptr(w.GEV), _ptr(w.Gph),
                   _ptr(self.gs), st)
         self.launches += 4
+
+    # ---- user-supplied encoder / decoder callables (poisson.py:94-97) ------------------------------------
+    # An arbitrary Python link cannot run inside a CUDA kernel: for those models the DATA TERM (and only it) is
+    # evaluated with torch ops on the device, dense over every entry like the reference's own formulation, and
+    # differentiated by autograd down to the operand tables (A', EV, phi); sampling, the 12 prior terms, the
+    # entropy, the chain rule to the 24 variational tensors and Adam stay in the native kernels.
+    def _table_to_sdk(self, tab):
+        """[NQ][D][REC] gather-record table -> (S, D, K)."""
+        w = self.ws
+        perm = torch.tensor(_abi.rec_perm(w.KP, w.SV), device=self.device)
+        t = tab[:w.NQ * self.D * w.SV * w.KP].view(w.NQ, self.D, w.SV * w.KP)[:, :, perm]
+        return t.view(w.NQ, self.D, w.SV, w.KP).permute(0, 2, 1, 3).reshape(self.S, self.D, w.KP)[..., :self.K]
+
+    def _sdk_to_table(self, t, tab):
+        w = self.ws
+        perm = torch.tensor(_abi.rec_perm(w.KP, w.SV), device=self.device)
+        o = torch.zeros(w.NQ, self.D, w.SV, w.KP, dtype=torch.float32, device=self.device)
+        o[:, :, :, :self.K] = t.reshape(w.NQ, w.SV, self.D, self.K).permute(0, 2, 1, 3)
+        rec = torch.empty(w.NQ, self.D, w.SV * w.KP, dtype=torch.float32, device=self.device)
+        rec[:, :, perm] = o.reshape(w.NQ, self.D, w.SV * w.KP)
+        tab[:rec.numel()].copy_(rec.reshape(-1))
+
+    def custom_forward(self, b: DeviceBatch, xd, need_grad):
+        """(z, rate, log-likelihood (S,B,D) with the guard of poisson.py:606-616 applied, leaves) for the operands
+        in the workspace; leaves = (A', v, phi) as autograd leaves when need_grad."""
+        enc, dec = self.custom_link
+        w, S, D = self.ws, self.S, self.D
+        self.dense_scatter(b, xd)
+        x = xd[:b.nrows * D].view(b.nrows, D)
+        eta = self.eta[:D]
+        A = self._table_to_sdk(w.Ap).contiguous()                                  # a u  (encoder divisor = 1)
+        v = (self._table_to_sdk(w.EV) / eta[None, :, None]).transpose(1, 2).contiguous()      # (S,K,D)
+        phi = w.PH[:w.NQ * D * w.SV].view(w.NQ, D, w.SV).permute(0, 2, 1).reshape(S, 1, D).contiguous()
+        if need_grad:
+            A, v, phi = (t.detach().requires_grad_(True) for t in (A, v, phi))
+        z = torch.matmul(enc(x), A)                                                # poisson.py:640-643
+        if self.scale_rows:
+            z = z * (b.rowsum * self.inv_xi)[None, :, None]                        # :644-649
+        rate = dec(torch.matmul(z, v)) + phi                                       # :173-177
+        lg = torch.lgamma(x + 1.0)
+        with torch.no_grad():
+            bad = ~torch.isfinite(torch.xlogy(x, rate) - rate - lg)
+        one = torch.ones((), dtype=rate.dtype, device=rate.device)
+        # log(rate) is only formed where it is used (finite entries with x > 0), so that masked branches do not
+        # inject 0 * inf into the gradient
+        ll = x * torch.log(torch.where(bad | (x == 0), one, rate)) - torch.where(bad, torch.zeros_like(rate), rate) - lg
+        mn = torch.where(bad, torch.zeros_like(ll), ll).min()                      # :606-609 min of the finite portion
+        ll = torch.where(bad, mn - 10.0, ll)                                       # :610-616
+        return z, rate, ll, (A, v, phi), bad
+
+    def custom_data_term(self, b: DeviceBatch, xd, forward_only=False):
+        w, S, D = self.ws, self.S, self.D
+        with torch.enable_grad():
+            z, rate, ll, leaves, bad = self.custom_forward(b, xd, need_grad=not forward_only)
+            if not forward_only:
+                gA, gv, gphi = torch.autograd.grad(ll.sum() - 0.5 * (z * z).sum(), leaves)
+        with torch.no_grad():
+            ll, z = ll.detach(), z.detach()
+            ds = torch.zeros(S, 4, dtype=torch.float64, device=self.device)
+            ds[:, 0] = ll.sum((1, 2), dtype=torch.float64)      # sum of the log-likelihood, replacement applied
+            ds[:, 2] = (z * z).sum((1, 2), dtype=torch.float64)  # -> the HalfNormal(1) prior of z (poisson.py:597-604)
+            w.datasums[:w.NQ * 4 * w.SV].copy_(ds.view(w.NQ, w.SV, 4).permute(0, 2, 1).reshape(-1))
+            self.last_row_ll = ll.sum(-1, dtype=torch.float64)   # (S,B): WAIC / row_log_likelihood
+            self.last_nbad = bad.sum()
+            if forward_only:
+                return
+            self._sdk_to_table(gA, w.GAp)
+            self._sdk_to_table(gv.transpose(1, 2) / self.eta[:D][None, :, None], w.GEV)     # d/dEV, EV = eta v
+            w.Gph[:w.NQ * D * w.SV].copy_(gphi.reshape(w.NQ, w.SV, D).permute(0, 2, 1).reshape(-1))
+
+    def custom_encode(self, b: DeviceBatch, xd):
+        """z (S,B,K) for the operands in the workspace (inference)."""
+        self.dense_scatter(b, xd)
+        with torch.no_grad():
+            x = xd[:b.nrows * self.D].view(b.nrows, self.D)
+            z = torch.matmul(self.custom_link[0](x), self._table_to_sdk(self.ws.Ap))
+            if self.scale_rows:
+                z = z * (b.rowsum * self.inv_xi)[None, :, None]
+        return z
+
+    def _step_custom(self, batch, fresh_noise, lr, clip_value, beta1, beta2, eps):
+        """The step with a torch data term: native sampling -> operands -> [torch: rate, log-likelihood, autograd]
+        -> native backward to the 24 tensors -> Adam."""
+        if self.world_size > 1:
+            raise _abi.SpmfError("custom encoder / decoder callables are single-GPU only")
+        w = self.ws
+        w.ensure_rows(batch.nrows)
+        xd = self._guard_scratch(batch.nrows)
+        if fresh_noise:
+            self.fill_noise()
+        self.gamma_grad()
+        self.draw_operands()
+        self.reset_guard()
+        self.custom_data_term(batch, xd)
+        self.backward_params(batch.nrows)
+        if lr is not None:
+            self.clear_comm_slack()
+            self.adam_step(lr, beta1, beta2, eps, clip_value)
+        return w.parts.view(self.S, _abi.NUM_PARTS)
 
     def gamma_grad(self):
         _abi.call("spmf_gamma_grad", _ptr(self.params), _ptr(self.noise), self.D, self.K, self.S,
@@ -385,6 +488,8 @@ class AdviEngine:
         """ONE native call: noise -> operands -> row pass -> column pass -> backward (-> Adam when `lr`
         is given and world_size == 1).  Gamma draws / implicit gradients run on a low-priority side
         stream underneath the gather-bound data-term kernels (stream_mode "prio")."""
+        if self.custom_link is not None:
+            return self._step_custom(batch, fresh_noise, lr, clip_value, beta1, beta2, eps)
         w = self.ws
         if batch.nrows > w.max_rows:
             w.ensure_rows(batch.nrows)

@@ -16,8 +16,10 @@ Differences that are deliberate:
   * the non-finite guard of poisson.py:606-616 is exact: a step that meets a non-finite
     log-likelihood is re-evaluated densely with the reference's min(finite) - 10 replacement;
   * `horshoe_plus=False` (the reference's own branch fails at construction: misplaced kwarg at
-    poisson.py:388) and arbitrary Python encoder/decoder callables (a CUDA kernel cannot run them)
-    raise -- no silent fallback.
+    poisson.py:388) raises -- no silent fallback;
+  * custom `encoder_function` / `decoder_function` (poisson.py:94-97) are torch callables; a Python callable
+    cannot run inside a CUDA kernel, so such a model evaluates its data term with torch ops + autograd on the
+    device (engine.custom_forward) between the native sampling and the native backward / Adam.
 """
 from __future__ import annotations
 
@@ -33,6 +35,8 @@ from . import _abi
 from .data import CsrShard, DeviceBatch, as_device_batch, _ptr, _stream
 from .engine import AdviEngine
 from .variables import VAR_LIST, NORMAL_VARS, var_shapes
+
+LINK_CUSTOM = 64      # host-side only: user-supplied encoder / decoder callables (data term in torch, engine.custom_forward)
 
 
 def waic_terms(ll):
@@ -136,12 +140,17 @@ class PoissonFactorization:
                  initialize_distributions=True, dtype=torch.float32, device=None,
                  entropy_weight=1.0, prior_weight=1.0, seed=0, process_group=None, hot_density=None,
                  exact_guard=None, **kwargs):
-        if encoder_function is not None or decoder_function is not None:
-            raise _abi.SpmfError("custom encoder/decoder callables have no CUDA path (the linear and "
-                                 "log_transform pairs of poisson.py:34-54 are built in)")
         if not horshoe_plus:
             raise _abi.SpmfError("horshoe_plus=False (AbsHorseshoe priors) has no CUDA path")
         self.link = self._link_id(bool(log_transform))
+        # poisson.py:94-97: user-supplied encoder g(x) / decoder f(y) -- torch callables on device tensors
+        # ((B,D) -> (B,D) and (S,B,D) -> (S,B,D), differentiable).  A Python callable cannot run inside a CUDA
+        # kernel: such a model evaluates its DATA TERM with torch ops + autograd (engine.custom_forward); the
+        # other half of the pair defaults to the reference's own function of eta_i (poisson.py:34-54).
+        self._custom_link = None
+        if encoder_function is not None or decoder_function is not None:
+            self._custom_link = (encoder_function or self._default_encoder, decoder_function or self._default_decoder)
+            self.link = LINK_CUSTOM
         if exact_guard is None:
             exact_guard = os.environ.get("SPMF_EXACT_GUARD", "1") != "0"
         self.exact_guard = bool(exact_guard)
@@ -182,6 +191,24 @@ class PoissonFactorization:
             self.create_distributions()
         print(f"Feature dim: {self.feature_dim} -> Latent dim {self.latent_dim}")   # poisson.py:110-111
 
+    def _default_encoder(self, x):
+        """poisson.py:34-43 as a torch callable (used when only a decoder is supplied)."""
+        eta = self.eta_i.reshape(-1).to(device=x.device, dtype=x.dtype)
+        return torch.log(x / eta + 1.0) if self.log_transform else x / eta
+
+    def _default_decoder(self, y):
+        """poisson.py:45-54 as a torch callable (used when only an encoder is supplied)."""
+        eta = self.eta_i.reshape(-1).to(device=y.device, dtype=y.dtype)
+        return torch.expm1(y * eta) if self.log_transform else y * eta
+
+    @property
+    def encoder_function(self):
+        return self._custom_link[0] if self._custom_link else self._default_encoder
+
+    @property
+    def decoder_function(self):
+        return self._custom_link[1] if self._custom_link else self._default_decoder
+
     @staticmethod
     def _link_id(log_transform):
         """SPMF_LINK_* of this model class (poisson.py:34-54, 177-183)."""
@@ -213,6 +240,7 @@ class PoissonFactorization:
                              self.entropy_weight, self.prior_weight, world, self.seed, link=self.link,
                              exact_guard=self.exact_guard, model=self._model_id)
             eng.process_group = self.process_group
+            eng.custom_link = self._custom_link
             if self._params is not None:                # engines share parameters / optimiser state
                 first = next(iter(self._engines.values()))
                 if eng.params.data_ptr() != first.params.data_ptr():
@@ -229,8 +257,8 @@ class PoissonFactorization:
         D = self.feature_dim
         eta = self.eta_i.reshape(-1).to(torch.float32)
         eng.eta[:D].copy_(eta)                                  # decoder scale (poisson.py:52-54)
-        if self.log_transform:
-            eng.eta[D:].fill_(1.0)                              # encoder log(x/eta + 1) acts on the counts
+        if self.log_transform or self._custom_link:
+            eng.eta[D:].fill_(1.0)                              # encoder log(x/eta + 1) / g(x) acts on the counts
         else:
             eng.eta[D:].copy_(eta)                              # encoder x/eta folded into A'
         xi = float(self.xi_u_global)
@@ -362,7 +390,7 @@ class PoissonFactorization:
             u, v, w, s = u[None], v[None], w[None], s[None]
         a = s[:, 0, :] / (s[:, 0, :] + s[:, 1, :])
         b = 1.0 - a
-        eta_enc = torch.ones_like(eta) if self.log_transform else eta
+        eta_enc = torch.ones_like(eta) if (self.log_transform or self._custom_link) else eta
         Ap = a[:, :, None] * u / eta_enc[None, :, None]              # (S,D,K)
         EV = eta[None, :, None] * v.transpose(-1, -2)                # (S,D,K)
         PH = eta[None, :] * b * w[:, 0, :]                           # (S,D)
@@ -402,6 +430,9 @@ class PoissonFactorization:
         zeros_w = torch.zeros((S, 1, D) if batched else (1, D), device=self.device)
         self._operands_from_theta(eng, u, zeros_v, zeros_w, s)
         ws = eng.ws
+        if self._custom_link:
+            z = eng.custom_encode(b, eng._guard_scratch(b.nrows))
+            return z if batched else z[0]
         if self.link & 1:              # log(x/eta + 1) encoder: dense kernel (spmf_dense.cu)
             xd = eng._guard_scratch(b.nrows)
             eng.dense_scatter(b, xd)
@@ -497,6 +528,9 @@ class PoissonFactorization:
         f32 = dict(device=self.device, dtype=torch.float32)
         s, u, v, w = (torch.as_tensor(t).to(**f32) for t in (s, u, v, w))
         z = self.encode(x, u, s)
+        if self._custom_link:
+            rate = self._custom_link[1](torch.matmul(z, v)) + self.intercept_matrix(w, s)
+            return {'log_likelihood': self._log_prob(x, rate), 'rate': rate}
         lin = torch.matmul(z, v) * self.eta_i.to(**f32)
         rate = (torch.expm1(lin) if self.log_transform else lin) + self.intercept_matrix(w, s)   # :52-54, :177
         return {'log_likelihood': self._log_prob(x, rate), 'rate': rate}
@@ -532,6 +566,10 @@ class PoissonFactorization:
         ws = eng.ws
         ws.ensure_rows(b.nrows)
         self._operands_from_theta(eng, params['u'], params['v'], params['w'], params['s'])
+        if self._custom_link:
+            eng.reset_guard()
+            eng.custom_data_term(b, eng._guard_scratch(b.nrows), forward_only=True)
+            return eng.last_row_ll
         if self.link != _abi.LINK_POISSON:        # dense links: per-row sums over every entry (spmf_dense.cu)
             eng.reset_guard()
             eng.dense_data_term(b, eng._guard_scratch(b.nrows), forward_only=True)
@@ -719,7 +757,10 @@ class PoissonFactorization:
                           symmetry_breaking_decay=self.symmetry_breaking_decay,
                           scale_columns=self.scale_columns, scale_rows=self.scale_rows,
                           log_transform=self.log_transform, count_key=self.count_key, seed=self.seed,
-                          entropy_weight=self.entropy_weight, prior_weight=self.prior_weight),
+                          entropy_weight=self.entropy_weight, prior_weight=self.prior_weight,
+                          **({'encoder_function': self._custom_link[0] if self._custom_link[0] != self._default_encoder else None,
+                              'decoder_function': self._custom_link[1] if self._custom_link[1] != self._default_decoder else None}
+                             if self._custom_link else {})),
         }
 
     def save(self, filename):
@@ -746,7 +787,11 @@ class PoissonFactorization:
     @classmethod
     def load(cls, filename, device=None):
         with open(filename, 'rb') as f:
-            state = pickle.load(f)
+            try:
+                import dill as _pk          # (custom encoder / decoder callables are dill pickles)
+            except ImportError:             # pragma: no cover
+                _pk = pickle
+            state = _pk.load(f)
         m = cls(device=device, **state['hyper'])
         m.reconstitute(state)
         m.set_calibration_expectations()

@@ -319,3 +319,101 @@ def test_guard_on_a_dense_ingested_batch():
     torch.cuda.synchronize()
     assert abs(float(eng.loss_value(p).item()) - float(eng.loss_value(p_ref).item())) <= 1e-6 * abs(float(eng.loss_value(p_ref).item()))
     assert rel_err(eng.grads.cpu().numpy(), g_ref.cpu().numpy()) < 2e-5
+
+
+def _softplus_pair():
+    enc = lambda x: torch.log1p(x)                                   # g(x): acts on the raw counts
+    dec = lambda y: torch.nn.functional.softplus(y)                  # f(y) >= 0
+    return enc, dec
+
+
+@pytest.mark.parametrize("D,K,B,S", [(64, 8, 96, 4), (90, 16, 70, 2)])
+def test_custom_encoder_decoder_step_matches_oracle(D, K, B, S):
+    """poisson.py:94-97: user-supplied encoder / decoder callables.  The data term runs in torch (autograd down to
+    the operand tables), everything else in the native kernels: one step == the float64 oracle with the same
+    functions plugged in, loss and all 24 gradients."""
+    import spmf_b200
+    from oracle.spmf_oracle import draw_noise
+    dev = torch.device("cuda:0")
+    enc, dec = _softplus_pair()
+    x = make_counts(B, D, seed=6, kind="linear")
+    N = 10 * B
+    oracle = make_oracle(D, K, N, x)
+    oracle.encoder_function, oracle.decoder_function = enc, dec     # as the reference assigns them, :94-97
+    params = perturbed_params(oracle, 0.3, seed=2)
+    noise = draw_noise(oracle, params, S, seed=3)
+    data = {'counts': torch.tensor(x, dtype=torch.float64)}
+    ref_loss, ref_grads, ref_parts = oracle.loss_and_grads(params, noise, data)
+    model = spmf_b200.PoissonFactorization(latent_dim=K, feature_dim=D, u_tau_scale=1.0 / np.sqrt(N * D),
+                                           encoder_function=enc, decoder_function=dec, device=dev)
+    model.compute_scales(lambda: [{'counts': x}])
+    eng = model._engine_for(S)
+    assert eng.custom_link is not None and not (eng.hot_cols > 0 and eng.hybrid_ok)
+    _load(eng, params)
+    eng.set_noise_from(noise)
+    batch = spmf_b200.as_device_batch(x, dev)
+    p = eng.loss_and_grad(batch, fresh_noise=False)
+    torch.cuda.synchronize()
+    loss = float(eng.loss_value(p).item())
+    assert abs(loss - ref_loss) <= TOL * abs(ref_loss), (loss, ref_loss)
+    pd = eng.parts_dict()
+    for name in ref_parts:
+        ref = ref_parts[name].numpy()
+        assert np.abs(pd[name].numpy() - ref).max() <= TOL * max(np.abs(ref).max(), 1.0), (name, pd[name].numpy(), ref)
+    grads = eng.layout.views(eng.grads)
+    for k, g in ref_grads.items():
+        tol = TOL if k.split('/')[0] in ('v', 'w', 'u', 's') else TOL_IG
+        e = rel_err(grads[k].cpu().numpy(), g.numpy())
+        assert e <= tol, (k, e)
+    # surface: encode / energy parts / likelihood components / per-row log-likelihood
+    th = model.surrogate_distribution.sample(2, seed=4)
+    thc = {k: v.cpu().double() for k, v in th.items()}
+    z = model.encode(x, th['u'], th['s']).cpu().double().numpy()
+    assert rel_err(z, oracle.encode(data['counts'], thc['u'], thc['s']).numpy()) < 1e-5
+    got = model.unormalized_log_prob_parts({'counts': x}, **th)
+    ref = oracle.unormalized_log_prob_parts(data, **thc)
+    for k in ref:
+        r = ref[k].numpy()
+        assert np.abs(got[k].cpu().numpy() - r).max() <= TOL * max(np.abs(r).max(), 1.0), (k,)
+    llc = model.log_likelihood_components(data={'counts': x}, **{k: th[k] for k in ('s', 'u', 'v', 'w')})
+    ollc = oracle.log_likelihood_components(data=data, **{k: thc[k] for k in ('s', 'u', 'v', 'w')})
+    assert rel_err(llc['rate'].cpu().double().numpy(), ollc['rate'].numpy()) < 1e-4
+    rll = model.row_log_likelihood({'counts': x}, **th).cpu().numpy()
+    assert rel_err(rll, ollc['log_likelihood'].sum(-1).numpy()) < 1e-5
+
+
+def test_custom_callables_equal_to_the_builtin_pair_reproduce_the_native_step():
+    """The reference's own linear pair handed in as callables must give what the CUDA kernels give: the torch
+    data term and the native one are two evaluations of the same function (one step, then a short fit)."""
+    import spmf_b200
+    dev = torch.device("cuda:0")
+    D, K, B, S = 80, 8, 128, 4
+    x = make_counts(4 * B, D, seed=9, kind="linear")
+    kw = dict(latent_dim=K, feature_dim=D, u_tau_scale=1.0 / np.sqrt(x.size), device=dev, seed=11)
+    native = spmf_b200.PoissonFactorization(hot_density=0.0, **kw)
+    native.compute_scales(lambda: [{'counts': x}])
+    eta = native.eta_i.reshape(-1).to(dev, torch.float32)
+    custom = spmf_b200.PoissonFactorization(encoder_function=lambda t: t / eta, decoder_function=lambda y: y * eta, **kw)
+    custom.compute_scales(lambda: [{'counts': x}])
+    e0, e1 = native._engine_for(S), custom._engine_for(S)
+    assert e1.custom_link is not None and e0.custom_link is None
+    b = spmf_b200.as_device_batch(x[:B], dev)
+    p0 = e0.loss_and_grad(b).clone()
+    p1 = e1.loss_and_grad(b).clone()
+    assert rel_err(p1.cpu().numpy(), p0.cpu().numpy()) < 1e-5
+    assert rel_err(e1.grads.cpu().numpy(), e0.grads.cpu().numpy()) < 5e-5
+    fac = lambda: ({'counts': x[i * B:(i + 1) * B]} for i in range(4))
+    l0 = native.fit(fac, num_steps=3, learning_rate=0.05, sample_size=S, verbose=False, rel_tol=None)
+    l1 = custom.fit(fac, num_steps=3, learning_rate=0.05, sample_size=S, verbose=False, rel_tol=None)
+    assert l1[-1] < l1[0] and np.allclose(l0, l1, rtol=1e-4), (l0, l1)
+    # a saved model carries its callables (dill) ... when they can be pickled
+    import os
+    import tempfile
+    m2 = spmf_b200.PoissonFactorization(encoder_function=_softplus_pair()[0], **kw)
+    with tempfile.TemporaryDirectory() as td:
+        fn = os.path.join(td, "m.pkl")
+        m2.save(fn)
+        m3 = spmf_b200.PoissonFactorization.load(fn, device=dev)
+        assert m3._custom_link is not None
+        t = torch.rand(3, D, device=dev)
+        assert torch.equal(m3.encoder_function(t), torch.log1p(t))
