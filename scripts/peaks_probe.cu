@@ -1,5 +1,5 @@
 // Micro-benchmarks of the two per-SM rates SURVEY 8(d) builds its rooflines on: FP32 FMA and MUFU
-// (lg2 / rcp / ex2 .approx) throughput of one B200, under the clock the device actually holds.
+// (lg2 / ex2 .approx) throughput of one B200, under the clock the device actually holds.
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o scripts/_build/peaks_probe scripts/peaks_probe.cu
 // Prints one JSON line.
 #include <cuda_runtime.h>
@@ -16,7 +16,6 @@ __global__ void __launch_bounds__(256) probe(float* out, int iters, float seed) 
     for (int j = 0; j < 8; ++j) {
       if (OP == 0) a[j] = fmaf(a[j], m, c);
       if (OP == 1) asm volatile("lg2.approx.ftz.f32 %0, %0;" : "+f"(a[j]));
-      if (OP == 2) asm volatile("rcp.approx.ftz.f32 %0, %0;" : "+f"(a[j]));
       if (OP == 3) asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(a[j]));
     }
     if (OP == 1) {
@@ -57,13 +56,13 @@ int main() {
   cudaDeviceProp p;
   cudaGetDeviceProperties(&p, 0);
   const int blocks = p.multiProcessorCount * 8, iters = 1 << 16;
-  const double fma = run<0>(blocks, iters), lg2 = run<1>(blocks, iters), rcp = run<2>(blocks, iters), ex2 = run<3>(blocks, iters);
+  const double fma = run<0>(blocks, iters), lg2 = run<1>(blocks, iters), ex2 = run<3>(blocks, iters);
   int clk = 0;
   cudaDeviceGetAttribute(&clk, cudaDevAttrClockRate, 0);
   printf("{\"gpu\": \"%s\", \"sms\": %d, \"max_clock_mhz\": %.0f, \"fp32_fma_tflops\": %.2f, "
-         "\"fp32_fma_per_clk_per_sm_at_max_clock\": %.1f, \"mufu_lg2_gops\": %.1f, \"mufu_rcp_gops\": %.1f, "
+         "\"fp32_fma_per_clk_per_sm_at_max_clock\": %.1f, \"mufu_lg2_gops\": %.1f, "
          "\"mufu_ex2_gops\": %.1f, \"mufu_lg2_per_clk_per_sm_at_max_clock\": %.2f}\n",
          p.name, p.multiProcessorCount, clk / 1e3, 2.0 * fma / 1e12, fma / (clk * 1e3) / p.multiProcessorCount,
-         lg2 / 1e9, rcp / 1e9, ex2 / 1e9, lg2 / (clk * 1e3) / p.multiProcessorCount);
+         lg2 / 1e9, ex2 / 1e9, lg2 / (clk * 1e3) / p.multiProcessorCount);
   return 0;
 }
