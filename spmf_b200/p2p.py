@@ -94,6 +94,8 @@ class PeerLink:
         ptrs = {"params": [0] * self.world, "grads": [0] * self.world, "flags": [0] * self.world}
         if good:
             try:
+                if os.environ.get("SPMF_P2P_TEST_FAIL_RANK") == str(self.rank):     # test hook: the collective fallback
+                    raise _abi.SpmfError("simulated mapping failure")
                 with torch.cuda.device(self.device):
                     for q, h in enumerate(everyone):
                         for name, hb, own in (("params", h[0], params.data_ptr()), ("grads", h[1], grads.data_ptr()),
