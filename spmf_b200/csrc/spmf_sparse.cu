@@ -1170,6 +1170,132 @@ hot_split_kernel(const long long* __restrict__ rowptr, const CT* __restrict__ co
   }
 }
 
+// ---- the 2-byte transfer format straight to the hybrid form, one pass ------------------------------------------
+// The streamed end-to-end step pays for this kernel in full (the device is busy under it), and the generic
+// kernel above is issue-bound (~340 warp instructions per 32 nonzeros, profiles/r2_final_ncu_upload_kernels_summary.txt):
+// two sweeps with a (rank, value) stash between them, 64-bit indices, a constant-memory table read with
+// divergent indices.  Here: row-local 32-bit indices; after the warps' gap sums are known ONE sweep does the
+// column scan, the rank lookup, the row constants and the placement -- covered entries are appended from the
+// front of the row's output range, the others from its back, through two shared-memory cursors bumped once per
+// warp and 32 entries (the order inside either part is irrelevant to every consumer: the cold row pass, the CSC
+// build and the guard's scatter are order-free, the dense block is position-indexed).
+template <bool STAGED_UNUSED = true>
+__global__ void __launch_bounds__(kSplitThreads, 2048 / kSplitThreads)
+hot_split8_kernel(const long long* __restrict__ rowptr, const unsigned char* __restrict__ gaps8,
+                  const unsigned char* __restrict__ vals8, int nrows, const int* __restrict__ rank, int H,
+                  long long* __restrict__ rowptr_out, int* __restrict__ cols_out, float* __restrict__ vals_out,
+                  int* __restrict__ rowmid, unsigned short* __restrict__ xhot, long long hchunks,
+                  float* __restrict__ rowsum, float* __restrict__ lgam, const int* __restrict__ ovf_idx,
+                  const float* __restrict__ ovf_val, int novf) {
+  extern __shared__ __align__(16) unsigned short xrow[];        // [Hp]
+  __shared__ int s_gap[kSplitWarps], s_cur[2];
+  __shared__ float s_sum[kSplitWarps], s_lg[kSplitWarps], s_tab[64];
+  const int row = blockIdx.x;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int hp = (int)hchunks * 64;
+  for (int i = threadIdx.x; i < hp / 8; i += blockDim.x) reinterpret_cast<uint4*>(xrow)[i] = make_uint4(0u, 0u, 0u, 0u);
+  if (row >= nrows) {                                            // padding row of the last 128-row tile
+    for (int c = threadIdx.x; c < hp / 8; c += blockDim.x)
+      __stcs(reinterpret_cast<uint4*>(xhot + tiledA_index(row, 8LL * c, hchunks)), make_uint4(0u, 0u, 0u, 0u));
+    return;
+  }
+  if (threadIdx.x < 64) s_tab[threadIdx.x] = kLgamTab[threadIdx.x];
+  if (threadIdx.x < 2) s_cur[threadIdx.x] = 0;
+  const long long base = rowptr[0], j0 = rowptr[row], j1 = rowptr[row + 1];
+  const int n = (int)(j1 - j0);
+  const long long o0 = j0 - base;
+  if (threadIdx.x == 0) {
+    rowptr_out[row] = o0;
+    if (row == nrows - 1) rowptr_out[nrows] = j1 - base;
+  }
+  const unsigned char* __restrict__ g8 = gaps8 + j0;            // row-local from here on
+  const unsigned char* __restrict__ v8 = vals8 + j0;
+  int* __restrict__ co = cols_out + o0;
+  float* __restrict__ vo = vals_out + o0;
+  const int e0 = (int)o0;                                        // entry index of the row's first entry (overflow list key)
+  const int seg = (n + kSplitThreads - 1) / kSplitThreads * 32;  // entries per warp, a multiple of 32
+  const int a0 = min(n, w * seg), a1 = min(n, a0 + seg);
+  int gs = 0;
+  for (int t = a0 + lane; t < a1; t += 32) gs += (int)__ldcs(g8 + t) + 1;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) gs += __shfl_xor_sync(0xffffffffu, gs, o);
+  if (lane == 0) s_gap[w] = gs;
+  __syncthreads();                                               // (also: xrow zeroed, table and cursors set)
+  int cbase = -1;                                                // column before my piece's first entry
+  for (int t = 0; t < w; ++t) cbase += s_gap[t];
+  float rs = 0.f, rl = 0.f;
+  const unsigned below = (1u << lane) - 1u;
+  for (int tb = a0; tb < a1; tb += 32) {
+    const int t = tb + lane;
+    const bool in = t < a1;
+    int g = in ? (int)__ldcs(g8 + t) + 1 : 0;
+    const unsigned b = in ? (unsigned)__ldcs(v8 + t) : 0u;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {                           // inclusive warp scan of the gaps
+      const int u = __shfl_up_sync(0xffffffffu, g, o);
+      if (lane >= o) g += u;
+    }
+    const int c = cbase + g;
+    cbase += __shfl_sync(0xffffffffu, g, 31);
+    int r = 0;
+    float x = 0.f;
+    if (in) {
+      r = rank ? __ldg(rank + c) : c;
+      x = (float)b;
+      if (b == 255u) {                                           // count above 254: sorted overflow list
+        const int e = e0 + t;
+        int lo = 0, hi = novf - 1;
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (__ldg(ovf_idx + mid) < e) lo = mid + 1; else hi = mid;
+        }
+        if (novf > 0 && __ldg(ovf_idx + lo) == e) x = __ldg(ovf_val + lo);
+      }
+      rs += x;
+      rl += (b < 64u) ? s_tab[b] : lgammaf(x + 1.f);
+    }
+    const bool cov = in && hot_covered(r, x, H);
+    const unsigned mc = __ballot_sync(0xffffffffu, cov);
+    const unsigned mu = __ballot_sync(0xffffffffu, in && !cov);
+    int bc = 0, bu = 0;
+    if (lane == 0) {
+      if (mc) bc = atomicAdd(&s_cur[0], __popc(mc));
+      if (mu) bu = atomicAdd(&s_cur[1], __popc(mu));
+    }
+    bc = __shfl_sync(0xffffffffu, bc, 0);
+    bu = __shfl_sync(0xffffffffu, bu, 0);
+    if (cov) {
+      const int o = bc + __popc(mc & below);
+      __stcs(co + o, r);
+      __stcs(vo + o, -x);
+      xrow[r] = (unsigned short)(__float_as_uint(x) >> 16);
+    } else if (in) {
+      const int o = n - 1 - (bu + __popc(mu & below));
+      __stcs(co + o, r);
+      __stcs(vo + o, x);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    rs += __shfl_xor_sync(0xffffffffu, rs, o);
+    rl += __shfl_xor_sync(0xffffffffu, rl, o);
+  }
+  if (lane == 0) { s_sum[w] = rs; s_lg[w] = rl; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    rowmid[row] = s_cur[0];
+    if (rowsum) {
+      float ts = 0.f, tl = 0.f;
+#pragma unroll
+      for (int t = 0; t < kSplitWarps; ++t) { ts += s_sum[t]; tl += s_lg[t]; }
+      rowsum[row] = ts;
+      lgam[row] = tl;
+    }
+  }
+  for (int c = threadIdx.x; c < hp / 8; c += blockDim.x)
+    __stcs(reinterpret_cast<uint4*>(xhot + tiledA_index(row, 8LL * c, hchunks)), reinterpret_cast<const uint4*>(xrow)[c]);
+}
+
 // ---- direct dense ingest: dense (B,D) counts in feature order -> hybrid form, no CSR round trip ------------
 // For dense-origin workloads (BASELINE C2 / C3: every column is hot) the batch arrives as a dense matrix
 // of small integers; going through CSR would write and re-read 8 B per nonzero only to scatter it back
@@ -1556,11 +1682,22 @@ static int launch_hot_split8(const long long* rowptr, const unsigned char* gaps8
       cudaError_t e = cudaFuncSetAttribute(hot_split_kernel<true, unsigned char, unsigned char, true>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
       if (e != cudaSuccess) return (int)e;
+      e = cudaFuncSetAttribute(hot_split8_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+      if (e != cudaSuccess) return (int)e;
       attr = true;
     }
-    hot_split_kernel<true, unsigned char, unsigned char, true><<<(nrows + 127) / 128 * 128, kSplitThreads, smem, st>>>(
-        rowptr, gaps8, vals8, nrows, rank, H, rowptr_out, cols_out, vals_out, rowmid, (unsigned short*)xhot, hp / 64,
-        rowsum, lgam, ovf_idx, ovf_val, novf);
+    static const bool two_pass = [] {               // ablation switch: the generic two-sweep kernel
+      const char* e = getenv("SPMF_SPLIT8_TWO_PASS");
+      return e && e[0] == '1';
+    }();
+    if (two_pass)
+      hot_split_kernel<true, unsigned char, unsigned char, true><<<(nrows + 127) / 128 * 128, kSplitThreads, smem, st>>>(
+          rowptr, gaps8, vals8, nrows, rank, H, rowptr_out, cols_out, vals_out, rowmid, (unsigned short*)xhot, hp / 64,
+          rowsum, lgam, ovf_idx, ovf_val, novf);
+    else
+      hot_split8_kernel<true><<<(nrows + 127) / 128 * 128, kSplitThreads, (size_t)hp * 2, st>>>(
+          rowptr, gaps8, vals8, nrows, rank, H, rowptr_out, cols_out, vals_out, rowmid, (unsigned short*)xhot, hp / 64,
+          rowsum, lgam, ovf_idx, ovf_val, novf);
   } else {
     cudaError_t e = cudaMemsetAsync(xhot, 0, (size_t)spmf_umma_tiled_a_elems(nrows, hp) * 2, st);
     if (e != cudaSuccess) return (int)e;
