@@ -1179,7 +1179,6 @@ hot_split_kernel(const long long* __restrict__ rowptr, const CT* __restrict__ co
 // front of the row's output range, the others from its back, through two shared-memory cursors bumped once per
 // warp and 32 entries (the order inside either part is irrelevant to every consumer: the cold row pass, the CSC
 // build and the guard's scatter are order-free, the dense block is position-indexed).
-template <bool STAGED_UNUSED = true>
 __global__ void __launch_bounds__(kSplitThreads, 2048 / kSplitThreads)
 hot_split8_kernel(const long long* __restrict__ rowptr, const unsigned char* __restrict__ gaps8,
                   const unsigned char* __restrict__ vals8, int nrows, const int* __restrict__ rank, int H,
@@ -1682,7 +1681,7 @@ static int launch_hot_split8(const long long* rowptr, const unsigned char* gaps8
       cudaError_t e = cudaFuncSetAttribute(hot_split_kernel<true, unsigned char, unsigned char, true>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
       if (e != cudaSuccess) return (int)e;
-      e = cudaFuncSetAttribute(hot_split8_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+      e = cudaFuncSetAttribute(hot_split8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
       if (e != cudaSuccess) return (int)e;
       attr = true;
     }
@@ -1695,7 +1694,7 @@ static int launch_hot_split8(const long long* rowptr, const unsigned char* gaps8
           rowptr, gaps8, vals8, nrows, rank, H, rowptr_out, cols_out, vals_out, rowmid, (unsigned short*)xhot, hp / 64,
           rowsum, lgam, ovf_idx, ovf_val, novf);
     else
-      hot_split8_kernel<true><<<(nrows + 127) / 128 * 128, kSplitThreads, (size_t)hp * 2, st>>>(
+      hot_split8_kernel<<<(nrows + 127) / 128 * 128, kSplitThreads, (size_t)hp * 2, st>>>(
           rowptr, gaps8, vals8, nrows, rank, H, rowptr_out, cols_out, vals_out, rowmid, (unsigned short*)xhot, hp / 64,
           rowsum, lgam, ovf_idx, ovf_val, novf);
   } else {
