@@ -11,13 +11,16 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import weakref
 
 import torch
 import torch.distributed as dist
 
 from . import _abi
 
-_BUFS = {}        # data_ptr -> PeerBuffer (keeps the allocation alive as long as the tensor is registered)
+# data_ptr -> PeerBuffer.  Weak: the tensor made from a buffer owns it (torch keeps the __cuda_array_interface__
+# object alive for the tensor's lifetime); when the last tensor goes, the allocation is freed.
+_BUFS = weakref.WeakValueDictionary()
 
 
 class PeerBuffer:
