@@ -352,8 +352,9 @@ class HostCsrBatch:
     # 2-byte format (spmf_csr_unpack8): column gaps and counts as bytes + the overflow list of large counts
     gaps8: Optional[torch.Tensor] = None
     vals8: Optional[torch.Tensor] = None
-    ovf_idx: Optional[torch.Tensor] = None     # int32, entry index relative to this batch
+    ovf_idx: Optional[torch.Tensor] = None     # int32 / int64 entry indices; `ovf_base` is subtracted on the device
     ovf_val: Optional[torch.Tensor] = None     # fp32
+    ovf_base: int = 0
 
     @property
     def nrows(self):
@@ -422,8 +423,8 @@ class HostCsr:
             self.gaps8 = torch.from_numpy(g8).pin_memory()
             self.vals8 = torch.from_numpy(v8).pin_memory()
             self._ovf_pos = oi                                  # sorted (entries are visited in order)
-            self.ovf_idx_all = torch.from_numpy(oi.astype(np.int32))
-            self.ovf_val_all = torch.from_numpy(ov)
+            self.ovf_idx_all = torch.from_numpy(oi.astype(np.int64)).pin_memory()    # absolute positions in the shard
+            self.ovf_val_all = torch.from_numpy(ov).pin_memory()
             self.cols = self.vals = None
             self.nrows = self.rowptr.numel() - 1
             return
@@ -448,10 +449,10 @@ class HostCsr:
         rp = self.rowptr[row0:row0 + nrows + 1]
         if self.u8:
             a, b = np.searchsorted(self._ovf_pos, [j0, j1])
-            oi = (self.ovf_idx_all[a:b] - j0).to(torch.int32).pin_memory() if b > a else None
-            ov = self.ovf_val_all[a:b].clone().pin_memory() if b > a else None
+            oi = self.ovf_idx_all[a:b] if b > a else None       # (slices of the pinned lists: nothing allocated)
+            ov = self.ovf_val_all[a:b] if b > a else None
             return HostCsrBatch(rp, None, None, self.D, base=j0, gaps8=self.gaps8[j0:j1], vals8=self.vals8[j0:j1],
-                                ovf_idx=oi, ovf_val=ov)
+                                ovf_idx=oi, ovf_val=ov, ovf_base=j0)
         return HostCsrBatch(rp, self.cols[j0:j1], self.vals[j0:j1], self.D, base=j0)
 
     def iter_batches(self, batch_rows):
@@ -606,7 +607,15 @@ class BatchUploader:
                 self.ovf_i = torch.empty(2 * novf, dtype=torch.int32, device=self.device)
                 self.ovf_v = torch.empty(2 * novf, dtype=torch.float32, device=self.device)
             if novf:
-                self.ovf_i[:novf].copy_(hb.ovf_idx, non_blocking=True)
+                if hb.ovf_base:
+                    # absolute int64 positions: rebased on the device, then narrowed to the kernels' int32
+                    if getattr(self, "ovf_i64", None) is None or self.ovf_i64.numel() < novf:
+                        self.ovf_i64 = torch.empty(max(2 * novf, 1024), dtype=torch.int64, device=self.device)
+                    self.ovf_i64[:novf].copy_(hb.ovf_idx, non_blocking=True)
+                    self.ovf_i64[:novf].sub_(int(hb.ovf_base))
+                    self.ovf_i[:novf].copy_(self.ovf_i64[:novf])
+                else:
+                    self.ovf_i[:novf].copy_(hb.ovf_idx, non_blocking=True)
                 self.ovf_v[:novf].copy_(hb.ovf_val, non_blocking=True)
             if self.hot is not None and os.environ.get("SPMF_FUSED_UNPACK8", "1") != "0":
                 packed8 = (self.g8, self.v8, self.ovf_i, self.ovf_v, novf)       # ... inside the hot split
