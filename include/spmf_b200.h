@@ -157,7 +157,7 @@ int spmf_colsum(const float* in, long long n, int c, int q, double* out, double*
  * (moments live on the owner only) and store the new values into every rank's parameter buffer; Adam on the
  * replicated tensors [n_block, n_params) locally; fold the ('z','x') (hi,lo) pairs of all ranks into parts /
  * loss_out (as spmf_unpack_parts); leave when every peer's stores have landed, then zero the local slack.
- * `epoch` must increase by one per call (same value on every rank).  Waits are bounded (~2 s): a missing peer
+ * `epoch` must increase by one per call (same value on every rank).  Waits are bounded (~10 s): a missing peer
  * sets a status word (spmf_p2p_status -> SPMF_ERR_PEER_TIMEOUT) instead of hanging the device. */
 #define SPMF_P2P_MAX_WORLD 8
 #define SPMF_P2P_HANDLE_BYTES 64

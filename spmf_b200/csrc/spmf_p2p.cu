@@ -39,7 +39,7 @@ namespace spmf {
     if (e__ != cudaSuccess) return (int)e__;     \
   } while (0)
 
-constexpr long long kSpinLimit = 4000000000LL;      // clock64 ticks (~2 s): give up, do not hang the device
+constexpr long long kSpinLimit = 20000000000LL;     // clock64 ticks (~10 s): give up, do not hang the device
 constexpr int kFlagReady = 0, kFlagDone = 32, kFlagCount = 64, kFlagStatus = 65;     // words of a flag page
 
 __device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
