@@ -189,3 +189,36 @@ def test_oracle_reproduces_golden(path):
     for k, v in parts.items():
         assert rel_err(v.numpy(), g["part:" + k]) < 1e-12, k
     assert len(GOLDEN) >= 3
+
+
+def test_callable_links_plug_into_the_oracle_like_the_reference():
+    """poisson.py:94-97 assigns user callables over encoder_function / decoder_function.  The oracle takes them the
+    same way (instance attributes): the built-in pair handed in as callables reproduces the built-in energy and
+    gradients exactly, and a different pair changes them (this is the checker the GPU custom-link tests rely on)."""
+    import torch
+    from oracle.spmf_oracle import OraclePoissonFactorization, draw_noise
+    D, K, B, S = 12, 3, 9, 2
+    rng = np.random.default_rng(5)
+    x = rng.poisson(1.5, size=(B, D)).astype(np.float64)
+    x[:, 0] = np.maximum(x[:, 0], 1)
+    data = {'counts': torch.tensor(x)}
+
+    def build():
+        m = OraclePoissonFactorization(K, D, u_tau_scale=1.0 / np.sqrt(100 * D))
+        m.compute_scales([data])
+        return m
+    base = build()
+    params = base.init_params()
+    noise = draw_noise(base, params, S, seed=1)
+    l0, g0, p0 = base.loss_and_grads(params, noise, data)
+    same = build()
+    eta = same.eta_i
+    same.encoder_function, same.decoder_function = (lambda t: t / eta), (lambda y: y * eta)
+    l1, g1, p1 = same.loss_and_grads(params, noise, data)
+    assert l1 == l0 and all(torch.equal(g1[k], g0[k]) for k in g0)
+    other = build()
+    other.encoder_function = lambda t: torch.log1p(t)
+    other.decoder_function = lambda y: torch.nn.functional.softplus(y)
+    l2, g2, _ = other.loss_and_grads(params, noise, data)
+    assert np.isfinite(l2) and abs(l2 - l0) > 1e-6 * abs(l0)
+    assert all(bool(torch.isfinite(v).all()) for v in g2.values())
